@@ -1,0 +1,514 @@
+/* TEST INFRASTRUCTURE (oracle) — not product code.
+ *
+ * Plain-C, FP64, single-rod CPU restatement of the physics step that
+ * gym-softrobot runs through PyElastica:
+ *   boundary   /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:183-184
+ *              (`time = PositionVerlet().step(simulator, time, dt)`)
+ *   plugins    /root/reference/gym_softrobot/envs/soft_pendulum/build.py:29-115
+ *              /root/reference/gym_softrobot/envs/soft_pendulum_3d/build.py:23-86
+ *   algorithm  pyelastica==1.0.0 (third-party, pinned in /root/reference/uv.lock:845-857,
+ *              NOT installable here) restated from SURVEY.md Appendix A — the
+ *              same restatement as oracle/shims/elastica (NumPy), operation
+ *              for operation.  PARITY UNPINNED against real PyElastica.
+ *
+ * Compile with -ffp-contract=off (no FMA contraction: Numba/NumPy do not fuse).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference
+ * arm may link or call this file.
+ */
+#include "rod_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <pthread.h>
+#include <unistd.h>
+
+#define PI 3.141592653589793
+
+struct ro_rod {
+  ro_config cfg;
+  int n;
+  double time;
+  /* state */
+  double *x, *v, *Q, *w;                 /* (3,n+1) (3,n+1) (3,3,n) (3,n) */
+  double *acc, *alpha;
+  /* constants (A.1) */
+  double *rest_len, *rest_vor, *mass, *volume, *radius;
+  double *J, *Jinv, *S, *B;              /* diagonals: (3,n) (3,n) (3,n) (3,n-1) */
+  double *rest_sigma, *rest_kappa;
+  /* derived (A.3) — refreshed only inside the force evaluation (A.6) */
+  double *len, *tang, *dil, *vdil, *dil_rate, *sigma, *kappa;
+  double *stress, *couple, *f_int, *t_int, *f_ext, *t_ext, *f_user;
+  /* plugins */
+  double fixed_pos[3], fixed_Q[9];
+  double c_v, *c_w;                      /* AnalyticalLinearDamper coefficients */
+  double *filt;                          /* Laplace filter scratch (3,n+1) */
+  double *tmp;                           /* scratch (3,n+1) x 4 */
+};
+
+static double *zalloc(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
+
+#define X(i, k) r->x[(i) * (n + 1) + (k)]
+#define V(i, k) r->v[(i) * (n + 1) + (k)]
+#define QQ(i, j, k) r->Q[((i) * 3 + (j)) * n + (k)]
+#define W(i, k) r->w[(i) * n + (k)]
+
+/* ---- A.3 geometry / strains (cosserat_rod.py: _compute_geometry_from_state ..) */
+static void compute_shear_stretch_strains(ro_rod *r) {
+  const int n = r->n;
+  for (int k = 0; k < n; k++) {
+    double d0 = X(0, k + 1) - X(0, k), d1 = X(1, k + 1) - X(1, k), d2 = X(2, k + 1) - X(2, k);
+    double len = sqrt(d0 * d0 + d1 * d1 + d2 * d2) + 1e-14;
+    r->len[k] = len;
+    r->tang[0 * n + k] = d0 / len;
+    r->tang[1 * n + k] = d1 / len;
+    r->tang[2 * n + k] = d2 / len;
+    r->radius[k] = sqrt(r->volume[k] / len / PI);
+    r->dil[k] = len / r->rest_len[k];
+  }
+  for (int k = 0; k < n - 1; k++)
+    r->vdil[k] = (0.5 * (r->len[k + 1] + r->len[k])) / r->rest_vor[k];
+  for (int k = 0; k < n; k++)
+    for (int i = 0; i < 3; i++) {
+      double qt = 0.0;
+      for (int j = 0; j < 3; j++) qt += QQ(i, j, k) * r->tang[j * n + k];
+      r->sigma[i * n + k] = r->dil[k] * qt - (i == 2 ? 1.0 : 0.0);
+    }
+}
+
+static void compute_bending_twist_strains(ro_rod *r) {
+  const int n = r->n;
+  for (int k = 0; k < n - 1; k++) {
+    double Rm[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++)
+        Rm[i][j] = QQ(i, 0, k + 1) * QQ(j, 0, k) + QQ(i, 1, k + 1) * QQ(j, 1, k) +
+                   QQ(i, 2, k + 1) * QQ(j, 2, k);
+    double v0 = Rm[2][1] - Rm[1][2], v1 = Rm[0][2] - Rm[2][0], v2 = Rm[1][0] - Rm[0][1];
+    double trace = Rm[0][0] + Rm[1][1] + Rm[2][2];
+    double theta = acos(0.5 * trace - 0.5 - 1e-10);
+    double fac = -0.5 * theta / sin(theta + 1e-14);
+    r->kappa[0 * (n - 1) + k] = (v0 * fac) / r->rest_vor[k];
+    r->kappa[1 * (n - 1) + k] = (v1 * fac) / r->rest_vor[k];
+    r->kappa[2 * (n - 1) + k] = (v2 * fac) / r->rest_vor[k];
+  }
+}
+
+static void compute_internal_forces_and_torques(ro_rod *r) {
+  const int n = r->n, nv = n - 1;
+  double *cs = r->tmp; /* (3,n) Q^T n / e */
+  compute_shear_stretch_strains(r);
+  for (int k = 0; k < n; k++)
+    for (int i = 0; i < 3; i++)
+      r->stress[i * n + k] = r->S[i * n + k] * (r->sigma[i * n + k] - r->rest_sigma[i * n + k]);
+  for (int k = 0; k < n; k++)
+    for (int i = 0; i < 3; i++) {
+      double s = 0.0;
+      for (int j = 0; j < 3; j++) s += QQ(j, i, k) * r->stress[j * n + k];
+      cs[i * n + k] = s / r->dil[k];
+    }
+  for (int i = 0; i < 3; i++) { /* Delta_h */
+    r->f_int[i * (n + 1) + 0] = cs[i * n + 0];
+    for (int k = 1; k < n; k++) r->f_int[i * (n + 1) + k] = cs[i * n + k] - cs[i * n + k - 1];
+    r->f_int[i * (n + 1) + n] = -cs[i * n + n - 1];
+  }
+
+  compute_bending_twist_strains(r);
+  for (int k = 0; k < nv; k++)
+    for (int i = 0; i < 3; i++)
+      r->couple[i * nv + k] = r->B[i * nv + k] * (r->kappa[i * nv + k] - r->rest_kappa[i * nv + k]);
+  /* dilatation rate */
+  for (int k = 0; k < n; k++) {
+    double rv0 = 0, rv1 = 0, rp1v = 0, rvp1 = 0;
+    for (int i = 0; i < 3; i++) {
+      rv0 += X(i, k) * V(i, k);
+      rv1 += X(i, k + 1) * V(i, k + 1);
+      rp1v += X(i, k + 1) * V(i, k);
+      rvp1 += X(i, k) * V(i, k + 1);
+    }
+    r->dil_rate[k] = (rv0 + rv1 - rvp1 - rp1v) / r->len[k] / r->rest_len[k];
+  }
+  double *m2 = r->tmp + 3 * (n + 1);     /* tau / eps^3          (3,nv) */
+  double *m3 = r->tmp + 6 * (n + 1);     /* (kappa x tau) D / eps^3 (3,nv) */
+  for (int k = 0; k < nv; k++) {
+    double e3 = 1.0 / (r->vdil[k] * r->vdil[k] * r->vdil[k]);
+    double k0 = r->kappa[k], k1 = r->kappa[nv + k], k2 = r->kappa[2 * nv + k];
+    double c0 = r->couple[k], c1 = r->couple[nv + k], c2 = r->couple[2 * nv + k];
+    m2[k] = c0 * e3; m2[nv + k] = c1 * e3; m2[2 * nv + k] = c2 * e3;
+    m3[k] = (k1 * c2 - k2 * c1) * r->rest_vor[k] * e3;
+    m3[nv + k] = (k2 * c0 - k0 * c2) * r->rest_vor[k] * e3;
+    m3[2 * nv + k] = (k0 * c1 - k1 * c0) * r->rest_vor[k] * e3;
+  }
+  for (int k = 0; k < n; k++) {
+    double bt2[3], bt3[3], qt[3], ssc[3], jw[3], lt[3], ud[3];
+    for (int i = 0; i < 3; i++) {
+      if (k == 0) { bt2[i] = m2[i * nv]; bt3[i] = 0.5 * m3[i * nv]; }
+      else if (k == n - 1) { bt2[i] = -m2[i * nv + nv - 1]; bt3[i] = 0.5 * m3[i * nv + nv - 1]; }
+      else { bt2[i] = m2[i * nv + k] - m2[i * nv + k - 1]; bt3[i] = 0.5 * (m3[i * nv + k] + m3[i * nv + k - 1]); }
+      double a = 0.0;
+      for (int j = 0; j < 3; j++) a += QQ(i, j, k) * r->tang[j * n + k];
+      qt[i] = a;
+    }
+    double n0 = r->stress[k], n1 = r->stress[n + k], n2 = r->stress[2 * n + k];
+    ssc[0] = (qt[1] * n2 - qt[2] * n1) * r->rest_len[k];
+    ssc[1] = (qt[2] * n0 - qt[0] * n2) * r->rest_len[k];
+    ssc[2] = (qt[0] * n1 - qt[1] * n0) * r->rest_len[k];
+    for (int i = 0; i < 3; i++) jw[i] = (r->J[i * n + k] * W(i, k)) / r->dil[k];
+    lt[0] = jw[1] * W(2, k) - jw[2] * W(1, k);
+    lt[1] = jw[2] * W(0, k) - jw[0] * W(2, k);
+    lt[2] = jw[0] * W(1, k) - jw[1] * W(0, k);
+    for (int i = 0; i < 3; i++) ud[i] = jw[i] * r->dil_rate[k] / r->dil[k];
+    for (int i = 0; i < 3; i++)
+      r->t_int[i * n + k] = bt2[i] + bt3[i] + ssc[i] + lt[i] + ud[i];
+  }
+}
+
+/* ---- A.2.1 kinematic half step */
+static void kinematic_step(ro_rod *r, double prefac) {
+  const int n = r->n;
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k <= n; k++) X(i, k) += prefac * V(i, k);
+  for (int k = 0; k < n; k++) {
+    double v0 = prefac * W(0, k), v1 = prefac * W(1, k), v2 = prefac * W(2, k);
+    double theta = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+    v0 /= theta + 1e-14; v1 /= theta + 1e-14; v2 /= theta + 1e-14;
+    theta = theta * 1.0;
+    double up = sin(theta), us = 1.0 - cos(theta);
+    double R[3][3];
+    R[0][0] = 1.0 - us * (v1 * v1 + v2 * v2);
+    R[1][1] = 1.0 - us * (v0 * v0 + v2 * v2);
+    R[2][2] = 1.0 - us * (v0 * v0 + v1 * v1);
+    R[0][1] = up * v2 + us * v0 * v1;
+    R[1][0] = -up * v2 + us * v0 * v1;
+    R[0][2] = -up * v1 + us * v0 * v2;
+    R[2][0] = up * v1 + us * v0 * v2;
+    R[1][2] = up * v0 + us * v1 * v2;
+    R[2][1] = -up * v0 + us * v1 * v2;
+    double Qn[3][3];
+    for (int i = 0; i < 3; i++)
+      for (int m = 0; m < 3; m++) {
+        double s = 0.0;
+        for (int j = 0; j < 3; j++) s += R[i][j] * QQ(j, m, k);
+        Qn[i][m] = s;
+      }
+    for (int i = 0; i < 3; i++)
+      for (int m = 0; m < 3; m++) QQ(i, m, k) = Qn[i][m];
+  }
+}
+
+/* ---- plugins */
+static void constrain_values(ro_rod *r, const double *base_pos) {
+  const int n = r->n;
+  switch (r->cfg.bc_kind) {
+    case RO_BC_ONE_END_FIXED:
+      for (int i = 0; i < 3; i++) X(i, 0) = r->fixed_pos[i];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) QQ(i, j, 0) = r->fixed_Q[i * 3 + j];
+      break;
+    case RO_BC_PENDULUM_SLIDER: /* build.py:71-74 */
+      X(1, 0) = r->fixed_pos[1];
+      X(2, 0) = r->fixed_pos[2];
+      for (int j = 0; j < 3; j++) { QQ(0, j, 0) = r->fixed_Q[0 * 3 + j]; QQ(2, j, 0) = r->fixed_Q[2 * 3 + j]; }
+      break;
+    case RO_BC_MOVING_BASE: /* soft_pendulum_3d/build.py:32-35 */
+      X(0, 0) = base_pos[0]; X(1, 0) = base_pos[1]; X(2, 0) = r->fixed_pos[2];
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) QQ(i, j, 0) = r->fixed_Q[i * 3 + j];
+      break;
+    default: break;
+  }
+}
+
+static void constrain_rates(ro_rod *r, const double *base_vel) {
+  const int n = r->n;
+  switch (r->cfg.bc_kind) {
+    case RO_BC_ONE_END_FIXED:
+      for (int i = 0; i < 3; i++) { V(i, 0) = 0.0; W(i, 0) = 0.0; }
+      break;
+    case RO_BC_PENDULUM_SLIDER: /* build.py:76-79 */
+      V(1, 0) = 0.0; V(2, 0) = 0.0; W(0, 0) = 0.0; W(2, 0) = 0.0;
+      break;
+    case RO_BC_MOVING_BASE: /* soft_pendulum_3d/build.py:37-40 */
+      V(0, 0) = base_vel[0]; V(1, 0) = base_vel[1]; V(2, 0) = 0.0;
+      for (int i = 0; i < 3; i++) W(i, 0) = 0.0;
+      break;
+    default: break;
+  }
+}
+
+static void laplace_filter(double *rate, double *ft, int m, int order) {
+  /* A.4: nb_filter_rate on a (3,m) array */
+  double *nw = (double *)malloc(sizeof(double) * (size_t)m);
+  for (int i = 0; i < 3; i++) {
+    double *f = ft + i * m, *q = rate + i * m;
+    memcpy(f, q, sizeof(double) * (size_t)m);
+    for (int p = 0; p < order; p++) {
+      for (int k = 1; k < m - 1; k++) nw[k] = (-f[k + 1] - f[k - 1] + 2.0 * f[k]) / 4.0;
+      for (int k = 1; k < m - 1; k++) f[k] = nw[k];
+      f[0] = 0.0; f[m - 1] = 0.0;
+    }
+    for (int k = 0; k < m; k++) q[k] = q[k] - f[k];
+  }
+  free(nw);
+}
+
+static void dampen_rates(ro_rod *r) {
+  const int n = r->n;
+  if (r->cfg.damping_constant >= 0.0) {
+    for (int i = 0; i < 3; i++)
+      for (int k = 0; k <= n; k++) V(i, k) = V(i, k) * r->c_v;
+    for (int i = 0; i < 3; i++)
+      for (int k = 0; k < n; k++) W(i, k) = W(i, k) * pow(r->c_w[i * n + k], r->dil[k]);
+  }
+  if (r->cfg.laplace_filter_order > 0) {
+    laplace_filter(r->v, r->filt, n + 1, r->cfg.laplace_filter_order);
+    laplace_filter(r->w, r->filt, n, r->cfg.laplace_filter_order);
+  }
+}
+
+/* ---- A.2 one PositionVerlet substep */
+static void substep(ro_rod *r, double action, const double *bp, const double *bv) {
+  const int n = r->n;
+  const double dt = r->cfg.dt, prefac = 0.5 * dt;
+  kinematic_step(r, prefac);
+  r->time += prefac;
+  constrain_values(r, bp);
+  compute_internal_forces_and_torques(r);
+  /* synchronize: gravity, then point force (registration order, build.py:88-105) */
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k <= n; k++)
+      r->f_ext[i * (n + 1) + k] += r->cfg.gravity[i] * r->mass[k] + r->f_user[i * (n + 1) + k];
+  if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
+  /* dynamic step */
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k <= n; k++)
+      r->acc[i * (n + 1) + k] = (r->f_int[i * (n + 1) + k] + r->f_ext[i * (n + 1) + k]) / r->mass[k];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < n; k++)
+      r->alpha[i * n + k] = (r->Jinv[i * n + k] * (r->t_int[i * n + k] + r->t_ext[i * n + k])) * r->dil[k];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k <= n; k++) V(i, k) += dt * r->acc[i * (n + 1) + k];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < n; k++) W(i, k) += dt * r->alpha[i * n + k];
+  if (r->cfg.damping_before_constraints) { dampen_rates(r); constrain_rates(r, bv); }
+  else { constrain_rates(r, bv); dampen_rates(r); }
+  kinematic_step(r, prefac);
+  r->time += prefac;
+  constrain_values(r, bp);
+  memset(r->f_ext, 0, sizeof(double) * 3 * (size_t)(n + 1));
+  memset(r->t_ext, 0, sizeof(double) * 3 * (size_t)n);
+}
+
+void ro_substeps(ro_rod *r, int n_substeps, double action, const double *bp, const double *bv) {
+  for (int s = 0; s < n_substeps; s++) substep(r, action, bp, bv);
+}
+
+/* ---- A.1 construction (factory_function.py: allocate) */
+ro_rod *ro_create(const ro_config *cfg) {
+  ro_rod *r = (ro_rod *)calloc(1, sizeof(ro_rod));
+  const int n = cfg->n_elem, nv = n - 1;
+  r->cfg = *cfg;
+  r->n = n;
+  r->time = 0.0;
+  r->x = zalloc(3 * (n + 1)); r->v = zalloc(3 * (n + 1)); r->Q = zalloc(9 * n); r->w = zalloc(3 * n);
+  r->acc = zalloc(3 * (n + 1)); r->alpha = zalloc(3 * n);
+  r->rest_len = zalloc(n); r->rest_vor = zalloc(nv); r->mass = zalloc(n + 1); r->volume = zalloc(n);
+  r->radius = zalloc(n); r->J = zalloc(3 * n); r->Jinv = zalloc(3 * n); r->S = zalloc(3 * n); r->B = zalloc(3 * nv);
+  r->rest_sigma = zalloc(3 * n); r->rest_kappa = zalloc(3 * nv);
+  r->len = zalloc(n); r->tang = zalloc(3 * n); r->dil = zalloc(n); r->vdil = zalloc(nv); r->dil_rate = zalloc(n);
+  r->sigma = zalloc(3 * n); r->kappa = zalloc(3 * nv); r->stress = zalloc(3 * n); r->couple = zalloc(3 * nv);
+  r->f_int = zalloc(3 * (n + 1)); r->t_int = zalloc(3 * n); r->f_ext = zalloc(3 * (n + 1)); r->t_ext = zalloc(3 * n);
+  r->f_user = zalloc(3 * (n + 1));
+  r->c_w = zalloc(3 * n); r->filt = zalloc(3 * (n + 1)); r->tmp = zalloc(12 * (n + 1));
+
+  /* np.linspace(start, end, n+1): arange(n+1)*step + start, last point = end */
+  for (int i = 0; i < 3; i++) {
+    double start = cfg->start[i], end = cfg->start[i] + cfg->direction[i] * cfg->base_length;
+    double step = (end - start) / (double)n;
+    for (int k = 0; k <= n; k++) X(i, k) = (double)k * step + start;
+    X(i, n) = end;
+  }
+  double nrm = sqrt(cfg->normal[0] * cfg->normal[0] + cfg->normal[1] * cfg->normal[1] +
+                    cfg->normal[2] * cfg->normal[2]);
+  double nor[3] = {cfg->normal[0] / nrm, cfg->normal[1] / nrm, cfg->normal[2] / nrm};
+  double E = cfg->youngs_modulus, G = cfg->shear_modulus;
+  if (!(G > 0.0)) G = cfg->shear_convention == 1 ? E / (0.5 + 1.0) : E / (2.0 * (1.0 + 0.5));
+  double *Bel = zalloc(3 * n);
+  for (int k = 0; k < n; k++) {
+    double d0 = X(0, k + 1) - X(0, k), d1 = X(1, k + 1) - X(1, k), d2 = X(2, k + 1) - X(2, k);
+    double rl = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    double t[3] = {d0 / rl, d1 / rl, d2 / rl};
+    r->rest_len[k] = rl;
+    for (int j = 0; j < 3; j++) { QQ(0, j, k) = nor[j]; QQ(2, j, k) = t[j]; }
+    QQ(1, 0, k) = t[1] * nor[2] - t[2] * nor[1];
+    QQ(1, 1, k) = t[2] * nor[0] - t[0] * nor[2];
+    QQ(1, 2, k) = t[0] * nor[1] - t[1] * nor[0];
+    double rad = cfg->base_radius;
+    r->radius[k] = rad;
+    double A0 = PI * rad * rad;
+    double I1 = A0 * A0 / (4.0 * PI), I2 = I1, I3 = 2.0 * I2;
+    double rho_l = cfg->density * rl;
+    r->J[0 * n + k] = I1 * rho_l; r->J[1 * n + k] = I2 * rho_l; r->J[2 * n + k] = I3 * rho_l;
+    for (int i = 0; i < 3; i++) r->Jinv[i * n + k] = 1.0 / r->J[i * n + k];
+    double ac = 27.0 / 28.0;
+    r->S[0 * n + k] = ac * G * A0; r->S[1 * n + k] = ac * G * A0; r->S[2 * n + k] = E * A0;
+    Bel[0 * n + k] = E * I1; Bel[1 * n + k] = E * I2; Bel[2 * n + k] = G * I3;
+    r->volume[k] = PI * (rad * rad) * rl;
+  }
+  for (int k = 0; k < nv; k++) {
+    r->rest_vor[k] = 0.5 * (r->rest_len[k + 1] + r->rest_len[k]);
+    for (int i = 0; i < 3; i++)
+      r->B[i * nv + k] = (Bel[i * n + k + 1] * r->rest_len[k + 1] + Bel[i * n + k] * r->rest_len[k]) /
+                         (r->rest_len[k + 1] + r->rest_len[k]);
+  }
+  free(Bel);
+  for (int k = 0; k < n; k++) {
+    r->mass[k] += 0.5 * cfg->density * r->volume[k];
+    r->mass[k + 1] += 0.5 * cfg->density * r->volume[k];
+  }
+  compute_shear_stretch_strains(r);
+  compute_bending_twist_strains(r);
+  /* finalize: constraint copies (B-7), damper coefficients (A.4) */
+  for (int i = 0; i < 3; i++) r->fixed_pos[i] = X(i, 0);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) r->fixed_Q[i * 3 + j] = QQ(i, j, 0);
+  if (cfg->damping_constant >= 0.0) {
+    r->c_v = exp(-cfg->damping_constant * cfg->dt);
+    for (int k = 0; k < n; k++) {
+      double em = 0.5 * (r->mass[k + 1] + r->mass[k]);
+      if (k == 0) em += 0.5 * r->mass[0];
+      if (k == n - 1) em += 0.5 * r->mass[n];
+      for (int i = 0; i < 3; i++)
+        r->c_w[i * n + k] = exp(-cfg->damping_constant * cfg->dt * em * r->Jinv[i * n + k]);
+    }
+  }
+  return r;
+}
+
+void ro_destroy(ro_rod *r) {
+  if (!r) return;
+  double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
+                    r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
+                    r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp};
+  for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
+  free(r);
+}
+
+double ro_time(const ro_rod *r) { return r->time; }
+int ro_n_elem(const ro_rod *r) { return r->n; }
+double *ro_position(ro_rod *r) { return r->x; }
+double *ro_velocity(ro_rod *r) { return r->v; }
+double *ro_director(ro_rod *r) { return r->Q; }
+double *ro_omega(ro_rod *r) { return r->w; }
+double *ro_tangents(ro_rod *r) { return r->tang; }
+double *ro_kappa(ro_rod *r) { return r->kappa; }
+double *ro_sigma(ro_rod *r) { return r->sigma; }
+double *ro_dilatation(ro_rod *r) { return r->dil; }
+double *ro_rest_kappa(ro_rod *r) { return r->rest_kappa; }
+double *ro_external_forces(ro_rod *r) { return r->f_user; }
+double *ro_mass(ro_rod *r) { return r->mass; }
+double *ro_internal_forces(ro_rod *r) { return r->f_int; }
+double *ro_internal_torques(ro_rod *r) { return r->t_int; }
+
+/* numpy pairwise summation (np.add.reduce on a contiguous float64 row, n < 128 block) */
+static double np_pairwise_sum(const double *a, int n) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; i++) res += a[i];
+    return res;
+  } else if (n <= 128) {
+    double rr[8];
+    for (int j = 0; j < 8; j++) rr[j] = a[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; j++) rr[j] += a[i + j];
+    double res = ((rr[0] + rr[1]) + (rr[2] + rr[3])) + ((rr[4] + rr[5]) + (rr[6] + rr[7]));
+    for (; i < n; i++) res += a[i];
+    return res;
+  } else {
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+  }
+}
+
+static double np_mod(double a, double b) { /* numpy float remainder (sign of divisor) */
+  double m = fmod(a, b);
+  if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
+  else m = copysign(0.0, b);
+  return m;
+}
+
+static double softpendulum_theta(ro_rod *r) { /* soft_pendulum.py:154-156 */
+  const int n = r->n;
+  double mx = np_pairwise_sum(r->tang + 0 * n, n) / (double)n;
+  double my = np_pairwise_sum(r->tang + 1 * n, n) / (double)n;
+  double theta = atan(mx / my);
+  return np_mod(theta + PI, 2 * PI) - PI;
+}
+
+void ro_softpendulum_obs(ro_rod *r, float prev_action, float obs[4]) {
+  const int n = r->n;
+  obs[0] = (float)X(0, 0);
+  obs[1] = (float)V(0, 0);
+  obs[2] = prev_action;
+  obs[3] = (float)softpendulum_theta(r);
+}
+
+void ro_softpendulum_step(ro_rod *r, float action, int step_skip, double final_time, float obs[4],
+                          double *reward, int *terminated, int *truncated) {
+  const int n = r->n;
+  ro_substeps(r, step_skip, (double)action, NULL, NULL);
+  int invalid = 0;
+  for (int i = 0; i < 3 * (n + 1); i++) invalid |= isnan(r->x[i]) || isnan(r->v[i]);
+  double survive = 0.0, forward = 0.0;
+  *terminated = 0;
+  if (invalid) { *terminated = 1; survive = -50.0; }
+  else {
+    double d = fabs(X(0, 0));
+    double th = softpendulum_theta(r);
+    forward = d * 10 + th * th;
+  }
+  *truncated = r->time > final_time;
+  *reward = forward - 0.0 + survive;
+  ro_softpendulum_obs(r, action, obs);
+}
+
+int ro_max_threads(void) {
+  long c = sysconf(_SC_NPROCESSORS_ONLN);
+  return c > 0 ? (int)c : 1;
+}
+
+typedef struct {
+  ro_rod **rods; const float *actions; int step_skip; double final_time;
+  float *obs; double *reward; int *terminated, *truncated; int lo, hi;
+} batch_job;
+
+static void *batch_worker(void *p) {
+  batch_job *j = (batch_job *)p;
+  for (int e = j->lo; e < j->hi; e++)
+    ro_softpendulum_step(j->rods[e], j->actions[e], j->step_skip, j->final_time, j->obs + 4 * e,
+                         j->reward + e, j->terminated + e, j->truncated + e);
+  return NULL;
+}
+
+/* contiguous env ranges, one POSIX thread each (the image has no libgomp) */
+void ro_softpendulum_step_batch(ro_rod **rods, int n_env, const float *actions, int step_skip,
+                                double final_time, float *obs, double *reward, int *terminated,
+                                int *truncated, int n_threads) {
+  if (n_threads <= 0) n_threads = ro_max_threads();
+  if (n_threads > n_env) n_threads = n_env;
+  if (n_threads < 1) n_threads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  batch_job *jobs = (batch_job *)malloc(sizeof(batch_job) * (size_t)n_threads);
+  for (int t = 0; t < n_threads; t++) {
+    batch_job j = {rods, actions, step_skip, final_time, obs, reward, terminated, truncated,
+                   (int)((long)n_env * t / n_threads), (int)((long)n_env * (t + 1) / n_threads)};
+    jobs[t] = j;
+    if (t > 0) pthread_create(&th[t], NULL, batch_worker, &jobs[t]);
+  }
+  batch_worker(&jobs[0]);
+  for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}

@@ -1,0 +1,72 @@
+/* TEST INFRASTRUCTURE (oracle) — not product code.  See rod_oracle.c. */
+#ifndef ROD_ORACLE_H
+#define ROD_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* boundary-condition kinds on node 0 / element 0 */
+enum {
+  RO_BC_FREE = 0,
+  RO_BC_ONE_END_FIXED = 1,   /* PyElastica OneEndFixedBC */
+  RO_BC_PENDULUM_SLIDER = 2, /* reference soft_pendulum/build.py:65-85 */
+  RO_BC_MOVING_BASE = 3      /* reference soft_pendulum_3d/build.py:23-40 */
+};
+
+typedef struct {
+  int n_elem;
+  double start[3], direction[3], normal[3];
+  double base_length, base_radius, density, youngs_modulus;
+  double shear_modulus;    /* <=0: PyElastica default (see shear_convention) */
+  int shear_convention;    /* 0: E/(2(1+nu)), nu=.5 ; 1: E/(1+nu) (SURVEY B-4) */
+  double dt;
+  double gravity[3];
+  double damping_constant; /* AnalyticalLinearDamper; <0 disables */
+  int laplace_filter_order; /* 0 disables */
+  int bc_kind;
+  int point_force_on_base; /* SoftPendulum: F_ext[0,0] = action (assignment) */
+  int damping_before_constraints; /* B-2: 1 = [dampen_rates, constrain_rates] */
+} ro_config;
+
+typedef struct ro_rod ro_rod;
+
+ro_rod *ro_create(const ro_config *cfg);
+void ro_destroy(ro_rod *);
+/* advance n substeps of PositionVerlet; `action` is the point force (kind 2)
+ * and base_pos/base_vel the commanded base (kind 3; may be NULL otherwise) */
+void ro_substeps(ro_rod *, int n_substeps, double action, const double *base_pos,
+                 const double *base_vel);
+double ro_time(const ro_rod *);
+int ro_n_elem(const ro_rod *);
+/* pointers into the rod's arrays, reference layout (3,n+1) / (3,3,n) / (3,n) row-major */
+double *ro_position(ro_rod *);
+double *ro_velocity(ro_rod *);
+double *ro_director(ro_rod *);
+double *ro_omega(ro_rod *);
+double *ro_tangents(ro_rod *);
+double *ro_kappa(ro_rod *);
+double *ro_sigma(ro_rod *);
+double *ro_dilatation(ro_rod *);
+double *ro_rest_kappa(ro_rod *);
+double *ro_external_forces(ro_rod *); /* (3,n+1) constant extra nodal load added every substep */
+double *ro_mass(ro_rod *);
+double *ro_internal_forces(ro_rod *);
+double *ro_internal_torques(ro_rod *);
+
+/* SoftPendulum-v0 env step on top of the rod: follows
+ * /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:176-251 */
+void ro_softpendulum_obs(ro_rod *, float prev_action, float obs[4]);
+void ro_softpendulum_step(ro_rod *, float action, int step_skip, double final_time,
+                          float obs[4], double *reward, int *terminated, int *truncated);
+
+/* batched helper for the CPU baseline: n_env independent SoftPendulum rods,
+ * pthread-parallel over contiguous env ranges (n_threads<=0: all cores) */
+void ro_softpendulum_step_batch(ro_rod **rods, int n_env, const float *actions, int step_skip,
+                                double final_time, float *obs, double *reward, int *terminated,
+                                int *truncated, int n_threads);
+int ro_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,193 @@
+"""TEST INFRASTRUCTURE (oracle) — not product code.
+
+ctypes wrapper over oracle/rod_oracle.c (the plain-C FP64 restatement of the
+reference physics step; PARITY UNPINNED against real PyElastica — see
+oracle/README.md).  Allowed importers: tests/, __graft_entry__.smoke(),
+bench.py's cpu_baseline / `--impl reference` leg.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "librod_oracle.so")
+
+BC_FREE, BC_ONE_END_FIXED, BC_PENDULUM_SLIDER, BC_MOVING_BASE = 0, 1, 2, 3
+
+
+class ROConfig(C.Structure):
+    _fields_ = [
+        ("n_elem", C.c_int),
+        ("start", C.c_double * 3),
+        ("direction", C.c_double * 3),
+        ("normal", C.c_double * 3),
+        ("base_length", C.c_double),
+        ("base_radius", C.c_double),
+        ("density", C.c_double),
+        ("youngs_modulus", C.c_double),
+        ("shear_modulus", C.c_double),
+        ("shear_convention", C.c_int),
+        ("dt", C.c_double),
+        ("gravity", C.c_double * 3),
+        ("damping_constant", C.c_double),
+        ("laplace_filter_order", C.c_int),
+        ("bc_kind", C.c_int),
+        ("point_force_on_base", C.c_int),
+        ("damping_before_constraints", C.c_int),
+    ]
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle (gcc, -ffp-contract=off).  Building the checker is not using it."""
+    src = os.path.join(_HERE, "rod_oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", _HERE, "-B", "_build/librod_oracle.so"], check=True,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.ro_create.restype = C.c_void_p
+        L.ro_create.argtypes = [C.POINTER(ROConfig)]
+        L.ro_destroy.argtypes = [C.c_void_p]
+        L.ro_substeps.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.ro_time.restype = C.c_double
+        L.ro_time.argtypes = [C.c_void_p]
+        for name in ("position", "velocity", "director", "omega", "tangents", "kappa", "sigma",
+                     "dilatation", "rest_kappa", "external_forces", "mass", "internal_forces",
+                     "internal_torques"):
+            f = getattr(L, "ro_" + name)
+            f.restype = C.POINTER(C.c_double)
+            f.argtypes = [C.c_void_p]
+        L.ro_softpendulum_obs.argtypes = [C.c_void_p, C.c_float, C.POINTER(C.c_float)]
+        L.ro_softpendulum_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_double,
+                                           C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                           C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ro_softpendulum_step_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int,
+                                                 C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p, C.c_int]
+        L.ro_max_threads.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+class OracleRod:
+    """One Cosserat rod stepped by the C oracle; arrays are NumPy views (reference layout)."""
+
+    def __init__(self, n_elem, start, direction, normal, base_length, base_radius, density,
+                 youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
+                 gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
+                 bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=True):
+        cfg = ROConfig()
+        cfg.n_elem = n_elem
+        cfg.start[:] = list(map(float, start))
+        cfg.direction[:] = list(map(float, direction))
+        cfg.normal[:] = list(map(float, normal))
+        cfg.base_length, cfg.base_radius, cfg.density = base_length, base_radius, density
+        cfg.youngs_modulus, cfg.shear_modulus, cfg.shear_convention = youngs_modulus, shear_modulus, shear_convention
+        cfg.dt = dt
+        cfg.gravity[:] = list(map(float, gravity))
+        cfg.damping_constant = damping_constant
+        cfg.laplace_filter_order = laplace_filter_order
+        cfg.bc_kind = bc_kind
+        cfg.point_force_on_base = int(point_force_on_base)
+        cfg.damping_before_constraints = int(damping_before_constraints)
+        self.cfg = cfg
+        self.n = n_elem
+        self._h = C.c_void_p(lib().ro_create(C.byref(cfg)))
+        n = n_elem
+        self.position_collection = self._view("position", (3, n + 1))
+        self.velocity_collection = self._view("velocity", (3, n + 1))
+        self.director_collection = self._view("director", (3, 3, n))
+        self.omega_collection = self._view("omega", (3, n))
+        self.tangents = self._view("tangents", (3, n))
+        self.kappa = self._view("kappa", (3, n - 1))
+        self.sigma = self._view("sigma", (3, n))
+        self.dilatation = self._view("dilatation", (n,))
+        self.rest_kappa = self._view("rest_kappa", (3, n - 1))
+        self.user_forces = self._view("external_forces", (3, n + 1))
+        self.mass = self._view("mass", (n + 1,))
+        self.internal_forces = self._view("internal_forces", (3, n + 1))
+        self.internal_torques = self._view("internal_torques", (3, n))
+
+    def _view(self, name, shape):
+        p = getattr(lib(), "ro_" + name)(self._h)
+        return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape)
+
+    @property
+    def time(self):
+        return lib().ro_time(self._h)
+
+    def substeps(self, n, action=0.0, base_pos=None, base_vel=None):
+        bp = None if base_pos is None else np.ascontiguousarray(base_pos, dtype=np.float64)
+        bv = None if base_vel is None else np.ascontiguousarray(base_vel, dtype=np.float64)
+        lib().ro_substeps(self._h, int(n), float(action),
+                          None if bp is None else bp.ctypes.data, None if bv is None else bv.ctypes.data)
+
+    def close(self):
+        if self._h:
+            lib().ro_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pendulum_direction_normal(u01: float):
+    """theta / direction / normal exactly as reference soft_pendulum/build.py:47-51."""
+    theta = np.deg2rad(90 + (u01 - 0.5) * 10)
+    direction = np.array([1.0 * np.cos(theta), 1.0 * np.sin(theta), 0.0])
+    normal = np.array([1.0 * np.sin(theta), -1.0 * np.cos(theta), 0.0])
+    return direction, normal
+
+
+class OracleSoftPendulum:
+    """SoftPendulum-v0 on the C oracle (reference soft_pendulum.py:59-251, build.py:29-115)."""
+
+    def __init__(self, final_time=5.0, time_step=1.0e-4, recording_fps=25, n_elems=50,
+                 shear_convention=0):
+        self.final_time, self.time_step, self.n_elems = final_time, time_step, n_elems
+        self.step_skip = int(1.0 / (recording_fps * time_step))
+        self.shear_convention = shear_convention
+        self.rod = None
+        self.prev_action = np.float32(0.0)
+
+    def reset(self, seed=None, u01=None):
+        if u01 is None:
+            u01 = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed))).random()
+        direction, normal = pendulum_direction_normal(u01)
+        if self.rod is not None:
+            self.rod.close()
+        self.rod = OracleRod(self.n_elems, np.zeros(3), direction, normal, 1.0, 0.05, 1000.0, 1e6,
+                             self.time_step, shear_convention=self.shear_convention,
+                             gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3,
+                             bc_kind=BC_PENDULUM_SLIDER, point_force_on_base=True)
+        self.prev_action = np.float32(0.0)
+        return self.obs(), {}
+
+    def obs(self):
+        out = (C.c_float * 4)()
+        lib().ro_softpendulum_obs(self.rod._h, C.c_float(float(self.prev_action)), out)
+        return np.array(out[:], dtype=np.float32)
+
+    def step(self, action):
+        a = np.float32(np.asarray(action, dtype=np.float32).reshape(-1)[0])
+        out = (C.c_float * 4)()
+        rew, term, trunc = C.c_double(), C.c_int(), C.c_int()
+        lib().ro_softpendulum_step(self.rod._h, C.c_float(float(a)), self.step_skip, self.final_time,
+                                   out, C.byref(rew), C.byref(term), C.byref(trunc))
+        self.prev_action = a
+        return (np.array(out[:], dtype=np.float32), rew.value, bool(term.value), bool(trunc.value),
+                {"time": np.float64(self.rod.time), "TimeLimit.truncated": bool(trunc.value)})
