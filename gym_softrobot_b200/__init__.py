@@ -1,0 +1,43 @@
+"""gym_softrobot_b200 — B200-native batched simulator for gym-softrobot's physics step.
+
+Keeps the reference's Gymnasium ids (`/root/reference/gym_softrobot/__init__.py:6-80`)
+for the envs whose hot path is built, and adds batched
+vector envs.  All physics runs in hand-written sm_100a CUDA kernels behind the
+C-ABI in include/softrod.h; importing this package never touches oracle/.
+"""
+from .compat import HAVE_GYMNASIUM
+from .version import VERSION as __version__
+
+# id -> (entry point, kwargs); same ids / kwargs as the reference registry
+REGISTRY = {
+    "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumEnv", {}),
+}
+VECTOR_REGISTRY = {
+    "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
+}
+
+
+def _load(entry_point):
+    import importlib
+    mod, attr = entry_point.split(":")
+    return getattr(importlib.import_module(mod), attr)
+
+
+def make(env_id, **kwargs):
+    """`gym.make(env_id)` equivalent that works without gymnasium installed."""
+    entry, kw = REGISTRY[env_id]
+    return _load(entry)(**{**kw, **kwargs})
+
+
+def make_vec(env_id, n_env, **kwargs):
+    """Batched env: N independent copies of `env_id` advanced by one kernel launch per step."""
+    entry, kw = VECTOR_REGISTRY[env_id]
+    return _load(entry)(n_env, **{**kw, **kwargs})
+
+
+if HAVE_GYMNASIUM:  # pragma: no cover - gymnasium is not in the build image
+    from gymnasium.envs.registration import register, registry as _registry
+
+    for _id, (_entry, _kw) in REGISTRY.items():
+        if _id not in _registry:
+            register(id=_id, entry_point=_entry, kwargs=_kw)

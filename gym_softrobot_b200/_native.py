@@ -1,0 +1,241 @@
+"""ctypes binding of the C-ABI in include/softrod.h (libsoftrod.so).
+
+This is the only door to the physics: there is no CPU fallback.  If the CUDA
+library is missing the import fails loudly; if there is no GPU, `sr_create`
+returns SR_E_NO_DEVICE and `Handle` raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+SR_OK = 0
+MODEL_ROD, MODEL_SOFT_PENDULUM, MODEL_SOFT_PENDULUM_3D = 0, 1, 2
+BC_FREE, BC_ONE_END_FIXED, BC_PENDULUM_SLIDER, BC_MOVING_BASE = 0, 1, 2, 3
+DTYPE_F64, DTYPE_F32 = 0, 1
+MATH_FAST, MATH_FAITHFUL = 0, 1
+
+# every symbol include/softrod.h declares (checked by tests/test_cabi.py)
+EXPORTED_SYMBOLS = [
+    "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
+    "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
+    "sr_get_state", "sr_set_state", "sr_launch_count", "sr_measure_fp64_peak",
+]
+
+
+class SrConfig(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("dtype", C.c_int32),
+        ("math", C.c_int32), ("n_env", C.c_int32), ("n_elem", C.c_int32), ("bc_kind", C.c_int32),
+        ("point_force_on_base", C.c_int32), ("damping_before_constraints", C.c_int32),
+        ("laplace_filter_order", C.c_int32), ("reserved0", C.c_int32),
+        ("dt", C.c_double), ("base_length", C.c_double), ("base_radius", C.c_double),
+        ("density", C.c_double), ("youngs_modulus", C.c_double), ("shear_modulus", C.c_double),
+        ("gravity", C.c_double * 3), ("damping_constant", C.c_double),
+    ]
+
+
+class SrStateView(C.Structure):
+    _fields_ = [
+        ("base", C.c_void_p), ("n_env", C.c_int32), ("n_fields", C.c_int32), ("stride", C.c_int32),
+        ("elem_size", C.c_int32), ("f_position", C.c_int32), ("f_velocity", C.c_int32),
+        ("f_director", C.c_int32), ("f_omega", C.c_int32), ("f_tangents", C.c_int32),
+        ("f_kappa", C.c_int32), ("f_sigma", C.c_int32), ("f_dilatation", C.c_int32),
+    ]
+
+
+class SoftRodError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libsoftrod.so (building it with nvcc if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if _build.is_stale():
+        path = _build.build_library()
+    if not os.path.exists(path):
+        raise SoftRodError(f"{path} missing: build it with `python -m gym_softrobot_b200.build` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    L.sr_abi_version.restype = C.c_int
+    L.sr_last_error.restype = C.c_char_p
+    L.sr_create.argtypes = [C.POINTER(SrConfig), C.POINTER(C.c_void_p)]
+    L.sr_destroy.argtypes = [C.c_void_p]
+    L.sr_destroy.restype = None
+    for f in ("sr_obs_dim", "sr_action_dim", "sr_init_dim"):
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.sr_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    L.sr_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sr_reset_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.sr_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sr_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sr_get_state.argtypes = [C.c_void_p, C.POINTER(SrStateView)]
+    L.sr_set_state.argtypes = [C.c_void_p, C.POINTER(SrStateView), C.c_void_p]
+    L.sr_launch_count.argtypes = [C.c_void_p]
+    L.sr_launch_count.restype = C.c_int64
+    L.sr_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    if L.sr_abi_version() != 1:
+        raise SoftRodError("libsoftrod.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != SR_OK:
+        raise SoftRodError(f"softrod error {rc}: {load_library().sr_last_error().decode()}")
+
+
+class _DevMem:
+    """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2,
+            "strides": None,
+        }
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    out = C.c_double()
+    _check(load_library().sr_measure_fp64_peak(device, C.byref(out)))
+    return out.value
+
+
+class Handle:
+    """One batched rod simulation on one GPU (wraps sr_handle*)."""
+
+    def __init__(self, *, model, n_env, n_elem, dt, base_length, base_radius, density, youngs_modulus,
+                 shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
+                 point_force_on_base=False, damping_before_constraints=True, laplace_filter_order=0,
+                 device=0, dtype=DTYPE_F64, math=MATH_FAST):
+        self._lib = load_library()
+        cfg = SrConfig()
+        cfg.struct_size = C.sizeof(SrConfig)
+        cfg.device, cfg.model, cfg.dtype, cfg.math = device, model, dtype, math
+        cfg.n_env, cfg.n_elem, cfg.bc_kind = n_env, n_elem, bc_kind
+        cfg.point_force_on_base = int(point_force_on_base)
+        cfg.damping_before_constraints = int(damping_before_constraints)
+        cfg.laplace_filter_order = laplace_filter_order
+        cfg.dt, cfg.base_length, cfg.base_radius = dt, base_length, base_radius
+        cfg.density, cfg.youngs_modulus, cfg.shear_modulus = density, youngs_modulus, shear_modulus
+        cfg.gravity[:] = [float(g) for g in gravity]
+        cfg.damping_constant = damping_constant
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        _check(self._lib.sr_create(C.byref(cfg), C.byref(self._h)))
+        self.n_env, self.n_elem, self.device = n_env, n_elem, device
+        self.obs_dim = self._lib.sr_obs_dim(self._h)
+        self.action_dim = self._lib.sr_action_dim(self._h)
+        self._state_tensor = None
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.sr_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.sr_launch_count(self._h))
+
+    # -- device-pointer entry points (torch tensors on self.device) -----------
+    @staticmethod
+    def _stream_ptr():
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def reset(self, init, env_idx=None):
+        """init: float64 cuda tensor [n, 9]; env_idx: int32 cuda tensor [n] or None."""
+        n = init.shape[0]
+        assert init.is_cuda and init.dtype.itemsize == 8 and init.is_contiguous() and init.shape[1] == 9
+        idx_ptr = None
+        if env_idx is not None:
+            assert env_idx.is_cuda and env_idx.is_contiguous() and env_idx.numel() == n
+            idx_ptr = C.c_void_p(env_idx.data_ptr())
+        _check(self._lib.sr_reset(self._h, idx_ptr, n, C.c_void_p(init.data_ptr()), self._stream_ptr()))
+
+    def step(self, action, n_substeps, obs, reward, terminated):
+        a_ptr = None
+        if self.action_dim > 0:
+            assert action.is_cuda and action.is_contiguous() and action.numel() == self.n_env * self.action_dim
+            a_ptr = C.c_void_p(action.data_ptr())
+        _check(self._lib.sr_step(self._h, a_ptr, int(n_substeps), C.c_void_p(obs.data_ptr()),
+                                 C.c_void_p(reward.data_ptr()), C.c_void_p(terminated.data_ptr()),
+                                 self._stream_ptr()))
+
+    def observe(self, prev_action, obs):
+        p = None if prev_action is None else C.c_void_p(prev_action.data_ptr())
+        _check(self._lib.sr_observe(self._h, p, C.c_void_p(obs.data_ptr()), self._stream_ptr()))
+
+    # -- host-buffer entry points (NumPy) ---------------------------------------
+    def reset_host(self, init, env_idx=None):
+        init = np.ascontiguousarray(init, dtype=np.float64)
+        n = init.shape[0]
+        idx = None
+        if env_idx is not None:
+            idx = np.ascontiguousarray(env_idx, dtype=np.int32)
+            assert idx.size == n
+        _check(self._lib.sr_reset_host(self._h, None if idx is None else idx.ctypes.data, n, init.ctypes.data))
+
+    def step_host(self, action, n_substeps, obs=None, reward=None, terminated=None):
+        if obs is None:
+            obs = np.empty((self.n_env, self.obs_dim), dtype=np.float32)
+            reward = np.empty(self.n_env, dtype=np.float64)
+            terminated = np.empty(self.n_env, dtype=np.uint8)
+        a_ptr = None
+        if self.action_dim > 0:
+            action = np.ascontiguousarray(action, dtype=np.float32)
+            assert action.size == self.n_env * self.action_dim
+            a_ptr = action.ctypes.data
+        _check(self._lib.sr_step_host(self._h, a_ptr, int(n_substeps), obs.ctypes.data, reward.ctypes.data,
+                                      terminated.ctypes.data))
+        return obs, reward, terminated
+
+    # -- state views -----------------------------------------------------------
+    def state_view(self) -> SrStateView:
+        v = SrStateView()
+        _check(self._lib.sr_get_state(self._h, C.byref(v)))
+        return v
+
+    def state_tensor(self):
+        """torch view [n_env, n_fields, stride] (float64) of the live SoA state."""
+        import torch
+        if self._state_tensor is None:
+            v = self.state_view()
+            mem = _DevMem(v.base, (v.n_env, v.n_fields, v.stride), "<f8")
+            self._state_tensor = torch.as_tensor(mem, device=f"cuda:{self.device}")
+            self._view = v
+        return self._state_tensor
+
+    def fields(self):
+        """Reference-named views: [n_env, 3, n+1] / [n_env, 3, 3, n] / [n_env, 3, n]."""
+        st = self.state_tensor()
+        v, n = self._view, self.n_elem
+        return {
+            "position_collection": st[:, v.f_position:v.f_position + 3, :n + 1],
+            "velocity_collection": st[:, v.f_velocity:v.f_velocity + 3, :n + 1],
+            "director_collection": st[:, v.f_director:v.f_director + 9, :n].unflatten(1, (3, 3)),
+            "omega_collection": st[:, v.f_omega:v.f_omega + 3, :n],
+            "tangents": st[:, v.f_tangents:v.f_tangents + 3, :n],
+            "kappa": st[:, v.f_kappa:v.f_kappa + 3, :n - 1],
+            "sigma": st[:, v.f_sigma:v.f_sigma + 3, :n],
+            "dilatation": st[:, v.f_dilatation, :n],
+        }
+
+    def set_state_from(self, other: "Handle"):
+        v = other.state_view()
+        _check(self._lib.sr_set_state(self._h, C.byref(v), self._stream_ptr()))

@@ -1,0 +1,680 @@
+// rod_kernels.cuh — the fused K-substep Cosserat-rod kernel for sm_100a.
+//
+// Mapping: one warp owns one rod (one env).  Lane l holds EPL consecutive
+// elements k = l*EPL + j (and node k, Voronoi point k) entirely in registers for
+// the whole launch; the difference / quadrature stencils (Delta_h, A_h) and the
+// Q_{k+1} access of the curvature are warp shuffles at lane boundaries.  State is
+// read from HBM once at launch entry and written once at exit (coalesced,
+// vectorised EPL-wide), so a launch of K substeps moves 16(18n+6)/(nK) bytes per
+// rod-element-substep (0.725 B at n=50, K=400): the kernel is FP64-pipe bound.
+//
+// What one substep computes (reference boundary
+// /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:183-184):
+//   x += dt/2 v ; Q <- exp(dt/2 w) Q ; constrain values ;
+//   l, t, e, eps ; sigma = e Q t - z ; n = S sigma ; f = Delta_h(Q^T n / e) ;
+//   kappa = log(Q_{k+1} Q_k^T)/D ; tau = B kappa ;
+//   T = Delta_h(tau/eps^3) + A_h(kappa x tau D/eps^3) + (Qt x n) l0 + (Jw/e) x w + (Jw/e) de/dt / e ;
+//   gravity + actuation ; v += dt (f+F)/m ; w += dt J^-1 (T) e ; constrain rates ; damping ;
+//   x += dt/2 v ; Q <- exp(dt/2 w) Q ; constrain values.
+#pragma once
+#include <stdint.h>
+#include "rod_math.cuh"
+
+namespace sr {
+
+// field indices inside one env's [n_fields][stride] block
+enum : int {
+  F_POS = 0, F_VEL = 3, F_DIR = 6, F_OMEGA = 15, F_TAN = 18, F_KAPPA = 21, F_SIGMA = 24,
+  F_DIL = 27, N_FIELDS = 28
+};
+constexpr int BC_DIM = 12;   // per-env anchors: fixed_position(3), fixed_directors(9)
+constexpr int AUX_DIM = 8;   // per-env model scratch (3D pendulum: base position(3), velocity(3))
+constexpr int WARPS_PER_CTA = 4;
+
+enum : int { BC_FREE = 0, BC_ONE_END_FIXED = 1, BC_PENDULUM_SLIDER = 2, BC_MOVING_BASE = 3 };
+enum : int { MODEL_ROD = 0, MODEL_SOFT_PENDULUM = 1, MODEL_SOFT_PENDULUM_3D = 2 };
+enum : int { MATH_FAST = 0, MATH_FAITHFUL = 1 };
+
+// Uniform-rod constants (all rods built by the reference are uniform:
+// CosseratRod.straight_rod with scalar radius, soft_pendulum/build.py:54-61).
+// Passed as a __grid_constant__ kernel parameter: operands come straight from
+// the constant bank, costing neither registers nor load instructions.
+template <typename T> struct RodArgs {
+  T *state;            // [n_env][N_FIELDS][stride]
+  const T *bc;         // [n_env][BC_DIM]
+  T *aux;              // [n_env][AUX_DIM]
+  const float *action; // [n_env][action_dim]
+  float *obs;          // [n_env][obs_dim]
+  double *reward;      // [n_env]
+  uint8_t *terminated; // [n_env]
+  int n_env, n_elem, stride, n_substeps;
+  int bc_kind, model, point_force, damp_first, damping_on, laplace_order, action_dim, obs_dim;
+  T dt, half_dt;
+  T rest_len, inv_rest_len, rest_vor, inv_rest_vor;
+  T S[3], B[3], J[3], Jinv[3];
+  T mass, inv_mass, dt_inv_mass;  // interior node (end nodes carry half the mass)
+  T g[3], gdt[3];
+  T c_v, c_w[3], logc_w[3];
+};
+
+template <typename T, int EPL> struct Vec;
+template <> struct Vec<double, 1> { using type = double; };
+template <> struct Vec<double, 2> { using type = double2; };
+template <> struct Vec<double, 4> { using type = double4; };
+template <> struct Vec<float, 1> { using type = float; };
+template <> struct Vec<float, 2> { using type = float2; };
+template <> struct Vec<float, 4> { using type = float4; };
+
+// EPL consecutive slots of one field row, as a single vector access (coalesced
+// across the warp: 32 * EPL * sizeof(T) contiguous bytes).
+template <typename T, int EPL>
+__device__ __forceinline__ void load_row(const T *row, int lane, T (&out)[EPL]) {
+  using VT = typename Vec<T, EPL>::type;
+  VT v = reinterpret_cast<const VT *>(row)[lane];
+  const T *p = reinterpret_cast<const T *>(&v);
+#pragma unroll
+  for (int j = 0; j < EPL; j++) out[j] = p[j];
+}
+template <typename T, int EPL>
+__device__ __forceinline__ void store_row(T *row, int lane, const T (&in)[EPL]) {
+  using VT = typename Vec<T, EPL>::type;
+  VT v;
+  T *p = reinterpret_cast<T *>(&v);
+#pragma unroll
+  for (int j = 0; j < EPL; j++) p[j] = in[j];
+  reinterpret_cast<VT *>(row)[lane] = v;
+}
+
+// value of the same quantity at slot k+1 / k-1 (neighbour lane at the edges)
+template <typename T, int EPL>
+__device__ __forceinline__ void shift_next(const T (&a)[EPL], T (&out)[EPL]) {
+  T edge = __shfl_down_sync(FULL, a[0], 1);
+#pragma unroll
+  for (int j = 0; j < EPL; j++) out[j] = (j < EPL - 1) ? a[(j + 1) % EPL] : edge;
+}
+template <typename T, int EPL>
+__device__ __forceinline__ void shift_prev(const T (&a)[EPL], int lane, T (&out)[EPL]) {
+  T edge = __shfl_up_sync(FULL, a[EPL - 1], 1);
+  if (lane == 0) edge = T(0);  // slot -1 does not exist: stencils see 0 there
+#pragma unroll
+  for (int j = 0; j < EPL; j++) out[j] = (j > 0) ? a[(j + EPL - 1) % EPL] : edge;
+}
+
+// ---- Rodrigues update Q <- R(h w) Q   -------------------------
+template <typename T, int MATH>
+__device__ __forceinline__ void rotate_directors(T h, const T w[3], T Q[9], bool use_fast) {
+  T a0 = h * w[0], a1 = h * w[1], a2 = h * w[2];
+  T q = fma(a2, a2, fma(a1, a1, a0 * a0));
+  if (MATH == MATH_FAST && use_fast) {
+    // R = I + A K + B K^2 with A = sin(t)/t, B = (1-cos t)/t^2; apply as Q += D Q, D = R - I
+    T A, B;
+    sinc_cosc(q, A, B);
+    T Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
+    T Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
+    T D00 = -fma(Ba1, a1, Ba2 * a2), D11 = -fma(Ba0, a0, Ba2 * a2), D22 = -fma(Ba0, a0, Ba1 * a1);
+    T D01 = fma(Ba0, a1, Aa2), D10 = fma(Ba0, a1, -Aa2);
+    T D02 = fma(Ba0, a2, -Aa1), D20 = fma(Ba0, a2, Aa1);
+    T D12 = fma(Ba1, a2, Aa0), D21 = fma(Ba1, a2, -Aa0);
+    T n[9];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      n[0 + m] = fma(D02, Q[6 + m], fma(D01, Q[3 + m], fma(D00, Q[0 + m], Q[0 + m])));
+      n[3 + m] = fma(D12, Q[6 + m], fma(D11, Q[3 + m], fma(D10, Q[0 + m], Q[3 + m])));
+      n[6 + m] = fma(D22, Q[6 + m], fma(D21, Q[3 + m], fma(D20, Q[0 + m], Q[6 + m])));
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) Q[i] = n[i];
+  } else {
+    // reference operation order (elastica/_rotations.py:_get_rotation_matrix)
+    T theta = sqrt_(q);
+    T d = theta + T(1e-14);
+    T v0 = a0 / d, v1 = a1 / d, v2 = a2 / d;
+    T up, cs;
+    sincos_(theta, &up, &cs);
+    T us = T(1.0) - cs;
+    T R00 = T(1.0) - us * (v1 * v1 + v2 * v2);
+    T R11 = T(1.0) - us * (v0 * v0 + v2 * v2);
+    T R22 = T(1.0) - us * (v0 * v0 + v1 * v1);
+    T R01 = up * v2 + us * v0 * v1, R10 = -up * v2 + us * v0 * v1;
+    T R02 = -up * v1 + us * v0 * v2, R20 = up * v1 + us * v0 * v2;
+    T R12 = up * v0 + us * v1 * v2, R21 = -up * v0 + us * v1 * v2;
+    T n[9];
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      n[0 + m] = R00 * Q[0 + m] + R01 * Q[3 + m] + R02 * Q[6 + m];
+      n[3 + m] = R10 * Q[0 + m] + R11 * Q[3 + m] + R12 * Q[6 + m];
+      n[6 + m] = R20 * Q[0 + m] + R21 * Q[3 + m] + R22 * Q[6 + m];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) Q[i] = n[i];
+  }
+}
+
+// numpy's pairwise float64 row sum (np.mean over the contiguous axis), n <= 128
+template <typename T> __device__ inline double np_pairwise_sum(const T *a, int n) {
+  if (n < 8) {
+    double r = 0.0;
+    for (int i = 0; i < n; i++) r += (double)a[i];
+    return r;
+  }
+  double r[8];
+  for (int j = 0; j < 8; j++) r[j] = (double)a[j];
+  int i;
+  for (i = 8; i < n - (n % 8); i += 8)
+    for (int j = 0; j < 8; j++) r[j] += (double)a[i + j];
+  double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+  for (; i < n; i++) res += (double)a[i];
+  return res;
+}
+
+__device__ inline double np_mod(double a, double b) {
+  double m = fmod(a, b);
+  if (m != 0.0) { if ((b < 0) != (m < 0)) m += b; }
+  else m = copysign(0.0, b);
+  return m;
+}
+
+// SoftPendulum-v0 observation / reward from the (stale) tangents in shared memory
+// (reference soft_pendulum.py:149-161, 196-214)
+template <typename T>
+__device__ inline void soft_pendulum_outputs(const T *tan_smem, int stride, int n, double x0,
+                                             double vx0, float prev_action, bool invalid,
+                                             float *obs, double *reward, uint8_t *terminated) {
+  const double PI = 3.141592653589793;
+  double mx = np_pairwise_sum(tan_smem + 0 * stride, n) / (double)n;
+  double my = np_pairwise_sum(tan_smem + 1 * stride, n) / (double)n;
+  double theta = atan(mx / my);
+  theta = np_mod(theta + PI, 2 * PI) - PI;
+  obs[0] = (float)x0;
+  obs[1] = (float)vx0;
+  obs[2] = prev_action;
+  obs[3] = (float)theta;
+  if (reward) {
+    double forward = 0.0, survive = 0.0;
+    if (invalid) survive = -50.0;
+    else forward = fabs(x0) * 10 + theta * theta;
+    *reward = forward - 0.0 + survive;
+    *terminated = invalid ? 1 : 0;
+  }
+}
+
+template <typename T, int EPL, int MATH>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
+  __shared__ T tan_smem[WARPS_PER_CTA][3 * 32 * EPL];
+  const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+  const int env = blockIdx.x * WARPS_PER_CTA + wic;
+  if (env >= A.n_env) return;
+  const int n = A.n_elem, stride = A.stride;
+  T *st = A.state + (size_t)env * N_FIELDS * stride;
+
+  T x[3][EPL], v[3][EPL], Q[9][EPL], w[3][EPL];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    load_row<T, EPL>(st + (F_POS + c) * stride, lane, x[c]);
+    load_row<T, EPL>(st + (F_VEL + c) * stride, lane, v[c]);
+    load_row<T, EPL>(st + (F_OMEGA + c) * stride, lane, w[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 9; c++) load_row<T, EPL>(st + (F_DIR + c) * stride, lane, Q[c]);
+
+  bool elem_ok[EPL], node_ok[EPL], vor_ok[EPL];
+  T minv_scale[EPL];
+#pragma unroll
+  for (int j = 0; j < EPL; j++) {
+    int k = lane * EPL + j;
+    elem_ok[j] = k < n;
+    node_ok[j] = k <= n;
+    vor_ok[j] = k < n - 1;
+    minv_scale[j] = (k == 0 || k == n) ? T(2) : T(1);
+  }
+  // per-env anchors and actuation (only lane 0 / node 0 uses them)
+  const T *bc = A.bc + (size_t)env * BC_DIM;
+  T act0 = T(0), base_px = T(0), base_py = T(0), base_vx = T(0), base_vy = T(0);
+  if (A.action_dim > 0) act0 = (T)A.action[(size_t)env * A.action_dim];
+  if (A.bc_kind == BC_MOVING_BASE) {
+    const T *aux = A.aux + (size_t)env * AUX_DIM;
+    base_px = aux[0]; base_py = aux[1]; base_vx = aux[3]; base_vy = aux[4];
+  }
+
+  auto constrain_values = [&]() {
+    if (lane == 0) {
+      if (A.bc_kind == BC_PENDULUM_SLIDER) {
+        x[1][0] = bc[1]; x[2][0] = bc[2];
+#pragma unroll
+        for (int m = 0; m < 3; m++) { Q[0 + m][0] = bc[3 + m]; Q[6 + m][0] = bc[9 + m]; }
+      } else if (A.bc_kind == BC_ONE_END_FIXED) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) x[c][0] = bc[c];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c][0] = bc[3 + c];
+      } else if (A.bc_kind == BC_MOVING_BASE) {
+        x[0][0] = base_px; x[1][0] = base_py; x[2][0] = bc[2];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c][0] = bc[3 + c];
+      }
+    }
+  };
+  auto constrain_rates = [&]() {
+    if (lane == 0) {
+      if (A.bc_kind == BC_PENDULUM_SLIDER) {
+        v[1][0] = T(0); v[2][0] = T(0); w[0][0] = T(0); w[2][0] = T(0);
+      } else if (A.bc_kind == BC_ONE_END_FIXED) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { v[c][0] = T(0); w[c][0] = T(0); }
+      } else if (A.bc_kind == BC_MOVING_BASE) {
+        v[0][0] = base_vx; v[1][0] = base_vy; v[2][0] = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) w[c][0] = T(0);
+      }
+    }
+  };
+  auto kinematic = [&](T h) {
+    bool fast = true;
+    if (MATH == MATH_FAST) {
+      T qmax = T(0);
+#pragma unroll
+      for (int j = 0; j < EPL; j++) {
+        T a0 = h * w[0][j], a1 = h * w[1][j], a2 = h * w[2][j];
+        qmax = fmax(qmax, fma(a2, a2, fma(a1, a1, a0 * a0)));
+      }
+      fast = !__any_sync(FULL, !(qmax <= T(kSmallRotQ)));
+    }
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) x[c][j] = fma(h, v[c][j], x[c][j]);
+      T wj[3] = {w[0][j], w[1][j], w[2][j]};
+      T Qj[9];
+#pragma unroll
+      for (int c = 0; c < 9; c++) Qj[c] = Q[c][j];
+      rotate_directors<T, MATH>(h, wj, Qj, fast);
+#pragma unroll
+      for (int c = 0; c < 9; c++) Q[c][j] = Qj[c];
+    }
+  };
+
+  const T h = A.half_dt, dt = A.dt;
+  bool invalid_any = false;
+
+#pragma unroll 1
+  for (int s = 0; s < A.n_substeps; s++) {
+    const bool last = (s == A.n_substeps - 1);
+    kinematic(h);
+    constrain_values();
+
+    // ---------------- geometry, shear/stretch strain, internal force ----------
+    T xn[3][EPL], vn[3][EPL];
+#pragma unroll
+    for (int c = 0; c < 3; c++) { shift_next<T, EPL>(x[c], xn[c]); shift_next<T, EPL>(v[c], vn[c]); }
+    T lg[EPL], e[EPL], inv_e[EPL], edot[EPL];
+    T tng[3][EPL], sig[3][EPL], nst[3][EPL], Qt[3][EPL], sfl[3][EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
+      T dx[3], dv[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { dx[c] = xn[c][j] - x[c][j]; dv[c] = vn[c][j] - v[c][j]; }
+      if (!elem_ok[j]) { dx[0] = T(0); dx[1] = T(0); dx[2] = A.rest_len; dv[0] = dv[1] = dv[2] = T(0); }
+      T l2 = dot3(dx, dx);
+      T t[3];
+      if (MATH == MATH_FAST) {
+        T il = rsqrt_(l2);
+        T l = l2 * il;
+        lg[j] = l + T(1e-14);                     // reference guard on the length
+        T ilg = fma(T(-1e-14) * il, il, il);      // 1/(l + 1e-14) to first order in 1e-14/l
+#pragma unroll
+        for (int c = 0; c < 3; c++) t[c] = dx[c] * ilg;
+        e[j] = lg[j] * A.inv_rest_len;
+        inv_e[j] = A.rest_len * ilg;
+        edot[j] = dot3(dx, dv) * ilg * A.inv_rest_len;
+      } else {
+        lg[j] = sqrt_(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) + T(1e-14);
+#pragma unroll
+        for (int c = 0; c < 3; c++) t[c] = dx[c] / lg[j];
+        e[j] = lg[j] / A.rest_len;
+        inv_e[j] = T(1.0) / e[j];
+        // r.v terms exactly as elastica/rod/cosserat_rod.py:_compute_dilatation_rate
+        T xk[3] = {x[0][j], x[1][j], x[2][j]}, vk[3] = {v[0][j], v[1][j], v[2][j]};
+        T xk1[3] = {xk[0] + dx[0], xk[1] + dx[1], xk[2] + dx[2]};
+        T vk1[3] = {vk[0] + dv[0], vk[1] + dv[1], vk[2] + dv[2]};
+        if (elem_ok[j]) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) { xk1[c] = xn[c][j]; vk1[c] = vn[c][j]; }
+        }
+        T rv0 = xk[0] * vk[0] + xk[1] * vk[1] + xk[2] * vk[2];
+        T rv1 = xk1[0] * vk1[0] + xk1[1] * vk1[1] + xk1[2] * vk1[2];
+        T rp1v = xk1[0] * vk[0] + xk1[1] * vk[1] + xk1[2] * vk[2];
+        T rvp1 = xk[0] * vk1[0] + xk[1] * vk1[1] + xk[2] * vk1[2];
+        edot[j] = (rv0 + rv1 - rvp1 - rp1v) / lg[j] / A.rest_len;
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        tng[i][j] = t[i];
+        T qt = (MATH == MATH_FAST)
+                   ? fma(Q[3 * i + 2][j], t[2], fma(Q[3 * i + 1][j], t[1], Q[3 * i][j] * t[0]))
+                   : (Q[3 * i][j] * t[0] + Q[3 * i + 1][j] * t[1] + Q[3 * i + 2][j] * t[2]);
+        Qt[i][j] = qt;
+        sig[i][j] = e[j] * qt - (i == 2 ? T(1) : T(0));
+        nst[i][j] = A.S[i] * sig[i][j];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T sv = (MATH == MATH_FAST)
+                   ? fma(Q[6 + i][j], nst[2][j], fma(Q[3 + i][j], nst[1][j], Q[i][j] * nst[0][j])) * inv_e[j]
+                   : (Q[i][j] * nst[0][j] + Q[3 + i][j] * nst[1][j] + Q[6 + i][j] * nst[2][j]) / e[j];
+        sfl[i][j] = elem_ok[j] ? sv : T(0);
+      }
+    }
+    T f[3][EPL];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      T sp[EPL];
+      shift_prev<T, EPL>(sfl[i], lane, sp);
+#pragma unroll
+      for (int j = 0; j < EPL; j++) f[i][j] = sfl[i][j] - sp[j];
+    }
+
+    // ---------------- curvature, bending couple, internal torque --------------
+    T Qn[9][EPL], lgn[EPL];
+#pragma unroll
+    for (int c = 0; c < 9; c++) shift_next<T, EPL>(Q[c], Qn[c]);
+    shift_next<T, EPL>(lg, lgn);
+    T kap[3][EPL], mcp[3][EPL], ccp[3][EPL];  // kappa ; tau/eps^3 ; (kappa x tau) D / eps^3
+    bool bend_fast = true;
+    T uu[EPL], vec[3][EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
+      // Rm = Q_{k+1} Q_k^T ; vec = axial(Rm - Rm^T) ; trace
+      auto rm = [&](int a, int b) {
+        return (MATH == MATH_FAST)
+                   ? fma(Qn[3 * a + 2][j], Q[3 * b + 2][j], fma(Qn[3 * a + 1][j], Q[3 * b + 1][j], Qn[3 * a][j] * Q[3 * b][j]))
+                   : (Qn[3 * a][j] * Q[3 * b][j] + Qn[3 * a + 1][j] * Q[3 * b + 1][j] + Qn[3 * a + 2][j] * Q[3 * b + 2][j]);
+      };
+      vec[0][j] = rm(2, 1) - rm(1, 2);
+      vec[1][j] = rm(0, 2) - rm(2, 0);
+      vec[2][j] = rm(1, 0) - rm(0, 1);
+      T tr = rm(0, 0) + rm(1, 1) + rm(2, 2);
+      if (!vor_ok[j]) { tr = T(3); vec[0][j] = vec[1][j] = vec[2][j] = T(0); }
+      // 1 - cos(theta_ref) with the reference's 1e-10 guard, halved: u = sin^2(theta_ref/2)
+      uu[j] = T(0.5) * ((T(1.5) - T(0.5) * tr) + T(1e-10));
+      if (!(uu[j] <= T(kSmallBendU))) bend_fast = false;
+    }
+    if (MATH == MATH_FAST) bend_fast = !__any_sync(FULL, !bend_fast);
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
+      T fac;
+      if (MATH == MATH_FAST && bend_fast) {
+        fac = T(-0.5) * theta_over_sin(uu[j]);
+      } else {
+        T theta = acos_(T(1.0) - T(2.0) * uu[j]);
+        fac = T(-0.5) * theta / sin_(theta + T(1e-14));
+      }
+      T tau[3], kxt[3], kp[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        kp[i] = (MATH == MATH_FAST) ? (vec[i][j] * fac) * A.inv_rest_vor : (vec[i][j] * fac) / A.rest_vor;
+        kap[i][j] = kp[i];
+        tau[i] = A.B[i] * kp[i];
+      }
+      cross3(kp, tau, kxt);
+      T eps = (MATH == MATH_FAST) ? (T(0.5) * (lgn[j] + lg[j])) * A.inv_rest_vor
+                                  : (T(0.5) * (lgn[j] + lg[j])) / A.rest_vor;
+      T ie3 = (MATH == MATH_FAST) ? rcp_(eps * eps * eps) : T(1.0) / (eps * eps * eps);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        mcp[i][j] = vor_ok[j] ? tau[i] * ie3 : T(0);
+        ccp[i][j] = vor_ok[j] ? kxt[i] * A.rest_vor * ie3 : T(0);
+      }
+    }
+    T tq[3][EPL];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (MATH == MATH_FAST) {
+        // T_k = (m_k - m_{k-1}) + (c_k + c_{k-1})/2 = P_k + N_{k-1}; one shuffle instead of two
+        T P[EPL], N[EPL], Np[EPL];
+#pragma unroll
+        for (int j = 0; j < EPL; j++) {
+          P[j] = fma(T(0.5), ccp[i][j], mcp[i][j]);
+          N[j] = fma(T(0.5), ccp[i][j], -mcp[i][j]);
+        }
+        shift_prev<T, EPL>(N, lane, Np);
+#pragma unroll
+        for (int j = 0; j < EPL; j++) tq[i][j] = P[j] + Np[j];
+      } else {
+        T mp[EPL], cp[EPL];
+        shift_prev<T, EPL>(mcp[i], lane, mp);
+        shift_prev<T, EPL>(ccp[i], lane, cp);
+#pragma unroll
+        for (int j = 0; j < EPL; j++) tq[i][j] = (mcp[i][j] - mp[j]) + T(0.5) * (ccp[i][j] + cp[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
+      T qt[3] = {Qt[0][j], Qt[1][j], Qt[2][j]}, ns[3] = {nst[0][j], nst[1][j], nst[2][j]};
+      T wj[3] = {w[0][j], w[1][j], w[2][j]};
+      T ssc[3], jw[3], lt[3];
+      cross3(qt, ns, ssc);
+#pragma unroll
+      for (int i = 0; i < 3; i++) jw[i] = (MATH == MATH_FAST) ? (A.J[i] * wj[i]) * inv_e[j] : (A.J[i] * wj[i]) / e[j];
+      cross3(jw, wj, lt);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T ud = (MATH == MATH_FAST) ? jw[i] * edot[j] * inv_e[j] : jw[i] * edot[j] / e[j];
+        tq[i][j] = tq[i][j] + ssc[i] * A.rest_len + lt[i] + ud;
+      }
+    }
+
+    // stale observables of the reference (tangents/kappa/sigma/dilatation are only
+    // refreshed here, half a kinematic step before the final state: SURVEY A.6)
+    if (last) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        store_row<T, EPL>(st + (F_TAN + i) * stride, lane, tng[i]);
+        store_row<T, EPL>(st + (F_KAPPA + i) * stride, lane, kap[i]);
+        store_row<T, EPL>(st + (F_SIGMA + i) * stride, lane, sig[i]);
+        store_row<T, EPL>(&tan_smem[wic][i * 32 * EPL], lane, tng[i]);
+      }
+      store_row<T, EPL>(st + F_DIL * stride, lane, e);
+    }
+
+    // ---------------- external loads + dynamic step ---------------------------
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
+      const bool base_node = (lane == 0 && j == 0);
+      if (MATH == MATH_FAST) {
+        T dtim = A.dt_inv_mass * minv_scale[j];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          T fi = f[i][j], gd = A.gdt[i];
+          if (i == 0 && A.point_force && base_node) { fi += act0; gd = T(0); }
+          T vnew = fma(fi, dtim, v[i][j]) + gd;
+          v[i][j] = node_ok[j] ? vnew : v[i][j];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          T wnew = fma(dt * e[j], A.Jinv[i] * tq[i][j], w[i][j]);
+          w[i][j] = elem_ok[j] ? wnew : w[i][j];
+        }
+      } else {
+        T m = A.mass / minv_scale[j];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          T fe = A.g[i] * m;
+          if (i == 0 && A.point_force && base_node) fe = act0;
+          T acc = (f[i][j] + fe) / m;
+          v[i][j] = node_ok[j] ? v[i][j] + dt * acc : v[i][j];
+          T alpha = (A.Jinv[i] * tq[i][j]) * e[j];
+          w[i][j] = elem_ok[j] ? w[i][j] + dt * alpha : w[i][j];
+        }
+      }
+    }
+
+    // ---------------- rate constraints and dissipation -------------------------
+    auto dampen = [&]() {
+      if (A.damping_on) {
+        bool ef = true;
+        T z[3][EPL];
+        if (MATH == MATH_FAST) {
+#pragma unroll
+          for (int j = 0; j < EPL; j++)
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              z[i][j] = (e[j] - T(1)) * A.logc_w[i];
+              if (!(fabs_(z[i][j]) <= T(kSmallExpZ))) ef = false;
+            }
+          ef = !__any_sync(FULL, !ef);
+        }
+#pragma unroll
+        for (int j = 0; j < EPL; j++)
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            v[i][j] = v[i][j] * A.c_v;
+            T cw;
+            if (MATH == MATH_FAST && ef) cw = A.c_w[i] * exp_small(z[i][j]);
+            else if (MATH == MATH_FAST) cw = exp_(e[j] * A.logc_w[i]);
+            else cw = pow_(A.c_w[i], e[j]);
+            w[i][j] = w[i][j] * cw;
+          }
+      }
+    };
+    if (A.damp_first) { dampen(); constrain_rates(); }
+    else { constrain_rates(); dampen(); }
+
+    kinematic(h);
+    constrain_values();
+  }
+
+  // ---------------- write back + NaN guard + model outputs ---------------------
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    store_row<T, EPL>(st + (F_POS + c) * stride, lane, x[c]);
+    store_row<T, EPL>(st + (F_VEL + c) * stride, lane, v[c]);
+    store_row<T, EPL>(st + (F_OMEGA + c) * stride, lane, w[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 9; c++) store_row<T, EPL>(st + (F_DIR + c) * stride, lane, Q[c]);
+#pragma unroll
+  for (int j = 0; j < EPL; j++)
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+      if (node_ok[j] && (x[c][j] != x[c][j] || v[c][j] != v[c][j])) invalid_any = true;
+  invalid_any = __any_sync(FULL, invalid_any);
+  __syncwarp();
+  if (lane == 0) {
+    if (A.model == MODEL_SOFT_PENDULUM) {
+      soft_pendulum_outputs<T>(tan_smem[wic], 32 * EPL, n, (double)x[0][0], (double)v[0][0],
+                               (float)act0, invalid_any, A.obs + (size_t)env * A.obs_dim,
+                               A.reward + env, A.terminated + env);
+    } else {
+      // plain rod: obs = tip position (3) + tip velocity (3); reward 0
+      A.reward[env] = 0.0;
+      A.terminated[env] = invalid_any ? 1 : 0;
+    }
+  }
+  if (A.model == MODEL_ROD) {
+    // tip node n lives at lane n/EPL slot n%EPL
+#pragma unroll
+    for (int j = 0; j < EPL; j++)
+      if (lane * EPL + j == n) {
+        float *o = A.obs + (size_t)env * A.obs_dim;
+        for (int c = 0; c < 3; c++) { o[c] = (float)x[c][j]; o[3 + c] = (float)v[c][j]; }
+      }
+  }
+}
+
+// ---- reset: CosseratRod.straight_rod + finalize-time anchors ----
+template <typename T>
+__global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx, int n_reset,
+                                 const double *init, int n, int stride, double base_length) {
+  int r = blockIdx.x;
+  if (r >= n_reset) return;
+  int env = env_idx ? env_idx[r] : r;
+  const double *ip = init + (size_t)r * 9;
+  double start[3] = {ip[0], ip[1], ip[2]}, dir[3] = {ip[3], ip[4], ip[5]}, nor[3] = {ip[6], ip[7], ip[8]};
+  double nn = sqrt(nor[0] * nor[0] + nor[1] * nor[1] + nor[2] * nor[2]);
+  for (int c = 0; c < 3; c++) nor[c] = nor[c] / nn;
+  T *st = state + (size_t)env * N_FIELDS * stride;
+  // np.linspace(start, end, n+1): k*step + start, last point = end exactly
+  double step[3], end[3];
+  for (int c = 0; c < 3; c++) {
+    end[c] = __dadd_rn(start[c], __dmul_rn(dir[c], base_length));
+    step[c] = (end[c] - start[c]) / (double)n;
+  }
+  auto pos = [&](int c, int k) { return k == n ? end[c] : __dadd_rn(__dmul_rn((double)k, step[c]), start[c]); };
+  for (int k = threadIdx.x; k < stride; k += blockDim.x) {
+    double xk[3] = {0, 0, 0}, t[3] = {0, 0, 1}, Qk[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    double tang[3] = {0, 0, 0}, sg[3] = {0, 0, 0}, dil = 1.0;
+    if (k <= n) for (int c = 0; c < 3; c++) xk[c] = pos(c, k);
+    if (k < n) {
+      double d[3];
+      for (int c = 0; c < 3; c++) d[c] = pos(c, k + 1) - xk[c];
+      double rl = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2])));
+      for (int c = 0; c < 3; c++) t[c] = d[c] / rl;
+      for (int c = 0; c < 3; c++) { Qk[c] = nor[c]; Qk[6 + c] = t[c]; }
+      Qk[3] = __dadd_rn(__dmul_rn(t[1], nor[2]), -__dmul_rn(t[2], nor[1]));
+      Qk[4] = __dadd_rn(__dmul_rn(t[2], nor[0]), -__dmul_rn(t[0], nor[2]));
+      Qk[5] = __dadd_rn(__dmul_rn(t[0], nor[1]), -__dmul_rn(t[1], nor[0]));
+      double lg = rl + 1e-14;
+      for (int c = 0; c < 3; c++) tang[c] = d[c] / lg;
+      dil = lg / rl;
+      for (int i = 0; i < 3; i++) {
+        double qt = __dadd_rn(__dadd_rn(__dmul_rn(Qk[3 * i], tang[0]), __dmul_rn(Qk[3 * i + 1], tang[1])),
+                              __dmul_rn(Qk[3 * i + 2], tang[2]));
+        sg[i] = __dmul_rn(dil, qt) - (i == 2 ? 1.0 : 0.0);
+      }
+    }
+    for (int c = 0; c < 3; c++) {
+      st[(F_POS + c) * stride + k] = (T)xk[c];
+      st[(F_VEL + c) * stride + k] = T(0);
+      st[(F_OMEGA + c) * stride + k] = T(0);
+      st[(F_TAN + c) * stride + k] = (T)tang[c];
+      st[(F_KAPPA + c) * stride + k] = T(0);
+      st[(F_SIGMA + c) * stride + k] = (T)sg[c];
+    }
+    for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + k] = (T)Qk[c];
+    st[F_DIL * stride + k] = (T)dil;
+    if (k == 0) {
+      T *b = bc + (size_t)env * BC_DIM;
+      for (int c = 0; c < 3; c++) b[c] = (T)xk[c];
+      for (int c = 0; c < 9; c++) b[3 + c] = (T)Qk[c];
+      T *a = aux + (size_t)env * AUX_DIM;
+      for (int c = 0; c < AUX_DIM; c++) a[c] = T(0);
+    }
+  }
+}
+
+// observation of the current state without stepping (reset obs; soft_pendulum.py:149-161)
+template <typename T>
+__global__ void rod_observe_kernel(const T *state, const float *prev_action, float *obs, int n_env,
+                                   int n, int stride, int model, int action_dim, int obs_dim) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n_env) return;
+  const T *st = state + (size_t)env * N_FIELDS * stride;
+  float pa = (prev_action && action_dim > 0) ? prev_action[(size_t)env * action_dim] : 0.0f;
+  if (model == MODEL_SOFT_PENDULUM) {
+    soft_pendulum_outputs<T>(st + F_TAN * stride, stride, n, (double)st[F_POS * stride],
+                             (double)st[F_VEL * stride], pa, false, obs + (size_t)env * obs_dim,
+                             nullptr, nullptr);
+  } else {
+    float *o = obs + (size_t)env * obs_dim;
+    for (int c = 0; c < 3; c++) {
+      o[c] = (float)st[(F_POS + c) * stride + n];
+      o[3 + c] = (float)st[(F_VEL + c) * stride + n];
+    }
+  }
+}
+
+// register-resident DFMA chains: the FP64 roofline denominator
+__global__ void dfma_peak_kernel(double *out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; i++) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace sr

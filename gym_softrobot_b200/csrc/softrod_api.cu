@@ -1,0 +1,341 @@
+// softrod_api.cu — C-ABI (include/softrod.h) over the fused rod kernels.
+//
+// Host side of the boundary that replaces
+//   `time = PositionVerlet().step(simulator, time, dt)` x step_skip
+//   (/root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:183-184)
+// and `CosseratRod.straight_rod(...)` + plugin registration
+//   (/root/reference/gym_softrobot/envs/soft_pendulum/build.py:54-113).
+// Rod constants follow SURVEY.md Appendix A.1 / A.4 in FP64 on the host.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/softrod.h"
+#include "rod_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+#define SR_CUDA(expr)                                                                      \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return fail(SR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+  } while (0)
+
+template <typename T> struct DeviceBufs {
+  T *state = nullptr, *bc = nullptr, *aux = nullptr;
+};
+
+}  // namespace
+
+struct sr_handle {
+  sr_config cfg;
+  int epl = 0, stride = 0, obs_dim = 0, action_dim = 0;
+  size_t elem_size = 8;
+  void *state = nullptr, *bc = nullptr, *aux = nullptr;
+  sr::RodArgs<double> a64;
+  sr::RodArgs<float> a32;
+  // staging for the host-buffer entry points
+  float *d_action = nullptr, *d_obs = nullptr, *h_action = nullptr, *h_obs = nullptr;
+  double *d_reward = nullptr, *h_reward = nullptr, *d_init = nullptr, *h_init = nullptr;
+  uint8_t *d_term = nullptr, *h_term = nullptr;
+  int32_t *d_idx = nullptr;
+  cudaStream_t own_stream = nullptr;
+  int64_t launches = 0;
+};
+
+namespace {
+
+// constants of a uniform straight rod, FP64 on the host.
+template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs<T> &A) {
+  const double PI = 3.141592653589793;
+  const int n = c.n_elem;
+  const double rl = c.base_length / n;
+  const double r = c.base_radius;
+  const double A0 = PI * r * r;
+  const double I1 = A0 * A0 / (4.0 * PI), I2 = I1, I3 = 2.0 * I2;
+  const double E = c.youngs_modulus;
+  const double G = c.shear_modulus > 0.0 ? c.shear_modulus : E / (2.0 * (1.0 + 0.5));
+  const double ac = 27.0 / 28.0;
+  const double rho_l = c.density * rl;
+  const double J[3] = {I1 * rho_l, I2 * rho_l, I3 * rho_l};
+  const double S[3] = {ac * G * A0, ac * G * A0, E * A0};
+  const double Bv[3] = {E * I1, E * I2, G * I3};  // uniform rod: Voronoi average = element value
+  const double volume = PI * (r * r) * rl;
+  const double mass = c.density * volume;  // interior node; end nodes carry mass/2
+  memset(&A, 0, sizeof(A));
+  A.n_env = c.n_env; A.n_elem = n; A.stride = stride;
+  A.bc_kind = c.bc_kind; A.model = c.model; A.point_force = c.point_force_on_base;
+  A.damp_first = c.damping_before_constraints; A.damping_on = c.damping_constant >= 0.0;
+  A.laplace_order = c.laplace_filter_order;
+  A.dt = (T)c.dt; A.half_dt = (T)(0.5 * c.dt);
+  A.rest_len = (T)rl; A.inv_rest_len = (T)(1.0 / rl);
+  A.rest_vor = (T)rl; A.inv_rest_vor = (T)(1.0 / rl);
+  for (int i = 0; i < 3; i++) {
+    A.S[i] = (T)S[i]; A.B[i] = (T)Bv[i]; A.J[i] = (T)J[i]; A.Jinv[i] = (T)(1.0 / J[i]);
+    A.g[i] = (T)c.gravity[i]; A.gdt[i] = (T)(c.gravity[i] * c.dt);
+  }
+  A.mass = (T)mass; A.inv_mass = (T)(1.0 / mass); A.dt_inv_mass = (T)(c.dt / mass);
+  if (c.damping_constant >= 0.0) {
+    // element mass incl. the end-element correction equals `mass` for a uniform rod
+    A.c_v = (T)exp(-c.damping_constant * c.dt);
+    for (int i = 0; i < 3; i++) {
+      double lc = -c.damping_constant * c.dt * mass * (1.0 / J[i]);
+      A.logc_w[i] = (T)lc;
+      A.c_w[i] = (T)exp(lc);
+    }
+  } else {
+    A.c_v = (T)1.0;
+    for (int i = 0; i < 3; i++) { A.logc_w[i] = (T)0.0; A.c_w[i] = (T)1.0; }
+  }
+}
+
+template <typename T, int EPL, int MATH> int launch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  int grid = (A.n_env + sr::WARPS_PER_CTA - 1) / sr::WARPS_PER_CTA;
+  sr::rod_substeps_kernel<T, EPL, MATH><<<grid, sr::WARPS_PER_CTA * 32, 0, s>>>(A);
+  h->launches++;
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  const bool fast = h->cfg.math == SR_MATH_FAST;
+  switch (h->epl) {
+    case 1: return fast ? launch_substeps<T, 1, sr::MATH_FAST>(h, A, s) : launch_substeps<T, 1, sr::MATH_FAITHFUL>(h, A, s);
+    case 2: return fast ? launch_substeps<T, 2, sr::MATH_FAST>(h, A, s) : launch_substeps<T, 2, sr::MATH_FAITHFUL>(h, A, s);
+    case 4: return fast ? launch_substeps<T, 4, sr::MATH_FAST>(h, A, s) : launch_substeps<T, 4, sr::MATH_FAITHFUL>(h, A, s);
+  }
+  return fail(SR_E_INVALID, "unsupported elements-per-lane");
+}
+
+}  // namespace
+
+extern "C" {
+
+int sr_abi_version(void) { return SR_ABI_VERSION; }
+const char *sr_last_error(void) { return g_err.c_str(); }
+
+int sr_create(const sr_config *cfg, sr_handle **out) {
+  if (!cfg || !out) return fail(SR_E_INVALID, "sr_create: null argument");
+  *out = nullptr;
+  if (cfg->struct_size != (int32_t)sizeof(sr_config))
+    return fail(SR_E_INVALID, "sr_create: sr_config.struct_size mismatch (ABI skew)");
+  if (cfg->n_env <= 0 || cfg->n_elem < 3) return fail(SR_E_INVALID, "sr_create: n_env > 0 and n_elem >= 3 required");
+  if (cfg->n_elem > 127) return fail(SR_E_INVALID, "sr_create: n_elem <= 127 in this build (one warp per rod, <= 4 elements per lane)");
+  if (cfg->dtype != SR_DTYPE_F64) return fail(SR_E_INVALID, "sr_create: only SR_DTYPE_F64 is built so far");
+  if (cfg->model != SR_MODEL_ROD && cfg->model != SR_MODEL_SOFT_PENDULUM)
+    return fail(SR_E_INVALID, "sr_create: unsupported model");
+  if (cfg->bc_kind < SR_BC_FREE || cfg->bc_kind > SR_BC_PENDULUM_SLIDER)
+    return fail(SR_E_INVALID, "sr_create: unsupported bc_kind");
+  if (cfg->laplace_filter_order != 0) return fail(SR_E_INVALID, "sr_create: Laplace filter not built yet");
+  if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
+      !(cfg->youngs_modulus > 0.0))
+    return fail(SR_E_INVALID, "sr_create: dt, base_length, base_radius, density, youngs_modulus must be > 0");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SR_E_NO_DEVICE, "sr_create: no CUDA device (this library has no CPU fallback)");
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(SR_E_INVALID, "sr_create: bad device ordinal");
+  SR_CUDA(cudaSetDevice(cfg->device));
+
+  sr_handle *h = new (std::nothrow) sr_handle();
+  if (!h) return fail(SR_E_ALLOC, "sr_create: out of host memory");
+  h->cfg = *cfg;
+  // nodes 0..n need n+1 slots in 32*EPL
+  h->epl = (cfg->n_elem + 1 <= 32) ? 1 : (cfg->n_elem + 1 <= 64) ? 2 : 4;
+  h->stride = 32 * h->epl;
+  h->elem_size = 8;
+  if (cfg->model == SR_MODEL_SOFT_PENDULUM) { h->obs_dim = 4; h->action_dim = 1; }
+  else { h->obs_dim = 6; h->action_dim = 0; }
+  const size_t n_env = (size_t)cfg->n_env;
+  const size_t state_bytes = n_env * sr::N_FIELDS * h->stride * h->elem_size;
+  cudaError_t e;
+  if ((e = cudaMalloc(&h->state, state_bytes)) != cudaSuccess ||
+      (e = cudaMalloc(&h->bc, n_env * sr::BC_DIM * h->elem_size)) != cudaSuccess ||
+      (e = cudaMalloc(&h->aux, n_env * sr::AUX_DIM * h->elem_size)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_action, n_env * (h->action_dim ? h->action_dim : 1) * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_obs, n_env * h->obs_dim * sizeof(float))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_reward, n_env * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_term, n_env)) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_init, n_env * 9 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_idx, n_env * sizeof(int32_t))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_action, n_env * (h->action_dim ? h->action_dim : 1) * sizeof(float))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_obs, n_env * h->obs_dim * sizeof(float))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_reward, n_env * sizeof(double))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_term, n_env)) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_init, n_env * 9 * sizeof(double))) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMemset(h->state, 0, state_bytes)) != cudaSuccess) {
+    std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+    sr_destroy(h);
+    return fail(SR_E_ALLOC, m);
+  }
+  fill_args<double>(*cfg, h->stride, h->a64);
+  h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
+  h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim;
+  *out = h;
+  return SR_OK;
+}
+
+void sr_destroy(sr_handle *h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
+  cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
+  cudaFreeHost(h->h_init);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int sr_obs_dim(const sr_handle *h) { return h ? h->obs_dim : 0; }
+int sr_action_dim(const sr_handle *h) { return h ? h->action_dim : 0; }
+int sr_init_dim(const sr_handle *h) { return h ? 9 : 0; }
+int64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
+
+int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init_dev, void *stream) {
+  if (!h || !init_dev) return fail(SR_E_INVALID, "sr_reset: null argument");
+  if (n < 0 || n > h->cfg.n_env) return fail(SR_E_INVALID, "sr_reset: n out of range");
+  if (n == 0) return SR_OK;
+  SR_CUDA(cudaSetDevice(h->cfg.device));
+  sr::rod_reset_kernel<double><<<n, 64, 0, (cudaStream_t)stream>>>(
+      (double *)h->state, (double *)h->bc, (double *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
+      h->stride, h->cfg.base_length);
+  h->launches++;
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_dev, double *reward_dev,
+            uint8_t *terminated_dev, void *stream) {
+  if (!h || !obs_dev || !reward_dev || !terminated_dev) return fail(SR_E_INVALID, "sr_step: null output pointer");
+  if (h->action_dim > 0 && !action_dev) return fail(SR_E_INVALID, "sr_step: action required for this model");
+  if (n_substeps < 0) return fail(SR_E_INVALID, "sr_step: n_substeps < 0");
+  SR_CUDA(cudaSetDevice(h->cfg.device));
+  sr::RodArgs<double> A = h->a64;
+  A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
+  A.n_substeps = n_substeps;
+  return dispatch_substeps<double>(h, A, (cudaStream_t)stream);
+}
+
+int sr_observe(sr_handle *h, const float *prev_action_dev, float *obs_dev, void *stream) {
+  if (!h || !obs_dev) return fail(SR_E_INVALID, "sr_observe: null argument");
+  SR_CUDA(cudaSetDevice(h->cfg.device));
+  int bs = 128, grid = (h->cfg.n_env + bs - 1) / bs;
+  sr::rod_observe_kernel<double><<<grid, bs, 0, (cudaStream_t)stream>>>(
+      (const double *)h->state, prev_action_dev, obs_dev, h->cfg.n_env, h->cfg.n_elem, h->stride,
+      h->cfg.model, h->action_dim, h->obs_dim);
+  h->launches++;
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
+int sr_reset_host(sr_handle *h, const int32_t *env_idx_host, int n, const double *init_host) {
+  if (!h || !init_host) return fail(SR_E_INVALID, "sr_reset_host: null argument");
+  if (n < 0 || n > h->cfg.n_env) return fail(SR_E_INVALID, "sr_reset_host: n out of range");
+  if (n == 0) return SR_OK;
+  SR_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->own_stream;
+  memcpy(h->h_init, init_host, (size_t)n * 9 * sizeof(double));
+  SR_CUDA(cudaMemcpyAsync(h->d_init, h->h_init, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (env_idx_host)
+    SR_CUDA(cudaMemcpyAsync(h->d_idx, env_idx_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  int rc = sr_reset(h, env_idx_host ? h->d_idx : nullptr, n, h->d_init, s);
+  if (rc != SR_OK) return rc;
+  SR_CUDA(cudaStreamSynchronize(s));
+  return SR_OK;
+}
+
+int sr_step_host(sr_handle *h, const float *action_host, int n_substeps, float *obs_host,
+                 double *reward_host, uint8_t *terminated_host) {
+  if (!h || !obs_host || !reward_host || !terminated_host) return fail(SR_E_INVALID, "sr_step_host: null output pointer");
+  if (h->action_dim > 0 && !action_host) return fail(SR_E_INVALID, "sr_step_host: action required for this model");
+  SR_CUDA(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = h->own_stream;
+  const size_t n_env = (size_t)h->cfg.n_env;
+  if (h->action_dim > 0) {
+    memcpy(h->h_action, action_host, n_env * h->action_dim * sizeof(float));
+    SR_CUDA(cudaMemcpyAsync(h->d_action, h->h_action, n_env * h->action_dim * sizeof(float),
+                            cudaMemcpyHostToDevice, s));
+  }
+  int rc = sr_step(h, h->action_dim > 0 ? h->d_action : nullptr, n_substeps, h->d_obs, h->d_reward, h->d_term, s);
+  if (rc != SR_OK) return rc;
+  SR_CUDA(cudaMemcpyAsync(h->h_obs, h->d_obs, n_env * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  SR_CUDA(cudaMemcpyAsync(h->h_reward, h->d_reward, n_env * sizeof(double), cudaMemcpyDeviceToHost, s));
+  SR_CUDA(cudaMemcpyAsync(h->h_term, h->d_term, n_env, cudaMemcpyDeviceToHost, s));
+  SR_CUDA(cudaStreamSynchronize(s));
+  memcpy(obs_host, h->h_obs, n_env * h->obs_dim * sizeof(float));
+  memcpy(reward_host, h->h_reward, n_env * sizeof(double));
+  memcpy(terminated_host, h->h_term, n_env);
+  return SR_OK;
+}
+
+int sr_get_state(sr_handle *h, sr_state_view *out) {
+  if (!h || !out) return fail(SR_E_INVALID, "sr_get_state: null argument");
+  out->base = h->state;
+  out->n_env = h->cfg.n_env; out->n_fields = sr::N_FIELDS; out->stride = h->stride;
+  out->elem_size = (int32_t)h->elem_size;
+  out->f_position = sr::F_POS; out->f_velocity = sr::F_VEL; out->f_director = sr::F_DIR;
+  out->f_omega = sr::F_OMEGA; out->f_tangents = sr::F_TAN; out->f_kappa = sr::F_KAPPA;
+  out->f_sigma = sr::F_SIGMA; out->f_dilatation = sr::F_DIL;
+  return SR_OK;
+}
+
+int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream) {
+  if (!h || !src || !src->base) return fail(SR_E_INVALID, "sr_set_state: null argument");
+  if (src->n_env != h->cfg.n_env || src->n_fields != sr::N_FIELDS || src->stride != h->stride ||
+      src->elem_size != (int32_t)h->elem_size)
+    return fail(SR_E_INVALID, "sr_set_state: layout mismatch");
+  SR_CUDA(cudaSetDevice(h->cfg.device));
+  size_t bytes = (size_t)h->cfg.n_env * sr::N_FIELDS * h->stride * h->elem_size;
+  SR_CUDA(cudaMemcpyAsync(h->state, src->base, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return SR_OK;
+}
+
+int sr_measure_fp64_peak(int device, double *tflops_out) {
+  if (!tflops_out) return fail(SR_E_INVALID, "sr_measure_fp64_peak: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(SR_E_NO_DEVICE, "sr_measure_fp64_peak: no CUDA device");
+  }
+  SR_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  SR_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 15;
+  double *d = nullptr;
+  SR_CUDA(cudaMalloc(&d, (size_t)threads * blocks * sizeof(double)));
+  cudaEvent_t e0, e1;
+  SR_CUDA(cudaEventCreate(&e0));
+  SR_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 6; rep++) {
+    SR_CUDA(cudaEventRecord(e0));
+    sr::dfma_peak_kernel<<<blocks, threads>>>(d, iters);
+    SR_CUDA(cudaEventRecord(e1));
+    SR_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    SR_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    double flops = 2.0 * 8.0 * (double)iters * threads * blocks;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+  *tflops_out = best;
+  return SR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+/* softrod.h — C-ABI of the B200-native batched Cosserat-rod stepper.
+ *
+ * The reference (skim0119/gym-softrobot) has no FFI: its physics-step boundary
+ * is PyElastica's Python plugin API,
+ *     time = PositionVerlet().step(simulator, time, dt)
+ *   (/root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:137-139,184;
+ *    keyword form at /root/reference/gym_softrobot/envs/snake/continuum_snake.py:377)
+ * plus live NumPy views of the rod arrays (position/velocity/director/omega
+ * _collection, tangents, kappa, sigma: soft_pendulum.py:152-154,
+ * envs/octopus/flat_env.py:233-247).  This header is what a ctypes binding on
+ * the reference side would bind instead (stub in INTEGRATION.md).
+ *
+ * Conventions: plain C, plain pointers and sizes, no torch/CUDA types in the
+ * signatures (`stream` is a cudaStream_t passed as void*; NULL = default stream).
+ * Every call returns 0 on success or a negative SR_E_* code; the message is
+ * available from sr_last_error() (thread-local).  A handle belongs to one CUDA
+ * device and is not thread-safe; calls are stream-ordered.  Device pointers
+ * passed in are borrowed for the duration of the call only.
+ */
+#ifndef SOFTROD_H
+#define SOFTROD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR_ABI_VERSION 1
+
+/* status codes */
+#define SR_OK 0
+#define SR_E_INVALID (-1)  /* bad argument / unsupported configuration */
+#define SR_E_CUDA (-2)     /* CUDA runtime error (message has the detail) */
+#define SR_E_NO_DEVICE (-3)
+#define SR_E_ALLOC (-4)
+
+/* environment models (which plugins are fused around the rod substep) */
+#define SR_MODEL_ROD 0            /* plain rod: BC + gravity + damping (BASELINE config 3) */
+#define SR_MODEL_SOFT_PENDULUM 1  /* replaces build_soft_pendulum + SoftPendulumEnv.step
+                                     (envs/soft_pendulum/build.py:29-115, soft_pendulum.py:176-251) */
+#define SR_MODEL_SOFT_PENDULUM_3D 2 /* envs/soft_pendulum_3d/build.py:23-86, soft_pendulum_3d.py:122-158 */
+
+/* boundary conditions on node 0 / element 0 */
+#define SR_BC_FREE 0
+#define SR_BC_ONE_END_FIXED 1    /* PyElastica OneEndFixedBC */
+#define SR_BC_PENDULUM_SLIDER 2  /* PendulumBoundaryConditions, soft_pendulum/build.py:65-85 */
+#define SR_BC_MOVING_BASE 3      /* MovingBaseConstraint, soft_pendulum_3d/build.py:23-40 */
+
+/* arithmetic type of the state and of the kernel */
+#define SR_DTYPE_F64 0
+#define SR_DTYPE_F32 1
+
+/* kernel math variant */
+#define SR_MATH_FAST 0     /* strength-reduced (polynomial exp/log maps, shared reciprocals) */
+#define SR_MATH_FAITHFUL 1 /* libm calls in the reference's operation order */
+
+/* Replaces CosseratRod.straight_rod(...) + the plugin registrations of the
+ * reference build functions (soft_pendulum/build.py:54-113).  All rods of a
+ * handle share these parameters; per-env data (initial direction/normal, BC
+ * anchors, actions) is given to sr_reset / sr_step. */
+typedef struct sr_config {
+  int32_t struct_size;  /* = sizeof(sr_config), checked */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t model;        /* SR_MODEL_* */
+  int32_t dtype;        /* SR_DTYPE_* */
+  int32_t math;         /* SR_MATH_* */
+  int32_t n_env;        /* independent environments (one rod each) */
+  int32_t n_elem;       /* elements per rod */
+  int32_t bc_kind;      /* SR_BC_* */
+  int32_t point_force_on_base; /* F_ext[0,0] = action[env,0] each substep (build.py:94-105) */
+  int32_t damping_before_constraints; /* 1: [dampen_rates, constrain_rates] */
+  int32_t laplace_filter_order;       /* LaplaceDissipationFilter order, 0 = off */
+  int32_t reserved0;
+  double dt;            /* substep */
+  double base_length, base_radius, density, youngs_modulus;
+  double shear_modulus; /* <= 0: PyElastica default E/(2(1+0.5)) */
+  double gravity[3];
+  double damping_constant; /* AnalyticalLinearDamper; < 0 = off */
+} sr_config;
+
+/* Device views of the structure-of-arrays state (replaces the NumPy views the
+ * reference env code reads).  Field f of env e, slot k is at
+ *   base + ((e * n_fields + f) * stride + k) * elem_size.
+ * Nodes use slots 0..n_elem, elements 0..n_elem-1, Voronoi points 0..n_elem-2. */
+typedef struct sr_state_view {
+  void *base;
+  int32_t n_env, n_fields, stride, elem_size;
+  /* first field index of each quantity (component-major, reference order) */
+  int32_t f_position;  /* 3 fields: x,y,z              (position_collection) */
+  int32_t f_velocity;  /* 3                            (velocity_collection) */
+  int32_t f_director;  /* 9: Q[i][j] at f_director+3i+j (director_collection) */
+  int32_t f_omega;     /* 3                            (omega_collection)    */
+  int32_t f_tangents;  /* 3  stale, last force evaluation       */
+  int32_t f_kappa;     /* 3  stale                                           */
+  int32_t f_sigma;     /* 3  stale                                           */
+  int32_t f_dilatation;/* 1  stale                                           */
+} sr_state_view;
+
+typedef struct sr_handle sr_handle;
+
+int sr_abi_version(void);
+const char *sr_last_error(void);
+
+/* Allocate device state for cfg->n_env rods and precompute rod constants. */
+int sr_create(const sr_config *cfg, sr_handle **out);
+void sr_destroy(sr_handle *h);
+
+/* per-env sizes for the chosen model */
+int sr_obs_dim(const sr_handle *h);
+int sr_action_dim(const sr_handle *h);
+int sr_init_dim(const sr_handle *h); /* doubles per env expected by sr_reset: 9 = start, direction, normal */
+
+/* (Re)build rods: replaces Env.reset -> build_* -> simulator.finalize().
+ * env_idx: int32 device array of n env indices, or NULL for envs 0..n-1.
+ * init: double device array [n][9] = start(3), direction(3), normal(3). */
+int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init_dev, void *stream);
+
+/* Advance every env by n_substeps PositionVerlet substeps in ONE kernel launch
+ * and evaluate the model's observation / reward / NaN guard
+ * (replaces the loop at soft_pendulum.py:183-184 and lines 196-214,149-161).
+ *   action_dev      float  [n_env][action_dim]   (may be NULL if action_dim == 0)
+ *   obs_dev         float  [n_env][obs_dim]
+ *   reward_dev      double [n_env]
+ *   terminated_dev  uint8  [n_env]   1 = NaN in position/velocity */
+int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_dev,
+            double *reward_dev, uint8_t *terminated_dev, void *stream);
+
+/* Same with HOST buffers: H2D of actions, launch, D2H of results, synchronised. */
+int sr_reset_host(sr_handle *h, const int32_t *env_idx_host, int n, const double *init_host);
+int sr_step_host(sr_handle *h, const float *action_host, int n_substeps, float *obs_host,
+                 double *reward_host, uint8_t *terminated_host);
+/* current observation without stepping (reset obs) */
+int sr_observe(sr_handle *h, const float *prev_action_dev, float *obs_dev, void *stream);
+
+int sr_get_state(sr_handle *h, sr_state_view *out);
+/* copy a full state (same layout, device memory) into the handle */
+int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
+
+/* number of kernels this library launched on behalf of the handle so far */
+int64_t sr_launch_count(const sr_handle *h);
+
+/* Measure the device's FP64 FMA issue peak with a register-resident DFMA chain
+ * (roofline denominator; not in MEASURED_PEAKS.json).  Returns TFLOP/s. */
+int sr_measure_fp64_peak(int device, double *tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTROD_H */

@@ -1,0 +1,131 @@
+"""TEST INFRASTRUCTURE (oracle) — generates tests/golden/*.npz.
+
+Runs the UNMODIFIED reference env classes (`/root/reference/gym_softrobot/...`)
+on top of the oracle's PyElastica/gymnasium shims (oracle/shims) and records
+golden input/output vectors.  The gym-softrobot layer (env logic, plugins,
+seeding, reward, truncation) is therefore the reference's own code; the
+PyElastica layer underneath is the NumPy restatement (pyelastica==1.0.0 is not
+installable here) — fixtures are labelled  parity="unpinned (restated PyElastica)".
+
+Run only in the build container (needs /root/reference):
+    python oracle/gen_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, _HERE)
+import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(_HERE), "tests", "golden")
+LABEL = "unpinned (reference gym-softrobot code on restated PyElastica, oracle/shims)"
+
+
+def rod_state(rod):
+    return dict(
+        position=rod.position_collection.copy(),
+        velocity=rod.velocity_collection.copy(),
+        director=rod.director_collection.copy(),
+        omega=rod.omega_collection.copy(),
+        tangents=rod.tangents.copy(),
+        kappa=rod.kappa.copy(),
+        sigma=rod.sigma.copy(),
+        dilatation=rod.dilatation.copy(),
+    )
+
+
+def pack(prefix, d, out):
+    for k, v in d.items():
+        out[f"{prefix}/{k}"] = v
+
+
+def gen_soft_pendulum_episode(seed=42, n_state_steps=4):
+    """Config 1 of BASELINE.json: SoftPendulum-v0, seed 42, random actions, full episode."""
+    env = ref_loader.load_reference_env("SoftPendulum-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    rod = env.unwrapped.shearable_rod
+    out = {"label": LABEL, "seed": seed, "obs0": obs0}
+    pack("state0", rod_state(rod), out)
+    actions, obs, rew, term, trunc, times = [], [], [], [], [], []
+    step = 0
+    while True:
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        actions.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr)
+        times.append(info["time"])
+        step += 1
+        if step <= n_state_steps:
+            pack(f"state{step}", rod_state(rod), out)
+        if te or tr:
+            break
+    pack("state_final", rod_state(rod), out)
+    out.update(actions=np.array(actions, dtype=np.float32), obs=np.array(obs, dtype=np.float32),
+               reward=np.array(rew, dtype=np.float64), terminated=np.array(term), truncated=np.array(trunc),
+               time=np.array(times, dtype=np.float64), n_steps=step)
+    np.savez_compressed(os.path.join(OUT, f"soft_pendulum_seed{seed}_episode.npz"), **out)
+    print("soft_pendulum episode:", step, "steps; last obs", obs[-1], "reward", rew[-1])
+
+
+def gen_soft_pendulum_substeps(seed=42):
+    """State after 1, 10, 100, 400, 1000 raw PositionVerlet substeps (constant action 7.5)."""
+    env = ref_loader.load_reference_env("SoftPendulum-v0")
+    env.reset(seed=seed)
+    e = env.unwrapped
+    rod = e.shearable_rod
+    e.set_action(np.array([7.5], dtype=np.float32))
+    out = {"label": LABEL, "seed": seed, "action": 7.5}
+    done = 0
+    for target in (1, 10, 100, 400, 1000):
+        for _ in range(target - done):
+            e.time = e.do_step(e.simulator, e.time, e.time_step)
+        done = target
+        pack(f"sub{target}", rod_state(rod), out)
+        out[f"sub{target}/time"] = e.time
+    np.savez_compressed(os.path.join(OUT, f"soft_pendulum_seed{seed}_substeps.npz"), **out)
+    print("soft_pendulum substeps: x_tip", rod.position_collection[:, -1])
+
+
+def gen_determinism(env_id, seed=0, n=3):
+    """The reference's own determinism protocol (tests/envs/test_determinism.py:7-58)."""
+    env = ref_loader.load_reference_env(env_id)
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    acts = [env.action_space.sample() for _ in range(n)]
+    resp = [env.step(a) for a in acts]
+    out = {"label": LABEL, "seed": seed, "obs0": obs0, "actions": np.array(acts),
+           "obs": np.array([r[0] for r in resp]), "reward": np.array([r[1] for r in resp], dtype=np.float64),
+           "terminated": np.array([r[2] for r in resp]), "truncated": np.array([r[3] for r in resp])}
+    pack("state_final", rod_state(env.unwrapped.shearable_rod), out)
+    np.savez_compressed(os.path.join(OUT, f"{env_id.replace('-', '_').lower()}_determinism_seed{seed}.npz"), **out)
+    print(env_id, "determinism: obs", resp[-1][0], "reward", resp[-1][1])
+
+
+def gen_soft_pendulum_3d(seed=42, n=6):
+    env = ref_loader.load_reference_env("SoftPendulum3D-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    rod = env.unwrapped.shearable_rod
+    out = {"label": LABEL, "seed": seed, "obs0": obs0}
+    pack("state0", rod_state(rod), out)
+    acts, obs, rew, term, trunc, tilt = [], [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr); tilt.append(info["tilt"])
+        pack(f"state{i + 1}", rod_state(rod), out)
+    out.update(actions=np.array(acts, dtype=np.float32), obs=np.array(obs, dtype=np.float32),
+               reward=np.array(rew), terminated=np.array(term), truncated=np.array(trunc), tilt=np.array(tilt))
+    np.savez_compressed(os.path.join(OUT, f"soft_pendulum_3d_seed{seed}.npz"), **out)
+    print("soft_pendulum_3d:", obs[-1], rew[-1])
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    gen_soft_pendulum_substeps()
+    gen_determinism("SoftPendulum-v0")
+    gen_determinism("SoftPendulum3D-v0")
+    gen_soft_pendulum_3d()
+    gen_soft_pendulum_episode()

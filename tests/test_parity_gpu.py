@@ -1,0 +1,212 @@
+"""GPU parity: CUDA path (through the C-ABI) vs golden fixtures and the C oracle.
+
+Tolerances (BASELINE.json north_star): FP64 state to rel 1e-9 over 1000 substeps,
+where "rel" is max|a-b| / max|b| per field; termination/truncation bit-exact;
+observations are float32 casts of FP64 values (compared to 2 float32 ulp); rewards
+are FP64 functions of the state (compared to 1e-9 — they cannot be bit-exact
+unless the state is).
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9
+FIELDS = {"position": "position_collection", "velocity": "velocity_collection",
+          "director": "director_collection", "omega": "omega_collection",
+          "tangents": "tangents", "kappa": "kappa", "sigma": "sigma", "dilatation": "dilatation"}
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def _native():
+    from gym_softrobot_b200 import _native as nat
+    return nat
+
+
+def make_pendulum_handle(n_env, math, n_elem=50, dt=1e-4):
+    from gym_softrobot_b200.envs.soft_pendulum import _make_handle
+    return _make_handle(n_env, n_elem, dt, 0, math)
+
+
+def u01_for_seed(seed):
+    return np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed))).random()
+
+
+@pytest.mark.parametrize("math", [0, 1], ids=["fast", "faithful"])
+def test_golden_substeps(golden_dir, math):
+    """State after 1/10/100/400/1000 raw substeps vs the reference-env-on-shim fixture."""
+    import torch
+    from gym_softrobot_b200.envs.soft_pendulum import pendulum_init_params
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_substeps.npz"))
+    h = make_pendulum_handle(1, math)
+    h.reset_host(pendulum_init_params(u01_for_seed(42)))
+    act = np.array([[g["action"]]], dtype=np.float32)
+    done = 0
+    for target in (1, 10, 100, 400, 1000):
+        h.step_host(act, target - done)
+        done = target
+        torch.cuda.synchronize()
+        f = {k: v[0].cpu().numpy() for k, v in h.fields().items()}
+        for gk, fk in FIELDS.items():
+            err = rel(f[fk], g[f"sub{target}/{gk}"])
+            # kappa/sigma are ~0 quantities at early times: compare on an absolute floor too
+            ok = err < TOL or np.abs(f[fk] - g[f"sub{target}/{gk}"]).max() < 1e-12
+            assert ok, f"math={math} substeps={target} field={gk} rel err {err:.3e}"
+    h.close()
+
+
+@pytest.mark.parametrize("math", [0, 1], ids=["fast", "faithful"])
+def test_golden_episode_single_env(golden_dir, math):
+    """Config 1 of BASELINE.json: seed 42, the recorded random actions, through the Gymnasium façade."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_episode.npz"))
+    env = gsb.make("SoftPendulum-v0", math=math)
+    obs0, info = env.reset(seed=42)
+    assert obs0.dtype == np.float32 and np.array_equal(obs0, g["obs0"])
+    n_check = 30  # 12000 substeps; the full 126-step episode is checked for flags/time only below
+    for i in range(n_check):
+        obs, r, te, tr, info = env.step(g["actions"][i])
+        assert te == bool(g["terminated"][i]) and tr == bool(g["truncated"][i])
+        assert info["time"] == g["time"][i]  # float64 time accumulation is bit-exact
+        assert isinstance(te, bool) and isinstance(tr, bool) and np.isscalar(r)
+        if i < 3:  # 1200 substeps: the 1e-9 window of the north star
+            st = env.rod_state()
+            for gk, fk in FIELDS.items():
+                if gk in ("kappa", "sigma"):
+                    continue
+                err = rel(st[fk], g[f"state{i + 1}/{gk}"])
+                assert err < TOL, f"step {i} field {gk} rel err {err:.3e}"
+            assert abs(r - g["reward"][i]) <= TOL * max(1.0, abs(g["reward"][i]))
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=2e-6, atol=1e-7)
+        assert abs(r - g["reward"][i]) <= 1e-6 * max(1.0, abs(g["reward"][i]))
+    env.close()
+
+
+def test_golden_episode_flags_full(golden_dir):
+    """Whole 126-step episode: termination/truncation sequence and info['time'] bit-exact."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_episode.npz"))
+    env = gsb.make("SoftPendulum-v0")
+    env.reset(seed=42)
+    n = int(g["n_steps"])
+    for i in range(n):
+        obs, r, te, tr, info = env.step(g["actions"][i])
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i])), i
+        assert info["time"] == g["time"][i]
+    assert tr and not te
+    # long-horizon drift stays small even after 50400 substeps
+    np.testing.assert_allclose(obs, g["obs"][n - 1], rtol=1e-4, atol=1e-5)
+    env.close()
+
+
+def test_reference_determinism_protocol(golden_dir):
+    """The reference's own test (tests/envs/test_determinism.py:7-58): two envs, seed 0, 3 steps, exact equality."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "softpendulum_v0_determinism_seed0.npz"))
+    runs = []
+    for _ in range(2):
+        env = gsb.make("SoftPendulum-v0")
+        o0, _ = env.reset(seed=0)
+        env.action_space.seed(0)
+        acts = [env.action_space.sample() for _ in range(3)]
+        resp = [env.step(a) for a in acts]
+        env.close()
+        runs.append((o0, acts, resp))
+    (o1, a1, r1), (o2, a2, r2) = runs
+    assert np.array_equal(o1, o2) and np.array_equal(o1, g["obs0"])
+    for x, y, ga in zip(a1, a2, g["actions"]):
+        assert np.array_equal(x, y) and np.array_equal(x, ga)
+    for (ob1, rw1, t1, x1, _), (ob2, rw2, t2, x2, _), gob, grw in zip(r1, r2, g["obs"], g["reward"]):
+        np.testing.assert_array_equal(ob1, ob2)
+        assert rw1 == rw2 and t1 == t2 and x1 == x2
+        np.testing.assert_allclose(ob1, gob, rtol=2e-6, atol=1e-7)
+        assert abs(rw1 - grw) < 1e-9
+
+
+@pytest.mark.parametrize("n_env", [1, 5, 128, 4096])
+def test_batched_vs_oracle(n_env):
+    """Batched kernel vs the C oracle on seeded per-env initial angles and actions (1200 substeps)."""
+    import torch
+    import rod_oracle
+    import gym_softrobot_b200 as gsb
+    env = gsb.make_vec("SoftPendulum-v0", n_env, autoreset=False)
+    obs, _ = env.reset(seed=42)
+    check = sorted(set([0, n_env - 1] + list(np.random.default_rng(1).integers(0, n_env, size=6))))
+    oracles = {i: rod_oracle.OracleSoftPendulum() for i in check}
+    for i, o in oracles.items():
+        o_obs, _ = o.reset(seed=42 + i)
+        assert np.array_equal(obs[i].cpu().numpy(), o_obs)
+    gen = torch.Generator(device="cuda").manual_seed(42)
+    for step in range(3):
+        a = (torch.rand((n_env, 1), generator=gen, device="cuda") * 44 - 22).float()
+        obs, rew, term, trunc, info = env.step(a)
+        f = {k: v.cpu().numpy() for k, v in env.fields().items()}
+        a_np = a.cpu().numpy()
+        for i, o in oracles.items():
+            ob, r, te, tr, oi = o.step(a_np[i])
+            for name in ("position_collection", "velocity_collection", "director_collection",
+                         "omega_collection", "tangents"):
+                err = rel(f[name][i], getattr(o.rod, name))
+                assert err < TOL, f"n_env={n_env} env={i} step={step} {name}: {err:.3e}"
+            assert bool(term[i]) == te and bool(trunc[i]) == tr
+            assert abs(float(rew[i]) - r) <= TOL * max(1.0, abs(r))
+            np.testing.assert_allclose(obs[i].cpu().numpy(), ob, rtol=2e-6, atol=1e-7)
+            assert float(info["time"][i]) == oi["time"]
+    env.close()
+
+
+def test_full_size_properties():
+    """BASELINE config 2 (4096 envs, n=50): size-independent properties.
+
+    (a) run-to-run determinism is bit-exact; (b) envs with identical seeds and actions
+    produce bit-identical states wherever they sit in the batch; (c) state stays finite.
+    """
+    import torch
+    from gym_softrobot_b200.envs.soft_pendulum import pendulum_init_params
+    n_env = 4096
+    u = np.random.default_rng(7).random(64)
+    u_all = np.tile(u, n_env // 64)
+    act = torch.as_tensor(np.tile(np.random.default_rng(8).uniform(-22, 22, 64), n_env // 64)
+                          .astype(np.float32).reshape(n_env, 1), device="cuda")
+    outs = []
+    for _ in range(2):
+        h = make_pendulum_handle(n_env, 0)
+        h.reset(torch.as_tensor(pendulum_init_params(u_all), device="cuda").contiguous())
+        obs = torch.empty((n_env, 4), dtype=torch.float32, device="cuda")
+        rew = torch.empty(n_env, dtype=torch.float64, device="cuda")
+        term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+        for _s in range(2):
+            h.step(act, 400, obs, rew, term)
+        torch.cuda.synchronize()
+        outs.append((h.state_tensor().clone(), obs.clone(), rew.clone(), term.clone()))
+        h.close()
+    (s1, o1, r1, t1), (s2, o2, r2, t2) = outs
+    assert torch.equal(s1, s2) and torch.equal(o1, o2) and torch.equal(r1, r2)
+    assert int(t1.sum()) == 0 and bool(torch.isfinite(s1).all())
+    s = s1.reshape(n_env // 64, 64, *s1.shape[1:])
+    assert torch.equal(s[0].expand_as(s), s), "identical envs diverged across the batch"
+
+
+def test_free_fall_and_nan_guard():
+    """PositionVerlet is exact for constant acceleration (free rod, no damping); NaN -> terminated."""
+    import torch
+    nat = _native()
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=3, n_elem=20, dt=1e-4, base_length=1.0, base_radius=0.05,
+                   density=1000.0, youngs_modulus=1e6, gravity=(0.0, -9.80665, 0.0))
+    init = np.zeros((3, 9)); init[:, 3] = 1.0; init[:, 7] = 1.0
+    h.reset_host(init)
+    y0 = h.fields()["position_collection"][:, 1].clone()
+    obs, rew, term = h.step_host(None, 1000)
+    t = 0.1
+    y = h.fields()["position_collection"][:, 1]
+    assert float((y - y0 - 0.5 * -9.80665 * t * t).abs().max()) < 1e-13
+    assert term.sum() == 0
+    h.fields()["velocity_collection"][1, 0, 3] = float("nan")
+    obs, rew, term = h.step_host(None, 2)
+    assert list(term) == [0, 1, 0]
+    h.close()
