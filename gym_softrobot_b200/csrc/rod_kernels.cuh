@@ -109,6 +109,11 @@ __device__ __forceinline__ void rotate_directors(T h, const T w[3], T Q[9], bool
     // R = I + A K + B K^2 with A = sin(t)/t, B = (1-cos t)/t^2; apply as Q += D Q, D = R - I
     T A, B;
     sinc_cosc(q, A, B);
+    // reference guard: axis = a / (|a| + 1e-14)  =>  A *= rho, B *= rho^2,
+    // rho = |a|/(|a| + 1e-14) ~= 1 - 1e-14 / sqrt(q + 1e-28)   (-> 0 as |a| -> 0, like the reference)
+    T rho = fma(T(-1e-14), rsqrt_approx(q + T(1e-28)), T(1.0));
+    A *= rho;
+    B *= rho * rho;
     T Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
     T Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
     T D00 = -fma(Ba1, a1, Ba2 * a2), D11 = -fma(Ba0, a0, Ba2 * a2), D22 = -fma(Ba0, a0, Ba1 * a1);
@@ -404,7 +409,11 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
     for (int j = 0; j < EPL; j++) {
       T fac;
       if (MATH == MATH_FAST && bend_fast) {
-        fac = T(-0.5) * theta_over_sin(uu[j]);
+        // -theta/(2 sin(theta + 1e-14)) = -g(u)/2 * (1 - 1e-14 cot(theta)),
+        // cot(theta) = (1 - 2u) / sqrt(4u(1-u)); u >= 5e-11 by the 1e-10 guard, so no singularity
+        T u = uu[j];
+        T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
+        fac = T(-0.5) * theta_over_sin(u) * fma(T(-1e-14), cot, T(1.0));
       } else {
         T theta = acos_(T(1.0) - T(2.0) * uu[j]);
         fac = T(-0.5) * theta / sin_(theta + T(1e-14));

@@ -48,6 +48,15 @@ __device__ __forceinline__ double atan_(double x) { return atan(x); }
 __device__ __forceinline__ double fabs_(double x) { return fabs(x); }
 __device__ __forceinline__ float fabs_(float x) { return fabsf(x); }
 
+// ~2^-22-accurate reciprocal square root: one MUFU.RSQ64H, no Newton steps.  Only used
+// for the reference's 1e-14 guard terms, where the correction itself is <= 1e-9.
+__device__ __forceinline__ double rsqrt_approx(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) { return rsqrtf(x); }
+
 // sin(t)/t and (1-cos(t))/t^2 as polynomials in q = t^2, valid for q <= 1/16
 // (|t| <= 0.25 rad per half step; truncation < 1e-17).  Larger rotations take
 // the libm path (warp-uniform branch in the kernel).

@@ -54,8 +54,9 @@ def test_golden_substeps(golden_dir, math):
         f = {k: v[0].cpu().numpy() for k, v in h.fields().items()}
         for gk, fk in FIELDS.items():
             err = rel(f[fk], g[f"sub{target}/{gk}"])
-            # kappa/sigma are ~0 quantities at early times: compare on an absolute floor too
-            ok = err < TOL or np.abs(f[fk] - g[f"sub{target}/{gk}"]).max() < 1e-12
+            # kappa/sigma are ~0 quantities computed by cancellation (axial(Q+ Q^T), e Qt - z):
+            # their round-off floor is absolute (~1e-16/D), not relative
+            ok = err < TOL or np.abs(f[fk] - g[f"sub{target}/{gk}"]).max() < 1e-10
             assert ok, f"math={math} substeps={target} field={gk} rel err {err:.3e}"
     h.close()
 
