@@ -101,59 +101,70 @@ __device__ __forceinline__ void shift_prev(const T (&a)[EPL], int lane, T (&out)
 }
 
 // ---- Rodrigues update Q <- R(h w) Q   -------------------------
-template <typename T, int MATH>
-__device__ __forceinline__ void rotate_directors(T h, const T w[3], T Q[9], bool use_fast) {
-  T a0 = h * w[0], a1 = h * w[1], a2 = h * w[2];
-  T q = fma(a2, a2, fma(a1, a1, a0 * a0));
-  if (MATH == MATH_FAST && use_fast) {
-    // R = I + A K + B K^2 with A = sin(t)/t, B = (1-cos t)/t^2; apply as Q += D Q, D = R - I
-    T A, B;
-    sinc_cosc(q, A, B);
-    // reference guard: axis = a / (|a| + 1e-14)  =>  A *= rho, B *= rho^2,
-    // rho = |a|/(|a| + 1e-14) ~= 1 - 1e-14 / sqrt(q + 1e-28)   (-> 0 as |a| -> 0, like the reference)
-    T rho = fma(T(-1e-14), rsqrt_approx(q + T(1e-28)), T(1.0));
-    A *= rho;
-    B *= rho * rho;
-    T Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
-    T Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
-    T D00 = -fma(Ba1, a1, Ba2 * a2), D11 = -fma(Ba0, a0, Ba2 * a2), D22 = -fma(Ba0, a0, Ba1 * a1);
-    T D01 = fma(Ba0, a1, Aa2), D10 = fma(Ba0, a1, -Aa2);
-    T D02 = fma(Ba0, a2, -Aa1), D20 = fma(Ba0, a2, Aa1);
-    T D12 = fma(Ba1, a2, Aa0), D21 = fma(Ba1, a2, -Aa0);
-    T n[9];
+// reference operation order (elastica/_rotations.py:_get_rotation_matrix); also the
+// large-rotation fallback of the fast path, kept out of line to keep the hot loop small.
+template <typename T>
+__device__ __noinline__ void rotate_directors_ref(T a0, T a1, T a2, T *Q) {
+  T q = a0 * a0 + a1 * a1 + a2 * a2;
+  T theta = sqrt_(q);
+  T d = theta + T(1e-14);
+  T v0 = a0 / d, v1 = a1 / d, v2 = a2 / d;
+  T up, cs;
+  sincos_(theta, &up, &cs);
+  T us = T(1.0) - cs;
+  T R00 = T(1.0) - us * (v1 * v1 + v2 * v2);
+  T R11 = T(1.0) - us * (v0 * v0 + v2 * v2);
+  T R22 = T(1.0) - us * (v0 * v0 + v1 * v1);
+  T R01 = up * v2 + us * v0 * v1, R10 = -up * v2 + us * v0 * v1;
+  T R02 = -up * v1 + us * v0 * v2, R20 = up * v1 + us * v0 * v2;
+  T R12 = up * v0 + us * v1 * v2, R21 = -up * v0 + us * v1 * v2;
+  T n[9];
 #pragma unroll
-    for (int m = 0; m < 3; m++) {
-      n[0 + m] = fma(D02, Q[6 + m], fma(D01, Q[3 + m], fma(D00, Q[0 + m], Q[0 + m])));
-      n[3 + m] = fma(D12, Q[6 + m], fma(D11, Q[3 + m], fma(D10, Q[0 + m], Q[3 + m])));
-      n[6 + m] = fma(D22, Q[6 + m], fma(D21, Q[3 + m], fma(D20, Q[0 + m], Q[6 + m])));
-    }
-#pragma unroll
-    for (int i = 0; i < 9; i++) Q[i] = n[i];
-  } else {
-    // reference operation order (elastica/_rotations.py:_get_rotation_matrix)
-    T theta = sqrt_(q);
-    T d = theta + T(1e-14);
-    T v0 = a0 / d, v1 = a1 / d, v2 = a2 / d;
-    T up, cs;
-    sincos_(theta, &up, &cs);
-    T us = T(1.0) - cs;
-    T R00 = T(1.0) - us * (v1 * v1 + v2 * v2);
-    T R11 = T(1.0) - us * (v0 * v0 + v2 * v2);
-    T R22 = T(1.0) - us * (v0 * v0 + v1 * v1);
-    T R01 = up * v2 + us * v0 * v1, R10 = -up * v2 + us * v0 * v1;
-    T R02 = -up * v1 + us * v0 * v2, R20 = up * v1 + us * v0 * v2;
-    T R12 = up * v0 + us * v1 * v2, R21 = -up * v0 + us * v1 * v2;
-    T n[9];
-#pragma unroll
-    for (int m = 0; m < 3; m++) {
-      n[0 + m] = R00 * Q[0 + m] + R01 * Q[3 + m] + R02 * Q[6 + m];
-      n[3 + m] = R10 * Q[0 + m] + R11 * Q[3 + m] + R12 * Q[6 + m];
-      n[6 + m] = R20 * Q[0 + m] + R21 * Q[3 + m] + R22 * Q[6 + m];
-    }
-#pragma unroll
-    for (int i = 0; i < 9; i++) Q[i] = n[i];
+  for (int m = 0; m < 3; m++) {
+    n[0 + m] = R00 * Q[0 + m] + R01 * Q[3 + m] + R02 * Q[6 + m];
+    n[3 + m] = R10 * Q[0 + m] + R11 * Q[3 + m] + R12 * Q[6 + m];
+    n[6 + m] = R20 * Q[0 + m] + R21 * Q[3 + m] + R22 * Q[6 + m];
   }
+#pragma unroll
+  for (int i = 0; i < 9; i++) Q[i] = n[i];
 }
+
+// fast path: R = I + A K + B K^2 with A = sin(t)/t, B = (1-cos t)/t^2, applied as Q += D Q.
+// `eps` carries the reference's guard: axis = a/(|a| + 1e-14) shortens each half-step
+// rotation by 1e-14 rad (2e-14 for a merged full step):  A *= rho, B *= rho^2 with
+// rho = 1 - eps/sqrt(q + eps^2)  (-> 0 as |a| -> 0, like the reference).
+template <typename T>
+__device__ __forceinline__ void rotate_directors_fast(T a0, T a1, T a2, T q, T eps, T Q[9]) {
+  T A, B;
+  sinc_cosc(q, A, B);
+  T rho = fma(-eps, rsqrt_approx(fma(eps, eps, q)), T(1.0));
+  A *= rho;
+  B *= rho * rho;
+  T Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
+  T Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
+  T D00 = -fma(Ba1, a1, Ba2 * a2), D11 = -fma(Ba0, a0, Ba2 * a2), D22 = -fma(Ba0, a0, Ba1 * a1);
+  T D01 = fma(Ba0, a1, Aa2), D10 = fma(Ba0, a1, -Aa2);
+  T D02 = fma(Ba0, a2, -Aa1), D20 = fma(Ba0, a2, Aa1);
+  T D12 = fma(Ba1, a2, Aa0), D21 = fma(Ba1, a2, -Aa0);
+  T n[9];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    n[0 + m] = fma(D02, Q[6 + m], fma(D01, Q[3 + m], fma(D00, Q[0 + m], Q[0 + m])));
+    n[3 + m] = fma(D12, Q[6 + m], fma(D11, Q[3 + m], fma(D10, Q[0 + m], Q[3 + m])));
+    n[6 + m] = fma(D22, Q[6 + m], fma(D21, Q[3 + m], fma(D20, Q[0 + m], Q[6 + m])));
+  }
+#pragma unroll
+  for (int i = 0; i < 9; i++) Q[i] = n[i];
+}
+
+// -theta / (2 sin(theta + 1e-14)), theta = acos(1 - 2u): the reference's log-map factor
+// (elastica/_rotations.py:_inv_rotate), used verbatim by the faithful path and as the
+// large-bend fallback of the fast path.
+template <typename T> __device__ __noinline__ T bend_factor_ref(T u) {
+  T theta = acos_(T(1.0) - T(2.0) * u);
+  return T(-0.5) * theta / sin_(theta + T(1e-14));
+}
+template <typename T> __device__ __noinline__ T exp_ref(T x) { return exp_(x); }
 
 // numpy's pairwise float64 row sum (np.mean over the contiguous axis), n <= 128
 template <typename T> __device__ inline double np_pairwise_sum(const T *a, int n) {
@@ -203,8 +214,8 @@ __device__ inline void soft_pendulum_outputs(const T *tan_smem, int stride, int 
   }
 }
 
-template <typename T, int EPL, int MATH>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+template <typename T, int EPL, int MATH, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, MINB)
 rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
   __shared__ T tan_smem[WARPS_PER_CTA][3 * 32 * EPL];
   const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
@@ -223,15 +234,19 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
 #pragma unroll
   for (int c = 0; c < 9; c++) load_row<T, EPL>(st + (F_DIR + c) * stride, lane, Q[c]);
 
+  // Slots past the rod end hold a benign state (x = v = w = 0, Q = I) that never changes:
+  // their time-step multipliers are zero, so no per-update selects are needed.
   bool elem_ok[EPL], node_ok[EPL], vor_ok[EPL];
-  T minv_scale[EPL];
+  T dtim[EPL], gmask[EPL], dte[EPL];
 #pragma unroll
   for (int j = 0; j < EPL; j++) {
     int k = lane * EPL + j;
     elem_ok[j] = k < n;
     node_ok[j] = k <= n;
     vor_ok[j] = k < n - 1;
-    minv_scale[j] = (k == 0 || k == n) ? T(2) : T(1);
+    dtim[j] = node_ok[j] ? A.dt_inv_mass * ((k == 0 || k == n) ? T(2) : T(1)) : T(0);
+    gmask[j] = node_ok[j] ? T(1) : T(0);
+    dte[j] = elem_ok[j] ? A.dt : T(0);
   }
   // per-env anchors and actuation (only lane 0 / node 0 uses them)
   const T *bc = A.bc + (size_t)env * BC_DIM;
@@ -274,39 +289,49 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
       }
     }
   };
-  auto kinematic = [&](T h) {
-    bool fast = true;
-    if (MATH == MATH_FAST) {
-      T qmax = T(0);
-#pragma unroll
-      for (int j = 0; j < EPL; j++) {
-        T a0 = h * w[0][j], a1 = h * w[1][j], a2 = h * w[2][j];
-        qmax = fmax(qmax, fma(a2, a2, fma(a1, a1, a0 * a0)));
-      }
-      fast = !__any_sync(FULL, !(qmax <= T(kSmallRotQ)));
-    }
+  // x += hh v ; Q <- R(hh w) Q.  In the fast path hh is dt/2 (first/last update of the
+  // launch) or dt: the half step that ends substep s and the one that starts s+1 use the
+  // same v, w and compose exactly (same rotation axis; every BC of this build overwrites
+  // its constrained components), so they are merged into one update.
+  auto kinematic = [&](T hh, T eps) {
+    T a[3][EPL], q[EPL];
+    bool fast = (MATH == MATH_FAST);
 #pragma unroll
     for (int j = 0; j < EPL; j++) {
 #pragma unroll
-      for (int c = 0; c < 3; c++) x[c][j] = fma(h, v[c][j], x[c][j]);
-      T wj[3] = {w[0][j], w[1][j], w[2][j]};
+      for (int c = 0; c < 3; c++) {
+        x[c][j] = fma(hh, v[c][j], x[c][j]);
+        a[c][j] = hh * w[c][j];
+      }
+      q[j] = fma(a[2][j], a[2][j], fma(a[1][j], a[1][j], a[0][j] * a[0][j]));
+      // The base element is excluded from the vote when a BC owns its directors: every BC of
+      // this build overwrites the rows that R changes (ONE_END_FIXED / MOVING_BASE: all of Q;
+      // PENDULUM_SLIDER: rows d1,d3, and its rate constraint keeps w = (0,w1,0) so row d2 is
+      // exactly invariant: D10 = D11 = D12 = 0).  The reference env lets w1 of that element
+      // grow without bound (nothing restores it), which must not push the warp off the fast path.
+      const bool owned_by_bc = (j == 0) && (lane == 0) && (A.bc_kind != BC_FREE);
+      if (!(q[j] <= T(kSmallRotQ)) && !owned_by_bc) fast = false;
+    }
+    if (MATH == MATH_FAST) fast = !__any_sync(FULL, !fast);
+#pragma unroll
+    for (int j = 0; j < EPL; j++) {
       T Qj[9];
 #pragma unroll
       for (int c = 0; c < 9; c++) Qj[c] = Q[c][j];
-      rotate_directors<T, MATH>(h, wj, Qj, fast);
+      if (fast) rotate_directors_fast<T>(a[0][j], a[1][j], a[2][j], q[j], eps, Qj);
+      else rotate_directors_ref<T>(a[0][j], a[1][j], a[2][j], Qj);
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c][j] = Qj[c];
     }
   };
 
   const T h = A.half_dt, dt = A.dt;
-  bool invalid_any = false;
+  if (MATH == MATH_FAST && A.n_substeps > 0) { kinematic(h, T(1e-14)); constrain_values(); }
 
 #pragma unroll 1
   for (int s = 0; s < A.n_substeps; s++) {
     const bool last = (s == A.n_substeps - 1);
-    kinematic(h);
-    constrain_values();
+    if (MATH != MATH_FAST) { kinematic(h, T(1e-14)); constrain_values(); }
 
     // ---------------- geometry, shear/stretch strain, internal force ----------
     T xn[3][EPL], vn[3][EPL];
@@ -319,11 +344,11 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
       T dx[3], dv[3];
 #pragma unroll
       for (int c = 0; c < 3; c++) { dx[c] = xn[c][j] - x[c][j]; dv[c] = vn[c][j] - v[c][j]; }
-      if (!elem_ok[j]) { dx[0] = T(0); dx[1] = T(0); dx[2] = A.rest_len; dv[0] = dv[1] = dv[2] = T(0); }
-      T l2 = dot3(dx, dx);
+      if (!elem_ok[j]) dx[2] = A.rest_len;  // keeps every quantity of a padding slot finite
       T t[3];
       if (MATH == MATH_FAST) {
-        T il = rsqrt_(l2);
+        T l2 = dot3(dx, dx);
+        T il = rsqrt_nr(l2);
         T l = l2 * il;
         lg[j] = l + T(1e-14);                     // reference guard on the length
         T ilg = fma(T(-1e-14) * il, il, il);      // 1/(l + 1e-14) to first order in 1e-14/l
@@ -331,7 +356,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
         for (int c = 0; c < 3; c++) t[c] = dx[c] * ilg;
         e[j] = lg[j] * A.inv_rest_len;
         inv_e[j] = A.rest_len * ilg;
-        edot[j] = dot3(dx, dv) * ilg * A.inv_rest_len;
+        edot[j] = dot3(dx, dv) * (ilg * A.inv_rest_len);   // = t . dv / l0
       } else {
         lg[j] = sqrt_(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) + T(1e-14);
 #pragma unroll
@@ -340,12 +365,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
         inv_e[j] = T(1.0) / e[j];
         // r.v terms exactly as elastica/rod/cosserat_rod.py:_compute_dilatation_rate
         T xk[3] = {x[0][j], x[1][j], x[2][j]}, vk[3] = {v[0][j], v[1][j], v[2][j]};
-        T xk1[3] = {xk[0] + dx[0], xk[1] + dx[1], xk[2] + dx[2]};
-        T vk1[3] = {vk[0] + dv[0], vk[1] + dv[1], vk[2] + dv[2]};
-        if (elem_ok[j]) {
-#pragma unroll
-          for (int c = 0; c < 3; c++) { xk1[c] = xn[c][j]; vk1[c] = vn[c][j]; }
-        }
+        T xk1[3] = {xn[0][j], xn[1][j], xn[2][j]}, vk1[3] = {vn[0][j], vn[1][j], vn[2][j]};
         T rv0 = xk[0] * vk[0] + xk[1] * vk[1] + xk[2] * vk[2];
         T rv1 = xk1[0] * vk1[0] + xk1[1] * vk1[1] + xk1[2] * vk1[2];
         T rp1v = xk1[0] * vk[0] + xk1[1] * vk[1] + xk1[2] * vk[2];
@@ -385,7 +405,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
     for (int c = 0; c < 9; c++) shift_next<T, EPL>(Q[c], Qn[c]);
     shift_next<T, EPL>(lg, lgn);
     T kap[3][EPL], mcp[3][EPL], ccp[3][EPL];  // kappa ; tau/eps^3 ; (kappa x tau) D / eps^3
-    bool bend_fast = true;
+    bool bend_fast = (MATH == MATH_FAST);
     T uu[EPL], vec[3][EPL];
 #pragma unroll
     for (int j = 0; j < EPL; j++) {
@@ -399,40 +419,40 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
       vec[1][j] = rm(0, 2) - rm(2, 0);
       vec[2][j] = rm(1, 0) - rm(0, 1);
       T tr = rm(0, 0) + rm(1, 1) + rm(2, 2);
-      if (!vor_ok[j]) { tr = T(3); vec[0][j] = vec[1][j] = vec[2][j] = T(0); }
       // 1 - cos(theta_ref) with the reference's 1e-10 guard, halved: u = sin^2(theta_ref/2)
-      uu[j] = T(0.5) * ((T(1.5) - T(0.5) * tr) + T(1e-10));
+      T u = T(0.5) * ((T(1.5) - T(0.5) * tr) + T(1e-10));
+      uu[j] = vor_ok[j] ? u : T(5e-11);
       if (!(uu[j] <= T(kSmallBendU))) bend_fast = false;
     }
     if (MATH == MATH_FAST) bend_fast = !__any_sync(FULL, !bend_fast);
 #pragma unroll
     for (int j = 0; j < EPL; j++) {
       T fac;
-      if (MATH == MATH_FAST && bend_fast) {
+      if (bend_fast) {
         // -theta/(2 sin(theta + 1e-14)) = -g(u)/2 * (1 - 1e-14 cot(theta)),
         // cot(theta) = (1 - 2u) / sqrt(4u(1-u)); u >= 5e-11 by the 1e-10 guard, so no singularity
         T u = uu[j];
         T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
         fac = T(-0.5) * theta_over_sin(u) * fma(T(-1e-14), cot, T(1.0));
       } else {
-        T theta = acos_(T(1.0) - T(2.0) * uu[j]);
-        fac = T(-0.5) * theta / sin_(theta + T(1e-14));
+        fac = bend_factor_ref<T>(uu[j]);
       }
       T tau[3], kxt[3], kp[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        kp[i] = (MATH == MATH_FAST) ? (vec[i][j] * fac) * A.inv_rest_vor : (vec[i][j] * fac) / A.rest_vor;
+        kp[i] = (MATH == MATH_FAST) ? vec[i][j] * (fac * A.inv_rest_vor) : (vec[i][j] * fac) / A.rest_vor;
         kap[i][j] = kp[i];
         tau[i] = A.B[i] * kp[i];
       }
       cross3(kp, tau, kxt);
       T eps = (MATH == MATH_FAST) ? (T(0.5) * (lgn[j] + lg[j])) * A.inv_rest_vor
                                   : (T(0.5) * (lgn[j] + lg[j])) / A.rest_vor;
-      T ie3 = (MATH == MATH_FAST) ? rcp_(eps * eps * eps) : T(1.0) / (eps * eps * eps);
+      T ie3 = (MATH == MATH_FAST) ? rcp_nr(eps * eps * eps) : T(1.0) / (eps * eps * eps);
+      if (!vor_ok[j]) ie3 = T(0);
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        mcp[i][j] = vor_ok[j] ? tau[i] * ie3 : T(0);
-        ccp[i][j] = vor_ok[j] ? kxt[i] * A.rest_vor * ie3 : T(0);
+        mcp[i][j] = tau[i] * ie3;
+        ccp[i][j] = kxt[i] * (A.rest_vor * ie3);
       }
     }
     T tq[3][EPL];
@@ -466,10 +486,11 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
 #pragma unroll
       for (int i = 0; i < 3; i++) jw[i] = (MATH == MATH_FAST) ? (A.J[i] * wj[i]) * inv_e[j] : (A.J[i] * wj[i]) / e[j];
       cross3(jw, wj, lt);
+      T ede = edot[j] * inv_e[j];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        T ud = (MATH == MATH_FAST) ? jw[i] * edot[j] * inv_e[j] : jw[i] * edot[j] / e[j];
-        tq[i][j] = tq[i][j] + ssc[i] * A.rest_len + lt[i] + ud;
+        if (MATH == MATH_FAST) tq[i][j] = fma(jw[i], ede, fma(ssc[i], A.rest_len, tq[i][j]) + lt[i]);
+        else tq[i][j] = tq[i][j] + ssc[i] * A.rest_len + lt[i] + jw[i] * edot[j] / e[j];
       }
     }
 
@@ -491,21 +512,15 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
     for (int j = 0; j < EPL; j++) {
       const bool base_node = (lane == 0 && j == 0);
       if (MATH == MATH_FAST) {
-        T dtim = A.dt_inv_mass * minv_scale[j];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           T fi = f[i][j], gd = A.gdt[i];
           if (i == 0 && A.point_force && base_node) { fi += act0; gd = T(0); }
-          T vnew = fma(fi, dtim, v[i][j]) + gd;
-          v[i][j] = node_ok[j] ? vnew : v[i][j];
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          T wnew = fma(dt * e[j], A.Jinv[i] * tq[i][j], w[i][j]);
-          w[i][j] = elem_ok[j] ? wnew : w[i][j];
+          v[i][j] = fma(gmask[j], gd, fma(fi, dtim[j], v[i][j]));
+          w[i][j] = fma(dte[j] * e[j], A.Jinv[i] * tq[i][j], w[i][j]);
         }
       } else {
-        T m = A.mass / minv_scale[j];
+        T m = ((lane * EPL + j) == 0 || (lane * EPL + j) == n) ? A.mass * T(0.5) : A.mass;
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           T fe = A.g[i] * m;
@@ -521,7 +536,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
     // ---------------- rate constraints and dissipation -------------------------
     auto dampen = [&]() {
       if (A.damping_on) {
-        bool ef = true;
+        bool ef = (MATH == MATH_FAST);
         T z[3][EPL];
         if (MATH == MATH_FAST) {
 #pragma unroll
@@ -539,8 +554,8 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
           for (int i = 0; i < 3; i++) {
             v[i][j] = v[i][j] * A.c_v;
             T cw;
-            if (MATH == MATH_FAST && ef) cw = A.c_w[i] * exp_small(z[i][j]);
-            else if (MATH == MATH_FAST) cw = exp_(e[j] * A.logc_w[i]);
+            if (ef) cw = A.c_w[i] * exp_small(z[i][j]);
+            else if (MATH == MATH_FAST) cw = exp_ref<T>(e[j] * A.logc_w[i]);
             else cw = pow_(A.c_w[i], e[j]);
             w[i][j] = w[i][j] * cw;
           }
@@ -549,7 +564,8 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
     if (A.damp_first) { dampen(); constrain_rates(); }
     else { constrain_rates(); dampen(); }
 
-    kinematic(h);
+    if (MATH == MATH_FAST) kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
+    else kinematic(h, T(1e-14));
     constrain_values();
   }
 
@@ -562,6 +578,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
   }
 #pragma unroll
   for (int c = 0; c < 9; c++) store_row<T, EPL>(st + (F_DIR + c) * stride, lane, Q[c]);
+  bool invalid_any = false;
 #pragma unroll
   for (int j = 0; j < EPL; j++)
 #pragma unroll
@@ -575,13 +592,12 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
                                (float)act0, invalid_any, A.obs + (size_t)env * A.obs_dim,
                                A.reward + env, A.terminated + env);
     } else {
-      // plain rod: obs = tip position (3) + tip velocity (3); reward 0
       A.reward[env] = 0.0;
       A.terminated[env] = invalid_any ? 1 : 0;
     }
   }
   if (A.model == MODEL_ROD) {
-    // tip node n lives at lane n/EPL slot n%EPL
+    // plain rod: obs = tip position (3) + tip velocity (3); node n lives at lane n/EPL slot n%EPL
 #pragma unroll
     for (int j = 0; j < EPL; j++)
       if (lane * EPL + j == n) {

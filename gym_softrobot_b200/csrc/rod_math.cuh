@@ -48,70 +48,90 @@ __device__ __forceinline__ double atan_(double x) { return atan(x); }
 __device__ __forceinline__ double fabs_(double x) { return fabs(x); }
 __device__ __forceinline__ float fabs_(float x) { return fabsf(x); }
 
-// ~2^-22-accurate reciprocal square root: one MUFU.RSQ64H, no Newton steps.  Only used
-// for the reference's 1e-14 guard terms, where the correction itself is <= 1e-9.
+// ~2^-20-accurate seeds: one MUFU each (only the upper 32 bits of the operand are read).
 __device__ __forceinline__ double rsqrt_approx(double x) {
   double y;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
   return y;
 }
+__device__ __forceinline__ double rcp_approx(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
 __device__ __forceinline__ float rsqrt_approx(float x) { return rsqrtf(x); }
+__device__ __forceinline__ float rcp_approx(float x) { return __frcp_rn(x); }
 
-// sin(t)/t and (1-cos(t))/t^2 as polynomials in q = t^2, valid for q <= 1/16
-// (|t| <= 0.25 rad per half step; truncation < 1e-17).  Larger rotations take
-// the libm path (warp-uniform branch in the kernel).
+// Full-precision 1/sqrt(x) and 1/x for normal positive x (lengths, dilatations):
+// MUFU seed + one third-order Newton step (seed error e ~ 2^-20 -> e^3 ~ 2^-60).
+// 5 / 3 FP64 instructions instead of the ~10 / ~8 (plus special-case branch) of
+// rsqrt() / __drcp_rn().  Checked against the IEEE results in tests/test_kernels_gpu.py.
+__device__ __forceinline__ double rsqrt_nr(double x) {
+  double y = rsqrt_approx(x);
+  double h = x * y;
+  double e = fma(-h, y, 1.0);              // 1 - x y^2
+  double p = fma(0.375, e, 0.5) * e;       // e/2 + 3 e^2/8
+  return fma(y, p, y);
+}
+__device__ __forceinline__ float rsqrt_nr(float x) { return rsqrtf(x); }
+__device__ __forceinline__ double rcp_nr(double x) {
+  double y = rcp_approx(x);
+  double e = fma(-x, y, 1.0);              // 1 - x y
+  return fma(y, fma(e, e, e), y);          // y (1 + e + e^2)
+}
+__device__ __forceinline__ float rcp_nr(float x) { return __frcp_rn(x); }
+
+// Polynomial maps below are degree-minimal interpolants at Chebyshev nodes, fitted in
+// 60-digit arithmetic (mpmath) and verified to <= 1 ulp (2.2e-16) on the stated range.
+
+// A = sin(t)/t and B = (1-cos t)/t^2 as functions of q = t^2, valid for q <= 0.25
+// (|rotation| <= 0.5 rad per kinematic update).  Larger rotations take the libm path.
 template <typename T> __device__ __forceinline__ void sinc_cosc(T q, T &A, T &B) {
-  // A = sum (-1)^k q^k/(2k+1)!   B = sum (-1)^k q^k/(2k+2)!
-  T a = T(1.0 / 6227020800.0);          // 1/13!
-  a = fma(a, q, T(-1.0 / 39916800.0));  // 1/11!
-  a = fma(a, q, T(1.0 / 362880.0));     // 1/9!
-  a = fma(a, q, T(-1.0 / 5040.0));
-  a = fma(a, q, T(1.0 / 120.0));
-  a = fma(a, q, T(-1.0 / 6.0));
+  T a = T(-2.4931934029233215e-08);
+  a = fma(a, q, T(2.7556981477681245e-06));
+  a = fma(a, q, T(-0.00019841269403598734));
+  a = fma(a, q, T(0.00833333333307693));
+  a = fma(a, q, T(-0.16666666666666116));
   A = fma(a, q, T(1.0));
-  T b = T(1.0 / 87178291200.0);         // 1/14!
-  b = fma(b, q, T(-1.0 / 479001600.0)); // 1/12!
-  b = fma(b, q, T(1.0 / 3628800.0));    // 1/10!
-  b = fma(b, q, T(-1.0 / 40320.0));
-  b = fma(b, q, T(1.0 / 720.0));
-  b = fma(b, q, T(-1.0 / 24.0));
+  T b = T(-2.0790894217124703e-09);
+  b = fma(b, q, T(2.7557077887523167e-07));
+  b = fma(b, q, T(-2.4801586988836374e-05));
+  b = fma(b, q, T(0.0013888888888705666));
+  b = fma(b, q, T(-0.041666666666666276));
   B = fma(b, q, T(0.5));
 }
-constexpr double kSmallRotQ = 0.0625;
+constexpr double kSmallRotQ = 0.25;
 
-// g(u) = theta / sin(theta) with u = sin^2(theta/2) = (1 - cos theta)/2:
-//   g = asin(s) / (s sqrt(1-s^2)), s^2 = u  =  sum_k 4^k (k!)^2/(2k+1)! u^k.
-// 12 terms: truncation < 1e-17 for u <= 0.0225 (theta <= 0.30 rad between
-// neighbouring elements); beyond that the kernel takes the acos path.
+// g(u) = theta / sin(theta) with u = sin^2(theta/2) = (1 - cos theta)/2, valid for
+// u <= 0.25, i.e. up to 60 degrees of bending between neighbouring elements (a rod bent
+// to a radius of one element length).  Beyond that the kernel takes the acos path.
 template <typename T> __device__ __forceinline__ T theta_over_sin(T u) {
-  // c_{k+1} = c_k * (2k+2)/(2k+3)
-  constexpr double c0 = 1.0, c1 = c0 * 2 / 3, c2 = c1 * 4 / 5, c3 = c2 * 6 / 7, c4 = c3 * 8 / 9,
-                   c5 = c4 * 10 / 11, c6 = c5 * 12 / 13, c7 = c6 * 14 / 15, c8 = c7 * 16 / 17,
-                   c9 = c8 * 18 / 19, c10 = c9 * 20 / 21, c11 = c10 * 22 / 23;
-  T g = T(c11);
-  g = fma(g, u, T(c10));
-  g = fma(g, u, T(c9));
-  g = fma(g, u, T(c8));
-  g = fma(g, u, T(c7));
-  g = fma(g, u, T(c6));
-  g = fma(g, u, T(c5));
-  g = fma(g, u, T(c4));
-  g = fma(g, u, T(c3));
-  g = fma(g, u, T(c2));
-  g = fma(g, u, T(c1));
-  g = fma(g, u, T(c0));
-  return g;
+  T g = T(0.7004333670912273);
+  g = fma(g, u, T(-0.010109211165683595));
+  g = fma(g, u, T(0.33627006293385214));
+  g = fma(g, u, T(0.2554785051838476));
+  g = fma(g, u, T(0.2856689010559272));
+  g = fma(g, u, T(0.2993695424665021));
+  g = fma(g, u, T(0.3182700383289065));
+  g = fma(g, u, T(0.3409918863270117));
+  g = fma(g, u, T(0.36940838269940973));
+  g = fma(g, u, T(0.4063492060981829));
+  g = fma(g, u, T(0.4571428571456908));
+  g = fma(g, u, T(0.5333333333333167));
+  g = fma(g, u, T(0.6666666666666667));
+  return fma(g, u, T(1.0));
 }
-constexpr double kSmallBendU = 0.0225;
+constexpr double kSmallBendU = 0.25;
 
-// exp(z) for |z| <= 1e-3 (degree 4, truncation 8e-18): used for c^(e) = c * exp((e-1) ln c)
+// exp(z) for |z| <= 0.01: used for c^(e) = c * exp((e-1) ln c) in the analytical damper
 template <typename T> __device__ __forceinline__ T exp_small(T z) {
-  T p = T(1.0 / 24.0);
-  p = fma(p, z, T(1.0 / 6.0));
-  p = fma(p, z, T(0.5));
+  T p = T(0.008333363095284598);
+  p = fma(p, z, T(0.041666875000418525));
+  p = fma(p, z, T(0.1666666666655506));
+  p = fma(p, z, T(0.49999999999218747));
   p = fma(p, z, T(1.0));
   return fma(p, z, T(1.0));
 }
-constexpr double kSmallExpZ = 1.0e-3;
+constexpr double kSmallExpZ = 1.0e-2;
 
 }  // namespace sr

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -102,20 +103,41 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   }
 }
 
-template <typename T, int EPL, int MATH> int launch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+template <typename T, int EPL, int MATH, int MINB>
+int launch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   int grid = (A.n_env + sr::WARPS_PER_CTA - 1) / sr::WARPS_PER_CTA;
-  sr::rod_substeps_kernel<T, EPL, MATH><<<grid, sr::WARPS_PER_CTA * 32, 0, s>>>(A);
+  sr::rod_substeps_kernel<T, EPL, MATH, MINB><<<grid, sr::WARPS_PER_CTA * 32, 0, s>>>(A);
   h->launches++;
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
 
+// occupancy variant: CTAs (of 4 warps) per SM the kernel is compiled for.  Tunable with
+// SOFTROD_MIN_CTAS={2,3,4} for experiments; the default is the measured best.
+int min_ctas_setting() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SOFTROD_MIN_CTAS");
+    v = e ? atoi(e) : 3;
+    if (v < 2 || v > 4) v = 3;
+  }
+  return v;
+}
+
+template <typename T, int EPL> int dispatch_math(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  if (h->cfg.math != SR_MATH_FAST) return launch_substeps<T, EPL, sr::MATH_FAITHFUL, 2>(h, A, s);
+  switch (min_ctas_setting()) {
+    case 2: return launch_substeps<T, EPL, sr::MATH_FAST, 2>(h, A, s);
+    case 4: return launch_substeps<T, EPL, sr::MATH_FAST, 4>(h, A, s);
+    default: return launch_substeps<T, EPL, sr::MATH_FAST, 3>(h, A, s);
+  }
+}
+
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  const bool fast = h->cfg.math == SR_MATH_FAST;
   switch (h->epl) {
-    case 1: return fast ? launch_substeps<T, 1, sr::MATH_FAST>(h, A, s) : launch_substeps<T, 1, sr::MATH_FAITHFUL>(h, A, s);
-    case 2: return fast ? launch_substeps<T, 2, sr::MATH_FAST>(h, A, s) : launch_substeps<T, 2, sr::MATH_FAITHFUL>(h, A, s);
-    case 4: return fast ? launch_substeps<T, 4, sr::MATH_FAST>(h, A, s) : launch_substeps<T, 4, sr::MATH_FAITHFUL>(h, A, s);
+    case 1: return dispatch_math<T, 1>(h, A, s);
+    case 2: return dispatch_math<T, 2>(h, A, s);
+    case 4: return dispatch_math<T, 4>(h, A, s);
   }
   return fail(SR_E_INVALID, "unsupported elements-per-lane");
 }
