@@ -12,7 +12,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsoftrod.so")
 SOURCES = ["softrod_api.cu"]
-HEADERS = ["rod_kernels.cuh", "rod_math.cuh", os.path.join("..", "..", "include", "softrod.h")]
+HEADERS = ["rod_kernels.cuh", "rod_kernel_packed.cuh", "rod_math.cuh", os.path.join("..", "..", "include", "softrod.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -1,0 +1,296 @@
+// rod_kernel_packed.cuh — CTA-packed variant of the fused K-substep kernel (sm_100a).
+//
+// Mapping: one thread owns node j and element j of a rod (j = 0..n; thread n owns the
+// tip node only), and rods are packed back to back across the CTA: a 256-thread CTA
+// holds floor(256/(n+1)) rods (5 rods x 51 threads = 255 lanes for n = 50), so ~99 %
+// of the lanes that issue FP64 instructions do useful work (the warp-per-rod kernel in
+// rod_kernels.cuh uses 25 of 32).  The whole per-thread state (x, v, Q, w: 18 values)
+// stays in registers for all K substeps; the neighbour values needed by the stencils
+// (x,v,Q of j+1, x of j+2; stress and couple of j-1) go through shared memory, with two
+// CTA barriers per substep.  Same arithmetic as the fast path of rod_kernels.cuh
+// (reference boundary
+// /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:183-184).
+#pragma once
+#include "rod_kernels.cuh"
+
+namespace sr {
+
+constexpr int PACKED_THREADS = 256;
+
+// shared-memory words per thread: x(3) v(3) Q(9) | s(3) N(3)
+constexpr int PACKED_SMEM_PER_THREAD = 21;
+
+template <typename T, int MINB>
+__global__ void __launch_bounds__(PACKED_THREADS, MINB)
+rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *sh = reinterpret_cast<T *>(smem_raw);
+  constexpr int NT = PACKED_THREADS;
+  T *sh_x = sh, *sh_v = sh + 3 * NT, *sh_Q = sh + 6 * NT, *sh_s = sh + 15 * NT, *sh_N = sh + 18 * NT;
+
+  const int tid = threadIdx.x;
+  const int n = A.n_elem, stride = A.stride, tpr = n + 1;  // threads per rod
+  const int r = tid / tpr, j = tid - r * tpr;
+  const int env = blockIdx.x * rods_per_cta + r;
+  const bool active = (r < rods_per_cta) && (env < A.n_env);
+  const bool elem_ok = active && j < n, vor_ok = active && j < n - 1, first = (j == 0);
+  // neighbour slots (clamped so that idle / edge threads read something harmless)
+  const int t_next = (active && j < n) ? tid + 1 : tid;
+  const int t_next2 = (active && j < n - 1) ? tid + 2 : t_next;
+  const int t_prev = (active && j > 0) ? tid - 1 : tid;
+
+  T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
+  T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
+  T *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      x[c] = st[(F_POS + c) * stride + j];
+      v[c] = st[(F_VEL + c) * stride + j];
+      w[c] = st[(F_OMEGA + c) * stride + j];   // slot n holds 0 (never written by anyone)
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
+  }
+  // time-step multipliers are zero where there is nothing to integrate (tip thread's
+  // pseudo-element, idle threads): no selects in the update expressions.
+  const T dtim = active ? A.dt_inv_mass * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
+  const T gmask = active ? T(1) : T(0);
+  const T dte = elem_ok ? A.dt : T(0);
+
+  const T *bc = A.bc + (size_t)(active ? env : 0) * BC_DIM;
+  T act0 = T(0), base_px = T(0), base_py = T(0), base_vx = T(0), base_vy = T(0);
+  if (active && A.action_dim > 0) act0 = (T)A.action[(size_t)env * A.action_dim];
+  if (active && A.bc_kind == BC_MOVING_BASE) {
+    const T *aux = A.aux + (size_t)env * AUX_DIM;
+    base_px = aux[0]; base_py = aux[1]; base_vx = aux[3]; base_vy = aux[4];
+  }
+  const bool bc_thread = active && first && A.bc_kind != BC_FREE;
+
+  auto constrain_values = [&]() {
+    if (bc_thread) {
+      if (A.bc_kind == BC_PENDULUM_SLIDER) {
+        x[1] = bc[1]; x[2] = bc[2];
+#pragma unroll
+        for (int m = 0; m < 3; m++) { Q[0 + m] = bc[3 + m]; Q[6 + m] = bc[9 + m]; }
+      } else if (A.bc_kind == BC_ONE_END_FIXED) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) x[c] = bc[c];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+      } else {
+        x[0] = base_px; x[1] = base_py; x[2] = bc[2];
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+      }
+    }
+  };
+  auto constrain_rates = [&]() {
+    if (bc_thread) {
+      if (A.bc_kind == BC_PENDULUM_SLIDER) {
+        v[1] = T(0); v[2] = T(0); w[0] = T(0); w[2] = T(0);
+      } else if (A.bc_kind == BC_ONE_END_FIXED) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { v[c] = T(0); w[c] = T(0); }
+      } else {
+        v[0] = base_vx; v[1] = base_vy; v[2] = T(0);
+#pragma unroll
+        for (int c = 0; c < 3; c++) w[c] = T(0);
+      }
+    }
+  };
+  // x += hh v ; Q <- R(hh w) Q (merged half steps, see rod_kernels.cuh)
+  auto kinematic = [&](T hh, T eps) {
+    T a0 = hh * w[0], a1 = hh * w[1], a2 = hh * w[2];
+#pragma unroll
+    for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
+    T q = fma(a2, a2, fma(a1, a1, a0 * a0));
+    // the BC-owned base element is excluded from the vote (see rod_kernels.cuh)
+    bool slow = !(q <= T(kSmallRotQ)) && !bc_thread;
+    if (!__any_sync(FULL, slow)) rotate_directors_fast<T>(a0, a1, a2, q, eps, Q);
+    else rotate_directors_ref<T>(a0, a1, a2, Q);
+  };
+
+  const T h = A.half_dt, dt = A.dt;
+  if (A.n_substeps > 0) { kinematic(h, T(1e-14)); constrain_values(); }
+
+#pragma unroll 1
+  for (int s = 0; s < A.n_substeps; s++) {
+    const bool last = (s == A.n_substeps - 1);
+    // ---- publish what the neighbours need ------------------------------------------
+#pragma unroll
+    for (int c = 0; c < 3; c++) { sh_x[c * NT + tid] = x[c]; sh_v[c * NT + tid] = v[c]; }
+#pragma unroll
+    for (int c = 0; c < 9; c++) sh_Q[c * NT + tid] = Q[c];
+    __syncthreads();
+
+    // ---- geometry, shear/stretch strain, internal force ------------------------------
+    T xn[3], dx[3], dv[3], dx2[3], Qn[9];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      xn[c] = sh_x[c * NT + t_next];
+      dx[c] = xn[c] - x[c];
+      dv[c] = sh_v[c * NT + t_next] - v[c];
+      dx2[c] = sh_x[c * NT + t_next2] - xn[c];
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) Qn[c] = sh_Q[c * NT + t_next];
+    if (!elem_ok) dx[2] = A.rest_len;   // keeps the pseudo-element's quantities finite
+    if (!vor_ok) dx2[2] = A.rest_len;
+    T l2 = dot3(dx, dx);
+    T il = rsqrt_nr(l2);
+    T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
+    T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
+    T l2n = dot3(dx2, dx2);
+    T lgn = fma(l2n, rsqrt_nr(l2n), T(1e-14));    // length of element j+1, recomputed locally
+    T t[3] = {dx[0] * ilg, dx[1] * ilg, dx[2] * ilg};
+    T e = lg * A.inv_rest_len;
+    T inv_e = A.rest_len * ilg;
+    T edot = dot3(dx, dv) * (ilg * A.inv_rest_len);
+    T Qt[3], sig[3], nst[3], sfl[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Qt[i] = fma(Q[3 * i + 2], t[2], fma(Q[3 * i + 1], t[1], Q[3 * i] * t[0]));
+      sig[i] = (i == 2) ? fma(e, Qt[i], T(-1)) : e * Qt[i];
+      nst[i] = A.S[i] * sig[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      T sv = fma(Q[6 + i], nst[2], fma(Q[3 + i], nst[1], Q[i] * nst[0])) * inv_e;
+      sfl[i] = elem_ok ? sv : T(0);
+      sh_s[i * NT + tid] = sfl[i];
+    }
+
+    // ---- curvature, bending couple ----------------------------------------------------
+    auto rm = [&](int a, int b) {
+      return fma(Qn[3 * a + 2], Q[3 * b + 2], fma(Qn[3 * a + 1], Q[3 * b + 1], Qn[3 * a] * Q[3 * b]));
+    };
+    T vec[3] = {rm(2, 1) - rm(1, 2), rm(0, 2) - rm(2, 0), rm(1, 0) - rm(0, 1)};
+    T tr = rm(0, 0) + rm(1, 1) + rm(2, 2);
+    T u = T(0.5) * ((T(1.5) - T(0.5) * tr) + T(1e-10));   // sin^2(theta_ref/2), 1e-10 guard
+    if (!vor_ok) u = T(5e-11);
+    T fac;
+    if (!__any_sync(FULL, !(u <= T(kSmallBendU)))) {
+      T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
+      fac = T(-0.5) * theta_over_sin(u) * fma(T(-1e-14), cot, T(1.0));
+    } else {
+      fac = bend_factor_ref<T>(u);
+    }
+    T kp[3], tau[3], kxt[3];
+    T fs = fac * A.inv_rest_vor;
+#pragma unroll
+    for (int i = 0; i < 3; i++) { kp[i] = vec[i] * fs; tau[i] = A.B[i] * kp[i]; }
+    cross3(kp, tau, kxt);
+    T eps = (T(0.5) * (lgn + lg)) * A.inv_rest_vor;
+    T ie3 = rcp_nr(eps * eps * eps);
+    if (!vor_ok) ie3 = T(0);
+    T hc = T(0.5) * A.rest_vor * ie3;
+    T P[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      T m = tau[i] * ie3;
+      P[i] = fma(kxt[i], hc, m);                 // m_j + c_j/2  (own element)
+      sh_N[i * NT + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
+    }
+    if (last) {
+      // stale observables of the reference: last force evaluation
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          st[(F_TAN + i) * stride + j] = t[i];
+          st[(F_KAPPA + i) * stride + j] = kp[i];
+          st[(F_SIGMA + i) * stride + j] = sig[i];
+        }
+        st[F_DIL * stride + j] = e;
+      }
+    }
+    __syncthreads();
+
+    // ---- assemble loads, dynamic step --------------------------------------------------
+    T ssc[3], jw[3], lt[3];
+    cross3(Qt, nst, ssc);
+#pragma unroll
+    for (int i = 0; i < 3; i++) jw[i] = (A.J[i] * w[i]) * inv_e;
+    cross3(jw, w, lt);
+    T ede = edot * inv_e;
+    T dtee = dte * e;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      T sp = first ? T(0) : sh_s[i * NT + t_prev];
+      T np = first ? T(0) : sh_N[i * NT + t_prev];
+      T fi = sfl[i] - sp;
+      T gd = A.gdt[i];
+      if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
+      v[i] = fma(gmask, gd, fma(fi, dtim, v[i]));
+      T tq = fma(jw[i], ede, fma(ssc[i], A.rest_len, P[i] + np) + lt[i]);
+      w[i] = fma(dtee, A.Jinv[i] * tq, w[i]);
+    }
+
+    // ---- rate constraints and dissipation ------------------------------------------------
+    auto dampen = [&]() {
+      if (A.damping_on) {
+        T em1 = e - T(1);
+        T z[3] = {em1 * A.logc_w[0], em1 * A.logc_w[1], em1 * A.logc_w[2]};
+        bool big = !(fabs_(z[0]) <= T(kSmallExpZ)) || !(fabs_(z[1]) <= T(kSmallExpZ)) ||
+                   !(fabs_(z[2]) <= T(kSmallExpZ));
+        big = __any_sync(FULL, big);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          v[i] = v[i] * A.c_v;
+          T cw = big ? exp_ref<T>(e * A.logc_w[i]) : A.c_w[i] * exp_small(z[i]);
+          w[i] = w[i] * cw;
+        }
+      }
+    };
+    if (A.damp_first) { dampen(); constrain_rates(); }
+    else { constrain_rates(); dampen(); }
+
+    kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
+    constrain_values();
+  }
+
+  // ---- write back, NaN guard, model outputs ------------------------------------------------
+  __syncthreads();   // all reads of the exchange buffers are done: reuse them below
+  bool bad = false;
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      st[(F_POS + c) * stride + j] = x[c];
+      st[(F_VEL + c) * stride + j] = v[c];
+      bad = bad || (x[c] != x[c]) || (v[c] != v[c]);
+    }
+    if (j < n) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) st[(F_OMEGA + c) * stride + j] = w[c];
+#pragma unroll
+      for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + j] = Q[c];
+    }
+  }
+  // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)
+  int *sh_flag = reinterpret_cast<int *>(sh_s);
+  if (tid < 64) sh_flag[tid] = 0;
+  if (active && A.model == MODEL_SOFT_PENDULUM) {
+    // the tangents were stored to global memory at the last substep; stage them for lane j=0
+#pragma unroll
+    for (int i = 0; i < 3; i++) sh_x[i * NT + tid] = (j < n) ? st[(F_TAN + i) * stride + j] : T(0);
+  }
+  __syncthreads();
+  if (active && bad) atomicOr(&sh_flag[r], 1);
+  __syncthreads();
+  if (active && first) {
+    const bool invalid = sh_flag[r] != 0;
+    if (A.model == MODEL_SOFT_PENDULUM) {
+      soft_pendulum_outputs<T>(sh_x + tid, NT, n, (double)x[0], (double)v[0], (float)act0, invalid,
+                               A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
+    } else {
+      A.reward[env] = 0.0;
+      A.terminated[env] = invalid ? 1 : 0;
+    }
+  }
+  if (active && A.model == MODEL_ROD && j == n) {
+    float *o = A.obs + (size_t)env * A.obs_dim;
+    for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
+  }
+}
+
+}  // namespace sr

@@ -18,6 +18,7 @@
 
 #include "../../include/softrod.h"
 #include "rod_kernels.cuh"
+#include "rod_kernel_packed.cuh"
 
 namespace {
 
@@ -133,7 +134,35 @@ template <typename T, int EPL> int dispatch_math(sr_handle *h, sr::RodArgs<T> &A
   }
 }
 
+// kernel choice for the fast path: "packed" (thread per element, rods packed across a CTA)
+// or "warp" (warp per rod).  SOFTROD_KERNEL overrides the default for experiments.
+bool use_packed_kernel(const sr_handle *h) {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SOFTROD_KERNEL");
+    v = (e && strcmp(e, "warp") == 0) ? 0 : 1;
+  }
+  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= sr::PACKED_THREADS / 2;
+}
+
+template <typename T, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  const int rods_per_cta = sr::PACKED_THREADS / (A.n_elem + 1);
+  const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
+  const size_t smem = (size_t)sr::PACKED_SMEM_PER_THREAD * sr::PACKED_THREADS * sizeof(T);
+  sr::rod_packed_kernel<T, MINB><<<grid, sr::PACKED_THREADS, smem, s>>>(A, rods_per_cta);
+  h->launches++;
+  SR_CUDA(cudaGetLastError());
+  return SR_OK;
+}
+
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  if (use_packed_kernel(h)) {
+    switch (min_ctas_setting()) {
+      case 2: return launch_packed<T, 2>(h, A, s);
+      case 4: return launch_packed<T, 4>(h, A, s);
+      default: return launch_packed<T, 3>(h, A, s);
+    }
+  }
   switch (h->epl) {
     case 1: return dispatch_math<T, 1>(h, A, s);
     case 2: return dispatch_math<T, 2>(h, A, s);
