@@ -17,16 +17,19 @@ namespace sr {
 
 constexpr int PACKED_THREADS = 256;
 
+// row stride of the exchange arrays: slot NT is a permanent zero (what the stencils see to
+// the left of element 0), so the base thread needs no select when it reads "j-1"
+constexpr int PACKED_ROW = PACKED_THREADS + 2;
 // shared-memory words per thread: x(3) v(3) Q(9) | s(3) N(3)
-constexpr int PACKED_SMEM_PER_THREAD = 21;
+constexpr int PACKED_SMEM_WORDS = 21 * PACKED_ROW;
 
 template <typename T, int MINB>
 __global__ void __launch_bounds__(PACKED_THREADS, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sh = reinterpret_cast<T *>(smem_raw);
-  constexpr int NT = PACKED_THREADS;
-  T *sh_x = sh, *sh_v = sh + 3 * NT, *sh_Q = sh + 6 * NT, *sh_s = sh + 15 * NT, *sh_N = sh + 18 * NT;
+  constexpr int NT = PACKED_THREADS, RS = PACKED_ROW;
+  T *sh_x = sh, *sh_v = sh + 3 * RS, *sh_Q = sh + 6 * RS, *sh_s = sh + 15 * RS, *sh_N = sh + 18 * RS;
 
   const int tid = threadIdx.x;
   const int n = A.n_elem, stride = A.stride, tpr = n + 1;  // threads per rod
@@ -37,7 +40,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   // neighbour slots (clamped so that idle / edge threads read something harmless)
   const int t_next = (active && j < n) ? tid + 1 : tid;
   const int t_next2 = (active && j < n - 1) ? tid + 2 : t_next;
-  const int t_prev = (active && j > 0) ? tid - 1 : tid;
+  const int t_prev = (active && j > 0) ? tid - 1 : NT;   // NT = the zero slot
+  if (tid < 6) sh_s[(tid % 3) * RS + NT + (tid / 3) * (3 * RS)] = T(0);  // zero slots of s and N
 
   T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
   T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
@@ -58,33 +62,38 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const T gmask = active ? T(1) : T(0);
   const T dte = elem_ok ? A.dt : T(0);
 
-  const T *bc = A.bc + (size_t)(active ? env : 0) * BC_DIM;
-  T act0 = T(0), base_px = T(0), base_py = T(0), base_vx = T(0), base_vy = T(0);
+  T act0 = T(0), base_vx = T(0), base_vy = T(0);
   if (active && A.action_dim > 0) act0 = (T)A.action[(size_t)env * A.action_dim];
-  if (active && A.bc_kind == BC_MOVING_BASE) {
-    const T *aux = A.aux + (size_t)env * AUX_DIM;
-    base_px = aux[0]; base_py = aux[1]; base_vx = aux[3]; base_vy = aux[4];
-  }
   const bool bc_thread = active && first && A.bc_kind != BC_FREE;
-
-  auto constrain_values = [&]() {
-    if (bc_thread) {
-      if (A.bc_kind == BC_PENDULUM_SLIDER) {
-        x[1] = bc[1]; x[2] = bc[2];
+  // Boundary conditions of this build pin node 0 / element 0 by OVERWRITING values after every
+  // kinematic update (soft_pendulum/build.py:71-74, OneEndFixedBC, soft_pendulum_3d/build.py:32-35).
+  // Applying the overwrite once here and then never moving the pinned quantities is the same
+  // thing: the base thread integrates its frame with a zero rotation vector (rot_on = 0; for
+  // the slider the free row d2 is invariant under R(0,w1,0) anyway), pinned position components
+  // have zero velocity after constrain_rates, and the moving base is re-pinned from registers.
+  const T rot_on = bc_thread ? T(0) : T(1);
+  T pin_x = T(0), pin_y = T(0);
+  if (bc_thread) {
+    const T *bc = A.bc + (size_t)env * BC_DIM;
+    if (A.bc_kind == BC_PENDULUM_SLIDER) {
+      x[1] = bc[1]; x[2] = bc[2];
 #pragma unroll
-        for (int m = 0; m < 3; m++) { Q[0 + m] = bc[3 + m]; Q[6 + m] = bc[9 + m]; }
-      } else if (A.bc_kind == BC_ONE_END_FIXED) {
+      for (int m = 0; m < 3; m++) { Q[0 + m] = bc[3 + m]; Q[6 + m] = bc[9 + m]; }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+      if (A.bc_kind == BC_ONE_END_FIXED) {
 #pragma unroll
         for (int c = 0; c < 3; c++) x[c] = bc[c];
-#pragma unroll
-        for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
       } else {
-        x[0] = base_px; x[1] = base_py; x[2] = bc[2];
-#pragma unroll
-        for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+        const T *aux = A.aux + (size_t)env * AUX_DIM;
+        pin_x = aux[0]; pin_y = aux[1]; base_vx = aux[3]; base_vy = aux[4];
+        x[0] = pin_x; x[1] = pin_y; x[2] = bc[2];
       }
     }
-  };
+  }
+  const bool moving = bc_thread && A.bc_kind == BC_MOVING_BASE;
+
   auto constrain_rates = [&]() {
     if (bc_thread) {
       if (A.bc_kind == BC_PENDULUM_SLIDER) {
@@ -101,51 +110,51 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   };
   // x += hh v ; Q <- R(hh w) Q (merged half steps, see rod_kernels.cuh)
   auto kinematic = [&](T hh, T eps) {
-    T a0 = hh * w[0], a1 = hh * w[1], a2 = hh * w[2];
+    const T hw = hh * rot_on;
+    T a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
 #pragma unroll
     for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
+    if (moving) { x[0] = pin_x; x[1] = pin_y; }
     T q = fma(a2, a2, fma(a1, a1, a0 * a0));
-    // the BC-owned base element is excluded from the vote (see rod_kernels.cuh)
-    bool slow = !(q <= T(kSmallRotQ)) && !bc_thread;
-    if (!__any_sync(FULL, slow)) rotate_directors_fast<T>(a0, a1, a2, q, eps, Q);
+    if (!__any_sync(FULL, !(q <= T(kSmallRotQ)))) rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
     else rotate_directors_ref<T>(a0, a1, a2, Q);
   };
 
   const T h = A.half_dt, dt = A.dt;
-  if (A.n_substeps > 0) { kinematic(h, T(1e-14)); constrain_values(); }
+  if (A.n_substeps > 0) kinematic(h, T(1e-14));
 
 #pragma unroll 1
   for (int s = 0; s < A.n_substeps; s++) {
     const bool last = (s == A.n_substeps - 1);
     // ---- publish what the neighbours need ------------------------------------------
 #pragma unroll
-    for (int c = 0; c < 3; c++) { sh_x[c * NT + tid] = x[c]; sh_v[c * NT + tid] = v[c]; }
+    for (int c = 0; c < 3; c++) { sh_x[c * RS + tid] = x[c]; sh_v[c * RS + tid] = v[c]; }
 #pragma unroll
-    for (int c = 0; c < 9; c++) sh_Q[c * NT + tid] = Q[c];
+    for (int c = 0; c < 9; c++) sh_Q[c * RS + tid] = Q[c];
     __syncthreads();
 
     // ---- geometry, shear/stretch strain, internal force ------------------------------
-    T xn[3], dx[3], dv[3], dx2[3], Qn[9];
+    T dx[3], dv[3], dx2[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      xn[c] = sh_x[c * NT + t_next];
-      dx[c] = xn[c] - x[c];
-      dv[c] = sh_v[c * NT + t_next] - v[c];
-      dx2[c] = sh_x[c * NT + t_next2] - xn[c];
+      T xn = sh_x[c * RS + t_next];
+      dx[c] = xn - x[c];
+      dv[c] = sh_v[c * RS + t_next] - v[c];
+      dx2[c] = sh_x[c * RS + t_next2] - xn;
     }
-#pragma unroll
-    for (int c = 0; c < 9; c++) Qn[c] = sh_Q[c * NT + t_next];
     if (!elem_ok) dx[2] = A.rest_len;   // keeps the pseudo-element's quantities finite
     if (!vor_ok) dx2[2] = A.rest_len;
     T l2 = dot3(dx, dx);
+    T l2n = dot3(dx2, dx2);
     T il = rsqrt_nr(l2);
+    T iln = rsqrt_nr(l2n);
     T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
     T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
-    T l2n = dot3(dx2, dx2);
-    T lgn = fma(l2n, rsqrt_nr(l2n), T(1e-14));    // length of element j+1, recomputed locally
+    T lgn = fma(l2n, iln, T(1e-14));              // length of element j+1, recomputed locally
     T t[3] = {dx[0] * ilg, dx[1] * ilg, dx[2] * ilg};
     T e = lg * A.inv_rest_len;
     T inv_e = A.rest_len * ilg;
+    T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
     T edot = dot3(dx, dv) * (ilg * A.inv_rest_len);
     T Qt[3], sig[3], nst[3], sfl[3];
 #pragma unroll
@@ -156,23 +165,37 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      T sv = fma(Q[6 + i], nst[2], fma(Q[3 + i], nst[1], Q[i] * nst[0])) * inv_e;
-      sfl[i] = elem_ok ? sv : T(0);
-      sh_s[i * NT + tid] = sfl[i];
+      sfl[i] = fma(Q[6 + i], nst[2], fma(Q[3 + i], nst[1], Q[i] * nst[0])) * inv_e_s;
+      sh_s[i * RS + tid] = sfl[i];
     }
 
     // ---- curvature, bending couple ----------------------------------------------------
-    auto rm = [&](int a, int b) {
-      return fma(Qn[3 * a + 2], Q[3 * b + 2], fma(Qn[3 * a + 1], Q[3 * b + 1], Qn[3 * a] * Q[3 * b]));
-    };
-    T vec[3] = {rm(2, 1) - rm(1, 2), rm(0, 2) - rm(2, 0), rm(1, 0) - rm(0, 1)};
-    T tr = rm(0, 0) + rm(1, 1) + rm(2, 2);
-    T u = T(0.5) * ((T(1.5) - T(0.5) * tr) + T(1e-10));   // sin^2(theta_ref/2), 1e-10 guard
+    T vec[3], tr;
+    {
+      T Qn[9];
+#pragma unroll
+      for (int c = 0; c < 9; c++) Qn[c] = sh_Q[c * RS + t_next];
+      auto rm = [&](int a, int b) {
+        return fma(Qn[3 * a + 2], Q[3 * b + 2], fma(Qn[3 * a + 1], Q[3 * b + 1], Qn[3 * a] * Q[3 * b]));
+      };
+      // axial part of Rm - Rm^T, each component one 6-term FMA chain
+      auto rm_diff = [&](int a, int b) {
+        T p = Qn[3 * a] * Q[3 * b];
+        p = fma(Qn[3 * a + 1], Q[3 * b + 1], p);
+        p = fma(Qn[3 * a + 2], Q[3 * b + 2], p);
+        p = fma(-Qn[3 * b], Q[3 * a], p);
+        p = fma(-Qn[3 * b + 1], Q[3 * a + 1], p);
+        return fma(-Qn[3 * b + 2], Q[3 * a + 2], p);
+      };
+      vec[0] = rm_diff(2, 1); vec[1] = rm_diff(0, 2); vec[2] = rm_diff(1, 0);
+      tr = rm(0, 0) + rm(1, 1) + rm(2, 2);
+    }
+    T u = fma(T(-0.25), tr, T(0.75 + 0.5e-10));   // sin^2(theta_ref/2) with the 1e-10 guard
     if (!vor_ok) u = T(5e-11);
     T fac;
     if (!__any_sync(FULL, !(u <= T(kSmallBendU)))) {
       T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
-      fac = T(-0.5) * theta_over_sin(u) * fma(T(-1e-14), cot, T(1.0));
+      fac = theta_over_sin(A.poly, u) * fma(T(0.5e-14), cot, T(-0.5));
     } else {
       fac = bend_factor_ref<T>(u);
     }
@@ -190,7 +213,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int i = 0; i < 3; i++) {
       T m = tau[i] * ie3;
       P[i] = fma(kxt[i], hc, m);                 // m_j + c_j/2  (own element)
-      sh_N[i * NT + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
+      sh_N[i * RS + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
     }
     if (last) {
       // stale observables of the reference: last force evaluation
@@ -216,13 +239,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T dtee = dte * e;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      T sp = first ? T(0) : sh_s[i * NT + t_prev];
-      T np = first ? T(0) : sh_N[i * NT + t_prev];
-      T fi = sfl[i] - sp;
+      T fi = sfl[i] - sh_s[i * RS + t_prev];
       T gd = A.gdt[i];
       if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
       v[i] = fma(gmask, gd, fma(fi, dtim, v[i]));
-      T tq = fma(jw[i], ede, fma(ssc[i], A.rest_len, P[i] + np) + lt[i]);
+      T tq = fma(jw[i], ede, fma(ssc[i], A.rest_len, P[i] + sh_N[i * RS + t_prev]) + lt[i]);
       w[i] = fma(dtee, A.Jinv[i] * tq, w[i]);
     }
 
@@ -230,23 +251,28 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     auto dampen = [&]() {
       if (A.damping_on) {
         T em1 = e - T(1);
-        T z[3] = {em1 * A.logc_w[0], em1 * A.logc_w[1], em1 * A.logc_w[2]};
-        bool big = !(fabs_(z[0]) <= T(kSmallExpZ)) || !(fabs_(z[1]) <= T(kSmallExpZ)) ||
-                   !(fabs_(z[2]) <= T(kSmallExpZ));
-        big = __any_sync(FULL, big);
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-          v[i] = v[i] * A.c_v;
-          T cw = big ? exp_ref<T>(e * A.logc_w[i]) : A.c_w[i] * exp_small(z[i]);
-          w[i] = w[i] * cw;
+        T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
+        bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
+                   !(fabs_(z2) <= T(kSmallExpZ));
+        T cw0, cw1, cw2;
+        if (!__any_sync(FULL, big)) {
+          cw0 = A.c_w[0] * exp_small(A.poly, z0);
+          cw2 = A.c_w[2] * exp_small(A.poly, z2);
+          cw1 = A.isotropic ? cw0 : A.c_w[1] * exp_small(A.poly, z1);
+        } else {
+          cw0 = exp_ref<T>(e * A.logc_w[0]);
+          cw1 = exp_ref<T>(e * A.logc_w[1]);
+          cw2 = exp_ref<T>(e * A.logc_w[2]);
         }
+#pragma unroll
+        for (int i = 0; i < 3; i++) v[i] = v[i] * A.c_v;
+        w[0] *= cw0; w[1] *= cw1; w[2] *= cw2;
       }
     };
     if (A.damp_first) { dampen(); constrain_rates(); }
     else { constrain_rates(); dampen(); }
 
     kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
-    constrain_values();
   }
 
   // ---- write back, NaN guard, model outputs ------------------------------------------------
@@ -272,7 +298,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   if (active && A.model == MODEL_SOFT_PENDULUM) {
     // the tangents were stored to global memory at the last substep; stage them for lane j=0
 #pragma unroll
-    for (int i = 0; i < 3; i++) sh_x[i * NT + tid] = (j < n) ? st[(F_TAN + i) * stride + j] : T(0);
+    for (int i = 0; i < 3; i++) sh_x[i * RS + tid] = (j < n) ? st[(F_TAN + i) * stride + j] : T(0);
   }
   __syncthreads();
   if (active && bad) atomicOr(&sh_flag[r], 1);
@@ -280,7 +306,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   if (active && first) {
     const bool invalid = sh_flag[r] != 0;
     if (A.model == MODEL_SOFT_PENDULUM) {
-      soft_pendulum_outputs<T>(sh_x + tid, NT, n, (double)x[0], (double)v[0], (float)act0, invalid,
+      soft_pendulum_outputs<T>(sh_x + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
                                A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
     } else {
       A.reward[env] = 0.0;

@@ -55,6 +55,8 @@ template <typename T> struct RodArgs {
   T mass, inv_mass, dt_inv_mass;  // interior node (end nodes carry half the mass)
   T g[3], gdt[3];
   T c_v, c_w[3], logc_w[3];
+  int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
+  PolyCoef<T> poly;
 };
 
 template <typename T, int EPL> struct Vec;
@@ -103,8 +105,13 @@ __device__ __forceinline__ void shift_prev(const T (&a)[EPL], int lane, T (&out)
 // ---- Rodrigues update Q <- R(h w) Q   -------------------------
 // reference operation order (elastica/_rotations.py:_get_rotation_matrix); also the
 // large-rotation fallback of the fast path, kept out of line to keep the hot loop small.
+template <typename T> struct Mat9 { T m[9]; };
+
 template <typename T>
-__device__ __noinline__ void rotate_directors_ref(T a0, T a1, T a2, T *Q) {
+__device__ __noinline__ Mat9<T> rotate_directors_ref_val(T a0, T a1, T a2, Mat9<T> Qin) {
+  const T *Q = Qin.m;
+  Mat9<T> out;
+  T *n = out.m;
   T q = a0 * a0 + a1 * a1 + a2 * a2;
   T theta = sqrt_(q);
   T d = theta + T(1e-14);
@@ -118,15 +125,22 @@ __device__ __noinline__ void rotate_directors_ref(T a0, T a1, T a2, T *Q) {
   T R01 = up * v2 + us * v0 * v1, R10 = -up * v2 + us * v0 * v1;
   T R02 = -up * v1 + us * v0 * v2, R20 = up * v1 + us * v0 * v2;
   T R12 = up * v0 + us * v1 * v2, R21 = -up * v0 + us * v1 * v2;
-  T n[9];
 #pragma unroll
   for (int m = 0; m < 3; m++) {
     n[0 + m] = R00 * Q[0 + m] + R01 * Q[3 + m] + R02 * Q[6 + m];
     n[3 + m] = R10 * Q[0 + m] + R11 * Q[3 + m] + R12 * Q[6 + m];
     n[6 + m] = R20 * Q[0 + m] + R21 * Q[3 + m] + R22 * Q[6 + m];
   }
+  return out;
+}
+// registers in, registers out: the directors never have their address taken in the hot loop
+template <typename T> __device__ __forceinline__ void rotate_directors_ref(T a0, T a1, T a2, T (&Q)[9]) {
+  Mat9<T> in;
 #pragma unroll
-  for (int i = 0; i < 9; i++) Q[i] = n[i];
+  for (int i = 0; i < 9; i++) in.m[i] = Q[i];
+  Mat9<T> out = rotate_directors_ref_val<T>(a0, a1, a2, in);
+#pragma unroll
+  for (int i = 0; i < 9; i++) Q[i] = out.m[i];
 }
 
 // fast path: R = I + A K + B K^2 with A = sin(t)/t, B = (1-cos t)/t^2, applied as Q += D Q.
@@ -134,9 +148,10 @@ __device__ __noinline__ void rotate_directors_ref(T a0, T a1, T a2, T *Q) {
 // rotation by 1e-14 rad (2e-14 for a merged full step):  A *= rho, B *= rho^2 with
 // rho = 1 - eps/sqrt(q + eps^2)  (-> 0 as |a| -> 0, like the reference).
 template <typename T>
-__device__ __forceinline__ void rotate_directors_fast(T a0, T a1, T a2, T q, T eps, T Q[9]) {
+__device__ __forceinline__ void rotate_directors_fast(const PolyCoef<T> &C, T a0, T a1, T a2, T q, T eps,
+                                                      T (&Q)[9]) {
   T A, B;
-  sinc_cosc(q, A, B);
+  sinc_cosc(C, q, A, B);
   T rho = fma(-eps, rsqrt_approx(fma(eps, eps, q)), T(1.0));
   A *= rho;
   B *= rho * rho;
@@ -318,7 +333,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
       T Qj[9];
 #pragma unroll
       for (int c = 0; c < 9; c++) Qj[c] = Q[c][j];
-      if (fast) rotate_directors_fast<T>(a[0][j], a[1][j], a[2][j], q[j], eps, Qj);
+      if (fast) rotate_directors_fast<T>(A.poly, a[0][j], a[1][j], a[2][j], q[j], eps, Qj);
       else rotate_directors_ref<T>(a[0][j], a[1][j], a[2][j], Qj);
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c][j] = Qj[c];
@@ -433,7 +448,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
         // cot(theta) = (1 - 2u) / sqrt(4u(1-u)); u >= 5e-11 by the 1e-10 guard, so no singularity
         T u = uu[j];
         T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
-        fac = T(-0.5) * theta_over_sin(u) * fma(T(-1e-14), cot, T(1.0));
+        fac = T(-0.5) * theta_over_sin(A.poly, u) * fma(T(-1e-14), cot, T(1.0));
       } else {
         fac = bend_factor_ref<T>(uu[j]);
       }
@@ -554,7 +569,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
           for (int i = 0; i < 3; i++) {
             v[i][j] = v[i][j] * A.c_v;
             T cw;
-            if (ef) cw = A.c_w[i] * exp_small(z[i][j]);
+            if (ef) cw = A.c_w[i] * exp_small(A.poly, z[i][j]);
             else if (MATH == MATH_FAST) cw = exp_ref<T>(e[j] * A.logc_w[i]);
             else cw = pow_(A.c_w[i], e[j]);
             w[i][j] = w[i][j] * cw;

@@ -83,55 +83,65 @@ __device__ __forceinline__ float rcp_nr(float x) { return __frcp_rn(x); }
 
 // Polynomial maps below are degree-minimal interpolants at Chebyshev nodes, fitted in
 // 60-digit arithmetic (mpmath) and verified to <= 1 ulp (2.2e-16) on the stated range.
+// The coefficients travel in the kernel-parameter constant bank (PolyCoef inside RodArgs),
+// so every Horner/Estrin step is one DFMA with a c[0][..] operand: no register, no move.
 
 // A = sin(t)/t and B = (1-cos t)/t^2 as functions of q = t^2, valid for q <= 0.25
-// (|rotation| <= 0.5 rad per kinematic update).  Larger rotations take the libm path.
-template <typename T> __device__ __forceinline__ void sinc_cosc(T q, T &A, T &B) {
-  T a = T(-2.4931934029233215e-08);
-  a = fma(a, q, T(2.7556981477681245e-06));
-  a = fma(a, q, T(-0.00019841269403598734));
-  a = fma(a, q, T(0.00833333333307693));
-  a = fma(a, q, T(-0.16666666666666116));
-  A = fma(a, q, T(1.0));
-  T b = T(-2.0790894217124703e-09);
-  b = fma(b, q, T(2.7557077887523167e-07));
-  b = fma(b, q, T(-2.4801586988836374e-05));
-  b = fma(b, q, T(0.0013888888888705666));
-  b = fma(b, q, T(-0.041666666666666276));
-  B = fma(b, q, T(0.5));
-}
+// (|rotation| <= 0.5 rad per kinematic update); ascending powers.
+#define SR_COEF_SINC {1.0, -0.16666666666666116, 0.00833333333307693, -0.00019841269403598734, \
+                      2.7556981477681245e-06, -2.4931934029233215e-08}
+#define SR_COEF_COSC {0.5, -0.041666666666666276, 0.0013888888888705666, -2.4801586988836374e-05, \
+                      2.7557077887523167e-07, -2.0790894217124703e-09}
 constexpr double kSmallRotQ = 0.25;
 
 // g(u) = theta / sin(theta) with u = sin^2(theta/2) = (1 - cos theta)/2, valid for
 // u <= 0.25, i.e. up to 60 degrees of bending between neighbouring elements (a rod bent
-// to a radius of one element length).  Beyond that the kernel takes the acos path.
-template <typename T> __device__ __forceinline__ T theta_over_sin(T u) {
-  T g = T(0.7004333670912273);
-  g = fma(g, u, T(-0.010109211165683595));
-  g = fma(g, u, T(0.33627006293385214));
-  g = fma(g, u, T(0.2554785051838476));
-  g = fma(g, u, T(0.2856689010559272));
-  g = fma(g, u, T(0.2993695424665021));
-  g = fma(g, u, T(0.3182700383289065));
-  g = fma(g, u, T(0.3409918863270117));
-  g = fma(g, u, T(0.36940838269940973));
-  g = fma(g, u, T(0.4063492060981829));
-  g = fma(g, u, T(0.4571428571456908));
-  g = fma(g, u, T(0.5333333333333167));
-  g = fma(g, u, T(0.6666666666666667));
-  return fma(g, u, T(1.0));
-}
+// to a radius of one element length); ascending powers, degree 13.
+#define SR_COEF_BEND {1.0, 0.6666666666666667, 0.5333333333333167, 0.4571428571456908, \
+                      0.4063492060981829, 0.36940838269940973, 0.3409918863270117, \
+                      0.3182700383289065, 0.2993695424665021, 0.2856689010559272, \
+                      0.2554785051838476, 0.33627006293385214, -0.010109211165683595, \
+                      0.7004333670912273}
 constexpr double kSmallBendU = 0.25;
 
-// exp(z) for |z| <= 0.01: used for c^(e) = c * exp((e-1) ln c) in the analytical damper
-template <typename T> __device__ __forceinline__ T exp_small(T z) {
-  T p = T(0.008333363095284598);
-  p = fma(p, z, T(0.041666875000418525));
-  p = fma(p, z, T(0.1666666666655506));
-  p = fma(p, z, T(0.49999999999218747));
-  p = fma(p, z, T(1.0));
-  return fma(p, z, T(1.0));
-}
+// exp(z) for |z| <= 0.01: c^(e) = c * exp((e-1) ln c) in the analytical damper; degree 5.
+#define SR_COEF_EXP {1.0, 1.0, 0.49999999999218747, 0.1666666666655506, 0.041666875000418525, \
+                     0.008333363095284598}
 constexpr double kSmallExpZ = 1.0e-2;
+
+template <typename T> struct PolyCoef {
+  T sinc[6], cosc[6], bend[14], expz[6];
+};
+
+template <typename T> __device__ __forceinline__ void sinc_cosc(const PolyCoef<T> &C, T q, T &A, T &B) {
+  T a = fma(C.sinc[5], q, C.sinc[4]);
+  T b = fma(C.cosc[5], q, C.cosc[4]);
+  a = fma(a, q, C.sinc[3]); b = fma(b, q, C.cosc[3]);
+  a = fma(a, q, C.sinc[2]); b = fma(b, q, C.cosc[2]);
+  a = fma(a, q, C.sinc[1]); b = fma(b, q, C.cosc[1]);
+  A = fma(a, q, C.sinc[0]); B = fma(b, q, C.cosc[0]);
+}
+
+// Estrin evaluation of the degree-13 bend polynomial: 7 independent first-level FMAs and a
+// depth of 5 instead of a 13-deep Horner chain (the kernel is bound by dependent-issue latency).
+template <typename T> __device__ __forceinline__ T theta_over_sin(const PolyCoef<T> &C, T u) {
+  const T *c = C.bend;
+  T u2 = u * u;
+  T p0 = fma(c[1], u, c[0]), p1 = fma(c[3], u, c[2]), p2 = fma(c[5], u, c[4]), p3 = fma(c[7], u, c[6]);
+  T p4 = fma(c[9], u, c[8]), p5 = fma(c[11], u, c[10]), p6 = fma(c[13], u, c[12]);
+  T u4 = u2 * u2;
+  T q0 = fma(p1, u2, p0), q1 = fma(p3, u2, p2), q2 = fma(p5, u2, p4);
+  T u8 = u4 * u4;
+  T r0 = fma(q1, u4, q0), r1 = fma(p6, u4, q2);
+  return fma(r1, u8, r0);
+}
+
+template <typename T> __device__ __forceinline__ T exp_small(const PolyCoef<T> &C, T z) {
+  T p = fma(C.expz[5], z, C.expz[4]);
+  p = fma(p, z, C.expz[3]);
+  p = fma(p, z, C.expz[2]);
+  p = fma(p, z, C.expz[1]);
+  return fma(p, z, C.expz[0]);
+}
 
 }  // namespace sr

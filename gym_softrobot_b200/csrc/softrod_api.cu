@@ -90,6 +90,12 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     A.g[i] = (T)c.gravity[i]; A.gdt[i] = (T)(c.gravity[i] * c.dt);
   }
   A.mass = (T)mass; A.inv_mass = (T)(1.0 / mass); A.dt_inv_mass = (T)(c.dt / mass);
+  A.isotropic = 1;  // straight_rod builds circular cross-sections: I1 == I2
+  {
+    const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
+    for (int i = 0; i < 6; i++) { A.poly.sinc[i] = (T)cs[i]; A.poly.cosc[i] = (T)cc[i]; A.poly.expz[i] = (T)ce[i]; }
+    for (int i = 0; i < 14; i++) A.poly.bend[i] = (T)cb[i];
+  }
   if (c.damping_constant >= 0.0) {
     // element mass incl. the end-element correction equals `mass` for a uniform rod
     A.c_v = (T)exp(-c.damping_constant * c.dt);
@@ -148,7 +154,7 @@ bool use_packed_kernel(const sr_handle *h) {
 template <typename T, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = sr::PACKED_THREADS / (A.n_elem + 1);
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
-  const size_t smem = (size_t)sr::PACKED_SMEM_PER_THREAD * sr::PACKED_THREADS * sizeof(T);
+  const size_t smem = (size_t)sr::PACKED_SMEM_WORDS * sizeof(T);
   sr::rod_packed_kernel<T, MINB><<<grid, sr::PACKED_THREADS, smem, s>>>(A, rods_per_cta);
   h->launches++;
   SR_CUDA(cudaGetLastError());
