@@ -2,7 +2,7 @@
 //
 // Mapping: one thread owns node j and element j of a rod (j = 0..n; thread n owns the
 // tip node only), and rods are packed back to back across the CTA: a 256-thread CTA
-// holds floor(256/(n+1)) rods (5 rods x 51 threads = 255 lanes for n = 50), so ~99 %
+// holds floor(NT/(n+1)) rods (5 rods x 51 threads = 255 lanes for n = 50, NT = 256), so ~99 %
 // of the lanes that issue FP64 instructions do useful work (the warp-per-rod kernel in
 // rod_kernels.cuh uses 25 of 32).  The whole per-thread state (x, v, Q, w: 18 values)
 // stays in registers for all K substeps; the neighbour values needed by the stencils
@@ -15,20 +15,19 @@
 
 namespace sr {
 
-constexpr int PACKED_THREADS = 256;
+constexpr int PACKED_MAX_THREADS = 512;
 
 // row stride of the exchange arrays: slot NT is a permanent zero (what the stencils see to
 // the left of element 0), so the base thread needs no select when it reads "j-1"
-constexpr int PACKED_ROW = PACKED_THREADS + 2;
-// shared-memory words per thread: x(3) v(3) Q(9) | s(3) N(3)
-constexpr int PACKED_SMEM_WORDS = 21 * PACKED_ROW;
+// shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide
+constexpr int packed_smem_words(int nt) { return 21 * (nt + 2); }
 
-template <typename T, int MINB>
-__global__ void __launch_bounds__(PACKED_THREADS, MINB)
+template <typename T, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T *sh = reinterpret_cast<T *>(smem_raw);
-  constexpr int NT = PACKED_THREADS, RS = PACKED_ROW;
+  constexpr int RS = NT + 2;
   T *sh_x = sh, *sh_v = sh + 3 * RS, *sh_Q = sh + 6 * RS, *sh_s = sh + 15 * RS, *sh_N = sh + 18 * RS;
 
   const int tid = threadIdx.x;
@@ -58,7 +57,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   }
   // time-step multipliers are zero where there is nothing to integrate (tip thread's
   // pseudo-element, idle threads): no selects in the update expressions.
-  const T dtim = active ? A.dt_inv_mass * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
+  // (c_v is 1 when the damper is off)
+  const T dtim_cv = active ? A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
   const T gmask = active ? T(1) : T(0);
   const T dte = elem_ok ? A.dt : T(0);
 
@@ -102,7 +102,9 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
         for (int c = 0; c < 3; c++) { v[c] = T(0); w[c] = T(0); }
       } else {
-        v[0] = base_vx; v[1] = base_vy; v[2] = T(0);
+        // [constrain, dampen] order: the damper rescales the commanded base velocity too
+        const T sc = A.damp_first ? T(1) : A.c_v;
+        v[0] = base_vx * sc; v[1] = base_vy * sc; v[2] = T(0);
 #pragma unroll
         for (int c = 0; c < 3; c++) w[c] = T(0);
       }
@@ -151,17 +153,16 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
     T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
     T lgn = fma(l2n, iln, T(1e-14));              // length of element j+1, recomputed locally
-    T t[3] = {dx[0] * ilg, dx[1] * ilg, dx[2] * ilg};
     T e = lg * A.inv_rest_len;
     T inv_e = A.rest_len * ilg;
     T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
     T edot = dot3(dx, dv) * (ilg * A.inv_rest_len);
-    T Qt[3], sig[3], nst[3], sfl[3];
+    // sigma = e Q t - z = Q dx / l0 - z exactly (e t = dx / l0): no tangent needed here
+    T Qdx[3], nst[3], sfl[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      Qt[i] = fma(Q[3 * i + 2], t[2], fma(Q[3 * i + 1], t[1], Q[3 * i] * t[0]));
-      sig[i] = (i == 2) ? fma(e, Qt[i], T(-1)) : e * Qt[i];
-      nst[i] = A.S[i] * sig[i];
+      Qdx[i] = fma(Q[3 * i + 2], dx[2], fma(Q[3 * i + 1], dx[1], Q[3 * i] * dx[0]));
+      nst[i] = (i == 2) ? fma(A.S_over_l[i], Qdx[i], -A.S[i]) : A.S_over_l[i] * Qdx[i];
     }
 #pragma unroll
     for (int i = 0; i < 3; i++) {
@@ -208,42 +209,51 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T ie3 = rcp_nr(eps * eps * eps);
     if (!vor_ok) ie3 = T(0);
     T hc = T(0.5) * A.rest_vor * ie3;
-    T P[3];
+    // local couples share one 1/e factor:  (Qt x n) l0 + (Jw/e) x w + (Jw/e) (de/dt)/e
+    //   = [ (Q dx) x n + (Jw) x w + (Jw) (de/dt)/e ] / e      (Qt l0 = Q dx / e)
+    // Everything that does not need the left neighbour is folded into tql[] before the second
+    // barrier, so only x,v,Q,w + tql + sfl + e stay live across it.
+    T pw[3] = {A.J[0] * w[0], A.J[1] * w[1], A.J[2] * w[2]};
+    T ede = edot * inv_e;
+    T G[3];
+    G[0] = fma(Qdx[1], nst[2], -(Qdx[2] * nst[1]));
+    G[1] = fma(Qdx[2], nst[0], -(Qdx[0] * nst[2]));
+    G[2] = fma(Qdx[0], nst[1], -(Qdx[1] * nst[0]));
+    G[0] = fma(pw[1], w[2], fma(-pw[2], w[1], G[0]));
+    G[1] = fma(pw[2], w[0], fma(-pw[0], w[2], G[1]));
+    G[2] = fma(pw[0], w[1], fma(-pw[1], w[0], G[2]));
+    T tql[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       T m = tau[i] * ie3;
-      P[i] = fma(kxt[i], hc, m);                 // m_j + c_j/2  (own element)
+      T Pi = fma(kxt[i], hc, m);                 // m_j + c_j/2  (own element)
       sh_N[i * RS + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
+      tql[i] = fma(fma(pw[i], ede, G[i]), inv_e, Pi);
     }
     if (last) {
       // stale observables of the reference: last force evaluation
       if (active) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          st[(F_TAN + i) * stride + j] = t[i];
+          st[(F_TAN + i) * stride + j] = dx[i] * ilg;
           st[(F_KAPPA + i) * stride + j] = kp[i];
-          st[(F_SIGMA + i) * stride + j] = sig[i];
+          st[(F_SIGMA + i) * stride + j] = fma(A.inv_rest_len, Qdx[i], (i == 2) ? T(-1) : T(0));
         }
         st[F_DIL * stride + j] = e;
       }
     }
     __syncthreads();
 
-    // ---- assemble loads, dynamic step --------------------------------------------------
-    T ssc[3], jw[3], lt[3];
-    cross3(Qt, nst, ssc);
-#pragma unroll
-    for (int i = 0; i < 3; i++) jw[i] = (A.J[i] * w[i]) * inv_e;
-    cross3(jw, w, lt);
-    T ede = edot * inv_e;
+    // ---- add the left neighbour's share, dynamic step -------------------------------------
     T dtee = dte * e;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       T fi = sfl[i] - sh_s[i * RS + t_prev];
-      T gd = A.gdt[i];
+      T gd = A.gdt_cv[i];
       if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
-      v[i] = fma(gmask, gd, fma(fi, dtim, v[i]));
-      T tq = fma(jw[i], ede, fma(ssc[i], A.rest_len, P[i] + sh_N[i * RS + t_prev]) + lt[i]);
+      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
+      v[i] = fma(fi, dtim_cv, fma(v[i], A.c_v, gmask * gd));
+      T tq = tql[i] + sh_N[i * RS + t_prev];
       w[i] = fma(dtee, A.Jinv[i] * tq, w[i]);
     }
 
@@ -264,8 +274,6 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
           cw1 = exp_ref<T>(e * A.logc_w[1]);
           cw2 = exp_ref<T>(e * A.logc_w[2]);
         }
-#pragma unroll
-        for (int i = 0; i < 3; i++) v[i] = v[i] * A.c_v;
         w[0] *= cw0; w[1] *= cw1; w[2] *= cw2;
       }
     };

@@ -54,6 +54,7 @@ template <typename T> struct RodArgs {
   T S[3], B[3], J[3], Jinv[3];
   T mass, inv_mass, dt_inv_mass;  // interior node (end nodes carry half the mass)
   T g[3], gdt[3];
+  T S_over_l[3], gdt_cv[3];   // S / rest_len ; dt g c_v  (packed kernel)
   T c_v, c_w[3], logc_w[3];
   int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
   PolyCoef<T> poly;

@@ -90,6 +90,10 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     A.g[i] = (T)c.gravity[i]; A.gdt[i] = (T)(c.gravity[i] * c.dt);
   }
   A.mass = (T)mass; A.inv_mass = (T)(1.0 / mass); A.dt_inv_mass = (T)(c.dt / mass);
+  for (int i = 0; i < 3; i++) {
+    A.S_over_l[i] = (T)(S[i] / rl);
+    A.gdt_cv[i] = (T)(c.gravity[i] * c.dt * (c.damping_constant >= 0.0 ? exp(-c.damping_constant * c.dt) : 1.0));
+  }
   A.isotropic = 1;  // straight_rod builds circular cross-sections: I1 == I2
   {
     const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
@@ -125,8 +129,8 @@ int min_ctas_setting() {
   static int v = -1;
   if (v < 0) {
     const char *e = getenv("SOFTROD_MIN_CTAS");
-    v = e ? atoi(e) : 3;
-    if (v < 2 || v > 4) v = 3;
+    v = e ? atoi(e) : 2;
+    if (v < 2 || v > 4) v = 2;
   }
   return v;
 }
@@ -148,26 +152,43 @@ bool use_packed_kernel(const sr_handle *h) {
     const char *e = getenv("SOFTROD_KERNEL");
     v = (e && strcmp(e, "warp") == 0) ? 0 : 1;
   }
-  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= sr::PACKED_THREADS / 2;
+  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 128;
 }
 
-template <typename T, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  const int rods_per_cta = sr::PACKED_THREADS / (A.n_elem + 1);
+template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  const int rods_per_cta = NT / (A.n_elem + 1);
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
-  const size_t smem = (size_t)sr::PACKED_SMEM_WORDS * sizeof(T);
-  sr::rod_packed_kernel<T, MINB><<<grid, sr::PACKED_THREADS, smem, s>>>(A, rods_per_cta);
+  const size_t smem = (size_t)sr::packed_smem_words(NT) * sizeof(T);
+  auto kern = sr::rod_packed_kernel<T, NT, MINB>;
+  static bool attr_set = false;   // per instantiation
+  if (!attr_set) {
+    SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  kern<<<grid, NT, smem, s>>>(A, rods_per_cta);
   h->launches++;
   SR_CUDA(cudaGetLastError());
   return SR_OK;
 }
 
+// CTA size of the packed kernel: SOFTROD_PACKED_THREADS={256,320,384} for experiments
+int packed_threads_setting() {
+  static int v = -1;
+  if (v < 0) {
+    const char *e = getenv("SOFTROD_PACKED_THREADS");
+    v = e ? atoi(e) : 256;
+    if (v != 256 && v != 320 && v != 384) v = 256;
+  }
+  return v;
+}
+
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_packed_kernel(h)) {
-    switch (min_ctas_setting()) {
-      case 2: return launch_packed<T, 2>(h, A, s);
-      case 4: return launch_packed<T, 4>(h, A, s);
-      default: return launch_packed<T, 3>(h, A, s);
-    }
+    const int nt = packed_threads_setting(), mb = min_ctas_setting();
+    if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
+    if (nt == 384) return launch_packed<T, 384, 2>(h, A, s);
+    if (mb == 3) return launch_packed<T, 256, 3>(h, A, s);
+    return launch_packed<T, 256, 2>(h, A, s);
   }
   switch (h->epl) {
     case 1: return dispatch_math<T, 1>(h, A, s);

@@ -1,0 +1,105 @@
+"""CPU: host-side logic of the drop-in layer (no kernels): seeding, spaces, time accumulation,
+env sharding (incl. a world_size-2 gloo run) and the registry."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import gym_softrobot_b200 as gsb
+from gym_softrobot_b200 import distributed as D
+from gym_softrobot_b200.compat import Box
+from gym_softrobot_b200.envs import soft_pendulum as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_registry_keeps_reference_ids():
+    assert "SoftPendulum-v0" in gsb.REGISTRY and "SoftPendulum-v0" in gsb.VECTOR_REGISTRY
+
+
+def test_init_params_match_reference_build(golden_dir):
+    """direction/normal from the env generator exactly as soft_pendulum/build.py:47-51."""
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_episode.npz"))
+    u = np.random.Generator(np.random.PCG64(np.random.SeedSequence(42))).random()
+    assert u == 0.7739560485559633
+    init = sp.pendulum_init_params(u)[0]
+    Q0 = g["state0/director"][:, :, 0]
+    # d3 = normalised position difference of the linspace nodes, d1 = normal/|normal|: equal to
+    # direction / normal up to one rounding (the reset kernel repeats the reference's arithmetic)
+    np.testing.assert_allclose(init[3:6], Q0[2], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(init[6:9], Q0[0], rtol=0, atol=4e-16)
+    x_tip = g["state0/position"][:, -1]
+    np.testing.assert_allclose(init[3:6] * 1.0, x_tip, rtol=0, atol=1e-16)
+
+
+def test_time_accumulation_and_truncation_index(golden_dir):
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_episode.npz"))
+    t = np.float64(0.0)
+    for i in range(int(g["n_steps"])):
+        t = sp._advance_time(t, 1e-4, 400)
+        assert t == g["time"][i]
+        assert bool(t > 5.0) == bool(g["truncated"][i])
+    assert 400 * 1e-4 * 125 == 5.0 and g["time"][124] < 5.0  # n*dt would truncate a step early
+
+
+def test_box_sampling_matches_golden_actions(golden_dir):
+    g = np.load(os.path.join(golden_dir, "softpendulum_v0_determinism_seed0.npz"))
+    box = Box(np.ones(1) * -22, np.ones(1) * 22, shape=(1,), dtype=np.float32)
+    box.seed(0)
+    for a in g["actions"]:
+        s = box.sample()
+        assert s.dtype == np.float32 and np.array_equal(s, a)
+    assert box.contains(np.array([3.0], dtype=np.float32)) and not box.contains(np.array([30.0], dtype=np.float32))
+
+
+@pytest.mark.parametrize("n,world", [(4096, 1), (4096, 8), (65536, 8), (10, 3), (2, 4), (0, 2)])
+def test_shard_envs_partitions_exactly(n, world):
+    shards = [D.shard_envs(n, r, world) for r in range(world)]
+    assert shards[0].start == 0 and shards[-1].stop == n
+    for a, b in zip(shards, shards[1:]):
+        assert a.stop == b.start
+    counts = [s.count for s in shards]
+    assert sum(counts) == n and max(counts) - min(counts) <= 1
+
+
+def test_shard_envs_rejects_bad_rank():
+    with pytest.raises(ValueError):
+        D.shard_envs(8, 2, 2)
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from gym_softrobot_b200 import distributed as D
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+sh = D.shard_envs(10, rank, world)
+st = D.EpisodeStats()
+# every rank reports one episode per env it owns, return = global env index
+for i in range(sh.start, sh.stop):
+    st.add(episodes=1, return_sum=float(i), length_sum=126, nan_count=int(i == 3))
+out = st.reduce()
+assert out["episodes"] == 10 and out["return_sum"] == 45.0 and out["length_sum"] == 1260 and out["nan_count"] == 1, out
+assert abs(out["mean_return"] - 4.5) < 1e-12
+# ranks own disjoint contiguous ranges covering everything
+lo = torch.tensor([sh.start, sh.stop]); all_lo = [torch.zeros(2, dtype=torch.long) for _ in range(world)]
+dist.all_gather(all_lo, lo)
+assert all_lo[0][0] == 0 and all_lo[-1][1] == 10 and all(all_lo[i][1] == all_lo[i+1][0] for i in range(world-1))
+dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharding_and_stats(tmp_path):
+    """N>1 path on CPU: world_size 2, gloo, rendezvous on 127.0.0.1."""
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), ROOT]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=180)
+    assert res.returncode == 0, res.stdout[-2000:]
+    assert res.stdout.count("ok") == 2

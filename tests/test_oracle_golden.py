@@ -1,0 +1,139 @@
+"""CPU: the C oracle (oracle/rod_oracle.c) against the golden fixtures and physical known answers.
+
+The fixtures in tests/golden were produced by oracle/gen_golden.py by running the
+UNMODIFIED reference env code on the oracle's PyElastica shim (parity unpinned against
+real PyElastica — see oracle/README.md).  The C oracle differs from that NumPy path only
+in libm (glibc vs NumPy SIMD kernels), i.e. at the 1e-11 level on velocities.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import rod_oracle as ro
+
+FIELDS = {"position": "position_collection", "velocity": "velocity_collection",
+          "director": "director_collection", "omega": "omega_collection", "tangents": "tangents"}
+
+
+def rel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def test_c_oracle_matches_golden_substeps(golden_dir):
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_substeps.npz"))
+    env = ro.OracleSoftPendulum()
+    env.reset(seed=42)
+    done = 0
+    for target in (1, 10, 100, 400, 1000):
+        env.rod.substeps(target - done, action=float(np.float32(g["action"])))
+        done = target
+        for gk, fk in FIELDS.items():
+            assert rel(getattr(env.rod, fk), g[f"sub{target}/{gk}"]) < 1e-9, (target, gk)
+        assert env.rod.time == float(g[f"sub{target}/time"])
+
+
+def test_c_oracle_matches_golden_episode(golden_dir):
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_episode.npz"))
+    env = ro.OracleSoftPendulum()
+    obs0, _ = env.reset(seed=42)
+    assert np.array_equal(obs0, g["obs0"])
+    n = int(g["n_steps"])
+    assert n == 126  # 125 steps to t = 5.0 (accumulated below 5.0), truncation fires on the 126th
+    for i in range(n):
+        obs, r, te, tr, info = env.step(g["actions"][i])
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+        assert info["time"] == g["time"][i]
+        if i < 3:
+            for gk, fk in FIELDS.items():
+                assert rel(getattr(env.rod, fk), g[f"state{i + 1}/{gk}"]) < 1e-9, (i, gk)
+            assert abs(r - g["reward"][i]) < 1e-9
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-5, atol=1e-6)
+    assert tr and not te
+
+
+def test_golden_actions_follow_gymnasium_box_sampling(golden_dir):
+    """Config 1 action list == Generator(PCG64(SeedSequence(42))).uniform(-22, 22, 1).astype(f32) (B-12)."""
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_seed42_episode.npz"))
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(42)))
+    mine = np.array([rng.uniform(low=np.float32(-22), high=np.float32(22), size=(1,)).astype(np.float32)
+                     for _ in range(int(g["n_steps"]))])
+    assert np.array_equal(mine, g["actions"])
+
+
+def test_determinism_protocol_on_oracle(golden_dir):
+    """tests/envs/test_determinism.py of the reference: same seed -> identical 3-step tuples."""
+    g = np.load(os.path.join(golden_dir, "softpendulum_v0_determinism_seed0.npz"))
+    outs = []
+    for _ in range(2):
+        env = ro.OracleSoftPendulum()
+        o0, _ = env.reset(seed=0)
+        outs.append([o0] + [env.step(a) for a in g["actions"]])
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][0], g["obs0"])
+    for (o1, r1, t1, x1, _), (o2, r2, t2, x2, _), go, gr in zip(outs[0][1:], outs[1][1:], g["obs"], g["reward"]):
+        assert np.array_equal(o1, o2) and r1 == r2 and t1 == t2 and x1 == x2
+        np.testing.assert_allclose(o1, go, rtol=1e-6, atol=1e-7)
+        assert abs(r1 - gr) < 1e-9
+
+
+def test_timoshenko_cantilever():
+    """PyElastica's canonical validation case: tip deflection of a clamped beam under a tip load.
+
+    Analytic Timoshenko: F L^3/(3EI) + F L/(alpha_c G A); the discrete clamp acts at the centre of
+    element 0, which shortens the bending arm by dl/2: expect the corrected value to 1e-3.
+    """
+    n, L, r, E, G, rho, F = 50, 3.0, 0.25, 1e6, 1e4, 5000.0, -15.0
+    dl = L / n
+    dt = 0.01 * dl
+    rod = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [0, 1.0, 0], L, r, rho, E, dt, shear_modulus=G,
+                       damping_constant=1.4, bc_kind=ro.BC_ONE_END_FIXED)
+    rod.user_forces[0, -1] = F
+    rod.substeps(int(60 / dt))
+    A = np.pi * r * r
+    I = A * A / (4 * np.pi)
+    expected = F * (L - 0.5 * dl) ** 3 / (3 * E * I) + F * L / ((27 / 28) * G * A)
+    assert abs(rod.position_collection[0, -1] / expected - 1) < 1e-3
+    assert np.abs(rod.velocity_collection).max() < 1e-5
+
+
+def test_free_fall_is_exact():
+    """PositionVerlet integrates constant acceleration exactly: x = x0 + g t^2 / 2."""
+    rod = ro.OracleRod(20, [0, 0, 0], [1.0, 0, 0], [0, 1.0, 0], 1.0, 0.05, 1000.0, 1e6, 1e-4,
+                       gravity=(0, -9.80665, 0))
+    y0 = rod.position_collection[1].copy()
+    rod.substeps(1000)
+    assert np.abs(rod.position_collection[1] - y0 - 0.5 * -9.80665 * rod.time ** 2).max() < 1e-13
+    assert np.abs(rod.omega_collection).max() == 0.0
+
+
+def test_strain_known_answers():
+    """Stretched straight rod -> sigma = (0,0,e-1); uniformly rotated frames -> kappa = theta/D about the axis."""
+    n = 10
+    rod = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [1.0, 0, 0], 1.0, 0.05, 1000.0, 1e6, 1e-6)
+    rod.position_collection[2] *= 1.05
+    theta = 0.01
+    for k in range(n):
+        c, s = np.cos(k * theta), np.sin(k * theta)
+        # rotate the material frame about d1 (lab x) by k*theta: rows are d1,d2,d3
+        rod.director_collection[:, :, k] = np.array([[1, 0, 0], [0, c, s], [0, -s, c]])
+    rod.substeps(1)  # strains are refreshed half a kinematic step later; velocities are still ~0
+    np.testing.assert_allclose(rod.dilatation, 1.05, rtol=1e-9)
+    kappa = rod.kappa
+    np.testing.assert_allclose(kappa[0], theta / 0.1, rtol=1e-4)
+    np.testing.assert_allclose(kappa[1:], 0.0, atol=1e-6)
+
+
+def test_integrator_is_second_order():
+    """PositionVerlet is second order: tip trajectories at dt, dt/2, dt/4 differ in the ratio 4
+    (undamped swinging cantilever, sampled at identical physical times)."""
+    def run(dt):
+        rod = ro.OracleRod(10, [0, 0, 0], [1.0, 0, 0], [0, 1.0, 0], 1.0, 0.05, 1000.0, 1e6, dt,
+                           gravity=(0, -9.80665, 0), bc_kind=ro.BC_ONE_END_FIXED)
+        out = []
+        for _ in range(20):   # 0.2 s of swing, sampled every 10 ms
+            rod.substeps(int(round(1e-2 / dt)))
+            out.append(rod.position_collection[:, -1].copy())
+        return np.array(out)
+    a, b, c = run(2e-4), run(1e-4), run(5e-5)
+    ratio = np.abs(a - b).max() / np.abs(b - c).max()
+    assert 3.5 < ratio < 4.5, ratio
