@@ -11,9 +11,11 @@ from .version import VERSION as __version__
 # id -> (entry point, kwargs); same ids / kwargs as the reference registry
 REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumEnv", {}),
+    "SoftPendulum3D-v0": ("gym_softrobot_b200.envs.soft_pendulum_3d:SoftPendulum3DEnv", {}),
 }
 VECTOR_REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
+    "SoftPendulum3D-v0": ("gym_softrobot_b200.envs.soft_pendulum_3d:SoftPendulum3DVectorEnv", {}),
 }
 
 

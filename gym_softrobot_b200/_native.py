@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_launch_count", "sr_measure_fp64_peak",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_launch_count", "sr_measure_fp64_peak",
 ]
 
 
@@ -34,6 +34,7 @@ class SrConfig(C.Structure):
         ("dt", C.c_double), ("base_length", C.c_double), ("base_radius", C.c_double),
         ("density", C.c_double), ("youngs_modulus", C.c_double), ("shear_modulus", C.c_double),
         ("gravity", C.c_double * 3), ("damping_constant", C.c_double),
+        ("base_step", C.c_double), ("base_limit", C.c_double), ("base_move_period", C.c_double),
     ]
 
 
@@ -79,6 +80,7 @@ def load_library():
     L.sr_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sr_get_state.argtypes = [C.c_void_p, C.POINTER(SrStateView)]
     L.sr_set_state.argtypes = [C.c_void_p, C.POINTER(SrStateView), C.c_void_p]
+    L.sr_get_aux.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_launch_count.argtypes = [C.c_void_p]
     L.sr_launch_count.restype = C.c_int64
     L.sr_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -115,7 +117,8 @@ class Handle:
     def __init__(self, *, model, n_env, n_elem, dt, base_length, base_radius, density, youngs_modulus,
                  shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
                  point_force_on_base=False, damping_before_constraints=True, laplace_filter_order=0,
-                 device=0, dtype=DTYPE_F64, math=MATH_FAST):
+                 device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
+                 base_move_period=0.0):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -128,6 +131,7 @@ class Handle:
         cfg.density, cfg.youngs_modulus, cfg.shear_modulus = density, youngs_modulus, shear_modulus
         cfg.gravity[:] = [float(g) for g in gravity]
         cfg.damping_constant = damping_constant
+        cfg.base_step, cfg.base_limit, cfg.base_move_period = base_step, base_limit, base_move_period
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(self._lib.sr_create(C.byref(cfg), C.byref(self._h)))
@@ -235,6 +239,13 @@ class Handle:
             "sigma": st[:, v.f_sigma:v.f_sigma + 3, :n],
             "dilatation": st[:, v.f_dilatation, :n],
         }
+
+    def aux_tensor(self):
+        """torch view [n_env, aux_dim] (float64) of the per-env model scratch (sr_get_aux)."""
+        import torch
+        ptr, dim = C.c_void_p(), C.c_int32()
+        _check(self._lib.sr_get_aux(self._h, C.byref(ptr), C.byref(dim)))
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), "<f8"), device=f"cuda:{self.device}")
 
     def set_state_from(self, other: "Handle"):
         v = other.state_view()

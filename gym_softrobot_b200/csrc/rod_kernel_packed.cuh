@@ -63,7 +63,9 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const T dte = elem_ok ? A.dt : T(0);
 
   T act0 = T(0), base_vx = T(0), base_vy = T(0);
-  if (active && A.action_dim > 0) act0 = (T)A.action[(size_t)env * A.action_dim];
+  float act_f0 = 0.0f, act_f1 = 0.0f;
+  if (active && A.action_dim > 0) { act_f0 = A.action[(size_t)env * A.action_dim]; act0 = (T)act_f0; }
+  if (active && A.action_dim > 1) act_f1 = A.action[(size_t)env * A.action_dim + 1];
   const bool bc_thread = active && first && A.bc_kind != BC_FREE;
   // Boundary conditions of this build pin node 0 / element 0 by OVERWRITING values after every
   // kinematic update (soft_pendulum/build.py:71-74, OneEndFixedBC, soft_pendulum_3d/build.py:32-35).
@@ -86,7 +88,17 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
         for (int c = 0; c < 3; c++) x[c] = bc[c];
       } else {
-        const T *aux = A.aux + (size_t)env * AUX_DIM;
+        T *aux = A.aux + (size_t)env * AUX_DIM;
+        if (A.model == MODEL_SOFT_PENDULUM_3D && A.n_substeps > 0) {
+          // set_action (soft_pendulum_3d.py:106-120): float32 displacement, float64 clipped position,
+          // velocity = actual displacement / (step_skip * time_step); the base jumps at once
+          T px = aux[0], py = aux[1];
+          T nx = px + (T)__fmul_rn(A.base_step_f32, act_f0), ny = py + (T)__fmul_rn(A.base_step_f32, act_f1);
+          nx = fmin(fmax(nx, -A.base_limit), A.base_limit);
+          ny = fmin(fmax(ny, -A.base_limit), A.base_limit);
+          aux[3] = (nx - px) * A.inv_move_period; aux[4] = (ny - py) * A.inv_move_period; aux[5] = T(0);
+          aux[0] = nx; aux[1] = ny;
+        }
         pin_x = aux[0]; pin_y = aux[1]; base_vx = aux[3]; base_vy = aux[4];
         x[0] = pin_x; x[1] = pin_y; x[2] = bc[2];
       }
@@ -276,6 +288,36 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         }
         w[0] *= cw0; w[1] *= cw1; w[2] *= cw2;
       }
+      if (A.laplace_order > 0) {
+        // LaplaceDissipationFilter (elastica/dissipation.py:nb_filter_rate): p passes of
+        // f <- (-f[k+1] - f[k-1] + 2 f[k]) / 4 on interior nodes / elements, ends held at 0; rate -= f.
+        // Two smem buffers alternate (x,v rows / first six Q rows), one barrier per pass.
+        const bool node_in = active && j > 0 && j < n, elem_in = active && j > 0 && j < n - 1;
+        T fv[3] = {node_in ? v[0] : T(0), node_in ? v[1] : T(0), node_in ? v[2] : T(0)};
+        T fw[3] = {elem_in ? w[0] : T(0), elem_in ? w[1] : T(0), elem_in ? w[2] : T(0)};
+        // pass 0 sees the *unfiltered* ends (w[0], w[-1] are only zeroed after the first update)
+        T ev[3] = {v[0], v[1], v[2]}, ew[3] = {w[0], w[1], w[2]};
+        for (int p = 0; p < A.laplace_order; p++) {
+          T *buf = (p & 1) ? sh_Q : sh_x;
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            buf[c * RS + tid] = (p == 0) ? ev[c] : fv[c];
+            buf[(3 + c) * RS + tid] = (p == 0) ? ew[c] : fw[c];
+          }
+          __syncthreads();
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            T mv = (p == 0) ? ev[c] : fv[c], mw = (p == 0) ? ew[c] : fw[c];
+            T nv = (-buf[c * RS + t_next] - buf[c * RS + ((j > 0) ? tid - 1 : tid)] + T(2) * mv) * T(0.25);
+            T nw = (-buf[(3 + c) * RS + t_next] - buf[(3 + c) * RS + ((j > 0) ? tid - 1 : tid)] + T(2) * mw) * T(0.25);
+            fv[c] = node_in ? nv : T(0);
+            fw[c] = elem_in ? nw : T(0);
+          }
+        }
+        __syncthreads();   // the last pass's reads finish before x,v,Q are published again
+#pragma unroll
+        for (int c = 0; c < 3; c++) { v[c] -= fv[c]; w[c] -= fw[c]; }
+      }
     };
     if (A.damp_first) { dampen(); constrain_rates(); }
     else { constrain_rates(); dampen(); }
@@ -303,7 +345,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)
   int *sh_flag = reinterpret_cast<int *>(sh_s);
   if (tid < 64) sh_flag[tid] = 0;
-  if (active && A.model == MODEL_SOFT_PENDULUM) {
+  if (active && (A.model == MODEL_SOFT_PENDULUM || A.model == MODEL_SOFT_PENDULUM_3D)) {
     // the tangents were stored to global memory at the last substep; stage them for lane j=0
 #pragma unroll
     for (int i = 0; i < 3; i++) sh_x[i * RS + tid] = (j < n) ? st[(F_TAN + i) * stride + j] : T(0);
@@ -316,6 +358,13 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (A.model == MODEL_SOFT_PENDULUM) {
       soft_pendulum_outputs<T>(sh_x + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
                                A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
+    } else if (A.model == MODEL_SOFT_PENDULUM_3D) {
+      const double x0[3] = {(double)x[0], (double)x[1], (double)x[2]};
+      const double v0[3] = {(double)v[0], (double)v[1], (double)v[2]};
+      T *aux = A.aux + (size_t)env * AUX_DIM;
+      soft_pendulum_3d_outputs<T>(sh_x + tid, RS, n, x0, v0, act_f0, act_f1, (double)aux[0], (double)aux[1],
+                                  invalid, A.obs + (size_t)env * A.obs_dim, A.reward + env,
+                                  A.terminated + env, aux + 6);
     } else {
       A.reward[env] = 0.0;
       A.terminated[env] = invalid ? 1 : 0;

@@ -56,6 +56,7 @@ template <typename T> struct RodArgs {
   T g[3], gdt[3];
   T S_over_l[3], gdt_cv[3];   // S / rest_len ; dt g c_v  (packed kernel)
   T c_v, c_w[3], logc_w[3];
+  T base_limit, inv_move_period; float base_step_f32;   // SoftPendulum3D base controller
   int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
   PolyCoef<T> poly;
 };
@@ -182,12 +183,18 @@ template <typename T> __device__ __noinline__ T bend_factor_ref(T u) {
 }
 template <typename T> __device__ __noinline__ T exp_ref(T x) { return exp_(x); }
 
-// numpy's pairwise float64 row sum (np.mean over the contiguous axis), n <= 128
-template <typename T> __device__ inline double np_pairwise_sum(const T *a, int n) {
+// numpy's pairwise float64 row sum (np.mean over the contiguous axis): 8 running sums for
+// blocks of <= 128 values, recursive halving above (numpy/core/src/umath/loops_utils.h.src)
+template <typename T> __device__ double np_pairwise_sum(const T *a, int n) {
   if (n < 8) {
     double r = 0.0;
     for (int i = 0; i < n; i++) r += (double)a[i];
     return r;
+  }
+  if (n > 128) {
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
   }
   double r[8];
   for (int j = 0; j < 8; j++) r[j] = (double)a[j];
@@ -226,6 +233,31 @@ __device__ inline void soft_pendulum_outputs(const T *tan_smem, int stride, int 
     if (invalid) survive = -50.0;
     else forward = fabs(x0) * 10 + theta * theta;
     *reward = forward - 0.0 + survive;
+    *terminated = invalid ? 1 : 0;
+  }
+}
+
+// SoftPendulum3D-v0 observation / reward (reference soft_pendulum_3d.py:94-104,122-158)
+template <typename T>
+__device__ inline void soft_pendulum_3d_outputs(const T *tan_smem, int stride, int n, const double x0[3],
+                                                const double v0[3], float a0, float a1, double base_x,
+                                                double base_y, bool invalid, float *obs, double *reward,
+                                                uint8_t *terminated, T *tilt_out) {
+  double t[3];
+  for (int c = 0; c < 3; c++) t[c] = np_pairwise_sum(tan_smem + c * stride, n) / (double)n;
+  double nrm = sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  double tz = t[2] / nrm;
+  tz = fmin(fmax(tz, -1.0), 1.0);
+  double tilt = acos(tz);
+  for (int c = 0; c < 3; c++) { obs[c] = (float)x0[c]; obs[3 + c] = (float)v0[c]; }
+  obs[6] = a0; obs[7] = a1; obs[8] = (float)tilt;
+  if (tilt_out) *tilt_out = (T)tilt;
+  if (reward) {
+    double base_distance = sqrt(base_x * base_x + base_y * base_y);
+    float aa = __fadd_rn(__fmul_rn(a0, a0), __fmul_rn(a1, a1));       // np.dot on float32
+    float pen = __fmul_rn(0.001f, aa);                                  // 1e-3 * float32 -> float32 (NEP 50)
+    double r = -(tilt * tilt + 0.1 * (base_distance * base_distance) + (double)pen);
+    *reward = invalid ? -50.0 : r;
     *terminated = invalid ? 1 : 0;
   }
 }
@@ -696,6 +728,13 @@ __global__ void rod_observe_kernel(const T *state, const float *prev_action, flo
     soft_pendulum_outputs<T>(st + F_TAN * stride, stride, n, (double)st[F_POS * stride],
                              (double)st[F_VEL * stride], pa, false, obs + (size_t)env * obs_dim,
                              nullptr, nullptr);
+  } else if (model == MODEL_SOFT_PENDULUM_3D) {
+    double x0[3], v0[3];
+    for (int c = 0; c < 3; c++) { x0[c] = (double)st[(F_POS + c) * stride]; v0[c] = (double)st[(F_VEL + c) * stride]; }
+    float a0 = prev_action ? prev_action[(size_t)env * action_dim] : 0.0f;
+    float a1 = prev_action ? prev_action[(size_t)env * action_dim + 1] : 0.0f;
+    soft_pendulum_3d_outputs<T>(st + F_TAN * stride, stride, n, x0, v0, a0, a1, 0.0, 0.0, false,
+                                obs + (size_t)env * obs_dim, nullptr, nullptr, (T *)nullptr);
   } else {
     float *o = obs + (size_t)env * obs_dim;
     for (int c = 0; c < 3; c++) {

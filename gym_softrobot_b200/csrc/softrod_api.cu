@@ -94,6 +94,9 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     A.S_over_l[i] = (T)(S[i] / rl);
     A.gdt_cv[i] = (T)(c.gravity[i] * c.dt * (c.damping_constant >= 0.0 ? exp(-c.damping_constant * c.dt) : 1.0));
   }
+  A.base_limit = (T)c.base_limit;
+  A.inv_move_period = (T)(c.base_move_period > 0.0 ? 1.0 / c.base_move_period : 0.0);
+  A.base_step_f32 = (float)c.base_step;
   A.isotropic = 1;  // straight_rod builds circular cross-sections: I1 == I2
   {
     const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
@@ -152,7 +155,7 @@ bool use_packed_kernel(const sr_handle *h) {
     const char *e = getenv("SOFTROD_KERNEL");
     v = (e && strcmp(e, "warp") == 0) ? 0 : 1;
   }
-  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 128;
+  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 256;
 }
 
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
@@ -171,20 +174,27 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
   return SR_OK;
 }
 
-// CTA size of the packed kernel: SOFTROD_PACKED_THREADS={256,320,384} for experiments
-int packed_threads_setting() {
-  static int v = -1;
-  if (v < 0) {
+// CTA size of the packed kernel.  Registers cap the SM at 512 resident threads (128 regs), so the
+// choice is 2 x 256 or 1 x 512; take whichever wastes fewer lanes for this rod length
+// (n = 50: 5 x 51 = 255/256; n = 100: 2 x 101 = 202/256 but 5 x 101 = 505/512).
+// SOFTROD_PACKED_THREADS={256,320,384,512} overrides it for experiments.
+int packed_threads_setting(int n_elem) {
+  static int forced = -1;
+  if (forced < 0) {
     const char *e = getenv("SOFTROD_PACKED_THREADS");
-    v = e ? atoi(e) : 256;
-    if (v != 256 && v != 320 && v != 384) v = 256;
+    forced = e ? atoi(e) : 0;
+    if (forced != 256 && forced != 320 && forced != 384 && forced != 512) forced = 0;
   }
-  return v;
+  if (forced) return forced;
+  const int tpr = n_elem + 1;
+  const double u256 = (double)((256 / tpr) * tpr) / 256.0, u512 = (double)((512 / tpr) * tpr) / 512.0;
+  return (u512 > u256 + 0.02) ? 512 : 256;
 }
 
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_packed_kernel(h)) {
-    const int nt = packed_threads_setting(), mb = min_ctas_setting();
+    const int nt = packed_threads_setting(h->cfg.n_elem), mb = min_ctas_setting();
+    if (nt == 512) return launch_packed<T, 512, 1>(h, A, s);
     if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
     if (nt == 384) return launch_packed<T, 384, 2>(h, A, s);
     if (mb == 3) return launch_packed<T, 256, 3>(h, A, s);
@@ -211,13 +221,20 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   if (cfg->struct_size != (int32_t)sizeof(sr_config))
     return fail(SR_E_INVALID, "sr_create: sr_config.struct_size mismatch (ABI skew)");
   if (cfg->n_env <= 0 || cfg->n_elem < 3) return fail(SR_E_INVALID, "sr_create: n_env > 0 and n_elem >= 3 required");
-  if (cfg->n_elem > 127) return fail(SR_E_INVALID, "sr_create: n_elem <= 127 in this build (one warp per rod, <= 4 elements per lane)");
+  if (cfg->n_elem > 255) return fail(SR_E_INVALID, "sr_create: n_elem <= 255 in this build");
+  if (cfg->n_elem > 127 && cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: faithful math supports n_elem <= 127");
   if (cfg->dtype != SR_DTYPE_F64) return fail(SR_E_INVALID, "sr_create: only SR_DTYPE_F64 is built so far");
-  if (cfg->model != SR_MODEL_ROD && cfg->model != SR_MODEL_SOFT_PENDULUM)
+  if (cfg->model != SR_MODEL_ROD && cfg->model != SR_MODEL_SOFT_PENDULUM && cfg->model != SR_MODEL_SOFT_PENDULUM_3D)
     return fail(SR_E_INVALID, "sr_create: unsupported model");
-  if (cfg->bc_kind < SR_BC_FREE || cfg->bc_kind > SR_BC_PENDULUM_SLIDER)
+  if (cfg->bc_kind < SR_BC_FREE || cfg->bc_kind > SR_BC_MOVING_BASE)
     return fail(SR_E_INVALID, "sr_create: unsupported bc_kind");
-  if (cfg->laplace_filter_order != 0) return fail(SR_E_INVALID, "sr_create: Laplace filter not built yet");
+  if (cfg->laplace_filter_order < 0 || cfg->laplace_filter_order > 64)
+    return fail(SR_E_INVALID, "sr_create: laplace_filter_order out of range");
+  if (cfg->math != SR_MATH_FAST && (cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE ||
+                                    cfg->model == SR_MODEL_SOFT_PENDULUM_3D))
+    return fail(SR_E_INVALID, "sr_create: Laplace filter / moving base are built for SR_MATH_FAST only");
+  if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
+    return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
       !(cfg->youngs_modulus > 0.0))
     return fail(SR_E_INVALID, "sr_create: dt, base_length, base_radius, density, youngs_modulus must be > 0");
@@ -234,9 +251,11 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   h->cfg = *cfg;
   // nodes 0..n need n+1 slots in 32*EPL
   h->epl = (cfg->n_elem + 1 <= 32) ? 1 : (cfg->n_elem + 1 <= 64) ? 2 : 4;
-  h->stride = 32 * h->epl;
+  // the warp-per-rod kernel reads 32*EPL slots per row; longer rods (packed kernel only) round up to 32
+  h->stride = (cfg->n_elem + 1 <= 128) ? 32 * h->epl : 32 * ((cfg->n_elem + 1 + 31) / 32);
   h->elem_size = 8;
   if (cfg->model == SR_MODEL_SOFT_PENDULUM) { h->obs_dim = 4; h->action_dim = 1; }
+  else if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D) { h->obs_dim = 9; h->action_dim = 2; }
   else { h->obs_dim = 6; h->action_dim = 0; }
   const size_t n_env = (size_t)cfg->n_env;
   const size_t state_bytes = n_env * sr::N_FIELDS * h->stride * h->elem_size;
@@ -369,6 +388,13 @@ int sr_get_state(sr_handle *h, sr_state_view *out) {
   out->f_position = sr::F_POS; out->f_velocity = sr::F_VEL; out->f_director = sr::F_DIR;
   out->f_omega = sr::F_OMEGA; out->f_tangents = sr::F_TAN; out->f_kappa = sr::F_KAPPA;
   out->f_sigma = sr::F_SIGMA; out->f_dilatation = sr::F_DIL;
+  return SR_OK;
+}
+
+int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim) {
+  if (!h || !aux_dev || !dim) return fail(SR_E_INVALID, "sr_get_aux: null argument");
+  *aux_dev = h->aux;
+  *dim = sr::AUX_DIM;
   return SR_OK;
 }
 

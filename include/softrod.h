@@ -78,6 +78,10 @@ typedef struct sr_config {
   double shear_modulus; /* <= 0: PyElastica default E/(2(1+0.5)) */
   double gravity[3];
   double damping_constant; /* AnalyticalLinearDamper; < 0 = off */
+  /* SR_MODEL_SOFT_PENDULUM_3D only (soft_pendulum_3d.py:55-56,106-120): the action moves the base by
+   * base_step * action per env-step, clipped to +-base_limit; its velocity is displacement / base_move_period
+   * with base_move_period = step_skip * time_step as computed by the host in double. */
+  double base_step, base_limit, base_move_period;
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -137,6 +141,10 @@ int sr_observe(sr_handle *h, const float *prev_action_dev, float *obs_dev, void 
 int sr_get_state(sr_handle *h, sr_state_view *out);
 /* copy a full state (same layout, device memory) into the handle */
 int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
+
+/* Per-env model scratch, double [n_env][*dim]: SoftPendulum3D keeps the base controller there
+ * (0-2 position, 3-5 velocity, 6 last tilt angle, `info["tilt"]` of soft_pendulum_3d.py:157). */
+int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim);
 
 /* number of kernels this library launched on behalf of the handle so far */
 int64_t sr_launch_count(const sr_handle *h);

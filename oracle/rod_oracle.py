@@ -191,3 +191,57 @@ class OracleSoftPendulum:
         self.prev_action = a
         return (np.array(out[:], dtype=np.float32), rew.value, bool(term.value), bool(trunc.value),
                 {"time": np.float64(self.rod.time), "TimeLimit.truncated": bool(trunc.value)})
+
+
+class OracleSoftPendulum3D:
+    """SoftPendulum3D-v0 on the C oracle: env logic restated from
+    /root/reference/gym_softrobot/envs/soft_pendulum_3d/soft_pendulum_3d.py:60-158 and build.py:43-86."""
+
+    def __init__(self, final_time=5.0, time_step=1.0e-4, recording_fps=25, n_elems=50):
+        self.final_time, self.time_step, self.n_elems = final_time, time_step, n_elems
+        self.step_skip = int(1.0 / (recording_fps * time_step))
+        self.base_step, self.base_limit = 1e-3, 0.5
+        self.rod = None
+
+    def reset(self, seed=None, tilt_deg=None):
+        if tilt_deg is None:
+            tilt_deg = np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed))).uniform(-1.0, 1.0)
+        tilt = np.deg2rad(tilt_deg)
+        direction = np.array([np.sin(tilt), 0.0, np.cos(tilt)])
+        normal = np.array([0.0, 1.0, 0.0])
+        if self.rod is not None:
+            self.rod.close()
+        self.rod = OracleRod(self.n_elems, np.zeros(3), direction, normal, 1.0, 0.1, 4000.0, 1e6, self.time_step,
+                             gravity=(0.0, 0.0, -9.80665), damping_constant=1.0, laplace_filter_order=7,
+                             bc_kind=BC_MOVING_BASE)
+        self.position, self.velocity = np.zeros(3), np.zeros(3)
+        self.prev_action = np.zeros(2, dtype=np.float32)
+        return self.get_state(), {}
+
+    def _tilt_angle(self):
+        tangent = np.mean(self.rod.tangents, axis=1)
+        tangent /= np.linalg.norm(tangent)
+        return float(np.arccos(np.clip(tangent[2], -1.0, 1.0)))
+
+    def get_state(self):
+        return np.hstack([self.rod.position_collection[:, 0], self.rod.velocity_collection[:, 0],
+                          self.prev_action, self._tilt_angle()]).astype(np.float32)
+
+    def step(self, action):
+        action = np.asarray(action, dtype=np.float32)
+        displacement = self.base_step * action
+        next_position = self.position.copy()
+        next_position[:2] = np.clip(next_position[:2] + displacement, -self.base_limit, self.base_limit)
+        actual = next_position - self.position
+        self.position[:] = next_position
+        self.velocity[:] = actual / (self.step_skip * self.time_step)
+        self.prev_action[:] = action
+        self.rod.substeps(self.step_skip, base_pos=self.position, base_vel=self.velocity)
+        invalid = bool(np.isnan(self.rod.position_collection).any() or np.isnan(self.rod.velocity_collection).any())
+        tilt = self._tilt_angle()
+        base_distance = np.linalg.norm(self.position[:2])
+        reward = -float(tilt ** 2 + 0.1 * base_distance ** 2 + 1e-3 * np.dot(action, action))
+        if invalid:
+            reward = -50.0
+        t = self.rod.time
+        return self.get_state(), reward, invalid, bool(t >= self.final_time), {"time": np.float64(t), "tilt": tilt}

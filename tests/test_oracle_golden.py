@@ -137,3 +137,18 @@ def test_integrator_is_second_order():
     a, b, c = run(2e-4), run(1e-4), run(5e-5)
     ratio = np.abs(a - b).max() / np.abs(b - c).max()
     assert 3.5 < ratio < 4.5, ratio
+
+
+def test_c_oracle_3d_matches_golden(golden_dir):
+    """SoftPendulum3D (moving base + Laplace filter): C oracle vs reference-env-on-shim fixture."""
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_3d_seed42.npz"))
+    env = ro.OracleSoftPendulum3D()
+    obs0, _ = env.reset(seed=42)
+    assert np.array_equal(obs0, g["obs0"])
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        for gk, fk in FIELDS.items():
+            assert rel(getattr(env.rod, fk), g[f"state{i + 1}/{gk}"]) < 1e-9, (i, gk)
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-6, atol=1e-7)
+        assert abs(r - g["reward"][i]) < 1e-12 and abs(info["tilt"] - g["tilt"][i]) < 1e-12
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))

@@ -211,3 +211,94 @@ def test_free_fall_and_nan_guard():
     obs, rew, term = h.step_host(None, 2)
     assert list(term) == [0, 1, 0]
     h.close()
+
+
+def _tilted_init(n_env, seed=42, max_deg=5.0):
+    """Config 3 of BASELINE.json: horizontal rod, per-env tilt of +-5 degrees about z (seeded)."""
+    ang = np.deg2rad(np.array([np.random.Generator(np.random.PCG64(np.random.SeedSequence(seed + i))).uniform(
+        -max_deg, max_deg) for i in range(n_env)]))
+    init = np.zeros((n_env, 9))
+    init[:, 3], init[:, 4] = np.cos(ang), np.sin(ang)      # direction
+    init[:, 6], init[:, 7] = -np.sin(ang), np.cos(ang)     # normal (perpendicular, in plane)
+    return init
+
+
+@pytest.mark.parametrize("n_elem,dt,radius", [(100, 5e-5, 0.025), (20, 1e-4, 0.05), (63, 5e-5, 0.03), (200, 2e-5, 0.025)])
+def test_generic_rod_vs_oracle(n_elem, dt, radius):
+    """BASELINE config 3 family: clamped rod (OneEndFixedBC) + gravity + analytical damping, no action."""
+    import rod_oracle as ro
+    nat = _native()
+    n_env = 7
+    init = _tilted_init(n_env)
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elem, dt=dt, base_length=1.0, base_radius=radius,
+                   density=1000.0, youngs_modulus=1e6, gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3,
+                   bc_kind=nat.BC_ONE_END_FIXED)
+    h.reset_host(init)
+    rods = [ro.OracleRod(n_elem, init[i, 0:3], init[i, 3:6], init[i, 6:9], 1.0, radius, 1000.0, 1e6, dt,
+                         gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3, bc_kind=ro.BC_ONE_END_FIXED)
+            for i in range(n_env)]
+    for chunk in (400, 600):   # 1000 substeps in two launches
+        obs, rew, term = h.step_host(None, chunk)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        for i, r in enumerate(rods):
+            r.substeps(chunk)
+            for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+                err = rel(f[name][i], getattr(r, name))
+                assert err < TOL, f"n={n_elem} env={i} {name}: {err:.3e}"
+            np.testing.assert_allclose(obs[i, :3], r.position_collection[:, -1], rtol=2e-6, atol=1e-7)
+        assert term.sum() == 0
+    h.close()
+
+
+def test_soft_pendulum_3d_golden(golden_dir):
+    """§8 f1: SoftPendulum3D-v0 through the Gymnasium facade vs the reference-env-on-shim fixture."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "soft_pendulum_3d_seed42.npz"))
+    env = gsb.make("SoftPendulum3D-v0")
+    obs0, _ = env.reset(seed=42)
+    assert obs0.dtype == np.float32 and obs0.shape == (9,)
+    np.testing.assert_array_equal(obs0, g["obs0"])
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        st = env.rod_state()
+        for gk, fk in FIELDS.items():
+            if gk in ("kappa", "sigma"):
+                continue
+            err = rel(st[fk], g[f"state{i + 1}/{gk}"])
+            assert err < TOL, f"step {i} field {gk} rel err {err:.3e}"
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=2e-6, atol=1e-7)
+        assert abs(r - g["reward"][i]) < 1e-9 and abs(info["tilt"] - g["tilt"][i]) < 1e-9
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+        assert isinstance(r, float) and isinstance(te, bool) and isinstance(tr, bool)
+    with pytest.raises(ValueError):
+        env.step(np.array([2.0, 0.0], dtype=np.float32))
+    env.close()
+
+
+def test_soft_pendulum_3d_batched_vs_oracle():
+    import torch
+    import rod_oracle
+    import gym_softrobot_b200 as gsb
+    n_env = 300
+    env = gsb.make_vec("SoftPendulum3D-v0", n_env, autoreset=False)
+    obs, _ = env.reset(seed=7)
+    check = [0, 1, 150, 299]
+    oracles = {i: rod_oracle.OracleSoftPendulum3D() for i in check}
+    for i, o in oracles.items():
+        o_obs, _ = o.reset(seed=7 + i)
+        np.testing.assert_array_equal(obs[i].cpu().numpy(), o_obs)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for step in range(3):
+        a = (torch.rand((n_env, 2), generator=gen, device="cuda") * 2 - 1).float()
+        obs, rew, term, trunc, info = env.step(a)
+        f = {k: v.cpu().numpy() for k, v in env.fields().items()}
+        a_np = a.cpu().numpy()
+        for i, o in oracles.items():
+            ob, r, te, tr, oi = o.step(a_np[i])
+            for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+                err = rel(f[name][i], getattr(o.rod, name))
+                assert err < TOL, f"env={i} step={step} {name}: {err:.3e}"
+            np.testing.assert_allclose(obs[i].cpu().numpy(), ob, rtol=2e-6, atol=1e-7)
+            assert abs(float(rew[i]) - r) < 1e-9 and bool(term[i]) == te and bool(trunc[i]) == tr
+            assert abs(float(info["tilt"][i]) - oi["tilt"]) < 1e-9
+    env.close()
