@@ -216,11 +216,11 @@ class Handle:
         return v
 
     def state_tensor(self):
-        """torch view [n_env, n_fields, stride] (float64) of the live SoA state."""
+        """torch view [n_env, n_fields, stride] (float64 / float32 per dtype) of the live SoA state."""
         import torch
         if self._state_tensor is None:
             v = self.state_view()
-            mem = _DevMem(v.base, (v.n_env, v.n_fields, v.stride), "<f8")
+            mem = _DevMem(v.base, (v.n_env, v.n_fields, v.stride), "<f8" if v.elem_size == 8 else "<f4")
             self._state_tensor = torch.as_tensor(mem, device=f"cuda:{self.device}")
             self._view = v
         return self._state_tensor
@@ -245,7 +245,8 @@ class Handle:
         import torch
         ptr, dim = C.c_void_p(), C.c_int32()
         _check(self._lib.sr_get_aux(self._h, C.byref(ptr), C.byref(dim)))
-        return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), "<f8"), device=f"cuda:{self.device}")
+        ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), ts), device=f"cuda:{self.device}")
 
     def set_state_from(self, other: "Handle"):
         v = other.state_view()

@@ -22,7 +22,10 @@ constexpr int PACKED_MAX_THREADS = 512;
 // shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide
 constexpr int packed_smem_words(int nt) { return 21 * (nt + 2); }
 
-template <typename T, int NT, int MINB>
+// LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
+// (SoftPendulum3D); kept out of the instantiation used by the other models so they do not pay
+// their registers / code size.
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,7 +87,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     } else {
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
-      if (A.bc_kind == BC_ONE_END_FIXED) {
+      if (!MOVING || A.bc_kind == BC_ONE_END_FIXED) {
 #pragma unroll
         for (int c = 0; c < 3; c++) x[c] = bc[c];
       } else {
@@ -104,13 +107,13 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       }
     }
   }
-  const bool moving = bc_thread && A.bc_kind == BC_MOVING_BASE;
+  const bool moving = MOVING && bc_thread && A.bc_kind == BC_MOVING_BASE;
 
   auto constrain_rates = [&]() {
     if (bc_thread) {
       if (A.bc_kind == BC_PENDULUM_SLIDER) {
         v[1] = T(0); v[2] = T(0); w[0] = T(0); w[2] = T(0);
-      } else if (A.bc_kind == BC_ONE_END_FIXED) {
+      } else if (!MOVING || A.bc_kind == BC_ONE_END_FIXED) {
 #pragma unroll
         for (int c = 0; c < 3; c++) { v[c] = T(0); w[c] = T(0); }
       } else {
@@ -205,10 +208,16 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
     T u = fma(T(-0.25), tr, T(0.75 + 0.5e-10));   // sin^2(theta_ref/2) with the 1e-10 guard
     if (!vor_ok) u = T(5e-11);
+    constexpr bool F64 = sizeof(T) == 8;
+    if (!F64) u = fmax(u, T(0));                  // FP32: the guard is below epsilon; keep u >= 0
     T fac;
     if (!__any_sync(FULL, !(u <= T(kSmallBendU)))) {
-      T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
-      fac = theta_over_sin(A.poly, u) * fma(T(0.5e-14), cot, T(-0.5));
+      if (F64) {
+        T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
+        fac = theta_over_sin(A.poly, u) * fma(T(0.5e-14), cot, T(-0.5));
+      } else {
+        fac = T(-0.5) * theta_over_sin(A.poly, u);   // the 1e-14 cot(theta) term is < 1e-9: invisible in FP32
+      }
     } else {
       fac = bend_factor_ref<T>(u);
     }
@@ -242,6 +251,24 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       sh_N[i * RS + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
       tql[i] = fma(fma(pw[i], ede, G[i]), inv_e, Pi);
     }
+    // rotational damper coefficients c_w^e = c_w exp((e-1) ln c_w): only need e, so they are
+    // evaluated here, ahead of the barrier, off the critical path of the dynamic step
+    T cw0 = T(1), cw1 = T(1), cw2 = T(1);
+    if (A.damping_on) {
+      T em1 = e - T(1);
+      T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
+      bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
+                 !(fabs_(z2) <= T(kSmallExpZ));
+      if (!__any_sync(FULL, big)) {
+        cw0 = A.c_w[0] * exp_small(A.poly, z0);
+        cw2 = A.c_w[2] * exp_small(A.poly, z2);
+        cw1 = A.isotropic ? cw0 : A.c_w[1] * exp_small(A.poly, z1);
+      } else {
+        cw0 = exp_ref<T>(e * A.logc_w[0]);
+        cw1 = exp_ref<T>(e * A.logc_w[1]);
+        cw2 = exp_ref<T>(e * A.logc_w[2]);
+      }
+    }
     if (last) {
       // stale observables of the reference: last force evaluation
       if (active) {
@@ -271,24 +298,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 
     // ---- rate constraints and dissipation ------------------------------------------------
     auto dampen = [&]() {
-      if (A.damping_on) {
-        T em1 = e - T(1);
-        T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
-        bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
-                   !(fabs_(z2) <= T(kSmallExpZ));
-        T cw0, cw1, cw2;
-        if (!__any_sync(FULL, big)) {
-          cw0 = A.c_w[0] * exp_small(A.poly, z0);
-          cw2 = A.c_w[2] * exp_small(A.poly, z2);
-          cw1 = A.isotropic ? cw0 : A.c_w[1] * exp_small(A.poly, z1);
-        } else {
-          cw0 = exp_ref<T>(e * A.logc_w[0]);
-          cw1 = exp_ref<T>(e * A.logc_w[1]);
-          cw2 = exp_ref<T>(e * A.logc_w[2]);
-        }
-        w[0] *= cw0; w[1] *= cw1; w[2] *= cw2;
-      }
-      if (A.laplace_order > 0) {
+      if (A.damping_on) { w[0] *= cw0; w[1] *= cw1; w[2] *= cw2; }
+      if (LAPLACE && A.laplace_order > 0) {
         // LaplaceDissipationFilter (elastica/dissipation.py:nb_filter_rate): p passes of
         // f <- (-f[k+1] - f[k-1] + 2 f[k]) / 4 on interior nodes / elements, ends held at 0; rate -= f.
         // Two smem buffers alternate (x,v rows / first six Q rows), one barrier per pass.
@@ -358,7 +369,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (A.model == MODEL_SOFT_PENDULUM) {
       soft_pendulum_outputs<T>(sh_x + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
                                A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
-    } else if (A.model == MODEL_SOFT_PENDULUM_3D) {
+    } else if (MOVING && A.model == MODEL_SOFT_PENDULUM_3D) {
       const double x0[3] = {(double)x[0], (double)x[1], (double)x[2]};
       const double v0[3] = {(double)v[0], (double)v[1], (double)v[2]};
       T *aux = A.aux + (size_t)env * AUX_DIM;

@@ -154,9 +154,11 @@ __device__ __forceinline__ void rotate_directors_fast(const PolyCoef<T> &C, T a0
                                                       T (&Q)[9]) {
   T A, B;
   sinc_cosc(C, q, A, B);
-  T rho = fma(-eps, rsqrt_approx(fma(eps, eps, q)), T(1.0));
-  A *= rho;
-  B *= rho * rho;
+  if (sizeof(T) == 8) {   // a 1e-14 rad shortening is far below FP32 resolution
+    T rho = fma(-eps, rsqrt_approx(fma(eps, eps, q)), T(1.0));
+    A *= rho;
+    B *= rho * rho;
+  }
   T Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
   T Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
   T D00 = -fma(Ba1, a1, Ba2 * a2), D11 = -fma(Ba0, a0, Ba2 * a2), D22 = -fma(Ba0, a0, Ba1 * a1);
@@ -179,6 +181,7 @@ __device__ __forceinline__ void rotate_directors_fast(const PolyCoef<T> &C, T a0
 // large-bend fallback of the fast path.
 template <typename T> __device__ __noinline__ T bend_factor_ref(T u) {
   T theta = acos_(T(1.0) - T(2.0) * u);
+  if (sizeof(T) == 4 && !(theta > T(1e-3))) return T(-0.5) * (T(1.0) + theta * theta * T(1.0 / 6.0));
   return T(-0.5) * theta / sin_(theta + T(1e-14));
 }
 template <typename T> __device__ __noinline__ T exp_ref(T x) { return exp_(x); }

@@ -158,11 +158,12 @@ bool use_packed_kernel(const sr_handle *h) {
   return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 256;
 }
 
-template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING>
+int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / (A.n_elem + 1);
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
   const size_t smem = (size_t)sr::packed_smem_words(NT) * sizeof(T);
-  auto kern = sr::rod_packed_kernel<T, NT, MINB>;
+  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -172,6 +173,13 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
   h->launches++;
   SR_CUDA(cudaGetLastError());
   return SR_OK;
+}
+
+template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
+  return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
+             ? launch_packed_impl<T, NT, MINB, true, true>(h, A, s)
+             : launch_packed_impl<T, NT, MINB, false, false>(h, A, s);
 }
 
 // CTA size of the packed kernel.  Registers cap the SM at 512 resident threads (128 regs), so the
@@ -223,7 +231,9 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   if (cfg->n_env <= 0 || cfg->n_elem < 3) return fail(SR_E_INVALID, "sr_create: n_env > 0 and n_elem >= 3 required");
   if (cfg->n_elem > 255) return fail(SR_E_INVALID, "sr_create: n_elem <= 255 in this build");
   if (cfg->n_elem > 127 && cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: faithful math supports n_elem <= 127");
-  if (cfg->dtype != SR_DTYPE_F64) return fail(SR_E_INVALID, "sr_create: only SR_DTYPE_F64 is built so far");
+  if (cfg->dtype != SR_DTYPE_F64 && cfg->dtype != SR_DTYPE_F32) return fail(SR_E_INVALID, "sr_create: bad dtype");
+  if (cfg->dtype == SR_DTYPE_F32 && (cfg->math != SR_MATH_FAST || cfg->n_elem > 255))
+    return fail(SR_E_INVALID, "sr_create: SR_DTYPE_F32 is built for SR_MATH_FAST (packed kernel) only");
   if (cfg->model != SR_MODEL_ROD && cfg->model != SR_MODEL_SOFT_PENDULUM && cfg->model != SR_MODEL_SOFT_PENDULUM_3D)
     return fail(SR_E_INVALID, "sr_create: unsupported model");
   if (cfg->bc_kind < SR_BC_FREE || cfg->bc_kind > SR_BC_MOVING_BASE)
@@ -253,7 +263,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   h->epl = (cfg->n_elem + 1 <= 32) ? 1 : (cfg->n_elem + 1 <= 64) ? 2 : 4;
   // the warp-per-rod kernel reads 32*EPL slots per row; longer rods (packed kernel only) round up to 32
   h->stride = (cfg->n_elem + 1 <= 128) ? 32 * h->epl : 32 * ((cfg->n_elem + 1 + 31) / 32);
-  h->elem_size = 8;
+  h->elem_size = cfg->dtype == SR_DTYPE_F32 ? 4 : 8;
   if (cfg->model == SR_MODEL_SOFT_PENDULUM) { h->obs_dim = 4; h->action_dim = 1; }
   else if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D) { h->obs_dim = 9; h->action_dim = 2; }
   else { h->obs_dim = 6; h->action_dim = 0; }
@@ -283,6 +293,9 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   fill_args<double>(*cfg, h->stride, h->a64);
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim;
+  fill_args<float>(*cfg, h->stride, h->a32);
+  h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
+  h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim;
   *out = h;
   return SR_OK;
 }
@@ -308,9 +321,14 @@ int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init
   if (n < 0 || n > h->cfg.n_env) return fail(SR_E_INVALID, "sr_reset: n out of range");
   if (n == 0) return SR_OK;
   SR_CUDA(cudaSetDevice(h->cfg.device));
-  sr::rod_reset_kernel<double><<<n, 64, 0, (cudaStream_t)stream>>>(
-      (double *)h->state, (double *)h->bc, (double *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-      h->stride, h->cfg.base_length);
+  if (h->cfg.dtype == SR_DTYPE_F32)
+    sr::rod_reset_kernel<float><<<n, 64, 0, (cudaStream_t)stream>>>(
+        (float *)h->state, (float *)h->bc, (float *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
+        h->stride, h->cfg.base_length);
+  else
+    sr::rod_reset_kernel<double><<<n, 64, 0, (cudaStream_t)stream>>>(
+        (double *)h->state, (double *)h->bc, (double *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
+        h->stride, h->cfg.base_length);
   h->launches++;
   SR_CUDA(cudaGetLastError());
   return SR_OK;
@@ -322,6 +340,14 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
   if (h->action_dim > 0 && !action_dev) return fail(SR_E_INVALID, "sr_step: action required for this model");
   if (n_substeps < 0) return fail(SR_E_INVALID, "sr_step: n_substeps < 0");
   SR_CUDA(cudaSetDevice(h->cfg.device));
+  if (h->cfg.dtype == SR_DTYPE_F32) {
+    sr::RodArgs<float> A = h->a32;
+    A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
+    A.n_substeps = n_substeps;
+    const int nt = packed_threads_setting(h->cfg.n_elem);
+    return nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
+                     : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
+  }
   sr::RodArgs<double> A = h->a64;
   A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
   A.n_substeps = n_substeps;
@@ -332,9 +358,14 @@ int sr_observe(sr_handle *h, const float *prev_action_dev, float *obs_dev, void 
   if (!h || !obs_dev) return fail(SR_E_INVALID, "sr_observe: null argument");
   SR_CUDA(cudaSetDevice(h->cfg.device));
   int bs = 128, grid = (h->cfg.n_env + bs - 1) / bs;
-  sr::rod_observe_kernel<double><<<grid, bs, 0, (cudaStream_t)stream>>>(
-      (const double *)h->state, prev_action_dev, obs_dev, h->cfg.n_env, h->cfg.n_elem, h->stride,
-      h->cfg.model, h->action_dim, h->obs_dim);
+  if (h->cfg.dtype == SR_DTYPE_F32)
+    sr::rod_observe_kernel<float><<<grid, bs, 0, (cudaStream_t)stream>>>(
+        (const float *)h->state, prev_action_dev, obs_dev, h->cfg.n_env, h->cfg.n_elem, h->stride,
+        h->cfg.model, h->action_dim, h->obs_dim);
+  else
+    sr::rod_observe_kernel<double><<<grid, bs, 0, (cudaStream_t)stream>>>(
+        (const double *)h->state, prev_action_dev, obs_dev, h->cfg.n_env, h->cfg.n_elem, h->stride,
+        h->cfg.model, h->action_dim, h->obs_dim);
   h->launches++;
   SR_CUDA(cudaGetLastError());
   return SR_OK;
@@ -393,7 +424,7 @@ int sr_get_state(sr_handle *h, sr_state_view *out) {
 
 int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim) {
   if (!h || !aux_dev || !dim) return fail(SR_E_INVALID, "sr_get_aux: null argument");
-  *aux_dev = h->aux;
+  *aux_dev = h->aux;   /* element type follows sr_config.dtype */
   *dim = sr::AUX_DIM;
   return SR_OK;
 }

@@ -40,11 +40,11 @@ def pendulum_init_params(u01):
     return init
 
 
-def _make_handle(n_env, n_elems, time_step, device, math):
+def _make_handle(n_env, n_elems, time_step, device, math, dtype=nat.DTYPE_F64):
     return nat.Handle(
         model=nat.MODEL_SOFT_PENDULUM, n_env=n_env, n_elem=n_elems, dt=time_step,
         gravity=_GRAVITY, damping_constant=_DAMPING_CONSTANT, bc_kind=nat.BC_PENDULUM_SLIDER,
-        point_force_on_base=True, damping_before_constraints=True, device=device, math=math,
+        point_force_on_base=True, damping_before_constraints=True, device=device, math=math, dtype=dtype,
         **_DEFAULT_SCALE_LENGTH, **_PENDULUM_PROPERTIES,
     )
 
@@ -147,7 +147,7 @@ class SoftPendulumVectorEnv:
 
     def __init__(self, n_env, final_time=5.0, time_step=1.0e-4, recording_fps=25, n_elems=50,
                  device: int = 0, math: int = nat.MATH_FAST, autoreset: bool = True,
-                 env_offset: int = 0):
+                 env_offset: int = 0, dtype: str = "float64"):
         import torch
         self.torch = torch
         self.n_env, self.n_elems = n_env, n_elems
@@ -158,7 +158,9 @@ class SoftPendulumVectorEnv:
         self.autoreset = autoreset
         self.single_action_space = Box(np.ones(1) * (-22), np.ones(1) * 22, shape=(1,), dtype=np.float32)
         self.single_observation_space = Box(-np.inf, np.inf, shape=(4,), dtype=np.float32)
-        self.handle = _make_handle(n_env, n_elems, time_step, device, math)
+        # FP64 matches PyElastica (1e-9); "float32" is the optional fast mode (state to ~1e-4)
+        self.handle = _make_handle(n_env, n_elems, time_step, device, math,
+                                   nat.DTYPE_F32 if dtype == "float32" else nat.DTYPE_F64)
         self.obs = torch.empty((n_env, 4), dtype=torch.float32, device=self.device)
         self.reward = torch.empty(n_env, dtype=torch.float64, device=self.device)
         self.terminated = torch.empty(n_env, dtype=torch.uint8, device=self.device)

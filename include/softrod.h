@@ -142,7 +142,7 @@ int sr_get_state(sr_handle *h, sr_state_view *out);
 /* copy a full state (same layout, device memory) into the handle */
 int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
 
-/* Per-env model scratch, double [n_env][*dim]: SoftPendulum3D keeps the base controller there
+/* Per-env model scratch, [n_env][*dim] of the handle's dtype: SoftPendulum3D keeps the base controller there
  * (0-2 position, 3-5 velocity, 6 last tilt angle, `info["tilt"]` of soft_pendulum_3d.py:157). */
 int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim);
 

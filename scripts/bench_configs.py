@@ -1,0 +1,49 @@
+"""Throughput of the BASELINE.json configs other than the headline one (diagnostic table for BASELINE.md)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np, torch
+import gym_softrobot_b200 as g
+from gym_softrobot_b200 import _native as nat
+
+def timed(step_fn, K=10, W=3):
+    for _ in range(W): step_fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in ev:
+        a.record(); step_fn(); b.record()
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in ev) / K * 1e-3
+
+peak = nat.measure_fp64_peak(0)
+rows = []
+def report(name, n_env, n_elem, K, sec, flop):
+    es = n_env * n_elem * K / sec
+    rows.append(dict(config=name, n_env=n_env, n_elem=n_elem, substeps=K, ms_per_step=sec * 1e3, env_steps_per_s=n_env / sec,
+                     elem_substeps_per_s=es, fp64_frac=es * flop / 1e12 / peak, flop_per_elem_substep=flop))
+    print(json.dumps(rows[-1]), flush=True)
+
+# config 2 (headline) at larger batches
+for n_env in (4096, 16384, 65536):
+    env = g.make_vec("SoftPendulum-v0", n_env, autoreset=False); env.reset(seed=42)
+    a = (torch.rand((n_env, 1), device="cuda") * 44 - 22).float()
+    report("SoftPendulum-v0", n_env, 50, 400, timed(lambda: env.handle.step(a, 400, env.obs, env.reward, env.terminated)), 440)
+    env.close()
+# config 3: clamped rod n=100, gravity + damping, 8192 envs per GPU
+n_env = 8192
+h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=100, dt=5e-5, base_length=1.0, base_radius=0.025, density=1000.0,
+               youngs_modulus=1e6, gravity=(0, -9.80665, 0), damping_constant=2e-3, bc_kind=nat.BC_ONE_END_FIXED)
+ang = np.deg2rad(np.random.default_rng(42).uniform(-5, 5, n_env)); init = np.zeros((n_env, 9))
+init[:, 3], init[:, 4], init[:, 6], init[:, 7] = np.cos(ang), np.sin(ang), -np.sin(ang), np.cos(ang)
+h.reset_host(init)
+obs = torch.empty((n_env, 6), dtype=torch.float32, device="cuda"); rew = torch.empty(n_env, dtype=torch.float64, device="cuda"); term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+report("rod n=100 clamped (config 3, per GPU)", n_env, 100, 400, timed(lambda: h.step(None, 400, obs, rew, term)), 440)
+assert int(term.sum()) == 0
+h.close()
+# f1: SoftPendulum3D
+n_env = 4096
+env = g.make_vec("SoftPendulum3D-v0", n_env, autoreset=False); env.reset(seed=42)
+a = (torch.rand((n_env, 2), device="cuda") * 2 - 1).float()
+report("SoftPendulum3D-v0", n_env, 50, 400, timed(lambda: env.handle.step(a, 400, env.obs, env.reward, env.terminated)), 440 + 168)
+env.close()
+print("fp64 peak", peak)
