@@ -12,10 +12,12 @@ from .version import VERSION as __version__
 REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumEnv", {}),
     "SoftPendulum3D-v0": ("gym_softrobot_b200.envs.soft_pendulum_3d:SoftPendulum3DEnv", {}),
+    "OctoArmSingle-v0": ("gym_softrobot_b200.envs.arm_single:ArmSingleEnv", {}),
 }
 VECTOR_REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
     "SoftPendulum3D-v0": ("gym_softrobot_b200.envs.soft_pendulum_3d:SoftPendulum3DVectorEnv", {}),
+    "OctoArmSingle-v0": ("gym_softrobot_b200.envs.arm_single:ArmSingleVectorEnv", {}),
 }
 
 

@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_launch_count", "sr_measure_fp64_peak",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_rest_kappa", "sr_launch_count", "sr_measure_fp64_peak",
 ]
 
 
@@ -35,6 +35,10 @@ class SrConfig(C.Structure):
         ("density", C.c_double), ("youngs_modulus", C.c_double), ("shear_modulus", C.c_double),
         ("gravity", C.c_double * 3), ("damping_constant", C.c_double),
         ("base_step", C.c_double), ("base_limit", C.c_double), ("base_move_period", C.c_double),
+        ("contact_on", C.c_int32), ("contact_before_forcing", C.c_int32),
+        ("plane_origin", C.c_double * 3), ("plane_normal", C.c_double * 3),
+        ("contact_k", C.c_double), ("contact_nu", C.c_double), ("slip_velocity_tol", C.c_double),
+        ("surface_tol", C.c_double), ("static_mu", C.c_double * 3), ("kinetic_mu", C.c_double * 3),
     ]
 
 
@@ -81,6 +85,7 @@ def load_library():
     L.sr_get_state.argtypes = [C.c_void_p, C.POINTER(SrStateView)]
     L.sr_set_state.argtypes = [C.c_void_p, C.POINTER(SrStateView), C.c_void_p]
     L.sr_get_aux.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_launch_count.argtypes = [C.c_void_p]
     L.sr_launch_count.restype = C.c_int64
     L.sr_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -118,7 +123,7 @@ class Handle:
                  shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
                  point_force_on_base=False, damping_before_constraints=True, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
-                 base_move_period=0.0):
+                 base_move_period=0.0, contact=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -132,6 +137,16 @@ class Handle:
         cfg.gravity[:] = [float(g) for g in gravity]
         cfg.damping_constant = damping_constant
         cfg.base_step, cfg.base_limit, cfg.base_move_period = base_step, base_limit, base_move_period
+        if contact is not None:   # plane_origin, plane_normal, k, nu, slip_velocity_tol, static_mu, kinetic_mu
+            cfg.contact_on = 1
+            cfg.contact_before_forcing = int(contact.get("before_forcing", True))
+            cfg.plane_origin[:] = [float(v) for v in contact["plane_origin"]]
+            cfg.plane_normal[:] = [float(v) for v in contact["plane_normal"]]
+            cfg.contact_k, cfg.contact_nu = contact["k"], contact["nu"]
+            cfg.slip_velocity_tol = contact["slip_velocity_tol"]
+            cfg.surface_tol = contact.get("surface_tol", 1e-4)   # PyElastica's fixed surface_tol
+            cfg.static_mu[:] = [float(v) for v in contact["static_mu"]]
+            cfg.kinetic_mu[:] = [float(v) for v in contact["kinetic_mu"]]
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(self._lib.sr_create(C.byref(cfg), C.byref(self._h)))
@@ -247,6 +262,16 @@ class Handle:
         _check(self._lib.sr_get_aux(self._h, C.byref(ptr), C.byref(dim)))
         ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
         return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), ts), device=f"cuda:{self.device}")
+
+    def rest_kappa_tensor(self):
+        """torch view [n_env, 3, n_elem-1] of the per-env rest curvature (sr_get_rest_kappa)."""
+        import torch
+        ptr = C.c_void_p()
+        _check(self._lib.sr_get_rest_kappa(self._h, C.byref(ptr)))
+        v = self.state_view()
+        ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
+        t = torch.as_tensor(_DevMem(ptr.value, (self.n_env, 3, v.stride), ts), device=f"cuda:{self.device}")
+        return t[:, :, :self.n_elem - 1]
 
     def set_state_from(self, other: "Handle"):
         v = other.state_view()

@@ -24,8 +24,9 @@ constexpr int packed_smem_words(int nt) { return 21 * (nt + 2); }
 
 // LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
 // (SoftPendulum3D); kept out of the instantiation used by the other models so they do not pay
-// their registers / code size.
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING>
+// their registers / code size.  CONTACT: plane contact with anisotropic friction and per-env rest
+// curvature (octopus-arm models): two more neighbour exchanges per substep.
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -65,6 +66,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const T gmask = active ? T(1) : T(0);
   const T dte = elem_ok ? A.dt : T(0);
 
+  T rk[3] = {T(0), T(0), T(0)};   // rest curvature at Voronoi point j (actuation), constant during a launch
+  if (CONTACT && A.rest_kappa && vor_ok) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) rk[c] = A.rest_kappa[((size_t)env * 3 + c) * stride + j];
+  }
   T act0 = T(0), base_vx = T(0), base_vy = T(0);
   float act_f0 = 0.0f, act_f1 = 0.0f;
   if (active && A.action_dim > 0) { act_f0 = A.action[(size_t)env * A.action_dim]; act0 = (T)act_f0; }
@@ -224,7 +230,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T kp[3], tau[3], kxt[3];
     T fs = fac * A.inv_rest_vor;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { kp[i] = vec[i] * fs; tau[i] = A.B[i] * kp[i]; }
+    for (int i = 0; i < 3; i++) { kp[i] = vec[i] * fs; tau[i] = A.B[i] * (CONTACT ? kp[i] - rk[i] : kp[i]); }
     cross3(kp, tau, kxt);
     T eps = (T(0.5) * (lgn + lg)) * A.inv_rest_vor;
     T ie3 = rcp_nr(eps * eps * eps);
@@ -283,17 +289,122 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
     __syncthreads();
 
-    // ---- add the left neighbour's share, dynamic step -------------------------------------
+    // ---- add the left neighbour's share, [contact], dynamic step ---------------------------
     T dtee = dte * e;
+    T fint[3], tq[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      T fi = sfl[i] - sh_s[i * RS + t_prev];
+      fint[i] = sfl[i] - sh_s[i * RS + t_prev];
+      tq[i] = tql[i] + sh_N[i * RS + t_prev];
+    }
+    if (CONTACT && A.contact_on) {
+      // RodPlaneContactWithAnisotropicFriction (elastica/_contact_functions.py), per element j
+      // between nodes j and j+1.  Stage 1: normal response + kinetic friction from the nodal forces
+      // accumulated so far; stage 2: static friction from the forces INCLUDING stage 1 of both
+      // neighbours (nodal forces mix adjacent elements), hence two more exchanges.
+      // stage-1 loads travel through the (now free) Q rows; the final loads through the s rows, which
+      // nobody overwrites before the next strain phase (the Q rows are re-published right after this step)
+      T *sh_c1 = sh_Q, *sh_c12 = sh_s;
+      const T *N = A.plane_normal;
+      const bool has_left = active && j > 0, has_right = active && j + 1 < n;
+      const T m0 = A.mass * ((j == 0) ? T(0.5) : T(1)), m1 = A.mass * ((j + 1 == n) ? T(0.5) : T(1));
+      T etf[3], evel[3], xe[3], t[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T f0 = fint[i], f1 = sh_s[i * RS + t_next] - sfl[i];   // internal force on nodes j, j+1
+        if (!A.contact_before_forcing) {                       // external forces so far: gravity (+ base force)
+          f0 += A.g[i] * m0; f1 += A.g[i] * m1;
+          if (i == 0 && A.point_force && first) f0 = fint[i] + act0;
+        }
+        etf[i] = T(0.5) * (f0 + f1) + ((j == 0) ? T(0.5) * f0 : T(0)) + ((j + 1 == n) ? T(0.5) * f1 : T(0));
+        T v1 = sh_v[i * RS + t_next];
+        evel[i] = (m1 * v1 + m0 * v[i]) / (m1 + m0);
+        xe[i] = x[i] + T(0.5) * dx[i];
+        t[i] = dx[i] * ilg;
+      }
+      T rad = sqrt_(A.vol_over_pi * ilg);
+      T fn = dot3(N, etf), dist = N[0] * (xe[0] - A.plane_origin[0]) + N[1] * (xe[1] - A.plane_origin[1]) +
+                                  N[2] * (xe[2] - A.plane_origin[2]);
+      T gap = dist - rad, pen = fmin(gap, T(0)), vn = dot3(N, evel);
+      const bool nocontact = !elem_ok || (gap > A.surface_tol);
+      T resp_mag = (nocontact || fn > T(0)) ? T(0) : fabs_(fn);   // |N fn| with |N| = 1
+      T c1[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T resp = (fn > T(0)) ? T(0) : -(N[i] * fn);
+        c1[i] = nocontact ? T(0) : resp - A.contact_k * (N[i] * pen) - A.contact_nu * (N[i] * vn);
+      }
+      T tn = dot3(N, t);
+      T tp[3] = {t[0] - N[0] * tn, t[1] - N[1] * tn, t[2] - N[2] * tn};
+      T inv_tp = T(1) / (sqrt_(dot3(tp, tp)) + T(1e-14));
+      T ax[3] = {tp[0] * inv_tp, tp[1] * inv_tp, tp[2] * inv_tp}, rl[3];
+      cross3(ax, N, rl);
+      auto slip_fn = [&](T a) {   // find_slipping_elements on |v|
+        return (a > A.slip_tol) ? fabs_(T(1) - fmin(T(1), a * A.inv_slip_tol - T(1))) : T(1);
+      };
+      auto sgn = [](T a) { return T((a > T(0)) - (a < T(0))); };
+      T vax = dot3(evel, ax), sg = sgn(vax);
+      T kmu = T(0.5) * (A.kin_mu[0] * (T(1) + sg) + A.kin_mu[1] * (T(1) - sg));
+      T slipa = slip_fn(fabs_(vax) * sqrt_(dot3(ax, ax)));
+      T arm[3] = {-N[0] * rad, -N[1] * rad, -N[2] * rad};
+      T qa[3], wq[3], rv[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) qa[i] = Q[3 * i] * arm[0] + Q[3 * i + 1] * arm[1] + Q[3 * i + 2] * arm[2];
+      cross3(w, qa, wq);
+#pragma unroll
+      for (int i = 0; i < 3; i++) rv[i] = Q[i] * wq[0] + Q[3 + i] * wq[1] + Q[6 + i] * wq[2];
+      T smag = dot3(evel, rl) + dot3(rv, rl);
+      T slipr = slip_fn(fabs_(smag) * sqrt_(dot3(rl, rl)));
+      T ut[3] = {smag * rl[0] + vax * ax[0], smag * rl[1] + vax * ax[1], smag * rl[2] + vax * ax[2]};
+      T ug[3] = {ut[0] + T(1e-14), ut[1] + T(1e-14), ut[2] + T(1e-14)};
+      T iun = T(1) / sqrt_(dot3(ug, ug));
+      T uax = dot3(ut, ax) * iun, url = dot3(ut, rl) * iun;
+      T ka = nocontact ? T(0) : -((T(1) - slipa) * kmu * resp_mag * uax);
+      T kr = nocontact ? T(0) : -((T(1) - slipr) * A.kin_mu[2] * resp_mag * url);
+      T fr[3], text[3], cr[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) { fr[i] = kr * rl[i]; c1[i] += ka * ax[i] + fr[i]; }
+      cross3(arm, fr, cr);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        text[i] = Q[3 * i] * cr[0] + Q[3 * i + 1] * cr[1] + Q[3 * i + 2] * cr[2];
+        sh_c1[i * RS + tid] = c1[i];
+      }
+      __syncthreads();
+      // stage 2: static friction
+      T etf2[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T cl = has_left ? sh_c1[i * RS + tid - 1] : T(0), crr = has_right ? sh_c1[i * RS + tid + 1] : T(0);
+        T nc0 = T(0.5) * (cl + c1[i]), nc1 = T(0.5) * (c1[i] + crr);   // stage-1 response on nodes j, j+1
+        etf2[i] = etf[i] + T(0.5) * (nc0 + nc1) + ((j == 0) ? T(0.5) * nc0 : T(0)) + ((j + 1 == n) ? T(0.5) * nc1 : T(0));
+      }
+      T fax = dot3(etf2, ax), sga = sgn(fax);
+      T smu = T(0.5) * (A.stat_mu[0] * (T(1) + sga) + A.stat_mu[1] * (T(1) - sga));
+      T sa = nocontact ? T(0) : -(fmin(fabs_(fax), slipa * smu * resp_mag) * sga);
+      T tsum[3] = {tq[0] + text[0], tq[1] + text[1], tq[2] + text[2]}, tt[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) tt[i] = Q[i] * tsum[0] + Q[3 + i] * tsum[1] + Q[6 + i] * tsum[2];
+      T noslip = -((rad * dot3(etf2, rl) - T(2) * dot3(tt, ax)) / T(3) / rad);
+      T sr_ = nocontact ? T(0) : fmin(fabs_(noslip), slipr * A.stat_mu[2] * resp_mag) * sgn(noslip);
+#pragma unroll
+      for (int i = 0; i < 3; i++) { fr[i] = sr_ * rl[i]; sh_c12[i * RS + tid] = c1[i] + sa * ax[i] + fr[i]; }
+      cross3(arm, fr, cr);
+#pragma unroll
+      for (int i = 0; i < 3; i++) tq[i] += text[i] + (Q[3 * i] * cr[0] + Q[3 * i + 1] * cr[1] + Q[3 * i + 2] * cr[2]);
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 3; i++)   // node j collects half of the plane's load on elements j-1 and j
+        fint[i] += T(0.5) * (sh_c12[i * RS + tid] + (has_left ? sh_c12[i * RS + tid - 1] : T(0)));
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      T fi = fint[i];
       T gd = A.gdt_cv[i];
       if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
       // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
       v[i] = fma(fi, dtim_cv, fma(v[i], A.c_v, gmask * gd));
-      T tq = tql[i] + sh_N[i * RS + t_prev];
-      w[i] = fma(dtee, A.Jinv[i] * tq, w[i]);
+      w[i] = fma(dtee, A.Jinv[i] * tq[i], w[i]);
     }
 
     // ---- rate constraints and dissipation ------------------------------------------------

@@ -57,6 +57,11 @@ template <typename T> struct RodArgs {
   T S_over_l[3], gdt_cv[3];   // S / rest_len ; dt g c_v  (packed kernel)
   T c_v, c_w[3], logc_w[3];
   T base_limit, inv_move_period; float base_step_f32;   // SoftPendulum3D base controller
+  // RodPlaneContactWithAnisotropicFriction + per-env rest curvature (flat_env.py:310-311)
+  const T *rest_kappa;  // [n_env][3][stride] or nullptr
+  int contact_on, contact_before_forcing;
+  T plane_origin[3], plane_normal[3], contact_k, contact_nu, slip_tol, inv_slip_tol, surface_tol;
+  T kin_mu[3], stat_mu[3], vol_over_pi;
   int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
   PolyCoef<T> poly;
 };

@@ -46,7 +46,7 @@ struct sr_handle {
   sr_config cfg;
   int epl = 0, stride = 0, obs_dim = 0, action_dim = 0;
   size_t elem_size = 8;
-  void *state = nullptr, *bc = nullptr, *aux = nullptr;
+  void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr;
   sr::RodArgs<double> a64;
   sr::RodArgs<float> a32;
   // staging for the host-buffer entry points
@@ -97,6 +97,19 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   A.base_limit = (T)c.base_limit;
   A.inv_move_period = (T)(c.base_move_period > 0.0 ? 1.0 / c.base_move_period : 0.0);
   A.base_step_f32 = (float)c.base_step;
+  A.rest_kappa = nullptr;
+  A.contact_on = c.contact_on; A.contact_before_forcing = c.contact_before_forcing;
+  {
+    double nn = sqrt(c.plane_normal[0] * c.plane_normal[0] + c.plane_normal[1] * c.plane_normal[1] + c.plane_normal[2] * c.plane_normal[2]);
+    for (int i = 0; i < 3; i++) {
+      A.plane_origin[i] = (T)c.plane_origin[i];
+      A.plane_normal[i] = (T)(nn > 0 ? c.plane_normal[i] / nn : 0.0);
+      A.kin_mu[i] = (T)c.kinetic_mu[i]; A.stat_mu[i] = (T)c.static_mu[i];
+    }
+  }
+  A.contact_k = (T)c.contact_k; A.contact_nu = (T)c.contact_nu; A.slip_tol = (T)c.slip_velocity_tol;
+  A.inv_slip_tol = (T)(c.slip_velocity_tol > 0 ? 1.0 / c.slip_velocity_tol : 0.0);
+  A.surface_tol = (T)c.surface_tol; A.vol_over_pi = (T)((r * r) * rl);
   A.isotropic = 1;  // straight_rod builds circular cross-sections: I1 == I2
   {
     const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
@@ -158,12 +171,12 @@ bool use_packed_kernel(const sr_handle *h) {
   return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 256;
 }
 
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING>
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT>
 int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / (A.n_elem + 1);
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
   const size_t smem = (size_t)sr::packed_smem_words(NT) * sizeof(T);
-  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING>;
+  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -177,9 +190,10 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
+  if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true>(h, A, s);
   return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
-             ? launch_packed_impl<T, NT, MINB, true, true>(h, A, s)
-             : launch_packed_impl<T, NT, MINB, false, false>(h, A, s);
+             ? launch_packed_impl<T, NT, MINB, true, true, false>(h, A, s)
+             : launch_packed_impl<T, NT, MINB, false, false, false>(h, A, s);
 }
 
 // CTA size of the packed kernel.  Registers cap the SM at 512 resident threads (128 regs), so the
@@ -243,6 +257,15 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   if (cfg->math != SR_MATH_FAST && (cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE ||
                                     cfg->model == SR_MODEL_SOFT_PENDULUM_3D))
     return fail(SR_E_INVALID, "sr_create: Laplace filter / moving base are built for SR_MATH_FAST only");
+  if (cfg->contact_on) {
+    if (cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: contact is built for SR_MATH_FAST only");
+    if (cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE)
+      return fail(SR_E_INVALID, "sr_create: contact cannot be combined with the Laplace filter / moving base yet");
+    if (!(cfg->slip_velocity_tol > 0.0) || !(cfg->contact_k >= 0.0) || !(cfg->contact_nu >= 0.0))
+      return fail(SR_E_INVALID, "sr_create: contact needs slip_velocity_tol > 0, k >= 0, nu >= 0");
+    double nn = cfg->plane_normal[0] * cfg->plane_normal[0] + cfg->plane_normal[1] * cfg->plane_normal[1] + cfg->plane_normal[2] * cfg->plane_normal[2];
+    if (!(nn > 0.0)) return fail(SR_E_INVALID, "sr_create: plane_normal must be non-zero");
+  }
   if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
     return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
@@ -303,7 +326,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -419,6 +442,21 @@ int sr_get_state(sr_handle *h, sr_state_view *out) {
   out->f_position = sr::F_POS; out->f_velocity = sr::F_VEL; out->f_director = sr::F_DIR;
   out->f_omega = sr::F_OMEGA; out->f_tangents = sr::F_TAN; out->f_kappa = sr::F_KAPPA;
   out->f_sigma = sr::F_SIGMA; out->f_dilatation = sr::F_DIL;
+  return SR_OK;
+}
+
+int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev) {
+  if (!h || !rest_kappa_dev) return fail(SR_E_INVALID, "sr_get_rest_kappa: null argument");
+  if (h->cfg.math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_get_rest_kappa: rest curvature is built for SR_MATH_FAST only");
+  if (!h->rest_kappa) {
+    SR_CUDA(cudaSetDevice(h->cfg.device));
+    size_t bytes = (size_t)h->cfg.n_env * 3 * h->stride * h->elem_size;
+    SR_CUDA(cudaMalloc(&h->rest_kappa, bytes));
+    SR_CUDA(cudaMemset(h->rest_kappa, 0, bytes));
+    h->a64.rest_kappa = (const double *)h->rest_kappa;
+    h->a32.rest_kappa = (const float *)h->rest_kappa;
+  }
+  *rest_kappa_dev = h->rest_kappa;
   return SR_OK;
 }
 

@@ -1,2 +1,3 @@
 from .soft_pendulum import SoftPendulumEnv, SoftPendulumVectorEnv, pendulum_init_params
 from .soft_pendulum_3d import SoftPendulum3DEnv, SoftPendulum3DVectorEnv, pendulum3d_init_params
+from .arm_single import ArmSingleEnv, ArmSingleVectorEnv, arm_contact_params, curvature_interp_matrix

@@ -82,6 +82,14 @@ typedef struct sr_config {
    * base_step * action per env-step, clipped to +-base_limit; its velocity is displacement / base_move_period
    * with base_move_period = step_skip * time_step as computed by the host in double. */
   double base_step, base_limit, base_move_period;
+  /* RodPlaneContactWithAnisotropicFriction on Plane(origin, normal) (envs/octopus/build.py:173-200,258-283);
+   * contact_on = 0 disables.  contact_before_forcing = 1 runs the contact operator before gravity inside
+   * `synchronize` (the order PyElastica's mixin registration yields for the reference's simulator classes,
+   * DESIGN.md B-1); mu arrays are [forward, backward, sideways]. */
+  int32_t contact_on, contact_before_forcing;
+  double plane_origin[3], plane_normal[3];
+  double contact_k, contact_nu, slip_velocity_tol, surface_tol;
+  double static_mu[3], kinetic_mu[3];
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -145,6 +153,11 @@ int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
 /* Per-env model scratch, [n_env][*dim] of the handle's dtype: SoftPendulum3D keeps the base controller there
  * (0-2 position, 3-5 velocity, 6 last tilt angle, `info["tilt"]` of soft_pendulum_3d.py:157). */
 int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim);
+
+/* Per-env rest curvature (the actuation of the octopus-arm envs: `rod.rest_kappa[0, :] = ...`,
+ * envs/octopus/arm_single_env.py:226-235, flat_env.py:288-311), [n_env][3][stride] of the handle's
+ * dtype, Voronoi points in slots 0..n_elem-2; allocated on first use, zero-initialised. */
+int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev);
 
 /* number of kernels this library launched on behalf of the handle so far */
 int64_t sr_launch_count(const sr_handle *h);

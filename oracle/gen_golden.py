@@ -122,6 +122,27 @@ def gen_soft_pendulum_3d(seed=42, n=6):
     print("soft_pendulum_3d:", obs[-1], rew[-1])
 
 
+def gen_arm_single(seed=42, n=5):
+    """OctoArmSingle-v0 (free rod on a frictional plane, rest-curvature actuation): 5 env-steps."""
+    env = ref_loader.load_reference_env("OctoArmSingle-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    rod = env.unwrapped.shearable_rod
+    out = {"label": LABEL + "; synchronize order = [contact, forcing] (reverse-MRO registration, B-1)",
+           "seed": seed, "obs0": obs0}
+    pack("state0", rod_state(rod), out)
+    acts, obs, rew, term, trunc = [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr)
+        pack(f"state{i + 1}", rod_state(rod), out)
+    out.update(actions=np.array(acts, dtype=np.float32), obs=np.array(obs, dtype=np.float32),
+               reward=np.array(rew, dtype=np.float64), terminated=np.array(term), truncated=np.array(trunc))
+    np.savez_compressed(os.path.join(OUT, f"octo_arm_single_seed{seed}.npz"), **out)
+    print("arm_single:", rew, term)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_soft_pendulum_substeps()
@@ -129,3 +150,4 @@ if __name__ == "__main__":
     gen_determinism("SoftPendulum3D-v0")
     gen_soft_pendulum_3d()
     gen_soft_pendulum_episode()
+    gen_arm_single()

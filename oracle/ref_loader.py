@@ -42,11 +42,43 @@ def install_shims():
             mpl.animation = _stub("matplotlib.animation")
 
 
+class _StubFinder:
+    """Fabricates importable placeholder modules for third-party packages that cannot be obtained
+    offline (COOMM muscle models: SURVEY §2 row 22).  Only import-time names are satisfied; using
+    them raises."""
+
+    PREFIXES = ("coomm",)
+
+    def find_spec(self, fullname, path=None, target=None):
+        import importlib.machinery
+        if fullname.split(".")[0] in self.PREFIXES:
+            return importlib.machinery.ModuleSpec(fullname, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        mod = types.ModuleType(spec.name)
+        mod.__path__ = []
+
+        def _getattr(name, _m=spec.name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {"__init__": lambda self, *a, **k: (_ for _ in ()).throw(
+                NotImplementedError(f"{_m}.{name} is not available offline"))})
+
+        mod.__getattr__ = _getattr
+        return mod
+
+    def exec_module(self, module):
+        pass
+
+
 def load_reference_env(env_id: str, **kwargs):
     """`gym.make(env_id)` against the real reference code + oracle shims."""
     if not reference_available():
         raise RuntimeError("reference tree not present (only exists in the build container)")
     install_shims()
+    if not any(isinstance(f, _StubFinder) for f in sys.meta_path):
+        sys.meta_path.append(_StubFinder())
     import gymnasium  # the shim
     import gym_softrobot  # noqa: F401  the real reference package (registers ids)
 

@@ -44,6 +44,7 @@ struct ro_rod {
   double c_v, *c_w;                      /* AnalyticalLinearDamper coefficients */
   double *filt;                          /* Laplace filter scratch (3,n+1) */
   double *tmp;                           /* scratch (3,n+1) x 4 */
+  double *ctmp;                          /* contact scratch, 26 n */
 };
 
 static double *zalloc(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
@@ -266,6 +267,138 @@ static void dampen_rates(ro_rod *r) {
   }
 }
 
+/* ---- A.5 rod-plane contact with anisotropic friction
+ * (elastica/_contact_functions.py: _calculate_contact_forces_rod_plane[_with_anisotropic_friction]) */
+static double slip_fn(const double v[3], double tol) {
+  double a = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  if (fabs(a) > tol) { double q = a / tol - 1.0; if (q > 1.0) q = 1.0; return fabs(1.0 - q); }
+  return 1.0;
+}
+static double sgn(double x) { return (x > 0) - (x < 0); }
+
+static void node_to_element_force(const ro_rod *r, double *out /* (3,n) */) {
+  const int n = r->n;
+  for (int i = 0; i < 3; i++) {
+    const double *fi = r->f_int + i * (n + 1), *fe = r->f_ext + i * (n + 1);
+    for (int k = 0; k < n; k++) out[i * n + k] = 0.0 + 0.5 * ((fi[k] + fe[k]) + (fi[k + 1] + fe[k + 1]));
+    out[i * n + 0] += 0.5 * (fi[0] + fe[0]);
+    out[i * n + n - 1] += 0.5 * (fi[n] + fe[n]);
+  }
+}
+static void elements_to_nodes(ro_rod *r, const double *fe /* (3,n) */) {
+  const int n = r->n;
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < n; k++) {
+      r->f_ext[i * (n + 1) + k] += 0.5 * fe[i * n + k];
+      r->f_ext[i * (n + 1) + k + 1] += 0.5 * fe[i * n + k];
+    }
+}
+
+static void apply_contact(ro_rod *r) {
+  const int n = r->n;
+  const ro_config *c = &r->cfg;
+  const double *N = c->plane_normal;
+  double *etf = r->ctmp, *resp_mag = r->ctmp + 3 * n, *force = r->ctmp + 4 * n, *etf2 = r->ctmp + 7 * n;
+  unsigned char *nocontact = (unsigned char *)(r->ctmp + 10 * n);
+  double evel[3], ax[3], rolldir[3];
+  /* normal response */
+  node_to_element_force(r, etf);
+  for (int k = 0; k < n; k++) {
+    double fn = N[0] * etf[k] + N[1] * etf[n + k] + N[2] * etf[2 * n + k];
+    double resp[3];
+    for (int i = 0; i < 3; i++) resp[i] = -(fn > 0 ? 0.0 : N[i] * fn);
+    double ep[3];
+    for (int i = 0; i < 3; i++) ep[i] = 0.5 * (X(i, k) + X(i, k + 1));
+    double dist = N[0] * (ep[0] - c->plane_origin[0]) + N[1] * (ep[1] - c->plane_origin[1]) + N[2] * (ep[2] - c->plane_origin[2]);
+    double pen = dist - r->radius[k]; if (pen > 0.0) pen = 0.0;
+    double msum = r->mass[k + 1] + r->mass[k];
+    for (int i = 0; i < 3; i++) evel[i] = (r->mass[k + 1] * V(i, k + 1) + r->mass[k] * V(i, k)) / msum;
+    double vn = N[0] * evel[0] + N[1] * evel[1] + N[2] * evel[2];
+    nocontact[k] = (dist - r->radius[k]) > c->surface_tol;
+    for (int i = 0; i < 3; i++) {
+      double tot = resp[i] + (-c->contact_k * (N[i] * pen)) + (-c->contact_nu * (N[i] * vn));
+      if (nocontact[k]) { resp[i] = 0.0; tot = 0.0; }
+      force[i * n + k] = tot;
+    }
+    resp_mag[k] = sqrt(resp[0] * resp[0] + resp[1] * resp[1] + resp[2] * resp[2]);
+  }
+  elements_to_nodes(r, force);
+  /* kinetic friction; per-element directions are kept for the static part */
+  double *axd = r->ctmp + 11 * n, *rld = r->ctmp + 14 * n, *slipa = r->ctmp + 17 * n, *slipr = r->ctmp + 18 * n;
+  double *fa = r->ctmp + 19 * n, *fr = r->ctmp + 22 * n;
+  for (int k = 0; k < n; k++) {
+    double t[3] = {r->tang[k], r->tang[n + k], r->tang[2 * n + k]};
+    double tn = N[0] * t[0] + N[1] * t[1] + N[2] * t[2];
+    double tp[3] = {t[0] - N[0] * tn, t[1] - N[1] * tn, t[2] - N[2] * tn};
+    double tpm = sqrt(tp[0] * tp[0] + tp[1] * tp[1] + tp[2] * tp[2]);
+    double inv = 1 / (tpm + 1e-14);
+    for (int i = 0; i < 3; i++) ax[i] = inv * tp[i];
+    double msum = r->mass[k + 1] + r->mass[k];
+    for (int i = 0; i < 3; i++) evel[i] = (r->mass[k + 1] * V(i, k + 1) + r->mass[k] * V(i, k)) / msum;
+    double vax = evel[0] * ax[0] + evel[1] * ax[1] + evel[2] * ax[2];
+    double va[3] = {vax * ax[0], vax * ax[1], vax * ax[2]};
+    double sg = sgn(vax);
+    double kmu = 0.5 * (c->kinetic_mu[0] * (1 + sg) + c->kinetic_mu[1] * (1 - sg));
+    slipa[k] = slip_fn(va, c->slip_velocity_tol);
+    rolldir[0] = ax[1] * N[2] - ax[2] * N[1]; rolldir[1] = ax[2] * N[0] - ax[0] * N[2]; rolldir[2] = ax[0] * N[1] - ax[1] * N[0];
+    double arm[3] = {-N[0] * r->radius[k], -N[1] * r->radius[k], -N[2] * r->radius[k]};
+    double vroll = evel[0] * rolldir[0] + evel[1] * rolldir[1] + evel[2] * rolldir[2];
+    double qa[3], wq[3], rv[3];
+    for (int i = 0; i < 3; i++) qa[i] = 0.0 + QQ(i, 0, k) * arm[0] + QQ(i, 1, k) * arm[1] + QQ(i, 2, k) * arm[2];
+    wq[0] = W(1, k) * qa[2] - W(2, k) * qa[1]; wq[1] = W(2, k) * qa[0] - W(0, k) * qa[2]; wq[2] = W(0, k) * qa[1] - W(1, k) * qa[0];
+    for (int i = 0; i < 3; i++) rv[i] = 0.0 + QQ(0, i, k) * wq[0] + QQ(1, i, k) * wq[1] + QQ(2, i, k) * wq[2];
+    double rvr = rv[0] * rolldir[0] + rv[1] * rolldir[1] + rv[2] * rolldir[2];
+    double smag = vroll + rvr;
+    double sv[3] = {smag * rolldir[0], smag * rolldir[1], smag * rolldir[2]};
+    slipr[k] = slip_fn(sv, c->slip_velocity_tol);
+    double ut[3] = {sv[0] + va[0], sv[1] + va[1], sv[2] + va[2]};
+    double un = sqrt((ut[0] + 1e-14) * (ut[0] + 1e-14) + (ut[1] + 1e-14) * (ut[1] + 1e-14) + (ut[2] + 1e-14) * (ut[2] + 1e-14));
+    for (int i = 0; i < 3; i++) ut[i] /= un;
+    double uax = ut[0] * ax[0] + ut[1] * ax[1] + ut[2] * ax[2];
+    double url = ut[0] * rolldir[0] + ut[1] * rolldir[1] + ut[2] * rolldir[2];
+    for (int i = 0; i < 3; i++) {
+      fa[i * n + k] = nocontact[k] ? 0.0 : -((1.0 - slipa[k]) * kmu * resp_mag[k] * uax * ax[i]);
+      fr[i * n + k] = nocontact[k] ? 0.0 : -((1.0 - slipr[k]) * c->kinetic_mu[2] * resp_mag[k] * url * rolldir[i]);
+      axd[i * n + k] = ax[i]; rld[i * n + k] = rolldir[i];
+    }
+    double frk[3] = {fr[k], fr[n + k], fr[2 * n + k]};
+    double cr[3] = {arm[1] * frk[2] - arm[2] * frk[1], arm[2] * frk[0] - arm[0] * frk[2], arm[0] * frk[1] - arm[1] * frk[0]};
+    for (int i = 0; i < 3; i++) r->t_ext[i * n + k] += 0.0 + QQ(i, 0, k) * cr[0] + QQ(i, 1, k) * cr[1] + QQ(i, 2, k) * cr[2];
+  }
+  elements_to_nodes(r, fa);
+  elements_to_nodes(r, fr);
+  /* static friction: forces re-collected with the responses added above */
+  node_to_element_force(r, etf2);
+  for (int k = 0; k < n; k++) {
+    for (int i = 0; i < 3; i++) { ax[i] = axd[i * n + k]; rolldir[i] = rld[i * n + k]; }
+    double fax = etf2[k] * ax[0] + etf2[n + k] * ax[1] + etf2[2 * n + k] * ax[2];
+    double sg = sgn(fax);
+    double smu = 0.5 * (c->static_mu[0] * (1 + sg) + c->static_mu[1] * (1 - sg));
+    double maxf = slipa[k] * smu * resp_mag[k];
+    double mag = fabs(fax) < maxf ? fabs(fax) : maxf;
+    for (int i = 0; i < 3; i++) fa[i * n + k] = nocontact[k] ? 0.0 : -(mag * sg * ax[i]);
+    double tt[3];
+    for (int i = 0; i < 3; i++)
+      tt[i] = 0.0 + QQ(0, i, k) * (r->t_int[k] + r->t_ext[k]) + QQ(1, i, k) * (r->t_int[n + k] + r->t_ext[n + k]) +
+              QQ(2, i, k) * (r->t_int[2 * n + k] + r->t_ext[2 * n + k]);
+    double tta = tt[0] * ax[0] + tt[1] * ax[1] + tt[2] * ax[2];
+    double frl = etf2[k] * rolldir[0] + etf2[n + k] * rolldir[1] + etf2[2 * n + k] * rolldir[2];
+    double noslip = -((r->radius[k] * frl - 2.0 * tta) / 3.0 / r->radius[k]);
+    double maxr = slipr[k] * c->static_mu[2] * resp_mag[k];
+    double magr = fabs(noslip) < maxr ? fabs(noslip) : maxr;
+    double sgr = sgn(noslip);
+    for (int i = 0; i < 3; i++) fr[i * n + k] = nocontact[k] ? 0.0 : (magr * sgr * rolldir[i]);
+  }
+  elements_to_nodes(r, fa);
+  elements_to_nodes(r, fr);
+  for (int k = 0; k < n; k++) {
+    double arm[3] = {-N[0] * r->radius[k], -N[1] * r->radius[k], -N[2] * r->radius[k]};
+    double frk[3] = {fr[k], fr[n + k], fr[2 * n + k]};
+    double cr[3] = {arm[1] * frk[2] - arm[2] * frk[1], arm[2] * frk[0] - arm[0] * frk[2], arm[0] * frk[1] - arm[1] * frk[0]};
+    for (int i = 0; i < 3; i++) r->t_ext[i * n + k] += 0.0 + QQ(i, 0, k) * cr[0] + QQ(i, 1, k) * cr[1] + QQ(i, 2, k) * cr[2];
+  }
+}
+
 /* ---- A.2 one PositionVerlet substep */
 static void substep(ro_rod *r, double action, const double *bp, const double *bv) {
   const int n = r->n;
@@ -274,11 +407,13 @@ static void substep(ro_rod *r, double action, const double *bp, const double *bv
   r->time += prefac;
   constrain_values(r, bp);
   compute_internal_forces_and_torques(r);
-  /* synchronize: gravity, then point force (registration order, build.py:88-105) */
+  /* synchronize: [contact] gravity, then point force (registration order, build.py:88-105) [contact] */
+  if (r->cfg.contact_on && r->cfg.contact_before_forcing) apply_contact(r);
   for (int i = 0; i < 3; i++)
     for (int k = 0; k <= n; k++)
       r->f_ext[i * (n + 1) + k] += r->cfg.gravity[i] * r->mass[k] + r->f_user[i * (n + 1) + k];
   if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
+  if (r->cfg.contact_on && !r->cfg.contact_before_forcing) apply_contact(r);
   /* dynamic step */
   for (int i = 0; i < 3; i++)
     for (int k = 0; k <= n; k++)
@@ -319,7 +454,7 @@ ro_rod *ro_create(const ro_config *cfg) {
   r->sigma = zalloc(3 * n); r->kappa = zalloc(3 * nv); r->stress = zalloc(3 * n); r->couple = zalloc(3 * nv);
   r->f_int = zalloc(3 * (n + 1)); r->t_int = zalloc(3 * n); r->f_ext = zalloc(3 * (n + 1)); r->t_ext = zalloc(3 * n);
   r->f_user = zalloc(3 * (n + 1));
-  r->c_w = zalloc(3 * n); r->filt = zalloc(3 * (n + 1)); r->tmp = zalloc(12 * (n + 1));
+  r->c_w = zalloc(3 * n); r->filt = zalloc(3 * (n + 1)); r->tmp = zalloc(12 * (n + 1)); r->ctmp = zalloc(26 * n + 8);
 
   /* np.linspace(start, end, n+1): arange(n+1)*step + start, last point = end */
   for (int i = 0; i < 3; i++) {
@@ -390,7 +525,7 @@ void ro_destroy(ro_rod *r) {
   double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
                     r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
                     r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
-                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp};
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp, r->ctmp};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
   free(r);
 }
@@ -410,6 +545,7 @@ double *ro_external_forces(ro_rod *r) { return r->f_user; }
 double *ro_mass(ro_rod *r) { return r->mass; }
 double *ro_internal_forces(ro_rod *r) { return r->f_int; }
 double *ro_internal_torques(ro_rod *r) { return r->t_int; }
+double *ro_radius(ro_rod *r) { return r->radius; }
 
 /* numpy pairwise summation (np.add.reduce on a contiguous float64 row, n < 128 block) */
 static double np_pairwise_sum(const double *a, int n) {

@@ -26,6 +26,12 @@ typedef struct {
   int bc_kind;
   int point_force_on_base; /* SoftPendulum: F_ext[0,0] = action (assignment) */
   int damping_before_constraints; /* B-2: 1 = [dampen_rates, constrain_rates] */
+  /* RodPlaneContactWithAnisotropicFriction on Plane(origin, normal); contact_on = 0 disables */
+  int contact_on;
+  int contact_before_forcing; /* B-1: 1 = contact operator runs before gravity/forcing in synchronize */
+  double plane_origin[3], plane_normal[3];
+  double contact_k, contact_nu, slip_velocity_tol, surface_tol;
+  double static_mu[3], kinetic_mu[3]; /* forward, backward, sideways */
 } ro_config;
 
 typedef struct ro_rod ro_rod;
@@ -52,6 +58,7 @@ double *ro_external_forces(ro_rod *); /* (3,n+1) constant extra nodal load added
 double *ro_mass(ro_rod *);
 double *ro_internal_forces(ro_rod *);
 double *ro_internal_torques(ro_rod *);
+double *ro_radius(ro_rod *);
 
 /* SoftPendulum-v0 env step on top of the rod: follows
  * /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:176-251 */

@@ -36,6 +36,16 @@ class ROConfig(C.Structure):
         ("bc_kind", C.c_int),
         ("point_force_on_base", C.c_int),
         ("damping_before_constraints", C.c_int),
+        ("contact_on", C.c_int),
+        ("contact_before_forcing", C.c_int),
+        ("plane_origin", C.c_double * 3),
+        ("plane_normal", C.c_double * 3),
+        ("contact_k", C.c_double),
+        ("contact_nu", C.c_double),
+        ("slip_velocity_tol", C.c_double),
+        ("surface_tol", C.c_double),
+        ("static_mu", C.c_double * 3),
+        ("kinetic_mu", C.c_double * 3),
     ]
 
 
@@ -64,7 +74,7 @@ def lib():
         L.ro_time.argtypes = [C.c_void_p]
         for name in ("position", "velocity", "director", "omega", "tangents", "kappa", "sigma",
                      "dilatation", "rest_kappa", "external_forces", "mass", "internal_forces",
-                     "internal_torques"):
+                     "internal_torques", "radius"):
             f = getattr(L, "ro_" + name)
             f.restype = C.POINTER(C.c_double)
             f.argtypes = [C.c_void_p]
@@ -86,7 +96,8 @@ class OracleRod:
     def __init__(self, n_elem, start, direction, normal, base_length, base_radius, density,
                  youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
                  gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
-                 bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=True):
+                 bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=True,
+                 contact=None):
         cfg = ROConfig()
         cfg.n_elem = n_elem
         cfg.start[:] = list(map(float, start))
@@ -101,6 +112,15 @@ class OracleRod:
         cfg.bc_kind = bc_kind
         cfg.point_force_on_base = int(point_force_on_base)
         cfg.damping_before_constraints = int(damping_before_constraints)
+        if contact is not None:   # dict: plane_origin, plane_normal, k, nu, slip_velocity_tol, static_mu, kinetic_mu
+            cfg.contact_on = 1
+            cfg.contact_before_forcing = int(contact.get("before_forcing", True))
+            cfg.plane_origin[:] = list(map(float, contact["plane_origin"]))
+            cfg.plane_normal[:] = list(map(float, contact["plane_normal"]))
+            cfg.contact_k, cfg.contact_nu = contact["k"], contact["nu"]
+            cfg.slip_velocity_tol, cfg.surface_tol = contact["slip_velocity_tol"], contact.get("surface_tol", 1e-4)
+            cfg.static_mu[:] = list(map(float, contact["static_mu"]))
+            cfg.kinetic_mu[:] = list(map(float, contact["kinetic_mu"]))
         self.cfg = cfg
         self.n = n_elem
         self._h = C.c_void_p(lib().ro_create(C.byref(cfg)))
@@ -118,6 +138,7 @@ class OracleRod:
         self.mass = self._view("mass", (n + 1,))
         self.internal_forces = self._view("internal_forces", (3, n + 1))
         self.internal_torques = self._view("internal_torques", (3, n))
+        self.radius = self._view("radius", (n,))
 
     def _view(self, name, shape):
         p = getattr(lib(), "ro_" + name)(self._h)

@@ -62,7 +62,8 @@ class BaseSystemCollection:
         raise ValueError("system was not appended to the simulator")
 
     def block_systems(self):
-        return self._systems
+        # only rods / rigid bodies are time-stepped; static surfaces (Plane) are not
+        return [s for s in self._systems if hasattr(s, "velocity_collection")]
 
     def finalize(self):
         assert not self._finalize_flag, "The finalize cannot be called twice."

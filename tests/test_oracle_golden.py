@@ -152,3 +152,24 @@ def test_c_oracle_3d_matches_golden(golden_dir):
         np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-6, atol=1e-7)
         assert abs(r - g["reward"][i]) < 1e-12 and abs(info["tilt"] - g["tilt"][i]) < 1e-12
         assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+
+
+def test_c_oracle_arm_single_matches_golden(golden_dir):
+    """Plane contact + anisotropic friction + rest-curvature actuation (OctoArmSingle-v0 rod):
+    C oracle vs the reference env run on the shim."""
+    from scipy.interpolate import interp1d
+    g = np.load(os.path.join(golden_dir, "octo_arm_single_seed42.npz"))
+    L0, r0, grav = 0.35, 0.35 * 0.02, -9.81
+    mu = L0 / (2.0 * 2.0 * abs(grav) * 0.1)
+    kin = np.array([mu, 1.5 * mu, 2.0 * mu])
+    contact = dict(plane_origin=[0, 0, -r0], plane_normal=[0, 0, 1.0], k=1e2, nu=1e1, slip_velocity_tol=1e-8,
+                   static_mu=2 * kin, kinetic_mu=kin, before_forcing=True)
+    rod = ro.OracleRod(50, [0, 0, 0], [1.0, 0, 0], [0, 0, 1.0], L0, r0, 1000.0, 1e6, 7e-5, gravity=(0, 0, grav),
+                       damping_constant=1e-2, contact=contact)
+    for i, a in enumerate(g["actions"]):
+        rod.rest_kappa[0, :] = interp1d(np.linspace(0, 1, 7), a, kind="cubic", axis=-1)(np.linspace(0, 1, 49))
+        rod.substeps(714)
+        for gk, fk in FIELDS.items():
+            assert rel(getattr(rod, fk), g[f"state{i + 1}/{gk}"]) < 1e-9, (i, gk)
+    # the plane carries the rod: it has settled ~ weight / k below the surface, not fallen through
+    assert -5e-4 < rod.position_collection[2].min() and rod.position_collection[2].max() < 0.05

@@ -333,3 +333,65 @@ def test_fp32_mode_accuracy():
             assert bool(term[i]) == te
     assert h.state_tensor().dtype.itemsize == 4
     h.close()
+
+
+def _arm_contact(before_forcing=True):
+    from gym_softrobot_b200.envs.arm_single import arm_contact_params
+    return arm_contact_params(before_forcing=before_forcing)
+
+
+@pytest.mark.parametrize("before_forcing", [True, False], ids=["contact-first", "forcing-first"])
+def test_plane_contact_friction_vs_oracle(before_forcing):
+    """§8 a14 + a16: free rod on a frictional plane, per-env rest curvature, both synchronize orders (B-1)."""
+    import torch
+    import rod_oracle as ro
+    from gym_softrobot_b200.envs.arm_single import curvature_interp_matrix, _ROD
+    nat = _native()
+    n_env, n, dt = 6, 50, 7e-5
+    c = _arm_contact(before_forcing)
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, gravity=(0.0, 0.0, -9.81), damping_constant=1e-2,
+                   bc_kind=nat.BC_FREE, contact=c, **_ROD)
+    init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+    h.reset_host(init)
+    W = curvature_interp_matrix(7, n - 1)
+    rng = np.random.default_rng(5)
+    rods = [ro.OracleRod(n, [0, 0, 0], [1.0, 0, 0], [0, 0, 1.0], _ROD["base_length"], _ROD["base_radius"], 1000.0, 1e6, dt,
+                         gravity=(0.0, 0.0, -9.81), damping_constant=1e-2, contact=c) for _ in range(n_env)]
+    for step in range(3):
+        acts = rng.uniform(-10, 10, size=(n_env, 7))
+        rk = acts @ W.T
+        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(rk, device="cuda")
+        obs, rew, term = h.step_host(None, 400)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        for i, r in enumerate(rods):
+            r.rest_kappa[0, :] = rk[i]
+            r.substeps(400)
+            for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+                err = rel(f[name][i], getattr(r, name))
+                assert err < TOL, f"step={step} env={i} {name}: {err:.3e}"
+    # the rod must actually be resting on the plane (contact active), not falling through or floating
+    z = f["position_collection"][:, 2, :]
+    assert z.min() > -1e-3 and z.max() < 0.05
+    h.close()
+
+
+def test_arm_single_env_golden(golden_dir):
+    """OctoArmSingle-v0 through the Gymnasium facade vs the reference-env-on-shim fixture."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "octo_arm_single_seed42.npz"))
+    env = gsb.make("OctoArmSingle-v0")
+    obs0, _ = env.reset(seed=42)
+    assert obs0.dtype == np.float32 and obs0.shape == (25,)
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=1e-6, atol=1e-6)
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        st = env.rod_state()
+        for gk, fk in FIELDS.items():
+            if gk in ("kappa", "sigma"):
+                continue
+            err = rel(st[fk], g[f"state{i + 1}/{gk}"])
+            assert err < 1e-8, f"step {i} field {gk} rel err {err:.3e}"   # 714 substeps per step, 3570 in total
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-4, atol=1e-5)
+        assert abs(r - float(g["reward"][i])) < 1e-6
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+    env.close()
