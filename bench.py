@@ -87,8 +87,11 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "SoftPendulum-v0 batched envs, n_elem=50, 400 substeps/env-step, FP64",
-                   "envs_per_step_sample": n_env},
+        "config": {"workload": "SoftPendulum-v0 batched 4096 envs/GPU, single rod n_elem=50, "
+                               "400 substeps per env-step, FP64 (BASELINE configs[1])",
+                   "envs_per_gpu": 4096, "n_elem": N_ELEM, "substeps_per_step": STEP_SKIP,
+                   "envs_per_step_sample": n_env,
+                   "note": "CPU arm: each step advances a bounded sample of the workload's envs by one env-step"},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                          "sample": f"{n_env} envs x {args.steps} env-steps (of the 4096-env workload), "
                                    f"C restatement of PyElastica path, {cores} pthreads"},
