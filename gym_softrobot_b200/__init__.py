@@ -13,11 +13,15 @@ REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumEnv", {}),
     "SoftPendulum3D-v0": ("gym_softrobot_b200.envs.soft_pendulum_3d:SoftPendulum3DEnv", {}),
     "OctoArmSingle-v0": ("gym_softrobot_b200.envs.arm_single:ArmSingleEnv", {}),
+    "OctoFlat-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", {}),
+    "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", dict(n_arm=1, n_action=8)),
 }
 VECTOR_REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
     "SoftPendulum3D-v0": ("gym_softrobot_b200.envs.soft_pendulum_3d:SoftPendulum3DVectorEnv", {}),
     "OctoArmSingle-v0": ("gym_softrobot_b200.envs.arm_single:ArmSingleVectorEnv", {}),
+    "OctoFlat-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", {}),
+    "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", dict(n_arm=1, n_action=8)),
 }
 
 

@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_rest_kappa", "sr_launch_count", "sr_measure_fp64_peak",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_launch_count", "sr_measure_fp64_peak",
 ]
 
 
@@ -30,7 +30,7 @@ class SrConfig(C.Structure):
         ("struct_size", C.c_int32), ("device", C.c_int32), ("model", C.c_int32), ("dtype", C.c_int32),
         ("math", C.c_int32), ("n_env", C.c_int32), ("n_elem", C.c_int32), ("bc_kind", C.c_int32),
         ("point_force_on_base", C.c_int32), ("damping_before_constraints", C.c_int32),
-        ("laplace_filter_order", C.c_int32), ("reserved0", C.c_int32),
+        ("laplace_filter_order", C.c_int32), ("n_rod_per_env", C.c_int32),
         ("dt", C.c_double), ("base_length", C.c_double), ("base_radius", C.c_double),
         ("density", C.c_double), ("youngs_modulus", C.c_double), ("shear_modulus", C.c_double),
         ("gravity", C.c_double * 3), ("damping_constant", C.c_double),
@@ -39,6 +39,10 @@ class SrConfig(C.Structure):
         ("plane_origin", C.c_double * 3), ("plane_normal", C.c_double * 3),
         ("contact_k", C.c_double), ("contact_nu", C.c_double), ("slip_velocity_tol", C.c_double),
         ("surface_tol", C.c_double), ("static_mu", C.c_double * 3), ("kinetic_mu", C.c_double * 3),
+        ("has_head", C.c_int32), ("reserved1", C.c_int32),
+        ("head_length", C.c_double), ("head_radius", C.c_double), ("head_density", C.c_double),
+        ("joint_k", C.c_double), ("joint_nu", C.c_double), ("joint_kt", C.c_double), ("joint_radius", C.c_double),
+        ("joint_angle_deg", C.c_double * 16),
     ]
 
 
@@ -85,6 +89,7 @@ def load_library():
     L.sr_get_state.argtypes = [C.c_void_p, C.POINTER(SrStateView)]
     L.sr_set_state.argtypes = [C.c_void_p, C.POINTER(SrStateView), C.c_void_p]
     L.sr_get_aux.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    L.sr_get_head.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_launch_count.argtypes = [C.c_void_p]
     L.sr_launch_count.restype = C.c_int64
@@ -123,7 +128,7 @@ class Handle:
                  shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
                  point_force_on_base=False, damping_before_constraints=True, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
-                 base_move_period=0.0, contact=None):
+                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -147,6 +152,15 @@ class Handle:
             cfg.surface_tol = contact.get("surface_tol", 1e-4)   # PyElastica's fixed surface_tol
             cfg.static_mu[:] = [float(v) for v in contact["static_mu"]]
             cfg.kinetic_mu[:] = [float(v) for v in contact["kinetic_mu"]]
+        cfg.n_rod_per_env = n_rod
+        if head is not None:      # dict: length, radius, density
+            cfg.has_head = 1
+            cfg.head_length, cfg.head_radius, cfg.head_density = head["length"], head["radius"], head["density"]
+        if joint is not None:     # dict: k, nu, kt, radius, angles_deg (one per rod)
+            cfg.joint_k, cfg.joint_nu, cfg.joint_kt, cfg.joint_radius = joint["k"], joint["nu"], joint["kt"], joint["radius"]
+            for a, ang in enumerate(joint["angles_deg"]):
+                cfg.joint_angle_deg[a] = float(ang)
+        self.n_rod = max(1, n_rod)
         self.cfg = cfg
         self._h = C.c_void_p()
         _check(self._lib.sr_create(C.byref(cfg), C.byref(self._h)))
@@ -180,7 +194,8 @@ class Handle:
     def reset(self, init, env_idx=None):
         """init: float64 cuda tensor [n, 9]; env_idx: int32 cuda tensor [n] or None."""
         n = init.shape[0]
-        assert init.is_cuda and init.dtype.itemsize == 8 and init.is_contiguous() and init.shape[1] == 9
+        assert init.is_cuda and init.dtype.itemsize == 8 and init.is_contiguous()
+        assert init.shape[1] == self._lib.sr_init_dim(self._h)
         idx_ptr = None
         if env_idx is not None:
             assert env_idx.is_cuda and env_idx.is_contiguous() and env_idx.numel() == n
@@ -241,8 +256,15 @@ class Handle:
         return self._state_tensor
 
     def fields(self):
-        """Reference-named views: [n_env, 3, n+1] / [n_env, 3, 3, n] / [n_env, 3, n]."""
+        """Reference-named views (SURVEY §8b): [n_env, 3, n+1] / [n_env, 3, 3, n] / [n_env, 3, n];
+        multi-rod handles insert a rod axis: [n_env, n_rod, 3, n+1] ..."""
         st = self.state_tensor()
+        if self.n_rod > 1:
+            out = self._fields_flat(st)
+            return {k: v.unflatten(0, (self.n_env, self.n_rod)) for k, v in out.items()}
+        return self._fields_flat(st)
+
+    def _fields_flat(self, st):
         v, n = self._view, self.n_elem
         return {
             "position_collection": st[:, v.f_position:v.f_position + 3, :n + 1],
@@ -263,14 +285,23 @@ class Handle:
         ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
         return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), ts), device=f"cuda:{self.device}")
 
+    def head_tensor(self):
+        """torch view [n_env, 20] of the rigid head: x(3) v(3) Q(9, rows) w(3) pinned z (sr_get_head)."""
+        import torch
+        ptr, dim = C.c_void_p(), C.c_int32()
+        _check(self._lib.sr_get_head(self._h, C.byref(ptr), C.byref(dim)))
+        ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), ts), device=f"cuda:{self.device}")
+
     def rest_kappa_tensor(self):
-        """torch view [n_env, 3, n_elem-1] of the per-env rest curvature (sr_get_rest_kappa)."""
+        """torch view [n_env (* n_rod), 3, n_elem-1] of the per-rod rest curvature (sr_get_rest_kappa)."""
         import torch
         ptr = C.c_void_p()
         _check(self._lib.sr_get_rest_kappa(self._h, C.byref(ptr)))
         v = self.state_view()
         ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
-        t = torch.as_tensor(_DevMem(ptr.value, (self.n_env, 3, v.stride), ts), device=f"cuda:{self.device}")
+        t = torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod, 3, v.stride), ts),
+                            device=f"cuda:{self.device}")
         return t[:, :, :self.n_elem - 1]
 
     def set_state_from(self, other: "Handle"):

@@ -20,13 +20,14 @@ constexpr int PACKED_MAX_THREADS = 512;
 // row stride of the exchange arrays: slot NT is a permanent zero (what the stencils see to
 // the left of element 0), so the base thread needs no select when it reads "j-1"
 // shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide
-constexpr int packed_smem_words(int nt) { return 21 * (nt + 2); }
+constexpr int packed_smem_words(int nt, bool multi) { return (multi ? 27 : 21) * (nt + 2); }
 
 // LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
 // (SoftPendulum3D); kept out of the instantiation used by the other models so they do not pay
 // their registers / code size.  CONTACT: plane contact with anisotropic friction and per-env rest
-// curvature (octopus-arm models): two more neighbour exchanges per substep.
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT>
+// curvature (octopus-arm models): two more neighbour exchanges per substep.  MULTI: several rods per
+// env plus one rigid head thread, coupled by FixedJoint2Rigid spring/torque joints.
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -36,9 +37,19 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 
   const int tid = threadIdx.x;
   const int n = A.n_elem, stride = A.stride, tpr = n + 1;  // threads per rod
-  const int r = tid / tpr, j = tid - r * tpr;
-  const int env = blockIdx.x * rods_per_cta + r;
-  const bool active = (r < rods_per_cta) && (env < A.n_env);
+  // env group = n_rod rods of tpr threads (+ one head thread); single-rod models: group = rod
+  const int n_rod = MULTI ? A.n_rod : 1, has_head = MULTI ? A.has_head : 0;
+  const int G = n_rod * tpr + has_head;
+  const int r = tid / G, u = tid - r * G;           // env slot inside the CTA, thread inside the group
+  const bool is_head = MULTI && has_head && (u == G - 1);
+  const int arm = (MULTI && !is_head) ? u / tpr : 0;
+  const int j = is_head ? 0 : u - arm * tpr;
+  const int env = blockIdx.x * rods_per_cta + r;    // rods_per_cta counts env groups
+  const bool live = (r < rods_per_cta) && (env < A.n_env);
+  const bool active = live && !is_head;             // a thread that owns a node / element of a rod
+  const int rod = env * n_rod + arm;                // global rod slot in the state arrays
+  const int t_head = r * G + G - 1;                 // where this env's head publishes its state
+  T *sh_J = sh + 21 * RS;                           // MULTI: joint reactions on the head, 6 rows
   const bool elem_ok = active && j < n, vor_ok = active && j < n - 1, first = (j == 0);
   // neighbour slots (clamped so that idle / edge threads read something harmless)
   const int t_next = (active && j < n) ? tid + 1 : tid;
@@ -48,7 +59,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 
   T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
   T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
-  T *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
+  T *st = A.state + (size_t)(active ? rod : 0) * N_FIELDS * stride;
   if (active) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -59,6 +70,14 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
   }
+  T *hd = (MULTI && is_head && live) ? A.head + (size_t)env * HEAD_DIM : nullptr;
+  if (MULTI && hd) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { x[c] = hd[c]; v[c] = hd[3 + c]; w[c] = hd[15 + c]; }
+#pragma unroll
+    for (int c = 0; c < 9; c++) Q[c] = hd[6 + c];
+  }
+  T fj[3] = {T(0), T(0), T(0)}, tj[3] = {T(0), T(0), T(0)};   // joint force on node 0 / torque on element 0
   // time-step multipliers are zero where there is nothing to integrate (tip thread's
   // pseudo-element, idle threads): no selects in the update expressions.
   // (c_v is 1 when the damper is off)
@@ -69,7 +88,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   T rk[3] = {T(0), T(0), T(0)};   // rest curvature at Voronoi point j (actuation), constant during a launch
   if (CONTACT && A.rest_kappa && vor_ok) {
 #pragma unroll
-    for (int c = 0; c < 3; c++) rk[c] = A.rest_kappa[((size_t)env * 3 + c) * stride + j];
+    for (int c = 0; c < 3; c++) rk[c] = A.rest_kappa[((size_t)rod * 3 + c) * stride + j];
   }
   T act0 = T(0), base_vx = T(0), base_vy = T(0);
   float act_f0 = 0.0f, act_f1 = 0.0f;
@@ -85,7 +104,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const T rot_on = bc_thread ? T(0) : T(1);
   T pin_x = T(0), pin_y = T(0);
   if (bc_thread) {
-    const T *bc = A.bc + (size_t)env * BC_DIM;
+    const T *bc = A.bc + (size_t)rod * BC_DIM;
     if (A.bc_kind == BC_PENDULUM_SLIDER) {
       x[1] = bc[1]; x[2] = bc[2];
 #pragma unroll
@@ -143,8 +162,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     else rotate_directors_ref<T>(a0, a1, a2, Q);
   };
 
+  // BodyBoundaryCondition on the head (utils/custom_elastica/constraint.py:43-58, 62-85)
+  auto head_constrain_values = [&]() {
+    if (MULTI && hd) {
+      x[2] = hd[18];
+      Q[6] = T(0); Q[7] = T(0); Q[8] = T(1);
+#pragma unroll
+      for (int i = 0; i < 2; i++) {
+        T len = sqrt_(Q[3 * i] * Q[3 * i] + Q[3 * i + 1] * Q[3 * i + 1]);
+        Q[3 * i] /= len; Q[3 * i + 1] /= len; Q[3 * i + 2] = T(0);
+      }
+    }
+  };
   const T h = A.half_dt, dt = A.dt;
-  if (A.n_substeps > 0) kinematic(h, T(1e-14));
+  if (A.n_substeps > 0) { kinematic(h, T(1e-14)); head_constrain_values(); }
 
 #pragma unroll 1
   for (int s = 0; s < A.n_substeps; s++) {
@@ -189,6 +220,38 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int i = 0; i < 3; i++) {
       sfl[i] = fma(Q[6 + i], nst[2], fma(Q[3 + i], nst[1], Q[i] * nst[0])) * inv_e_s;
       sh_s[i * RS + tid] = sfl[i];
+    }
+
+    if (MULTI && active && first && has_head) {
+      // FixedJoint2Rigid(head, -1, arm, 0) (utils/custom_elastica/joint.py:48-123 forces, :125-219 torques)
+      T hx[3], hv[3], d2[3], Qh[9];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { hx[c] = sh_x[c * RS + t_head]; hv[c] = sh_v[c * RS + t_head]; d2[c] = sh_Q[(3 + c) * RS + t_head]; }
+#pragma unroll
+      for (int c = 0; c < 9; c++) Qh[c] = sh_Q[c * RS + t_head];
+      const T cs = A.joint_cs[arm][0], sn = A.joint_cs[arm][1];
+      T dir[3] = {-(cs * d2[0] - sn * d2[1]), -(sn * d2[0] + cs * d2[1]), -d2[2]};   // -Rz(angle) d2
+      T anchor[3] = {hx[0] + A.joint_radius * dir[0], hx[1] + A.joint_radius * dir[1], T(0) + A.joint_radius * dir[2]};
+      T dd[3] = {x[0] - anchor[0], x[1] - anchor[1], x[2] - anchor[2]};
+      T dist = sqrt_(dot3(dd, dd));
+      T inv = (dist <= T(2.220446049250313e-12)) ? T(0) : T(1) / dist;
+      T nh[3] = {dd[0] * inv, dd[1] * inv, dd[2] * inv};
+      T rvn = (v[0] - hv[0]) * nh[0] + (v[1] - hv[1]) * nh[1] + (v[2] - hv[2]) * nh[2];
+      T cf[3], tgt[3], fd[3], tau[3];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        cf[c] = A.joint_k * dd[c] - A.joint_nu * (rvn * nh[c]);
+        fj[c] = -cf[c];
+        tgt[c] = anchor[c] + A.rest_len * dir[c];
+        fd[c] = -A.joint_kt * ((x[c] + dx[c]) - tgt[c]);       // x + dx = node 1 of the arm
+      }
+      cross3(dx, fd, tau);                                        // link_direction x force
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        tj[i] = Q[3 * i] * tau[0] + Q[3 * i + 1] * tau[1] + Q[3 * i + 2] * tau[2];
+        sh_J[i * RS + tid] = cf[i];
+        sh_J[(3 + i) * RS + tid] = -(Qh[3 * i] * tau[0] + Qh[3 * i + 1] * tau[1] + Qh[3 * i + 2] * tau[2]);
+      }
     }
 
     // ---- curvature, bending couple ----------------------------------------------------
@@ -242,20 +305,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     // barrier, so only x,v,Q,w + tql + sfl + e stay live across it.
     T pw[3] = {A.J[0] * w[0], A.J[1] * w[1], A.J[2] * w[2]};
     T ede = edot * inv_e;
-    T G[3];
-    G[0] = fma(Qdx[1], nst[2], -(Qdx[2] * nst[1]));
-    G[1] = fma(Qdx[2], nst[0], -(Qdx[0] * nst[2]));
-    G[2] = fma(Qdx[0], nst[1], -(Qdx[1] * nst[0]));
-    G[0] = fma(pw[1], w[2], fma(-pw[2], w[1], G[0]));
-    G[1] = fma(pw[2], w[0], fma(-pw[0], w[2], G[1]));
-    G[2] = fma(pw[0], w[1], fma(-pw[1], w[0], G[2]));
+    T Gc[3];
+    Gc[0] = fma(Qdx[1], nst[2], -(Qdx[2] * nst[1]));
+    Gc[1] = fma(Qdx[2], nst[0], -(Qdx[0] * nst[2]));
+    Gc[2] = fma(Qdx[0], nst[1], -(Qdx[1] * nst[0]));
+    Gc[0] = fma(pw[1], w[2], fma(-pw[2], w[1], Gc[0]));
+    Gc[1] = fma(pw[2], w[0], fma(-pw[0], w[2], Gc[1]));
+    Gc[2] = fma(pw[0], w[1], fma(-pw[1], w[0], Gc[2]));
     T tql[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       T m = tau[i] * ie3;
       T Pi = fma(kxt[i], hc, m);                 // m_j + c_j/2  (own element)
       sh_N[i * RS + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
-      tql[i] = fma(fma(pw[i], ede, G[i]), inv_e, Pi);
+      tql[i] = fma(fma(pw[i], ede, Gc[i]), inv_e, Pi);
     }
     // rotational damper coefficients c_w^e = c_w exp((e-1) ln c_w): only need e, so they are
     // evaluated here, ahead of the barrier, off the critical path of the dynamic step
@@ -397,14 +460,36 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       for (int i = 0; i < 3; i++)   // node j collects half of the plane's load on elements j-1 and j
         fint[i] += T(0.5) * (sh_c12[i * RS + tid] + (has_left ? sh_c12[i * RS + tid - 1] : T(0)));
     }
+    if (MULTI && is_head) {
+      // rigid head: a = F/m, alpha = J^-1 ((J w) x w + T)  (SURVEY D.1); loads = the joints' reactions,
+      // summed in connection order; no gravity, no damper (build.py:141-152); then the rate part of
+      // BodyBoundaryCondition: v_z = 0, w_x = w_y = 0
+      if (hd) {
+        T F[3] = {T(0), T(0), T(0)}, Tq[3] = {T(0), T(0), T(0)};
+        for (int a = 0; a < n_rod; a++) {
+          const int ta = r * G + a * tpr;
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      T fi = fint[i];
-      T gd = A.gdt_cv[i];
-      if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
-      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
-      v[i] = fma(fi, dtim_cv, fma(v[i], A.c_v, gmask * gd));
-      w[i] = fma(dtee, A.Jinv[i] * tq[i], w[i]);
+          for (int i = 0; i < 3; i++) { F[i] += sh_J[i * RS + ta]; Tq[i] += sh_J[(3 + i) * RS + ta]; }
+        }
+        T Jw[3] = {A.head_J[0] * w[0], A.head_J[1] * w[1], A.head_J[2] * w[2]}, lt[3];
+        cross3(Jw, w, lt);
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          v[i] = fma(F[i], A.head_dt_inv_mass, v[i]);
+          w[i] = fma(dt, A.head_Jinv[i] * (lt[i] + Tq[i]), w[i]);
+        }
+        v[2] = T(0); w[0] = T(0); w[1] = T(0);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        T fi = fint[i] + (MULTI ? fj[i] : T(0));
+        T gd = A.gdt_cv[i];
+        if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
+        // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
+        v[i] = fma(fi, dtim_cv, fma(v[i], A.c_v, gmask * gd));
+        w[i] = fma(dtee, A.Jinv[i] * (tq[i] + (MULTI ? tj[i] : T(0))), w[i]);
+      }
     }
 
     // ---- rate constraints and dissipation ------------------------------------------------
@@ -441,15 +526,26 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         for (int c = 0; c < 3; c++) { v[c] -= fv[c]; w[c] -= fw[c]; }
       }
     };
-    if (A.damp_first) { dampen(); constrain_rates(); }
-    else { constrain_rates(); dampen(); }
+    if (!(MULTI && is_head)) {
+      if (A.damp_first) { dampen(); constrain_rates(); }
+      else { constrain_rates(); dampen(); }
+    }
 
     kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
+    head_constrain_values();
   }
 
   // ---- write back, NaN guard, model outputs ------------------------------------------------
   __syncthreads();   // all reads of the exchange buffers are done: reuse them below
   bool bad = false;
+  if (MULTI && hd) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) { hd[c] = x[c]; hd[3 + c] = v[c]; hd[15 + c] = w[c]; }
+#pragma unroll
+    for (int c = 0; c < 9; c++) hd[6 + c] = Q[c];
+    float *o = A.obs + (size_t)env * A.obs_dim;
+    for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
+  }
   if (active) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -475,7 +571,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   __syncthreads();
   if (active && bad) atomicOr(&sh_flag[r], 1);
   __syncthreads();
-  if (active && first) {
+  if (active && first && arm == 0) {
     const bool invalid = sh_flag[r] != 0;
     if (A.model == MODEL_SOFT_PENDULUM) {
       soft_pendulum_outputs<T>(sh_x + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
@@ -492,7 +588,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       A.terminated[env] = invalid ? 1 : 0;
     }
   }
-  if (active && A.model == MODEL_ROD && j == n) {
+  if (active && A.model == MODEL_ROD && j == n && !MULTI) {
     float *o = A.obs + (size_t)env * A.obs_dim;
     for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
   }

@@ -28,6 +28,7 @@ enum : int {
   F_DIL = 27, N_FIELDS = 28
 };
 constexpr int BC_DIM = 12;   // per-env anchors: fixed_position(3), fixed_directors(9)
+constexpr int HEAD_DIM = 20;  // rigid head: x(3) v(3) Q(9) w(3) pinned z(1) pad(1)
 constexpr int AUX_DIM = 8;   // per-env model scratch (3D pendulum: base position(3), velocity(3))
 constexpr int WARPS_PER_CTA = 4;
 
@@ -62,6 +63,12 @@ template <typename T> struct RodArgs {
   int contact_on, contact_before_forcing;
   T plane_origin[3], plane_normal[3], contact_k, contact_nu, slip_tol, inv_slip_tol, surface_tol;
   T kin_mu[3], stat_mu[3], vol_over_pi;
+  // multi-rod environments (octopus: n_rod arms + one rigid Cylinder head joined by FixedJoint2Rigid,
+  // envs/octopus/build.py:52-217, utils/custom_elastica/joint.py, constraint.py)
+  int n_rod, has_head;
+  T *head;                       // [n_env][HEAD_DIM]
+  T joint_k, joint_nu, joint_kt, joint_radius, joint_cs[16][2];   // cos/sin of each arm's mounting angle
+  T head_dt_inv_mass, head_J[3], head_Jinv[3];
   int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
   PolyCoef<T> poly;
 };
@@ -666,11 +673,14 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
 // ---- reset: CosseratRod.straight_rod + finalize-time anchors ----
 template <typename T>
 __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx, int n_reset,
-                                 const double *init, int n, int stride, double base_length) {
+                                 const double *init, int n, int stride, double base_length, int n_rod,
+                                 int init_dim) {
+  // one block per rod to rebuild: block r -> env slot r / n_rod, rod r % n_rod
   int r = blockIdx.x;
-  if (r >= n_reset) return;
-  int env = env_idx ? env_idx[r] : r;
-  const double *ip = init + (size_t)r * 9;
+  if (r >= n_reset * n_rod) return;
+  int e = r / n_rod, arm = r - e * n_rod;
+  int env = (env_idx ? env_idx[e] : e) * n_rod + arm;   // global rod slot
+  const double *ip = init + (size_t)e * init_dim + (size_t)arm * 9;
   double start[3] = {ip[0], ip[1], ip[2]}, dir[3] = {ip[3], ip[4], ip[5]}, nor[3] = {ip[6], ip[7], ip[8]};
   double nn = sqrt(nor[0] * nor[0] + nor[1] * nor[1] + nor[2] * nor[2]);
   for (int c = 0; c < 3; c++) nor[c] = nor[c] / nn;
@@ -722,6 +732,24 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
       for (int c = 0; c < AUX_DIM; c++) a[c] = T(0);
     }
   }
+}
+
+// Cylinder(start, direction, normal, length, ...) of the octopus head: centre of mass at
+// start + direction L/2, rows of Q = normal, direction x normal, direction; BodyBoundaryCondition pins z.
+template <typename T>
+__global__ void head_reset_kernel(T *head, const int32_t *env_idx, int n_reset, const double *init,
+                                  int init_dim, int n_rod, double head_length) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_reset) return;
+  int env = env_idx ? env_idx[e] : e;
+  const double *ip = init + (size_t)e * init_dim + (size_t)n_rod * 9;
+  T *h = head + (size_t)env * HEAD_DIM;
+  double d[3] = {ip[3], ip[4], ip[5]}, nr[3] = {ip[6], ip[7], ip[8]};
+  for (int c = 0; c < 3; c++) { h[c] = (T)(ip[c] + d[c] * head_length / 2); h[3 + c] = T(0); h[15 + c] = T(0); }
+  double b[3] = {d[1] * nr[2] - d[2] * nr[1], d[2] * nr[0] - d[0] * nr[2], d[0] * nr[1] - d[1] * nr[0]};
+  for (int c = 0; c < 3; c++) { h[6 + c] = (T)nr[c]; h[9 + c] = (T)b[c]; h[12 + c] = (T)d[c]; }
+  h[18] = h[2];
+  h[19] = T(0);
 }
 
 // observation of the current state without stepping (reset obs; soft_pendulum.py:149-161)

@@ -46,7 +46,8 @@ struct sr_handle {
   sr_config cfg;
   int epl = 0, stride = 0, obs_dim = 0, action_dim = 0;
   size_t elem_size = 8;
-  void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr;
+  void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr, *head = nullptr;
+  int n_rod = 1, init_dim = 9;
   sr::RodArgs<double> a64;
   sr::RodArgs<float> a32;
   // staging for the host-buffer entry points
@@ -98,6 +99,20 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   A.inv_move_period = (T)(c.base_move_period > 0.0 ? 1.0 / c.base_move_period : 0.0);
   A.base_step_f32 = (float)c.base_step;
   A.rest_kappa = nullptr;
+  A.n_rod = c.n_rod_per_env > 1 ? c.n_rod_per_env : 1; A.has_head = c.has_head; A.head = nullptr;
+  A.joint_k = (T)c.joint_k; A.joint_nu = (T)c.joint_nu; A.joint_kt = (T)c.joint_kt; A.joint_radius = (T)c.joint_radius;
+  for (int a = 0; a < 16; a++) {   // z_rotation(): theta = angle / 180 * pi
+    double th = c.joint_angle_deg[a] / 180.0 * PI;
+    A.joint_cs[a][0] = (T)cos(th); A.joint_cs[a][1] = (T)sin(th);
+  }
+  if (c.has_head) {   // Cylinder: m = rho pi r^2 L ; J = diag(I0) rho L, I0 = (A^2/4pi, A^2/4pi, A^2/2pi)
+    const double Ah = PI * c.head_radius * c.head_radius, Ih = Ah * Ah / (4.0 * PI);
+    const double mh = PI * c.head_radius * c.head_radius * c.head_length * c.head_density;
+    const double Jh[3] = {Ih * c.head_density * c.head_length, Ih * c.head_density * c.head_length,
+                          2.0 * Ih * c.head_density * c.head_length};
+    A.head_dt_inv_mass = (T)(c.dt / mh);
+    for (int i = 0; i < 3; i++) { A.head_J[i] = (T)Jh[i]; A.head_Jinv[i] = (T)(1.0 / Jh[i]); }
+  }
   A.contact_on = c.contact_on; A.contact_before_forcing = c.contact_before_forcing;
   {
     double nn = sqrt(c.plane_normal[0] * c.plane_normal[0] + c.plane_normal[1] * c.plane_normal[1] + c.plane_normal[2] * c.plane_normal[2]);
@@ -171,12 +186,14 @@ bool use_packed_kernel(const sr_handle *h) {
   return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 256;
 }
 
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT>
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI>
 int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  const int rods_per_cta = NT / (A.n_elem + 1);
+  const int group = (MULTI ? A.n_rod : 1) * (A.n_elem + 1) + (MULTI ? A.has_head : 0);   // threads per env
+  const int rods_per_cta = NT / group;
+  if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
-  const size_t smem = (size_t)sr::packed_smem_words(NT) * sizeof(T);
-  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT>;
+  const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI) * sizeof(T);
+  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -190,17 +207,18 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
-  if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true>(h, A, s);
+  if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
+  if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
   return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
-             ? launch_packed_impl<T, NT, MINB, true, true, false>(h, A, s)
-             : launch_packed_impl<T, NT, MINB, false, false, false>(h, A, s);
+             ? launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s)
+             : launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
 }
 
 // CTA size of the packed kernel.  Registers cap the SM at 512 resident threads (128 regs), so the
 // choice is 2 x 256 or 1 x 512; take whichever wastes fewer lanes for this rod length
 // (n = 50: 5 x 51 = 255/256; n = 100: 2 x 101 = 202/256 but 5 x 101 = 505/512).
 // SOFTROD_PACKED_THREADS={256,320,384,512} overrides it for experiments.
-int packed_threads_setting(int n_elem) {
+int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("SOFTROD_PACKED_THREADS");
@@ -208,14 +226,14 @@ int packed_threads_setting(int n_elem) {
     if (forced != 256 && forced != 320 && forced != 384 && forced != 512) forced = 0;
   }
   if (forced) return forced;
-  const int tpr = n_elem + 1;
+  const int tpr = (n_rod > 1 ? n_rod : 1) * (n_elem + 1) + has_head;   // threads per env group
   const double u256 = (double)((256 / tpr) * tpr) / 256.0, u512 = (double)((512 / tpr) * tpr) / 512.0;
   return (u512 > u256 + 0.02) ? 512 : 256;
 }
 
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_packed_kernel(h)) {
-    const int nt = packed_threads_setting(h->cfg.n_elem), mb = min_ctas_setting();
+    const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head), mb = min_ctas_setting();
     if (nt == 512) return launch_packed<T, 512, 1>(h, A, s);
     if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
     if (nt == 384) return launch_packed<T, 384, 2>(h, A, s);
@@ -257,6 +275,16 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   if (cfg->math != SR_MATH_FAST && (cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE ||
                                     cfg->model == SR_MODEL_SOFT_PENDULUM_3D))
     return fail(SR_E_INVALID, "sr_create: Laplace filter / moving base are built for SR_MATH_FAST only");
+  if (cfg->n_rod_per_env > 1 || cfg->has_head) {
+    const int nr = cfg->n_rod_per_env > 1 ? cfg->n_rod_per_env : 1;
+    if (cfg->math != SR_MATH_FAST || cfg->model != SR_MODEL_ROD || cfg->bc_kind != SR_BC_FREE || cfg->laplace_filter_order != 0)
+      return fail(SR_E_INVALID, "sr_create: multi-rod assemblies need SR_MATH_FAST, SR_MODEL_ROD, SR_BC_FREE, no Laplace filter");
+    if (nr > 16) return fail(SR_E_INVALID, "sr_create: at most 16 rods per environment");
+    if (nr * (cfg->n_elem + 1) + (cfg->has_head ? 1 : 0) > 512)
+      return fail(SR_E_INVALID, "sr_create: one environment must fit a 512-thread CTA");
+    if (cfg->has_head && (!(cfg->head_length > 0.0) || !(cfg->head_radius > 0.0) || !(cfg->head_density > 0.0)))
+      return fail(SR_E_INVALID, "sr_create: head_length, head_radius, head_density must be > 0");
+  }
   if (cfg->contact_on) {
     if (cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: contact is built for SR_MATH_FAST only");
     if (cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE)
@@ -282,6 +310,8 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   sr_handle *h = new (std::nothrow) sr_handle();
   if (!h) return fail(SR_E_ALLOC, "sr_create: out of host memory");
   h->cfg = *cfg;
+  h->n_rod = cfg->n_rod_per_env > 1 ? cfg->n_rod_per_env : 1;
+  h->init_dim = 9 * (h->n_rod + (cfg->has_head ? 1 : 0));
   // nodes 0..n need n+1 slots in 32*EPL
   h->epl = (cfg->n_elem + 1 <= 32) ? 1 : (cfg->n_elem + 1 <= 64) ? 2 : 4;
   // the warp-per-rod kernel reads 32*EPL slots per row; longer rods (packed kernel only) round up to 32
@@ -290,23 +320,24 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   if (cfg->model == SR_MODEL_SOFT_PENDULUM) { h->obs_dim = 4; h->action_dim = 1; }
   else if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D) { h->obs_dim = 9; h->action_dim = 2; }
   else { h->obs_dim = 6; h->action_dim = 0; }
-  const size_t n_env = (size_t)cfg->n_env;
-  const size_t state_bytes = n_env * sr::N_FIELDS * h->stride * h->elem_size;
+  const size_t n_env = (size_t)cfg->n_env, n_rods = n_env * h->n_rod;
+  const size_t state_bytes = n_rods * sr::N_FIELDS * h->stride * h->elem_size;
   cudaError_t e;
   if ((e = cudaMalloc(&h->state, state_bytes)) != cudaSuccess ||
-      (e = cudaMalloc(&h->bc, n_env * sr::BC_DIM * h->elem_size)) != cudaSuccess ||
+      (e = cudaMalloc(&h->bc, n_rods * sr::BC_DIM * h->elem_size)) != cudaSuccess ||
+      (e = cudaMalloc(&h->head, n_env * sr::HEAD_DIM * h->elem_size)) != cudaSuccess ||
       (e = cudaMalloc(&h->aux, n_env * sr::AUX_DIM * h->elem_size)) != cudaSuccess ||
       (e = cudaMalloc(&h->d_action, n_env * (h->action_dim ? h->action_dim : 1) * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_obs, n_env * h->obs_dim * sizeof(float))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_reward, n_env * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_term, n_env)) != cudaSuccess ||
-      (e = cudaMalloc(&h->d_init, n_env * 9 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMalloc(&h->d_init, n_env * h->init_dim * sizeof(double))) != cudaSuccess ||
       (e = cudaMalloc(&h->d_idx, n_env * sizeof(int32_t))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_action, n_env * (h->action_dim ? h->action_dim : 1) * sizeof(float))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_obs, n_env * h->obs_dim * sizeof(float))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_reward, n_env * sizeof(double))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_term, n_env)) != cudaSuccess ||
-      (e = cudaMallocHost(&h->h_init, n_env * 9 * sizeof(double))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_init, n_env * h->init_dim * sizeof(double))) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMemset(h->state, 0, state_bytes)) != cudaSuccess) {
     std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
@@ -315,10 +346,10 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   }
   fill_args<double>(*cfg, h->stride, h->a64);
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
-  h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim;
+  h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
   fill_args<float>(*cfg, h->stride, h->a32);
   h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
-  h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim;
+  h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim; h->a32.head = (float *)h->head;
   *out = h;
   return SR_OK;
 }
@@ -326,7 +357,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -336,7 +367,7 @@ void sr_destroy(sr_handle *h) {
 
 int sr_obs_dim(const sr_handle *h) { return h ? h->obs_dim : 0; }
 int sr_action_dim(const sr_handle *h) { return h ? h->action_dim : 0; }
-int sr_init_dim(const sr_handle *h) { return h ? 9 : 0; }
+int sr_init_dim(const sr_handle *h) { return h ? h->init_dim : 0; }
 int64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
 
 int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init_dev, void *stream) {
@@ -344,14 +375,22 @@ int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init
   if (n < 0 || n > h->cfg.n_env) return fail(SR_E_INVALID, "sr_reset: n out of range");
   if (n == 0) return SR_OK;
   SR_CUDA(cudaSetDevice(h->cfg.device));
-  if (h->cfg.dtype == SR_DTYPE_F32)
-    sr::rod_reset_kernel<float><<<n, 64, 0, (cudaStream_t)stream>>>(
+  const int nblk = n * h->n_rod;
+  if (h->cfg.dtype == SR_DTYPE_F32) {
+    sr::rod_reset_kernel<float><<<nblk, 64, 0, (cudaStream_t)stream>>>(
         (float *)h->state, (float *)h->bc, (float *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-        h->stride, h->cfg.base_length);
-  else
-    sr::rod_reset_kernel<double><<<n, 64, 0, (cudaStream_t)stream>>>(
+        h->stride, h->cfg.base_length, h->n_rod, h->init_dim);
+    if (h->cfg.has_head)
+      sr::head_reset_kernel<float><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+          (float *)h->head, env_idx_dev, n, init_dev, h->init_dim, h->n_rod, h->cfg.head_length);
+  } else {
+    sr::rod_reset_kernel<double><<<nblk, 64, 0, (cudaStream_t)stream>>>(
         (double *)h->state, (double *)h->bc, (double *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-        h->stride, h->cfg.base_length);
+        h->stride, h->cfg.base_length, h->n_rod, h->init_dim);
+    if (h->cfg.has_head)
+      sr::head_reset_kernel<double><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+          (double *)h->head, env_idx_dev, n, init_dev, h->init_dim, h->n_rod, h->cfg.head_length);
+  }
   h->launches++;
   SR_CUDA(cudaGetLastError());
   return SR_OK;
@@ -367,7 +406,7 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
     sr::RodArgs<float> A = h->a32;
     A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
     A.n_substeps = n_substeps;
-    const int nt = packed_threads_setting(h->cfg.n_elem);
+    const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head);
     return nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
                      : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
   }
@@ -400,8 +439,8 @@ int sr_reset_host(sr_handle *h, const int32_t *env_idx_host, int n, const double
   if (n == 0) return SR_OK;
   SR_CUDA(cudaSetDevice(h->cfg.device));
   cudaStream_t s = h->own_stream;
-  memcpy(h->h_init, init_host, (size_t)n * 9 * sizeof(double));
-  SR_CUDA(cudaMemcpyAsync(h->d_init, h->h_init, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice, s));
+  memcpy(h->h_init, init_host, (size_t)n * h->init_dim * sizeof(double));
+  SR_CUDA(cudaMemcpyAsync(h->d_init, h->h_init, (size_t)n * h->init_dim * sizeof(double), cudaMemcpyHostToDevice, s));
   if (env_idx_host)
     SR_CUDA(cudaMemcpyAsync(h->d_idx, env_idx_host, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   int rc = sr_reset(h, env_idx_host ? h->d_idx : nullptr, n, h->d_init, s);
@@ -437,7 +476,8 @@ int sr_step_host(sr_handle *h, const float *action_host, int n_substeps, float *
 int sr_get_state(sr_handle *h, sr_state_view *out) {
   if (!h || !out) return fail(SR_E_INVALID, "sr_get_state: null argument");
   out->base = h->state;
-  out->n_env = h->cfg.n_env; out->n_fields = sr::N_FIELDS; out->stride = h->stride;
+  out->n_env = h->cfg.n_env * h->n_rod;   /* rod rows: env-major, rod-minor */
+  out->n_fields = sr::N_FIELDS; out->stride = h->stride;
   out->elem_size = (int32_t)h->elem_size;
   out->f_position = sr::F_POS; out->f_velocity = sr::F_VEL; out->f_director = sr::F_DIR;
   out->f_omega = sr::F_OMEGA; out->f_tangents = sr::F_TAN; out->f_kappa = sr::F_KAPPA;
@@ -450,13 +490,21 @@ int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev) {
   if (h->cfg.math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_get_rest_kappa: rest curvature is built for SR_MATH_FAST only");
   if (!h->rest_kappa) {
     SR_CUDA(cudaSetDevice(h->cfg.device));
-    size_t bytes = (size_t)h->cfg.n_env * 3 * h->stride * h->elem_size;
+    size_t bytes = (size_t)h->cfg.n_env * h->n_rod * 3 * h->stride * h->elem_size;
     SR_CUDA(cudaMalloc(&h->rest_kappa, bytes));
     SR_CUDA(cudaMemset(h->rest_kappa, 0, bytes));
     h->a64.rest_kappa = (const double *)h->rest_kappa;
     h->a32.rest_kappa = (const float *)h->rest_kappa;
   }
   *rest_kappa_dev = h->rest_kappa;
+  return SR_OK;
+}
+
+int sr_get_head(sr_handle *h, void **head_dev, int32_t *dim) {
+  if (!h || !head_dev || !dim) return fail(SR_E_INVALID, "sr_get_head: null argument");
+  if (!h->cfg.has_head) return fail(SR_E_INVALID, "sr_get_head: this handle has no rigid head");
+  *head_dev = h->head;
+  *dim = sr::HEAD_DIM;
   return SR_OK;
 }
 
@@ -469,11 +517,11 @@ int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim) {
 
 int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream) {
   if (!h || !src || !src->base) return fail(SR_E_INVALID, "sr_set_state: null argument");
-  if (src->n_env != h->cfg.n_env || src->n_fields != sr::N_FIELDS || src->stride != h->stride ||
+  if (src->n_env != h->cfg.n_env * h->n_rod || src->n_fields != sr::N_FIELDS || src->stride != h->stride ||
       src->elem_size != (int32_t)h->elem_size)
     return fail(SR_E_INVALID, "sr_set_state: layout mismatch");
   SR_CUDA(cudaSetDevice(h->cfg.device));
-  size_t bytes = (size_t)h->cfg.n_env * sr::N_FIELDS * h->stride * h->elem_size;
+  size_t bytes = (size_t)h->cfg.n_env * h->n_rod * sr::N_FIELDS * h->stride * h->elem_size;
   SR_CUDA(cudaMemcpyAsync(h->state, src->base, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return SR_OK;
 }

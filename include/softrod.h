@@ -72,7 +72,7 @@ typedef struct sr_config {
   int32_t point_force_on_base; /* F_ext[0,0] = action[env,0] each substep (build.py:94-105) */
   int32_t damping_before_constraints; /* 1: [dampen_rates, constrain_rates] */
   int32_t laplace_filter_order;       /* LaplaceDissipationFilter order, 0 = off */
-  int32_t reserved0;
+  int32_t n_rod_per_env; /* rods per environment; 0 or 1 = single rod.  > 1: multi-rod assembly (octopus) */
   double dt;            /* substep */
   double base_length, base_radius, density, youngs_modulus;
   double shear_modulus; /* <= 0: PyElastica default E/(2(1+0.5)) */
@@ -90,6 +90,15 @@ typedef struct sr_config {
   double plane_origin[3], plane_normal[3];
   double contact_k, contact_nu, slip_velocity_tol, surface_tol;
   double static_mu[3], kinetic_mu[3];
+  /* Multi-rod assembly (envs/octopus/build.py:52-217): n_rod_per_env arms + (has_head) one rigid Cylinder
+   * head held upright by BodyBoundaryCondition and tied to node 0 / element 0 of every arm by a
+   * FixedJoint2Rigid(k, nu, kt, angle, radius) (utils/custom_elastica/joint.py, constraint.py).
+   * joint_angle_deg[a] is arm a's mounting angle.  sr_reset then expects 9*(n_rod+1) doubles per env:
+   * start/direction/normal of every arm followed by those of the head cylinder. */
+  int32_t has_head, reserved1;
+  double head_length, head_radius, head_density;
+  double joint_k, joint_nu, joint_kt, joint_radius;
+  double joint_angle_deg[16];
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -154,9 +163,14 @@ int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
  * (0-2 position, 3-5 velocity, 6 last tilt angle, `info["tilt"]` of soft_pendulum_3d.py:157). */
 int sr_get_aux(sr_handle *h, void **aux_dev, int32_t *dim);
 
+/* Rigid head of a multi-rod assembly, [n_env][*dim] of the handle's dtype:
+ * 0-2 position, 3-5 velocity, 6-14 directors (rows), 15-17 omega, 18 pinned height. */
+int sr_get_head(sr_handle *h, void **head_dev, int32_t *dim);
+
 /* Per-env rest curvature (the actuation of the octopus-arm envs: `rod.rest_kappa[0, :] = ...`,
  * envs/octopus/arm_single_env.py:226-235, flat_env.py:288-311), [n_env][3][stride] of the handle's
- * dtype, Voronoi points in slots 0..n_elem-2; allocated on first use, zero-initialised. */
+ * dtype (n_env * n_rod_per_env rows for assemblies), Voronoi points in slots 0..n_elem-2; allocated on
+ * first use, zero-initialised. */
 int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev);
 
 /* number of kernels this library launched on behalf of the handle so far */

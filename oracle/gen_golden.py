@@ -143,6 +143,41 @@ def gen_arm_single(seed=42, n=5):
     print("arm_single:", rew, term)
 
 
+def gen_octo_flat(seed=42, n=3, recording_fps=50):
+    """OctoFlat-v0 (8 arms + rigid head + FixedJoint2Rigid joints + plane contact, rest-curvature
+    actuation).  recording_fps=50 (285 substeps per env-step instead of 2857) keeps the NumPy run short;
+    every other parameter is the registered default."""
+    env = ref_loader.load_reference_env("OctoFlat-v0", recording_fps=recording_fps)
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    out = {"label": LABEL + "; synchronize = [contact, forcing, connections], rates = [damping, constraints] (B-1/B-2)",
+           "seed": seed, "recording_fps": recording_fps, "step_skip": e.step_skip, "target": e._target.copy(),
+           "obs0/individual": obs0["individual"], "obs0/shared": obs0["shared"]}
+
+    def snap(tag):
+        for a, rod in enumerate(e.shearable_rods):
+            pack(f"{tag}/arm{a}", rod_state(rod), out)
+        h = e.rigid_rod
+        out[f"{tag}/head/position"] = h.position_collection.copy()
+        out[f"{tag}/head/velocity"] = h.velocity_collection.copy()
+        out[f"{tag}/head/director"] = h.director_collection.copy()
+        out[f"{tag}/head/omega"] = h.omega_collection.copy()
+
+    snap("state0")
+    acts, rew, term, trunc = [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); rew.append(r); term.append(te); trunc.append(tr)
+        out[f"obs{i + 1}/individual"], out[f"obs{i + 1}/shared"] = o["individual"], o["shared"]
+        snap(f"state{i + 1}")
+    out.update(actions=np.array(acts, dtype=np.float32), reward=np.array(rew, dtype=np.float64),
+               terminated=np.array(term), truncated=np.array(trunc))
+    np.savez_compressed(os.path.join(OUT, f"octo_flat_seed{seed}.npz"), **out)
+    print("octo_flat:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gen_soft_pendulum_substeps()
@@ -151,3 +186,4 @@ if __name__ == "__main__":
     gen_soft_pendulum_3d()
     gen_soft_pendulum_episode()
     gen_arm_single()
+    gen_octo_flat()

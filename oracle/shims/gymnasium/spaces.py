@@ -74,3 +74,32 @@ class Box(Space):
 
     def __repr__(self):
         return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+
+class Dict(Space):
+    """`gymnasium.spaces.Dict` stand-in: an ordered mapping of sub-spaces."""
+
+    def __init__(self, spaces=None, seed=None, **kw):
+        self.spaces = dict(spaces or {}, **kw)
+        super().__init__(None, None, seed)
+
+    def __getitem__(self, k):
+        return self.spaces[k]
+
+    def sample(self):
+        return {k: s.sample() for k, s in self.spaces.items()}
+
+    def contains(self, x):
+        return isinstance(x, dict) and all(k in x and s.contains(x[k]) for k, s in self.spaces.items())
+
+
+class Discrete(Space):
+    def __init__(self, n, seed=None, start=0):
+        self.n, self.start = int(n), int(start)
+        super().__init__((), np.int64, seed)
+
+    def sample(self):
+        return np.int64(self.start + self.np_random.integers(self.n))
+
+    def contains(self, x):
+        return self.start <= int(x) < self.start + self.n

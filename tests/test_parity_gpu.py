@@ -395,3 +395,34 @@ def test_arm_single_env_golden(golden_dir):
         assert abs(r - float(g["reward"][i])) < 1e-6
         assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
     env.close()
+
+
+def test_octo_flat_env_golden(golden_dir):
+    """§8 a12/a13/a15 (config 4 topology): OctoFlat-v0 — 8 arms + rigid head + FixedJoint2Rigid joints +
+    plane contact — through the Gymnasium facade vs the reference-env-on-shim fixture (recording_fps=50)."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "octo_flat_seed42.npz"))
+    env = gsb.make("OctoFlat-v0", recording_fps=int(g["recording_fps"]))
+    assert env.step_skip == int(g["step_skip"])
+    obs0, _ = env.reset(seed=42)
+    np.testing.assert_allclose(env._target, g["target"], rtol=0, atol=0)
+    np.testing.assert_allclose(obs0["individual"], g["obs0/individual"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(obs0["shared"], g["obs0/shared"], rtol=1e-6, atol=1e-7)
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        st = env.state()
+        for arm in range(8):
+            for gk, fk in (("position", "position_collection"), ("velocity", "velocity_collection"),
+                           ("director", "director_collection"), ("omega", "omega_collection")):
+                err = rel(st[fk][arm], g[f"state{i + 1}/arm{arm}/{gk}"])
+                assert err < 1e-8, f"step {i} arm {arm} {gk}: {err:.3e}"
+        hd = st["head"]
+        assert rel(hd[0:3], g[f"state{i + 1}/head/position"][:, 0]) < 1e-8
+        assert rel(hd[3:6], g[f"state{i + 1}/head/velocity"][:, 0]) < 1e-8
+        assert rel(hd[6:15].reshape(3, 3), g[f"state{i + 1}/head/director"][:, :, 0]) < 1e-8
+        assert rel(hd[15:18], g[f"state{i + 1}/head/omega"][:, 0]) < 1e-8
+        np.testing.assert_allclose(obs["individual"], g[f"obs{i + 1}/individual"], rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(obs["shared"], g[f"obs{i + 1}/shared"], rtol=1e-4, atol=1e-6)
+        assert abs(r - float(g["reward"][i])) < 1e-6
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+    env.close()
