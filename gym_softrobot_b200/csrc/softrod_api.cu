@@ -227,8 +227,13 @@ int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   }
   if (forced) return forced;
   const int tpr = (n_rod > 1 ? n_rod : 1) * (n_elem + 1) + has_head;   // threads per env group
-  const double u256 = (double)((256 / tpr) * tpr) / 256.0, u512 = (double)((512 / tpr) * tpr) / 512.0;
-  return (u512 > u256 + 0.02) ? 512 : 256;
+  auto util = [&](int nt) { return (double)((nt / tpr) * tpr) / nt; };
+  // 2 x 256 (128 regs) is the default; 1 x 384 (168 regs) / 1 x 512 (128 regs) only when they waste
+  // clearly fewer lanes for this group size
+  int best = 256;
+  if (util(384) > util(best) + 0.02) best = 384;
+  if (util(512) > util(best) + 0.02) best = 512;
+  return best;
 }
 
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
@@ -236,7 +241,7 @@ template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cud
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head), mb = min_ctas_setting();
     if (nt == 512) return launch_packed<T, 512, 1>(h, A, s);
     if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
-    if (nt == 384) return launch_packed<T, 384, 2>(h, A, s);
+    if (nt == 384) return launch_packed<T, 384, 1>(h, A, s);
     if (mb == 3) return launch_packed<T, 256, 3>(h, A, s);
     return launch_packed<T, 256, 2>(h, A, s);
   }
@@ -407,8 +412,9 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
     A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
     A.n_substeps = n_substeps;
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head);
-    return nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
-                     : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
+    return nt == 512   ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
+           : nt == 384 ? launch_packed<float, 384, 1>(h, A, (cudaStream_t)stream)
+                       : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
   }
   sr::RodArgs<double> A = h->a64;
   A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;

@@ -130,7 +130,12 @@ class ArmSingleVectorEnv:
         action = action.to(device=self.device, dtype=torch.float32).reshape(self.n_env, self.n_action)
         self.prev_action = action.clone()
         # set_action: rest_kappa[0, :] = cubic interpolation of the 7 control values
-        self.handle.rest_kappa_tensor()[:, 0, :] = action.double() @ self._W.T
+        # fixed-order accumulation instead of a GEMM: results must not depend on the batch size
+        a64 = action.double()
+        kap = a64[:, 0:1] * self._W[:, 0]
+        for k in range(1, self.n_action):
+            kap = kap + a64[:, k:k + 1] * self._W[:, k]
+        self.handle.rest_kappa_tensor()[:, 0, :] = kap
         obs6, rew, term = self._scratch
         self.handle.step(None, self.step_skip, obs6, rew, term)
         self.step_count += 1

@@ -142,7 +142,12 @@ class OctoFlatVectorEnv:
         torch = self.torch
         action = action.to(device=self.device, dtype=torch.float32).reshape(self.n_env, self.n_arm * self.n_action)
         self.prev_action = action.clone()
-        kap = action.double().reshape(self.n_env, self.n_arm, self.n_action) @ self._W.T     # [N, arm, n_seg]
+        # rest curvature = W a, accumulated control point by control point (fixed order: a GEMM would
+        # pick batch-size dependent kernels and make results depend on n_env at the 1e-16 level)
+        a3 = action.double().reshape(self.n_env, self.n_arm, self.n_action)
+        kap = a3[:, :, 0:1] * self._W[:, 0]
+        for k in range(1, self.n_action):
+            kap = kap + a3[:, :, k:k + 1] * self._W[:, k]                                 # [N, arm, n_seg]
         self.handle.rest_kappa_tensor().unflatten(0, (self.n_env, self.n_arm))[:, :, 0, :] = kap
         hd = self.handle.head_tensor()
         xposbefore = hd[:, 0:2].clone()

@@ -426,3 +426,26 @@ def test_octo_flat_env_golden(golden_dir):
         assert abs(r - float(g["reward"][i])) < 1e-6
         assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
     env.close()
+
+
+def test_octo_flat_batched_consistency():
+    """Batched OctoFlat: envs are independent — every env fed the same actions evolves bit-identically
+    wherever it sits in the batch / CTA, and matches a batch of one."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    acts = torch.as_tensor(np.random.default_rng(3).uniform(-22, 22, size=(2, 24)).astype(np.float32), device="cuda")
+    outs = []
+    for n_env in (1, 37):
+        env = gsb.make_vec("OctoFlat-v0", n_env, recording_fps=100, autoreset=False)
+        env.reset(seed=5)
+        for s in range(2):
+            obs, rew, term, trunc, info = env.step(acts[s].expand(n_env, 24))
+        torch.cuda.synchronize()
+        outs.append((env.handle.state_tensor().clone(), env.handle.head_tensor().clone(), rew.clone()))
+        assert int(term.sum()) == 0
+        env.close()
+    (s1, h1, r1), (s37, h37, r37) = outs
+    s37 = s37.reshape(37, 8, *s37.shape[1:])
+    assert torch.equal(s37[0].expand_as(s37), s37) and torch.equal(h37[0].expand_as(h37), h37)
+    assert torch.equal(s37[0], s1.reshape(8, *s1.shape[1:])) and torch.equal(h37[0], h1[0])
+    assert torch.isfinite(s37).all()
