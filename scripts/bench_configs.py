@@ -46,4 +46,27 @@ env = g.make_vec("SoftPendulum3D-v0", n_env, autoreset=False); env.reset(seed=42
 a = (torch.rand((n_env, 2), device="cuda") * 2 - 1).float()
 report("SoftPendulum3D-v0", n_env, 50, 400, timed(lambda: env.handle.step(a, 400, env.obs, env.reward, env.terminated)), 440 + 168)
 env.close()
+# config 5 topology: free rod on a frictional plane, rest-curvature actuation (OctoArmSingle-v0, n=50; and n=200)
+from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD
+for n_elem, dt in ((50, 7e-5), (200, 2e-5)):
+    n_env = 4096
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elem, dt=dt, gravity=(0, 0, -9.81), damping_constant=1e-2,
+                   bc_kind=nat.BC_FREE, contact=arm_contact_params(), **_ROD)
+    init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+    h.reset_host(init)
+    h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.random.default_rng(1).uniform(-5, 5, (n_env, 1)) * np.ones((1, n_elem - 1)), device="cuda")
+    obs = torch.empty((n_env, 6), dtype=torch.float32, device="cuda"); rew = torch.empty(n_env, dtype=torch.float64, device="cuda"); term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+    report(f"rod on frictional plane n={n_elem} (config 5 topology)", n_env, n_elem, 400, timed(lambda: h.step(None, 400, obs, rew, term), K=5), 440 + 280)
+    assert int(term.sum()) == 0
+    h.close()
+# config 4: 8-arm assembly with head + joints + contact (OctoFlat topology), n_elem = 10 (registered env) and 40 (BASELINE)
+from gym_softrobot_b200.envs.octo_flat import OctoFlatVectorEnv
+# n_elem = 40 needs dt <= 3e-5: the k = 1e6 joint spring on a 0.67 g end node has w dt = 2.7 at 7e-5
+for n_elem, n_env, dt in ((10, 16384, 7e-5), (40, 16384, 3e-5)):
+    env = OctoFlatVectorEnv(n_env, n_elems=n_elem, time_step=dt, autoreset=False); env.reset(seed=42)
+    env.handle.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.random.default_rng(2).uniform(-5, 5, (n_env * 8, 1)) * np.ones((1, n_elem - 1)), device="cuda")
+    o6, rew, term = env._scratch
+    report(f"8-arm assembly n_elem={n_elem} (config 4 topology)", n_env, 8 * n_elem, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=5), 440 + 280)
+    assert int(term.sum()) == 0
+    env.close()
 print("fp64 peak", peak)
