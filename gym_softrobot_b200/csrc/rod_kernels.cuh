@@ -160,7 +160,9 @@ template <typename T> __device__ __forceinline__ void rotate_directors_ref(T a0,
 // fast path: R = I + A K + B K^2 with A = sin(t)/t, B = (1-cos t)/t^2, applied as Q += D Q.
 // `eps` carries the reference's guard: axis = a/(|a| + 1e-14) shortens each half-step
 // rotation by 1e-14 rad (2e-14 for a merged full step):  A *= rho, B *= rho^2 with
-// rho = 1 - eps/sqrt(q + eps^2)  (-> 0 as |a| -> 0, like the reference).
+// rho = 1 - eps/sqrt(q + eps^2)  (-> 0 as |a| -> 0, like the reference).  Measured: dropping this
+// guard moves the velocity error after 2400 substeps from 2e-11 to 5e-10 (it is a systematic 2e-10
+// relative slow-down of every rotation), for a 1 % speed-up — it stays.
 template <typename T>
 __device__ __forceinline__ void rotate_directors_fast(const PolyCoef<T> &C, T a0, T a1, T a2, T q, T eps,
                                                       T (&Q)[9]) {
