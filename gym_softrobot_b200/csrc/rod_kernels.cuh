@@ -730,8 +730,10 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
       T *b = bc + (size_t)env * BC_DIM;
       for (int c = 0; c < 3; c++) b[c] = (T)xk[c];
       for (int c = 0; c < 9; c++) b[3 + c] = (T)Qk[c];
-      T *a = aux + (size_t)env * AUX_DIM;
-      for (int c = 0; c < AUX_DIM; c++) a[c] = T(0);
+      if (arm == 0) {   // aux is per environment, not per rod
+        T *a = aux + (size_t)(env / n_rod) * AUX_DIM;
+        for (int c = 0; c < AUX_DIM; c++) a[c] = T(0);
+      }
     }
   }
 }

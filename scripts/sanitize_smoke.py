@@ -1,0 +1,29 @@
+"""Tiny run of every kernel variant, meant to be executed under compute-sanitizer (racecheck / memcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import gym_softrobot_b200 as g
+from gym_softrobot_b200 import _native as nat
+from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD
+
+K = 6
+env = g.make_vec("SoftPendulum-v0", 7, autoreset=False); env.reset(seed=1)
+env.handle.step(torch.ones((7, 1), device="cuda"), K, env.obs, env.reward, env.terminated); env.close()
+env = g.make_vec("SoftPendulum-v0", 7, autoreset=False, dtype="float32"); env.reset(seed=1)
+env.handle.step(torch.ones((7, 1), device="cuda"), K, env.obs, env.reward, env.terminated); env.close()
+env = g.make_vec("SoftPendulum-v0", 3, autoreset=False, math=nat.MATH_FAITHFUL); env.reset(seed=1)
+env.handle.step(torch.ones((3, 1), device="cuda"), K, env.obs, env.reward, env.terminated); env.close()
+env = g.make_vec("SoftPendulum3D-v0", 6, autoreset=False); env.reset(seed=1)
+env.handle.step(torch.full((6, 2), 0.5, device="cuda"), K, env.obs, env.reward, env.terminated); env.close()
+h = nat.Handle(model=nat.MODEL_ROD, n_env=5, n_elem=100, dt=5e-5, base_length=1.0, base_radius=0.025, density=1000.0,
+               youngs_modulus=1e6, gravity=(0, -9.80665, 0), damping_constant=2e-3, bc_kind=nat.BC_ONE_END_FIXED)
+init = np.zeros((5, 9)); init[:, 3] = 1; init[:, 7] = 1; h.reset_host(init); h.step_host(None, K); h.close()
+h = nat.Handle(model=nat.MODEL_ROD, n_env=6, n_elem=50, dt=7e-5, gravity=(0, 0, -9.81), damping_constant=1e-2,
+               bc_kind=nat.BC_FREE, contact=arm_contact_params(), **_ROD)
+init = np.zeros((6, 9)); init[:, 3] = 1; init[:, 8] = 1; h.reset_host(init); h.rest_kappa_tensor()[:, 0, :] = 3.0
+h.step_host(None, K); h.close()
+env = g.make_vec("OctoFlat-v0", 5, autoreset=False); env.reset(seed=1)
+env.handle.rest_kappa_tensor()[:, 0, :] = 2.0
+o6, rew, term = env._scratch
+env.handle.step(None, K, o6, rew, term); torch.cuda.synchronize(); env.close()
+print("sanitize_smoke done")
