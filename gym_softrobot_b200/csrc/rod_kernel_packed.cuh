@@ -15,7 +15,7 @@
 
 namespace sr {
 
-constexpr int PACKED_MAX_THREADS = 512;
+constexpr int PACKED_MAX_THREADS = 1024;
 
 // row stride of the exchange arrays: slot NT is a permanent zero (what the stencils see to
 // the left of element 0), so the base thread needs no select when it reads "j-1"

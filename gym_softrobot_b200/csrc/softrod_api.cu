@@ -183,7 +183,7 @@ bool use_packed_kernel(const sr_handle *h) {
     const char *e = getenv("SOFTROD_KERNEL");
     v = (e && strcmp(e, "warp") == 0) ? 0 : 1;
   }
-  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 256;
+  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 1024;
 }
 
 template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI>
@@ -223,7 +223,7 @@ int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   if (forced < 0) {
     const char *e = getenv("SOFTROD_PACKED_THREADS");
     forced = e ? atoi(e) : 0;
-    if (forced != 256 && forced != 320 && forced != 384 && forced != 512) forced = 0;
+    if (forced != 256 && forced != 320 && forced != 384 && forced != 512 && forced != 1024) forced = 0;
   }
   if (forced) return forced;
   const int tpr = (n_rod > 1 ? n_rod : 1) * (n_elem + 1) + has_head;   // threads per env group
@@ -233,12 +233,14 @@ int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   int best = 256;
   if (util(384) > util(best) + 0.02) best = 384;
   if (util(512) > util(best) + 0.02) best = 512;
+  if (tpr > 512) best = 1024;   // long rods: one rod per 1024-thread CTA (64 registers: functional, not fast)
   return best;
 }
 
 template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_packed_kernel(h)) {
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head), mb = min_ctas_setting();
+    if (nt == 1024) return launch_packed<T, 1024, 1>(h, A, s);
     if (nt == 512) return launch_packed<T, 512, 1>(h, A, s);
     if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
     if (nt == 384) return launch_packed<T, 384, 1>(h, A, s);
@@ -266,10 +268,10 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   if (cfg->struct_size != (int32_t)sizeof(sr_config))
     return fail(SR_E_INVALID, "sr_create: sr_config.struct_size mismatch (ABI skew)");
   if (cfg->n_env <= 0 || cfg->n_elem < 3) return fail(SR_E_INVALID, "sr_create: n_env > 0 and n_elem >= 3 required");
-  if (cfg->n_elem > 255) return fail(SR_E_INVALID, "sr_create: n_elem <= 255 in this build");
+  if (cfg->n_elem > 1023) return fail(SR_E_INVALID, "sr_create: n_elem <= 1023 in this build (one rod per CTA)");
   if (cfg->n_elem > 127 && cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: faithful math supports n_elem <= 127");
   if (cfg->dtype != SR_DTYPE_F64 && cfg->dtype != SR_DTYPE_F32) return fail(SR_E_INVALID, "sr_create: bad dtype");
-  if (cfg->dtype == SR_DTYPE_F32 && (cfg->math != SR_MATH_FAST || cfg->n_elem > 255))
+  if (cfg->dtype == SR_DTYPE_F32 && cfg->math != SR_MATH_FAST)
     return fail(SR_E_INVALID, "sr_create: SR_DTYPE_F32 is built for SR_MATH_FAST (packed kernel) only");
   if (cfg->model != SR_MODEL_ROD && cfg->model != SR_MODEL_SOFT_PENDULUM && cfg->model != SR_MODEL_SOFT_PENDULUM_3D)
     return fail(SR_E_INVALID, "sr_create: unsupported model");
@@ -285,8 +287,8 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     if (cfg->math != SR_MATH_FAST || cfg->model != SR_MODEL_ROD || cfg->bc_kind != SR_BC_FREE || cfg->laplace_filter_order != 0)
       return fail(SR_E_INVALID, "sr_create: multi-rod assemblies need SR_MATH_FAST, SR_MODEL_ROD, SR_BC_FREE, no Laplace filter");
     if (nr > 16) return fail(SR_E_INVALID, "sr_create: at most 16 rods per environment");
-    if (nr * (cfg->n_elem + 1) + (cfg->has_head ? 1 : 0) > 512)
-      return fail(SR_E_INVALID, "sr_create: one environment must fit a 512-thread CTA");
+    if (nr * (cfg->n_elem + 1) + (cfg->has_head ? 1 : 0) > 1024)
+      return fail(SR_E_INVALID, "sr_create: one environment must fit a 1024-thread CTA");
     if (cfg->has_head && (!(cfg->head_length > 0.0) || !(cfg->head_radius > 0.0) || !(cfg->head_density > 0.0)))
       return fail(SR_E_INVALID, "sr_create: head_length, head_radius, head_density must be > 0");
   }
@@ -412,7 +414,8 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
     A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
     A.n_substeps = n_substeps;
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head);
-    return nt == 512   ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
+    return nt == 1024  ? launch_packed<float, 1024, 1>(h, A, (cudaStream_t)stream)
+           : nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
            : nt == 384 ? launch_packed<float, 384, 1>(h, A, (cudaStream_t)stream)
                        : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
   }

@@ -449,3 +449,41 @@ def test_octo_flat_batched_consistency():
     assert torch.equal(s37[0].expand_as(s37), s37) and torch.equal(h37[0].expand_as(h37), h37)
     assert torch.equal(s37[0], s1.reshape(8, *s1.shape[1:])) and torch.equal(h37[0], h1[0])
     assert torch.isfinite(s37).all()
+
+
+def test_long_slender_rod_with_contact_fp64_and_fp32():
+    """BASELINE config 5: long slender rod, n_elem = 512, ground contact + anisotropic friction,
+    FP64 vs oracle (1e-9) and the FP32 mode next to it (positions / directors to 1e-4)."""
+    import torch
+    import rod_oracle as ro
+    from gym_softrobot_b200.envs.arm_single import arm_contact_params
+    nat = _native()
+    n, dt, L, r = 512, 5e-6, 1.0, 0.005
+    c = arm_contact_params()
+    c["plane_origin"] = [0.0, 0.0, -r]
+    rod_kw = dict(base_length=L, base_radius=r, density=1000.0, youngs_modulus=1e6)
+    n_env = 3
+    init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+    rk = np.random.default_rng(9).uniform(-3, 3, size=(n_env, 1)) * np.sin(np.linspace(0, 3 * np.pi, n - 1))[None, :]
+    rods = [ro.OracleRod(n, [0, 0, 0], [1.0, 0, 0], [0, 0, 1.0], L, r, 1000.0, 1e6, dt, gravity=(0.0, 0.0, -9.81),
+                         damping_constant=1e-2, contact=c) for _ in range(n_env)]
+    for i, o in enumerate(rods):
+        o.rest_kappa[0, :] = rk[i]
+        o.substeps(400)
+    # rates: the rod has barely started to move after 2 ms (|v|max ~ 1.5e-4 m/s) while position round-off
+    # (1e-16 m) times the stiff frequency c/dl = 1.6e4 1/s is ~2e-12 m/s: the relative floor is ~1e-8 here
+    for dtype, tol_x, tol_r in ((nat.DTYPE_F64, TOL, 1e-7), (nat.DTYPE_F32, 1e-4, None)):
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, gravity=(0.0, 0.0, -9.81),
+                       damping_constant=1e-2, bc_kind=nat.BC_FREE, contact=c, dtype=dtype, **rod_kw)
+        h.reset_host(init)
+        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(rk, device="cuda").to(h.rest_kappa_tensor().dtype)
+        obs, rew, term = h.step_host(None, 400)
+        f = {k: v.double().cpu().numpy() for k, v in h.fields().items()}
+        assert term.sum() == 0
+        for i, o in enumerate(rods):
+            assert rel(f["position_collection"][i], o.position_collection) < tol_x
+            assert rel(f["director_collection"][i], o.director_collection) < tol_x
+            if tol_r is not None:
+                assert rel(f["velocity_collection"][i], o.velocity_collection) < tol_r
+                assert rel(f["omega_collection"][i], o.omega_collection) < tol_r
+        h.close()
