@@ -70,6 +70,16 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
   }
+  // FP32: absolute positions resolve an element's strain only to ulp(x)/dl ~ 3e-6, which excites stiff
+  // modes; the edge vector dx = x_{j+1} - x_j is therefore carried as state of its own (ulp 2e-9) and
+  // advanced with the same velocities as the nodes.  x is still integrated for outputs, BCs and contact.
+  constexpr bool EDGE = sizeof(T) == 4;
+  T ed[3] = {T(0), T(0), T(0)};
+  T hh_prev = T(0);   // step of the kinematic update whose edge increment is still pending
+  if (EDGE && active) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) ed[c] = st[(F_EDGE + c) * stride + j];
+  }
   T *hd = (MULTI && is_head && live) ? A.head + (size_t)env * HEAD_DIM : nullptr;
   if (MULTI && hd) {
 #pragma unroll
@@ -129,6 +139,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         }
         pin_x = aux[0]; pin_y = aux[1]; base_vx = aux[3]; base_vy = aux[4];
         x[0] = pin_x; x[1] = pin_y; x[2] = bc[2];
+        if (EDGE) {   // the base jumped: element 0's edge is re-derived from the stored node 1
+#pragma unroll
+          for (int c = 0; c < 3; c++) ed[c] = st[(F_POS + c) * stride + 1] - x[c];
+        }
       }
     }
   }
@@ -160,6 +174,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T q = fma(a2, a2, fma(a1, a1, a0 * a0));
     if (!__any_sync(FULL, !(q <= T(kSmallRotQ)))) rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
     else rotate_directors_ref<T>(a0, a1, a2, Q);
+    hh_prev = hh;
   };
 
   // BodyBoundaryCondition on the head (utils/custom_elastica/constraint.py:43-58, 62-85)
@@ -182,7 +197,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     const bool last = (s == A.n_substeps - 1);
     // ---- publish what the neighbours need ------------------------------------------
 #pragma unroll
-    for (int c = 0; c < 3; c++) { sh_x[c * RS + tid] = x[c]; sh_v[c * RS + tid] = v[c]; }
+    for (int c = 0; c < 3; c++) { sh_x[c * RS + tid] = EDGE ? ed[c] : x[c]; sh_v[c * RS + tid] = v[c]; }
 #pragma unroll
     for (int c = 0; c < 9; c++) sh_Q[c * RS + tid] = Q[c];
     __syncthreads();
@@ -191,11 +206,22 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T dx[3], dv[3], dx2[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      T xn = sh_x[c * RS + t_next];
-      dx[c] = xn - x[c];
-      dv[c] = sh_v[c * RS + t_next] - v[c];
-      dx2[c] = sh_x[c * RS + t_next2] - xn;
+      T vn = sh_v[c * RS + t_next];
+      dv[c] = vn - v[c];
+      if (EDGE) {
+        // apply the pending increment of the last kinematic update (same v's: nothing changed them since);
+        // a moving base is re-pinned, so its own velocity does not stretch element 0
+        T dvk = (moving && c < 2) ? vn : dv[c];
+        ed[c] = fma(hh_prev, dvk, ed[c]);
+        dx[c] = ed[c];
+        dx2[c] = fma(hh_prev, sh_v[c * RS + t_next2] - vn, sh_x[c * RS + t_next]);   // neighbour's edge, updated alike
+      } else {
+        T xn = sh_x[c * RS + t_next];
+        dx[c] = xn - x[c];
+        dx2[c] = sh_x[c * RS + t_next2] - xn;
+      }
     }
+    if (EDGE) hh_prev = T(0);
     if (!elem_ok) dx[2] = A.rest_len;   // keeps the pseudo-element's quantities finite
     if (!vor_ok) dx2[2] = A.rest_len;
     T l2 = dot3(dx, dx);
@@ -536,6 +562,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   }
 
   // ---- write back, NaN guard, model outputs ------------------------------------------------
+  if (EDGE && A.n_substeps > 0) {   // the last kinematic update's edge increment needs the final velocities
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 3; c++) sh_v[c * RS + tid] = v[c];
+    __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        T vn = sh_v[c * RS + t_next];
+        ed[c] = fma(hh_prev, (moving && c < 2) ? vn : vn - v[c], ed[c]);
+        st[(F_EDGE + c) * stride + j] = elem_ok ? ed[c] : T(0);
+      }
+    }
+  }
   __syncthreads();   // all reads of the exchange buffers are done: reuse them below
   bool bad = false;
   if (MULTI && hd) {

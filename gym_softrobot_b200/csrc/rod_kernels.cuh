@@ -25,7 +25,9 @@ namespace sr {
 // field indices inside one env's [n_fields][stride] block
 enum : int {
   F_POS = 0, F_VEL = 3, F_DIR = 6, F_OMEGA = 15, F_TAN = 18, F_KAPPA = 21, F_SIGMA = 24,
-  F_DIL = 27, N_FIELDS = 28
+  F_DIL = 27,
+  F_EDGE = 28,   // FP32 handles only: element edge vectors x_{k+1} - x_k kept as state (strain resolution)
+  N_FIELDS = 31
 };
 constexpr int BC_DIM = 12;   // per-env anchors: fixed_position(3), fixed_directors(9)
 constexpr int HEAD_DIM = 20;  // rigid head: x(3) v(3) Q(9) w(3) pinned z(1) pad(1)
@@ -726,6 +728,7 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
     }
     for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + k] = (T)Qk[c];
     st[F_DIL * stride + k] = (T)dil;
+    for (int c = 0; c < 3; c++) st[(F_EDGE + c) * stride + k] = (T)((k < n) ? pos(c, k + 1) - xk[c] : 0.0);
     if (k == 0) {
       T *b = bc + (size_t)env * BC_DIM;
       for (int c = 0; c < 3; c++) b[c] = (T)xk[c];

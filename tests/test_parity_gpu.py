@@ -305,9 +305,10 @@ def test_soft_pendulum_3d_batched_vs_oracle():
 
 
 def test_fp32_mode_accuracy():
-    """Optional FP32 mode (north star: 1e-4 over 1000 substeps).  Measured: positions and directors
-    meet 1e-4; velocities / angular velocities carry stiff-mode noise from the FP32 absolute positions
-    (6e-3 / 2e-3) — a known gap, see DESIGN.md §5 (fix: compensated position update)."""
+    """Optional FP32 mode (north star: 1e-4 over 1000 substeps).  Measured after 1200 substeps: positions
+    1e-5 and directors 2e-5 (bar met); velocities 4e-4 (element edge vectors are carried as FP32 state so the
+    strain keeps ~1e-7 resolution; with absolute positions only it was 6e-3); angular velocities are
+    dominated by the reference's runaway base-element w1 (~1e5 rad/s), 2e-3 of that."""
     import rod_oracle
     from gym_softrobot_b200.envs.soft_pendulum import pendulum_init_params
     nat = _native()
@@ -327,8 +328,8 @@ def test_fp32_mode_accuracy():
             ob, r, te, tr, _ = o.step(acts[s][i])
             assert rel(f["position_collection"][i], o.rod.position_collection) < 1e-4
             assert rel(f["director_collection"][i], o.rod.director_collection) < 1e-4
-            assert rel(f["velocity_collection"][i], o.rod.velocity_collection) < 5e-2
-            assert rel(f["omega_collection"][i], o.rod.omega_collection) < 5e-2
+            assert rel(f["velocity_collection"][i], o.rod.velocity_collection) < 2e-3
+            assert rel(f["omega_collection"][i], o.rod.omega_collection) < 1e-2
             np.testing.assert_allclose(obs[i], ob, rtol=5e-3, atol=5e-3)
             assert bool(term[i]) == te
     assert h.state_tensor().dtype.itemsize == 4
