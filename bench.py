@@ -188,6 +188,7 @@ def run_ours(args):
     obs, rew, term = env.obs, env.reward, env.terminated
 
     fp64_peak = nat.measure_fp64_peak(local)
+    fp64_peak_3reg = nat.measure_fp64_peak(local, three_register_operands=True)
 
     # ---- device-resident leg: inputs already in HBM, one launch per step ----------
     for s in range(W):
@@ -269,6 +270,8 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": achieved_tflops / fp64_peak,
                          "peak_source": "DFMA-chain microbenchmark run live (sr_measure_fp64_peak)",
                          "flop_per_element_substep": FLOP_PER_ELEM_SUBSTEP, "traffic": traffic,
+                         "peak_three_register_operands": fp64_peak_3reg,
+                         "frac_of_three_register_peak": achieved_tflops / fp64_peak_3reg,
                          "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": achieved_gbs / hbm_peak, "peak_source": hbm_src}},
             "cpu_baseline": cpu_baseline,

@@ -238,13 +238,23 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     // sigma = e Q t - z = Q dx / l0 - z exactly (e t = dx / l0): no tangent needed here
     T Qdx[3], nst[3], sfl[3];
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      Qdx[i] = fma(Q[3 * i + 2], dx[2], fma(Q[3 * i + 1], dx[1], Q[3 * i] * dx[0]));
+    for (int i = 0; i < 3; i++) Qdx[i] = Q[3 * i] * dx[0];          // sweeps share dx[k] / nst[k]
+#pragma unroll
+    for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 1], dx[1], Qdx[i]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
       nst[i] = (i == 2) ? fma(A.S_over_l[i], Qdx[i], -A.S[i]) : A.S_over_l[i] * Qdx[i];
-    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
+#pragma unroll
+    for (int i = 0; i < 3; i++) sfl[i] = fma(Q[3 + i], nst[1], sfl[i]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) sfl[i] = fma(Q[6 + i], nst[2], sfl[i]);
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      sfl[i] = fma(Q[6 + i], nst[2], fma(Q[3 + i], nst[1], Q[i] * nst[0])) * inv_e_s;
+      sfl[i] *= inv_e_s;
       sh_s[i * RS + tid] = sfl[i];
     }
 

@@ -177,17 +177,26 @@ __device__ __forceinline__ void rotate_directors_fast(const PolyCoef<T> &C, T a0
   }
   T Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
   T Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
-  T D00 = -fma(Ba1, a1, Ba2 * a2), D11 = -fma(Ba0, a0, Ba2 * a2), D22 = -fma(Ba0, a0, Ba1 * a1);
-  T D01 = fma(Ba0, a1, Aa2), D10 = fma(Ba0, a1, -Aa2);
-  T D02 = fma(Ba0, a2, -Aa1), D20 = fma(Ba0, a2, Aa1);
-  T D12 = fma(Ba1, a2, Aa0), D21 = fma(Ba1, a2, -Aa0);
+  T D[9];
+  D[0] = -fma(Ba1, a1, Ba2 * a2); D[4] = -fma(Ba0, a0, Ba2 * a2); D[8] = -fma(Ba0, a0, Ba1 * a1);
+  D[1] = fma(Ba0, a1, Aa2); D[3] = fma(Ba0, a1, -Aa2);
+  D[2] = fma(Ba0, a2, -Aa1); D[6] = fma(Ba0, a2, Aa1);
+  D[5] = fma(Ba1, a2, Aa0); D[7] = fma(Ba1, a2, -Aa0);
+  // Q += D Q in three sweeps over k; inside a sweep the three FMAs of a row share D[i][k] (operand-reuse
+  // cache: a DFMA with three fresh register operands issues at 2/3 rate on B200)
   T n[9];
 #pragma unroll
-  for (int m = 0; m < 3; m++) {
-    n[0 + m] = fma(D02, Q[6 + m], fma(D01, Q[3 + m], fma(D00, Q[0 + m], Q[0 + m])));
-    n[3 + m] = fma(D12, Q[6 + m], fma(D11, Q[3 + m], fma(D10, Q[0 + m], Q[3 + m])));
-    n[6 + m] = fma(D22, Q[6 + m], fma(D21, Q[3 + m], fma(D20, Q[0 + m], Q[6 + m])));
-  }
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) n[3 * i + m] = fma(D[3 * i], Q[m], Q[3 * i + m]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) n[3 * i + m] = fma(D[3 * i + 1], Q[3 + m], n[3 * i + m]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) n[3 * i + m] = fma(D[3 * i + 2], Q[6 + m], n[3 * i + m]);
 #pragma unroll
   for (int i = 0; i < 9; i++) Q[i] = n[i];
 }
@@ -797,6 +806,24 @@ __global__ void dfma_peak_kernel(double *out, int iters) {
     a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
   }
   double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// same probe with three distinct 64-bit REGISTER operands per DFMA (what the rod kernel issues): shows
+// whether operand delivery from the register file, not the FMA units, caps the FP64 issue rate
+__global__ void dfma_peak_regs_kernel(double *out, const double *in, int iters) {
+  double a[8], b[8], c[8];
+  for (int i = 0; i < 8; i++) {
+    a[i] = in[(threadIdx.x + i) & 63]; b[i] = in[(threadIdx.x + 8 + i) & 63]; c[i] = in[(threadIdx.x + 16 + i) & 63];
+  }
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = fma(a[i], b[i], c[i]);
+#pragma unroll
+    for (int i = 0; i < 8; i++) b[i] = fma(b[i], c[(i + 1) & 7], a[(i + 3) & 7]);
+  }
+  double s = 0;
+  for (int i = 0; i < 8; i++) s += a[i] + b[i];
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 

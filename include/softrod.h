@@ -179,6 +179,10 @@ int64_t sr_launch_count(const sr_handle *h);
 /* Measure the device's FP64 FMA issue peak with a register-resident DFMA chain
  * (roofline denominator; not in MEASURED_PEAKS.json).  Returns TFLOP/s. */
 int sr_measure_fp64_peak(int device, double *tflops_out);
+/* Same probe with three distinct 64-bit register operands per DFMA (the common case in real code):
+ * on B200 the register file delivers two 64-bit operands per 2-cycle issue slot, so this rate is 2/3 of
+ * the figure above (24.7 vs 36.4 TFLOP/s measured).  Context for the roofline fraction, not its denominator. */
+int sr_measure_fp64_peak_regs(int device, double *tflops_out);
 
 #ifdef __cplusplus
 }
