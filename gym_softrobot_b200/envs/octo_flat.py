@@ -107,9 +107,14 @@ class OctoFlatVectorEnv:
             out.append((2 - 0.5) * np.random.Generator(np.random.PCG64(ss)).random(2) + 0.5)
         return np.array(out)
 
+    def _fields(self):
+        """Rod views with an explicit arm axis, [n_env, n_arm, ...], also for the single-arm Lite env."""
+        f = self.handle.fields()
+        return f if self.n_arm > 1 else {k: v.unsqueeze(1) for k, v in f.items()}
+
     def _obs(self):
         torch = self.torch
-        f, hd = self.handle.fields(), self.handle.head_tensor()
+        f, hd = self._fields(), self.handle.head_tensor()
         c = hd[:, None, 0:2, None]                                   # head centre (x, y)
         x, v = f["position_collection"], f["velocity_collection"]
         pa = self.prev_action.reshape(self.n_env, self.n_arm, self.n_action).double()
@@ -155,7 +160,7 @@ class OctoFlatVectorEnv:
         self.handle.step(None, self.step_skip, o6, rew, term)
         self.step_count += 1
         invalid = term.bool()
-        xy = self.handle.fields()["position_collection"][:, :, :2, :]            # [N, arm, 2, n+1]
+        xy = self._fields()["position_collection"][:, :, :2, :]                  # [N, arm, 2, n+1]
         crossing = torch.zeros(self.n_env, dtype=torch.int64, device=self.device)
         for i in range(self.n_arm - 1):                                          # pairs (i-1, i), as the reference
             crossing += count_crossings(xy[:, i - 1], xy[:, i])
@@ -186,7 +191,7 @@ class OctoFlatVectorEnv:
         return obs, reward, terminated, truncated, info
 
     def fields(self):
-        return self.handle.fields()
+        return self._fields()
 
     def close(self):
         self.handle.close()

@@ -103,3 +103,46 @@ def test_two_rank_gloo_sharding_and_stats(tmp_path):
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env, timeout=180)
     assert res.returncode == 0, res.stdout[-2000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_curvature_interp_matrices_match_scipy_calls():
+    """The actuation interpolation is linear in the action: the precomputed matrices must reproduce the
+    reference's per-step scipy calls (arm_single_env.py:229-234, flat_env.py:296-309)."""
+    from scipy.interpolate import interp1d
+    from gym_softrobot_b200.envs.arm_single import curvature_interp_matrix
+    from gym_softrobot_b200.envs.octo_flat import padded_curvature_interp_matrix
+    rng = np.random.default_rng(0)
+    a = rng.uniform(-22, 22, 7)
+    ref = interp1d(np.linspace(0, 1, 7), a, kind="cubic", axis=-1)(np.linspace(0, 1, 49))
+    np.testing.assert_allclose(curvature_interp_matrix(7, 49) @ a, ref, rtol=0, atol=1e-12)
+    a = rng.uniform(-22, 22, (8, 3))
+    padded = np.concatenate([np.zeros((8, 1)), a, np.zeros((8, 1))], axis=-1)
+    ref = interp1d(np.linspace(0, 1, 5), padded, kind="cubic", axis=-1)(np.linspace(0, 1, 9))
+    np.testing.assert_allclose(a @ padded_curvature_interp_matrix(3, 9).T, ref, rtol=0, atol=1e-12)
+
+
+def test_count_crossings_known_answers():
+    """Batched polyline-intersection count (utils/intersection.py semantics) on hand-made cases."""
+    import torch
+    from gym_softrobot_b200.envs.octo_flat import count_crossings
+    t = np.linspace(0, 1, 11)
+    line_a = np.stack([t, np.zeros_like(t)])                      # along x at y = 0
+    cross1 = np.stack([np.full_like(t, 0.52), t - 0.5])          # vertical through it: 1 crossing
+    apart = np.stack([t, np.full_like(t, 0.7)])                  # parallel above: 0
+    zig = np.stack([t, 0.3 * np.sin(3 * np.pi * t + 0.4)])       # sine: 3 crossings of y = 0 inside (0, 1)
+    p1 = torch.as_tensor(np.stack([line_a, line_a, line_a]))
+    p2 = torch.as_tensor(np.stack([cross1, apart, zig]))
+    assert count_crossings(p1, p2).tolist() == [1, 0, 3]
+
+
+def test_octopus_init_matches_reference_layout(golden_dir):
+    """Arm start points / directions of build_octopus (build.py:66-90) vs the fixture's initial state."""
+    from gym_softrobot_b200.envs.octo_flat import octopus_init_params
+    g = np.load(os.path.join(golden_dir, "octo_flat_seed42.npz"))
+    row = octopus_init_params(8)[0]
+    for a in range(8):
+        x0 = g[f"state0/arm{a}/position"][:, 0]
+        np.testing.assert_allclose(row[9 * a:9 * a + 3], x0, rtol=0, atol=1e-15)
+        d3 = g[f"state0/arm{a}/director"][2, :, 0]
+        np.testing.assert_allclose(row[9 * a + 3:9 * a + 6], d3, rtol=0, atol=1e-15)
+    np.testing.assert_allclose(g["state0/head/position"][:, 0], [0, 0, 0], atol=1e-18)
