@@ -127,7 +127,8 @@ def test_count_crossings_known_answers():
     from gym_softrobot_b200.envs.octo_flat import count_crossings
     t = np.linspace(0, 1, 11)
     line_a = np.stack([t, np.zeros_like(t)])                      # along x at y = 0
-    cross1 = np.stack([np.full_like(t, 0.52), t - 0.5])          # vertical through it: 1 crossing
+    cross1 = np.stack([np.full_like(t, 0.52), t - 0.47])         # vertical through it: 1 crossing (off-node:
+    # a crossing exactly at a shared node counts for both segments, as in the reference's inclusive test)
     apart = np.stack([t, np.full_like(t, 0.7)])                  # parallel above: 0
     zig = np.stack([t, 0.3 * np.sin(3 * np.pi * t + 0.4)])       # sine: 3 crossings of y = 0 inside (0, 1)
     p1 = torch.as_tensor(np.stack([line_a, line_a, line_a]))
