@@ -184,8 +184,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       Q[6] = T(0); Q[7] = T(0); Q[8] = T(1);
 #pragma unroll
       for (int i = 0; i < 2; i++) {
-        T len = sqrt_(Q[3 * i] * Q[3 * i] + Q[3 * i + 1] * Q[3 * i + 1]);
-        Q[3 * i] /= len; Q[3 * i + 1] /= len; Q[3 * i + 2] = T(0);
+        T il = rsqrt_nr(Q[3 * i] * Q[3 * i] + Q[3 * i + 1] * Q[3 * i + 1]);   // rows stay ~unit: never 0
+        Q[3 * i] *= il; Q[3 * i + 1] *= il; Q[3 * i + 2] = T(0);
       }
     }
   };
@@ -270,7 +270,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T anchor[3] = {hx[0] + A.joint_radius * dir[0], hx[1] + A.joint_radius * dir[1], T(0) + A.joint_radius * dir[2]};
       T dd[3] = {x[0] - anchor[0], x[1] - anchor[1], x[2] - anchor[2]};
       T dist = sqrt_(dot3(dd, dd));
-      T inv = (dist <= T(2.220446049250313e-12)) ? T(0) : T(1) / dist;
+      T inv = (dist <= T(2.220446049250313e-12)) ? T(0) : rcp_nr(dist);   // (the guard discards rcp(0))
       T nh[3] = {dd[0] * inv, dd[1] * inv, dd[2] * inv};
       T rvn = (v[0] - hv[0]) * nh[0] + (v[1] - hv[1]) * nh[1] + (v[2] - hv[2]) * nh[2];
       T cf[3], tgt[3], fd[3], tau[3];
@@ -407,6 +407,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       const T *N = A.plane_normal;
       const bool has_left = active && j > 0, has_right = active && j + 1 < n;
       const T m0 = A.mass * ((j == 0) ? T(0.5) : T(1)), m1 = A.mass * ((j + 1 == n) ? T(0.5) : T(1));
+      const T w0 = m0 / (m1 + m0), w1 = m1 / (m1 + m0);   // loop-invariant mass weights of the element velocity
       T etf[3], evel[3], xe[3], t[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
@@ -417,11 +418,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         }
         etf[i] = T(0.5) * (f0 + f1) + ((j == 0) ? T(0.5) * f0 : T(0)) + ((j + 1 == n) ? T(0.5) * f1 : T(0));
         T v1 = sh_v[i * RS + t_next];
-        evel[i] = (m1 * v1 + m0 * v[i]) / (m1 + m0);
+        evel[i] = fma(w1, v1, w0 * v[i]);
         xe[i] = x[i] + T(0.5) * dx[i];
         t[i] = dx[i] * ilg;
       }
-      T rad = sqrt_(A.vol_over_pi * ilg);
+      T rad2 = A.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
       T fn = dot3(N, etf), dist = N[0] * (xe[0] - A.plane_origin[0]) + N[1] * (xe[1] - A.plane_origin[1]) +
                                   N[2] * (xe[2] - A.plane_origin[2]);
       T gap = dist - rad, pen = fmin(gap, T(0)), vn = dot3(N, evel);
@@ -435,7 +436,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       }
       T tn = dot3(N, t);
       T tp[3] = {t[0] - N[0] * tn, t[1] - N[1] * tn, t[2] - N[2] * tn};
-      T inv_tp = T(1) / (sqrt_(dot3(tp, tp)) + T(1e-14));
+      T inv_tp = rcp_nr(sqrt_(dot3(tp, tp)) + T(1e-14));
       T ax[3] = {tp[0] * inv_tp, tp[1] * inv_tp, tp[2] * inv_tp}, rl[3];
       cross3(ax, N, rl);
       auto slip_fn = [&](T a) {   // find_slipping_elements on |v|
@@ -456,7 +457,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T slipr = slip_fn(fabs_(smag) * sqrt_(dot3(rl, rl)));
       T ut[3] = {smag * rl[0] + vax * ax[0], smag * rl[1] + vax * ax[1], smag * rl[2] + vax * ax[2]};
       T ug[3] = {ut[0] + T(1e-14), ut[1] + T(1e-14), ut[2] + T(1e-14)};
-      T iun = T(1) / sqrt_(dot3(ug, ug));
+      T iun = rsqrt_nr(dot3(ug, ug));
       T uax = dot3(ut, ax) * iun, url = dot3(ut, rl) * iun;
       T ka = nocontact ? T(0) : -((T(1) - slipa) * kmu * resp_mag * uax);
       T kr = nocontact ? T(0) : -((T(1) - slipr) * A.kin_mu[2] * resp_mag * url);
@@ -484,7 +485,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T tsum[3] = {tq[0] + text[0], tq[1] + text[1], tq[2] + text[2]}, tt[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) tt[i] = Q[i] * tsum[0] + Q[3 + i] * tsum[1] + Q[6 + i] * tsum[2];
-      T noslip = -((rad * dot3(etf2, rl) - T(2) * dot3(tt, ax)) / T(3) / rad);
+      T noslip = -((rad * dot3(etf2, rl) - T(2) * dot3(tt, ax)) * (T(1.0 / 3.0) * inv_rad));
       T sr_ = nocontact ? T(0) : fmin(fabs_(noslip), slipr * A.stat_mu[2] * resp_mag) * sgn(noslip);
 #pragma unroll
       for (int i = 0; i < 3; i++) { fr[i] = sr_ * rl[i]; sh_c12[i * RS + tid] = c1[i] + sa * ax[i] + fr[i]; }
