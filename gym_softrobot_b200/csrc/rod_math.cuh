@@ -16,8 +16,6 @@ namespace sr {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-template <typename T> struct V3 { T x, y, z; };
-
 template <typename T> __device__ __forceinline__ T dot3(const T a[3], const T b[3]) {
   return fma(a[2], b[2], fma(a[1], b[1], a[0] * b[0]));
 }

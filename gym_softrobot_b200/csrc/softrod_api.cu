@@ -36,10 +36,6 @@ int fail(int code, const std::string &msg) {
       return fail(SR_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
   } while (0)
 
-template <typename T> struct DeviceBufs {
-  T *state = nullptr, *bc = nullptr, *aux = nullptr;
-};
-
 }  // namespace
 
 struct sr_handle {
