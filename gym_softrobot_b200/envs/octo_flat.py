@@ -96,16 +96,19 @@ class OctoFlatVectorEnv:
         self.step_count = torch.zeros(n_env, dtype=torch.int64, device=self.device)
         self.prev_action = torch.zeros((n_env, n_arm * n_action), dtype=torch.float32, device=self.device)
         self.target = torch.zeros((n_env, 2), dtype=torch.float64, device=self.device)
-        self._seed, self._episode = 0, np.zeros(n_env, dtype=np.int64)
+        self._seed, self._n_autoreset = 0, 0
 
-    def _targets(self, env_ids):
-        # flat_env.py:223: (2 - 0.5) * np_random.random(2) + 0.5 from the env's generator
-        out = []
-        for i in env_ids:
-            key = int(self._seed + self.env_offset + i)
-            ss = np.random.SeedSequence(key if self._episode[i] == 0 else [key, int(self._episode[i])])
-            out.append((2 - 0.5) * np.random.Generator(np.random.PCG64(ss)).random(2) + 0.5)
-        return np.array(out)
+    def _targets(self, env_ids, initial):
+        # flat_env.py:223: (2 - 0.5) * np_random.random(2) + 0.5.  reset(seed): env i draws like a reference
+        # env reset with seed + global index; autoreset: one batched stream
+        if initial:
+            u = np.array([np.random.Generator(np.random.PCG64(np.random.SeedSequence(
+                int(self._seed + self.env_offset + i)))).random(2) for i in env_ids])
+        else:
+            self._n_autoreset += 1
+            ss = np.random.SeedSequence([int(self._seed), int(self.env_offset), int(self._n_autoreset)])
+            u = np.random.Generator(np.random.PCG64(ss)).random((len(env_ids), 2))
+        return (2 - 0.5) * u + 0.5
 
     def _fields(self):
         """Rod views with an explicit arm axis, [n_env, n_arm, ...], also for the single-arm Lite env."""
@@ -123,7 +126,7 @@ class OctoFlatVectorEnv:
         shared = torch.cat([self.target - hd[:, 0:2], hd[:, 3:5], hd[:, 6:15]], dim=1).float()
         return {"individual": ind, "shared": shared}
 
-    def _reset_envs(self, idx=None):
+    def _reset_envs(self, idx=None, initial=False):
         torch = self.torch
         ids = np.arange(self.n_env) if idx is None else idx.cpu().numpy()
         init = torch.as_tensor(np.repeat(self._init_row, len(ids), axis=0), device=self.device).contiguous()
@@ -133,12 +136,12 @@ class OctoFlatVectorEnv:
             rk.zero_()
         else:
             rk[idx] = 0
-        self.target[ids] = torch.as_tensor(self._targets(ids), device=self.device)
+        self.target[ids] = torch.as_tensor(self._targets(ids, initial), device=self.device)
 
     def reset(self, seed: int = 0):
         self._seed = seed
-        self._episode[:] = 0
-        self._reset_envs()
+        self._n_autoreset = 0
+        self._reset_envs(initial=True)
         self.step_count.zero_()
         self.prev_action.zero_()
         return self._obs(), {}
@@ -181,7 +184,6 @@ class OctoFlatVectorEnv:
             idx = torch.nonzero(done).flatten()
             info["final_obs"] = {k: v[idx].clone() for k, v in obs.items()}
             info["reset_idx"] = idx
-            self._episode[idx.cpu().numpy()] += 1
             self._reset_envs(idx)
             self.step_count[idx] = 0
             self.prev_action[idx] = 0

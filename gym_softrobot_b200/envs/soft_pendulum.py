@@ -174,23 +174,24 @@ class SoftPendulumVectorEnv:
         self._first_truncated = int(np.argmax(self._time_table > final_time))
         self.step_count = torch.zeros(n_env, dtype=torch.int64, device=self.device)
         self._seed = 0
-        self._episode = np.zeros(n_env, dtype=np.int64)
+        self._n_autoreset = 0
 
-    def _draws(self, env_ids):
-        # one PCG64(SeedSequence(seed + global_env + n_env_total * episode)) draw per env
-        return np.array([
-            np.random.Generator(np.random.PCG64(np.random.SeedSequence(
-                int(self._seed + self.env_offset + i)))).random() if self._episode[i] == 0 else
-            np.random.Generator(np.random.PCG64(np.random.SeedSequence(
-                [int(self._seed + self.env_offset + i), int(self._episode[i])]))).random()
-            for i in env_ids
-        ])
+    def _draws(self, env_ids, initial):
+        """Uniform draws behind the initial angle (build.py:47-49).  At reset(seed) env i draws from
+        PCG64(SeedSequence(seed + global_index)) — exactly a reference env reset with that seed; re-draws
+        at autoreset come from one batched stream keyed by (seed, shard offset, reset counter)."""
+        if initial:
+            return np.array([np.random.Generator(np.random.PCG64(np.random.SeedSequence(
+                int(self._seed + self.env_offset + i)))).random() for i in env_ids])
+        self._n_autoreset += 1
+        ss = np.random.SeedSequence([int(self._seed), int(self.env_offset), int(self._n_autoreset)])
+        return np.random.Generator(np.random.PCG64(ss)).random(len(env_ids))
 
     def reset(self, seed: int = 0):
         torch = self.torch
         self._seed = seed
-        self._episode[:] = 0
-        init = torch.as_tensor(pendulum_init_params(self._draws(range(self.n_env))), device=self.device)
+        self._n_autoreset = 0
+        init = torch.as_tensor(pendulum_init_params(self._draws(range(self.n_env), True)), device=self.device)
         self.handle.reset(init.contiguous())
         self.step_count.zero_()
         self.handle.observe(None, self.obs)
@@ -212,8 +213,7 @@ class SoftPendulumVectorEnv:
             ids = idx.cpu().numpy()
             info["final_obs"] = obs[idx].clone()
             info["reset_idx"] = idx
-            self._episode[ids] += 1
-            init = torch.as_tensor(pendulum_init_params(self._draws(ids)), device=self.device)
+            init = torch.as_tensor(pendulum_init_params(self._draws(ids, False)), device=self.device)
             self.handle.reset(init.contiguous(), idx.to(torch.int32).contiguous())
             self.step_count[idx] = 0
             fresh = torch.empty_like(self.obs)

@@ -133,21 +133,22 @@ class SoftPendulum3DVectorEnv:
         self._first_truncated = int(np.argmax(self._time_table >= final_time))   # `>=` in the 3-D env
         self.step_count = torch.zeros(n_env, dtype=torch.int64, device=self.device)
         self._seed = 0
-        self._episode = np.zeros(n_env, dtype=np.int64)
+        self._n_autoreset = 0
 
-    def _draws(self, env_ids):
-        out = []
-        for i in env_ids:
-            key = int(self._seed + self.env_offset + i)
-            ss = np.random.SeedSequence(key if self._episode[i] == 0 else [key, int(self._episode[i])])
-            out.append(np.random.Generator(np.random.PCG64(ss)).uniform(-1.0, 1.0))
-        return np.array(out)
+    def _draws(self, env_ids, initial):
+        # reset(seed): env i == a reference env reset with seed + global index; autoreset: one batched stream
+        if initial:
+            return np.array([np.random.Generator(np.random.PCG64(np.random.SeedSequence(
+                int(self._seed + self.env_offset + i)))).uniform(-1.0, 1.0) for i in env_ids])
+        self._n_autoreset += 1
+        ss = np.random.SeedSequence([int(self._seed), int(self.env_offset), int(self._n_autoreset)])
+        return np.random.Generator(np.random.PCG64(ss)).uniform(-1.0, 1.0, len(env_ids))
 
     def reset(self, seed: int = 0):
         torch = self.torch
         self._seed = seed
-        self._episode[:] = 0
-        init = torch.as_tensor(pendulum3d_init_params(self._draws(range(self.n_env))), device=self.device)
+        self._n_autoreset = 0
+        init = torch.as_tensor(pendulum3d_init_params(self._draws(range(self.n_env), True)), device=self.device)
         self.handle.reset(init.contiguous())
         self.step_count.zero_()
         self.handle.observe(None, self.obs)
@@ -168,8 +169,7 @@ class SoftPendulum3DVectorEnv:
             idx = torch.nonzero(done).flatten()
             ids = idx.cpu().numpy()
             info["final_obs"], info["reset_idx"] = obs[idx].clone(), idx
-            self._episode[ids] += 1
-            init = torch.as_tensor(pendulum3d_init_params(self._draws(ids)), device=self.device)
+            init = torch.as_tensor(pendulum3d_init_params(self._draws(ids, False)), device=self.device)
             self.handle.reset(init.contiguous(), idx.to(torch.int32).contiguous())
             self.step_count[idx] = 0
             fresh = torch.empty_like(self.obs)
