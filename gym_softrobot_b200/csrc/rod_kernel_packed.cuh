@@ -95,6 +95,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const T gmask = active ? T(1) : T(0);
   const T dte = elem_ok ? A.dt : T(0);
 
+  const T gam = elem_ok ? st[F_GAMMA * stride + j] : T(1);   // (L/n) / rest_length_j, see F_GAMMA
   T rk[3] = {T(0), T(0), T(0)};   // rest curvature at Voronoi point j (actuation), constant during a launch
   if (CONTACT && A.rest_kappa && vor_ok) {
 #pragma unroll
@@ -231,7 +232,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
     T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
     T lgn = fma(l2n, iln, T(1e-14));              // length of element j+1, recomputed locally
-    T e = lg * A.inv_rest_len;
+    T e = lg * A.inv_rest_len * gam;
     T inv_e = A.rest_len * ilg;
     T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
     T edot = dot3(dx, dv) * (ilg * A.inv_rest_len);
@@ -242,7 +243,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 1], dx[1], Qdx[i]);
 #pragma unroll
-    for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]);
+    for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]) * gam;   // strain against the element's own rest length
 #pragma unroll
     for (int i = 0; i < 3; i++)
       nst[i] = (i == 2) ? fma(A.S_over_l[i], Qdx[i], -A.S[i]) : A.S_over_l[i] * Qdx[i];

@@ -27,7 +27,9 @@ enum : int {
   F_POS = 0, F_VEL = 3, F_DIR = 6, F_OMEGA = 15, F_TAN = 18, F_KAPPA = 21, F_SIGMA = 24,
   F_DIL = 27,
   F_EDGE = 28,   // FP32 handles only: element edge vectors x_{k+1} - x_k kept as state (strain resolution)
-  N_FIELDS = 31
+  F_GAMMA = 31,  // (L/n) / rest_length_k: the reference derives every rest length from the rounded linspace
+                 // positions, so they differ from L/n by ~1e-14 relative; the stretch strain must see that
+  N_FIELDS = 32
 };
 constexpr int BC_DIM = 12;   // per-env anchors: fixed_position(3), fixed_directors(9)
 constexpr int HEAD_DIM = 20;  // rigid head: x(3) v(3) Q(9) w(3) pinned z(1) pad(1)
@@ -313,7 +315,8 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
   // Slots past the rod end hold a benign state (x = v = w = 0, Q = I) that never changes:
   // their time-step multipliers are zero, so no per-update selects are needed.
   bool elem_ok[EPL], node_ok[EPL], vor_ok[EPL];
-  T dtim[EPL], gmask[EPL], dte[EPL];
+  T dtim[EPL], gmask[EPL], dte[EPL], gam[EPL];
+  load_row<T, EPL>(st + F_GAMMA * stride, lane, gam);
 #pragma unroll
   for (int j = 0; j < EPL; j++) {
     int k = lane * EPL + j;
@@ -430,14 +433,14 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
         T ilg = fma(T(-1e-14) * il, il, il);      // 1/(l + 1e-14) to first order in 1e-14/l
 #pragma unroll
         for (int c = 0; c < 3; c++) t[c] = dx[c] * ilg;
-        e[j] = lg[j] * A.inv_rest_len;
+        e[j] = lg[j] * A.inv_rest_len * gam[j];
         inv_e[j] = A.rest_len * ilg;
         edot[j] = dot3(dx, dv) * (ilg * A.inv_rest_len);   // = t . dv / l0
       } else {
         lg[j] = sqrt_(dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2]) + T(1e-14);
 #pragma unroll
         for (int c = 0; c < 3; c++) t[c] = dx[c] / lg[j];
-        e[j] = lg[j] / A.rest_len;
+        e[j] = lg[j] / A.rest_len * gam[j];
         inv_e[j] = T(1.0) / e[j];
         // r.v terms exactly as elastica/rod/cosserat_rod.py:_compute_dilatation_rate
         T xk[3] = {x[0][j], x[1][j], x[2][j]}, vk[3] = {v[0][j], v[1][j], v[2][j]};
@@ -707,13 +710,14 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
   auto pos = [&](int c, int k) { return k == n ? end[c] : __dadd_rn(__dmul_rn((double)k, step[c]), start[c]); };
   for (int k = threadIdx.x; k < stride; k += blockDim.x) {
     double xk[3] = {0, 0, 0}, t[3] = {0, 0, 1}, Qk[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    double tang[3] = {0, 0, 0}, sg[3] = {0, 0, 0}, dil = 1.0;
+    double tang[3] = {0, 0, 0}, sg[3] = {0, 0, 0}, dil = 1.0, gam = 1.0;
     if (k <= n) for (int c = 0; c < 3; c++) xk[c] = pos(c, k);
     if (k < n) {
       double d[3];
       for (int c = 0; c < 3; c++) d[c] = pos(c, k + 1) - xk[c];
       double rl = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(d[0], d[0]), __dmul_rn(d[1], d[1])), __dmul_rn(d[2], d[2])));
       for (int c = 0; c < 3; c++) t[c] = d[c] / rl;
+      gam = (base_length / (double)n) / rl;
       for (int c = 0; c < 3; c++) { Qk[c] = nor[c]; Qk[6 + c] = t[c]; }
       Qk[3] = __dadd_rn(__dmul_rn(t[1], nor[2]), -__dmul_rn(t[2], nor[1]));
       Qk[4] = __dadd_rn(__dmul_rn(t[2], nor[0]), -__dmul_rn(t[0], nor[2]));
@@ -737,6 +741,7 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
     }
     for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + k] = (T)Qk[c];
     st[F_DIL * stride + k] = (T)dil;
+    st[F_GAMMA * stride + k] = (T)gam;
     for (int c = 0; c < 3; c++) st[(F_EDGE + c) * stride + k] = (T)((k < n) ? pos(c, k + 1) - xk[c] : 0.0);
     if (k == 0) {
       T *b = bc + (size_t)env * BC_DIM;

@@ -104,7 +104,7 @@ def test_state_get_set_roundtrip():
     h1.step(a, 300, o1, r1, t1); h2.step(a, 300, o2, r2, t2)
     torch.cuda.synchronize()
     v = h1.state_view()
-    assert (v.n_env, v.n_fields, v.stride, v.elem_size) == (n_env, 31, 64, 8)
+    assert (v.n_env, v.n_fields, v.stride, v.elem_size) == (n_env, 32, 64, 8)
     assert torch.equal(h1.state_tensor(), h2.state_tensor()) and torch.equal(o1, o2) and torch.equal(r1, r2)
     assert h1.launch_count >= 3
     h1.close(); h2.close()

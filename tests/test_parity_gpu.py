@@ -488,3 +488,56 @@ def test_long_slender_rod_with_contact_fp64_and_fp32():
                 assert rel(f["velocity_collection"][i], o.velocity_collection) < tol_r
                 assert rel(f["omega_collection"][i], o.omega_collection) < tol_r
         h.close()
+
+
+def _random_rod_case(rng):
+    n = int(rng.integers(5, 121))
+    L = float(rng.uniform(0.3, 2.0))
+    r = float(L / n * rng.uniform(0.4, 1.6))          # element aspect ratio around 1
+    E = float(10 ** rng.uniform(5.0, 7.0))
+    rho = float(rng.uniform(500, 4000))
+    dl = L / n
+    dt = float(0.005 * dl / np.sqrt(E / rho) * rng.uniform(0.5, 1.5)) * 10   # ~5 % of the axial CFL limit
+    g = rng.normal(size=3); g = 9.81 * g / np.linalg.norm(g)
+    damping = float(10 ** rng.uniform(-3, 0)) if rng.random() < 0.8 else -1.0
+    bc = int(rng.choice([0, 1]))                          # free / one end fixed
+    d = rng.normal(size=3); d /= np.linalg.norm(d)
+    nn = np.cross(d, rng.normal(size=3)); nn /= np.linalg.norm(nn)
+    start = rng.uniform(-1, 1, size=3)
+    return dict(n=n, L=L, r=r, E=E, rho=rho, dt=dt, g=g, damping=damping, bc=bc, init=np.concatenate([start, d, nn]))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_randomized_rods_vs_oracle(seed):
+    """Seeded random rods (n_elem 5..120, arbitrary orientation, material, gravity direction, damping, BC)
+    through both kernels vs the C oracle: 300 substeps, state to 1e-9 (rates: plus the configuration's
+    own round-off floor, see below)."""
+    import rod_oracle as ro
+    nat = _native()
+    c = _random_rod_case(np.random.default_rng(1000 + seed))
+    o = ro.OracleRod(c["n"], c["init"][0:3], c["init"][3:6], c["init"][6:9], c["L"], c["r"], c["rho"], c["E"], c["dt"],
+                     gravity=c["g"], damping_constant=c["damping"], bc_kind=c["bc"])
+    o.substeps(300)
+    assert np.isfinite(o.position_collection).all(), "unstable random case (test generator problem)"
+    for math in (nat.MATH_FAST, nat.MATH_FAITHFUL):
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=3, n_elem=c["n"], dt=c["dt"], base_length=c["L"], base_radius=c["r"],
+                       density=c["rho"], youngs_modulus=c["E"], gravity=tuple(c["g"]), damping_constant=c["damping"],
+                       bc_kind=c["bc"], math=math)
+        h.reset_host(np.repeat(c["init"][None, :], 3, axis=0))
+        h.step_host(None, 120); h.step_host(None, 180)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        # Round-off floor of the configuration: absolute coordinates of size |x| resolve an element's strain
+        # only to eps |x| / dl per substep in ANY implementation (the oracle included); through the axial
+        # stiffness that is a velocity noise of ~ eps |x| c / dl (c = sqrt(E/rho)), and ~ that / r for omega.
+        # A rod that has barely started to move (small |v|) must be compared against that floor as well.
+        dl, cs = c["L"] / c["n"], np.sqrt(c["E"] / c["rho"])
+        floor_v = 64 * 2.2e-16 * np.abs(o.position_collection).max() * cs / dl
+        floors = {"position_collection": 0.0, "director_collection": 0.0, "velocity_collection": floor_v,
+                  "omega_collection": floor_v / c["r"]}
+        for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+            ref = getattr(o, name)
+            err_abs = float(np.abs(f[name][1] - ref).max())
+            err = err_abs / max(np.abs(ref).max(), 1e-300)
+            assert err_abs <= TOL * np.abs(ref).max() + floors[name], \
+                f"seed={seed} math={math} n={c['n']} bc={c['bc']} {name}: rel {err:.3e} abs {err_abs:.3e} floor {floors[name]:.3e}"
+        h.close()
