@@ -15,6 +15,7 @@ REGISTRY = {
     "OctoArmSingle-v0": ("gym_softrobot_b200.envs.arm_single:ArmSingleEnv", {}),
     "OctoFlat-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", {}),
     "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", dict(n_arm=1, n_action=8)),
+    "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeEnv", {}),
 }
 VECTOR_REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
@@ -22,6 +23,7 @@ VECTOR_REGISTRY = {
     "OctoArmSingle-v0": ("gym_softrobot_b200.envs.arm_single:ArmSingleVectorEnv", {}),
     "OctoFlat-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", {}),
     "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", dict(n_arm=1, n_action=8)),
+    "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeVectorEnv", {}),
 }
 
 

@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs",
 ]
 
 
@@ -43,6 +43,9 @@ class SrConfig(C.Structure):
         ("head_length", C.c_double), ("head_radius", C.c_double), ("head_density", C.c_double),
         ("joint_k", C.c_double), ("joint_nu", C.c_double), ("joint_kt", C.c_double), ("joint_radius", C.c_double),
         ("joint_angle_deg", C.c_double * 16),
+        ("muscle_on", C.c_int32), ("reserved2", C.c_int32),
+        ("muscle_period", C.c_double), ("muscle_ramp_up_time", C.c_double), ("muscle_phase_shift", C.c_double),
+        ("muscle_direction", C.c_double * 3),
     ]
 
 
@@ -91,6 +94,7 @@ def load_library():
     L.sr_get_aux.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_head.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sr_get_muscle.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_launch_count.argtypes = [C.c_void_p]
     L.sr_launch_count.restype = C.c_int64
     L.sr_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -131,9 +135,9 @@ class Handle:
 
     def __init__(self, *, model, n_env, n_elem, dt, base_length, base_radius, density, youngs_modulus,
                  shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
-                 point_force_on_base=False, damping_before_constraints=True, laplace_filter_order=0,
+                 point_force_on_base=False, damping_before_constraints=False, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
-                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None):
+                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -149,7 +153,7 @@ class Handle:
         cfg.base_step, cfg.base_limit, cfg.base_move_period = base_step, base_limit, base_move_period
         if contact is not None:   # plane_origin, plane_normal, k, nu, slip_velocity_tol, static_mu, kinetic_mu
             cfg.contact_on = 1
-            cfg.contact_before_forcing = int(contact.get("before_forcing", True))
+            cfg.contact_before_forcing = int(contact.get("before_forcing", False))
             cfg.plane_origin[:] = [float(v) for v in contact["plane_origin"]]
             cfg.plane_normal[:] = [float(v) for v in contact["plane_normal"]]
             cfg.contact_k, cfg.contact_nu = contact["k"], contact["nu"]
@@ -165,6 +169,11 @@ class Handle:
             cfg.joint_k, cfg.joint_nu, cfg.joint_kt, cfg.joint_radius = joint["k"], joint["nu"], joint["kt"], joint["radius"]
             for a, ang in enumerate(joint["angles_deg"]):
                 cfg.joint_angle_deg[a] = float(ang)
+        if muscle is not None:    # dict: period, ramp_up_time, phase_shift, direction (MuscleTorques kwargs)
+            cfg.muscle_on = 1
+            cfg.muscle_period, cfg.muscle_ramp_up_time = muscle["period"], muscle["ramp_up_time"]
+            cfg.muscle_phase_shift = muscle.get("phase_shift", 0.0)
+            cfg.muscle_direction[:] = [float(v) for v in muscle["direction"]]
         self.n_rod = max(1, n_rod)
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -308,6 +317,13 @@ class Handle:
         t = torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod, 3, v.stride), ts),
                             device=f"cuda:{self.device}")
         return t[:, :, :self.n_elem - 1]
+
+    def muscle_tensor(self):
+        """torch view [n_env, n_elem + 2] (float64): simulation time, wave number, beta(s_k) (sr_get_muscle)."""
+        import torch
+        ptr, dim = C.c_void_p(), C.c_int32()
+        _check(self._lib.sr_get_muscle(self._h, C.byref(ptr), C.byref(dim)))
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), "<f8"), device=f"cuda:{self.device}")
 
     def set_state_from(self, other: "Handle"):
         v = other.state_view()

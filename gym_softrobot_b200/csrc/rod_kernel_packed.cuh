@@ -101,6 +101,21 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int c = 0; c < 3; c++) rk[c] = A.rest_kappa[((size_t)rod * 3 + c) * stride + j];
   }
+  // MuscleTorques (continuum_snake.py:186-198; PyElastica external_forces.MuscleTorques): element k gets
+  // Q_k d (m_k [k >= 1] - m_{k+1} [k <= n-2]),  m_k = min(1, t/ramp) beta_{n-1-k} sin(w t - kw s_{n-1-k} + phi)
+  // (the reference walks the magnitudes tail-to-head); s_i = (i+1)/n on the uniform rest template.
+  const bool muscle = CONTACT && !MULTI && A.muscle_on && elem_ok;
+  double mus_t = 0.0, mus_b0 = 0.0, mus_b1 = 0.0, mus_s0 = 0.0, mus_s1 = 0.0;
+  if (CONTACT && !MULTI && A.muscle_on && live) {
+    const double *mu = A.muscle + (size_t)env * A.muscle_dim;
+    mus_t = mu[0];
+    if (muscle) {
+      const double kw = mu[1], inv_n = 1.0 / (double)n;
+      const int i0 = n - 1 - j, i1 = n - 2 - j;
+      if (j >= 1) { mus_b0 = mu[2 + i0]; mus_s0 = kw * ((double)(i0 + 1) * inv_n); }
+      if (j <= n - 2) { mus_b1 = mu[2 + i1]; mus_s1 = kw * ((double)(i1 + 1) * inv_n); }
+    }
+  }
   T act0 = T(0), base_vx = T(0), base_vy = T(0);
   float act_f0 = 0.0f, act_f1 = 0.0f;
   if (active && A.action_dim > 0) { act_f0 = A.action[(size_t)env * A.action_dim]; act0 = (T)act_f0; }
@@ -196,6 +211,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll 1
   for (int s = 0; s < A.n_substeps; s++) {
     const bool last = (s == A.n_substeps - 1);
+    T mtq[3] = {T(0), T(0), T(0)};
+    if (CONTACT && !MULTI && A.muscle_on) {
+      mus_t += (double)h;   // time of the force evaluation: after the first half step
+      if (muscle) {
+        const double wt = A.mus_omega * mus_t, fct = fmin(1.0, mus_t / A.mus_ramp);
+        const double m0 = (fct * mus_b0) * sin((wt - mus_s0) + A.mus_phase);
+        const double m1 = (fct * mus_b1) * sin((wt - mus_s1) + A.mus_phase);
+        const T cf = (T)(m0 - m1);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+          mtq[i] = (Q[3 * i] * A.mus_dir[0] + Q[3 * i + 1] * A.mus_dir[1] + Q[3 * i + 2] * A.mus_dir[2]) * cf;
+      }
+      mus_t += (double)h;
+    }
     // ---- publish what the neighbours need ------------------------------------------
 #pragma unroll
     for (int c = 0; c < 3; c++) { sh_x[c * RS + tid] = EDGE ? ed[c] : x[c]; sh_v[c * RS + tid] = v[c]; }
@@ -397,6 +426,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       fint[i] = sfl[i] - sh_s[i * RS + t_prev];
       tq[i] = tql[i] + sh_N[i * RS + t_prev];
     }
+    // forcing registered before the contact: the static-friction torque balance sees the muscle couple
+    if (CONTACT && !MULTI && A.muscle_on && !A.contact_before_forcing) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) tq[i] += mtq[i];
+    }
     if (CONTACT && A.contact_on) {
       // RodPlaneContactWithAnisotropicFriction (elastica/_contact_functions.py), per element j
       // between nodes j and j+1.  Stage 1: normal response + kinetic friction from the nodal forces
@@ -413,9 +447,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         T f0 = fint[i], f1 = sh_s[i * RS + t_next] - sfl[i];   // internal force on nodes j, j+1
-        if (!A.contact_before_forcing) {                       // external forces so far: gravity (+ base force)
+        if (!A.contact_before_forcing) {                       // external loads so far: gravity, joints (+ base force)
           f0 += A.g[i] * m0; f1 += A.g[i] * m1;
           if (i == 0 && A.point_force && first) f0 = fint[i] + act0;
+          if (MULTI) f0 += fj[i];                              // joint force on node 0 (zero elsewhere)
         }
         etf[i] = T(0.5) * (f0 + f1) + ((j == 0) ? T(0.5) * f0 : T(0)) + ((j + 1 == n) ? T(0.5) * f1 : T(0));
         T v1 = sh_v[i * RS + t_next];
@@ -484,6 +519,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T smu = T(0.5) * (A.stat_mu[0] * (T(1) + sga) + A.stat_mu[1] * (T(1) - sga));
       T sa = nocontact ? T(0) : -(fmin(fabs_(fax), slipa * smu * resp_mag) * sga);
       T tsum[3] = {tq[0] + text[0], tq[1] + text[1], tq[2] + text[2]}, tt[3];
+      if (MULTI && !A.contact_before_forcing) {   // the joint's couple on element 0 is already registered
+#pragma unroll
+        for (int i = 0; i < 3; i++) tsum[i] += tj[i];
+      }
 #pragma unroll
       for (int i = 0; i < 3; i++) tt[i] = Q[i] * tsum[0] + Q[3 + i] * tsum[1] + Q[6 + i] * tsum[2];
       T noslip = -((rad * dot3(etf2, rl) - T(2) * dot3(tt, ax)) * (T(1.0 / 3.0) * inv_rad));
@@ -497,6 +536,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
       for (int i = 0; i < 3; i++)   // node j collects half of the plane's load on elements j-1 and j
         fint[i] += T(0.5) * (sh_c12[i * RS + tid] + (has_left ? sh_c12[i * RS + tid - 1] : T(0)));
+    }
+    if (CONTACT && !MULTI && A.muscle_on && A.contact_before_forcing) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) tq[i] += mtq[i];
     }
     if (MULTI && is_head) {
       // rigid head: a = F/m, alpha = J^-1 ((J w) x w + T)  (SURVEY D.1); loads = the joints' reactions,
@@ -625,6 +668,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   __syncthreads();
   if (active && first && arm == 0) {
     const bool invalid = sh_flag[r] != 0;
+    if (CONTACT && !MULTI && A.muscle_on) A.muscle[(size_t)env * A.muscle_dim] = mus_t;
     if (A.model == MODEL_SOFT_PENDULUM) {
       soft_pendulum_outputs<T>(sh_x + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
                                A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);

@@ -74,6 +74,9 @@ template <typename T> struct RodArgs {
   T joint_k, joint_nu, joint_kt, joint_radius, joint_cs[16][2];   // cos/sin of each arm's mounting angle
   T head_dt_inv_mass, head_J[3], head_Jinv[3];
   int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
+  // MuscleTorques travelling wave (continuum_snake.py:186-198): [n_env][muscle_dim] = time, wave number, beta[n]
+  double *muscle; int muscle_on, muscle_dim;
+  double mus_omega, mus_ramp, mus_phase; T mus_dir[3];
   PolyCoef<T> poly;
 };
 
@@ -690,7 +693,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
 template <typename T>
 __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx, int n_reset,
                                  const double *init, int n, int stride, double base_length, int n_rod,
-                                 int init_dim) {
+                                 int init_dim, double *muscle, int muscle_dim) {
   // one block per rod to rebuild: block r -> env slot r / n_rod, rod r % n_rod
   int r = blockIdx.x;
   if (r >= n_reset * n_rod) return;
@@ -750,6 +753,7 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
       if (arm == 0) {   // aux is per environment, not per rod
         T *a = aux + (size_t)(env / n_rod) * AUX_DIM;
         for (int c = 0; c < AUX_DIM; c++) a[c] = T(0);
+        if (muscle) muscle[(size_t)(env / n_rod) * muscle_dim] = 0.0;   // simulation time restarts
       }
     }
   }

@@ -43,6 +43,7 @@ struct sr_handle {
   int epl = 0, stride = 0, obs_dim = 0, action_dim = 0;
   size_t elem_size = 8;
   void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr, *head = nullptr;
+  double *muscle = nullptr; int muscle_dim = 0;
   int n_rod = 1, init_dim = 9;
   sr::RodArgs<double> a64;
   sr::RodArgs<float> a32;
@@ -121,6 +122,10 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   A.contact_k = (T)c.contact_k; A.contact_nu = (T)c.contact_nu; A.slip_tol = (T)c.slip_velocity_tol;
   A.inv_slip_tol = (T)(c.slip_velocity_tol > 0 ? 1.0 / c.slip_velocity_tol : 0.0);
   A.surface_tol = (T)c.surface_tol; A.vol_over_pi = (T)((r * r) * rl);
+  A.muscle = nullptr; A.muscle_on = c.muscle_on; A.muscle_dim = n + 2;
+  A.mus_omega = c.muscle_period > 0.0 ? 2.0 * PI / c.muscle_period : 0.0;
+  A.mus_ramp = c.muscle_ramp_up_time; A.mus_phase = c.muscle_phase_shift;
+  for (int i = 0; i < 3; i++) A.mus_dir[i] = (T)c.muscle_direction[i];
   A.isotropic = 1;  // straight_rod builds circular cross-sections: I1 == I2
   {
     const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
@@ -204,7 +209,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
   if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
-  if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
+  if (A.contact_on || A.rest_kappa || A.muscle_on) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
   return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
              ? launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s)
              : launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
@@ -297,6 +302,13 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     double nn = cfg->plane_normal[0] * cfg->plane_normal[0] + cfg->plane_normal[1] * cfg->plane_normal[1] + cfg->plane_normal[2] * cfg->plane_normal[2];
     if (!(nn > 0.0)) return fail(SR_E_INVALID, "sr_create: plane_normal must be non-zero");
   }
+  if (cfg->muscle_on) {
+    if (cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: muscle torques are built for SR_MATH_FAST only");
+    if (cfg->n_rod_per_env > 1 || cfg->has_head || cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE)
+      return fail(SR_E_INVALID, "sr_create: muscle torques cannot be combined with assemblies / Laplace filter / moving base yet");
+    if (!(cfg->muscle_period > 0.0) || !(cfg->muscle_ramp_up_time > 0.0))
+      return fail(SR_E_INVALID, "sr_create: muscle_period and muscle_ramp_up_time must be > 0");
+  }
   if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
     return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
@@ -347,10 +359,21 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     sr_destroy(h);
     return fail(SR_E_ALLOC, m);
   }
+  if (cfg->muscle_on) {
+    h->muscle_dim = cfg->n_elem + 2;
+    const size_t mb = n_env * h->muscle_dim * sizeof(double);
+    if ((e = cudaMalloc(&h->muscle, mb)) != cudaSuccess || (e = cudaMemset(h->muscle, 0, mb)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
   fill_args<double>(*cfg, h->stride, h->a64);
+  h->a64.muscle = h->muscle;
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
   fill_args<float>(*cfg, h->stride, h->a32);
+  h->a32.muscle = h->muscle;
   h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
   h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim; h->a32.head = (float *)h->head;
   *out = h;
@@ -360,7 +383,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -382,14 +405,14 @@ int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init
   if (h->cfg.dtype == SR_DTYPE_F32) {
     sr::rod_reset_kernel<float><<<nblk, 64, 0, (cudaStream_t)stream>>>(
         (float *)h->state, (float *)h->bc, (float *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-        h->stride, h->cfg.base_length, h->n_rod, h->init_dim);
+        h->stride, h->cfg.base_length, h->n_rod, h->init_dim, h->muscle, h->muscle_dim);
     if (h->cfg.has_head)
       sr::head_reset_kernel<float><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
           (float *)h->head, env_idx_dev, n, init_dev, h->init_dim, h->n_rod, h->cfg.head_length);
   } else {
     sr::rod_reset_kernel<double><<<nblk, 64, 0, (cudaStream_t)stream>>>(
         (double *)h->state, (double *)h->bc, (double *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-        h->stride, h->cfg.base_length, h->n_rod, h->init_dim);
+        h->stride, h->cfg.base_length, h->n_rod, h->init_dim, h->muscle, h->muscle_dim);
     if (h->cfg.has_head)
       sr::head_reset_kernel<double><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
           (double *)h->head, env_idx_dev, n, init_dev, h->init_dim, h->n_rod, h->cfg.head_length);
@@ -487,6 +510,13 @@ int sr_get_state(sr_handle *h, sr_state_view *out) {
   out->f_position = sr::F_POS; out->f_velocity = sr::F_VEL; out->f_director = sr::F_DIR;
   out->f_omega = sr::F_OMEGA; out->f_tangents = sr::F_TAN; out->f_kappa = sr::F_KAPPA;
   out->f_sigma = sr::F_SIGMA; out->f_dilatation = sr::F_DIL;
+  return SR_OK;
+}
+
+int sr_get_muscle(sr_handle *h, double **muscle_dev, int32_t *dim) {
+  if (!h || !muscle_dev || !dim) return fail(SR_E_INVALID, "sr_get_muscle: null argument");
+  if (!h->muscle) return fail(SR_E_INVALID, "sr_get_muscle: handle was created without muscle_on");
+  *muscle_dev = h->muscle; *dim = h->muscle_dim;
   return SR_OK;
 }
 

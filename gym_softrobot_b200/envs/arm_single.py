@@ -19,7 +19,7 @@ _ROD = dict(base_length=0.35, base_radius=0.35 * 0.02, density=1000.0, youngs_mo
 _G = -9.81
 
 
-def arm_contact_params(friction_multiplier=1.0, friction_symmetry=False, before_forcing=True):
+def arm_contact_params(friction_multiplier=1.0, friction_symmetry=False, before_forcing=False):
     """Plane + friction parameters of build_arm / build_octopus (build.py:173-200, 258-283)."""
     L0, r0 = _ROD["base_length"], _ROD["base_radius"]
     period, froude = 2.0, 0.1
@@ -40,7 +40,7 @@ def curvature_interp_matrix(n_action, n_seg):
 
 def _make_handle(n_env, n_elems, time_step, device, dtype=nat.DTYPE_F64):
     return nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elems, dt=time_step, gravity=(0.0, 0.0, _G),
-                      damping_constant=1e-2, bc_kind=nat.BC_FREE, damping_before_constraints=True,
+                      damping_constant=1e-2, bc_kind=nat.BC_FREE, damping_before_constraints=False,
                       device=device, dtype=dtype, contact=arm_contact_params(), **_ROD)
 
 

@@ -44,7 +44,7 @@ def _make_handle(n_env, n_elems, time_step, device, math, dtype=nat.DTYPE_F64):
     return nat.Handle(
         model=nat.MODEL_SOFT_PENDULUM, n_env=n_env, n_elem=n_elems, dt=time_step,
         gravity=_GRAVITY, damping_constant=_DAMPING_CONSTANT, bc_kind=nat.BC_PENDULUM_SLIDER,
-        point_force_on_base=True, damping_before_constraints=True, device=device, math=math, dtype=dtype,
+        point_force_on_base=True, damping_before_constraints=False, device=device, math=math, dtype=dtype,
         **_DEFAULT_SCALE_LENGTH, **_PENDULUM_PROPERTIES,
     )
 

@@ -33,7 +33,7 @@ def _make_handle(n_env, n_elems, time_step, step_skip, device):
     return nat.Handle(
         model=nat.MODEL_SOFT_PENDULUM_3D, n_env=n_env, n_elem=n_elems, dt=time_step, gravity=_GRAVITY,
         damping_constant=1.0, laplace_filter_order=7, bc_kind=nat.BC_MOVING_BASE,
-        damping_before_constraints=True, device=device, base_step=_BASE_STEP, base_limit=_BASE_LIMIT,
+        damping_before_constraints=False, device=device, base_step=_BASE_STEP, base_limit=_BASE_LIMIT,
         base_move_period=step_skip * time_step, **_ROD,
     )
 

@@ -70,7 +70,7 @@ typedef struct sr_config {
   int32_t n_elem;       /* elements per rod */
   int32_t bc_kind;      /* SR_BC_* */
   int32_t point_force_on_base; /* F_ext[0,0] = action[env,0] each substep (build.py:94-105) */
-  int32_t damping_before_constraints; /* 1: [dampen_rates, constrain_rates] */
+  int32_t damping_before_constraints; /* 1: [dampen_rates, constrain_rates]; 0 (the envs): [constrain_rates, dampers] = build-code call order */
   int32_t laplace_filter_order;       /* LaplaceDissipationFilter order, 0 = off */
   int32_t n_rod_per_env; /* rods per environment; 0 or 1 = single rod.  > 1: multi-rod assembly (octopus) */
   double dt;            /* substep */
@@ -83,9 +83,9 @@ typedef struct sr_config {
    * with base_move_period = step_skip * time_step as computed by the host in double. */
   double base_step, base_limit, base_move_period;
   /* RodPlaneContactWithAnisotropicFriction on Plane(origin, normal) (envs/octopus/build.py:173-200,258-283);
-   * contact_on = 0 disables.  contact_before_forcing = 1 runs the contact operator before gravity inside
-   * `synchronize` (the order PyElastica's mixin registration yields for the reference's simulator classes,
-   * DESIGN.md B-1); mu arrays are [forward, backward, sideways]. */
+   * contact_on = 0 disables.  contact_before_forcing = 1 runs the contact operator before gravity / joints /
+   * muscle torques inside `synchronize`; 0 (what the envs use: the reference's build code registers the
+   * contact last) lets it see those loads; mu arrays are [forward, backward, sideways]. */
   int32_t contact_on, contact_before_forcing;
   double plane_origin[3], plane_normal[3];
   double contact_k, contact_nu, slip_velocity_tol, surface_tol;
@@ -99,6 +99,15 @@ typedef struct sr_config {
   double head_length, head_radius, head_density;
   double joint_k, joint_nu, joint_kt, joint_radius;
   double joint_angle_deg[16];
+
+  /* Travelling-wave muscle torque (PyElastica `MuscleTorques`; envs/snake/continuum_snake.py:186-198,325-337):
+   * element couples of magnitude min(1, t/ramp) * beta(s) * sin(2 pi t/period - wave_number s + phase)
+   * about `muscle_direction` (material frame), iterated tail-to-head.  beta(s) and wave_number are
+   * per-env device data the caller fills before sr_step (sr_get_muscle); the handle keeps each
+   * env's simulation time (advanced by dt/2 twice per substep, zeroed by sr_reset). */
+  int32_t muscle_on, reserved2;
+  double muscle_period, muscle_ramp_up_time, muscle_phase_shift;
+  double muscle_direction[3];
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -172,6 +181,11 @@ int sr_get_head(sr_handle *h, void **head_dev, int32_t *dim);
  * dtype (n_env * n_rod_per_env rows for assemblies), Voronoi points in slots 0..n_elem-2; allocated on
  * first use, zero-initialised. */
 int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev);
+
+/* Per-env muscle-torque data (muscle_on handles), [n_env][*dim] float64 whatever the handle's dtype:
+ * 0 simulation time, 1 wave_number, 2..2+n_elem-1 beta(s_k) at s_k = cumsum(rest_lengths)_k / L
+ * (`MuscleTorques.__init__`, re-run by `set_action` of continuum_snake.py:186-198). */
+int sr_get_muscle(sr_handle *h, double **muscle_dev, int32_t *dim);
 
 /* number of kernels this library launched on behalf of the handle so far */
 int64_t sr_launch_count(const sr_handle *h);

@@ -128,7 +128,7 @@ def gen_arm_single(seed=42, n=5):
     obs0, _ = env.reset(seed=seed)
     env.action_space.seed(seed)
     rod = env.unwrapped.shearable_rod
-    out = {"label": LABEL + "; synchronize order = [contact, forcing] (reverse-MRO registration, B-1)",
+    out = {"label": LABEL + "; operator order = build-code call order (OperatorGroupFIFO): synchronize = [forcing..., contact]",
            "seed": seed, "obs0": obs0}
     pack("state0", rod_state(rod), out)
     acts, obs, rew, term, trunc = [], [], [], [], []
@@ -151,7 +151,7 @@ def gen_octo_flat(seed=42, n=3, recording_fps=50):
     obs0, _ = env.reset(seed=seed)
     env.action_space.seed(seed)
     e = env.unwrapped
-    out = {"label": LABEL + "; synchronize = [contact, forcing, connections], rates = [damping, constraints] (B-1/B-2)",
+    out = {"label": LABEL + "; operator order = build-code call order (OperatorGroupFIFO): synchronize = [connections, forcing, contact]",
            "seed": seed, "recording_fps": recording_fps, "step_skip": e.step_skip, "target": e._target.copy(),
            "obs0/individual": obs0["individual"], "obs0/shared": obs0["shared"]}
 
@@ -178,8 +178,51 @@ def gen_octo_flat(seed=42, n=3, recording_fps=50):
     print("octo_flat:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
 
 
+def gen_snake(seed=42, n_state=3, n=33):
+    """ContinuumSnake-v0 (n=50 rod, travelling-wave MuscleTorques rebuilt per action, anisotropic plane
+    friction, dt=8e-6, 25 000 substeps per env-step).  33 env-steps so that the reward
+    (`compute_projected_velocity`, non-zero from the 31st step on) is exercised; full states are kept
+    for the first `n_state` steps, the callback samples (time, centre of mass, its velocity) for all."""
+    env = ref_loader.load_reference_env("ContinuumSnake-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    rod = e.shearable_rod
+    out = {"label": LABEL + "; operator order = build-code call order (OperatorGroupFIFO): synchronize = [forcing..., contact]",
+           "seed": seed, "obs0": obs0, "step_skip": e.step_skip}
+    pack("state0", rod_state(rod), out)
+    acts, rew, term, trunc, times = [], [], [], [], []
+    # full-range random actions (|b| up to 1e-2, re-drawn every 0.2 s) blow the NumPy simulation up after ~4 s,
+    # so the fixture perturbs the published gait of the PyElastica snake case instead: still a new,
+    # seed-determined action in the Box every step
+    b_gait = np.array([3.4e-3, 3.3e-3, 4.2e-3, 2.6e-3, 3.6e-3, 3.5e-3])
+    for i in range(n):
+        s = env.action_space.sample().astype(np.float64)
+        a = np.concatenate([b_gait + 0.1 * s[:6], [0.97 + 0.04 * (s[6] - 1.75)]]).astype(np.float32)
+        assert env.action_space.contains(a)
+        o, r, te, tr, info = env.step(a)
+        assert np.isfinite(o).all(), f"simulation diverged at step {i + 1}"
+        acts.append(a); rew.append(r); term.append(te); trunc.append(tr); times.append(float(e.time))
+        if i < n_state:
+            out[f"obs{i + 1}"] = o
+            pack(f"state{i + 1}", rod_state(rod), out)
+            out[f"beta{i + 1}"] = e.muscle_torque.my_spline.copy()
+        print("snake step", i + 1, "reward", r, flush=True)
+    out[f"obs{n}"] = o
+    pack("state_final", rod_state(rod), out)
+    out.update(actions=np.array(acts, dtype=np.float32), reward=np.array(rew, dtype=np.float64),
+               terminated=np.array(term), truncated=np.array(trunc), time=np.array(times),
+               cb_time=np.array(e.data["time"]), cb_step=np.array(e.data["step"]),
+               cb_com=np.array(e.data["center_of_mass"]), cb_avg_velocity=np.array(e.data["avg_velocity"]))
+    np.savez_compressed(os.path.join(OUT, f"continuum_snake_seed{seed}.npz"), **out)
+    print("snake:", rew[-3:], "com", e.data["center_of_mass"][-1])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "snake":
+        gen_snake()
+        sys.exit(0)
     gen_soft_pendulum_substeps()
     gen_determinism("SoftPendulum-v0")
     gen_determinism("SoftPendulum3D-v0")
@@ -187,3 +230,4 @@ if __name__ == "__main__":
     gen_soft_pendulum_episode()
     gen_arm_single()
     gen_octo_flat()
+    gen_snake()   # ~25 min of NumPy stepping

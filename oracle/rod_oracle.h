@@ -25,10 +25,10 @@ typedef struct {
   int laplace_filter_order; /* 0 disables */
   int bc_kind;
   int point_force_on_base; /* SoftPendulum: F_ext[0,0] = action (assignment) */
-  int damping_before_constraints; /* B-2: 1 = [dampen_rates, constrain_rates] */
+  int damping_before_constraints; /* 1 = [dampen_rates, constrain_rates]; 0 = call order of the envs */
   /* RodPlaneContactWithAnisotropicFriction on Plane(origin, normal); contact_on = 0 disables */
   int contact_on;
-  int contact_before_forcing; /* B-1: 1 = contact operator runs before gravity/forcing in synchronize */
+  int contact_before_forcing; /* 1 = contact operator runs before gravity/forcing in synchronize; 0 = after (the envs) */
   double plane_origin[3], plane_normal[3];
   double contact_k, contact_nu, slip_velocity_tol, surface_tol;
   double static_mu[3], kinetic_mu[3]; /* forward, backward, sideways */

@@ -96,7 +96,7 @@ class OracleRod:
     def __init__(self, n_elem, start, direction, normal, base_length, base_radius, density,
                  youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
                  gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
-                 bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=True,
+                 bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=False,
                  contact=None):
         cfg = ROConfig()
         cfg.n_elem = n_elem
@@ -114,7 +114,7 @@ class OracleRod:
         cfg.damping_before_constraints = int(damping_before_constraints)
         if contact is not None:   # dict: plane_origin, plane_normal, k, nu, slip_velocity_tol, static_mu, kinetic_mu
             cfg.contact_on = 1
-            cfg.contact_before_forcing = int(contact.get("before_forcing", True))
+            cfg.contact_before_forcing = int(contact.get("before_forcing", False))
             cfg.plane_origin[:] = list(map(float, contact["plane_origin"]))
             cfg.plane_normal[:] = list(map(float, contact["plane_normal"]))
             cfg.contact_k, cfg.contact_nu = contact["k"], contact["nu"]

@@ -20,7 +20,7 @@ from .modules import (
     CallBacks,
 )
 from .timestepper import PositionVerlet, extend_stepper_interface, integrate
-from .external_forces import NoForces, GravityForces, EndpointForces
+from .external_forces import NoForces, GravityForces, EndpointForces, MuscleTorques
 from .dissipation import DamperBase, AnalyticalLinearDamper, LaplaceDissipationFilter
 from .boundary_conditions import ConstraintBase, FreeBC, OneEndFixedBC
 from .callback_functions import CallBackBaseClass

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     assert os.path.exists(path)
     lib = C.CDLL(path)
     syms = declared_symbols()
-    assert len(syms) >= 20
+    assert len(syms) >= 21
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in softrod.h but not exported"
     assert sorted(nat.EXPORTED_SYMBOLS) == syms, "python binding list out of sync with the header"
@@ -33,7 +33,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_config_struct_layout_matches_header():
     # 12 int32 + 10 doubles, naturally aligned
-    assert C.sizeof(nat.SrConfig) == 12 * 4 + 13 * 8 + 2 * 4 + 16 * 8 + 2 * 4 + 23 * 8
+    assert C.sizeof(nat.SrConfig) == 12 * 4 + 13 * 8 + 2 * 4 + 16 * 8 + 2 * 4 + 23 * 8 + 2 * 4 + 6 * 8
     assert C.sizeof(nat.SrStateView) == 8 + 12 * 4
 
 

@@ -147,3 +147,27 @@ def test_octopus_init_matches_reference_layout(golden_dir):
         d3 = g[f"state0/arm{a}/director"][2, :, 0]
         np.testing.assert_allclose(row[9 * a + 3:9 * a + 6], d3, rtol=0, atol=1e-15)
     np.testing.assert_allclose(g["state0/head/position"][:, 0], [0, 0, 0], atol=1e-18)
+
+
+def test_snake_beta_spline_and_reward_match_reference(golden_dir):
+    """ContinuumSnake-v0 host logic: the linearised B-spline amplitude equals the reference's
+    `MuscleTorques.my_spline` (fixture, continuum_snake.py:186-198), and the batched
+    `compute_projected_velocity` port reproduces every step's reward from the recorded callback
+    samples (continuum_snake.py:40-101, 207-209)."""
+    import torch
+    from gym_softrobot_b200.envs.snake import beta_spline_matrix, projected_forward_velocity
+    if not os.path.exists(os.path.join(golden_dir, "continuum_snake_seed42.npz")):
+        pytest.skip("fixture not generated yet (oracle/gen_golden.py snake, ~25 min)")
+    g = np.load(os.path.join(golden_dir, "continuum_snake_seed42.npz"))
+    W = beta_spline_matrix(6, 50)
+    for i in range(3):
+        b = g["actions"][i, :6].astype(np.float64)
+        np.testing.assert_allclose(W @ b, g[f"beta{i + 1}"], rtol=0, atol=1e-17)
+    step_skip, every = int(g["step_skip"]), 2083
+    com, vel, t = torch.as_tensor(g["cb_com"])[None], torch.as_tensor(g["cb_avg_velocity"])[None], g["cb_time"]
+    assert np.array_equal(g["cb_step"], every * np.arange(len(t)))
+    for i, r in enumerate(g["reward"]):
+        S = 1 + (step_skip * (i + 1)) // every          # samples recorded when step i returns
+        got = projected_forward_velocity(t[:S], com[:, :S], vel[:, :S], 2.0)[0].item()
+        assert abs(got - float(r)) <= 1e-12 * max(1.0, abs(float(r))), (i, got, r)
+    assert np.count_nonzero(g["reward"]) >= 2           # the non-trivial branch is exercised

@@ -163,7 +163,7 @@ def test_c_oracle_arm_single_matches_golden(golden_dir):
     mu = L0 / (2.0 * 2.0 * abs(grav) * 0.1)
     kin = np.array([mu, 1.5 * mu, 2.0 * mu])
     contact = dict(plane_origin=[0, 0, -r0], plane_normal=[0, 0, 1.0], k=1e2, nu=1e1, slip_velocity_tol=1e-8,
-                   static_mu=2 * kin, kinetic_mu=kin, before_forcing=True)
+                   static_mu=2 * kin, kinetic_mu=kin, before_forcing=False)
     rod = ro.OracleRod(50, [0, 0, 0], [1.0, 0, 0], [0, 0, 1.0], L0, r0, 1000.0, 1e6, 7e-5, gravity=(0, 0, grav),
                        damping_constant=1e-2, contact=contact)
     for i, a in enumerate(g["actions"]):

@@ -466,15 +466,24 @@ def test_octo_flat_batched_consistency():
     assert torch.isfinite(s37).all()
 
 
-def test_long_slender_rod_with_contact_fp64_and_fp32():
+@pytest.mark.parametrize("before_forcing", [True, False], ids=["contact-first", "forcing-first"])
+def test_long_slender_rod_with_contact_fp64_and_fp32(before_forcing):
     """BASELINE config 5: long slender rod, n_elem = 512, ground contact + anisotropic friction,
-    FP64 vs oracle (1e-9) and the FP32 mode next to it (positions / directors to 1e-4)."""
+    FP64 vs oracle and the FP32 mode next to it (positions / directors to 1e-4).
+
+    contact-first: the plane sees no weight, so friction is off and the comparison is round-off
+    limited (1e-9).  forcing-first (the envs' order): the rod starts at rest and its elements pass
+    slowly through the regularised stick-slip band |v| in [tol, 2 tol] = [1e-8, 2e-8] m/s, where the
+    reference's slip function has slope 1/tol: one explicit substep multiplies a velocity difference
+    by dt mu g / tol ~ 4e2, so two correct implementations chatter apart up to the friction-force
+    scale (measured 9e-10 m, 4e-7 in the directors (roll), 6e-4 of |v|max after 400 substeps); the bounds
+    below are that scale."""
     import torch
     import rod_oracle as ro
     from gym_softrobot_b200.envs.arm_single import arm_contact_params
     nat = _native()
     n, dt, L, r = 512, 5e-6, 1.0, 0.005
-    c = arm_contact_params()
+    c = arm_contact_params(before_forcing=before_forcing)
     c["plane_origin"] = [0.0, 0.0, -r]
     rod_kw = dict(base_length=L, base_radius=r, density=1000.0, youngs_modulus=1e6)
     n_env = 3
@@ -485,9 +494,10 @@ def test_long_slender_rod_with_contact_fp64_and_fp32():
     for i, o in enumerate(rods):
         o.rest_kappa[0, :] = rk[i]
         o.substeps(400)
-    # rates: the rod has barely started to move after 2 ms (|v|max ~ 1.5e-4 m/s) while position round-off
-    # (1e-16 m) times the stiff frequency c/dl = 1.6e4 1/s is ~2e-12 m/s: the relative floor is ~1e-8 here
-    for dtype, tol_x, tol_r in ((nat.DTYPE_F64, TOL, 1e-7), (nat.DTYPE_F32, 1e-4, None)):
+    # rates (contact-first): the rod has barely started to move after 2 ms (|v|max ~ 1.5e-4 m/s) while position
+    # round-off (1e-16 m) times the stiff frequency c/dl = 1.6e4 1/s is ~2e-12 m/s: the relative floor is ~1e-8
+    tol64 = (TOL, TOL, 1e-7) if before_forcing else (1e-8, 5e-6, 5e-3)
+    for dtype, tol_x, tol_q, tol_r in ((nat.DTYPE_F64, *tol64), (nat.DTYPE_F32, 1e-4, 1e-4, None)):
         h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, gravity=(0.0, 0.0, -9.81),
                        damping_constant=1e-2, bc_kind=nat.BC_FREE, contact=c, dtype=dtype, **rod_kw)
         h.reset_host(init)
@@ -497,10 +507,11 @@ def test_long_slender_rod_with_contact_fp64_and_fp32():
         assert term.sum() == 0
         for i, o in enumerate(rods):
             assert rel(f["position_collection"][i], o.position_collection) < tol_x
-            assert rel(f["director_collection"][i], o.director_collection) < tol_x
+            assert rel(f["director_collection"][i], o.director_collection) < tol_q
             if tol_r is not None:
                 assert rel(f["velocity_collection"][i], o.velocity_collection) < tol_r
-                assert rel(f["omega_collection"][i], o.omega_collection) < tol_r
+                # roll rate: chatter amplitude dt mu g / r on top of |w| ~ 0.7 rad/s (measured 9e-3)
+                assert rel(f["omega_collection"][i], o.omega_collection) < (tol_r if before_forcing else 3e-2)
         h.close()
 
 
@@ -548,3 +559,38 @@ def test_randomized_rods_vs_oracle(seed):
             assert err_abs <= TOL * np.abs(ref).max() + floors[name], \
                 f"seed={seed} math={math} n={c['n']} bc={c['bc']} {name}: rel {err:.3e} abs {err_abs:.3e} floor {floors[name]:.3e}"
         h.close()
+
+
+def test_continuum_snake_env_golden(golden_dir):
+    """§8 f2: ContinuumSnake-v0 — travelling-wave MuscleTorques + anisotropic plane friction, 25 000
+    substeps per env-step — through the Gymnasium facade vs the reference-env-on-shim fixture.  Full
+    states for the first steps, every callback sample (centre of mass and its velocity, taken inside
+    the episode every 2083 substeps) and every reward for all 33 steps (825 000 substeps)."""
+    import gym_softrobot_b200 as gsb
+    if not os.path.exists(os.path.join(golden_dir, "continuum_snake_seed42.npz")):
+        pytest.skip("fixture not generated yet (oracle/gen_golden.py snake, ~25 min)")
+    g = np.load(os.path.join(golden_dir, "continuum_snake_seed42.npz"))
+    env = gsb.make("ContinuumSnake-v0")
+    assert env.step_skip == int(g["step_skip"]) == 25000
+    obs0, _ = env.reset(seed=42)
+    assert obs0.dtype == np.float32 and obs0.shape == (756,)
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=1e-6, atol=1e-7)
+    n_state = sum(1 for k in g.files if k.startswith("beta"))
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        assert abs(env.time - float(g["time"][i])) < 1e-12
+        if i < n_state:
+            st = env.rod_state()
+            for gk in ("position", "velocity", "director", "omega"):
+                err = rel(st[FIELDS[gk]], g[f"state{i + 1}/{gk}"])
+                assert err < 1e-7, f"step {i} field {gk} rel err {err:.3e}"
+            np.testing.assert_allclose(obs, g[f"obs{i + 1}"], rtol=1e-4, atol=1e-6)
+        assert abs(r - float(g["reward"][i])) < 1e-6 * max(1.0, abs(float(g["reward"][i]))), (i, r, g["reward"][i])
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+    S = len(g["cb_time"])
+    v = env._vec
+    assert len(v._times) == S
+    np.testing.assert_allclose(np.array(v._times), g["cb_time"], rtol=0, atol=1e-12)
+    com, vel = v._com[0, :S].cpu().numpy(), v._vel[0, :S].cpu().numpy()
+    assert rel(com, g["cb_com"]) < 1e-6 and rel(vel, g["cb_avg_velocity"]) < 1e-4
+    env.close()
