@@ -16,6 +16,7 @@ REGISTRY = {
     "OctoFlat-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", {}),
     "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", dict(n_arm=1, n_action=8)),
     "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeEnv", {}),
+    "SoftArmTracking-v0": ("gym_softrobot_b200.envs.soft_arm_tracking:SoftArmTrackingEnv", {}),
 }
 VECTOR_REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
@@ -24,6 +25,7 @@ VECTOR_REGISTRY = {
     "OctoFlat-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", {}),
     "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", dict(n_arm=1, n_action=8)),
     "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeVectorEnv", {}),
+    "SoftArmTracking-v0": ("gym_softrobot_b200.envs.soft_arm_tracking:SoftArmTrackingVectorEnv", {}),
 }
 
 

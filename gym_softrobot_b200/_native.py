@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs",
 ]
 
 
@@ -46,6 +46,8 @@ class SrConfig(C.Structure):
         ("muscle_on", C.c_int32), ("reserved2", C.c_int32),
         ("muscle_period", C.c_double), ("muscle_ramp_up_time", C.c_double), ("muscle_phase_shift", C.c_double),
         ("muscle_direction", C.c_double * 3),
+        ("spline_dir_mask", C.c_int32), ("spline_n_ctrl", C.c_int32),
+        ("spline_scale", C.c_double), ("spline_max_rate", C.c_double),
     ]
 
 
@@ -95,6 +97,8 @@ def load_library():
     L.sr_get_head.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_get_muscle.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    L.sr_get_spline.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
+    L.sr_spline_basis.argtypes = [C.c_int32, C.c_double, C.c_void_p]
     L.sr_launch_count.argtypes = [C.c_void_p]
     L.sr_launch_count.restype = C.c_int64
     L.sr_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
@@ -120,6 +124,16 @@ class _DevMem:
         }
 
 
+def spline_basis(n_ctrl: int, base_length: float):
+    """Cardinal polynomials [n_ctrl + 1 intervals, n_ctrl, 4] of the not-a-knot cubic the kernel uses
+    (sr_spline_basis; host-only, works without a GPU)."""
+    import numpy as np
+    lib = load_library()
+    out = np.zeros((n_ctrl + 1, n_ctrl, 4))
+    _check(lib.sr_spline_basis(n_ctrl, float(base_length), out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
 def measure_fp64_peak(device: int = 0, three_register_operands: bool = False) -> float:
     """DFMA issue peak in TFLOP/s (8 independent chains per thread).  With `three_register_operands` every
     DFMA reads three distinct 64-bit registers, which B200's register file sustains at only 2/3 of the rate."""
@@ -137,7 +151,7 @@ class Handle:
                  shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
                  point_force_on_base=False, damping_before_constraints=False, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
-                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None):
+                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None, spline=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -174,6 +188,10 @@ class Handle:
             cfg.muscle_period, cfg.muscle_ramp_up_time = muscle["period"], muscle["ramp_up_time"]
             cfg.muscle_phase_shift = muscle.get("phase_shift", 0.0)
             cfg.muscle_direction[:] = [float(v) for v in muscle["direction"]]
+        if spline is not None:    # dict: directions (subset of 0,1,2), n_ctrl, scale, max_rate
+            cfg.spline_dir_mask = sum(1 << int(d) for d in spline["directions"])
+            cfg.spline_n_ctrl = spline["n_ctrl"]
+            cfg.spline_scale, cfg.spline_max_rate = spline["scale"], spline.get("max_rate", float("inf"))
         self.n_rod = max(1, n_rod)
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -324,6 +342,17 @@ class Handle:
         ptr, dim = C.c_void_p(), C.c_int32()
         _check(self._lib.sr_get_muscle(self._h, C.byref(ptr), C.byref(dim)))
         return torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), "<f8"), device=f"cuda:{self.device}")
+
+    def spline_tensors(self):
+        """(points, magnitudes): torch views of the spline-torque state (sr_get_spline), float64:
+        points [n_env, 3, 2P+2] = per material direction P targets, P cached values, initial-call flag, pad;
+        magnitudes [n_env, 3, n_elem] = the cached per-element torque."""
+        import torch
+        ptr, dim = C.c_void_p(), C.c_int32()
+        _check(self._lib.sr_get_spline(self._h, C.byref(ptr), C.byref(dim)))
+        t = torch.as_tensor(_DevMem(ptr.value, (self.n_env, dim.value), "<f8"), device=f"cuda:{self.device}")
+        ch = 2 * self.cfg.spline_n_ctrl + 2
+        return t[:, :3 * ch].unflatten(1, (3, ch)), t[:, 3 * ch:].unflatten(1, (3, self.n_elem))
 
     def set_state_from(self, other: "Handle"):
         v = other.state_view()

@@ -19,8 +19,11 @@ constexpr int PACKED_MAX_THREADS = 1024;
 
 // row stride of the exchange arrays: slot NT is a permanent zero (what the stencils see to
 // the left of element 0), so the base thread needs no select when it reads "j-1"
-// shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide
-constexpr int packed_smem_words(int nt, bool multi) { return (multi ? 27 : 21) * (nt + 2); }
+// shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide (+ 6 joint-reaction rows for
+// assemblies, + 1 element-length row for the spline-torque forcing of the contact / forcing variant)
+constexpr int packed_smem_words(int nt, bool multi, bool contact = false) {
+  return (multi ? 27 : (contact ? 22 : 21)) * (nt + 2);
+}
 
 // LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
 // (SoftPendulum3D); kept out of the instantiation used by the other models so they do not pay
@@ -115,6 +118,21 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       if (j >= 1) { mus_b0 = mu[2 + i0]; mus_s0 = kw * ((double)(i0 + 1) * inv_n); }
       if (j <= n - 2) { mus_b1 = mu[2 + i1]; mus_s1 = kw * ((double)(i1 + 1) * inv_n); }
     }
+  }
+  // MuscleTorquesWithVaryingBetaSplines (muscle_torques_with_bspline.py:126-160,181-228): per enabled
+  // material direction d, external_torques[d, k] += mag_d[k]; mag is re-evaluated (not-a-knot cubic through
+  // the rate-limited control values, at s = cumsum(current lengths)) in every substep that finds the cached
+  // values different from the caller's targets, and kept otherwise — across launches too.
+  const bool spl = CONTACT && !MULTI && A.spline_mask != 0;
+  __shared__ int sh_need[CONTACT && !MULTI ? 128 : 1];
+  T *sh_L = sh + 21 * RS;
+  double *sp = (spl && live) ? A.spline + (size_t)env * A.spline_dim : nullptr;
+  const int sP = A.spline_p, sCH = 2 * sP + 2;
+  T smag[3] = {T(0), T(0), T(0)};
+  if (spl && elem_ok) {
+#pragma unroll
+    for (int d = 0; d < 3; d++)
+      if (A.spline_mask >> d & 1) smag[d] = (T)sp[3 * sCH + d * n + j];
   }
   T act0 = T(0), base_vx = T(0), base_vy = T(0);
   float act_f0 = 0.0f, act_f1 = 0.0f;
@@ -261,6 +279,28 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
     T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
     T lgn = fma(l2n, iln, T(1e-14));              // length of element j+1, recomputed locally
+    if (spl) {
+      sh_L[tid] = lg;
+      if (active && first) {   // the forcing's own bookkeeping, once per env
+        int need = 0;
+        for (int d = 0; d < 3; d++) {
+          if (!(A.spline_mask >> d & 1)) continue;
+          double *ch = sp + d * sCH;
+          bool differ = ch[2 * sP] == 0.0;                      // initial_call_flag
+          for (int i = 0; i < sP; i++) differ = differ || !(ch[sP + i] == ch[i]);   // not np.array_equal
+          if (differ) {
+            ch[2 * sP] = 1.0;
+            for (int i = 0; i < sP; i++) {                      // filter_activation
+              const double dd = ch[i] - ch[sP + i];
+              const double sg = (double)((dd > 0.0) - (dd < 0.0));
+              ch[sP + i] += sg * fmin(A.spline_rate, fabs(dd));
+            }
+            need |= 1 << d;
+          }
+        }
+        sh_need[r] = need;
+      }
+    }
     T e = lg * A.inv_rest_len * gam;
     T inv_e = A.rest_len * ilg;
     T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
@@ -425,6 +465,27 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int i = 0; i < 3; i++) {
       fint[i] = sfl[i] - sh_s[i * RS + t_prev];
       tq[i] = tql[i] + sh_N[i * RS + t_prev];
+    }
+    if (spl) {
+      const int need = live ? sh_need[r] : 0;
+      if (need && elem_ok) {
+        double s_k = 0.0;                                        // np.cumsum(system.lengths)[j]
+        for (int i = 0; i <= j; i++) s_k += (double)sh_L[tid - j + i];
+        const int m = min(max((int)floor(s_k * A.spline_inv_dx), 0), sP);
+        const double t = s_k - (double)m / A.spline_inv_dx;
+        for (int d = 0; d < 3; d++) {
+          if (!(need >> d & 1)) continue;
+          const double *ch = sp + d * sCH, *tb = A.spline_tab + (size_t)m * sP * 4;
+          double val = 0.0;
+          for (int i = 0; i < sP; i++)
+            val += ch[sP + i] * (tb[4 * i] + t * (tb[4 * i + 1] + t * (tb[4 * i + 2] + t * tb[4 * i + 3])));
+          val *= A.spline_scale;
+          sp[3 * sCH + d * n + j] = val;
+          smag[d] = (T)val;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) tq[i] += smag[i];
     }
     // forcing registered before the contact: the static-friction torque balance sees the muscle couple
     if (CONTACT && !MULTI && A.muscle_on && !A.contact_before_forcing) {

@@ -77,6 +77,9 @@ template <typename T> struct RodArgs {
   // MuscleTorques travelling wave (continuum_snake.py:186-198): [n_env][muscle_dim] = time, wave number, beta[n]
   double *muscle; int muscle_on, muscle_dim;
   double mus_omega, mus_ramp, mus_phase; T mus_dir[3];
+  // MuscleTorquesWithVaryingBetaSplines (muscle_torques_with_bspline.py): [n_env][spline_dim] state, basis table
+  double *spline; const double *spline_tab; int spline_mask, spline_p, spline_dim;
+  double spline_scale, spline_rate, spline_inv_dx;
   PolyCoef<T> poly;
 };
 
@@ -693,7 +696,7 @@ rod_substeps_kernel(const __grid_constant__ RodArgs<T> A) {
 template <typename T>
 __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx, int n_reset,
                                  const double *init, int n, int stride, double base_length, int n_rod,
-                                 int init_dim, double *muscle, int muscle_dim) {
+                                 int init_dim, double *muscle, int muscle_dim, double *spline, int spline_dim) {
   // one block per rod to rebuild: block r -> env slot r / n_rod, rod r % n_rod
   int r = blockIdx.x;
   if (r >= n_reset * n_rod) return;
@@ -754,6 +757,10 @@ __global__ void rod_reset_kernel(T *state, T *bc, T *aux, const int32_t *env_idx
         T *a = aux + (size_t)(env / n_rod) * AUX_DIM;
         for (int c = 0; c < AUX_DIM; c++) a[c] = T(0);
         if (muscle) muscle[(size_t)(env / n_rod) * muscle_dim] = 0.0;   // simulation time restarts
+        if (spline) {   // a fresh forcing instance: zero targets / cached points / flags / magnitudes
+          double *sp = spline + (size_t)(env / n_rod) * spline_dim;
+          for (int c = 0; c < spline_dim; c++) sp[c] = 0.0;
+        }
       }
     }
   }

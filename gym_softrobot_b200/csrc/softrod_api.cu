@@ -14,6 +14,7 @@
 
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/softrod.h"
@@ -44,6 +45,7 @@ struct sr_handle {
   size_t elem_size = 8;
   void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr, *head = nullptr;
   double *muscle = nullptr; int muscle_dim = 0;
+  double *spline = nullptr, *spline_tab = nullptr; int spline_dim = 0;
   int n_rod = 1, init_dim = 9;
   sr::RodArgs<double> a64;
   sr::RodArgs<float> a32;
@@ -126,6 +128,10 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   A.mus_omega = c.muscle_period > 0.0 ? 2.0 * PI / c.muscle_period : 0.0;
   A.mus_ramp = c.muscle_ramp_up_time; A.mus_phase = c.muscle_phase_shift;
   for (int i = 0; i < 3; i++) A.mus_dir[i] = (T)c.muscle_direction[i];
+  A.spline = nullptr; A.spline_tab = nullptr; A.spline_mask = c.spline_dir_mask & 7; A.spline_p = c.spline_n_ctrl;
+  A.spline_dim = 3 * (2 * c.spline_n_ctrl + 2) + 3 * n;
+  A.spline_scale = c.spline_scale; A.spline_rate = c.spline_max_rate;
+  A.spline_inv_dx = c.spline_n_ctrl > 0 ? (c.spline_n_ctrl + 1) / c.base_length : 0.0;
   A.isotropic = 1;  // straight_rod builds circular cross-sections: I1 == I2
   {
     const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
@@ -193,7 +199,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / group;
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
-  const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI) * sizeof(T);
+  const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI, CONTACT) * sizeof(T);
   auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
@@ -209,7 +215,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
   if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
-  if (A.contact_on || A.rest_kappa || A.muscle_on) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
+  if (A.contact_on || A.rest_kappa || A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
   return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
              ? launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s)
              : launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
@@ -309,6 +315,14 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     if (!(cfg->muscle_period > 0.0) || !(cfg->muscle_ramp_up_time > 0.0))
       return fail(SR_E_INVALID, "sr_create: muscle_period and muscle_ramp_up_time must be > 0");
   }
+  if (cfg->spline_dir_mask) {
+    if (cfg->math != SR_MATH_FAST) return fail(SR_E_INVALID, "sr_create: spline torques are built for SR_MATH_FAST only");
+    if (cfg->n_rod_per_env > 1 || cfg->has_head || cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE)
+      return fail(SR_E_INVALID, "sr_create: spline torques cannot be combined with assemblies / Laplace filter / moving base yet");
+    if (cfg->spline_dir_mask & ~7) return fail(SR_E_INVALID, "sr_create: spline_dir_mask has bits 0..2 only");
+    if (cfg->spline_n_ctrl < 2 || cfg->spline_n_ctrl > 14) return fail(SR_E_INVALID, "sr_create: spline_n_ctrl must be in [2, 14]");
+    if (!(cfg->spline_max_rate > 0.0)) return fail(SR_E_INVALID, "sr_create: spline_max_rate must be > 0 (inf = unlimited)");
+  }
   if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
     return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
@@ -368,11 +382,27 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       return fail(SR_E_ALLOC, m);
     }
   }
+  if (cfg->spline_dir_mask) {
+    const int P = cfg->spline_n_ctrl;
+    h->spline_dim = 3 * (2 * P + 2) + 3 * cfg->n_elem;
+    const size_t sb = n_env * h->spline_dim * sizeof(double), tb = (size_t)(P + 1) * P * 4 * sizeof(double);
+    std::vector<double> tab((size_t)(P + 1) * P * 4);
+    sr_spline_basis(P, cfg->base_length, tab.data());
+    if ((e = cudaMalloc(&h->spline, sb)) != cudaSuccess || (e = cudaMemset(h->spline, 0, sb)) != cudaSuccess ||
+        (e = cudaMalloc(&h->spline_tab, tb)) != cudaSuccess ||
+        (e = cudaMemcpy(h->spline_tab, tab.data(), tb, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
   fill_args<double>(*cfg, h->stride, h->a64);
+  h->a64.spline = h->spline; h->a64.spline_tab = h->spline_tab;
   h->a64.muscle = h->muscle;
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
   fill_args<float>(*cfg, h->stride, h->a32);
+  h->a32.spline = h->spline; h->a32.spline_tab = h->spline_tab;
   h->a32.muscle = h->muscle;
   h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
   h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim; h->a32.head = (float *)h->head;
@@ -383,7 +413,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -405,14 +435,14 @@ int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init
   if (h->cfg.dtype == SR_DTYPE_F32) {
     sr::rod_reset_kernel<float><<<nblk, 64, 0, (cudaStream_t)stream>>>(
         (float *)h->state, (float *)h->bc, (float *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-        h->stride, h->cfg.base_length, h->n_rod, h->init_dim, h->muscle, h->muscle_dim);
+        h->stride, h->cfg.base_length, h->n_rod, h->init_dim, h->muscle, h->muscle_dim, h->spline, h->spline_dim);
     if (h->cfg.has_head)
       sr::head_reset_kernel<float><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
           (float *)h->head, env_idx_dev, n, init_dev, h->init_dim, h->n_rod, h->cfg.head_length);
   } else {
     sr::rod_reset_kernel<double><<<nblk, 64, 0, (cudaStream_t)stream>>>(
         (double *)h->state, (double *)h->bc, (double *)h->aux, env_idx_dev, n, init_dev, h->cfg.n_elem,
-        h->stride, h->cfg.base_length, h->n_rod, h->init_dim, h->muscle, h->muscle_dim);
+        h->stride, h->cfg.base_length, h->n_rod, h->init_dim, h->muscle, h->muscle_dim, h->spline, h->spline_dim);
     if (h->cfg.has_head)
       sr::head_reset_kernel<double><<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
           (double *)h->head, env_idx_dev, n, init_dev, h->init_dim, h->n_rod, h->cfg.head_length);
@@ -517,6 +547,52 @@ int sr_get_muscle(sr_handle *h, double **muscle_dev, int32_t *dim) {
   if (!h || !muscle_dev || !dim) return fail(SR_E_INVALID, "sr_get_muscle: null argument");
   if (!h->muscle) return fail(SR_E_INVALID, "sr_get_muscle: handle was created without muscle_on");
   *muscle_dev = h->muscle; *dim = h->muscle_dim;
+  return SR_OK;
+}
+
+int sr_get_spline(sr_handle *h, double **spline_dev, int32_t *dim) {
+  if (!h || !spline_dev || !dim) return fail(SR_E_INVALID, "sr_get_spline: null argument");
+  if (!h->spline) return fail(SR_E_INVALID, "sr_get_spline: handle was created without spline_dir_mask");
+  *spline_dev = h->spline; *dim = h->spline_dim;
+  return SR_OK;
+}
+
+int sr_spline_basis(int32_t P, double base_length, double *out) {
+  if (!out || P < 2 || P > 14 || !(base_length > 0.0)) return fail(SR_E_INVALID, "sr_spline_basis: bad argument");
+  // not-a-knot cubic through x_m = m dx, m = 0..N (N = P + 1 intervals), one unit control value at a time:
+  // second derivatives M from  M_{m-1} + 4 M_m + M_{m+1} = 6 (y_{m-1} - 2 y_m + y_{m+1}) / dx^2  (m = 1..N-1)
+  // and third-derivative continuity at x_1 and x_{N-1}; solved densely (N + 1 <= 16 unknowns).
+  const int N = P + 1, K = N + 1;
+  const double dx = base_length / N;
+  for (int i = 0; i < P; i++) {
+    double y[16] = {0}, Am[16][17] = {{0}};
+    y[i + 1] = 1.0;
+    Am[0][0] = 1.0; Am[0][1] = -2.0; Am[0][2] = 1.0;
+    Am[N][N] = 1.0; Am[N][N - 1] = -2.0; Am[N][N - 2] = 1.0;
+    for (int m = 1; m < N; m++) {
+      Am[m][m - 1] = 1.0; Am[m][m] = 4.0; Am[m][m + 1] = 1.0;
+      Am[m][K] = 6.0 * (y[m - 1] - 2.0 * y[m] + y[m + 1]) / (dx * dx);
+    }
+    for (int c = 0; c < K; c++) {   // Gaussian elimination with partial pivoting
+      int piv = c;
+      for (int r2 = c + 1; r2 < K; r2++) if (fabs(Am[r2][c]) > fabs(Am[piv][c])) piv = r2;
+      for (int k = 0; k <= K; k++) std::swap(Am[c][k], Am[piv][k]);
+      for (int r2 = 0; r2 < K; r2++) {
+        if (r2 == c) continue;
+        const double f = Am[r2][c] / Am[c][c];
+        for (int k = c; k <= K; k++) Am[r2][k] -= f * Am[c][k];
+      }
+    }
+    double M[16];
+    for (int m = 0; m < K; m++) M[m] = Am[m][K] / Am[m][m];
+    for (int m = 0; m < N; m++) {
+      double *o = out + ((size_t)m * P + i) * 4;
+      o[0] = y[m];
+      o[1] = (y[m + 1] - y[m]) / dx - dx * (2.0 * M[m] + M[m + 1]) / 6.0;
+      o[2] = 0.5 * M[m];
+      o[3] = (M[m + 1] - M[m]) / (6.0 * dx);
+    }
+  }
   return SR_OK;
 }
 

@@ -3,3 +3,4 @@ from .soft_pendulum_3d import SoftPendulum3DEnv, SoftPendulum3DVectorEnv, pendul
 from .arm_single import ArmSingleEnv, ArmSingleVectorEnv, arm_contact_params, curvature_interp_matrix
 from .octo_flat import FlatEnv, OctoFlatVectorEnv, octopus_init_params, padded_curvature_interp_matrix, count_crossings
 from .snake import ContinuumSnakeEnv, ContinuumSnakeVectorEnv, snake_contact_params, beta_spline_matrix, projected_forward_velocity
+from .soft_arm_tracking import SoftArmTrackingEnv, SoftArmTrackingVectorEnv, target_trajectory

@@ -108,6 +108,16 @@ typedef struct sr_config {
   int32_t muscle_on, reserved2;
   double muscle_period, muscle_ramp_up_time, muscle_phase_shift;
   double muscle_direction[3];
+
+  /* Spline muscle torques (`MuscleTorquesWithVaryingBetaSplines`, utils/custom_elastica/muscle_torque/
+   * muscle_torques_with_bspline.py:8-228; envs/soft_arm/soft_arm_tracking.py:366-400): bit d of
+   * spline_dir_mask enables one forcing instance adding  scale * spline(cumsum(lengths))_k  to
+   * external_torques[d, k] (material frame).  The spline is the not-a-knot cubic through spline_n_ctrl
+   * equidistant control values (zero at both ends); whenever the rate-limited cached values differ from
+   * the caller's targets it is re-fitted and re-evaluated at the CURRENT element lengths, inside the
+   * substep where the reference does it.  Targets / cached values / cached magnitudes: sr_get_spline. */
+  int32_t spline_dir_mask, spline_n_ctrl;
+  double spline_scale, spline_max_rate;
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -186,6 +196,16 @@ int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev);
  * 0 simulation time, 1 wave_number, 2..2+n_elem-1 beta(s_k) at s_k = cumsum(rest_lengths)_k / L
  * (`MuscleTorques.__init__`, re-run by `set_action` of continuum_snake.py:186-198). */
 int sr_get_muscle(sr_handle *h, double **muscle_dev, int32_t *dim);
+
+/* Per-env spline-torque data (spline_dir_mask handles), [n_env][*dim] float64; with P = spline_n_ctrl,
+ * channel d = 0..2 occupies [d*(2P+2), (d+1)*(2P+2)): P targets (what `points_func_array` returns),
+ * P cached values, the initial-call flag, one pad; then 3 x n_elem cached torque magnitudes. */
+int sr_get_spline(sr_handle *h, double **spline_dev, int32_t *dim);
+/* Cardinal polynomials of the not-a-knot cubic spline through n_ctrl + 2 equidistant points on
+ * [0, base_length] with zero end values (what scipy's make_interp_spline(x, y) returns, as used at
+ * muscle_torques_with_bspline.py:146-148): out[(m * n_ctrl + i) * 4 + p] is the coefficient of t^p,
+ * t = s - x_m, of control value i's contribution on interval m (n_ctrl + 1 intervals).  Host-only. */
+int sr_spline_basis(int32_t n_ctrl, double base_length, double *out);
 
 /* number of kernels this library launched on behalf of the handle so far */
 int64_t sr_launch_count(const sr_handle *h);

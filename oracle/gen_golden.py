@@ -218,10 +218,40 @@ def gen_snake(seed=42, n_state=3, n=33):
     print("snake:", rew[-3:], "com", e.data["center_of_mass"][-1])
 
 
+def gen_soft_arm(seed=42, n=40, game_mode=1):
+    """SoftArmTracking-v0 (clamped n=40 arm, two spline muscle-torque forcings re-fitted at the current
+    lengths, fixed or moving target): `n` env-steps of 50 substeps, random actions from the Box."""
+    env = ref_loader.load_reference_env("SoftArmTracking-v0", game_mode=game_mode)
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    rod = e.shearable_rod
+    out = {"label": LABEL + "; operator order = build-code call order (OperatorGroupFIFO)",
+           "seed": seed, "game_mode": game_mode, "obs0": obs0, "targets": e.wsol[::int(e.num_steps_per_update)].copy()}
+    pack("state0", rod_state(rod), out)
+    acts, obs, rew, term, trunc, ctime, mags = [], [], [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        if i in (3, 4):
+            a = acts[-1].copy()      # a repeated action: the forcing keeps its cached torque profile
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr); ctime.append(info["ctime"])
+        if i < 6 or i == n - 1:
+            pack(f"state{i + 1}", rod_state(rod), out)
+    out.update(actions=np.array(acts), obs=np.array(obs), reward=np.array(rew, dtype=np.float64),
+               terminated=np.array(term), truncated=np.array(trunc), ctime=np.array(ctime))
+    np.savez_compressed(os.path.join(OUT, f"soft_arm_tracking_mode{game_mode}_seed{seed}.npz"), **out)
+    print("soft_arm mode", game_mode, ":", rew[-1], obs[-1][8:11])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
         gen_snake()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "soft_arm":
+        gen_soft_arm(game_mode=1)
+        gen_soft_arm(game_mode=2)
         sys.exit(0)
     gen_soft_pendulum_substeps()
     gen_determinism("SoftPendulum-v0")
@@ -230,4 +260,6 @@ if __name__ == "__main__":
     gen_soft_pendulum_episode()
     gen_arm_single()
     gen_octo_flat()
+    gen_soft_arm(game_mode=1)
+    gen_soft_arm(game_mode=2)
     gen_snake()   # ~25 min of NumPy stepping

@@ -26,7 +26,7 @@ from .boundary_conditions import ConstraintBase, FreeBC, OneEndFixedBC
 from .callback_functions import CallBackBaseClass
 from .contact_forces import Plane, RodPlaneContactWithAnisotropicFriction, NoContact, SurfaceBase
 from .joint import FreeJoint
-from .rigidbody import Cylinder, RigidBodyBase
+from .rigidbody import Cylinder, Sphere, RigidBodyBase
 
 
 def __getattr__(name):

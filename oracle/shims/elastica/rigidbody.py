@@ -18,6 +18,57 @@ class RigidBodyBase:
     pass
 
 
+class _RigidOps:
+    """dynamics shared by the rigid bodies: a = F/m, alpha = J^-1 ((J w) x w + T)"""
+
+    def compute_internal_forces_and_torques(self, time=0.0):
+        pass
+
+    update_internal_forces_and_torques = compute_internal_forces_and_torques
+
+    def update_accelerations(self, time=0.0):
+        np.copyto(self.acceleration_collection, self.external_forces / self.mass)
+        J_omega = _batch_matvec(self.mass_second_moment_of_inertia, self.omega_collection)
+        lagrangian_transport = _batch_cross(J_omega, self.omega_collection)
+        np.copyto(self.alpha_collection,
+                  _batch_matvec(self.inv_mass_second_moment_of_inertia,
+                                lagrangian_transport + self.external_torques))
+
+    def zeroed_out_external_forces_and_torques(self, time=0.0):
+        self.external_forces[:] = 0.0
+        self.external_torques[:] = 0.0
+
+    def compute_position_center_of_mass(self):
+        return self.position_collection[..., 0].copy()
+
+
+class Sphere(_RigidOps, RigidBodyBase):
+    """``elastica/rigidbody/sphere.py`` ([PE-recall]): J = 2/5 m r^2 I, identity directors.  In the
+    reference it is a load-free target marker whose position / velocity the env overwrites every
+    substep (`envs/soft_arm/soft_arm_tracking.py:223-224,437-447`)."""
+
+    def __init__(self, center, base_radius, density):
+        self.n_elems = 1
+        self.n_nodes = 1
+        self.radius = base_radius
+        self.density = density
+        self.length = 2 * base_radius
+        self.volume = 4.0 / 3.0 * np.pi * base_radius ** 3
+        self.mass = np.array([self.volume * density])
+        J = np.zeros((3, 3))
+        np.fill_diagonal(J, 2.0 / 5.0 * self.mass[0] * base_radius ** 2)
+        self.mass_second_moment_of_inertia = J.reshape(3, 3, 1)
+        self.inv_mass_second_moment_of_inertia = np.linalg.inv(J).reshape(3, 3, 1)
+        self.position_collection = np.asarray(center, dtype=np.float64).reshape(3, 1).copy()
+        self.velocity_collection = np.zeros((3, 1))
+        self.omega_collection = np.zeros((3, 1))
+        self.acceleration_collection = np.zeros((3, 1))
+        self.alpha_collection = np.zeros((3, 1))
+        self.director_collection = np.eye(3).reshape(3, 3, 1).copy()
+        self.external_forces = np.zeros((3, 1))
+        self.external_torques = np.zeros((3, 1))
+
+
 class Cylinder(RigidBodyBase):
     def __init__(self, start, direction, normal, base_length, base_radius, density):
         start = np.asarray(start, dtype=np.float64)

@@ -171,3 +171,34 @@ def test_snake_beta_spline_and_reward_match_reference(golden_dir):
         got = projected_forward_velocity(t[:S], com[:, :S], vel[:, :S], 2.0)[0].item()
         assert abs(got - float(r)) <= 1e-12 * max(1.0, abs(float(r))), (i, got, r)
     assert np.count_nonzero(g["reward"]) >= 2           # the non-trivial branch is exercised
+
+
+def test_soft_arm_target_trajectory_matches_reference(golden_dir):
+    """SoftArmTracking-v0 game_mode 2: the seeded target trajectory (`generate_trajectory`,
+    soft_arm_tracking.py:44-98) bit for bit, from the env's own generator after reset(seed=42)."""
+    from gym_softrobot_b200.envs.soft_arm_tracking import target_trajectory
+    g = np.load(os.path.join(golden_dir, "soft_arm_tracking_mode2_seed42.npz"))
+    rng = np.random.Generator(np.random.PCG64(np.random.SeedSequence(42)))
+    w = target_trajectory(5.0, 2e-4, 0.1, rng)
+    assert w.shape == (27500, 3)
+    assert np.array_equal(w[::50], g["targets"])
+
+
+def test_native_spline_basis_matches_scipy_not_a_knot():
+    """sr_spline_basis (host-only entry point) == scipy's make_interp_spline(x, y) with zero end values,
+    the spline MuscleTorquesWithVaryingBetaSplines fits (muscle_torques_with_bspline.py:146-148),
+    including the extrapolation past base_length that a stretched arm evaluates."""
+    from scipy.interpolate import make_interp_spline
+    from gym_softrobot_b200 import _native as nat
+    rng = np.random.default_rng(5)
+    for P, L in ((4, 1000.0), (2, 0.35), (7, 3.0)):
+        tab = nat.spline_basis(P, L)
+        x = np.linspace(0, L, P + 2)
+        y = np.zeros(P + 2); y[1:-1] = rng.uniform(-1, 1, P)
+        ref = make_interp_spline(x, y)
+        s = np.sort(rng.uniform(0, 1.08 * L, 300))
+        m = np.clip(np.floor(s * (P + 1) / L).astype(int), 0, P)
+        t = s - m * (L / (P + 1))
+        val = sum(y[1 + i] * (tab[m, i, 0] + t * (tab[m, i, 1] + t * (tab[m, i, 2] + t * tab[m, i, 3])))
+                  for i in range(P))
+        assert np.abs(val - ref(s)).max() < 5e-15 * max(1.0, np.abs(ref(s)).max())

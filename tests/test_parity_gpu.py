@@ -594,3 +594,29 @@ def test_continuum_snake_env_golden(golden_dir):
     com, vel = v._com[0, :S].cpu().numpy(), v._vel[0, :S].cpu().numpy()
     assert rel(com, g["cb_com"]) < 1e-6 and rel(vel, g["cb_avg_velocity"]) < 1e-4
     env.close()
+
+
+@pytest.mark.parametrize("mode", [1, 2], ids=["fixed-target", "moving-target"])
+def test_soft_arm_tracking_env_golden(golden_dir, mode):
+    """§8 f4 (spline muscle actuation): SoftArmTracking-v0 — clamped arm, two
+    MuscleTorquesWithVaryingBetaSplines forcings re-fitted in-kernel at the current element lengths —
+    through the Gymnasium facade vs the reference-env-on-shim fixture (40 env-steps of 50 substeps,
+    float64 observations; steps 4-5 repeat an action so the cached torque profile path is exercised)."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, f"soft_arm_tracking_mode{mode}_seed42.npz"))
+    env = gsb.make("SoftArmTracking-v0", game_mode=mode)
+    obs0, _ = env.reset(seed=42)
+    assert obs0.dtype == np.float64 and obs0.shape == (14,)
+    np.testing.assert_allclose(obs0, g["obs0"], rtol=0, atol=1e-15)
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        if f"state{i + 1}/position" in g.files:
+            st = env.rod_state()
+            for gk in ("position", "velocity", "director", "omega", "kappa"):
+                err = rel(st[FIELDS[gk]], g[f"state{i + 1}/{gk}"])
+                assert err < 1e-9, f"step {i} field {gk} rel err {err:.3e}"
+        np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-9, atol=1e-12)
+        assert abs(r - float(g["reward"][i])) < 1e-9
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+        assert info["ctime"] == float(g["ctime"][i])
+    env.close()
