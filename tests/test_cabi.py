@@ -24,17 +24,26 @@ def test_library_builds_and_exports_header_symbols():
     assert os.path.exists(path)
     lib = C.CDLL(path)
     syms = declared_symbols()
-    assert len(syms) >= 21
+    assert len(syms) >= 23
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in softrod.h but not exported"
     assert sorted(nat.EXPORTED_SYMBOLS) == syms, "python binding list out of sync with the header"
     assert lib.sr_abi_version() == 1
 
 
-def test_config_struct_layout_matches_header():
-    # 12 int32 + 10 doubles, naturally aligned
-    assert C.sizeof(nat.SrConfig) == 12 * 4 + 13 * 8 + 2 * 4 + 16 * 8 + 2 * 4 + 23 * 8 + 2 * 4 + 6 * 8
-    assert C.sizeof(nat.SrStateView) == 8 + 12 * 4
+def test_config_struct_layout_matches_header(tmp_path):
+    """ctypes mirror == the C header, as a C compiler lays it out (sizeof and the offset of the last field)."""
+    import subprocess
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "softrod.h"\n'
+                   'int main(void){printf("%zu %zu %zu\\n", sizeof(sr_config), offsetof(sr_config, spline_max_rate),'
+                   ' sizeof(sr_state_view));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    size, off_last, view = map(int, subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split())
+    assert C.sizeof(nat.SrConfig) == size
+    assert nat.SrConfig.spline_max_rate.offset == off_last
+    assert C.sizeof(nat.SrStateView) == view == 8 + 12 * 4
 
 
 def _cfg(**kw):
