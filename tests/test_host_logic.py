@@ -156,8 +156,6 @@ def test_snake_beta_spline_and_reward_match_reference(golden_dir):
     samples (continuum_snake.py:40-101, 207-209)."""
     import torch
     from gym_softrobot_b200.envs.snake import beta_spline_matrix, projected_forward_velocity
-    if not os.path.exists(os.path.join(golden_dir, "continuum_snake_seed42.npz")):
-        pytest.skip("fixture not generated yet (oracle/gen_golden.py snake, ~25 min)")
     g = np.load(os.path.join(golden_dir, "continuum_snake_seed42.npz"))
     W = beta_spline_matrix(6, 50)
     for i in range(3):

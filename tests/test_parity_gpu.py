@@ -561,39 +561,78 @@ def test_randomized_rods_vs_oracle(seed):
         h.close()
 
 
-def test_continuum_snake_env_golden(golden_dir):
+def test_continuum_snake_env_golden_first_steps(golden_dir):
     """§8 f2: ContinuumSnake-v0 — travelling-wave MuscleTorques + anisotropic plane friction, 25 000
-    substeps per env-step — through the Gymnasium facade vs the reference-env-on-shim fixture.  Full
-    states for the first steps, every callback sample (centre of mass and its velocity, taken inside
-    the episode every 2083 substeps) and every reward for all 33 steps (825 000 substeps)."""
+    substeps per env-step — through the Gymnasium facade vs the reference-env-on-shim fixture.
+
+    This env has kinetic friction only, regularised over |v| in [1e-8, 2e-8] m/s and integrated
+    explicitly with dt mu g / tol ~ 1e3: wherever the rod sticks sideways the reference itself
+    chatters with amplitude a = dt * 2 mu g ~ 1.4e-5 m/s (and a / r ~ 4e-3 rad/s in roll), with a
+    round-off dependent phase.  Without friction the same kernel path agrees with the shim to 1e-11
+    (DESIGN.md 5); with it, two correct implementations agree to a few chatter amplitudes, which is
+    what the bounds below are (measured: 2.3e-7 m, 2.4e-5 m/s, 1.4e-5, 5.6e-3 rad/s)."""
     import gym_softrobot_b200 as gsb
-    if not os.path.exists(os.path.join(golden_dir, "continuum_snake_seed42.npz")):
-        pytest.skip("fixture not generated yet (oracle/gen_golden.py snake, ~25 min)")
     g = np.load(os.path.join(golden_dir, "continuum_snake_seed42.npz"))
     env = gsb.make("ContinuumSnake-v0")
     assert env.step_skip == int(g["step_skip"]) == 25000
     obs0, _ = env.reset(seed=42)
     assert obs0.dtype == np.float32 and obs0.shape == (756,)
-    np.testing.assert_allclose(obs0, g["obs0"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(obs0, g["obs0"])
+    bounds = {"position": 1e-6, "velocity": 1e-4, "director": 5e-5, "omega": 3e-2}   # absolute
     n_state = sum(1 for k in g.files if k.startswith("beta"))
-    for i, a in enumerate(g["actions"]):
-        obs, r, te, tr, info = env.step(a)
-        assert abs(env.time - float(g["time"][i])) < 1e-12
-        if i < n_state:
-            st = env.rod_state()
-            for gk in ("position", "velocity", "director", "omega"):
-                err = rel(st[FIELDS[gk]], g[f"state{i + 1}/{gk}"])
-                assert err < 1e-7, f"step {i} field {gk} rel err {err:.3e}"
-            np.testing.assert_allclose(obs, g[f"obs{i + 1}"], rtol=1e-4, atol=1e-6)
-        assert abs(r - float(g["reward"][i])) < 1e-6 * max(1.0, abs(float(g["reward"][i]))), (i, r, g["reward"][i])
-        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
-    S = len(g["cb_time"])
-    v = env._vec
-    assert len(v._times) == S
-    np.testing.assert_allclose(np.array(v._times), g["cb_time"], rtol=0, atol=1e-12)
-    com, vel = v._com[0, :S].cpu().numpy(), v._vel[0, :S].cpu().numpy()
-    assert rel(com, g["cb_com"]) < 1e-6 and rel(vel, g["cb_avg_velocity"]) < 1e-4
+    for i in range(n_state):
+        obs, r, te, tr, info = env.step(g["actions"][i])
+        assert env.time == float(g["time"][i])                 # the in-kernel clock, bit for bit
+        st = env.rod_state()
+        for gk, tol in bounds.items():
+            err = float(np.abs(st[FIELDS[gk]] - g[f"state{i + 1}/{gk}"]).max())
+            assert err < tol, f"step {i} field {gk} abs err {err:.3e}"
+        np.testing.assert_allclose(obs[:306], g[f"obs{i + 1}"][:306], rtol=0, atol=1e-4)    # x, v
+        np.testing.assert_allclose(obs[306:], g[f"obs{i + 1}"][306:], rtol=0, atol=5e-5)    # Q
+        assert r == 0.0 == float(g["reward"][i]) and (te, tr) == (False, False)
     env.close()
+
+
+def test_continuum_snake_long_horizon_is_a_replica_of_the_reference(golden_dir):
+    """33 env-steps (825 000 substeps, 6.6 s): the chatter above makes the trajectory sensitive — GPU
+    runs whose initial node positions differ by 1e-15 m drift apart by 4e-8 m (0.2 s), 3e-5 m (2 s),
+    4e-3 m (6.6 s) in the centre of mass.  Parity criterion for such a system: the reference run must be
+    indistinguishable from one more perturbed replica.  Eight envs (one exact, seven perturbed) are
+    stepped with the fixture's actions; at every callback sample the reference's centre of mass must lie
+    within 4x the replicas' own spread, and every reward within 4 sigma of the replicas' rewards."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "continuum_snake_seed42.npz"))
+    N = 8
+    v = gsb.make_vec("ContinuumSnake-v0", N, autoreset=False)
+    v.reset()
+    x = v.handle.fields()["position_collection"]
+    noise = 1e-15 * torch.randn(x.shape, device="cuda", dtype=torch.float64,
+                                generator=torch.Generator(device="cuda").manual_seed(1))
+    noise[0] = 0
+    x += noise
+    rewards = []
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = v.step(torch.as_tensor(a, device="cuda")[None].repeat(N, 1))
+        rewards.append(r.cpu().numpy())
+        assert float(info["time"][0]) == float(g["time"][i])
+        assert not bool(te.any()) and bool(tr.any()) == bool(g["truncated"][i])
+    rewards = np.array(rewards)                                   # [33, N]
+    S = len(g["cb_time"])
+    assert len(v._times) == S and np.array_equal(np.array(v._times), g["cb_time"])
+    com, vel = v._com[:, :S].cpu().numpy(), v._vel[:, :S].cpu().numpy()
+    for arr, ref, floor in ((com, g["cb_com"], 1e-7), (vel, g["cb_avg_velocity"], 5e-6)):
+        spread = np.abs(arr[1:] - arr[:1]).max(axis=(0, 2))       # replicas vs the exact run, per sample
+        dev = np.abs(arr[0] - ref).max(axis=1)
+        worst = float((dev / (4 * spread + floor)).max())
+        assert worst < 1.0, f"reference outside the replicas' spread by {worst:.2f}x"
+    assert np.all(rewards[g["reward"] == 0.0] == 0.0)             # no reward before three periods
+    nz = g["reward"] != 0.0
+    assert nz.sum() >= 3
+    mean, std = rewards[nz].mean(axis=1), rewards[nz].std(axis=1)
+    assert np.all(np.abs(g["reward"][nz] - mean) < 4 * std + 1e-6), (g["reward"][nz], mean, std)
+    assert np.all(std < 0.05 * np.abs(mean))                      # and the spread itself is a few per cent
+    v.close()
 
 
 @pytest.mark.parametrize("mode", [1, 2], ids=["fixed-target", "moving-target"])
