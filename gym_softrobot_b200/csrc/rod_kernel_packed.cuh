@@ -21,16 +21,17 @@ constexpr int PACKED_MAX_THREADS = 1024;
 // the left of element 0), so the base thread needs no select when it reads "j-1"
 // shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide (+ 6 joint-reaction rows for
 // assemblies, + 1 element-length row for the spline-torque forcing of the contact / forcing variant)
-constexpr int packed_smem_words(int nt, bool multi, bool contact = false) {
-  return (multi ? 27 : (contact ? 22 : 21)) * (nt + 2);
+constexpr int packed_smem_words(int nt, bool multi, bool torque = false) {
+  return (multi ? 27 : (torque ? 22 : 21)) * (nt + 2);
 }
 
 // LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
 // (SoftPendulum3D); kept out of the instantiation used by the other models so they do not pay
-// their registers / code size.  CONTACT: plane contact with anisotropic friction and per-env rest
+// their registers / code size.  TORQUE (with CONTACT, single rod): the muscle-torque forcings
+// (travelling wave, spline) and the element-length row they need.  CONTACT: plane contact with anisotropic friction and per-env rest
 // curvature (octopus-arm models): two more neighbour exchanges per substep.  MULTI: several rods per
 // env plus one rigid head thread, coupled by FixedJoint2Rigid spring/torque joints.
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI>
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -107,9 +108,9 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   // MuscleTorques (continuum_snake.py:186-198; PyElastica external_forces.MuscleTorques): element k gets
   // Q_k d (m_k [k >= 1] - m_{k+1} [k <= n-2]),  m_k = min(1, t/ramp) beta_{n-1-k} sin(w t - kw s_{n-1-k} + phi)
   // (the reference walks the magnitudes tail-to-head); s_i = (i+1)/n on the uniform rest template.
-  const bool muscle = CONTACT && !MULTI && A.muscle_on && elem_ok;
+  const bool muscle = TORQUE && A.muscle_on && elem_ok;
   double mus_t = 0.0, mus_b0 = 0.0, mus_b1 = 0.0, mus_s0 = 0.0, mus_s1 = 0.0;
-  if (CONTACT && !MULTI && A.muscle_on && live) {
+  if (TORQUE && A.muscle_on && live) {
     const double *mu = A.muscle + (size_t)env * A.muscle_dim;
     mus_t = mu[0];
     if (muscle) {
@@ -123,8 +124,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   // material direction d, external_torques[d, k] += mag_d[k]; mag is re-evaluated (not-a-knot cubic through
   // the rate-limited control values, at s = cumsum(current lengths)) in every substep that finds the cached
   // values different from the caller's targets, and kept otherwise — across launches too.
-  const bool spl = CONTACT && !MULTI && A.spline_mask != 0;
-  __shared__ int sh_need[CONTACT && !MULTI ? 128 : 1];
+  const bool spl = TORQUE && A.spline_mask != 0;
+  __shared__ int sh_need[TORQUE ? 128 : 1];
   T *sh_L = sh + 21 * RS;
   double *sp = (spl && live) ? A.spline + (size_t)env * A.spline_dim : nullptr;
   const int sP = A.spline_p, sCH = 2 * sP + 2;
@@ -230,7 +231,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   for (int s = 0; s < A.n_substeps; s++) {
     const bool last = (s == A.n_substeps - 1);
     T mtq[3] = {T(0), T(0), T(0)};
-    if (CONTACT && !MULTI && A.muscle_on) {
+    if (TORQUE && A.muscle_on) {
       mus_t += (double)h;   // time of the force evaluation: after the first half step
       if (muscle) {
         const double wt = A.mus_omega * mus_t, fct = fmin(1.0, mus_t / A.mus_ramp);
@@ -488,7 +489,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       for (int i = 0; i < 3; i++) tq[i] += smag[i];
     }
     // forcing registered before the contact: the static-friction torque balance sees the muscle couple
-    if (CONTACT && !MULTI && A.muscle_on && !A.contact_before_forcing) {
+    if (TORQUE && A.muscle_on && !A.contact_before_forcing) {
 #pragma unroll
       for (int i = 0; i < 3; i++) tq[i] += mtq[i];
     }
@@ -598,7 +599,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       for (int i = 0; i < 3; i++)   // node j collects half of the plane's load on elements j-1 and j
         fint[i] += T(0.5) * (sh_c12[i * RS + tid] + (has_left ? sh_c12[i * RS + tid - 1] : T(0)));
     }
-    if (CONTACT && !MULTI && A.muscle_on && A.contact_before_forcing) {
+    if (TORQUE && A.muscle_on && A.contact_before_forcing) {
 #pragma unroll
       for (int i = 0; i < 3; i++) tq[i] += mtq[i];
     }
@@ -729,7 +730,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   __syncthreads();
   if (active && first && arm == 0) {
     const bool invalid = sh_flag[r] != 0;
-    if (CONTACT && !MULTI && A.muscle_on) A.muscle[(size_t)env * A.muscle_dim] = mus_t;
+    if (TORQUE && A.muscle_on) A.muscle[(size_t)env * A.muscle_dim] = mus_t;
     if (A.model == MODEL_SOFT_PENDULUM) {
       soft_pendulum_outputs<T>(sh_x + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
                                A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);

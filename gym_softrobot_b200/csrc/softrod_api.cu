@@ -193,14 +193,14 @@ bool use_packed_kernel(const sr_handle *h) {
   return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 1024;
 }
 
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI>
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false>
 int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int group = (MULTI ? A.n_rod : 1) * (A.n_elem + 1) + (MULTI ? A.has_head : 0);   // threads per env
   const int rods_per_cta = NT / group;
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
-  const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI, CONTACT) * sizeof(T);
-  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI>;
+  const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI, TORQUE) * sizeof(T);
+  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -215,7 +215,8 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
   if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
-  if (A.contact_on || A.rest_kappa || A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
+  if (A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
+  if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
   return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
              ? launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s)
              : launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);

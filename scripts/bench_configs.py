@@ -69,4 +69,20 @@ for n_elem, n_env, dt in ((10, 16384, 7e-5), (40, 16384, 3e-5)):
     report(f"8-arm assembly n_elem={n_elem} (config 4 topology)", n_env, 8 * n_elem, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=5), 440 + 280)
     assert int(term.sum()) == 0
     env.close()
+# f2: ContinuumSnake-v0 (muscle torques + kinetic friction): one callback segment of 2083 substeps per launch
+n_env = 4096
+env = g.make_vec("ContinuumSnake-v0", n_env, autoreset=False); env.reset()
+mu = env.handle.muscle_tensor()
+mu[:, 2:] = torch.as_tensor(np.random.default_rng(3).uniform(-4e-3, 4e-3, (n_env, 6)), device="cuda") @ env._W.T
+mu[:, 1] = 2 * np.pi / 0.97
+o6, rew, term = env._scratch
+report("ContinuumSnake-v0 (per 2083-substep callback segment; env-step = 12 of these)", n_env, 50, 2083,
+       timed(lambda: env.handle.step(None, 2083, o6, rew, term), K=3, W=1), 440 + 280 + 120)
+env.close()
+# f4: SoftArmTracking-v0 (spline muscle torques, clamped arm n=40, 50 substeps per env-step)
+n_env = 16384
+env = g.make_vec("SoftArmTracking-v0", n_env, autoreset=False); env.reset(seed=1)
+acts = torch.rand((n_env, 8), device="cuda", dtype=torch.float64) * 2 - 1
+report("SoftArmTracking-v0 (whole env.step incl. host layer)", n_env, 40, 50, timed(lambda: env.step(acts), K=10), 440 + 20)
+env.close()
 print("fp64 peak", peak)
