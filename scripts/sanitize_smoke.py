@@ -26,4 +26,13 @@ env = g.make_vec("OctoFlat-v0", 5, autoreset=False); env.reset(seed=1)
 env.handle.rest_kappa_tensor()[:, 0, :] = 2.0
 o6, rew, term = env._scratch
 env.handle.step(None, K, o6, rew, term); torch.cuda.synchronize(); env.close()
+# torque forcings: travelling-wave muscle torques + kinetic friction (ContinuumSnake), spline torques (SoftArmTracking)
+env = g.make_vec("ContinuumSnake-v0", 6, autoreset=False); env.reset()
+mu = env.handle.muscle_tensor(); mu[:, 2:] = 3e-3; mu[:, 1] = 6.4
+o6, rew, term = env._scratch
+env.handle.step(None, K, o6, rew, term); torch.cuda.synchronize(); env.close()
+env = g.make_vec("SoftArmTracking-v0", 7, game_mode=2, autoreset=False); env.reset(seed=3)
+for _ in range(2):
+    env.step(torch.full((7, 8), 0.3, device="cuda", dtype=torch.float64))
+torch.cuda.synchronize(); env.close()
 print("sanitize_smoke done")
