@@ -231,7 +231,7 @@ int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   if (forced < 0) {
     const char *e = getenv("SOFTROD_PACKED_THREADS");
     forced = e ? atoi(e) : 0;
-    if (forced != 256 && forced != 320 && forced != 384 && forced != 512 && forced != 1024) forced = 0;
+    if (forced != 256 && forced != 320 && forced != 384 && forced != 512 && forced != 544 && forced != 768 && forced != 1024) forced = 0;
   }
   if (forced) return forced;
   const int tpr = (n_rod > 1 ? n_rod : 1) * (n_elem + 1) + has_head;   // threads per env group
@@ -241,7 +241,9 @@ int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   int best = 256;
   if (util(384) > util(best) + 0.02) best = 384;
   if (util(512) > util(best) + 0.02) best = 512;
-  if (tpr > 512) best = 1024;   // long rods: one rod per 1024-thread CTA (64 registers: functional, not fast)
+  // long rods: one rod per CTA, as few warps as hold it so that each thread keeps as many registers as
+  // possible (544 threads: 120 registers, 768: 80, 1024: 64)
+  if (tpr > 512) best = tpr <= 544 ? 544 : (tpr <= 768 ? 768 : 1024);
   return best;
 }
 
@@ -249,6 +251,8 @@ template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cud
   if (use_packed_kernel(h)) {
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head), mb = min_ctas_setting();
     if (nt == 1024) return launch_packed<T, 1024, 1>(h, A, s);
+    if (nt == 768) return launch_packed<T, 768, 1>(h, A, s);
+    if (nt == 544) return launch_packed<T, 544, 1>(h, A, s);
     if (nt == 512) return launch_packed<T, 512, 1>(h, A, s);
     if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
     if (nt == 384) return launch_packed<T, 384, 1>(h, A, s);
@@ -464,7 +468,7 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
     A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
     A.n_substeps = n_substeps;
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head);
-    return nt == 1024  ? launch_packed<float, 1024, 1>(h, A, (cudaStream_t)stream)
+    return nt > 512    ? launch_packed<float, 1024, 1>(h, A, (cudaStream_t)stream)
            : nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
            : nt == 384 ? launch_packed<float, 384, 1>(h, A, (cudaStream_t)stream)
                        : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
