@@ -61,10 +61,13 @@ def count_crossings(p1, p2):
 
 
 class OctoFlatVectorEnv:
-    """N independent OctoFlat-v0 envs (centralized policy mode), torch CUDA I/O."""
+    """N independent OctoFlat-v0 envs, torch CUDA I/O.  `policy_mode` as in the reference (flat_env.py:84-145,
+    248-271): "decentralized" declares a per-arm action space and appends the arm's one-hot id to each
+    row of the individual observation; the physics and the batched action layout are the same."""
 
     def __init__(self, n_env, final_time=5.0, time_step=7.0e-5, recording_fps=5, n_elems=10, n_arm=8,
-                 n_action=3, device: int = 0, autoreset: bool = True, env_offset: int = 0):
+                 n_action=3, device: int = 0, autoreset: bool = True, env_offset: int = 0,
+                 policy_mode: str = "centralized"):
         import torch
         self.torch = torch
         self.n_env, self.n_elems, self.n_seg, self.n_arm, self.n_action = n_env, n_elems, n_elems - 1, n_arm, n_action
@@ -72,9 +75,18 @@ class OctoFlatVectorEnv:
         self.step_skip = int(1.0 / (recording_fps * time_step))
         self.device = torch.device(f"cuda:{device}")
         self.autoreset, self.env_offset = autoreset, env_offset
-        lo = np.repeat(np.ones(n_action) * -22, n_arm)
-        self.single_action_space = Box(lo, -lo, shape=(n_arm * n_action,), dtype=np.float32)
-        self.obs_shapes = {"individual": (n_arm, self.n_seg + (n_elems + 1) * 4 + n_action), "shared": (13,)}
+        if policy_mode not in ("centralized", "decentralized"):
+            raise NotImplementedError(policy_mode)
+        self.policy_mode = policy_mode
+        d_ind = self.n_seg + (n_elems + 1) * 4 + n_action
+        if policy_mode == "centralized":
+            lo = np.repeat(np.ones(n_action) * -22, n_arm)
+            self.single_action_space = Box(lo, -lo, shape=(n_arm * n_action,), dtype=np.float32)
+            self.obs_shapes = {"individual": (n_arm, d_ind), "shared": (13,)}
+        else:
+            lo = np.ones(n_action) * -22
+            self.single_action_space = Box(lo, -lo, shape=(n_action,), dtype=np.float32)
+            self.obs_shapes = {"individual": (d_ind + n_arm,), "shared": (13,)}
         r0 = _ROD["base_radius"]
         self.handle = nat.Handle(
             model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elems, dt=time_step, gravity=(0.0, 0.0, _G),
@@ -121,8 +133,11 @@ class OctoFlatVectorEnv:
         c = hd[:, None, 0:2, None]                                   # head centre (x, y)
         x, v = f["position_collection"], f["velocity_collection"]
         pa = self.prev_action.reshape(self.n_env, self.n_arm, self.n_action).double()
-        ind = torch.cat([f["kappa"][:, :, 0, :], x[:, :, 0, :] - c[:, :, 0], x[:, :, 1, :] - c[:, :, 1],
-                         v[:, :, 0, :], v[:, :, 1, :], pa], dim=2).float()
+        cols = [f["kappa"][:, :, 0, :], x[:, :, 0, :] - c[:, :, 0], x[:, :, 1, :] - c[:, :, 1],
+                v[:, :, 0, :], v[:, :, 1, :], pa]
+        if self.policy_mode == "decentralized":
+            cols.append(torch.eye(self.n_arm, dtype=torch.float64, device=self.device).expand(self.n_env, -1, -1))
+        ind = torch.cat(cols, dim=2).float()
         shared = torch.cat([self.target - hd[:, 0:2], hd[:, 3:5], hd[:, 6:15]], dim=1).float()
         return {"individual": ind, "shared": shared}
 
@@ -200,7 +215,7 @@ class OctoFlatVectorEnv:
 
 
 class FlatEnv(Env):
-    """Drop-in for the reference `FlatEnv` in centralized policy mode (flat_env.py:54-66): a batch of one."""
+    """Drop-in for the reference `FlatEnv` (flat_env.py:54-66, both policy modes): a batch of one."""
 
     metadata = {"render_modes": ["rgb_array", "human"], "render_fps": 5}
 
@@ -210,11 +225,10 @@ class FlatEnv(Env):
         super().__init__()
         if render_mode not in {None, *self.metadata["render_modes"]}:
             raise ValueError(f"Unsupported render mode: {render_mode}")
-        if policy_mode != "centralized":
-            raise NotImplementedError("only the centralized policy mode is built")
         self.render_mode = render_mode
+        self.policy_mode = policy_mode
         self._vec = OctoFlatVectorEnv(1, final_time, time_step, recording_fps, n_elems, n_arm, n_action, device,
-                                      autoreset=False)
+                                      autoreset=False, policy_mode=policy_mode)
         self.final_time, self.time_step, self.step_skip = final_time, time_step, self._vec.step_skip
         self.n_arm, self.n_elems, self.n_action = n_arm, n_elems, n_action
         self.action_space = self._vec.single_action_space

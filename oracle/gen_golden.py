@@ -178,6 +178,22 @@ def gen_octo_flat(seed=42, n=3, recording_fps=50):
     print("octo_flat:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
 
 
+def gen_octo_flat_decentralized(seed=42, recording_fps=50):
+    """OctoFlat-v0, policy_mode="decentralized": same physics, per-arm action space, one-hot arm id in the
+    individual observation (flat_env.py:111-145,248-260).  One env-step is enough to pin the layout."""
+    env = ref_loader.load_reference_env("OctoFlat-v0", recording_fps=recording_fps, policy_mode="decentralized")
+    obs0, _ = env.reset(seed=seed)
+    e = env.unwrapped
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(-22, 22, size=(e.n_arm, e.n_action)).astype(np.float32)     # one action per arm
+    o, r, te, tr, info = e.step(a)
+    np.savez_compressed(os.path.join(OUT, f"octo_flat_decentralized_seed{seed}.npz"), label=LABEL, seed=seed,
+                        recording_fps=recording_fps, action=a, action_shape=np.array(env.action_space.shape),
+                        **{"obs0/individual": obs0["individual"], "obs0/shared": obs0["shared"],
+                           "obs1/individual": o["individual"], "obs1/shared": o["shared"]}, reward=np.float64(r))
+    print("octo_flat decentralized:", o["individual"].shape, r)
+
+
 def gen_snake(seed=42, n_state=3, n=33):
     """ContinuumSnake-v0 (n=50 rod, travelling-wave MuscleTorques rebuilt per action, anisotropic plane
     friction, dt=8e-6, 25 000 substeps per env-step).  33 env-steps so that the reward
@@ -249,6 +265,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
         gen_snake()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "decentralized":
+        gen_octo_flat_decentralized()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "soft_arm":
         gen_soft_arm(game_mode=1)
         gen_soft_arm(game_mode=2)
@@ -260,6 +279,7 @@ if __name__ == "__main__":
     gen_soft_pendulum_episode()
     gen_arm_single()
     gen_octo_flat()
+    gen_octo_flat_decentralized()
     gen_soft_arm(game_mode=1)
     gen_soft_arm(game_mode=2)
     gen_snake()   # ~25 min of NumPy stepping

@@ -659,3 +659,21 @@ def test_soft_arm_tracking_env_golden(golden_dir, mode):
         assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
         assert info["ctime"] == float(g["ctime"][i])
     env.close()
+
+
+def test_octo_flat_decentralized_mode_golden(golden_dir):
+    """FlatEnv(policy_mode="decentralized") (flat_env.py:111-145,248-260): per-arm action space, one action
+    row per arm, one-hot arm id appended to every row of the individual observation."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "octo_flat_decentralized_seed42.npz"))
+    env = gsb.make("OctoFlat-v0", recording_fps=int(g["recording_fps"]), policy_mode="decentralized")
+    assert env.action_space.shape == tuple(g["action_shape"]) == (3,)
+    obs0, _ = env.reset(seed=42)
+    assert obs0["individual"].shape == g["obs0/individual"].shape == (8, 64)
+    np.testing.assert_allclose(obs0["individual"], g["obs0/individual"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_array_equal(obs0["individual"][:, -8:], np.eye(8, dtype=np.float32))
+    obs, r, te, tr, info = env.step(g["action"])                 # [n_arm, n_action]
+    np.testing.assert_allclose(obs["individual"], g["obs1/individual"], rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(obs["shared"], g["obs1/shared"], rtol=1e-4, atol=1e-6)
+    assert abs(r - float(g["reward"])) < 1e-6 and not te and not tr
+    env.close()
