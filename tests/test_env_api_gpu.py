@@ -6,7 +6,9 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-IDS = ["SoftPendulum-v0", "SoftPendulum3D-v0", "OctoArmSingle-v0", "OctoFlat-v0", "OctoFlatLite-v0"]
+IDS = ["SoftPendulum-v0", "SoftPendulum3D-v0", "OctoArmSingle-v0", "OctoFlat-v0", "OctoFlatLite-v0",
+       "ContinuumSnake-v0", "SoftArmTracking-v0"]
+INFO_KEY = {"ContinuumSnake-v0": None, "SoftArmTracking-v0": "ctime"}     # what the reference env puts in info
 FAST_KW = {"OctoArmSingle-v0": dict(recording_fps=100), "OctoFlat-v0": dict(recording_fps=100),
            "OctoFlatLite-v0": dict(recording_fps=100)}
 
@@ -30,7 +32,8 @@ def test_env_api(env_id):
     ob, reward, terminated, truncated, info = env.step(a)
     assert _contains(getattr(env, "observation_space", None), ob)
     assert np.isscalar(reward) and isinstance(terminated, bool) and isinstance(truncated, bool)
-    assert "time" in info
+    key = INFO_KEY.get(env_id, "time")
+    assert key is None or key in info
     # reset(seed) twice gives the same first observation (check_env's determinism requirement)
     o1, _ = env.reset(seed=3)
     o2, _ = env.reset(seed=3)
@@ -83,6 +86,75 @@ def test_vector_env_autoreset_and_truncation():
             assert torch.equal(obs[:, 1], torch.zeros(n_env, device="cuda"))   # fresh rods are at rest
             assert not torch.equal(obs, info["final_obs"])
     assert int(env.step_count.min()) == 2 and torch.isfinite(obs).all()
+    env.close()
+
+
+def test_soft_arm_vector_env_truncation_and_autoreset():
+    """Batched SoftArmTracking (moving targets): truncation on env-step 500 (tick * sim_dt >= 5 evaluated in
+    float64 like soft_arm_tracking.py:254), rebuilt inside the same step(), fresh targets per episode."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    n_env = 5
+    env = gsb.make_vec("SoftArmTracking-v0", n_env, game_mode=2)
+    obs0, _ = env.reset(seed=7)
+    assert env.n_updates == 500 and obs0.dtype == torch.float64 and obs0.shape == (n_env, 14)
+    first_targets = env._targets.clone()
+    assert not torch.equal(first_targets[0], first_targets[1])            # one stream per env
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    for s in range(1, 503):
+        # moderate actions: full-range white noise re-drawn every 10 ms can blow the arm up (the reference
+        # anticipates it: "Episode blew up. Maybe try a smaller dt?"); that path is tested separately below
+        a = 0.3 * (torch.rand((n_env, 8), generator=gen, device="cuda", dtype=torch.float64) * 2 - 1)
+        obs, rew, term, trunc, info = env.step(a)
+        assert not bool(term.any()) and bool(trunc.all()) == (s == 500)
+        assert torch.isfinite(obs).all() and bool((rew <= 0).all())
+        if s == 500:
+            assert info["final_obs"].shape == (n_env, 14) and int(env.tick.max()) == 0
+            assert torch.equal(obs[:, :8], torch.zeros((n_env, 8), dtype=torch.float64, device="cuda"))   # straight arm
+            assert torch.allclose(obs[:, 8:11], torch.tensor([0.0, 1.0, 0.0], dtype=torch.float64, device="cuda").expand(n_env, 3))
+            assert not torch.equal(env._targets, first_targets)           # new trajectories
+            pts, mags = env.handle.spline_tensors()
+            assert float(pts.abs().max()) == 0.0 and float(mags.abs().max()) == 0.0   # fresh forcing instances
+    assert int(env.tick.min()) == 2
+    env.close()
+
+
+def test_soft_arm_blow_up_path():
+    """soft_arm_tracking.py:247-252: a NaN state gives reward -100, a nan_to_num'ed observation and
+    terminated=True; the batched env rebuilds that env only."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    env = gsb.make_vec("SoftArmTracking-v0", 4)
+    env.reset(seed=0)
+    a = torch.zeros((4, 8), dtype=torch.float64, device="cuda")
+    env.step(a)
+    env.fields()["velocity_collection"][2, 0, 5] = float("nan")
+    obs, rew, term, trunc, info = env.step(a)
+    assert term.tolist() == [False, False, True, False] and not bool(trunc.any())
+    assert float(rew[2]) == -100.0 and bool((rew[[0, 1, 3]] > -1.0).all())
+    assert torch.isfinite(info["final_obs"]).all() and info["reset_idx"].tolist() == [2]
+    assert env.tick.tolist() == [2, 2, 0, 2] and torch.isfinite(obs).all()
+    env.close()
+
+
+def test_snake_vector_env_truncation_and_autoreset():
+    """Batched ContinuumSnake: the in-kernel clock reaches final_time = 22.02 s on env-step 111
+    (continuum_snake.py:279-287, 211-212), every env is rebuilt in that step and the clock restarts."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    n_env = 3
+    env = gsb.make_vec("ContinuumSnake-v0", n_env)
+    obs0, _ = env.reset()
+    a = torch.tensor([[3.4e-3, 3.3e-3, 4.2e-3, 2.6e-3, 3.6e-3, 3.5e-3, 0.97]], device="cuda").repeat(n_env, 1)
+    for s in range(1, 113):
+        obs, rew, term, trunc, info = env.step(a)
+        assert not bool(term.any()) and bool(trunc.all()) == (s == 111), s
+        if s == 110:
+            assert float(rew.min()) > 0.01                                # the published gait crawls forward
+        if s == 111:
+            assert torch.equal(obs, obs0) and float(env.handle.muscle_tensor()[:, 0].max()) == 0.0
+            assert len(env._times) == 1 and info["final_obs"].shape == (n_env, 756)
+    assert abs(float(info["time"][0]) - 0.2) < 1e-9 and torch.isfinite(obs).all()
     env.close()
 
 
