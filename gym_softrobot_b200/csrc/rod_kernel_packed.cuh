@@ -647,22 +647,28 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         T fw[3] = {elem_in ? w[0] : T(0), elem_in ? w[1] : T(0), elem_in ? w[2] : T(0)};
         // pass 0 sees the *unfiltered* ends (w[0], w[-1] are only zeroed after the first update)
         T ev[3] = {v[0], v[1], v[2]}, ew[3] = {w[0], w[1], w[2]};
-        for (int p = 0; p < A.laplace_order; p++) {
-          T *buf = (p & 1) ? sh_Q : sh_x;
+        const int t_left = (j > 0) ? tid - 1 : tid;
+        auto pass = [&](T *buf, bool first_pass) {
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            buf[c * RS + tid] = (p == 0) ? ev[c] : fv[c];
-            buf[(3 + c) * RS + tid] = (p == 0) ? ew[c] : fw[c];
+            buf[c * RS + tid] = first_pass ? ev[c] : fv[c];
+            buf[(3 + c) * RS + tid] = first_pass ? ew[c] : fw[c];
           }
           __syncthreads();
 #pragma unroll
           for (int c = 0; c < 3; c++) {
-            T mv = (p == 0) ? ev[c] : fv[c], mw = (p == 0) ? ew[c] : fw[c];
-            T nv = (-buf[c * RS + t_next] - buf[c * RS + ((j > 0) ? tid - 1 : tid)] + T(2) * mv) * T(0.25);
-            T nw = (-buf[(3 + c) * RS + t_next] - buf[(3 + c) * RS + ((j > 0) ? tid - 1 : tid)] + T(2) * mw) * T(0.25);
+            T mv = first_pass ? ev[c] : fv[c], mw = first_pass ? ew[c] : fw[c];
+            T nv = (-buf[c * RS + t_next] - buf[c * RS + t_left] + T(2) * mv) * T(0.25);
+            T nw = (-buf[(3 + c) * RS + t_next] - buf[(3 + c) * RS + t_left] + T(2) * mw) * T(0.25);
             fv[c] = node_in ? nv : T(0);
             fw[c] = elem_in ? nw : T(0);
           }
+        };
+        if (A.laplace_order == 7) {   // SoftPendulum3D-v0's order: unrolled, buffers and the first-pass case resolved at compile time
+#pragma unroll
+          for (int p = 0; p < 7; p++) pass((p & 1) ? sh_Q : sh_x, p == 0);
+        } else {
+          for (int p = 0; p < A.laplace_order; p++) pass((p & 1) ? sh_Q : sh_x, p == 0);
         }
         __syncthreads();   // the last pass's reads finish before x,v,Q are published again
 #pragma unroll
