@@ -173,3 +173,32 @@ def test_c_oracle_arm_single_matches_golden(golden_dir):
             assert rel(getattr(rod, fk), g[f"state{i + 1}/{gk}"]) < 1e-9, (i, gk)
     # the plane carries the rod: it has settled ~ weight / k below the surface, not fallen through
     assert -5e-4 < rod.position_collection[2].min() and rod.position_collection[2].max() < 0.05
+
+
+def _sliding_contact(before_forcing):
+    r = 0.01
+    return dict(plane_origin=[0.0, 0.0, -r], plane_normal=[0.0, 0.0, 1.0], k=1e2, nu=1e1, slip_velocity_tol=1e-8,
+                static_mu=[0.4, 0.6, 0.8], kinetic_mu=[0.2, 0.3, 0.4], before_forcing=before_forcing)
+
+
+@pytest.mark.parametrize("v0,mu", [(0.1, 0.2), (-0.1, 0.3)], ids=["forward", "backward"])
+def test_sliding_rod_decelerates_at_mu_g(v0, mu):
+    """Known answer from physics, independent of any recollection of PyElastica: a straight rod sliding
+    along its axis on the plane loses speed at mu_kinetic * g (forward / backward coefficients,
+    `RodPlaneContactWithAnisotropicFriction`).  It also settles the operator order inside
+    `synchronize` (oracle/shims/elastica/modules.py): if the contact ran BEFORE gravity it would see no
+    weight to cancel, the friction magnitude would be zero and the rod would not slow down at all."""
+    g, dt, steps = 9.81, 1e-5, 2000
+    speeds = {}
+    for before in (False, True):
+        rod = ro.OracleRod(20, [0, 0, 0], [1.0, 0, 0], [0, 0, 1.0], 1.0, 0.01, 1000.0, 1e6, dt,
+                           gravity=(0.0, 0.0, -g), contact=_sliding_contact(before))
+        rod.velocity_collection[0, :] = v0
+        rod.substeps(steps)
+        speeds[before] = rod.velocity_collection[0].copy()
+        if not before:
+            assert np.abs(rod.position_collection[2]).max() < 1e-9      # its weight is carried: it stays on the plane
+        rod.close()
+    expected = v0 - np.sign(v0) * mu * g * dt * steps
+    assert np.abs(speeds[False] - expected).max() < 1e-3 * abs(v0)      # forcing -> contact: Coulomb friction
+    assert np.abs(speeds[True] - v0).max() < 1e-6 * abs(v0)             # contact -> forcing: frictionless

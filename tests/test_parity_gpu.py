@@ -677,3 +677,26 @@ def test_octo_flat_decentralized_mode_golden(golden_dir):
     np.testing.assert_allclose(obs["shared"], g["obs1/shared"], rtol=1e-4, atol=1e-6)
     assert abs(r - float(g["reward"])) < 1e-6 and not te and not tr
     env.close()
+
+
+@pytest.mark.parametrize("v0,mu", [(0.1, 0.2), (-0.1, 0.3)], ids=["forward", "backward"])
+def test_sliding_rod_decelerates_at_mu_g_on_gpu(v0, mu):
+    """The Coulomb-friction known answer of tests/test_oracle_golden.py on the CUDA path: a rod sliding along
+    its axis slows down at mu_kinetic * g when the contact runs after gravity (the envs' order) and not at
+    all when it runs before."""
+    import torch
+    nat = _native()
+    g, dt, steps, r = 9.81, 1e-5, 2000, 0.01
+    for before in (False, True):
+        c = dict(plane_origin=[0.0, 0.0, -r], plane_normal=[0.0, 0.0, 1.0], k=1e2, nu=1e1, slip_velocity_tol=1e-8,
+                 static_mu=[0.4, 0.6, 0.8], kinetic_mu=[0.2, 0.3, 0.4], before_forcing=before)
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=4, n_elem=20, dt=dt, base_length=1.0, base_radius=r, density=1000.0,
+                       youngs_modulus=1e6, gravity=(0.0, 0.0, -g), bc_kind=nat.BC_FREE, contact=c)
+        init = np.zeros((4, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+        h.reset_host(init)
+        h.fields()["velocity_collection"][:, 0, :] = v0
+        h.step_host(None, steps)
+        v = h.fields()["velocity_collection"][:, 0, :].cpu().numpy()
+        expected = v0 if before else v0 - np.sign(v0) * mu * g * dt * steps
+        assert np.abs(v - expected).max() < 1e-3 * abs(v0)
+        h.close()
