@@ -15,6 +15,7 @@ try:  # pragma: no cover - depends on the image
     HAVE_GYMNASIUM = True
     Env = _gym.Env
     Box = _spaces.Box
+    Dict = _spaces.Dict
 except ImportError:
     HAVE_GYMNASIUM = False
 
@@ -106,3 +107,34 @@ except ImportError:
 
         def __repr__(self):
             return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+    class Dict:
+        """`gymnasium.spaces.Dict` stand-in: an ordered mapping of sub-spaces (FlatEnv's observation space,
+        flat_env.py:99-130)."""
+
+        def __init__(self, spaces=None, seed=None, **kwargs):
+            self.spaces = dict(spaces or {}, **kwargs)
+            if seed is not None:
+                self.seed(seed)
+
+        def __getitem__(self, key):
+            return self.spaces[key]
+
+        def keys(self):
+            return self.spaces.keys()
+
+        def items(self):
+            return self.spaces.items()
+
+        def seed(self, seed=None):
+            return {k: s.seed(None if seed is None else seed + i) for i, (k, s) in enumerate(self.spaces.items())}
+
+        def sample(self):
+            return {k: s.sample() for k, s in self.spaces.items()}
+
+        def contains(self, x):
+            return (isinstance(x, dict) and x.keys() == self.spaces.keys()
+                    and all(self.spaces[k].contains(v) for k, v in x.items()))
+
+        def __repr__(self):
+            return "Dict(" + ", ".join(f"{k!r}: {s!r}" for k, s in self.spaces.items()) + ")"

@@ -12,7 +12,7 @@ from typing import Optional
 import numpy as np
 
 from .. import _native as nat
-from ..compat import Box, Env
+from ..compat import Box, Dict, Env
 from .arm_single import arm_contact_params, _ROD, _G
 from .soft_pendulum import _advance_time
 
@@ -232,6 +232,11 @@ class FlatEnv(Env):
         self.final_time, self.time_step, self.step_skip = final_time, time_step, self._vec.step_skip
         self.n_arm, self.n_elems, self.n_action = n_arm, n_elems, n_action
         self.action_space = self._vec.single_action_space
+        # flat_env.py:99-130: the declared individual shape is per arm in decentralized mode
+        shapes = self._vec.obs_shapes
+        self.observation_space = Dict({
+            "individual": Box(-np.inf, np.inf, shape=shapes["individual"], dtype=np.float32),
+            "shared": Box(-np.inf, np.inf, shape=shapes["shared"], dtype=np.float32)})
         self.time = np.float64(0.0)
         self.counter = 0
 

@@ -15,7 +15,7 @@ FAST_KW = {"OctoArmSingle-v0": dict(recording_fps=100), "OctoFlat-v0": dict(reco
 
 def _contains(space_or_shapes, obs):
     if isinstance(obs, dict):
-        return all(np.isfinite(v).all() and v.dtype == np.float32 for v in obs.values())
+        return all(np.isfinite(v).all() and v.dtype == np.float32 for v in obs.values()) and space_or_shapes.contains(obs)
     return space_or_shapes.contains(obs)
 
 
