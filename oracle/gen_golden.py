@@ -194,6 +194,48 @@ def gen_octo_flat_decentralized(seed=42, recording_fps=50):
     print("octo_flat decentralized:", o["individual"].shape, r)
 
 
+def gen_spline_forcing(seed=5):
+    """The reference's `MuscleTorquesWithVaryingBetaSplines` (muscle_torques_with_bspline.py) driven directly,
+    outside any env, to cover what SoftArmTracking-v0 does not: a finite max_rate_of_change_of_activation
+    (the spline is re-fitted at the current lengths on every substep until the cached control values reach
+    the targets), the tangent (twist) direction, 3 control points, targets changed every 50 substeps."""
+    ref_loader.install_shims()
+    import elastica as ea
+    from gym_softrobot.utils.custom_elastica.muscle_torque import MuscleTorquesWithVaryingBetaSplines
+
+    class Sim(ea.BaseSystemCollection, ea.Constraints, ea.Forcing, ea.Damping):
+        pass
+
+    n, L, r, E, dt = 24, 0.5, 0.02, 1e6, 5e-5
+    sim = Sim()
+    rod = ea.CosseratRod.straight_rod(n, np.zeros(3), np.array([0.0, 0.0, 1.0]), np.array([1.0, 0.0, 0.0]), L, r, 1000.0,
+                                      youngs_modulus=E)
+    sim.append(rod)
+    sim.constrain(rod).using(ea.OneEndFixedBC, constrained_position_idx=(0,), constrained_director_idx=(0,))
+    sim.dampen(rod).using(ea.AnalyticalLinearDamper, damping_constant=0.5, time_step=dt)
+    pts = {"normal": [], "tangent": []}
+    for d in ("normal", "tangent"):
+        sim.add_forcing_to(rod).using(MuscleTorquesWithVaryingBetaSplines, base_length=L, number_of_control_points=3,
+                                      points_func_array=pts[d], muscle_torque_scale=1.0, direction=d, step_skip=10 ** 9,
+                                      max_rate_of_change_of_activation=0.04)
+    sim.finalize()
+    stepper, t = ea.PositionVerlet(), np.float64(0.0)
+    rng = np.random.default_rng(seed)
+    out = {"label": LABEL, "n_elem": n, "base_length": L, "base_radius": r, "youngs_modulus": E, "dt": dt,
+           "damping_constant": 0.5, "scale": 1.0, "max_rate": 0.04, "n_ctrl": 3, "segment": 50}
+    targets = []
+    for seg in range(8):
+        tgt = rng.uniform(-1, 1, (2, 3))
+        pts["normal"][:] = tgt[0]; pts["tangent"][:] = tgt[1]
+        targets.append(tgt)
+        for _ in range(50):
+            t = stepper.step(sim, t, dt)
+        pack(f"seg{seg + 1}", rod_state(rod), out)
+    out["targets"] = np.array(targets)
+    np.savez_compressed(os.path.join(OUT, f"spline_forcing_seed{seed}.npz"), **out)
+    print("spline forcing: tip", rod.position_collection[:, -1], "twist", rod.kappa[2].mean())
+
+
 def gen_snake(seed=42, n_state=3, n=33):
     """ContinuumSnake-v0 (n=50 rod, travelling-wave MuscleTorques rebuilt per action, anisotropic plane
     friction, dt=8e-6, 25 000 substeps per env-step).  33 env-steps so that the reward
@@ -265,6 +307,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
         gen_snake()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "spline":
+        gen_spline_forcing()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "decentralized":
         gen_octo_flat_decentralized()
         sys.exit(0)
@@ -280,6 +325,7 @@ if __name__ == "__main__":
     gen_arm_single()
     gen_octo_flat()
     gen_octo_flat_decentralized()
+    gen_spline_forcing()
     gen_soft_arm(game_mode=1)
     gen_soft_arm(game_mode=2)
     gen_snake()   # ~25 min of NumPy stepping

@@ -700,3 +700,33 @@ def test_sliding_rod_decelerates_at_mu_g_on_gpu(v0, mu):
         expected = v0 if before else v0 - np.sign(v0) * mu * g * dt * steps
         assert np.abs(v - expected).max() < 1e-3 * abs(v0)
         h.close()
+
+
+def test_spline_torque_forcing_rate_limited_and_tangent(golden_dir):
+    """The spline-torque ABI beyond what SoftArmTracking-v0 uses: finite max_rate (the cached control values
+    creep towards the targets by 0.04 per substep, each time re-fitting the spline at the current lengths),
+    twist (tangent) direction, 3 control points — against the reference's forcing class driven directly on
+    the shim rod (oracle/gen_golden.py:gen_spline_forcing)."""
+    import torch
+    nat = _native()
+    g = np.load(os.path.join(golden_dir, "spline_forcing_seed5.npz"))
+    n, seg = int(g["n_elem"]), int(g["segment"])
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=3, n_elem=n, dt=float(g["dt"]), base_length=float(g["base_length"]),
+                   base_radius=float(g["base_radius"]), density=1000.0, youngs_modulus=float(g["youngs_modulus"]),
+                   damping_constant=float(g["damping_constant"]), bc_kind=nat.BC_ONE_END_FIXED,
+                   spline=dict(directions=(0, 2), n_ctrl=int(g["n_ctrl"]), scale=float(g["scale"]), max_rate=float(g["max_rate"])))
+    init = np.zeros((3, 9)); init[:, 5] = 1.0; init[:, 6] = 1.0          # direction +z, normal +x
+    h.reset_host(init)
+    pts, mags = h.spline_tensors()
+    for s, tgt in enumerate(g["targets"]):
+        pts[:, 0, :3] = torch.as_tensor(tgt[0], device="cuda")
+        pts[:, 2, :3] = torch.as_tensor(tgt[1], device="cuda")
+        h.step_host(None, seg)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        for gk in ("position", "velocity", "director", "omega", "kappa"):
+            for e in range(3):
+                err = rel(f[FIELDS[gk]][e], g[f"seg{s + 1}/{gk}"])
+                assert err < 1e-9, f"segment {s} field {gk} rel err {err:.3e}"
+    # 50 substeps at 0.04 per substep cover a change of (just about) 2: the cached values are at the targets
+    assert torch.allclose(pts[:, 0, 3:6], pts[:, 0, :3], rtol=0, atol=0.05) and float(mags[:, 1].abs().max()) == 0.0
+    h.close()
