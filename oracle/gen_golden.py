@@ -236,6 +236,64 @@ def gen_spline_forcing(seed=5):
     print("spline forcing: tip", rod.position_collection[:, -1], "twist", rod.kappa[2].mean())
 
 
+def gen_muscle_torques(seed=9):
+    """PyElastica `MuscleTorques` (shim restatement) on the snake rod WITHOUT friction, so that the
+    comparison is round-off limited (with kinetic friction the reference dynamics chatter):
+    case A = plane with zero friction coefficients + gravity (normal response only), case B = no plane, no
+    gravity, oblique torque direction and a phase shift.  Both rebuild the forcing (new beta spline / wave
+    number) half way, like `set_action` does."""
+    ref_loader.install_shims()
+    import elastica as ea
+
+    class Sim(ea.BaseSystemCollection, ea.Constraints, ea.Forcing, ea.Damping, ea.Contact):
+        pass
+
+    n, L, E, dt, period = 50, 0.35, 1e6, 8e-6, 2.0
+    r = L * 0.011
+    rng = np.random.default_rng(seed)
+    out = {"label": LABEL, "n_elem": n, "dt": dt, "period": period, "segment": 1500}
+    for case, (plane, direction, phase) in {"A": (True, np.array([0.0, 1.0, 0.0]), 0.0),
+                                            "B": (False, np.array([0.6, 0.8, 0.0]), 0.7)}.items():
+        sim = Sim()
+        rod = ea.CosseratRod.straight_rod(n, np.zeros(3), np.array([0.0, 0.0, 1.0]), np.array([0.0, 1.0, 0.0]), L, r, 1000.0,
+                                          youngs_modulus=E, shear_modulus=E / 1.5)
+        sim.append(rod)
+        sim.dampen(rod).using(ea.AnalyticalLinearDamper, damping_constant=1e-4, time_step=dt)
+        if plane:
+            sim.add_forcing_to(rod).using(ea.GravityForces, acc_gravity=np.array([0.0, -9.80665, 0.0]))
+        ref = {}
+
+        class Probe(ea.MuscleTorques):
+            def __init__(self, *a, **k):
+                super().__init__(*a, **k)
+                ref["f"] = self
+
+        kw = dict(base_length=L, period=period, phase_shift=phase, rest_lengths=rod.rest_lengths, ramp_up_time=period,
+                  direction=direction, with_spline=True)
+        sim.add_forcing_to(rod).using(Probe, b_coeff=np.zeros(6), wave_number=2 * np.pi, **kw)
+        if plane:
+            pl = ea.Plane(plane_origin=np.array([0.0, -r, 0.0]), plane_normal=np.array([0.0, 1.0, 0.0]))
+            sim.append(pl)
+            sim.detect_contact_between(rod, pl).using(ea.RodPlaneContactWithAnisotropicFriction, k=1.0, nu=1e-6,
+                                                      slip_velocity_tol=1e-8, static_mu_array=np.zeros(3),
+                                                      kinetic_mu_array=np.zeros(3))
+        sim.finalize()
+        stepper, t = ea.PositionVerlet(), np.float64(0.0)
+        for seg in range(2):
+            b = rng.uniform(-5e-3, 5e-3, 6).astype(np.float32)
+            wl = np.float32(rng.uniform(0.7, 1.5))
+            ref["f"].__init__(b_coeff=b, wave_number=2.0 * np.pi / wl, **kw)
+            out[f"{case}/b{seg}"], out[f"{case}/wave_number{seg}"] = b, np.float64(ref["f"].wave_number)
+            out[f"{case}/beta{seg}"] = ref["f"].my_spline.copy()
+            for _ in range(1500):
+                t = stepper.step(sim, t, dt)
+            pack(f"{case}/seg{seg + 1}", rod_state(rod), out)
+        out[f"{case}/time"] = t
+        out[f"{case}/direction"], out[f"{case}/phase"] = direction, phase
+        print("muscle case", case, "max |omega|", np.abs(rod.omega_collection).max())
+    np.savez_compressed(os.path.join(OUT, f"muscle_torques_seed{seed}.npz"), **out)
+
+
 def gen_snake(seed=42, n_state=3, n=33):
     """ContinuumSnake-v0 (n=50 rod, travelling-wave MuscleTorques rebuilt per action, anisotropic plane
     friction, dt=8e-6, 25 000 substeps per env-step).  33 env-steps so that the reward
@@ -307,6 +365,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
         gen_snake()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "muscle":
+        gen_muscle_torques()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "spline":
         gen_spline_forcing()
         sys.exit(0)
@@ -326,6 +387,7 @@ if __name__ == "__main__":
     gen_octo_flat()
     gen_octo_flat_decentralized()
     gen_spline_forcing()
+    gen_muscle_torques()
     gen_soft_arm(game_mode=1)
     gen_soft_arm(game_mode=2)
     gen_snake()   # ~25 min of NumPy stepping

@@ -730,3 +730,44 @@ def test_spline_torque_forcing_rate_limited_and_tangent(golden_dir):
     # 50 substeps at 0.04 per substep cover a change of (just about) 2: the cached values are at the targets
     assert torch.allclose(pts[:, 0, 3:6], pts[:, 0, :3], rtol=0, atol=0.05) and float(mags[:, 1].abs().max()) == 0.0
     h.close()
+
+
+@pytest.mark.parametrize("case", ["A", "B"], ids=["frictionless-plane", "free-oblique-phase"])
+def test_muscle_torques_without_friction_are_roundoff_limited(golden_dir, case):
+    """The travelling-wave `MuscleTorques` path at full precision: the snake rod without friction (A: plane
+    with zero friction coefficients + gravity; B: no plane, oblique torque direction, phase shift), forcing
+    rebuilt half way like `set_action` does.  3000 substeps, 1e-9 — the statistical criterion of the
+    ContinuumSnake tests is needed for the friction law only."""
+    import torch
+    from gym_softrobot_b200.envs.snake import snake_contact_params, beta_spline_matrix
+    nat = _native()
+    g = np.load(os.path.join(golden_dir, "muscle_torques_seed9.npz"))
+    n, L, E = int(g["n_elem"]), 0.35, 1e6
+    contact = None
+    if case == "A":
+        contact = snake_contact_params()
+        contact["kinetic_mu"] = np.zeros(3)
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=2, n_elem=n, dt=float(g["dt"]), base_length=L, base_radius=L * 0.011,
+                   density=1000.0, youngs_modulus=E, shear_modulus=E / 1.5, damping_constant=1e-4,
+                   gravity=(0.0, -9.80665, 0.0) if case == "A" else (0.0, 0.0, 0.0), contact=contact,
+                   muscle=dict(period=float(g["period"]), ramp_up_time=float(g["period"]), phase_shift=float(g[f"{case}/phase"]),
+                               direction=g[f"{case}/direction"]))
+    init = np.zeros((2, 9)); init[:, 5] = 1.0; init[:, 7] = 1.0
+    h.reset_host(init)
+    mu = h.muscle_tensor()
+    W = beta_spline_matrix(6, n)
+    for seg in range(2):
+        beta = W @ g[f"{case}/b{seg}"].astype(np.float64)
+        np.testing.assert_allclose(beta, g[f"{case}/beta{seg}"], rtol=0, atol=1e-17)
+        mu[:, 2:] = torch.as_tensor(beta, device="cuda")
+        mu[:, 1] = float(g[f"{case}/wave_number{seg}"])
+        h.step_host(None, int(g["segment"]))
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        floors = rate_floors(E, 1000.0, L, n, L * 0.011, L)      # the rod hardly moves in 12-24 ms: see rate_floors
+        for gk in ("position", "velocity", "director", "omega"):
+            ref = g[f"{case}/seg{seg + 1}/{gk}"]
+            err = float(np.abs(f[FIELDS[gk]][1] - ref).max())
+            tol = 1e-9 * float(np.abs(ref).max()) + floors[FIELDS[gk]]
+            assert err < tol, f"case {case} segment {seg} field {gk}: abs err {err:.3e} > {tol:.3e} (|ref| {np.abs(ref).max():.3e})"
+    assert float(mu[0, 0]) == float(g[f"{case}/time"])
+    h.close()
