@@ -31,7 +31,12 @@ constexpr int packed_smem_words(int nt, bool multi, bool torque = false) {
 // (travelling wave, spline) and the element-length row they need.  CONTACT: plane contact with anisotropic friction and per-env rest
 // curvature (octopus-arm models): two more neighbour exchanges per substep.  MULTI: several rods per
 // env plus one rigid head thread, coupled by FixedJoint2Rigid spring/torque joints.
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false>
+// FASTONLY: no warp votes / libm fallbacks in the substep body (they split it into basic blocks and cost ~5 %);
+// a thread that sees an argument outside the polynomials' range raises a flag instead, the env's state is
+// then NOT written back (global memory still holds the pre-launch state) and redo[env] is set: the safe
+// instantiation, launched right behind with redo_filter = 1, steps exactly those envs.
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false,
+          bool FASTONLY = false>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -49,7 +54,14 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const int arm = (MULTI && !is_head) ? u / tpr : 0;
   const int j = is_head ? 0 : u - arm * tpr;
   const int env = blockIdx.x * rods_per_cta + r;    // rods_per_cta counts env groups
-  const bool live = (r < rods_per_cta) && (env < A.n_env);
+  const bool in_grid = (r < rods_per_cta) && (env < A.n_env);
+  bool selected = true;
+  if (!FASTONLY && A.redo_filter) {   // fallback launch: flagged envs only; most CTAs have none and leave
+    selected = in_grid && A.redo[env] != 0;
+    if (!__syncthreads_or(selected)) return;
+  }
+  const bool live = in_grid && selected;
+  bool dom_bad = false;               // FASTONLY: an argument left the fast-math domain
   const bool active = live && !is_head;             // a thread that owns a node / element of a rod
   const int rod = env * n_rod + arm;                // global rod slot in the state arrays
   const int t_head = r * G + G - 1;                 // where this env's head publishes its state
@@ -207,7 +219,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
     if (moving) { x[0] = pin_x; x[1] = pin_y; }
     T q = fma(a2, a2, fma(a1, a1, a0 * a0));
-    if (!__any_sync(FULL, !(q <= T(kSmallRotQ)))) rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
+    if (FASTONLY) {
+      dom_bad = dom_bad || (q > T(kSmallRotQ));
+      rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
+    } else if (!__any_sync(FULL, !(q <= T(kSmallRotQ)))) rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
     else rotate_directors_ref<T>(a0, a1, a2, Q);
     hh_prev = hh;
   };
@@ -387,7 +402,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     constexpr bool F64 = sizeof(T) == 8;
     if (!F64) u = fmax(u, T(0));                  // FP32: the guard is below epsilon; keep u >= 0
     T fac;
-    if (!__any_sync(FULL, !(u <= T(kSmallBendU)))) {
+    if (FASTONLY) dom_bad = dom_bad || (u > T(kSmallBendU));
+    if (FASTONLY || !__any_sync(FULL, !(u <= T(kSmallBendU)))) {
       if (F64) {
         T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
         fac = theta_over_sin(A.poly, u) * fma(T(0.5e-14), cot, T(-0.5));
@@ -435,7 +451,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
       bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
                  !(fabs_(z2) <= T(kSmallExpZ));
-      if (!__any_sync(FULL, big)) {
+      if (FASTONLY) dom_bad = dom_bad || (fabs_(z0) > T(kSmallExpZ)) || (fabs_(z1) > T(kSmallExpZ)) || (fabs_(z2) > T(kSmallExpZ));
+      if (FASTONLY || !__any_sync(FULL, big)) {
         cw0 = A.c_w[0] * exp_small(A.poly, z0);
         cw2 = A.c_w[2] * exp_small(A.poly, z2);
         cw1 = A.isotropic ? cw0 : A.c_w[1] * exp_small(A.poly, z1);
@@ -700,8 +717,18 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
   }
   __syncthreads();   // all reads of the exchange buffers are done: reuse them below
+  bool redo = false;
+  if (FASTONLY) {    // env-level OR of the domain flags; a flagged env keeps its pre-launch state in global memory
+    int *sh_dom = reinterpret_cast<int *>(sh_N);
+    if (tid < 64) sh_dom[tid] = 0;
+    __syncthreads();
+    if (live && dom_bad) atomicOr(&sh_dom[r], 1);
+    __syncthreads();
+    redo = live && sh_dom[r] != 0;
+    if (redo && active && first && arm == 0) A.redo[env] = 1;
+  }
   bool bad = false;
-  if (MULTI && hd) {
+  if (MULTI && hd && !redo) {
 #pragma unroll
     for (int c = 0; c < 3; c++) { hd[c] = x[c]; hd[3 + c] = v[c]; hd[15 + c] = w[c]; }
 #pragma unroll
@@ -709,7 +736,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     float *o = A.obs + (size_t)env * A.obs_dim;
     for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
   }
-  if (active) {
+  if (active && !redo) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       st[(F_POS + c) * stride + j] = x[c];
@@ -734,7 +761,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   __syncthreads();
   if (active && bad) atomicOr(&sh_flag[r], 1);
   __syncthreads();
-  if (active && first && arm == 0) {
+  if (!FASTONLY && A.redo_filter && active && first && arm == 0) A.redo[env] = 0;
+  if (active && first && arm == 0 && !redo) {
     const bool invalid = sh_flag[r] != 0;
     if (TORQUE && A.muscle_on) A.muscle[(size_t)env * A.muscle_dim] = mus_t;
     if (A.model == MODEL_SOFT_PENDULUM) {
@@ -752,7 +780,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       A.terminated[env] = invalid ? 1 : 0;
     }
   }
-  if (active && A.model == MODEL_ROD && j == n && !MULTI) {
+  if (active && A.model == MODEL_ROD && j == n && !MULTI && !redo) {
     float *o = A.obs + (size_t)env * A.obs_dim;
     for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
   }

@@ -74,6 +74,9 @@ template <typename T> struct RodArgs {
   T joint_k, joint_nu, joint_kt, joint_radius, joint_cs[16][2];   // cos/sin of each arm's mounting angle
   T head_dt_inv_mass, head_J[3], head_Jinv[3];
   int isotropic;       // J1 == J2 (circular cross-section): c_w[0] == c_w[1]
+  // fast-only / fallback pair of the packed kernel: envs that leave the fast-math domain are flagged in
+  // redo[] by the fast-only kernel (which leaves their state untouched) and re-run by the safe kernel
+  int *redo; int redo_filter;   // redo_filter: this (safe) launch steps flagged envs only and clears the flag
   // MuscleTorques travelling wave (continuum_snake.py:186-198): [n_env][muscle_dim] = time, wave number, beta[n]
   double *muscle; int muscle_on, muscle_dim;
   double mus_omega, mus_ramp, mus_phase; T mus_dir[3];

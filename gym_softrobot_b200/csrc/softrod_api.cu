@@ -14,6 +14,7 @@
 
 #include <new>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -46,6 +47,7 @@ struct sr_handle {
   void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr, *head = nullptr;
   double *muscle = nullptr; int muscle_dim = 0;
   double *spline = nullptr, *spline_tab = nullptr; int spline_dim = 0;
+  int *redo = nullptr;   // per-env flags of the fast-only / fallback kernel pair
   int n_rod = 1, init_dim = 9;
   sr::RodArgs<double> a64;
   sr::RodArgs<float> a32;
@@ -193,14 +195,21 @@ bool use_packed_kernel(const sr_handle *h) {
   return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 1024;
 }
 
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false>
+int fastpath_setting() {   // SOFTROD_FASTPATH=0: single safe kernel with warp-vote fallbacks (experiments)
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SOFTROD_FASTPATH"); v = e ? atoi(e) != 0 : 1; }
+  return v;
+}
+
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false,
+          bool FASTONLY = false>
 int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int group = (MULTI ? A.n_rod : 1) * (A.n_elem + 1) + (MULTI ? A.has_head : 0);   // threads per env
   const int rods_per_cta = NT / group;
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
   const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI, TORQUE) * sizeof(T);
-  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE>;
+  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE, FASTONLY>;
   static bool attr_set = false;   // per instantiation
   if (!attr_set) {
     SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -217,9 +226,17 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
   if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
   if (A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
   if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
-  return (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
-             ? launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s)
-             : launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
+  if (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
+    return launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s);
+  if constexpr (std::is_same<T, double>::value) {
+    if (fastpath_setting() && A.redo) {
+      // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
+      int rc = launch_packed_impl<T, NT, MINB, false, false, false, false, false, true>(h, A, s);
+      if (rc != SR_OK) return rc;
+      A.redo_filter = 1;
+    }
+  }
+  return launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
 }
 
 // CTA size of the packed kernel.  Registers cap the SM at 512 resident threads (128 regs), so the
@@ -373,6 +390,8 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       (e = cudaMallocHost(&h->h_term, n_env)) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_init, n_env * h->init_dim * sizeof(double))) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaMalloc(&h->redo, n_env * sizeof(int))) != cudaSuccess ||
+      (e = cudaMemset(h->redo, 0, n_env * sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->state, 0, state_bytes)) != cudaSuccess) {
     std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
     sr_destroy(h);
@@ -403,6 +422,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   }
   fill_args<double>(*cfg, h->stride, h->a64);
   h->a64.spline = h->spline; h->a64.spline_tab = h->spline_tab;
+  h->a64.redo = h->redo;
   h->a64.muscle = h->muscle;
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
@@ -418,7 +438,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);

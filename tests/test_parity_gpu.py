@@ -771,3 +771,43 @@ def test_muscle_torques_without_friction_are_roundoff_limited(golden_dir, case):
             assert err < tol, f"case {case} segment {seg} field {gk}: abs err {err:.3e} > {tol:.3e} (|ref| {np.abs(ref).max():.3e})"
     assert float(mu[0, 0]) == float(g[f"{case}/time"])
     h.close()
+
+
+def test_fast_only_kernel_falls_back_per_env():
+    """The default path is a fast-only kernel (no warp-vote fallbacks in the substep body) followed by the
+    safe kernel over the envs the first one flagged.  Here two of six free rods spin so fast that the half-step
+    rotation leaves the polynomial range (|h w| = 1 rad per half step: q = 1 > 0.25), so they must be
+    re-run by the fallback with libm-class accuracy while the others stay on the fast path; every env is
+    compared with the oracle, twice in a row (the flags must have been cleared).  Only 20 substeps in all: a rod
+    spinning at 2e4 rad/s amplifies round-off exponentially (7e-9 after 20 substeps, O(1) after 50, in the safe
+    single-kernel path exactly as in this one — their results are bit-identical)."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    n_env, n, dt, radius = 6, 30, 1e-4, 0.05
+    init = _tilted_init(n_env)
+    kw = dict(density=1000.0, youngs_modulus=1e6)
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, base_length=1.0, base_radius=radius,
+                   gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3, bc_kind=nat.BC_FREE, **kw)
+    h.reset_host(init)
+    rods = [ro.OracleRod(n, init[i, 0:3], init[i, 3:6], init[i, 6:9], 1.0, radius, 1000.0, 1e6, dt,
+                         gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3) for i in range(n_env)]
+    spin = np.zeros((n_env, 3, n))
+    spin[1, 2, :] = 2.0e4                     # rigid spin about the rod axis (d3): no strain, huge rotation per substep
+    spin[4, 2, :] = -2.0e4
+    h.fields()["omega_collection"][:] = torch.as_tensor(spin, device="cuda")
+    for i, r in enumerate(rods):
+        r.omega_collection[:] = spin[i]
+    for chunk in (8, 12):
+        obs, rew, term = h.step_host(None, chunk)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        for i, r in enumerate(rods):
+            r.substeps(chunk)
+            floors = rate_floors(1e6, 1000.0, 1.0, n, radius, np.abs(r.position_collection).max())
+            for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+                ref = getattr(r, name)
+                err = float(np.abs(f[name][i] - ref).max())
+                assert err <= 1e-9 * np.abs(ref).max() + floors[name], f"env {i} {name}: abs err {err:.3e}"
+        assert term.sum() == 0
+    assert h.launch_count >= 1 + 2 * 2        # reset + (fast-only, fallback) per step
+    h.close()
