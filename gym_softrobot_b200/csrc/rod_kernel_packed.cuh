@@ -220,8 +220,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (moving) { x[0] = pin_x; x[1] = pin_y; }
     T q = fma(a2, a2, fma(a1, a1, a0 * a0));
     if (FASTONLY) {
-      dom_bad = dom_bad || (q > T(kSmallRotQ));
-      rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
+      dom_bad = dom_bad || (q > T(kNarrowRotQ));
+      rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
     } else if (!__any_sync(FULL, !(q <= T(kSmallRotQ)))) rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
     else rotate_directors_ref<T>(a0, a1, a2, Q);
     hh_prev = hh;
@@ -402,11 +402,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     constexpr bool F64 = sizeof(T) == 8;
     if (!F64) u = fmax(u, T(0));                  // FP32: the guard is below epsilon; keep u >= 0
     T fac;
-    if (FASTONLY) dom_bad = dom_bad || (u > T(kSmallBendU));
+    if (FASTONLY) dom_bad = dom_bad || (u > T(kNarrowBendU));
     if (FASTONLY || !__any_sync(FULL, !(u <= T(kSmallBendU)))) {
       if (F64) {
         T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
-        fac = theta_over_sin(A.poly, u) * fma(T(0.5e-14), cot, T(-0.5));
+        fac = (FASTONLY ? theta_over_sin_narrow(A.poly, u) : theta_over_sin(A.poly, u)) * fma(T(0.5e-14), cot, T(-0.5));
       } else {
         fac = T(-0.5) * theta_over_sin(A.poly, u);   // the 1e-14 cot(theta) term is < 1e-9: invisible in FP32
       }
@@ -451,11 +451,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
       bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
                  !(fabs_(z2) <= T(kSmallExpZ));
-      if (FASTONLY) dom_bad = dom_bad || (fabs_(z0) > T(kSmallExpZ)) || (fabs_(z1) > T(kSmallExpZ)) || (fabs_(z2) > T(kSmallExpZ));
+      if (FASTONLY) dom_bad = dom_bad || (fabs_(z0) > T(kNarrowExpZ)) || (fabs_(z1) > T(kNarrowExpZ)) || (fabs_(z2) > T(kNarrowExpZ));
       if (FASTONLY || !__any_sync(FULL, big)) {
-        cw0 = A.c_w[0] * exp_small(A.poly, z0);
-        cw2 = A.c_w[2] * exp_small(A.poly, z2);
-        cw1 = A.isotropic ? cw0 : A.c_w[1] * exp_small(A.poly, z1);
+        cw0 = A.c_w[0] * (FASTONLY ? exp_narrow(A.poly, z0) : exp_small(A.poly, z0));
+        cw2 = A.c_w[2] * (FASTONLY ? exp_narrow(A.poly, z2) : exp_small(A.poly, z2));
+        cw1 = A.isotropic ? cw0 : A.c_w[1] * (FASTONLY ? exp_narrow(A.poly, z1) : exp_small(A.poly, z1));
       } else {
         cw0 = exp_ref<T>(e * A.logc_w[0]);
         cw1 = exp_ref<T>(e * A.logc_w[1]);

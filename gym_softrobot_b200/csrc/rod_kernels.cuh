@@ -176,11 +176,12 @@ template <typename T> __device__ __forceinline__ void rotate_directors_ref(T a0,
 // rho = 1 - eps/sqrt(q + eps^2)  (-> 0 as |a| -> 0, like the reference).  Measured: dropping this
 // guard moves the velocity error after 2400 substeps from 2e-11 to 5e-10 (it is a systematic 2e-10
 // relative slow-down of every rotation), for a 1 % speed-up — it stays.
-template <typename T>
+template <typename T, bool NARROW = false>
 __device__ __forceinline__ void rotate_directors_fast(const PolyCoef<T> &C, T a0, T a1, T a2, T q, T eps,
                                                       T (&Q)[9]) {
   T A, B;
-  sinc_cosc(C, q, A, B);
+  if (NARROW) sinc_cosc_narrow(C, q, A, B);
+  else sinc_cosc(C, q, A, B);
   if (sizeof(T) == 8) {   // a 1e-14 rad shortening is far below FP32 resolution
     T rho = fma(-eps, rsqrt_approx(fma(eps, eps, q)), T(1.0));
     A *= rho;

@@ -111,8 +111,20 @@ constexpr double kSmallBendU = 0.25;
                      0.008333363095284598}
 constexpr double kSmallExpZ = 1.0e-2;
 
+// Narrow-domain versions for the fast-only kernel (rod_kernel_packed.cuh, FASTONLY): an env whose arguments
+// leave these ranges is re-run by the safe kernel with the wide maps above, so the common case can use
+// lower degrees: q <= 0.01 (0.1 rad per kinematic update), u <= 0.04 (23 degrees between neighbouring
+// elements), |z| <= 2.5e-4.  Same fitting procedure, <= 1 ulp on the stated range.
+#define SR_COEF_SINC3 {0.9999999999999998, -0.16666666666597785, 0.008333332988923206, -0.00019835759066305837}
+#define SR_COEF_COSC3 {0.5, -0.04166666666659778, 0.0013888888544469368, -2.4796076411816044e-05}
+#define SR_COEF_BEND7 {0.9999999999999999, 0.6666666666668902, 0.5333333332161609, 0.4571428805086313, \
+                       0.4063469227387624, 0.3695291784110767, 0.33747354927661083, 0.3708210729102131}
+#define SR_COEF_EXP3 {1.0, 1.0, 0.5000000026041667, 0.1666666671875}
+constexpr double kNarrowRotQ = 0.01, kNarrowBendU = 0.04, kNarrowExpZ = 2.5e-4;
+
 template <typename T> struct PolyCoef {
   T sinc[6], cosc[6], bend[14], expz[6];
+  T sinc3[4], cosc3[4], bend7[8], exp3[4];
 };
 
 template <typename T> __device__ __forceinline__ void sinc_cosc(const PolyCoef<T> &C, T q, T &A, T &B) {
@@ -144,6 +156,28 @@ template <typename T> __device__ __forceinline__ T exp_small(const PolyCoef<T> &
   p = fma(p, z, C.expz[2]);
   p = fma(p, z, C.expz[1]);
   return fma(p, z, C.expz[0]);
+}
+
+template <typename T> __device__ __forceinline__ void sinc_cosc_narrow(const PolyCoef<T> &C, T q, T &A, T &B) {
+  T a = fma(C.sinc3[3], q, C.sinc3[2]);
+  T b = fma(C.cosc3[3], q, C.cosc3[2]);
+  a = fma(a, q, C.sinc3[1]); b = fma(b, q, C.cosc3[1]);
+  A = fma(a, q, C.sinc3[0]); B = fma(b, q, C.cosc3[0]);
+}
+
+template <typename T> __device__ __forceinline__ T theta_over_sin_narrow(const PolyCoef<T> &C, T u) {
+  const T *c = C.bend7;
+  T u2 = u * u;
+  T p0 = fma(c[1], u, c[0]), p1 = fma(c[3], u, c[2]), p2 = fma(c[5], u, c[4]), p3 = fma(c[7], u, c[6]);
+  T u4 = u2 * u2;
+  T q0 = fma(p1, u2, p0), q1 = fma(p3, u2, p2);
+  return fma(q1, u4, q0);
+}
+
+template <typename T> __device__ __forceinline__ T exp_narrow(const PolyCoef<T> &C, T z) {
+  T p = fma(C.exp3[3], z, C.exp3[2]);
+  p = fma(p, z, C.exp3[1]);
+  return fma(p, z, C.exp3[0]);
 }
 
 }  // namespace sr

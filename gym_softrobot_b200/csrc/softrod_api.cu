@@ -139,6 +139,9 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     const double cs[] = SR_COEF_SINC, cc[] = SR_COEF_COSC, cb[] = SR_COEF_BEND, ce[] = SR_COEF_EXP;
     for (int i = 0; i < 6; i++) { A.poly.sinc[i] = (T)cs[i]; A.poly.cosc[i] = (T)cc[i]; A.poly.expz[i] = (T)ce[i]; }
     for (int i = 0; i < 14; i++) A.poly.bend[i] = (T)cb[i];
+    const double ns[] = SR_COEF_SINC3, nc[] = SR_COEF_COSC3, nb[] = SR_COEF_BEND7, ne[] = SR_COEF_EXP3;
+    for (int i = 0; i < 4; i++) { A.poly.sinc3[i] = (T)ns[i]; A.poly.cosc3[i] = (T)nc[i]; A.poly.exp3[i] = (T)ne[i]; }
+    for (int i = 0; i < 8; i++) A.poly.bend7[i] = (T)nb[i];
   }
   if (c.damping_constant >= 0.0) {
     // element mass incl. the end-element correction equals `mass` for a uniform rod
