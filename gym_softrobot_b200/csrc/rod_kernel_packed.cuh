@@ -181,10 +181,17 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
           T nx = px + (T)__fmul_rn(A.base_step_f32, act_f0), ny = py + (T)__fmul_rn(A.base_step_f32, act_f1);
           nx = fmin(fmax(nx, -A.base_limit), A.base_limit);
           ny = fmin(fmax(ny, -A.base_limit), A.base_limit);
-          aux[3] = (nx - px) * A.inv_move_period; aux[4] = (ny - py) * A.inv_move_period; aux[5] = T(0);
-          aux[0] = nx; aux[1] = ny;
+          const T nvx = (nx - px) * A.inv_move_period, nvy = (ny - py) * A.inv_move_period;
+          if (FASTONLY) {   // keep global memory at the pre-launch state until the epilogue knows the env is not re-run
+            pin_x = nx; pin_y = ny; base_vx = nvx; base_vy = nvy;
+          } else {
+            aux[3] = nvx; aux[4] = nvy; aux[5] = T(0);
+            aux[0] = nx; aux[1] = ny;
+          }
         }
-        pin_x = aux[0]; pin_y = aux[1]; base_vx = aux[3]; base_vy = aux[4];
+        if (!(FASTONLY && A.model == MODEL_SOFT_PENDULUM_3D && A.n_substeps > 0)) {
+          pin_x = aux[0]; pin_y = aux[1]; base_vx = aux[3]; base_vy = aux[4];
+        }
         x[0] = pin_x; x[1] = pin_y; x[2] = bc[2];
         if (EDGE) {   // the base jumped: element 0's edge is re-derived from the stored node 1
 #pragma unroll
@@ -195,7 +202,16 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   }
   const bool moving = MOVING && bc_thread && A.bc_kind == BC_MOVING_BASE;
 
+  // branch-free form for the fast-only kernels: which rate components the BC thread zeroes, decided once
+  const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
+  const bool pin_fixed = bc_thread && A.bc_kind != BC_PENDULUM_SLIDER && (!MOVING || A.bc_kind == BC_ONE_END_FIXED);
   auto constrain_rates = [&]() {
+    if (FASTONLY && !MOVING) {
+      const bool z12 = pin_slider || pin_fixed;   // v_y, v_z, w_x, w_z are pinned by both; v_x, w_y by the clamp only
+      v[0] = pin_fixed ? T(0) : v[0]; v[1] = z12 ? T(0) : v[1]; v[2] = z12 ? T(0) : v[2];
+      w[0] = z12 ? T(0) : w[0]; w[1] = pin_fixed ? T(0) : w[1]; w[2] = z12 ? T(0) : w[2];
+      return;
+    }
     if (bc_thread) {
       if (A.bc_kind == BC_PENDULUM_SLIDER) {
         v[1] = T(0); v[2] = T(0); w[0] = T(0); w[2] = T(0);
@@ -405,7 +421,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (FASTONLY) dom_bad = dom_bad || (u > T(kNarrowBendU));
     if (FASTONLY || !__any_sync(FULL, !(u <= T(kSmallBendU)))) {
       if (F64) {
-        T cot = fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
+        // cot(theta) = (1 - 2u) / (2 sqrt(u (1 - u))); it only scales the 1e-14 guard term, so on the narrow range
+        // its expansion rsqrt(4u) (1 - 1.5 u) (relative error < 0.63 u^2 <= 1e-3) is more than enough
+        T cot = FASTONLY ? rsqrt_approx(T(4.0) * u) * fma(T(-1.5), u, T(1.0))
+                         : fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
         fac = (FASTONLY ? theta_over_sin_narrow(A.poly, u) : theta_over_sin(A.poly, u)) * fma(T(0.5e-14), cot, T(-0.5));
       } else {
         fac = T(-0.5) * theta_over_sin(A.poly, u);   // the 1e-14 cot(theta) term is < 1e-9: invisible in FP32
@@ -446,16 +465,19 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     // rotational damper coefficients c_w^e = c_w exp((e-1) ln c_w): only need e, so they are
     // evaluated here, ahead of the barrier, off the critical path of the dynamic step
     T cw0 = T(1), cw1 = T(1), cw2 = T(1);
-    if (A.damping_on) {
+    if (FASTONLY || A.damping_on) {   // damper off = identity constants (c_w = 1, ln c_w = 0): no branch needed
       T em1 = e - T(1);
       T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
       bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
                  !(fabs_(z2) <= T(kSmallExpZ));
-      if (FASTONLY) dom_bad = dom_bad || (fabs_(z0) > T(kNarrowExpZ)) || (fabs_(z1) > T(kNarrowExpZ)) || (fabs_(z2) > T(kNarrowExpZ));
+      // the contact models damp harder and stretch more (z up to ~1e-3): they keep the wide exp map
+      constexpr bool NARROW_EXP = FASTONLY && !CONTACT && !LAPLACE;
+      constexpr double kz = NARROW_EXP ? kNarrowExpZ : kSmallExpZ;
+      if (FASTONLY) dom_bad = dom_bad || (fabs_(z0) > T(kz)) || (fabs_(z1) > T(kz)) || (fabs_(z2) > T(kz));
       if (FASTONLY || !__any_sync(FULL, big)) {
-        cw0 = A.c_w[0] * (FASTONLY ? exp_narrow(A.poly, z0) : exp_small(A.poly, z0));
-        cw2 = A.c_w[2] * (FASTONLY ? exp_narrow(A.poly, z2) : exp_small(A.poly, z2));
-        cw1 = A.isotropic ? cw0 : A.c_w[1] * (FASTONLY ? exp_narrow(A.poly, z1) : exp_small(A.poly, z1));
+        cw0 = A.c_w[0] * (NARROW_EXP ? exp_narrow(A.poly, z0) : exp_small(A.poly, z0));
+        cw2 = A.c_w[2] * (NARROW_EXP ? exp_narrow(A.poly, z2) : exp_small(A.poly, z2));
+        cw1 = A.isotropic ? cw0 : A.c_w[1] * (NARROW_EXP ? exp_narrow(A.poly, z1) : exp_small(A.poly, z1));
       } else {
         cw0 = exp_ref<T>(e * A.logc_w[0]);
         cw1 = exp_ref<T>(e * A.logc_w[1]);
@@ -654,7 +676,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 
     // ---- rate constraints and dissipation ------------------------------------------------
     auto dampen = [&]() {
-      if (A.damping_on) { w[0] *= cw0; w[1] *= cw1; w[2] *= cw2; }
+      if (FASTONLY || A.damping_on) { w[0] *= cw0; w[1] *= cw1; w[2] *= cw2; }
       if (LAPLACE && A.laplace_order > 0) {
         // LaplaceDissipationFilter (elastica/dissipation.py:nb_filter_rate): p passes of
         // f <- (-f[k+1] - f[k-1] + 2 f[k]) / 4 on interior nodes / elements, ends held at 0; rate -= f.
@@ -693,7 +715,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       }
     };
     if (!(MULTI && is_head)) {
-      if (A.damp_first) { dampen(); constrain_rates(); }
+      // BCs that only zero components commute with the (multiplicative / interior-only) dampers: no order branch
+      if ((FASTONLY && !MOVING) || A.damp_first) { dampen(); constrain_rates(); }
       else { constrain_rates(); dampen(); }
     }
 
@@ -772,6 +795,9 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       const double x0[3] = {(double)x[0], (double)x[1], (double)x[2]};
       const double v0[3] = {(double)v[0], (double)v[1], (double)v[2]};
       T *aux = A.aux + (size_t)env * AUX_DIM;
+      if (FASTONLY && A.n_substeps > 0) {   // the base controller's state, deferred from the prologue
+        aux[0] = pin_x; aux[1] = pin_y; aux[3] = base_vx; aux[4] = base_vy; aux[5] = T(0);
+      }
       soft_pendulum_3d_outputs<T>(sh_x + tid, RS, n, x0, v0, act_f0, act_f1, (double)aux[0], (double)aux[1],
                                   invalid, A.obs + (size_t)env * A.obs_dim, A.reward + env,
                                   A.terminated + env, aux + 6);

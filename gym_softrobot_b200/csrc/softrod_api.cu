@@ -228,9 +228,26 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
   if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
   if (A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
-  if (A.contact_on || A.rest_kappa) return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
-  if (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE)
+  if (A.contact_on || A.rest_kappa) {
+    if constexpr (std::is_same<T, double>::value) {
+      if (fastpath_setting() && A.redo) {
+        int rc = launch_packed_impl<T, NT, MINB, false, false, true, false, false, true>(h, A, s);
+        if (rc != SR_OK) return rc;
+        A.redo_filter = 1;
+      }
+    }
+    return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
+  }
+  if (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE) {
+    if constexpr (std::is_same<T, double>::value) {
+      if (fastpath_setting() && A.redo) {
+        int rc = launch_packed_impl<T, NT, MINB, true, true, false, false, false, true>(h, A, s);
+        if (rc != SR_OK) return rc;
+        A.redo_filter = 1;
+      }
+    }
     return launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s);
+  }
   if constexpr (std::is_same<T, double>::value) {
     if (fastpath_setting() && A.redo) {
       // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
