@@ -748,7 +748,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (live && dom_bad) atomicOr(&sh_dom[r], 1);
     __syncthreads();
     redo = live && sh_dom[r] != 0;
-    if (redo && active && first && arm == 0) A.redo[env] = 1;
+    if (redo && active && first && arm == 0) {
+      A.redo[env] = 1;
+      if (A.redo_count) atomicAdd(A.redo_count, 1ULL);
+    }
   }
   bool bad = false;
   if (MULTI && hd && !redo) {

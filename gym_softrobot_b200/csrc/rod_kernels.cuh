@@ -77,6 +77,7 @@ template <typename T> struct RodArgs {
   // fast-only / fallback pair of the packed kernel: envs that leave the fast-math domain are flagged in
   // redo[] by the fast-only kernel (which leaves their state untouched) and re-run by the safe kernel
   int *redo; int redo_filter;   // redo_filter: this (safe) launch steps flagged envs only and clears the flag
+  unsigned long long *redo_count;   // running number of env-steps handed to the fallback (adaptive switch)
   // MuscleTorques travelling wave (continuum_snake.py:186-198): [n_env][muscle_dim] = time, wave number, beta[n]
   double *muscle; int muscle_on, muscle_dim;
   double mus_omega, mus_ramp, mus_phase; T mus_dir[3];

@@ -48,6 +48,9 @@ struct sr_handle {
   double *muscle = nullptr; int muscle_dim = 0;
   double *spline = nullptr, *spline_tab = nullptr; int spline_dim = 0;
   int *redo = nullptr;   // per-env flags of the fast-only / fallback kernel pair
+  unsigned long long *redo_count = nullptr, *h_redo_count = nullptr, pair_last_count = 0;
+  cudaEvent_t pair_event = nullptr; bool pair_copy_pending = false;
+  long long pair_steps = 0, pair_off_until = 0, pair_steps_at_copy = 0, pair_steps_at_prev_copy = 0;
   int n_rod = 1, init_dim = 9;
   sr::RodArgs<double> a64;
   sr::RodArgs<float> a32;
@@ -224,13 +227,39 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   return SR_OK;
 }
 
+// Whether this step runs the fast-only kernel + fallback pair.  The fast-only kernel counts the envs it hands to
+// the fallback (redo_count); every 32 steps the count is fetched asynchronously, and while more than a quarter of
+// the env-steps of a window needed the fallback (a workload that lives outside the narrow fast-math range would
+// otherwise pay for both kernels every step) the handle uses the single safe kernel, probing again 512 steps later.
+template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  if (!fastpath_setting() || !A.redo) return false;
+  h->pair_steps++;
+  if (h->pair_off_until > h->pair_steps) return false;
+  if (h->pair_copy_pending && cudaEventQuery(h->pair_event) == cudaSuccess) {
+    h->pair_copy_pending = false;
+    const unsigned long long seen = *h->h_redo_count, delta = seen - h->pair_last_count;
+    const long long window = (h->pair_steps_at_copy - h->pair_steps_at_prev_copy) * (long long)A.n_env;
+    h->pair_last_count = seen;
+    h->pair_steps_at_prev_copy = h->pair_steps_at_copy;
+    if (window > 0 && (double)delta > 0.25 * (double)window) { h->pair_off_until = h->pair_steps + 512; return false; }
+  }
+  if (!h->pair_copy_pending && h->pair_steps % 32 == 0) {
+    cudaMemcpyAsync(h->h_redo_count, h->redo_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(h->pair_event, s);
+    h->pair_copy_pending = true;
+    h->pair_steps_at_copy = h->pair_steps;
+  }
+  A.redo_count = h->redo_count;
+  return true;
+}
+
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
   if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
   if (A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
   if (A.contact_on || A.rest_kappa) {
     if constexpr (std::is_same<T, double>::value) {
-      if (fastpath_setting() && A.redo) {
+      if (use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, false, false, true, false, false, true>(h, A, s);
         if (rc != SR_OK) return rc;
         A.redo_filter = 1;
@@ -240,7 +269,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
   }
   if (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE) {
     if constexpr (std::is_same<T, double>::value) {
-      if (fastpath_setting() && A.redo) {
+      if (use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, true, true, false, false, false, true>(h, A, s);
         if (rc != SR_OK) return rc;
         A.redo_filter = 1;
@@ -249,7 +278,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     return launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s);
   }
   if constexpr (std::is_same<T, double>::value) {
-    if (fastpath_setting() && A.redo) {
+    if (use_fast_pair(h, A, s)) {
       // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
       int rc = launch_packed_impl<T, NT, MINB, false, false, false, false, false, true>(h, A, s);
       if (rc != SR_OK) return rc;
@@ -412,6 +441,10 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMalloc(&h->redo, n_env * sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->redo, 0, n_env * sizeof(int))) != cudaSuccess ||
+      (e = cudaMalloc(&h->redo_count, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMemset(h->redo_count, 0, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMallocHost(&h->h_redo_count, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaEventCreateWithFlags(&h->pair_event, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaMemset(h->state, 0, state_bytes)) != cudaSuccess) {
     std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
     sr_destroy(h);
@@ -440,6 +473,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       return fail(SR_E_ALLOC, m);
     }
   }
+  *h->h_redo_count = 0;
   fill_args<double>(*cfg, h->stride, h->a64);
   h->a64.spline = h->spline; h->a64.spline_tab = h->spline_tab;
   h->a64.redo = h->redo;
@@ -458,7 +492,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);

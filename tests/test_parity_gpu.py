@@ -811,3 +811,33 @@ def test_fast_only_kernel_falls_back_per_env():
         assert term.sum() == 0
     assert h.launch_count >= 1 + 2 * 2        # reset + (fast-only, fallback) per step
     h.close()
+
+
+def test_fast_pair_switches_itself_off_when_most_envs_fall_back():
+    """Adaptive switch of the fast-only / fallback pair: a handle whose envs all live outside the narrow fast-math
+    range (here: every rod spins at 3000 rad/s, 0.15 rad per half-step rotation > 0.1) would pay for two
+    kernels per step; after the first asynchronous check of the fallback counter (steps 32-64) it must be down to
+    the single safe kernel.  A well-behaved handle next to it keeps the pair."""
+    import torch
+    nat = _native()
+    n_env, n = 8, 20
+
+    def make(spin):
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=1e-4, base_length=1.0, base_radius=0.05,
+                       density=1000.0, youngs_modulus=1e6, gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3)
+        h.reset_host(_tilted_init(n_env))
+        if spin:
+            h.fields()["omega_collection"][:, 2, :] = 3000.0
+        return h
+
+    for spin, per_step_late in ((True, 1), (False, 2)):
+        h = make(spin)
+        counts = []
+        for _ in range(110):
+            h.step_host(None, 1)
+            counts.append(h.launch_count)
+        assert counts[0] - 1 == 2                                    # reset + (fast-only, fallback)
+        late = np.diff(counts[-10:])
+        assert np.all(late == per_step_late), (spin, late)
+        assert torch.isfinite(h.state_tensor()).all()
+        h.close()
