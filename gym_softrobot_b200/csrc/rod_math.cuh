@@ -120,11 +120,16 @@ constexpr double kSmallExpZ = 1.0e-2;
 #define SR_COEF_BEND7 {0.9999999999999999, 0.6666666666668902, 0.5333333332161609, 0.4571428805086313, \
                        0.4063469227387624, 0.3695291784110767, 0.33747354927661083, 0.3708210729102131}
 #define SR_COEF_EXP3 {1.0, 1.0, 0.5000000026041667, 0.1666666671875}
-constexpr double kNarrowRotQ = 0.01, kNarrowBendU = 0.04, kNarrowExpZ = 2.5e-4;
+// actuated arms on the plane reach 25-30 degrees per element under random actions: their fast-only kernel uses
+// u <= 0.1 (37 degrees), degree 9
+#define SR_COEF_BEND9 {0.9999999999999999, 0.666666666666836, 0.5333333332775754, 0.4571428642472279, \
+                       0.40634874789975095, 0.3694252997188034, 0.34061379942887826, 0.32344955229361544, \
+                       0.2573124543735613, 0.46543435203468897}
+constexpr double kNarrowRotQ = 0.01, kNarrowBendU = 0.04, kMidBendU = 0.1, kNarrowExpZ = 2.5e-4;
 
 template <typename T> struct PolyCoef {
   T sinc[6], cosc[6], bend[14], expz[6];
-  T sinc3[4], cosc3[4], bend7[8], exp3[4];
+  T sinc3[4], cosc3[4], bend7[8], exp3[4], bend9[10];
 };
 
 template <typename T> __device__ __forceinline__ void sinc_cosc(const PolyCoef<T> &C, T q, T &A, T &B) {
@@ -172,6 +177,16 @@ template <typename T> __device__ __forceinline__ T theta_over_sin_narrow(const P
   T u4 = u2 * u2;
   T q0 = fma(p1, u2, p0), q1 = fma(p3, u2, p2);
   return fma(q1, u4, q0);
+}
+
+template <typename T> __device__ __forceinline__ T theta_over_sin_mid(const PolyCoef<T> &C, T u) {
+  const T *c = C.bend9;
+  T u2 = u * u;
+  T p0 = fma(c[1], u, c[0]), p1 = fma(c[3], u, c[2]), p2 = fma(c[5], u, c[4]), p3 = fma(c[7], u, c[6]), p4 = fma(c[9], u, c[8]);
+  T u4 = u2 * u2;
+  T q0 = fma(p1, u2, p0), q1 = fma(p3, u2, p2);
+  T u8 = u4 * u4;
+  return fma(p4, u8, fma(q1, u4, q0));
 }
 
 template <typename T> __device__ __forceinline__ T exp_narrow(const PolyCoef<T> &C, T z) {

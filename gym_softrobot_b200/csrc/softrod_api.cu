@@ -145,6 +145,8 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     const double ns[] = SR_COEF_SINC3, nc[] = SR_COEF_COSC3, nb[] = SR_COEF_BEND7, ne[] = SR_COEF_EXP3;
     for (int i = 0; i < 4; i++) { A.poly.sinc3[i] = (T)ns[i]; A.poly.cosc3[i] = (T)nc[i]; A.poly.exp3[i] = (T)ne[i]; }
     for (int i = 0; i < 8; i++) A.poly.bend7[i] = (T)nb[i];
+    const double nm[] = SR_COEF_BEND9;
+    for (int i = 0; i < 10; i++) A.poly.bend9[i] = (T)nm[i];
   }
   if (c.damping_constant >= 0.0) {
     // element mass incl. the end-element correction equals `mass` for a uniform rod
