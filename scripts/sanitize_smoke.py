@@ -35,4 +35,10 @@ env = g.make_vec("SoftArmTracking-v0", 7, game_mode=2, autoreset=False); env.res
 for _ in range(2):
     env.step(torch.full((7, 8), 0.3, device="cuda", dtype=torch.float64))
 torch.cuda.synchronize(); env.close()
+# fast-only / fallback pair with flagged envs: two of five free rods spin outside the narrow rotation range
+h = nat.Handle(model=nat.MODEL_ROD, n_env=5, n_elem=30, dt=1e-4, base_length=1.0, base_radius=0.05, density=1000.0,
+               youngs_modulus=1e6, gravity=(0, -9.80665, 0), damping_constant=2e-3)
+init = np.zeros((5, 9)); init[:, 3] = 1; init[:, 7] = 1; h.reset_host(init)
+h.fields()["omega_collection"][1, 2, :] = 2.0e4; h.fields()["omega_collection"][3, 2, :] = -2.0e4
+h.step_host(None, K); h.step_host(None, K); h.close()
 print("sanitize_smoke done")
