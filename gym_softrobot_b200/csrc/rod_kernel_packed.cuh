@@ -418,15 +418,17 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     constexpr bool F64 = sizeof(T) == 8;
     if (!F64) u = fmax(u, T(0));                  // FP32: the guard is below epsilon; keep u >= 0
     T fac;
-    constexpr bool MID_BEND = FASTONLY && CONTACT;   // actuated arms bend more per element than free / clamped rods
-    if (FASTONLY) dom_bad = dom_bad || (u > T(MID_BEND ? kMidBendU : kNarrowBendU));
+    // actuated arms bend more per element than free / clamped rods; the 10-element arms of the octopus
+    // assemblies (up to ~45 degrees per element) keep the full-range map
+    constexpr bool MID_BEND = FASTONLY && CONTACT && !MULTI, WIDE_BEND = FASTONLY && MULTI;
+    if (FASTONLY) dom_bad = dom_bad || (u > T(WIDE_BEND ? kSmallBendU : MID_BEND ? kMidBendU : kNarrowBendU));
     if (FASTONLY || !__any_sync(FULL, !(u <= T(kSmallBendU)))) {
       if (F64) {
         // cot(theta) = (1 - 2u) / (2 sqrt(u (1 - u))); it only scales the 1e-14 guard term, so on the narrow range
         // its expansion rsqrt(4u) (1 - 1.5 u) (relative error < 0.63 u^2 <= 1e-3) is more than enough
-        T cot = FASTONLY ? rsqrt_approx(T(4.0) * u) * fma(T(-1.5), u, T(1.0))
+        T cot = (FASTONLY && !WIDE_BEND) ? rsqrt_approx(T(4.0) * u) * fma(T(-1.5), u, T(1.0))
                          : fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
-        fac = (MID_BEND ? theta_over_sin_mid(A.poly, u) : FASTONLY ? theta_over_sin_narrow(A.poly, u) : theta_over_sin(A.poly, u)) *
+        fac = (MID_BEND ? theta_over_sin_mid(A.poly, u) : (FASTONLY && !WIDE_BEND) ? theta_over_sin_narrow(A.poly, u) : theta_over_sin(A.poly, u)) *
               fma(T(0.5e-14), cot, T(-0.5));
       } else {
         fac = T(-0.5) * theta_over_sin(A.poly, u);   // the 1e-14 cot(theta) term is < 1e-9: invisible in FP32

@@ -257,7 +257,16 @@ template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaSt
 
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
-  if (A.n_rod > 1 || A.has_head) return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
+  if (A.n_rod > 1 || A.has_head) {
+    if constexpr (std::is_same<T, double>::value) {
+      if (use_fast_pair(h, A, s)) {
+        int rc = launch_packed_impl<T, NT, MINB, false, false, true, true, false, true>(h, A, s);
+        if (rc != SR_OK) return rc;
+        A.redo_filter = 1;
+      }
+    }
+    return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
+  }
   if (A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
   if (A.contact_on || A.rest_kappa) {
     if constexpr (std::is_same<T, double>::value) {
