@@ -776,7 +776,8 @@ def test_muscle_torques_without_friction_are_roundoff_limited(golden_dir, case):
 def test_fast_only_kernel_falls_back_per_env():
     """The default path is a fast-only kernel (no warp-vote fallbacks in the substep body) followed by the
     safe kernel over the envs the first one flagged.  Here two of six free rods spin so fast that the half-step
-    rotation leaves the polynomial range (|h w| = 1 rad per half step: q = 1 > 0.25), so they must be
+    rotation leaves the polynomial range (|h w| = 1 rad per half step: q = 1 > 0.25) and a third carries a
+    30 degree kink between two elements (outside the narrow bend map), so they must be
     re-run by the fallback with libm-class accuracy while the others stay on the fast path; every env is
     compared with the oracle, twice in a row (the flags must have been cleared).  Only 20 substeps in all: a rod
     spinning at 2e4 rad/s amplifies round-off exponentially (7e-9 after 20 substeps, O(1) after 50, in the safe
@@ -798,6 +799,14 @@ def test_fast_only_kernel_falls_back_per_env():
     h.fields()["omega_collection"][:] = torch.as_tensor(spin, device="cuda")
     for i, r in enumerate(rods):
         r.omega_collection[:] = spin[i]
+    # env 2: a 30 degree kink between elements 14 and 15 (u = sin^2(15 deg) = 0.067 > 0.04): the bend map's range
+    kink = np.deg2rad(30.0)
+    Rk = np.array([[np.cos(kink), np.sin(kink), 0.0], [-np.sin(kink), np.cos(kink), 0.0], [0.0, 0.0, 1.0]])
+    Q2 = rods[2].director_collection.copy()
+    for k in range(15, n):
+        Q2[:, :, k] = Rk @ Q2[:, :, k]           # rotate the frames of the outer half about d3
+    rods[2].director_collection[:] = Q2
+    h.fields()["director_collection"][2] = torch.as_tensor(Q2, device="cuda")
     for chunk in (8, 12):
         obs, rew, term = h.step_host(None, chunk)
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
