@@ -22,7 +22,7 @@ constexpr int PACKED_MAX_THREADS = 1024;
 // shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide (+ 6 joint-reaction rows for
 // assemblies, + 1 element-length row for the spline-torque forcing of the contact / forcing variant)
 constexpr int packed_smem_words(int nt, bool multi, bool torque = false) {
-  return (multi ? 27 : (torque ? 22 : 21)) * (nt + 2);
+  return (multi ? 27 : 24) * (nt + 2);
 }
 
 // LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
@@ -71,7 +71,14 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   const int t_next = (active && j < n) ? tid + 1 : tid;
   const int t_next2 = (active && j < n - 1) ? tid + 2 : t_next;
   const int t_prev = (active && j > 0) ? tid - 1 : NT;   // NT = the zero slot
-  if (tid < 6) sh_s[(tid % 3) * RS + NT + (tid / 3) * (3 * RS)] = T(0);  // zero slots of s and N
+  // Lean FP64 kernels exchange through array-of-structures records instead of the rows above, so that neighbour
+  // data moves with 128-bit accesses (24 LDS/STS per substep instead of 45): per thread 18 doubles
+  // {x0 x1 | x2 v0 | v1 v2 | Q0 Q1 | Q2 Q3 | Q4 Q5 | Q6 Q7 | Q8 - | - -} (stride 144 B: conflict-free for LDS.128)
+  // followed by 6-double records {s0 s1 | s2 N0 | N1 N2} (stride 48 B).  Record NT of the second array is the zero slot.
+  constexpr bool AOS = sizeof(T) == 8 && !LAPLACE && !CONTACT && !MULTI;
+  T *rec = sh, *sn = sh + 18 * RS;
+  if (AOS) { if (tid < 6) sn[6 * NT + tid] = T(0); }
+  else if (tid < 6) sh_s[(tid % 3) * RS + NT + (tid / 3) * (3 * RS)] = T(0);  // zero slots of s and N
 
   T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
   T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
@@ -277,15 +284,39 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
     // ---- publish what the neighbours need ------------------------------------------
 #pragma unroll
-    for (int c = 0; c < 3; c++) { sh_x[c * RS + tid] = EDGE ? ed[c] : x[c]; sh_v[c * RS + tid] = v[c]; }
+    for (int c = 0; c < 3; c++) {
+      if (!AOS) { sh_x[c * RS + tid] = EDGE ? ed[c] : x[c]; sh_v[c * RS + tid] = v[c]; }
+    }
+    if (AOS) {
+      double2 *o = reinterpret_cast<double2 *>(rec + 18 * tid);
+      o[0] = make_double2(x[0], x[1]); o[1] = make_double2(x[2], v[0]); o[2] = make_double2(v[1], v[2]);
+      o[3] = make_double2(Q[0], Q[1]); o[4] = make_double2(Q[2], Q[3]); o[5] = make_double2(Q[4], Q[5]);
+      o[6] = make_double2(Q[6], Q[7]); rec[18 * tid + 14] = Q[8];
+    }
 #pragma unroll
-    for (int c = 0; c < 9; c++) sh_Q[c * RS + tid] = Q[c];
+    for (int c = 0; c < 9; c++) if (!AOS) sh_Q[c * RS + tid] = Q[c];
     __syncthreads();
 
     // ---- geometry, shear/stretch strain, internal force ------------------------------
     T dx[3], dv[3], dx2[3];
+    T nb_x[3], nb_v[3], nb_x2[3], nb_Q[9];   // AOS: the neighbour's record, fetched with 128-bit loads
+    if (AOS) {
+      const double2 *q = reinterpret_cast<const double2 *>(rec + 18 * t_next);
+      const double2 a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3], a4 = q[4], a5 = q[5], a6 = q[6];
+      nb_x[0] = a0.x; nb_x[1] = a0.y; nb_x[2] = a1.x; nb_v[0] = a1.y; nb_v[1] = a2.x; nb_v[2] = a2.y;
+      nb_Q[0] = a3.x; nb_Q[1] = a3.y; nb_Q[2] = a4.x; nb_Q[3] = a4.y; nb_Q[4] = a5.x; nb_Q[5] = a5.y;
+      nb_Q[6] = a6.x; nb_Q[7] = a6.y; nb_Q[8] = rec[18 * t_next + 14];
+      const double2 b0 = *reinterpret_cast<const double2 *>(rec + 18 * t_next2);
+      nb_x2[0] = b0.x; nb_x2[1] = b0.y; nb_x2[2] = rec[18 * t_next2 + 2];
+    }
 #pragma unroll
     for (int c = 0; c < 3; c++) {
+      if (AOS) {
+        dv[c] = nb_v[c] - v[c];
+        dx[c] = nb_x[c] - x[c];
+        dx2[c] = nb_x2[c] - nb_x[c];
+        continue;
+      }
       T vn = sh_v[c * RS + t_next];
       dv[c] = vn - v[c];
       if (EDGE) {
@@ -357,7 +388,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       sfl[i] *= inv_e_s;
-      sh_s[i * RS + tid] = sfl[i];
+      if (!AOS) sh_s[i * RS + tid] = sfl[i];
     }
 
     if (MULTI && active && first && has_head) {
@@ -397,7 +428,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     {
       T Qn[9];
 #pragma unroll
-      for (int c = 0; c < 9; c++) Qn[c] = sh_Q[c * RS + t_next];
+      for (int c = 0; c < 9; c++) Qn[c] = AOS ? nb_Q[c] : sh_Q[c * RS + t_next];
       auto rm = [&](int a, int b) {
         return fma(Qn[3 * a + 2], Q[3 * b + 2], fma(Qn[3 * a + 1], Q[3 * b + 1], Qn[3 * a] * Q[3 * b]));
       };
@@ -463,8 +494,14 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int i = 0; i < 3; i++) {
       T m = tau[i] * ie3;
       T Pi = fma(kxt[i], hc, m);                 // m_j + c_j/2  (own element)
-      sh_N[i * RS + tid] = fma(kxt[i], hc, -m);  // c_j/2 - m_j  (element j+1)
+      const T Nout = fma(kxt[i], hc, -m);        // c_j/2 - m_j  (element j+1)
+      if (AOS) nb_x2[i] = Nout;                  // (reused as staging for the 128-bit store below)
+      else sh_N[i * RS + tid] = Nout;
       tql[i] = fma(fma(pw[i], ede, Gc[i]), inv_e, Pi);
+    }
+    if (AOS) {   // {s0 s1 | s2 N0 | N1 N2}
+      double2 *o = reinterpret_cast<double2 *>(sn + 6 * tid);
+      o[0] = make_double2(sfl[0], sfl[1]); o[1] = make_double2(sfl[2], nb_x2[0]); o[2] = make_double2(nb_x2[1], nb_x2[2]);
     }
     // rotational damper coefficients c_w^e = c_w exp((e-1) ln c_w): only need e, so they are
     // evaluated here, ahead of the barrier, off the critical path of the dynamic step
@@ -507,8 +544,16 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T fint[3], tq[3];
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      fint[i] = sfl[i] - sh_s[i * RS + t_prev];
-      tq[i] = tql[i] + sh_N[i * RS + t_prev];
+      if (!AOS) {
+        fint[i] = sfl[i] - sh_s[i * RS + t_prev];
+        tq[i] = tql[i] + sh_N[i * RS + t_prev];
+      }
+    }
+    if (AOS) {
+      const double2 *q = reinterpret_cast<const double2 *>(sn + 6 * t_prev);
+      const double2 a0 = q[0], a1 = q[1], a2 = q[2];
+      fint[0] = sfl[0] - a0.x; fint[1] = sfl[1] - a0.y; fint[2] = sfl[2] - a1.x;
+      tq[0] = tql[0] + a1.y; tq[1] = tql[1] + a2.x; tq[2] = tql[2] + a2.y;
     }
     if (spl) {
       const int need = live ? sh_need[r] : 0;
