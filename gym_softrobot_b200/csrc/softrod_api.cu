@@ -229,10 +229,11 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   return SR_OK;
 }
 
-// Whether this step runs the fast-only kernel + fallback pair.  The fast-only kernel counts the envs it hands to
-// the fallback (redo_count); every 32 steps the count is fetched asynchronously, and while more than a quarter of
-// the env-steps of a window needed the fallback (a workload that lives outside the narrow fast-math range would
-// otherwise pay for both kernels every step) the handle uses the single safe kernel, probing again 512 steps later.
+// Whether this step runs the fast-only kernel + fallback pair.  One flagged env re-runs its whole CTA (4-5 envs)
+// in the fallback, so the pair only pays while about 1 % of the envs or fewer leave the fast-math range (a pair
+// gains 5-10 %).  The fast-only kernel counts the env-steps it hands over (redo_count); every 8 steps the count is
+// fetched asynchronously, and when more than 1 % of a window's env-steps fell back (violently actuated arms do)
+// the handle uses the single safe kernel for the next 512 steps, then probes again.
 template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (!fastpath_setting() || !A.redo) return false;
   h->pair_steps++;
@@ -243,9 +244,9 @@ template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaSt
     const long long window = (h->pair_steps_at_copy - h->pair_steps_at_prev_copy) * (long long)A.n_env;
     h->pair_last_count = seen;
     h->pair_steps_at_prev_copy = h->pair_steps_at_copy;
-    if (window > 0 && (double)delta > 0.25 * (double)window) { h->pair_off_until = h->pair_steps + 512; return false; }
+    if (window > 0 && (double)delta > 0.01 * (double)window) { h->pair_off_until = h->pair_steps + 512; return false; }
   }
-  if (!h->pair_copy_pending && h->pair_steps % 32 == 0) {
+  if (!h->pair_copy_pending && h->pair_steps % 8 == 0) {
     cudaMemcpyAsync(h->h_redo_count, h->redo_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
     cudaEventRecord(h->pair_event, s);
     h->pair_copy_pending = true;

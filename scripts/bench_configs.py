@@ -98,7 +98,7 @@ acts = torch.rand((n_env, 8), device="cuda", dtype=torch.float64) * 2 - 1
 report("SoftArmTracking-v0 (whole env.step incl. host layer)", n_env, 40, 50, timed(lambda: env.step(acts), K=10), 440 + 20)
 env.close()
 # end to end through the public vector-env API: host (pinned) actions -> device, step(), observations + rewards -> host
-def e2e(name, env_id, n_env, act_shape, lo, hi, K, dtype=torch.float32, **kw):
+def e2e(name, env_id, n_env, act_shape, lo, hi, K, dtype=torch.float32, W=18, **kw):   # W: past the adaptive switch's first checks
     env = g.make_vec(env_id, n_env, **kw)
     env.reset(seed=1)
     host_a = ((torch.rand((n_env,) + act_shape, dtype=dtype) * (hi - lo) + lo) if np.isscalar(lo) else
@@ -107,7 +107,7 @@ def e2e(name, env_id, n_env, act_shape, lo, hi, K, dtype=torch.float32, **kw):
         obs, rew, term, trunc, info = env.step(host_a.to("cuda", non_blocking=True))
         o = obs["individual"] if isinstance(obs, dict) else obs
         return o.cpu(), rew.cpu()
-    sec = timed(step, K=K, W=2)
+    sec = timed(step, K=K, W=W)
     rows.append(dict(config=name + " e2e (vector-env step, host in/out)", n_env=n_env, ms_per_step=sec * 1e3, env_steps_per_s=n_env / sec))
     print(json.dumps(rows[-1]), flush=True)
     env.close()
@@ -117,6 +117,6 @@ e2e("SoftPendulum3D-v0", "SoftPendulum3D-v0", 4096, (2,), -1.0, 1.0, 10)
 e2e("OctoArmSingle-v0", "OctoArmSingle-v0", 4096, (7,), -22.0, 22.0, 5)
 e2e("OctoFlat-v0", "OctoFlat-v0", 4096, (24,), -22.0, 22.0, 3)
 snake_lo = np.array([-4e-3] * 6 + [0.9], dtype=np.float32); snake_hi = np.array([4e-3] * 6 + [1.1], dtype=np.float32)
-e2e("ContinuumSnake-v0", "ContinuumSnake-v0", 4096, (7,), snake_lo, snake_hi, 2)
+e2e("ContinuumSnake-v0", "ContinuumSnake-v0", 4096, (7,), snake_lo, snake_hi, 2, W=2)
 e2e("SoftArmTracking-v0", "SoftArmTracking-v0", 16384, (8,), -0.3, 0.3, 10, dtype=torch.float64)
 print("fp64 peak", peak)

@@ -825,7 +825,7 @@ def test_fast_only_kernel_falls_back_per_env():
 def test_fast_pair_switches_itself_off_when_most_envs_fall_back():
     """Adaptive switch of the fast-only / fallback pair: a handle whose envs all live outside the narrow fast-math
     range (here: every rod spins at 3000 rad/s, 0.15 rad per half-step rotation > 0.1) would pay for two
-    kernels per step; after the first asynchronous check of the fallback counter (steps 32-64) it must be down to
+    kernels per step; after the first asynchronous check of the fallback counter (steps 8-16) it must be down to
     the single safe kernel.  A well-behaved handle next to it keeps the pair."""
     import torch
     nat = _native()
