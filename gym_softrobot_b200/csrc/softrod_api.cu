@@ -554,7 +554,9 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
     A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
     A.n_substeps = n_substeps;
     const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head);
-    return nt > 512    ? launch_packed<float, 1024, 1>(h, A, (cudaStream_t)stream)
+    return nt == 1024  ? launch_packed<float, 1024, 1>(h, A, (cudaStream_t)stream)
+           : nt == 768 ? launch_packed<float, 768, 1>(h, A, (cudaStream_t)stream)
+           : nt == 544 ? launch_packed<float, 544, 1>(h, A, (cudaStream_t)stream)
            : nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
            : nt == 384 ? launch_packed<float, 384, 1>(h, A, (cudaStream_t)stream)
                        : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);

@@ -59,18 +59,20 @@ for n_elem, dt in ((50, 7e-5), (200, 2e-5)):
     report(f"rod on frictional plane n={n_elem} (config 5 topology)", n_env, n_elem, 400, timed(lambda: h.step(None, 400, obs, rew, term), K=5), 440 + 280)
     assert int(term.sum()) == 0
     h.close()
-# config 5 as specified: long slender rod n_elem = 512 on the frictional plane (one rod per CTA)
+# config 5 as specified: long slender rod n_elem = 512 on the frictional plane (one rod per CTA), FP64 and FP32 modes
 n_env, n_elem = 4096, 512
-h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elem, dt=5e-6, gravity=(0, 0, -9.81), damping_constant=1e-2,
-               bc_kind=nat.BC_FREE, contact={**arm_contact_params(), "plane_origin": [0.0, 0.0, -0.005]}, base_length=1.0,
-               base_radius=0.005, density=1000.0, youngs_modulus=1e6)
-init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
-h.reset_host(init)
-h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.random.default_rng(1).uniform(-3, 3, (n_env, 1)) * np.ones((1, n_elem - 1)), device="cuda")
-obs = torch.empty((n_env, 6), dtype=torch.float32, device="cuda"); rew = torch.empty(n_env, dtype=torch.float64, device="cuda"); term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
-report("long slender rod n=512 on frictional plane (config 5 as specified)", n_env, n_elem, 50, timed(lambda: h.step(None, 50, obs, rew, term), K=5), 440 + 280)
-assert int(term.sum()) == 0
-h.close()
+for dtype, tag in ((nat.DTYPE_F64, "FP64"), (nat.DTYPE_F32, "FP32")):
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elem, dt=5e-6, gravity=(0, 0, -9.81), damping_constant=1e-2,
+                   bc_kind=nat.BC_FREE, contact={**arm_contact_params(), "plane_origin": [0.0, 0.0, -0.005]}, base_length=1.0,
+                   base_radius=0.005, density=1000.0, youngs_modulus=1e6, dtype=dtype)
+    init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+    h.reset_host(init)
+    rk = h.rest_kappa_tensor()
+    rk[:, 0, :] = torch.as_tensor(np.random.default_rng(1).uniform(-3, 3, (n_env, 1)) * np.ones((1, n_elem - 1)), device="cuda").to(rk.dtype)
+    obs = torch.empty((n_env, 6), dtype=torch.float32, device="cuda"); rew = torch.empty(n_env, dtype=torch.float64, device="cuda"); term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+    report(f"long slender rod n=512 on frictional plane (config 5 as specified), {tag}", n_env, n_elem, 50, timed(lambda: h.step(None, 50, obs, rew, term), K=5), 440 + 280)
+    assert int(term.sum()) == 0
+    h.close()
 # config 4: 8-arm assembly with head + joints + contact (OctoFlat topology), n_elem = 10 (registered env) and 40 (BASELINE)
 from gym_softrobot_b200.envs.octo_flat import OctoFlatVectorEnv
 # n_elem = 40 needs dt <= 3e-5: the k = 1e6 joint spring on a 0.67 g end node has w dt = 2.7 at 7e-5
