@@ -268,7 +268,17 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     }
     return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
   }
-  if (A.muscle_on || A.spline_mask) return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
+  if (A.muscle_on || A.spline_mask) {
+    if constexpr (std::is_same<T, double>::value) {
+      // (the spline forcing updates its cached control values / magnitudes inside the launch: safe kernel only)
+      if (!A.spline_mask && use_fast_pair(h, A, s)) {
+        int rc = launch_packed_impl<T, NT, MINB, false, false, true, false, true, true>(h, A, s);
+        if (rc != SR_OK) return rc;
+        A.redo_filter = 1;
+      }
+    }
+    return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
+  }
   if (A.contact_on || A.rest_kappa) {
     if constexpr (std::is_same<T, double>::value) {
       if (use_fast_pair(h, A, s)) {
