@@ -783,8 +783,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         T vn = sh_v[c * RS + t_next];
-        ed[c] = fma(hh_prev, (moving && c < 2) ? vn : vn - v[c], ed[c]);
-        st[(F_EDGE + c) * stride + j] = elem_ok ? ed[c] : T(0);
+        ed[c] = fma(hh_prev, (moving && c < 2) ? vn : vn - v[c], ed[c]);   // (stored below, once the env is known to be final)
       }
     }
   }
@@ -801,6 +800,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       A.redo[env] = 1;
       if (A.redo_count) atomicAdd(A.redo_count, 1ULL);
     }
+  }
+  if (EDGE && A.n_substeps > 0 && active && !redo) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) st[(F_EDGE + c) * stride + j] = elem_ok ? ed[c] : T(0);
   }
   bool bad = false;
   if (MULTI && hd && !redo) {

@@ -299,7 +299,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     }
     return launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s);
   }
-  if constexpr (std::is_same<T, double>::value) {
+  {   // lean instantiation: FP64 and FP32
     if (use_fast_pair(h, A, s)) {
       // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
       int rc = launch_packed_impl<T, NT, MINB, false, false, false, false, false, true>(h, A, s);
@@ -504,6 +504,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
   fill_args<float>(*cfg, h->stride, h->a32);
   h->a32.spline = h->spline; h->a32.spline_tab = h->spline_tab;
+  h->a32.redo = h->redo;
   h->a32.muscle = h->muscle;
   h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
   h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim; h->a32.head = (float *)h->head;
