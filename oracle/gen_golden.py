@@ -334,6 +334,25 @@ def gen_snake(seed=42, n_state=3, n=33):
     print("snake:", rew[-3:], "com", e.data["center_of_mass"][-1])
 
 
+def gen_snake_perturbed(seed=42):
+    """The same ContinuumSnake-v0 episode as gen_snake (same seed, same actions) with the initial node positions
+    perturbed by 1e-15 m: how far two runs of the REFERENCE drift apart on their own (kinetic-friction chatter,
+    DESIGN.md 5).  ~25 min of NumPy stepping."""
+    g = np.load(os.path.join(OUT, f"continuum_snake_seed{seed}.npz"))
+    env = ref_loader.load_reference_env("ContinuumSnake-v0")
+    env.reset(seed=seed)
+    e = env.unwrapped
+    rng = np.random.default_rng(1)
+    e.shearable_rod.position_collection += 1e-15 * rng.standard_normal(e.shearable_rod.position_collection.shape)
+    rew = [env.step(a)[1] for a in g["actions"]]
+    np.savez_compressed(os.path.join(OUT, f"continuum_snake_seed{seed}_perturbed.npz"),
+                        label=LABEL + "; same seed and actions as continuum_snake_seed42.npz, initial node positions "
+                        "perturbed by 1e-15 * N(0,1) (default_rng(1))",
+                        reward=np.array(rew), cb_com=np.array(e.data["center_of_mass"]),
+                        cb_avg_velocity=np.array(e.data["avg_velocity"]))
+    print("snake perturbed: rewards", rew[-3:], "vs", g["reward"][-3:])
+
+
 def gen_soft_arm(seed=42, n=40, game_mode=1):
     """SoftArmTracking-v0 (clamped n=40 arm, two spline muscle-torque forcings re-fitted at the current
     lengths, fixed or moving target): `n` env-steps of 50 substeps, random actions from the Box."""
@@ -364,6 +383,7 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
         gen_snake()
+        gen_snake_perturbed()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "muscle":
         gen_muscle_torques()
@@ -391,3 +411,4 @@ if __name__ == "__main__":
     gen_soft_arm(game_mode=1)
     gen_soft_arm(game_mode=2)
     gen_snake()   # ~25 min of NumPy stepping
+    gen_snake_perturbed()   # another ~25 min

@@ -632,6 +632,14 @@ def test_continuum_snake_long_horizon_is_a_replica_of_the_reference(golden_dir):
     mean, std = rewards[nz].mean(axis=1), rewards[nz].std(axis=1)
     assert np.all(np.abs(g["reward"][nz] - mean) < 4 * std + 1e-6), (g["reward"][nz], mean, std)
     assert np.all(std < 0.05 * np.abs(mean))                      # and the spread itself is a few per cent
+    # the reference drifts from ITSELF by the same amounts: its own 1e-15-perturbed replica (second fixture) is as far
+    # from the reference run as the GPU replicas are from each other, and passes the same two checks
+    p = np.load(os.path.join(golden_dir, "continuum_snake_seed42_perturbed.npz"))
+    own = np.abs(p["cb_com"] - g["cb_com"]).max(axis=1)
+    gpu_spread = np.abs(com[1:] - com[:1]).max(axis=(0, 2))
+    for k in (12, 36, 120, 240, S - 1):
+        assert 0.1 * gpu_spread[k] < own[k] < 10 * gpu_spread[k] + 1e-7, (k, own[k], gpu_spread[k])
+    assert np.all(np.abs(p["reward"][nz] - mean) < 4 * std + 1e-6)
     v.close()
 
 
