@@ -99,11 +99,11 @@ constexpr double kSmallRotQ = 0.25;
 // g(u) = theta / sin(theta) with u = sin^2(theta/2) = (1 - cos theta)/2, valid for
 // u <= 0.25, i.e. up to 60 degrees of bending between neighbouring elements (a rod bent
 // to a radius of one element length); ascending powers, degree 13.
-#define SR_COEF_BEND {1.0, 0.6666666666666667, 0.5333333333333167, 0.4571428571456908, \
-                      0.4063492060981829, 0.36940838269940973, 0.3409918863270117, \
-                      0.3182700383289065, 0.2993695424665021, 0.2856689010559272, \
-                      0.2554785051838476, 0.33627006293385214, -0.010109211165683595, \
-                      0.7004333670912273}
+#define SR_COEF_BEND {1.0, 0.6666666666667322, 0.5333333333163501, \
+                      0.4571428588719633, 0.40634911476368524, 0.3694112649313803, \
+                      0.3409332932493519, 0.3190722876223924, 0.29180058074110277, \
+                      0.33511256175349097, 0.03513915536852488, 0.9776555580022731, \
+                      -1.1132861271784307, 1.5537792943093436}
 constexpr double kSmallBendU = 0.25;
 
 // exp(z) for |z| <= 0.01: c^(e) = c * exp((e-1) ln c) in the analytical damper; degree 5.
