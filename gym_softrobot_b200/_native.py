@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals",
 ]
 
 
@@ -103,6 +103,7 @@ def load_library():
     L.sr_launch_count.restype = C.c_int64
     L.sr_measure_fp64_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
     L.sr_measure_fp64_peak_regs.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    L.sr_selftest_reciprocals.argtypes = [C.c_int, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_double)]
     if L.sr_abi_version() != 1:
         raise SoftRodError("libsoftrod.so ABI version mismatch")
     _lib = L
@@ -132,6 +133,14 @@ def spline_basis(n_ctrl: int, base_length: float):
     out = np.zeros((n_ctrl + 1, n_ctrl, 4))
     _check(lib.sr_spline_basis(n_ctrl, float(base_length), out.ctypes.data_as(C.c_void_p)))
     return out
+
+
+def selftest_reciprocals(n=1 << 20, lo=1e-12, hi=1e12, device=0):
+    """(max rel err of rsqrt_nr, of rcp_nr) over n log-spaced arguments (sr_selftest_reciprocals)."""
+    lib = load_library()
+    out = (C.c_double * 2)()
+    _check(lib.sr_selftest_reciprocals(device, n, lo, hi, out))
+    return out[0], out[1]
 
 
 def measure_fp64_peak(device: int = 0, three_register_operands: bool = False) -> float:

@@ -848,4 +848,19 @@ __global__ void dfma_peak_regs_kernel(double *out, const double *in, int iters) 
   if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// sr_selftest_reciprocals: max relative error of rsqrt_nr / rcp_nr against the IEEE-rounded results
+__global__ void reciprocal_selftest_kernel(int n, double lo, double hi, double *out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double e0 = 0.0, e1 = 0.0;
+  if (i < n) {
+    const double x = lo * exp(log(hi / lo) * (double)i / (double)(n - 1));
+    const double r0 = 1.0 / sqrt(x), r1 = 1.0 / x;           // correctly rounded sqrt and divisions
+    e0 = fabs(rsqrt_nr(x) / r0 - 1.0);
+    e1 = fabs(rcp_nr(x) / r1 - 1.0);
+  }
+  // errors are non-negative doubles: their bit patterns order like unsigned integers
+  atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(e0));
+  atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)__double_as_longlong(e1));
+}
+
 }  // namespace sr

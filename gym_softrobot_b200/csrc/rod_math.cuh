@@ -63,7 +63,8 @@ __device__ __forceinline__ float rcp_approx(float x) { return __frcp_rn(x); }
 // Full-precision 1/sqrt(x) and 1/x for normal positive x (lengths, dilatations):
 // MUFU seed + one third-order Newton step (seed error e ~ 2^-20 -> e^3 ~ 2^-60).
 // 5 / 3 FP64 instructions instead of the ~10 / ~8 (plus special-case branch) of
-// rsqrt() / __drcp_rn().  Checked against the IEEE results in tests/test_kernels_gpu.py.
+// rsqrt() / __drcp_rn().  Checked against the IEEE results by sr_selftest_reciprocals
+// (tests/test_parity_gpu.py::test_newton_reciprocals_are_one_ulp).
 __device__ __forceinline__ double rsqrt_nr(double x) {
   double y = rsqrt_approx(x);
   double h = x * y;

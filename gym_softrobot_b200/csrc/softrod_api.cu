@@ -784,4 +784,20 @@ static int measure_fp64_peak_impl(int device, double *tflops_out, bool three_reg
 int sr_measure_fp64_peak(int device, double *tflops_out) { return measure_fp64_peak_impl(device, tflops_out, false); }
 int sr_measure_fp64_peak_regs(int device, double *tflops_out) { return measure_fp64_peak_impl(device, tflops_out, true); }
 
+int sr_selftest_reciprocals(int device, int32_t n, double lo, double hi, double *out) {
+  if (!out || n < 2 || !(lo > 0.0) || !(hi > lo)) return fail(SR_E_INVALID, "sr_selftest_reciprocals: bad argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SR_E_NO_DEVICE, "no CUDA device"); }
+  SR_CUDA(cudaSetDevice(device));
+  double *d = nullptr;
+  SR_CUDA(cudaMalloc(&d, 2 * sizeof(double)));
+  SR_CUDA(cudaMemset(d, 0, 2 * sizeof(double)));
+  sr::reciprocal_selftest_kernel<<<(n + 255) / 256, 256>>>(n, lo, hi, d);
+  SR_CUDA(cudaGetLastError());
+  cudaError_t e = cudaMemcpy(out, d, 2 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SR_E_CUDA, cudaGetErrorString(e));
+  return SR_OK;
+}
+
 }  // extern "C"

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     assert os.path.exists(path)
     lib = C.CDLL(path)
     syms = declared_symbols()
-    assert len(syms) >= 23
+    assert len(syms) >= 24
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in softrod.h but not exported"
     assert sorted(nat.EXPORTED_SYMBOLS) == syms, "python binding list out of sync with the header"

@@ -858,3 +858,11 @@ def test_fast_pair_switches_itself_off_when_most_envs_fall_back():
         assert np.all(late == per_step_late), (spin, late)
         assert torch.isfinite(h.state_tensor()).all()
         h.close()
+
+
+def test_newton_reciprocals_are_one_ulp():
+    """rsqrt_nr / rcp_nr (MUFU seed + one third-order Newton step, csrc/rod_math.cuh) against the correctly rounded
+    IEEE results over 2^20 log-spaced arguments spanning the lengths / dilatations the kernels see and far beyond."""
+    nat = _native()
+    e_rsqrt, e_rcp = nat.selftest_reciprocals(1 << 20, 1e-12, 1e12)
+    assert 0.0 < e_rsqrt < 3.4e-16 and 0.0 < e_rcp < 2.3e-16, (e_rsqrt, e_rcp)   # <= 1.5 ulp / <= 1 ulp
