@@ -238,7 +238,9 @@ template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaSt
   if (!fastpath_setting() || !A.redo) return false;
   h->pair_steps++;
   if (h->pair_off_until > h->pair_steps) return false;
-  if (h->pair_copy_pending && cudaEventQuery(h->pair_event) == cudaSuccess) {
+  cudaError_t q = h->pair_copy_pending ? cudaEventQuery(h->pair_event) : cudaErrorNotReady;
+  if (h->pair_copy_pending && q == cudaErrorNotReady) (void)cudaGetLastError();   // "not ready" is an answer, not an error to report later
+  if (h->pair_copy_pending && q == cudaSuccess) {
     h->pair_copy_pending = false;
     const unsigned long long seen = *h->h_redo_count, delta = seen - h->pair_last_count;
     const long long window = (h->pair_steps_at_copy - h->pair_steps_at_prev_copy) * (long long)A.n_env;
