@@ -99,3 +99,23 @@ def test_product_never_imports_oracle():
                 n += 1
                 assert not bad.search(open(os.path.join(dirpath, f)).read()), f
     assert n >= 8
+
+
+def test_integration_doc_stub_lists_the_header_fields_in_order():
+    """INTEGRATION.md shows the ctypes mirror a reference maintainer would write: its field list must be the
+    header's `sr_config`, name for name, in order (and so must the package's own mirror)."""
+    hdr = open(os.path.join(ROOT, "include", "softrod.h")).read()
+    body = re.search(r"typedef struct sr_config \{(.*?)\} sr_config;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1]              # drop the type
+        fields += [re.sub(r"\[.*?\]", "", n).strip() for n in names.split(",")]
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    stub = re.search(r"class SrConfig\(C\.Structure\):(.*?)\n\n", doc, re.S).group(1)
+    doc_fields = re.findall(r'\("([a-z0-9_]+)",', stub)
+    assert doc_fields == fields
+    assert [f for f, _ in nat.SrConfig._fields_] == fields
