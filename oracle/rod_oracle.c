@@ -45,6 +45,7 @@ struct ro_rod {
   double *filt;                          /* Laplace filter scratch (3,n+1) */
   double *tmp;                           /* scratch (3,n+1) x 4 */
   double *ctmp;                          /* contact scratch, 26 n */
+  double *muscle;                        /* MuscleTorques: wave number, beta (1 + n) */
 };
 
 static double *zalloc(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
@@ -399,6 +400,33 @@ static void apply_contact(ro_rod *r) {
   }
 }
 
+/* ---- MuscleTorques.apply_torques (PyElastica external_forces.py [PE-recall]; restated in
+ * oracle/shims/elastica/external_forces.py): magnitudes beta(s) sin(w t - k s + phi), ramped, walked tail-to-head,
+ * applied as equal and opposite couples on consecutive elements in the material frame. */
+static void apply_muscle_torques(ro_rod *r) {
+  const int n = r->n;
+  const double t = r->time, kw = r->muscle[0], *beta = r->muscle + 1, *d = r->cfg.muscle_direction;
+  const double factor = fmin(1.0, t / r->cfg.muscle_ramp_up_time);
+  const double omega = 2.0 * M_PI / r->cfg.muscle_period;
+  double *mag = r->tmp; /* (n) scratch */
+  double total = 0.0, cum = 0.0;
+  for (int k = 0; k < n; k++) total += r->rest_len[k];   /* s = cumsum(rest_lengths) (left to right); s /= s[-1] */
+  for (int i = 0; i < n; i++) {
+    cum += r->rest_len[i];
+    const double s = cum / total;
+    mag[i] = factor * beta[i] * sin(omega * t - kw * s + r->cfg.muscle_phase_shift);
+  }
+  for (int k = 0; k < n; k++) {
+    const double mk = mag[n - 1 - k];                       /* torque_mag[::-1] */
+    const double mk1 = (k + 1 < n) ? mag[n - 2 - k] : 0.0;
+    for (int i = 0; i < 3; i++) {
+      const double qd = QQ(i, 0, k) * d[0] + QQ(i, 1, k) * d[1] + QQ(i, 2, k) * d[2];
+      if (k >= 1) r->t_ext[i * n + k] += qd * mk;
+      if (k + 1 < n) r->t_ext[i * n + k] -= qd * mk1;
+    }
+  }
+}
+
 /* ---- A.2 one PositionVerlet substep */
 static void substep(ro_rod *r, double action, const double *bp, const double *bv) {
   const int n = r->n;
@@ -413,6 +441,7 @@ static void substep(ro_rod *r, double action, const double *bp, const double *bv
     for (int k = 0; k <= n; k++)
       r->f_ext[i * (n + 1) + k] += r->cfg.gravity[i] * r->mass[k] + r->f_user[i * (n + 1) + k];
   if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
+  if (r->cfg.muscle_on) apply_muscle_torques(r);         /* a forcing, registered after gravity (continuum_snake.py:325-337) */
   if (r->cfg.contact_on && !r->cfg.contact_before_forcing) apply_contact(r);
   /* dynamic step */
   for (int i = 0; i < 3; i++)
@@ -450,6 +479,7 @@ ro_rod *ro_create(const ro_config *cfg) {
   r->rest_len = zalloc(n); r->rest_vor = zalloc(nv); r->mass = zalloc(n + 1); r->volume = zalloc(n);
   r->radius = zalloc(n); r->J = zalloc(3 * n); r->Jinv = zalloc(3 * n); r->S = zalloc(3 * n); r->B = zalloc(3 * nv);
   r->rest_sigma = zalloc(3 * n); r->rest_kappa = zalloc(3 * nv);
+  r->muscle = zalloc(1 + n);
   r->len = zalloc(n); r->tang = zalloc(3 * n); r->dil = zalloc(n); r->vdil = zalloc(nv); r->dil_rate = zalloc(n);
   r->sigma = zalloc(3 * n); r->kappa = zalloc(3 * nv); r->stress = zalloc(3 * n); r->couple = zalloc(3 * nv);
   r->f_int = zalloc(3 * (n + 1)); r->t_int = zalloc(3 * n); r->f_ext = zalloc(3 * (n + 1)); r->t_ext = zalloc(3 * n);
@@ -525,7 +555,7 @@ void ro_destroy(ro_rod *r) {
   double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
                     r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
                     r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
-                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp, r->ctmp};
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
   free(r);
 }
@@ -546,6 +576,7 @@ double *ro_mass(ro_rod *r) { return r->mass; }
 double *ro_internal_forces(ro_rod *r) { return r->f_int; }
 double *ro_internal_torques(ro_rod *r) { return r->t_int; }
 double *ro_radius(ro_rod *r) { return r->radius; }
+double *ro_muscle(ro_rod *r) { return r->muscle; }
 
 /* numpy pairwise summation (np.add.reduce on a contiguous float64 row, n < 128 block) */
 static double np_pairwise_sum(const double *a, int n) {

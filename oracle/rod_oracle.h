@@ -32,6 +32,11 @@ typedef struct {
   double plane_origin[3], plane_normal[3];
   double contact_k, contact_nu, slip_velocity_tol, surface_tol;
   double static_mu[3], kinetic_mu[3]; /* forward, backward, sideways */
+  /* PyElastica MuscleTorques (travelling wave; [PE-recall], call site
+   * /root/reference/gym_softrobot/envs/snake/continuum_snake.py:186-198,325-337); muscle_on = 0 disables.
+   * beta(s) and the wave number are set through ro_muscle() (what `set_action` rebuilds). */
+  int muscle_on;
+  double muscle_period, muscle_ramp_up_time, muscle_phase_shift, muscle_direction[3];
 } ro_config;
 
 typedef struct ro_rod ro_rod;
@@ -59,6 +64,7 @@ double *ro_mass(ro_rod *);
 double *ro_internal_forces(ro_rod *);
 double *ro_internal_torques(ro_rod *);
 double *ro_radius(ro_rod *);
+double *ro_muscle(ro_rod *); /* [1 + n]: wave_number, then beta(s_k) at s_k = cumsum(rest_lengths)_k / L */
 
 /* SoftPendulum-v0 env step on top of the rod: follows
  * /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:176-251 */

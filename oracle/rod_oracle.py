@@ -46,6 +46,11 @@ class ROConfig(C.Structure):
         ("surface_tol", C.c_double),
         ("static_mu", C.c_double * 3),
         ("kinetic_mu", C.c_double * 3),
+        ("muscle_on", C.c_int),
+        ("muscle_period", C.c_double),
+        ("muscle_ramp_up_time", C.c_double),
+        ("muscle_phase_shift", C.c_double),
+        ("muscle_direction", C.c_double * 3),
     ]
 
 
@@ -74,7 +79,7 @@ def lib():
         L.ro_time.argtypes = [C.c_void_p]
         for name in ("position", "velocity", "director", "omega", "tangents", "kappa", "sigma",
                      "dilatation", "rest_kappa", "external_forces", "mass", "internal_forces",
-                     "internal_torques", "radius"):
+                     "internal_torques", "radius", "muscle"):
             f = getattr(L, "ro_" + name)
             f.restype = C.POINTER(C.c_double)
             f.argtypes = [C.c_void_p]
@@ -97,7 +102,7 @@ class OracleRod:
                  youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
                  gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
                  bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=False,
-                 contact=None):
+                 contact=None, muscle=None):
         cfg = ROConfig()
         cfg.n_elem = n_elem
         cfg.start[:] = list(map(float, start))
@@ -121,6 +126,11 @@ class OracleRod:
             cfg.slip_velocity_tol, cfg.surface_tol = contact["slip_velocity_tol"], contact.get("surface_tol", 1e-4)
             cfg.static_mu[:] = list(map(float, contact["static_mu"]))
             cfg.kinetic_mu[:] = list(map(float, contact["kinetic_mu"]))
+        if muscle is not None:    # dict: period, ramp_up_time, phase_shift, direction (MuscleTorques kwargs)
+            cfg.muscle_on = 1
+            cfg.muscle_period, cfg.muscle_ramp_up_time = muscle["period"], muscle["ramp_up_time"]
+            cfg.muscle_phase_shift = muscle.get("phase_shift", 0.0)
+            cfg.muscle_direction[:] = list(map(float, muscle["direction"]))
         self.cfg = cfg
         self.n = n_elem
         self._h = C.c_void_p(lib().ro_create(C.byref(cfg)))
@@ -139,6 +149,7 @@ class OracleRod:
         self.internal_forces = self._view("internal_forces", (3, n + 1))
         self.internal_torques = self._view("internal_torques", (3, n))
         self.radius = self._view("radius", (n,))
+        self.muscle = self._view("muscle", (n + 1,))       # wave number, beta(s_k)
 
     def _view(self, name, shape):
         p = getattr(lib(), "ro_" + name)(self._h)

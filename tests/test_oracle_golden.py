@@ -202,3 +202,35 @@ def test_sliding_rod_decelerates_at_mu_g(v0, mu):
     expected = v0 - np.sign(v0) * mu * g * dt * steps
     assert np.abs(speeds[False] - expected).max() < 1e-3 * abs(v0)      # forcing -> contact: Coulomb friction
     assert np.abs(speeds[True] - v0).max() < 1e-6 * abs(v0)             # contact -> forcing: frictionless
+
+
+@pytest.mark.parametrize("case", ["A", "B"], ids=["frictionless-plane", "free-oblique-phase"])
+def test_c_oracle_muscle_torques_match_shim_fixture(golden_dir, case):
+    """C restatement of PyElastica's MuscleTorques (rod_oracle.c:apply_muscle_torques) against the fixture produced
+    by the NumPy shim's MuscleTorques (oracle/gen_golden.py:gen_muscle_torques): two independent restatements of the
+    same recalled forcing, plane response included in case A, forcing rebuilt half way like `set_action` does."""
+    g = np.load(os.path.join(golden_dir, "muscle_torques_seed9.npz"))
+    n, L, E, dt = int(g["n_elem"]), 0.35, 1e6, float(g["dt"])
+    r0 = L * 0.011
+    contact = None
+    if case == "A":
+        contact = dict(plane_origin=[0.0, -r0, 0.0], plane_normal=[0.0, 1.0, 0.0], k=1.0, nu=1e-6, slip_velocity_tol=1e-8,
+                       static_mu=[0.0] * 3, kinetic_mu=[0.0] * 3, before_forcing=False)
+    rod = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [0, 1.0, 0], L, r0, 1000.0, E, dt, shear_modulus=E / 1.5,
+                       gravity=(0.0, -9.80665, 0.0) if case == "A" else (0.0, 0.0, 0.0), damping_constant=1e-4,
+                       contact=contact,
+                       muscle=dict(period=float(g["period"]), ramp_up_time=float(g["period"]),
+                                   phase_shift=float(g[f"{case}/phase"]), direction=g[f"{case}/direction"]))
+    c = np.sqrt(E / 1000.0)
+    floor_v = 64 * 2.2e-16 * L * c / (L / n)                     # round-off floor of a rod that has barely moved
+    for seg in range(2):
+        rod.muscle[0] = float(g[f"{case}/wave_number{seg}"])
+        rod.muscle[1:] = g[f"{case}/beta{seg}"]
+        rod.substeps(int(g["segment"]))
+        for name, floor in (("position", 0.0), ("velocity", floor_v), ("director", 0.0), ("omega", floor_v / r0)):
+            ref = g[f"{case}/seg{seg + 1}/{name}"]
+            got = getattr(rod, name + "_collection")
+            err = float(np.abs(got - ref).max())
+            assert err < 1e-9 * float(np.abs(ref).max()) + floor, (case, seg, name, err)
+    assert rod.time == float(g[f"{case}/time"])
+    rod.close()
