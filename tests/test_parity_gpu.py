@@ -866,3 +866,39 @@ def test_newton_reciprocals_are_one_ulp():
     nat = _native()
     e_rsqrt, e_rcp = nat.selftest_reciprocals(1 << 20, 1e-12, 1e12)
     assert 0.0 < e_rsqrt < 3.4e-16 and 0.0 < e_rcp < 2.3e-16, (e_rsqrt, e_rcp)   # <= 1.5 ulp / <= 1 ulp
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_muscle_torques_vs_c_oracle_randomized(seed):
+    """Travelling-wave muscle torques at parameters no fixture holds: rod size, wave number, phase, direction and
+    beta profile drawn per seed, CUDA path vs the C oracle's own restatement (free rod, no friction), 1e-9."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    rng = np.random.default_rng(100 + seed)
+    n = int(rng.integers(12, 60)); L = float(rng.uniform(0.2, 0.6)); r0 = L * float(rng.uniform(0.008, 0.02))
+    E, rho, dt, period = 1e6, 1000.0, 8e-6, float(rng.uniform(1.0, 3.0))
+    direction = rng.standard_normal(3); direction /= np.linalg.norm(direction)
+    mus = dict(period=period, ramp_up_time=0.5 * period, phase_shift=float(rng.uniform(0, 6.28)), direction=direction)
+    beta = rng.uniform(-4e-3, 4e-3, n) * np.sin(np.linspace(0, np.pi, n))
+    kw = float(rng.uniform(3.0, 12.0))
+    init = np.zeros((2, 9)); init[:, 5] = 1.0; init[:, 7] = 1.0
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=2, n_elem=n, dt=dt, base_length=L, base_radius=r0, density=rho,
+                   youngs_modulus=E, shear_modulus=E / 1.5, damping_constant=1e-4, muscle=mus)
+    h.reset_host(init)
+    mu = h.muscle_tensor()
+    mu[:, 1] = kw
+    mu[:, 2:] = torch.as_tensor(beta, device="cuda")
+    o = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [0, 1.0, 0], L, r0, rho, E, dt, shear_modulus=E / 1.5,
+                     damping_constant=1e-4, muscle=mus)
+    o.muscle[0] = kw; o.muscle[1:] = beta
+    for chunk in (700, 800):
+        h.step_host(None, chunk); o.substeps(chunk)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        floors = rate_floors(E, rho, L, n, r0, L)
+        for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+            ref = getattr(o, name)
+            err = float(np.abs(f[name][1] - ref).max())
+            assert err < 1e-9 * float(np.abs(ref).max()) + floors[name], f"seed {seed} {name}: {err:.3e} vs |ref| {np.abs(ref).max():.3e}"
+    assert float(mu[0, 0]) == o.time
+    h.close(); o.close()
