@@ -46,6 +46,7 @@ struct ro_rod {
   double *tmp;                           /* scratch (3,n+1) x 4 */
   double *ctmp;                          /* contact scratch, 26 n */
   double *muscle;                        /* MuscleTorques: wave number, beta (1 + n) */
+  double *spl_pts, *spl_mag;             /* spline forcing: [3][2P+1] control data, [3][n] cached magnitudes */
 };
 
 static double *zalloc(size_t n) { return (double *)calloc(n ? n : 1, sizeof(double)); }
@@ -427,6 +428,74 @@ static void apply_muscle_torques(ro_rod *r) {
   }
 }
 
+/* ---- MuscleTorquesWithVaryingBetaSplines.apply_torques (muscle_torques_with_bspline.py:126-160, filter :206-228,
+ * compute :181-204).  The spline is scipy's make_interp_spline(x, y) = the not-a-knot interpolating cubic; it is
+ * solved here for its second derivatives and evaluated in the classical two-sided form. */
+static double notaknot_eval(int N, double dx, const double *y, const double *M, double s) {
+  int m = (int)floor(s / dx);
+  if (m < 0) m = 0;
+  if (m > N - 1) m = N - 1;                 /* beyond the last knot: the last piece continues (extrapolate=True) */
+  const double a = (m + 1) * dx - s, b = s - m * dx;
+  return M[m] * a * a * a / (6.0 * dx) + M[m + 1] * b * b * b / (6.0 * dx) +
+         (y[m] / dx - M[m] * dx / 6.0) * a + (y[m + 1] / dx - M[m + 1] * dx / 6.0) * b;
+}
+
+static void notaknot_second_derivatives(int N, double dx, const double *y, double *M) {
+  /* unknowns M_0..M_N; rows: third-derivative continuity at x_1 and x_{N-1}, C2 conditions in between */
+  const int K = N + 1;
+  double A[18][19];
+  memset(A, 0, sizeof(A));
+  A[0][0] = 1.0; A[0][1] = -2.0; A[0][2] = 1.0;
+  A[N][N] = 1.0; A[N][N - 1] = -2.0; A[N][N - 2] = 1.0;
+  for (int m = 1; m < N; m++) {
+    A[m][m - 1] = 1.0; A[m][m] = 4.0; A[m][m + 1] = 1.0;
+    A[m][K] = 6.0 * (y[m - 1] - 2.0 * y[m] + y[m + 1]) / (dx * dx);
+  }
+  for (int c = 0; c < K; c++) {
+    int piv = c;
+    for (int q = c + 1; q < K; q++) if (fabs(A[q][c]) > fabs(A[piv][c])) piv = q;
+    if (piv != c) for (int k = 0; k <= K; k++) { double t = A[c][k]; A[c][k] = A[piv][k]; A[piv][k] = t; }
+    for (int q = c + 1; q < K; q++) {
+      const double f = A[q][c] / A[c][c];
+      for (int k = c; k <= K; k++) A[q][k] -= f * A[c][k];
+    }
+  }
+  for (int c = K - 1; c >= 0; c--) {
+    double acc = A[c][K];
+    for (int k = c + 1; k < K; k++) acc -= A[c][k] * M[k];
+    M[c] = acc / A[c][c];
+  }
+}
+
+static void apply_spline_torques(ro_rod *r) {
+  const int n = r->n, P = r->cfg.spline_n_ctrl, N = P + 1;
+  const double dx = r->cfg.base_length / N;
+  for (int d = 0; d < 3; d++) {
+    if (!(r->cfg.spline_dir_mask >> d & 1)) continue;
+    double *tgt = r->spl_pts + d * (2 * P + 1), *cached = tgt + P, *flag = tgt + 2 * P, *mag = r->spl_mag + d * n;
+    int differ = (*flag == 0.0);
+    for (int i = 0; i < P; i++) differ = differ || !(cached[i] == tgt[i]);      /* not np.array_equal */
+    if (differ) {
+      *flag = 1.0;
+      for (int i = 0; i < P; i++) {                                             /* filter_activation */
+        const double diff = tgt[i] - cached[i];
+        const double sg = (diff > 0.0) - (diff < 0.0);
+        cached[i] += sg * fmin(r->cfg.spline_max_rate, fabs(diff));
+      }
+      double y[18], M[18];
+      y[0] = 0.0; y[N] = 0.0;
+      for (int i = 0; i < P; i++) y[1 + i] = cached[i];
+      notaknot_second_derivatives(N, dx, y, M);
+      double s = 0.0;
+      for (int k = 0; k < n; k++) {                                             /* np.cumsum(system.lengths) */
+        s += r->len[k];
+        mag[k] = r->cfg.spline_scale * notaknot_eval(N, dx, y, M, s);
+      }
+    }
+    for (int k = 0; k < n; k++) r->t_ext[d * n + k] += mag[k];                  /* compute_muscle_torques */
+  }
+}
+
 /* ---- A.2 one PositionVerlet substep */
 static void substep(ro_rod *r, double action, const double *bp, const double *bv) {
   const int n = r->n;
@@ -442,6 +511,7 @@ static void substep(ro_rod *r, double action, const double *bp, const double *bv
       r->f_ext[i * (n + 1) + k] += r->cfg.gravity[i] * r->mass[k] + r->f_user[i * (n + 1) + k];
   if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
   if (r->cfg.muscle_on) apply_muscle_torques(r);         /* a forcing, registered after gravity (continuum_snake.py:325-337) */
+  if (r->cfg.spline_dir_mask) apply_spline_torques(r);   /* forcings (soft_arm_tracking.py:366-400) */
   if (r->cfg.contact_on && !r->cfg.contact_before_forcing) apply_contact(r);
   /* dynamic step */
   for (int i = 0; i < 3; i++)
@@ -480,6 +550,8 @@ ro_rod *ro_create(const ro_config *cfg) {
   r->radius = zalloc(n); r->J = zalloc(3 * n); r->Jinv = zalloc(3 * n); r->S = zalloc(3 * n); r->B = zalloc(3 * nv);
   r->rest_sigma = zalloc(3 * n); r->rest_kappa = zalloc(3 * nv);
   r->muscle = zalloc(1 + n);
+  r->spl_pts = zalloc(3 * (2 * (size_t)(cfg->spline_n_ctrl > 0 ? cfg->spline_n_ctrl : 0) + 1));
+  r->spl_mag = zalloc(3 * (size_t)n);
   r->len = zalloc(n); r->tang = zalloc(3 * n); r->dil = zalloc(n); r->vdil = zalloc(nv); r->dil_rate = zalloc(n);
   r->sigma = zalloc(3 * n); r->kappa = zalloc(3 * nv); r->stress = zalloc(3 * n); r->couple = zalloc(3 * nv);
   r->f_int = zalloc(3 * (n + 1)); r->t_int = zalloc(3 * n); r->f_ext = zalloc(3 * (n + 1)); r->t_ext = zalloc(3 * n);
@@ -555,7 +627,7 @@ void ro_destroy(ro_rod *r) {
   double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
                     r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
                     r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
-                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle};
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
   free(r);
 }
@@ -577,6 +649,8 @@ double *ro_internal_forces(ro_rod *r) { return r->f_int; }
 double *ro_internal_torques(ro_rod *r) { return r->t_int; }
 double *ro_radius(ro_rod *r) { return r->radius; }
 double *ro_muscle(ro_rod *r) { return r->muscle; }
+double *ro_spline_points(ro_rod *r) { return r->spl_pts; }
+double *ro_spline_magnitude(ro_rod *r) { return r->spl_mag; }
 
 /* numpy pairwise summation (np.add.reduce on a contiguous float64 row, n < 128 block) */
 static double np_pairwise_sum(const double *a, int n) {

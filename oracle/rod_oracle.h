@@ -37,6 +37,11 @@ typedef struct {
    * beta(s) and the wave number are set through ro_muscle() (what `set_action` rebuilds). */
   int muscle_on;
   double muscle_period, muscle_ramp_up_time, muscle_phase_shift, muscle_direction[3];
+  /* MuscleTorquesWithVaryingBetaSplines (/root/reference/gym_softrobot/utils/custom_elastica/muscle_torque/
+   * muscle_torques_with_bspline.py:46-228; call sites envs/soft_arm/soft_arm_tracking.py:366-400): bit d of
+   * spline_dir_mask = one forcing instance on material direction d (0 normal, 1 binormal, 2 tangent). */
+  int spline_dir_mask, spline_n_ctrl;
+  double spline_scale, spline_max_rate;
 } ro_config;
 
 typedef struct ro_rod ro_rod;
@@ -64,7 +69,9 @@ double *ro_mass(ro_rod *);
 double *ro_internal_forces(ro_rod *);
 double *ro_internal_torques(ro_rod *);
 double *ro_radius(ro_rod *);
-double *ro_muscle(ro_rod *); /* [1 + n]: wave_number, then beta(s_k) at s_k = cumsum(rest_lengths)_k / L */
+double *ro_muscle(ro_rod *);
+double *ro_spline_points(ro_rod *); /* [3][2P+1]: P targets (points_func_array), P cached values, initial-call flag */
+double *ro_spline_magnitude(ro_rod *); /* [3][n]: torque_magnitude_cache of each instance */ /* [1 + n]: wave_number, then beta(s_k) at s_k = cumsum(rest_lengths)_k / L */
 
 /* SoftPendulum-v0 env step on top of the rod: follows
  * /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:176-251 */

@@ -51,6 +51,10 @@ class ROConfig(C.Structure):
         ("muscle_ramp_up_time", C.c_double),
         ("muscle_phase_shift", C.c_double),
         ("muscle_direction", C.c_double * 3),
+        ("spline_dir_mask", C.c_int),
+        ("spline_n_ctrl", C.c_int),
+        ("spline_scale", C.c_double),
+        ("spline_max_rate", C.c_double),
     ]
 
 
@@ -79,7 +83,7 @@ def lib():
         L.ro_time.argtypes = [C.c_void_p]
         for name in ("position", "velocity", "director", "omega", "tangents", "kappa", "sigma",
                      "dilatation", "rest_kappa", "external_forces", "mass", "internal_forces",
-                     "internal_torques", "radius", "muscle"):
+                     "internal_torques", "radius", "muscle", "spline_points", "spline_magnitude"):
             f = getattr(L, "ro_" + name)
             f.restype = C.POINTER(C.c_double)
             f.argtypes = [C.c_void_p]
@@ -102,7 +106,7 @@ class OracleRod:
                  youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
                  gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
                  bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=False,
-                 contact=None, muscle=None):
+                 contact=None, muscle=None, spline=None):
         cfg = ROConfig()
         cfg.n_elem = n_elem
         cfg.start[:] = list(map(float, start))
@@ -131,6 +135,10 @@ class OracleRod:
             cfg.muscle_period, cfg.muscle_ramp_up_time = muscle["period"], muscle["ramp_up_time"]
             cfg.muscle_phase_shift = muscle.get("phase_shift", 0.0)
             cfg.muscle_direction[:] = list(map(float, muscle["direction"]))
+        if spline is not None:    # dict: directions (subset of 0,1,2), n_ctrl, scale, max_rate
+            cfg.spline_dir_mask = sum(1 << int(d) for d in spline["directions"])
+            cfg.spline_n_ctrl = spline["n_ctrl"]
+            cfg.spline_scale, cfg.spline_max_rate = spline["scale"], spline.get("max_rate", float("inf"))
         self.cfg = cfg
         self.n = n_elem
         self._h = C.c_void_p(lib().ro_create(C.byref(cfg)))
@@ -150,6 +158,9 @@ class OracleRod:
         self.internal_torques = self._view("internal_torques", (3, n))
         self.radius = self._view("radius", (n,))
         self.muscle = self._view("muscle", (n + 1,))       # wave number, beta(s_k)
+        P = max(int(cfg.spline_n_ctrl), 0)
+        self.spline_points = self._view("spline_points", (3, 2 * P + 1))     # per direction: P targets, P cached, flag
+        self.spline_magnitude = self._view("spline_magnitude", (3, n))
 
     def _view(self, name, shape):
         p = getattr(lib(), "ro_" + name)(self._h)

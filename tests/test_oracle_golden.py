@@ -234,3 +234,27 @@ def test_c_oracle_muscle_torques_match_shim_fixture(golden_dir, case):
             assert err < 1e-9 * float(np.abs(ref).max()) + floor, (case, seg, name, err)
     assert rod.time == float(g[f"{case}/time"])
     rod.close()
+
+
+def test_c_oracle_spline_torques_match_reference_forcing_fixture(golden_dir):
+    """C restatement of `MuscleTorquesWithVaryingBetaSplines` (rod_oracle.c:apply_spline_torques: rate-limited
+    control values, not-a-knot cubic solved for its second derivatives, evaluated at cumsum(current lengths)) against
+    the fixture produced by the REFERENCE's forcing class itself on the shim rod (gen_golden.py:gen_spline_forcing):
+    normal + tangent instances, 3 control points, max rate 0.04 per substep, targets changed every 50 substeps."""
+    g = np.load(os.path.join(golden_dir, "spline_forcing_seed5.npz"))
+    n, L, r0, E, dt = int(g["n_elem"]), float(g["base_length"]), float(g["base_radius"]), float(g["youngs_modulus"]), float(g["dt"])
+    rod = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [1.0, 0, 0], L, r0, 1000.0, E, dt, damping_constant=float(g["damping_constant"]),
+                       bc_kind=ro.BC_ONE_END_FIXED,
+                       spline=dict(directions=(0, 2), n_ctrl=int(g["n_ctrl"]), scale=float(g["scale"]), max_rate=float(g["max_rate"])))
+    P = int(g["n_ctrl"])
+    for s, tgt in enumerate(g["targets"]):
+        rod.spline_points[0, :P] = tgt[0]
+        rod.spline_points[2, :P] = tgt[1]
+        rod.substeps(int(g["segment"]))
+        for name in ("position", "velocity", "director", "omega", "kappa"):
+            ref = g[f"seg{s + 1}/{name}"]
+            got = getattr(rod, name + "_collection") if name != "kappa" else rod.kappa
+            err = float(np.abs(got - ref).max())
+            assert err < 1e-9 * float(np.abs(ref).max()), (s, name, err, float(np.abs(ref).max()))
+    assert np.all(rod.spline_magnitude[1] == 0.0) and np.abs(rod.spline_magnitude[0]).max() > 0.0
+    rod.close()
