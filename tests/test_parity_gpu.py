@@ -902,3 +902,42 @@ def test_muscle_torques_vs_c_oracle_randomized(seed):
             assert err < 1e-9 * float(np.abs(ref).max()) + floors[name], f"seed {seed} {name}: {err:.3e} vs |ref| {np.abs(ref).max():.3e}"
     assert float(mu[0, 0]) == o.time
     h.close(); o.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_spline_torques_vs_c_oracle_randomized(seed):
+    """Spline muscle torques at parameters no fixture holds (rod size, number of control points, directions, rate
+    limit, scale drawn per seed; targets changed every 40 substeps): CUDA path vs the C oracle's independent
+    restatement of the reference forcing, clamped rod, 1e-9."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    rng = np.random.default_rng(200 + seed)
+    n = int(rng.integers(10, 64)); L = float(rng.uniform(0.3, 1.5)); r0 = L / n * float(rng.uniform(0.5, 1.2))
+    E, rho, dt = 1e6, 1000.0, 2e-5
+    P = int(rng.integers(2, 7))
+    dirs = tuple(sorted(rng.choice(3, size=int(rng.integers(1, 4)), replace=False).tolist()))
+    EI = E * np.pi * r0 ** 4 / 4
+    spl = dict(directions=dirs, n_ctrl=P, scale=float(EI * rng.uniform(0.5, 3.0)), max_rate=float(rng.uniform(0.02, 0.2)))
+    init = np.zeros((2, 9)); init[:, 5] = 1.0; init[:, 6] = 1.0
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=2, n_elem=n, dt=dt, base_length=L, base_radius=r0, density=rho,
+                   youngs_modulus=E, damping_constant=0.5, bc_kind=nat.BC_ONE_END_FIXED, spline=spl)
+    h.reset_host(init)
+    o = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [1.0, 0, 0], L, r0, rho, E, dt, damping_constant=0.5,
+                     bc_kind=ro.BC_ONE_END_FIXED, spline=spl)
+    pts, mags = h.spline_tensors()
+    for seg in range(6):
+        tgt = rng.uniform(-1, 1, (3, P))
+        for d in dirs:
+            pts[:, d, :P] = torch.as_tensor(tgt[d], device="cuda")
+            o.spline_points[d, :P] = tgt[d]
+        h.step_host(None, 40); o.substeps(40)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        floors = rate_floors(E, rho, L, n, r0, L)
+        for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+            ref = getattr(o, name)
+            err = float(np.abs(f[name][1] - ref).max())
+            assert err < 1e-9 * float(np.abs(ref).max()) + floors[name], f"seed {seed} seg {seg} {name}: {err:.3e} vs |ref| {np.abs(ref).max():.3e}"
+        for d in dirs:
+            np.testing.assert_allclose(mags[1, d].cpu().numpy(), o.spline_magnitude[d], rtol=1e-9, atol=1e-12 * spl["scale"])
+    h.close(); o.close()
