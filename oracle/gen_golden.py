@@ -194,6 +194,42 @@ def gen_octo_flat_decentralized(seed=42, recording_fps=50):
     print("octo_flat decentralized:", o["individual"].shape, r)
 
 
+def gen_octo_cfg4(seed=42, n=3, n_elems=40, time_step=3e-5, recording_fps=100):
+    """BASELINE config 4 as specified: build_octopus(n_arm=8, n_elem=40) topology (envs/octopus/build.py:52-217)
+    under FlatEnv's rest-curvature actuation.  dt = 3e-5 because the registered 7e-5 is unstable for 40 elements
+    (joint spring k = 1e6 on a 0.67 g end node: dt < 2 / sqrt(k / m) = 5.2e-5); 3 x 333 = 999 substeps.
+    The rest curvatures the env wrote are stored so that checkers need no scipy."""
+    env = ref_loader.load_reference_env("OctoFlat-v0", n_elems=n_elems, time_step=time_step, recording_fps=recording_fps)
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    out = {"label": LABEL + "; operator order = build-code call order (OperatorGroupFIFO): synchronize = [connections, forcing, contact]",
+           "seed": seed, "n_elems": n_elems, "time_step": time_step, "recording_fps": recording_fps,
+           "step_skip": e.step_skip, "target": e._target.copy()}
+
+    def snap(tag):
+        for a, rod in enumerate(e.shearable_rods):
+            pack(f"{tag}/arm{a}", rod_state(rod), out)
+        h = e.rigid_rod
+        out[f"{tag}/head/position"] = h.position_collection.copy()
+        out[f"{tag}/head/velocity"] = h.velocity_collection.copy()
+        out[f"{tag}/head/director"] = h.director_collection.copy()
+        out[f"{tag}/head/omega"] = h.omega_collection.copy()
+
+    snap("state0")
+    acts, rew, term, rk = [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); rew.append(r); term.append(te)
+        rk.append(np.stack([rod.rest_kappa.copy() for rod in e.shearable_rods]))
+        snap(f"state{i + 1}")
+    out.update(actions=np.array(acts, dtype=np.float32), reward=np.array(rew, dtype=np.float64),
+               terminated=np.array(term), rest_kappa=np.array(rk))
+    np.savez_compressed(os.path.join(OUT, f"octo_cfg4_8x{n_elems}_seed{seed}.npz"), **out)
+    print("octo cfg4:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
+
+
 def gen_spline_forcing(seed=5):
     """The reference's `MuscleTorquesWithVaryingBetaSplines` (muscle_torques_with_bspline.py) driven directly,
     outside any env, to cover what SoftArmTracking-v0 does not: a finite max_rate_of_change_of_activation
@@ -394,6 +430,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "decentralized":
         gen_octo_flat_decentralized()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
+        gen_octo_cfg4()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "soft_arm":
         gen_soft_arm(game_mode=1)
         gen_soft_arm(game_mode=2)
@@ -406,6 +445,7 @@ if __name__ == "__main__":
     gen_arm_single()
     gen_octo_flat()
     gen_octo_flat_decentralized()
+    gen_octo_cfg4()
     gen_spline_forcing()
     gen_muscle_torques()
     gen_soft_arm(game_mode=1)

@@ -38,7 +38,9 @@ struct ro_rod {
   double *rest_sigma, *rest_kappa;
   /* derived (A.3) — refreshed only inside the force evaluation (A.6) */
   double *len, *tang, *dil, *vdil, *dil_rate, *sigma, *kappa;
-  double *stress, *couple, *f_int, *t_int, *f_ext, *t_ext, *f_user;
+  double *stress, *couple, *f_int, *t_int, *f_ext, *t_ext, *f_user, *t_user;
+  int n_sucker, sucker_idx[8];            /* ControllableFixConstraint: indices and ratios */
+  double sucker_ratio[8];
   /* plugins */
   double fixed_pos[3], fixed_Q[9];
   double c_v, *c_w;                      /* AnalyticalLinearDamper coefficients */
@@ -167,27 +169,30 @@ static void compute_internal_forces_and_torques(ro_rod *r) {
 }
 
 /* ---- A.2.1 kinematic half step */
+static void rotation_matrix(double v0, double v1, double v2, double R[3][3]) {
+  /* _get_rotation_matrix(1.0, axis): axis / (|axis| + 1e-14), Rodrigues, transpose convention */
+  double theta = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+  v0 /= theta + 1e-14; v1 /= theta + 1e-14; v2 /= theta + 1e-14;
+  theta = theta * 1.0;
+  double up = sin(theta), us = 1.0 - cos(theta);
+  R[0][0] = 1.0 - us * (v1 * v1 + v2 * v2);
+  R[1][1] = 1.0 - us * (v0 * v0 + v2 * v2);
+  R[2][2] = 1.0 - us * (v0 * v0 + v1 * v1);
+  R[0][1] = up * v2 + us * v0 * v1;
+  R[1][0] = -up * v2 + us * v0 * v1;
+  R[0][2] = -up * v1 + us * v0 * v2;
+  R[2][0] = up * v1 + us * v0 * v2;
+  R[1][2] = up * v0 + us * v1 * v2;
+  R[2][1] = -up * v0 + us * v1 * v2;
+}
+
 static void kinematic_step(ro_rod *r, double prefac) {
   const int n = r->n;
   for (int i = 0; i < 3; i++)
     for (int k = 0; k <= n; k++) X(i, k) += prefac * V(i, k);
   for (int k = 0; k < n; k++) {
-    double v0 = prefac * W(0, k), v1 = prefac * W(1, k), v2 = prefac * W(2, k);
-    double theta = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
-    v0 /= theta + 1e-14; v1 /= theta + 1e-14; v2 /= theta + 1e-14;
-    theta = theta * 1.0;
-    double up = sin(theta), us = 1.0 - cos(theta);
-    double R[3][3];
-    R[0][0] = 1.0 - us * (v1 * v1 + v2 * v2);
-    R[1][1] = 1.0 - us * (v0 * v0 + v2 * v2);
-    R[2][2] = 1.0 - us * (v0 * v0 + v1 * v1);
-    R[0][1] = up * v2 + us * v0 * v1;
-    R[1][0] = -up * v2 + us * v0 * v1;
-    R[0][2] = -up * v1 + us * v0 * v2;
-    R[2][0] = up * v1 + us * v0 * v2;
-    R[1][2] = up * v0 + us * v1 * v2;
-    R[2][1] = -up * v0 + us * v1 * v2;
-    double Qn[3][3];
+    double R[3][3], Qn[3][3];
+    rotation_matrix(prefac * W(0, k), prefac * W(1, k), prefac * W(2, k), R);
     for (int i = 0; i < 3; i++)
       for (int m = 0; m < 3; m++) {
         double s = 0.0;
@@ -496,24 +501,29 @@ static void apply_spline_torques(ro_rod *r) {
   }
 }
 
-/* ---- A.2 one PositionVerlet substep */
-static void substep(ro_rod *r, double action, const double *bp, const double *bv) {
-  const int n = r->n;
-  const double dt = r->cfg.dt, prefac = 0.5 * dt;
-  kinematic_step(r, prefac);
-  r->time += prefac;
+/* ---- A.2 one PositionVerlet substep, in the phases the multi-system stepper interleaves */
+static void phase_first_half(ro_rod *r, const double *bp) {
+  kinematic_step(r, 0.5 * r->cfg.dt);
+  r->time += 0.5 * r->cfg.dt;
   constrain_values(r, bp);
-  compute_internal_forces_and_torques(r);
-  /* synchronize: [contact] gravity, then point force (registration order, build.py:88-105) [contact] */
-  if (r->cfg.contact_on && r->cfg.contact_before_forcing) apply_contact(r);
+}
+
+static void phase_forcing(ro_rod *r, double action) {
+  /* forcings in registration order: gravity, then point force (build.py:88-105), muscle / spline torques */
+  const int n = r->n;
   for (int i = 0; i < 3; i++)
     for (int k = 0; k <= n; k++)
       r->f_ext[i * (n + 1) + k] += r->cfg.gravity[i] * r->mass[k] + r->f_user[i * (n + 1) + k];
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < n; k++) r->t_ext[i * n + k] += r->t_user[i * n + k];
   if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
   if (r->cfg.muscle_on) apply_muscle_torques(r);         /* a forcing, registered after gravity (continuum_snake.py:325-337) */
   if (r->cfg.spline_dir_mask) apply_spline_torques(r);   /* forcings (soft_arm_tracking.py:366-400) */
-  if (r->cfg.contact_on && !r->cfg.contact_before_forcing) apply_contact(r);
-  /* dynamic step */
+}
+
+static void phase_dynamic(ro_rod *r) {
+  const int n = r->n;
+  const double dt = r->cfg.dt;
   for (int i = 0; i < 3; i++)
     for (int k = 0; k <= n; k++)
       r->acc[i * (n + 1) + k] = (r->f_int[i * (n + 1) + k] + r->f_ext[i * (n + 1) + k]) / r->mass[k];
@@ -524,13 +534,43 @@ static void substep(ro_rod *r, double action, const double *bp, const double *bv
     for (int k = 0; k <= n; k++) V(i, k) += dt * r->acc[i * (n + 1) + k];
   for (int i = 0; i < 3; i++)
     for (int k = 0; k < n; k++) W(i, k) += dt * r->alpha[i * n + k];
-  if (r->cfg.damping_before_constraints) { dampen_rates(r); constrain_rates(r, bv); }
-  else { constrain_rates(r, bv); dampen_rates(r); }
-  kinematic_step(r, prefac);
-  r->time += prefac;
+}
+
+/* ControllableFixConstraint.constrain_rates (envs/octopus/controllable_constraint.py:46-69): rates of the
+ * listed node / element indices are scaled by (1 - ratio); FreeBC otherwise (no values constraint) */
+static void sucker_rates(ro_rod *r) {
+  const int n = r->n;
+  for (int q = 0; q < r->n_sucker; q++) {
+    const int idx = r->sucker_idx[q];
+    const double f = 1.0 - r->sucker_ratio[q];
+    for (int i = 0; i < 3; i++) { V(i, idx) *= f; W(i, idx) *= f; }
+  }
+}
+
+static void phase_rates(ro_rod *r, const double *bv) {
+  if (r->cfg.damping_before_constraints) { dampen_rates(r); constrain_rates(r, bv); sucker_rates(r); }
+  else { constrain_rates(r, bv); sucker_rates(r); dampen_rates(r); }
+}
+
+static void phase_second_half(ro_rod *r, const double *bp) {
+  const int n = r->n;
+  kinematic_step(r, 0.5 * r->cfg.dt);
+  r->time += 0.5 * r->cfg.dt;
   constrain_values(r, bp);
   memset(r->f_ext, 0, sizeof(double) * 3 * (size_t)(n + 1));
   memset(r->t_ext, 0, sizeof(double) * 3 * (size_t)n);
+}
+
+static void substep(ro_rod *r, double action, const double *bp, const double *bv) {
+  phase_first_half(r, bp);
+  compute_internal_forces_and_torques(r);
+  /* synchronize: [contact] forcings [contact] */
+  if (r->cfg.contact_on && r->cfg.contact_before_forcing) apply_contact(r);
+  phase_forcing(r, action);
+  if (r->cfg.contact_on && !r->cfg.contact_before_forcing) apply_contact(r);
+  phase_dynamic(r);
+  phase_rates(r, bv);
+  phase_second_half(r, bp);
 }
 
 void ro_substeps(ro_rod *r, int n_substeps, double action, const double *bp, const double *bv) {
@@ -555,7 +595,7 @@ ro_rod *ro_create(const ro_config *cfg) {
   r->len = zalloc(n); r->tang = zalloc(3 * n); r->dil = zalloc(n); r->vdil = zalloc(nv); r->dil_rate = zalloc(n);
   r->sigma = zalloc(3 * n); r->kappa = zalloc(3 * nv); r->stress = zalloc(3 * n); r->couple = zalloc(3 * nv);
   r->f_int = zalloc(3 * (n + 1)); r->t_int = zalloc(3 * n); r->f_ext = zalloc(3 * (n + 1)); r->t_ext = zalloc(3 * n);
-  r->f_user = zalloc(3 * (n + 1));
+  r->f_user = zalloc(3 * (n + 1)); r->t_user = zalloc(3 * n);
   r->c_w = zalloc(3 * n); r->filt = zalloc(3 * (n + 1)); r->tmp = zalloc(12 * (n + 1)); r->ctmp = zalloc(26 * n + 8);
 
   /* np.linspace(start, end, n+1): arange(n+1)*step + start, last point = end */
@@ -580,7 +620,12 @@ ro_rod *ro_create(const ro_config *cfg) {
     QQ(1, 0, k) = t[1] * nor[2] - t[2] * nor[1];
     QQ(1, 1, k) = t[2] * nor[0] - t[0] * nor[2];
     QQ(1, 2, k) = t[0] * nor[1] - t[1] * nor[0];
+    /* base_radius may be an array: np.linspace(base, tip, n_elem) (build_muscle_octopus.py:61-63) */
     double rad = cfg->base_radius;
+    if (cfg->tip_radius > 0.0 && n > 1) {
+      const double step = (cfg->tip_radius - cfg->base_radius) / (double)(n - 1);
+      rad = (k == n - 1) ? cfg->tip_radius : (double)k * step + cfg->base_radius;
+    }
     r->radius[k] = rad;
     double A0 = PI * rad * rad;
     double I1 = A0 * A0 / (4.0 * PI), I2 = I1, I3 = 2.0 * I2;
@@ -627,7 +672,7 @@ void ro_destroy(ro_rod *r) {
   double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
                     r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
                     r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
-                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag};
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->t_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
   free(r);
 }
@@ -644,6 +689,13 @@ double *ro_sigma(ro_rod *r) { return r->sigma; }
 double *ro_dilatation(ro_rod *r) { return r->dil; }
 double *ro_rest_kappa(ro_rod *r) { return r->rest_kappa; }
 double *ro_external_forces(ro_rod *r) { return r->f_user; }
+double *ro_external_torques(ro_rod *r) { return r->t_user; }
+void ro_set_sucker(ro_rod *r, int slot, int index, double ratio) {
+  if (slot < 0 || slot >= 8) return;
+  if (slot >= r->n_sucker) r->n_sucker = slot + 1;
+  r->sucker_idx[slot] = index < 0 ? index + r->n : index;   /* -1 = last element (python indexing on the element arrays) */
+  r->sucker_ratio[slot] = ratio;
+}
 double *ro_mass(ro_rod *r) { return r->mass; }
 double *ro_internal_forces(ro_rod *r) { return r->f_int; }
 double *ro_internal_torques(ro_rod *r) { return r->t_int; }
@@ -753,3 +805,150 @@ void ro_softpendulum_step_batch(ro_rod **rods, int n_env, const float *actions, 
   for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
   free(th); free(jobs);
 }
+
+/* ==== multi-system assembly: n_arm rods + rigid Cylinder head + FixedJoint2Rigid joints ===================
+ * Restates what PositionVerlet does over the systems assembled by
+ *   /root/reference/gym_softrobot/envs/octopus/build.py:52-217 (build_octopus)
+ * with the gym-softrobot plugins
+ *   /root/reference/gym_softrobot/utils/custom_elastica/joint.py:48-123 (forces), :125-219 (torques)
+ *   /root/reference/gym_softrobot/utils/custom_elastica/constraint.py:43-58 (values), :62-85 (rates)
+ * and PyElastica's Cylinder (same recalled inertia as oracle/shims/elastica/rigidbody.py).
+ * Operator order = the build code's call order (OperatorGroupFIFO): synchronize = [joint a: forces, torques
+ * (a = 0..n_arm-1), gravity per arm, contact per arm]; constrain_rates = [head BC, dampers per arm].
+ * Systems are stepped arms first, head last (append order). */
+struct ro_assembly {
+  ro_asm_config cfg;
+  int n_arm;
+  ro_rod *arm[RO_MAX_ARMS];
+  double time;
+  /* head: one node, one "element" */
+  double hx[3], hv[3], hQ[9], hw[3], hF[3], hT[3];
+  double h_mass, hJ[3], hJinv[3];
+  double h_fixed_pos[3];
+};
+
+static void head_kinematic(ro_assembly *a, double prefac) {
+  for (int i = 0; i < 3; i++) a->hx[i] += prefac * a->hv[i];
+  double R[3][3], Qn[9];
+  rotation_matrix(prefac * a->hw[0], prefac * a->hw[1], prefac * a->hw[2], R);
+  for (int i = 0; i < 3; i++)
+    for (int m = 0; m < 3; m++) {
+      double s = 0.0;
+      for (int j = 0; j < 3; j++) s += R[i][j] * a->hQ[j * 3 + m];
+      Qn[i * 3 + m] = s;
+    }
+  memcpy(a->hQ, Qn, sizeof(Qn));
+}
+
+static void head_constrain_values(ro_assembly *a) { /* constraint.py:43-58 */
+  a->hx[2] = a->h_fixed_pos[2];
+  a->hQ[6] = 0.0; a->hQ[7] = 0.0; a->hQ[8] = 1.0;
+  for (int i = 0; i < 2; i++) {
+    double len = sqrt(a->hQ[3 * i] * a->hQ[3 * i] + a->hQ[3 * i + 1] * a->hQ[3 * i + 1]);
+    for (int j = 0; j < 2; j++) a->hQ[3 * i + j] /= len;
+    a->hQ[3 * i + 2] = 0.0;
+  }
+}
+
+static void apply_joint(ro_assembly *a, int ai) {
+  ro_rod *r = a->arm[ai];
+  const int n = r->n;
+  const ro_asm_config *c = &a->cfg;
+  /* apply_forces (joint.py:48-68): rigid_rod_pos = head position with z := 0 */
+  double pos[3] = {a->hx[0], a->hx[1], 0.0};
+  /* z_rotation(binormal, angle) (joint.py:7-17): theta = angle / 180 * pi */
+  const double th = c->joint_angle_deg[ai] / 180.0 * PI;
+  const double cs = cos(th), sn = sin(th);
+  const double b[3] = {a->hQ[3], a->hQ[4], a->hQ[5]};   /* director_collection[1, :, -1] */
+  double dir[3] = {-(cs * b[0] + -sn * b[1] + 0.0 * b[2]), -(sn * b[0] + cs * b[1] + 0.0 * b[2]),
+                   -(0.0 * b[0] + 0.0 * b[1] + 1.0 * b[2])};
+  for (int i = 0; i < 3; i++) pos[i] += dir[i] * c->joint_radius;   /* rigid_rod_pos += connection point (in place) */
+  double d[3] = {X(0, 0) - pos[0], X(1, 0) - pos[1], X(2, 0) - pos[2]};
+  double dist = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  double nh[3] = {0.0, 0.0, 0.0};
+  if (!(dist <= 2.220446049250313e-16 * 1e4)) { nh[0] = d[0] / dist; nh[1] = d[1] / dist; nh[2] = d[2] / dist; }
+  double rel[3] = {V(0, 0) - a->hv[0], V(1, 0) - a->hv[1], V(2, 0) - a->hv[2]};
+  double rn = rel[0] * nh[0] + rel[1] * nh[1] + rel[2] * nh[2];
+  for (int i = 0; i < 3; i++) {
+    double cf = c->joint_k * d[i] + (-c->joint_nu * (rn * nh[i]));
+    a->hF[i] += cf;
+    r->f_ext[i * (n + 1) + 0] -= cf;
+  }
+  /* apply_torques (joint.py:125-219) with the mutated rigid_rod_pos */
+  double link[3] = {X(0, 1) - X(0, 0), X(1, 1) - X(1, 0), X(2, 1) - X(2, 0)};
+  double fd[3];
+  for (int i = 0; i < 3; i++) {
+    double tgt = pos[i] + r->rest_len[0] * dir[i];
+    fd[i] = -c->joint_kt * (X(i, 1) - tgt);
+  }
+  double tq[3] = {link[1] * fd[2] - link[2] * fd[1], link[2] * fd[0] - link[0] * fd[2], link[0] * fd[1] - link[1] * fd[0]};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      a->hT[i] -= a->hQ[3 * i + j] * tq[j];
+      r->t_ext[i * n + 0] += QQ(i, j, 0) * tq[j];
+    }
+}
+
+static void asm_substep(ro_assembly *a) {
+  const double dt = a->cfg.dt, prefac = 0.5 * dt;
+  for (int i = 0; i < a->n_arm; i++) phase_first_half(a->arm[i], NULL);   /* arms carry no BC of their own */
+  head_kinematic(a, prefac);
+  a->time += prefac;
+  if (a->cfg.has_head) head_constrain_values(a);
+  for (int i = 0; i < a->n_arm; i++) compute_internal_forces_and_torques(a->arm[i]);
+  if (a->cfg.has_head)
+    for (int i = 0; i < a->n_arm; i++) apply_joint(a, i);
+  for (int i = 0; i < a->n_arm; i++) phase_forcing(a->arm[i], 0.0);
+  for (int i = 0; i < a->n_arm; i++)
+    if (a->arm[i]->cfg.contact_on) apply_contact(a->arm[i]);
+  for (int i = 0; i < a->n_arm; i++) phase_dynamic(a->arm[i]);
+  {   /* rigid body: a = F/m ; alpha = J^-1 ((J w) x w + T) */
+    double Jw[3] = {a->hJ[0] * a->hw[0], a->hJ[1] * a->hw[1], a->hJ[2] * a->hw[2]};
+    double lt[3] = {Jw[1] * a->hw[2] - Jw[2] * a->hw[1], Jw[2] * a->hw[0] - Jw[0] * a->hw[2], Jw[0] * a->hw[1] - Jw[1] * a->hw[0]};
+    for (int i = 0; i < 3; i++) {
+      double acc = a->hF[i] / a->h_mass, alpha = a->hJinv[i] * (lt[i] + a->hT[i]);
+      a->hv[i] += dt * acc;
+      a->hw[i] += dt * alpha;
+    }
+  }
+  if (a->cfg.has_head) { a->hv[2] = 0.0; a->hw[0] = 0.0; a->hw[1] = 0.0; }   /* constraint.py:62-85 */
+  for (int i = 0; i < a->n_arm; i++) phase_rates(a->arm[i], NULL);
+  for (int i = 0; i < a->n_arm; i++) phase_second_half(a->arm[i], NULL);
+  head_kinematic(a, prefac);
+  a->time += prefac;
+  if (a->cfg.has_head) head_constrain_values(a);
+  for (int i = 0; i < 3; i++) { a->hF[i] = 0.0; a->hT[i] = 0.0; }
+}
+
+ro_assembly *ro_asm_create(const ro_config *arm_cfgs, const ro_asm_config *cfg) {
+  if (cfg->n_arm < 1 || cfg->n_arm > RO_MAX_ARMS) return NULL;
+  ro_assembly *a = (ro_assembly *)calloc(1, sizeof(ro_assembly));
+  a->cfg = *cfg;
+  a->n_arm = cfg->n_arm;
+  for (int i = 0; i < a->n_arm; i++) a->arm[i] = ro_create(&arm_cfgs[i]);
+  /* Cylinder(start, direction, normal, length, radius, density): centre of mass, rows normal / binormal / direction */
+  const double *s = cfg->head_start, *d = cfg->head_direction, *nm = cfg->head_normal;
+  for (int i = 0; i < 3; i++) a->hx[i] = s[i] + d[i] * cfg->head_length / 2;
+  for (int j = 0; j < 3; j++) { a->hQ[j] = nm[j]; a->hQ[6 + j] = d[j]; }
+  a->hQ[3] = d[1] * nm[2] - d[2] * nm[1]; a->hQ[4] = d[2] * nm[0] - d[0] * nm[2]; a->hQ[5] = d[0] * nm[1] - d[1] * nm[0];
+  const double A0 = PI * cfg->head_radius * cfg->head_radius, I1 = A0 * A0 / (4.0 * PI);
+  const double I0[3] = {I1, I1, 2.0 * I1};
+  a->h_mass = PI * cfg->head_radius * cfg->head_radius * cfg->head_length * cfg->head_density;
+  for (int i = 0; i < 3; i++) { a->hJ[i] = I0[i] * cfg->head_density * cfg->head_length; a->hJinv[i] = 1.0 / a->hJ[i]; }
+  for (int i = 0; i < 3; i++) a->h_fixed_pos[i] = a->hx[i];   /* B-7: copy at finalize */
+  if (cfg->has_head) { head_constrain_values(a); a->hv[2] = 0.0; a->hw[0] = 0.0; a->hw[1] = 0.0; }
+  return a;
+}
+
+void ro_asm_destroy(ro_assembly *a) {
+  if (!a) return;
+  for (int i = 0; i < a->n_arm; i++) ro_destroy(a->arm[i]);
+  free(a);
+}
+void ro_asm_substeps(ro_assembly *a, int n_substeps) { for (int s = 0; s < n_substeps; s++) asm_substep(a); }
+ro_rod *ro_asm_arm(ro_assembly *a, int i) { return (i >= 0 && i < a->n_arm) ? a->arm[i] : NULL; }
+double ro_asm_time(const ro_assembly *a) { return a->time; }
+double *ro_asm_head_position(ro_assembly *a) { return a->hx; }
+double *ro_asm_head_velocity(ro_assembly *a) { return a->hv; }
+double *ro_asm_head_director(ro_assembly *a) { return a->hQ; }
+double *ro_asm_head_omega(ro_assembly *a) { return a->hw; }

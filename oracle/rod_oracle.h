@@ -42,6 +42,9 @@ typedef struct {
    * spline_dir_mask = one forcing instance on material direction d (0 normal, 1 binormal, 2 tangent). */
   int spline_dir_mask, spline_n_ctrl;
   double spline_scale, spline_max_rate;
+  /* tapered rod: base_radius array = np.linspace(base_radius, tip_radius, n_elem)
+   * (/root/reference/gym_softrobot/envs/octopus/build_muscle_octopus.py:61-63); <= 0: uniform */
+  double tip_radius;
 } ro_config;
 
 typedef struct ro_rod ro_rod;
@@ -65,6 +68,10 @@ double *ro_sigma(ro_rod *);
 double *ro_dilatation(ro_rod *);
 double *ro_rest_kappa(ro_rod *);
 double *ro_external_forces(ro_rod *); /* (3,n+1) constant extra nodal load added every substep */
+double *ro_external_torques(ro_rod *); /* (3,n) constant extra element couple (material frame) added every substep */
+/* ControllableFixConstraint (/root/reference/gym_softrobot/envs/octopus/controllable_constraint.py:42-69):
+ * after the dynamic step, v[:, index] and omega[:, index] are scaled by (1 - ratio); up to 8 slots */
+void ro_set_sucker(ro_rod *, int slot, int index, double ratio);
 double *ro_mass(ro_rod *);
 double *ro_internal_forces(ro_rod *);
 double *ro_internal_torques(ro_rod *);
@@ -85,6 +92,28 @@ void ro_softpendulum_step_batch(ro_rod **rods, int n_env, const float *actions, 
                                 double final_time, float *obs, double *reward, int *terminated,
                                 int *truncated, int n_threads);
 int ro_max_threads(void);
+
+/* ---- multi-rod assembly (octopus): n_arm rods + rigid Cylinder head + FixedJoint2Rigid joints + BodyBoundaryCondition
+ * (/root/reference/gym_softrobot/envs/octopus/build.py:52-217, utils/custom_elastica/joint.py, constraint.py) */
+#define RO_MAX_ARMS 16
+typedef struct {
+  int n_arm, has_head;
+  double dt;
+  double head_start[3], head_direction[3], head_normal[3];
+  double head_length, head_radius, head_density;
+  double joint_k, joint_nu, joint_kt, joint_radius;
+  double joint_angle_deg[RO_MAX_ARMS];
+} ro_asm_config;
+typedef struct ro_assembly ro_assembly;
+ro_assembly *ro_asm_create(const ro_config *arm_cfgs /* [n_arm] */, const ro_asm_config *cfg);
+void ro_asm_destroy(ro_assembly *);
+void ro_asm_substeps(ro_assembly *, int n_substeps);
+ro_rod *ro_asm_arm(ro_assembly *, int i);   /* owned by the assembly */
+double ro_asm_time(const ro_assembly *);
+double *ro_asm_head_position(ro_assembly *);  /* (3) */
+double *ro_asm_head_velocity(ro_assembly *);  /* (3) */
+double *ro_asm_head_director(ro_assembly *);  /* (3,3) rows */
+double *ro_asm_head_omega(ro_assembly *);     /* (3) */
 
 #ifdef __cplusplus
 }

@@ -55,6 +55,29 @@ class ROConfig(C.Structure):
         ("spline_n_ctrl", C.c_int),
         ("spline_scale", C.c_double),
         ("spline_max_rate", C.c_double),
+        ("tip_radius", C.c_double),
+    ]
+
+
+RO_MAX_ARMS = 16
+
+
+class ROAsmConfig(C.Structure):
+    _fields_ = [
+        ("n_arm", C.c_int),
+        ("has_head", C.c_int),
+        ("dt", C.c_double),
+        ("head_start", C.c_double * 3),
+        ("head_direction", C.c_double * 3),
+        ("head_normal", C.c_double * 3),
+        ("head_length", C.c_double),
+        ("head_radius", C.c_double),
+        ("head_density", C.c_double),
+        ("joint_k", C.c_double),
+        ("joint_nu", C.c_double),
+        ("joint_kt", C.c_double),
+        ("joint_radius", C.c_double),
+        ("joint_angle_deg", C.c_double * RO_MAX_ARMS),
     ]
 
 
@@ -83,7 +106,8 @@ def lib():
         L.ro_time.argtypes = [C.c_void_p]
         for name in ("position", "velocity", "director", "omega", "tangents", "kappa", "sigma",
                      "dilatation", "rest_kappa", "external_forces", "mass", "internal_forces",
-                     "internal_torques", "radius", "muscle", "spline_points", "spline_magnitude"):
+                     "internal_torques", "radius", "muscle", "spline_points", "spline_magnitude",
+                     "external_torques"):
             f = getattr(L, "ro_" + name)
             f.restype = C.POINTER(C.c_double)
             f.argtypes = [C.c_void_p]
@@ -95,6 +119,19 @@ def lib():
                                                  C.c_double, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_int]
         L.ro_max_threads.restype = C.c_int
+        L.ro_set_sucker.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.ro_asm_create.restype = C.c_void_p
+        L.ro_asm_create.argtypes = [C.POINTER(ROConfig), C.POINTER(ROAsmConfig)]
+        L.ro_asm_destroy.argtypes = [C.c_void_p]
+        L.ro_asm_substeps.argtypes = [C.c_void_p, C.c_int]
+        L.ro_asm_arm.restype = C.c_void_p
+        L.ro_asm_arm.argtypes = [C.c_void_p, C.c_int]
+        L.ro_asm_time.restype = C.c_double
+        L.ro_asm_time.argtypes = [C.c_void_p]
+        for name in ("position", "velocity", "director", "omega"):
+            f = getattr(L, "ro_asm_head_" + name)
+            f.restype = C.POINTER(C.c_double)
+            f.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -102,12 +139,14 @@ def lib():
 class OracleRod:
     """One Cosserat rod stepped by the C oracle; arrays are NumPy views (reference layout)."""
 
-    def __init__(self, n_elem, start, direction, normal, base_length, base_radius, density,
-                 youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
-                 gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
-                 bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=False,
-                 contact=None, muscle=None, spline=None):
+    @staticmethod
+    def _make_config(n_elem, start, direction, normal, base_length, base_radius, density,
+                     youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
+                     gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
+                     bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=False,
+                     contact=None, muscle=None, spline=None, tip_radius=0.0):
         cfg = ROConfig()
+        cfg.tip_radius = float(tip_radius)
         cfg.n_elem = n_elem
         cfg.start[:] = list(map(float, start))
         cfg.direction[:] = list(map(float, direction))
@@ -139,9 +178,14 @@ class OracleRod:
             cfg.spline_dir_mask = sum(1 << int(d) for d in spline["directions"])
             cfg.spline_n_ctrl = spline["n_ctrl"]
             cfg.spline_scale, cfg.spline_max_rate = spline["scale"], spline.get("max_rate", float("inf"))
+        return cfg
+
+    def __init__(self, n_elem, *args, _handle=None, **kwargs):
+        cfg = self._make_config(n_elem, *args, **kwargs)
         self.cfg = cfg
         self.n = n_elem
-        self._h = C.c_void_p(lib().ro_create(C.byref(cfg)))
+        self._owned = _handle is None
+        self._h = C.c_void_p(lib().ro_create(C.byref(cfg))) if _handle is None else C.c_void_p(_handle)
         n = n_elem
         self.position_collection = self._view("position", (3, n + 1))
         self.velocity_collection = self._view("velocity", (3, n + 1))
@@ -153,6 +197,7 @@ class OracleRod:
         self.dilatation = self._view("dilatation", (n,))
         self.rest_kappa = self._view("rest_kappa", (3, n - 1))
         self.user_forces = self._view("external_forces", (3, n + 1))
+        self.user_torques = self._view("external_torques", (3, n))   # material frame, added every substep
         self.mass = self._view("mass", (n + 1,))
         self.internal_forces = self._view("internal_forces", (3, n + 1))
         self.internal_torques = self._view("internal_torques", (3, n))
@@ -176,9 +221,69 @@ class OracleRod:
         lib().ro_substeps(self._h, int(n), float(action),
                           None if bp is None else bp.ctypes.data, None if bv is None else bv.ctypes.data)
 
+    def set_sucker(self, slot, index, ratio):
+        """ControllableFixConstraint(index, reduction_ratio) in slot `slot` (ratio 0 = released)."""
+        lib().ro_set_sucker(self._h, int(slot), int(index), float(ratio))
+
     def close(self):
         if self._h:
-            lib().ro_destroy(self._h)
+            if self._owned:
+                lib().ro_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class OracleAssembly:
+    """n_arm rods + rigid Cylinder head + FixedJoint2Rigid joints + BodyBoundaryCondition on the C oracle
+    (reference envs/octopus/build.py:52-217 topology).  `arm_kwargs` are OracleRod keyword sets (one per arm)."""
+
+    def __init__(self, arm_kwargs, dt, head=None, joint=None, angles_deg=None):
+        n_arm = len(arm_kwargs)
+        assert 1 <= n_arm <= RO_MAX_ARMS
+        self._cfg_holders = []
+        cfgs = (ROConfig * n_arm)()
+        for i, kw in enumerate(arm_kwargs):
+            cfgs[i] = OracleRod._make_config(dt=dt, **kw)
+        ac = ROAsmConfig()
+        ac.n_arm, ac.dt = n_arm, dt
+        ac.has_head = int(head is not None)
+        if head is not None:   # dict: start, direction, normal, length, radius, density
+            ac.head_start[:] = list(map(float, head["start"]))
+            ac.head_direction[:] = list(map(float, head["direction"]))
+            ac.head_normal[:] = list(map(float, head["normal"]))
+            ac.head_length, ac.head_radius, ac.head_density = head["length"], head["radius"], head["density"]
+            ac.joint_k, ac.joint_nu, ac.joint_kt, ac.joint_radius = joint["k"], joint["nu"], joint["kt"], joint["radius"]
+            for i, a in enumerate(angles_deg):
+                ac.joint_angle_deg[i] = float(a)
+        else:   # keep the (unused) rigid body well defined
+            ac.head_direction[:] = [0.0, 0.0, 1.0]
+            ac.head_normal[:] = [0.0, 1.0, 0.0]
+            ac.head_length = ac.head_radius = ac.head_density = 1.0
+        self._h = C.c_void_p(lib().ro_asm_create(cfgs, C.byref(ac)))
+        assert self._h
+        self.arms = [OracleRod(dt=dt, _handle=lib().ro_asm_arm(self._h, i), **kw) for i, kw in enumerate(arm_kwargs)]
+        hv = lambda name, shape: np.ctypeslib.as_array(getattr(lib(), "ro_asm_head_" + name)(self._h),
+                                                       shape=(int(np.prod(shape)),)).reshape(shape)
+        self.head_position, self.head_velocity = hv("position", (3,)), hv("velocity", (3,))
+        self.head_director, self.head_omega = hv("director", (3, 3)), hv("omega", (3,))
+
+    @property
+    def time(self):
+        return lib().ro_asm_time(self._h)
+
+    def substeps(self, n):
+        lib().ro_asm_substeps(self._h, int(n))
+
+    def close(self):
+        if self._h:
+            for a in self.arms:
+                a.close()
+            lib().ro_asm_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -288,3 +393,30 @@ class OracleSoftPendulum3D:
             reward = -50.0
         t = self.rod.time
         return self.get_state(), reward, invalid, bool(t >= self.final_time), {"time": np.float64(t), "tilt": tilt}
+
+
+def octopus_assembly(n_arm=8, n_elem=10, time_step=7e-5, head_radius=0.04, head_density=700.0,
+                     body_arm_k=1e6, body_arm_kt=1.0, body_arm_nu=1e-3, friction_multiplier=1.0,
+                     base_length=0.35, base_radius=0.35 * 0.02, youngs_modulus=1e6, density=1000.0):
+    """The systems `build_octopus` assembles (reference envs/octopus/build.py:52-217), on the C oracle:
+    n_arm arms at 360/n_arm degrees around a rigid Cylinder head, FixedJoint2Rigid joints, gravity and
+    AnalyticalLinearDamper(1e-2) on the arms, anisotropic plane friction under each arm."""
+    L0, r0 = base_length, base_radius
+    g = -9.81
+    mu = L0 / (2.0 * 2.0 * abs(g) * 0.1)
+    kinetic = np.array([mu, 1.5 * mu, 2.0 * mu]) * friction_multiplier
+    contact = dict(plane_origin=(0.0, 0.0, -r0), plane_normal=(0.0, 0.0, 1.0), k=1e2, nu=1e1,
+                   slip_velocity_tol=1e-8, static_mu=2 * kinetic, kinetic_mu=kinetic)
+    angles = [360 / n_arm * i for i in range(n_arm)]
+    arms = []
+    for ang in angles:
+        # scipy Rotation.from_euler("z", ang, degrees=True).apply(v) for v along x
+        c, s = np.cos(np.deg2rad(ang)), np.sin(np.deg2rad(ang))
+        arms.append(dict(n_elem=n_elem, start=(c * head_radius, s * head_radius, 0.0), direction=(c, s, 0.0),
+                         normal=(0.0, 0.0, 1.0), base_length=L0, base_radius=r0, density=density,
+                         youngs_modulus=youngs_modulus, gravity=(0.0, 0.0, g), damping_constant=1e-2,
+                         contact=contact))
+    head = dict(start=(0.0, 0.0, -r0), direction=(0.0, 0.0, 1.0), normal=(0.0, 1.0, 0.0), length=2 * r0,
+                radius=head_radius, density=head_density)
+    joint = dict(k=body_arm_k, nu=body_arm_nu, kt=body_arm_kt, radius=head_radius)
+    return OracleAssembly(arms, time_step, head=head, joint=joint, angles_deg=angles)

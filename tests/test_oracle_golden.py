@@ -258,3 +258,55 @@ def test_c_oracle_spline_torques_match_reference_forcing_fixture(golden_dir):
             assert err < 1e-9 * float(np.abs(ref).max()), (s, name, err, float(np.abs(ref).max()))
     assert np.all(rod.spline_magnitude[1] == 0.0) and np.abs(rod.spline_magnitude[0]).max() > 0.0
     rod.close()
+
+
+ASM_FIELDS = dict(FIELDS, kappa="kappa", sigma="sigma", dilatation="dilatation")
+# Scale floors: a field is compared relative to max(|ref|) over the arm, but not below the magnitude it reaches
+# once the arm is actuated (a straight arm at rest has kappa, sigma, v, omega of pure round-off size).
+ASM_FLOOR = dict(position=1e-2, velocity=1e-3, director=1.0, omega=1e-2, tangents=1.0, kappa=1.0, sigma=1e-3,
+                 dilatation=1.0)
+
+
+def _check_assembly(asm, g, tag, tol):
+    worst = 0.0
+    for a, rod in enumerate(asm.arms):
+        for gk, fk in ASM_FIELDS.items():
+            ref = g[f"{tag}/arm{a}/{gk}"]
+            err = float(np.abs(getattr(rod, fk) - ref).max() / max(np.abs(ref).max(), ASM_FLOOR[gk]))
+            worst = max(worst, err)
+            assert err < tol, (tag, a, gk, err)
+    for gk, mine in (("position", asm.head_position), ("velocity", asm.head_velocity),
+                     ("director", asm.head_director), ("omega", asm.head_omega)):
+        ref = g[f"{tag}/head/{gk}"].reshape(mine.shape)
+        err = float(np.abs(mine - ref).max() / max(np.abs(ref).max(), ASM_FLOOR[gk]))
+        worst = max(worst, err)
+        assert err < tol, (tag, "head", gk, err)
+    return worst
+
+
+@pytest.mark.parametrize("fixture,n_elem,dt", [("octo_flat_seed42.npz", 10, 7e-5), ("octo_cfg4_8x40_seed42.npz", 40, 3e-5)])
+def test_c_oracle_assembly_matches_reference_octopus_fixture(golden_dir, fixture, n_elem, dt):
+    """Multi-rod C oracle (arms + Cylinder head + FixedJoint2Rigid + BodyBoundaryCondition + plane friction) vs
+    fixtures produced by the reference's own build_octopus / FlatEnv / joint.py / constraint.py on the shim."""
+    g = np.load(os.path.join(golden_dir, fixture))
+    asm = ro.octopus_assembly(n_arm=8, n_elem=n_elem, time_step=dt)
+    _check_assembly(asm, g, "state0", 1e-12)
+    skip = int(g["step_skip"])
+    if "rest_kappa" in g.files:
+        rks = g["rest_kappa"]
+    else:   # the older fixture stores actions only: FlatEnv.set_action (flat_env.py:288-311)
+        from scipy.interpolate import interp1d
+        rks = []
+        for a in g["actions"]:
+            k = np.concatenate([np.zeros((8, 1)), a.reshape(8, 3), np.zeros((8, 1))], axis=-1)
+            k = interp1d(np.linspace(0, 1, 5), k, kind="cubic", axis=-1)(np.linspace(0, 1, n_elem - 1))
+            rk = np.zeros((8, 3, n_elem - 1)); rk[:, 0, :] = k
+            rks.append(rk)
+    worst = 0.0
+    for i, rk in enumerate(rks):
+        for a, rod in enumerate(asm.arms):
+            rod.rest_kappa[...] = rk[a]
+        asm.substeps(skip)
+        worst = max(worst, _check_assembly(asm, g, f"state{i + 1}", 1e-9))
+    print("assembly oracle vs shim fixture: worst", worst)
+    asm.close()
