@@ -941,3 +941,119 @@ def test_spline_torques_vs_c_oracle_randomized(seed):
         for d in dirs:
             np.testing.assert_allclose(mags[1, d].cpu().numpy(), o.spline_magnitude[d], rtol=1e-9, atol=1e-12 * spl["scale"])
     h.close(); o.close()
+
+
+# ---- multi-rod assemblies against the multi-rod C oracle ------------------------------------
+# Scale floors of the assembly comparisons: a field is compared relative to max|ref| over the arm, but not below
+# the magnitude it has once the arm is actuated (a straight arm at rest holds kappa / sigma / rates of pure
+# round-off size, where "relative" is meaningless).  Same table as tests/test_oracle_golden.py.
+ASM_FLOOR = dict(position_collection=1e-2, velocity_collection=1e-3, director_collection=1.0, omega_collection=1e-2,
+                 tangents=1.0, kappa=1.0, sigma=1e-3, dilatation=1.0)
+
+
+def _asm_err(mine, ref, key):
+    return float(np.abs(mine - ref).max() / max(np.abs(ref).max(), ASM_FLOOR[key]))
+
+
+def test_octo_cfg4_8x40_vs_reference_fixture(golden_dir):
+    """BASELINE config 4 as specified — build_octopus(n_arm=8, n_elem=40) (envs/octopus/build.py:52-217) under
+    FlatEnv actuation — at the dt that is stable for 40 elements (3e-5), 3 x 333 = 999 substeps, every field
+    (kappa, sigma, dilatation included) at 1e-9 against the fixture the reference's own env / joint / constraint
+    code produced on the shim (oracle/gen_golden.py:gen_octo_cfg4)."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "octo_cfg4_8x40_seed42.npz"))
+    env = gsb.make("OctoFlat-v0", n_elems=int(g["n_elems"]), time_step=float(g["time_step"]),
+                   recording_fps=int(g["recording_fps"]))
+    assert env.step_skip == int(g["step_skip"]) == 333
+    env.reset(seed=42)
+    np.testing.assert_allclose(env._target, g["target"], rtol=0, atol=0)
+    worst = 0.0
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        st = env.state()
+        # the host-side interpolation matrix reproduces what the reference's set_action wrote
+        rk = env._vec.handle.rest_kappa_tensor().cpu().numpy()
+        assert np.abs(rk - g["rest_kappa"][i]).max() < 1e-12 * np.abs(g["rest_kappa"][i]).max()
+        for arm in range(8):
+            for gk, fk in FIELDS.items():
+                err = _asm_err(st[fk][arm], g[f"state{i + 1}/arm{arm}/{gk}"], fk)
+                worst = max(worst, err)
+                assert err < TOL, f"step {i} arm {arm} {gk}: {err:.3e}"
+        hd = st["head"]
+        for sl, gk, fk in ((slice(0, 3), "position", "position_collection"), (slice(3, 6), "velocity", "velocity_collection"),
+                           (slice(6, 15), "director", "director_collection"), (slice(15, 18), "omega", "omega_collection")):
+            err = _asm_err(hd[sl], g[f"state{i + 1}/head/{gk}"].reshape(-1), fk)
+            worst = max(worst, err)
+            assert err < TOL, f"step {i} head {gk}: {err:.3e}"
+        assert abs(r - float(g["reward"][i])) < 1e-6 and te == bool(g["terminated"][i])
+    print(f"cfg4 8x40 vs reference fixture: worst {worst:.2e}")
+    env.close()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_randomized_assembly_vs_c_oracle(seed):
+    """Arms + rigid head + FixedJoint2Rigid + BodyBoundaryCondition + plane friction with per-seed arm count, element
+    count, joint stiffness / damping / torsional stiffness, head size and density and per-arm rest curvature, against
+    the multi-rod C oracle (oracle/rod_oracle.c: ro_assembly): 1e-9 on every field over 900 substeps."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    rng = np.random.default_rng(1000 + seed)
+    n_arm = int(rng.integers(2, 9))
+    n_elem = [8, 10, 13, 20, 31, 40][seed]   # every seed a different element count, 40 (config 4) included
+    L0, r0 = 0.35, 0.35 * 0.02
+    head_radius, head_density = float(rng.uniform(0.03, 0.06)), float(rng.uniform(300, 900))
+    kt, nu = float(10 ** rng.uniform(-1, 2)), float(10 ** rng.uniform(-4, -2))
+    # explicit stability of the joint spring on the half-mass end node: dt < 2 sqrt(m / k), keep a factor 3
+    m_end = 0.5 * 1000.0 * np.pi * r0 * r0 * L0 / n_elem
+    k = float(10 ** rng.uniform(4.5, 6))
+    dt = float(min(7e-5, 2 * np.sqrt(m_end / k) / 3, 0.25 * (L0 / n_elem) / np.sqrt(1e6 / 1000.0)))
+    asm = ro.octopus_assembly(n_arm=n_arm, n_elem=n_elem, time_step=dt, head_radius=head_radius, head_density=head_density,
+                              body_arm_k=k, body_arm_kt=kt, body_arm_nu=nu)
+    from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
+    n_env = 3
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elem, dt=dt, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
+                   bc_kind=nat.BC_FREE, contact=arm_contact_params(), n_rod=n_arm,
+                   head=dict(length=2 * r0, radius=head_radius, density=head_density),
+                   joint=dict(radius=head_radius, angles_deg=[360 / n_arm * a for a in range(n_arm)], k=k, nu=nu, kt=kt),
+                   **_ROD)
+    row = []
+    for a in range(n_arm):
+        c, s = np.cos(np.deg2rad(360 / n_arm * a)), np.sin(np.deg2rad(360 / n_arm * a))
+        row += [c * head_radius, s * head_radius, 0.0, c, s, 0.0, 0.0, 0.0, 1.0]
+    row += [0.0, 0.0, -r0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0]
+    h.reset(torch.as_tensor(np.repeat(np.array([row]), n_env, axis=0), device="cuda").contiguous())
+    o6 = torch.empty((n_env, 6), dtype=torch.float32, device="cuda")
+    rew = torch.empty(n_env, dtype=torch.float64, device="cuda")
+    term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+    worst = 0.0
+    for chunk in range(3):
+        # smooth random rest curvature about d1 and a little about d2 (flat_env actuates d1 only), per arm
+        s = np.linspace(0, 1, n_elem - 1)
+        rk = np.zeros((n_arm, 3, n_elem - 1))
+        for a in range(n_arm):
+            rk[a, 0] = rng.uniform(-12, 12) * np.sin(np.pi * s) + rng.uniform(-6, 6) * np.sin(2 * np.pi * s)
+            rk[a, 1] = rng.uniform(-3, 3) * np.sin(np.pi * s)
+        h.rest_kappa_tensor().unflatten(0, (n_env, n_arm))[:] = torch.as_tensor(rk, device="cuda")
+        for a, rod in enumerate(asm.arms):
+            rod.rest_kappa[...] = rk[a]
+        h.step(None, 300, o6, rew, term)
+        asm.substeps(300)
+        f = {k_: v.cpu().numpy() for k_, v in h.fields().items()}
+        if n_arm == 1:
+            f = {k_: v[:, None] for k_, v in f.items()}
+        hd = h.head_tensor().cpu().numpy()
+        assert int(term.sum()) == 0
+        for e in range(n_env):
+            for a, rod in enumerate(asm.arms):
+                for fk in FIELDS.values():
+                    err = _asm_err(f[fk][e, a], getattr(rod, fk), fk)
+                    worst = max(worst, err)
+                    assert err < TOL, f"seed {seed} (n_arm {n_arm}, n_elem {n_elem}, k {k:.2e}) chunk {chunk} env {e} arm {a} {fk}: {err:.3e}"
+            for sl, mine, fk in ((slice(0, 3), asm.head_position, "position_collection"), (slice(3, 6), asm.head_velocity, "velocity_collection"),
+                                 (slice(6, 15), asm.head_director.reshape(-1), "director_collection"), (slice(15, 18), asm.head_omega, "omega_collection")):
+                err = _asm_err(hd[e, sl], mine, fk)
+                worst = max(worst, err)
+                assert err < TOL, f"seed {seed} chunk {chunk} head {fk}: {err:.3e}"
+    print(f"randomized assembly seed {seed}: n_arm {n_arm} n_elem {n_elem} dt {dt:.2e} worst {worst:.2e}")
+    h.close(); asm.close()
