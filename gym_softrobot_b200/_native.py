@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals",
+    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
 ]
 
 
@@ -141,6 +141,15 @@ def selftest_reciprocals(n=1 << 20, lo=1e-12, hi=1e12, device=0):
     out = (C.c_double * 2)()
     _check(lib.sr_selftest_reciprocals(device, n, lo, hi, out))
     return out[0], out[1]
+
+
+def probe_latency(device=0):
+    """dict of dependent-issue latencies in cycles (sr_probe_latency)."""
+    lib = load_library()
+    lib.sr_probe_latency.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    out = (C.c_double * 8)()
+    _check(lib.sr_probe_latency(device, out))
+    return {"dfma": out[0], "dadd": out[1], "mufu_rsq64h+dfma": out[2], "sts_bar_lds_bar": out[3], "dfma_imm": out[4]}
 
 
 def measure_fp64_peak(device: int = 0, three_register_operands: bool = False) -> float:

@@ -1,0 +1,22 @@
+// launch.cuh — host-callable launchers of the kernel instantiations.  Every (type, CTA size, feature set) is
+// compiled in its own translation unit (inst_*.cu, selected by -D macros from build.py) so that the library
+// builds in parallel; softrod_api.cu sees declarations only.
+#pragma once
+#include <cuda_runtime.h>
+#include "rod_kernels.cuh"
+
+namespace sr {
+
+// generic CTA-packed kernel (rod_kernel_packed.cuh); opts the dynamic shared memory in on the current device
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY>
+cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid, cudaStream_t s);
+
+// lean FP64 kernel (rod_kernel_lean.cuh); grid / split schedule are in A.sk_*
+template <int NT, int MINB, bool FASTONLY> cudaError_t launch_lean_kernel(const RodArgs<double> &A, int grid, cudaStream_t s);
+// resident CTAs per SM of that instantiation on the current device (sizes the stream-K grid)
+template <int NT, int MINB, bool FASTONLY> int lean_ctas_per_sm();
+
+// warp-per-rod kernel, faithful (libm, reference operation order) math: the parity build
+template <typename T, int EPL> cudaError_t launch_warp_faithful(const RodArgs<T> &A, int grid, cudaStream_t s);
+
+}  // namespace sr

@@ -1,0 +1,465 @@
+// rod_kernel_lean.cuh — the headline kernel: FP64, single rod per env, no contact / filter / joints / forcing
+// (SoftPendulum-v0 and plain rods: BASELINE configs 2 and 3), sm_100a.
+//
+// Same mapping as rod_kernel_packed.cuh (one thread per node/element, rods packed back to back across a
+// 256-thread CTA, state in registers for the whole launch, neighbour data through array-of-structures
+// records in shared memory, two CTA barriers per substep), with two things the generic kernel does not have:
+//
+// 1. Work is dealt to the SMs by substep count, not by CTA (stream-K style).  A launch is n_items x K
+//    "item-substeps" (item = the rods one CTA holds).  When there are more items than resident CTA slots the
+//    grid is exactly the resident slot count and slot p owns the contiguous range [p W/P, (p+1) W/P) of the
+//    item-major linear index: a few whole items plus at most one item shared with slot p-1 and one shared with
+//    slot p+1.  A slot runs the part it shares with its successor FIRST (substeps 0..a of that item, no
+//    dependency), hands the 18 integrated values per thread over through global scratch + a flag, runs its
+//    whole items, and finishes with the part it shares with its predecessor (substeps b..K-1), whose input has
+//    long been published by then.  Every slot therefore executes the same number of substeps (+-1) and the
+//    2.77-wave tail of 4096 envs on 296 slots disappears.  Arithmetic is unchanged by the split: the registers
+//    that would have stayed live are stored and re-loaded bit for bit.
+//
+// 2. The arithmetic is trimmed to what a uniform rod with a circular cross-section needs (every rod the
+//    reference builds: CosseratRod.straight_rod, /root/reference/gym_softrobot/envs/soft_pendulum/build.py:54-61):
+//    J1 = J2, B1 = B2, S1 = S2 make (J w) x w, kappa x (B kappa) and (Q t) x n two-term expressions; the
+//    log-map factor theta/sin(theta) is a polynomial in |axial(R - R^T)|^2 (no trace needed); the rotational
+//    damper c_w^e is a cubic in (e - 1) with host-made coefficients; range checks run on the integer pipe.
+//
+// Range handling (both variants compute bit-identical results for every thread whose arguments are in range):
+//   FASTONLY = true : no fallback code; a thread that leaves the range flags its env, whose state is then not
+//                     written back and which the safe variant re-runs (redo[]).
+//   FASTONLY = false: per-thread fallback to the libm-class reference maps (never a warp vote: an env's bits
+//                     must not depend on which other envs share its warps).
+//
+// Algorithm: SURVEY.md Appendix A.2/A.3; reference boundary
+// /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:183-184.
+#pragma once
+#include "rod_kernels.cuh"
+
+namespace sr {
+
+// high word of a double as an ordered integer (x >= 0): range tests on the integer pipe instead of DSETP.
+// NaN compares as "large" (0x7ff8....), i.e. out of range, which is what the callers want.
+__device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+
+constexpr int LEAN_REC = 18;        // exchange record per thread (doubles), 144-byte stride: conflict-free LDS.128
+constexpr int lean_smem_words(int nt) { return (LEAN_REC + 6) * (nt + 2); }
+
+template <int NT, int MINB, bool FASTONLY>
+__global__ void __launch_bounds__(NT, MINB)
+rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
+  using T = double;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T *rec = reinterpret_cast<T *>(smem_raw);            // {x0 x1 | x2 v0 | v1 v2 | Q0 Q1 | ... | Q6 Q7 | Q8 - | - -}
+  T *sn = rec + LEAN_REC * (NT + 2);                   // {s0 s1 | s2 N0 | N1 m2}; record NT = zeros (left of element 0)
+  __shared__ int sh_flag[256], sh_dom[256];   // one per rod of the CTA (<= NT / 4)
+
+  const int tid = threadIdx.x;
+  const int n = A.n_elem, stride = A.stride, tpr = n + 1;
+  const int rods_per_cta = A.sk_rods_per_cta;
+  const int r = tid / tpr, j = tid - r * tpr;
+  const bool in_cta = r < rods_per_cta;
+  const bool first = (j == 0);
+  if (tid < 6) sn[6 * NT + tid] = T(0);
+
+  // Barriers: data only crosses threads of the same rod, so a substep's two synchronisations can be per rod
+  // (named barriers over the warps that hold the rod's threads; a warp holding the end of one rod and the start of
+  // the next takes part in both, in rod order) instead of CTA-wide: rods then drift apart and fill each other's
+  // pipeline bubbles.  Needs tpr >= 32 (a warp touches at most two rods) and <= 15 rods per CTA (barrier ids 1..15).
+  int bar_id0 = 0, bar_cnt0 = 0, bar_id1 = 0, bar_cnt1 = 0;
+  const bool rod_barriers = A.sk_rodsync && tpr >= 32 && rods_per_cta <= 15;
+  if (rod_barriers) {
+    const int wp = tid >> 5;
+    for (int rr = 0; rr < rods_per_cta; rr++) {
+      const int wa = (rr * tpr) >> 5, wb = (rr * tpr + tpr - 1) >> 5;
+      if (wp >= wa && wp <= wb) {
+        if (bar_cnt0 == 0) { bar_id0 = rr + 1; bar_cnt0 = 32 * (wb - wa + 1); }
+        else { bar_id1 = rr + 1; bar_cnt1 = 32 * (wb - wa + 1); }
+      }
+    }
+  }
+  auto rod_sync = [&]() {
+    if (!rod_barriers) { __syncthreads(); return; }
+    if (bar_cnt0) asm volatile("bar.sync %0, %1;" ::"r"(bar_id0), "r"(bar_cnt0) : "memory");
+    if (bar_cnt1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id1), "r"(bar_cnt1) : "memory");
+  };
+
+  // ---- the segments this CTA runs ------------------------------------------------------------------------------
+  const int K = A.n_substeps;
+  const int P = gridDim.x, p = blockIdx.x;
+  int i0, i1, off0, end1;
+  if (A.sk_split) {
+    const long long W = (long long)A.sk_items * K, b0 = W * p / P, b1 = W * (p + 1) / P;
+    if (b1 <= b0) return;
+    i0 = (int)(b0 / K); off0 = (int)(b0 - (long long)i0 * K);
+    i1 = (int)((b1 - 1) / K); end1 = (int)(b1 - (long long)i1 * K);
+  } else {
+    i0 = i1 = p; off0 = 0; end1 = K;
+  }
+  // order: shared-with-successor part first, whole items next, shared-with-predecessor part last
+  const bool tail_first = (i1 > i0) && (end1 < K);
+  const bool head_last = (off0 > 0) && (i1 > i0);
+  const int n_seg = i1 - i0 + 1;
+  const int mid_lo = i0 + (head_last ? 1 : 0), n_mid = (i1 - (tail_first ? 1 : 0)) - mid_lo + 1;
+
+  for (int q = 0; q < n_seg; q++) {
+    int item;
+    if (tail_first && q == 0) item = i1;
+    else {
+      const int k = q - (tail_first ? 1 : 0);
+      item = (k < n_mid) ? mid_lo + k : i0;
+    }
+    const int s_begin = (item == i0) ? off0 : 0, s_end = (item == i1) ? end1 : K;
+    const int env = item * rods_per_cta + r;
+    const bool in_grid = in_cta && (env < A.n_env);
+    bool selected = true;
+    if (!FASTONLY && A.redo_filter) {   // fallback launch: flagged envs only; most CTAs have none and leave
+      selected = in_grid && A.redo[env] != 0;
+      if (!__syncthreads_or(selected)) continue;
+    }
+    const bool active = in_grid && selected;
+    bool dom_bad = false;
+    const bool elem_ok = active && j < n, vor_ok = active && j < n - 1;
+    const int t_next = elem_ok ? tid + 1 : tid;
+    const int t_next2 = vor_ok ? tid + 2 : t_next;
+    const int t_prev = (active && j > 0) ? tid - 1 : NT;
+
+    T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
+    T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
+    T *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
+    if (s_begin > 0) {
+      // continue an item the previous slot started: wait for its hand-over, then take the registers back
+      if (tid == 0) {
+        volatile int *f = A.sk_flag + (p - 1);
+        while (*f == 0) __nanosleep(200);
+        __threadfence();
+      }
+      __syncthreads();
+      const T *sc = A.sk_scratch + (size_t)(p - 1) * LEAN_REC * NT;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { x[c] = sc[c * NT + tid]; v[c] = sc[(3 + c) * NT + tid]; w[c] = sc[(15 + c) * NT + tid]; }
+#pragma unroll
+      for (int c = 0; c < 9; c++) Q[c] = sc[(6 + c) * NT + tid];
+      __syncthreads();
+      if (tid == 0) A.sk_flag[p - 1] = 0;   // (graph-safe: the flag is back to 0 before the launch ends)
+    } else if (active) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        x[c] = st[(F_POS + c) * stride + j];
+        v[c] = st[(F_VEL + c) * stride + j];
+        w[c] = st[(F_OMEGA + c) * stride + j];   // slot n holds 0 (never written by anyone)
+      }
+#pragma unroll
+      for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
+    }
+    // per-thread constants: zero where there is nothing to integrate (tip thread's pseudo-element, idle threads)
+    const T dtim_cv = active ? A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
+    const T gJ0 = elem_ok ? A.dt * A.Jinv[0] : T(0), gJ2 = elem_ok ? A.dt * A.Jinv[2] : T(0);
+    const T gam = elem_ok ? st[F_GAMMA * stride + j] : T(1);   // (L/n) / rest_length_j, see F_GAMMA
+    const T irg = A.inv_rest_len * gam;
+    T act0 = T(0);
+    if (active && A.action_dim > 0) act0 = (T)A.action[(size_t)env * A.action_dim];
+    const bool bc_thread = active && first && A.bc_kind != BC_FREE;
+    // BCs pin node 0 / element 0 by overwriting after every kinematic update; applying the overwrite once and
+    // never moving the pinned quantities is the same thing (see rod_kernel_packed.cuh)
+    const T rot_on = bc_thread ? T(0) : T(1);
+    if (bc_thread) {
+      const T *bc = A.bc + (size_t)env * BC_DIM;
+      if (A.bc_kind == BC_PENDULUM_SLIDER) {
+        x[1] = bc[1]; x[2] = bc[2];
+#pragma unroll
+        for (int m = 0; m < 3; m++) { Q[0 + m] = bc[3 + m]; Q[6 + m] = bc[9 + m]; }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+#pragma unroll
+        for (int c = 0; c < 3; c++) x[c] = bc[c];
+      }
+    }
+    const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
+    const bool pin_fixed = bc_thread && A.bc_kind != BC_PENDULUM_SLIDER;
+    const bool z12 = pin_slider || pin_fixed;   // v_y, v_z, w_x, w_z are pinned by both; v_x, w_y by the clamp only
+    const bool force_thread = active && first && A.point_force;
+
+    // x += hh v ; Q <- R(hh w) Q (merged half steps)
+    auto kinematic = [&](T hh, T eps) {
+      const T hw = hh * rot_on;
+      T a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
+#pragma unroll
+      for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
+      T q = fma(a2, a2, fma(a1, a1, a0 * a0));
+      const bool out = hi_abs(q) > A.lim_rot_hi;
+      if (FASTONLY) {
+        dom_bad = dom_bad || out;
+        rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
+      } else if (!out) rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
+      else rotate_directors_ref<T>(a0, a1, a2, Q);
+    };
+
+    const T h = A.half_dt, dt = A.dt;
+    if (s_begin == 0 && K > 0) kinematic(h, T(1e-14));
+
+#pragma unroll 1
+    for (int s = s_begin; s < s_end; s++) {
+      const bool last = (s == K - 1);
+      // ---- publish what the neighbours need ----------------------------------------------------------------
+      {
+        double2 *o = reinterpret_cast<double2 *>(rec + LEAN_REC * tid);
+        o[0] = make_double2(x[0], x[1]); o[1] = make_double2(x[2], v[0]); o[2] = make_double2(v[1], v[2]);
+        o[3] = make_double2(Q[0], Q[1]); o[4] = make_double2(Q[2], Q[3]); o[5] = make_double2(Q[4], Q[5]);
+        o[6] = make_double2(Q[6], Q[7]); rec[LEAN_REC * tid + 14] = Q[8];
+      }
+      rod_sync();
+
+      // ---- geometry, shear/stretch strain, internal force ---------------------------------------------------
+      T dx[3], dv[3], dx2[3], Qn[9];
+      {
+        const double2 *qq = reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next);
+        const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2], a3 = qq[3], a4 = qq[4], a5 = qq[5], a6 = qq[6];
+        Qn[0] = a3.x; Qn[1] = a3.y; Qn[2] = a4.x; Qn[3] = a4.y; Qn[4] = a5.x; Qn[5] = a5.y;
+        Qn[6] = a6.x; Qn[7] = a6.y; Qn[8] = rec[LEAN_REC * t_next + 14];
+        const double2 b0 = *reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next2);
+        const T b2 = rec[LEAN_REC * t_next2 + 2];
+        dx[0] = a0.x - x[0]; dx[1] = a0.y - x[1]; dx[2] = a1.x - x[2];
+        dv[0] = a1.y - v[0]; dv[1] = a2.x - v[1]; dv[2] = a2.y - v[2];
+        dx2[0] = b0.x - a0.x; dx2[1] = b0.y - a0.y; dx2[2] = b2 - a1.x;
+      }
+      if (!elem_ok) dx[2] = A.rest_len;   // keeps the pseudo-element's quantities finite
+      if (!vor_ok) dx2[2] = A.rest_len;
+      const T l2 = dot3(dx, dx), l2n = dot3(dx2, dx2);
+      const T il = rsqrt_nr(l2), iln = rsqrt_nr(l2n);
+      const T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
+      const T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
+      const T lgn = fma(l2n, iln, T(1e-14));              // length of element j+1, recomputed locally
+      const T e = lg * irg;
+      const T em1 = fma(lg, irg, T(-1.0));
+      const T inv_e = A.rest_len * ilg;
+      const T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
+      const T ede = dot3(dx, dv) * (ilg * ilg);           // (de/dt) / e = (dx . dv) / l^2
+      // sigma = e Q t - z = Q dx / l0 - z exactly (e t = dx / l0): no tangent needed here
+      T Qdx[3], nst[3], sfl[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) Qdx[i] = Q[3 * i] * dx[0];
+#pragma unroll
+      for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 1], dx[1], Qdx[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]);
+      // n = S (sigma - 0): shear components are O(strain); the stretch component is a difference of near-equal
+      // numbers and must see the element's own rest length (gam = (L/n) / l0_k = 1 +- 1e-14)
+      nst[0] = A.S_over_l[0] * Qdx[0];
+      nst[1] = A.S_over_l[0] * Qdx[1];
+      nst[2] = fma(A.S_over_l[2], Qdx[2] * gam, -A.S[2]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
+#pragma unroll
+      for (int i = 0; i < 3; i++) sfl[i] = fma(Q[3 + i], nst[1], sfl[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) sfl[i] = fma(Q[6 + i], nst[2], sfl[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) sfl[i] *= inv_e_s;
+
+      // ---- curvature, bending couple --------------------------------------------------------------------------
+      T vec[3];
+      {
+        // axial part of Rm - Rm^T (Rm = Q_{j+1} Q_j^T), each component one 6-term FMA chain
+        auto rm_diff = [&](int a, int b) {
+          T t = Qn[3 * a] * Q[3 * b];
+          t = fma(Qn[3 * a + 1], Q[3 * b + 1], t);
+          t = fma(Qn[3 * a + 2], Q[3 * b + 2], t);
+          t = fma(-Qn[3 * b], Q[3 * a], t);
+          t = fma(-Qn[3 * b + 1], Q[3 * a + 1], t);
+          return fma(-Qn[3 * b + 2], Q[3 * a + 2], t);
+        };
+        vec[0] = rm_diff(2, 1); vec[1] = rm_diff(0, 2); vec[2] = rm_diff(1, 0);
+      }
+      // |vec|^2 = 4 sin^2(theta): below 90 degrees the log-map factor -theta'/(2 sin theta') / D (theta' the
+      // reference's guarded angle acos(cos(theta) - 1e-10)) is a smooth function of it alone.  A bend cannot pass
+      // the polynomial's range unseen: every element rotates by <= 0.1 rad per update (the rotation range check),
+      // so the angle between neighbours grows by <= 0.2 rad per substep and lands in (range, 90 degrees) first;
+      // the first substep of a segment checks the trace once to rule out a state that starts beyond.
+      T w2 = dot3(vec, vec);
+      if (!vor_ok) w2 = T(0);
+      bool bend_out = hi_abs(w2) > A.lim_bend_hi;
+      T u_ref = T(0);
+      if (s == s_begin || !FASTONLY) {
+        const T tr = fma(Qn[8], Q[8], fma(Qn[7], Q[7], fma(Qn[6], Q[6], fma(Qn[5], Q[5], fma(Qn[4], Q[4], fma(Qn[3], Q[3],
+                     fma(Qn[2], Q[2], fma(Qn[1], Q[1], Qn[0] * Q[0]))))))));
+        bend_out = bend_out || (vor_ok && !(tr > T(2.0)));   // cos(theta) <= 1/2
+        u_ref = fma(T(-0.25), tr, T(0.75 + 0.5e-10));        // sin^2(theta'/2), for the reference map
+      }
+      if (FASTONLY) dom_bad = dom_bad || bend_out;
+      T fs;
+      {
+        const T *c = A.bendw;   // ascending powers of w2, pre-multiplied by -1/(2 D); even / odd halves interleaved
+        const T z = w2 * w2;
+        T pe = fma(c[10], z, c[8]), po = fma(c[9], z, c[7]);
+        pe = fma(pe, z, c[6]); po = fma(po, z, c[5]);
+        pe = fma(pe, z, c[4]); po = fma(po, z, c[3]);
+        pe = fma(pe, z, c[2]); po = fma(po, z, c[1]);
+        pe = fma(pe, z, c[0]);
+        fs = fma(po, w2, pe);
+      }
+      // reference map (elastica/_rotations.py:_inv_rotate) for this thread only
+      if (!FASTONLY && bend_out) fs = bend_factor_ref<T>(u_ref) * A.inv_rest_vor;
+      T kp[3], tau[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) kp[i] = vec[i] * fs;
+      tau[0] = A.B[0] * kp[0]; tau[1] = A.B[0] * kp[1]; tau[2] = A.B[2] * kp[2];
+      // kappa x (B kappa) with B1 = B2:  ((B3 - B1) k2 k3, (B1 - B3) k1 k3, 0)
+      const T k2b = kp[2] * A.B_diff;                     // B3 - B1
+      const T kx0 = kp[1] * k2b, kx1 = -(kp[0] * k2b);
+      const T eps_v = (lgn + lg) * A.half_inv_rest_vor;
+      T ie3 = rcp_nr(eps_v * eps_v * eps_v);
+      if (!vor_ok) ie3 = T(0);
+      const T hc = A.half_rest_vor * ie3;
+      const T m0 = tau[0] * ie3, m1 = tau[1] * ie3, m2 = tau[2] * ie3;
+      // local couples share one 1/e factor:  (Qt x n) l0 + (Jw/e) x w + (Jw/e) (de/dt)/e
+      //   = [ (Q dx) x n + (Jw) x w + (Jw) (de/dt)/e ] / e ; with S1 = S2 and J1 = J2 the cross products collapse:
+      //   (Q dx) x n = (Qdx1 c, -Qdx0 c, 0), c = n3 - S1' Qdx3 ;  (Jw) x w = (w1 t, -w0 t, 0), t = (J1 - J3) w3
+      const T cc = fma(-A.S_over_l[0], Qdx[2], nst[2]);
+      const T tg = w[2] * A.J_diff;                       // J1 - J3
+      const T je = ede * A.J[0], je2 = ede * A.J[2];
+      const T h0 = fma(Qdx[1], cc, fma(w[1], tg, je * w[0]));
+      const T h1 = fma(-Qdx[0], cc, fma(-w[0], tg, je * w[1]));
+      const T h2 = je2 * w[2];
+      T tql[3];
+      tql[0] = fma(h0, inv_e, fma(kx0, hc, m0));          // + m_j + c_j/2  (own element)
+      tql[1] = fma(h1, inv_e, fma(kx1, hc, m1));
+      tql[2] = fma(h2, inv_e, m2);
+      {   // {s0 s1 | s2 N0 | N1 m2}: N = c_j/2 - m_j goes to element j+1 (third component: -m2, negated by the reader)
+        double2 *o = reinterpret_cast<double2 *>(sn + 6 * tid);
+        o[0] = make_double2(sfl[0], sfl[1]);
+        o[1] = make_double2(sfl[2], fma(kx0, hc, -m0));
+        o[2] = make_double2(fma(kx1, hc, -m1), m2);
+      }
+      // rotational damper c_w^e = c_w exp((e-1) ln c_w) as a cubic in (e-1) (coefficients made on the host);
+      // c_w1 = c_w2 for a circular cross-section
+      T cw0, cw2;
+      {
+        const bool out = hi_abs(em1) > A.lim_em1_hi;
+        if (FASTONLY) dom_bad = dom_bad || out;
+        if (FASTONLY || !out) {
+          cw0 = fma(fma(fma(A.cwp[0][3], em1, A.cwp[0][2]), em1, A.cwp[0][1]), em1, A.cwp[0][0]);
+          cw2 = fma(fma(fma(A.cwp[1][3], em1, A.cwp[1][2]), em1, A.cwp[1][1]), em1, A.cwp[1][0]);
+        } else {
+          cw0 = exp_ref<T>(e * A.logc_w[0]);
+          cw2 = exp_ref<T>(e * A.logc_w[2]);
+        }
+      }
+      if (last && active) {
+        // stale observables of the reference: last force evaluation
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          st[(F_TAN + i) * stride + j] = dx[i] * ilg;
+          st[(F_KAPPA + i) * stride + j] = kp[i];
+          st[(F_SIGMA + i) * stride + j] = fma(irg, Qdx[i], (i == 2) ? T(-1) : T(0));
+        }
+        st[F_DIL * stride + j] = e;
+      }
+      rod_sync();
+
+      // ---- add the left neighbour's share, dynamic step ---------------------------------------------------------
+      T fint[3], tq[3];
+      {
+        const double2 *qq = reinterpret_cast<const double2 *>(sn + 6 * t_prev);
+        const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2];
+        fint[0] = sfl[0] - a0.x; fint[1] = sfl[1] - a0.y; fint[2] = sfl[2] - a1.x;
+        tq[0] = tql[0] + a1.y; tq[1] = tql[1] + a2.x; tq[2] = tql[2] - a2.y;
+      }
+      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update; the base point force
+      // replaces gravity's x component on node 0 (soft_pendulum/build.py:94-105: assignment)
+      {
+        const T f0 = force_thread ? fint[0] + act0 : fint[0];
+        const T g0 = force_thread ? T(0) : A.gdt_cv[0];
+        v[0] = fma(f0, dtim_cv, fma(v[0], A.c_v, g0));
+        v[1] = fma(fint[1], dtim_cv, fma(v[1], A.c_v, A.gdt_cv[1]));
+        v[2] = fma(fint[2], dtim_cv, fma(v[2], A.c_v, A.gdt_cv[2]));
+      }
+      {
+        const T g = e * gJ0, g2 = e * gJ2;                // dt e / J
+        w[0] = fma(g, tq[0], w[0]) * cw0;
+        w[1] = fma(g, tq[1], w[1]) * cw0;
+        w[2] = fma(g2, tq[2], w[2]) * cw2;
+      }
+      // rate constraints (zeroing BCs commute with the multiplicative damper)
+      v[0] = pin_fixed ? T(0) : v[0]; v[1] = z12 ? T(0) : v[1]; v[2] = z12 ? T(0) : v[2];
+      w[0] = z12 ? T(0) : w[0]; w[1] = pin_fixed ? T(0) : w[1]; w[2] = z12 ? T(0) : w[2];
+
+      kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
+    }
+
+    __syncthreads();   // all reads of the exchange buffers are done
+    if (s_end < K) {
+      // ---- hand the item over to the next slot -------------------------------------------------------------------
+      if (FASTONLY) {
+        if (tid < 256) sh_dom[tid] = 0;
+        __syncthreads();
+        if (active && dom_bad) atomicOr(&sh_dom[r], 1);
+        __syncthreads();
+        if (active && first && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
+      }
+      T *sc = A.sk_scratch + (size_t)p * LEAN_REC * NT;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { sc[c * NT + tid] = x[c]; sc[(3 + c) * NT + tid] = v[c]; sc[(15 + c) * NT + tid] = w[c]; }
+#pragma unroll
+      for (int c = 0; c < 9; c++) sc[(6 + c) * NT + tid] = Q[c];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) { *(volatile int *)(A.sk_flag + p) = 1; }
+      continue;
+    }
+
+    // ---- write back, NaN guard, model outputs --------------------------------------------------------------------
+    bool redo = false;
+    if (FASTONLY) {    // env-level OR of the range flags; a flagged env keeps its pre-launch state in global memory
+      if (tid < 256) sh_dom[tid] = 0;
+      __syncthreads();
+      if (active && dom_bad) atomicOr(&sh_dom[r], 1);
+      __syncthreads();
+      // (a part of this item run by the previous slot may have flagged the env already)
+      redo = active && (sh_dom[r] != 0 || A.redo[env] != 0);
+      if (redo && first && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
+    }
+    bool bad = false;
+    if (active && !redo) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        st[(F_POS + c) * stride + j] = x[c];
+        st[(F_VEL + c) * stride + j] = v[c];
+        bad = bad || (x[c] != x[c]) || (v[c] != v[c]);
+      }
+      if (j < n) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) st[(F_OMEGA + c) * stride + j] = w[c];
+#pragma unroll
+        for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + j] = Q[c];
+      }
+    }
+    // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)
+    T *sh_t = rec;   // 3 rows of NT + 2
+    constexpr int RS = NT + 2;
+    if (tid < 256) sh_flag[tid] = 0;
+    if (active && A.model == MODEL_SOFT_PENDULUM) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) sh_t[i * RS + tid] = (j < n) ? st[(F_TAN + i) * stride + j] : T(0);
+    }
+    __syncthreads();
+    if (active && bad) atomicOr(&sh_flag[r], 1);
+    __syncthreads();
+    if (!FASTONLY && A.redo_filter && active && first) A.redo[env] = 0;
+    if (active && first && !redo) {
+      const bool invalid = sh_flag[r] != 0;
+      if (A.model == MODEL_SOFT_PENDULUM) {
+        soft_pendulum_outputs<T>(sh_t + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
+                                 A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
+      } else {
+        A.reward[env] = 0.0;
+        A.terminated[env] = invalid ? 1 : 0;
+      }
+    }
+    if (active && A.model == MODEL_ROD && j == n && !redo) {
+      float *o = A.obs + (size_t)env * A.obs_dim;
+      for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
+    }
+    __syncthreads();   // the staging rows are free again before the next item publishes
+  }
+}
+
+}  // namespace sr

@@ -242,10 +242,13 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
     if (moving) { x[0] = pin_x; x[1] = pin_y; }
     T q = fma(a2, a2, fma(a1, a1, a0 * a0));
+    // Range handling is per thread, never a warp vote: an env's bits must not depend on which other envs share
+    // its warps.  Inside the range the safe variant evaluates exactly what the fast-only variant evaluates.
+    const bool rot_out = !(q <= T(kNarrowRotQ));
     if (FASTONLY) {
-      dom_bad = dom_bad || (q > T(kNarrowRotQ));
+      dom_bad = dom_bad || rot_out;
       rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
-    } else if (!__any_sync(FULL, !(q <= T(kSmallRotQ)))) rotate_directors_fast<T>(A.poly, a0, a1, a2, q, eps, Q);
+    } else if (!rot_out) rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
     else rotate_directors_ref<T>(a0, a1, a2, Q);
     hh_prev = hh;
   };
@@ -449,20 +452,23 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     constexpr bool F64 = sizeof(T) == 8;
     if (!F64) u = fmax(u, T(0));                  // FP32: the guard is below epsilon; keep u >= 0
     T fac;
-    // actuated arms bend more per element than free / clamped rods; the 10-element arms of the octopus
-    // assemblies (up to ~45 degrees per element) keep the full-range map
-    constexpr bool MID_BEND = FASTONLY && CONTACT && !MULTI, WIDE_BEND = FASTONLY && MULTI;
-    if (FASTONLY) dom_bad = dom_bad || (u > T(WIDE_BEND ? kSmallBendU : MID_BEND ? kMidBendU : kNarrowBendU));
-    if (FASTONLY || !__any_sync(FULL, !(u <= T(kSmallBendU)))) {
+    // actuated arms bend more per element than free / clamped rods (the contact models use u <= 0.1, 37 degrees); the
+    // 10-element arms of the octopus assemblies (up to ~45 degrees per element) keep the full-range map.  One map per
+    // instantiation, shared by its fast-only and safe variants; beyond its range the safe variant falls back, per
+    // thread, to the reference's acos / sin.
+    constexpr bool MID_BEND = CONTACT && !MULTI, WIDE_BEND = MULTI;
+    const bool bend_out = !(u <= T(WIDE_BEND ? kSmallBendU : MID_BEND ? kMidBendU : kNarrowBendU));
+    if (FASTONLY) dom_bad = dom_bad || bend_out;
+    if (FASTONLY || !bend_out) {
+      const T g = MID_BEND ? theta_over_sin_mid(A.poly, u) : !WIDE_BEND ? theta_over_sin_narrow(A.poly, u) : theta_over_sin(A.poly, u);
       if (F64) {
-        // cot(theta) = (1 - 2u) / (2 sqrt(u (1 - u))); it only scales the 1e-14 guard term, so on the narrow range
-        // its expansion rsqrt(4u) (1 - 1.5 u) (relative error < 0.63 u^2 <= 1e-3) is more than enough
-        T cot = (FASTONLY && !WIDE_BEND) ? rsqrt_approx(T(4.0) * u) * fma(T(-1.5), u, T(1.0))
-                         : fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
-        fac = (MID_BEND ? theta_over_sin_mid(A.poly, u) : (FASTONLY && !WIDE_BEND) ? theta_over_sin_narrow(A.poly, u) : theta_over_sin(A.poly, u)) *
-              fma(T(0.5e-14), cot, T(-0.5));
+        // cot(theta) = (1 - 2u) / (2 sqrt(u (1 - u))); it only scales the 1e-14 guard term, so on the narrower ranges
+        // its expansion rsqrt(4u) (1 - 1.5 u) (relative error < 0.63 u^2 <= 6e-3) is more than enough
+        T cot = !WIDE_BEND ? rsqrt_approx(T(4.0) * u) * fma(T(-1.5), u, T(1.0))
+                           : fma(T(-2.0), u, T(1.0)) * rsqrt_approx(T(4.0) * u * (T(1.0) - u));
+        fac = g * fma(T(0.5e-14), cot, T(-0.5));
       } else {
-        fac = T(-0.5) * theta_over_sin(A.poly, u);   // the 1e-14 cot(theta) term is < 1e-9: invisible in FP32
+        fac = T(-0.5) * g;   // the 1e-14 cot(theta) term is < 1e-9: invisible in FP32
       }
     } else {
       fac = bend_factor_ref<T>(u);
@@ -509,13 +515,12 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (FASTONLY || A.damping_on) {   // damper off = identity constants (c_w = 1, ln c_w = 0): no branch needed
       T em1 = e - T(1);
       T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
-      bool big = !(fabs_(z0) <= T(kSmallExpZ)) || !(fabs_(z1) <= T(kSmallExpZ)) ||
-                 !(fabs_(z2) <= T(kSmallExpZ));
-      // the contact models damp harder and stretch more (z up to ~1e-3): they keep the wide exp map
-      constexpr bool NARROW_EXP = FASTONLY && !CONTACT && !LAPLACE;
+      // the contact / filtered models damp harder and stretch more (z up to ~1e-3): they use the wide exp map
+      constexpr bool NARROW_EXP = !CONTACT && !LAPLACE;
       constexpr double kz = NARROW_EXP ? kNarrowExpZ : kSmallExpZ;
-      if (FASTONLY) dom_bad = dom_bad || (fabs_(z0) > T(kz)) || (fabs_(z1) > T(kz)) || (fabs_(z2) > T(kz));
-      if (FASTONLY || !__any_sync(FULL, big)) {
+      const bool exp_out = !(fabs_(z0) <= T(kz)) || !(fabs_(z1) <= T(kz)) || !(fabs_(z2) <= T(kz));
+      if (FASTONLY) dom_bad = dom_bad || exp_out;
+      if (FASTONLY || !exp_out) {
         cw0 = A.c_w[0] * (NARROW_EXP ? exp_narrow(A.poly, z0) : exp_small(A.poly, z0));
         cw2 = A.c_w[2] * (NARROW_EXP ? exp_narrow(A.poly, z2) : exp_small(A.poly, z2));
         cw1 = A.isotropic ? cw0 : A.c_w[1] * (NARROW_EXP ? exp_narrow(A.poly, z1) : exp_small(A.poly, z1));

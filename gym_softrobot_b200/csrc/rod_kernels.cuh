@@ -85,6 +85,17 @@ template <typename T> struct RodArgs {
   double *spline; const double *spline_tab; int spline_mask, spline_p, spline_dim;
   double spline_scale, spline_rate, spline_inv_dx;
   PolyCoef<T> poly;
+  // ---- lean kernel (rod_kernel_lean.cuh) ---------------------------------------------------------------------
+  // circular cross-section shortcuts and host-made tables
+  T B_diff, J_diff;                   // B3 - B1, J1 - J3
+  T half_inv_rest_vor, half_rest_vor; // 1 / (2 D), D / 2
+  T bendw[11];                        // -theta'/(2 D sin theta') as a polynomial in |axial(R - R^T)|^2 (SR_COEF_BENDW)
+  T cwp[2][4];                        // c_w^e as a cubic in (e - 1), components 0 (= 1) and 2
+  int lim_rot_hi, lim_bend_hi, lim_em1_hi;   // range limits as high words (integer-pipe compares)
+  // stream-K schedule: items of sk_rods_per_cta envs; sk_split = slots own equal substep ranges and hand partial
+  // items over through sk_scratch[slot][18][NT] / sk_flag[slot]
+  int sk_rods_per_cta, sk_items, sk_split, sk_rodsync;   // sk_rodsync: per-rod named barriers inside the substep loop
+  T *sk_scratch; int *sk_flag;
 };
 
 template <typename T, int EPL> struct Vec;
@@ -815,52 +826,6 @@ __global__ void rod_observe_kernel(const T *state, const float *prev_action, flo
       o[3 + c] = (float)st[(F_VEL + c) * stride + n];
     }
   }
-}
-
-// register-resident DFMA chains: the FP64 roofline denominator
-__global__ void dfma_peak_kernel(double *out, int iters) {
-  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-         a6 = a0 + 6, a7 = a0 + 7;
-  const double m = 1.0000001, c = 1e-9;
-  for (int i = 0; i < iters; i++) {
-    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
-    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
-  }
-  double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// same probe with three distinct 64-bit REGISTER operands per DFMA (what the rod kernel issues): shows
-// whether operand delivery from the register file, not the FMA units, caps the FP64 issue rate
-__global__ void dfma_peak_regs_kernel(double *out, const double *in, int iters) {
-  double a[8], b[8], c[8];
-  for (int i = 0; i < 8; i++) {
-    a[i] = in[(threadIdx.x + i) & 63]; b[i] = in[(threadIdx.x + 8 + i) & 63]; c[i] = in[(threadIdx.x + 16 + i) & 63];
-  }
-  for (int it = 0; it < iters; it++) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) a[i] = fma(a[i], b[i], c[i]);
-#pragma unroll
-    for (int i = 0; i < 8; i++) b[i] = fma(b[i], c[(i + 1) & 7], a[(i + 3) & 7]);
-  }
-  double s = 0;
-  for (int i = 0; i < 8; i++) s += a[i] + b[i];
-  if (s == 12345.678) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-// sr_selftest_reciprocals: max relative error of rsqrt_nr / rcp_nr against the IEEE-rounded results
-__global__ void reciprocal_selftest_kernel(int n, double lo, double hi, double *out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double e0 = 0.0, e1 = 0.0;
-  if (i < n) {
-    const double x = lo * exp(log(hi / lo) * (double)i / (double)(n - 1));
-    const double r0 = 1.0 / sqrt(x), r1 = 1.0 / x;           // correctly rounded sqrt and divisions
-    e0 = fabs(rsqrt_nr(x) / r0 - 1.0);
-    e1 = fabs(rcp_nr(x) / r1 - 1.0);
-  }
-  // errors are non-negative doubles: their bit patterns order like unsigned integers
-  atomicMax(reinterpret_cast<unsigned long long *>(out), (unsigned long long)__double_as_longlong(e0));
-  atomicMax(reinterpret_cast<unsigned long long *>(out + 1), (unsigned long long)__double_as_longlong(e1));
 }
 
 }  // namespace sr

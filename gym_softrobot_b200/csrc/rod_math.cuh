@@ -126,6 +126,13 @@ constexpr double kSmallExpZ = 1.0e-2;
 #define SR_COEF_BEND9 {0.9999999999999999, 0.666666666666836, 0.5333333332775754, 0.4571428642472279, \
                        0.40634874789975095, 0.3694252997188034, 0.34061379942887826, 0.32344955229361544, \
                        0.2573124543735613, 0.46543435203468897}
+// theta'/sin(theta') as a function of w2 = |axial(R - R^T)|^2 = 4 sin^2(theta), theta' = acos(cos(theta) - 1e-10) (the
+// reference's guarded angle), for w2 <= 0.6144 (the same 23.07 degrees as kNarrowBendU); degree 10, 1.6e-17 fit error
+// (scripts/fit_poly.py bendw 0.6144).  The lean kernel needs no trace of R with this map.
+#define SR_COEF_BENDW {1.0000000000333333, 0.041666666669996605, 0.004687500000696534, 0.0006975446373716595, \
+                       0.00011867954236079726, 2.1847272372761355e-05, 4.239023801646341e-06, 8.449104406962946e-07, \
+                       1.9022731141479846e-07, 2.1403135860719077e-08, 1.7464483725740306e-08}
+constexpr double kNarrowBendW2 = 0.6144;
 constexpr double kNarrowRotQ = 0.01, kNarrowBendU = 0.04, kMidBendU = 0.1, kNarrowExpZ = 2.5e-4;
 
 template <typename T> struct PolyCoef {

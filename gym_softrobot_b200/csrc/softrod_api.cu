@@ -19,8 +19,8 @@
 #include <vector>
 
 #include "../../include/softrod.h"
-#include "rod_kernels.cuh"
-#include "rod_kernel_packed.cuh"
+#include "launch.cuh"
+#include "util_kernels.cuh"
 
 namespace {
 
@@ -61,6 +61,8 @@ struct sr_handle {
   int32_t *d_idx = nullptr;
   cudaStream_t own_stream = nullptr;
   int64_t launches = 0;
+  // stream-K schedule of the lean kernel: resident CTA slots, hand-over scratch and flags
+  int sk_slots = 0; void *sk_scratch = nullptr; int *sk_flag = nullptr;
 };
 
 namespace {
@@ -148,11 +150,13 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     const double nm[] = SR_COEF_BEND9;
     for (int i = 0; i < 10; i++) A.poly.bend9[i] = (T)nm[i];
   }
+  double lcw[3] = {0.0, 0.0, 0.0};
   if (c.damping_constant >= 0.0) {
     // element mass incl. the end-element correction equals `mass` for a uniform rod
     A.c_v = (T)exp(-c.damping_constant * c.dt);
     for (int i = 0; i < 3; i++) {
       double lc = -c.damping_constant * c.dt * mass * (1.0 / J[i]);
+      lcw[i] = lc;
       A.logc_w[i] = (T)lc;
       A.c_w[i] = (T)exp(lc);
     }
@@ -160,80 +164,56 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     A.c_v = (T)1.0;
     for (int i = 0; i < 3; i++) { A.logc_w[i] = (T)0.0; A.c_w[i] = (T)1.0; }
   }
-}
-
-template <typename T, int EPL, int MATH, int MINB>
-int launch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  int grid = (A.n_env + sr::WARPS_PER_CTA - 1) / sr::WARPS_PER_CTA;
-  sr::rod_substeps_kernel<T, EPL, MATH, MINB><<<grid, sr::WARPS_PER_CTA * 32, 0, s>>>(A);
-  h->launches++;
-  SR_CUDA(cudaGetLastError());
-  return SR_OK;
-}
-
-// occupancy variant: CTAs (of 4 warps) per SM the kernel is compiled for.  Tunable with
-// SOFTROD_MIN_CTAS={2,3,4} for experiments; the default is the measured best.
-int min_ctas_setting() {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SOFTROD_MIN_CTAS");
-    v = e ? atoi(e) : 2;
-    if (v < 2 || v > 4) v = 2;
-  }
-  return v;
-}
-
-template <typename T, int EPL> int dispatch_math(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  if (h->cfg.math != SR_MATH_FAST) return launch_substeps<T, EPL, sr::MATH_FAITHFUL, 2>(h, A, s);
-  switch (min_ctas_setting()) {
-    case 2: return launch_substeps<T, EPL, sr::MATH_FAST, 2>(h, A, s);
-    case 4: return launch_substeps<T, EPL, sr::MATH_FAST, 4>(h, A, s);
-    default: return launch_substeps<T, EPL, sr::MATH_FAST, 3>(h, A, s);
+  // ---- lean kernel tables (rod_kernel_lean.cuh) ----------------------------------------------------------------
+  auto hi_word = [](double x) { long long b; memcpy(&b, &x, 8); return (int)((b >> 32) & 0x7fffffff); };
+  A.B_diff = (T)(Bv[2] - Bv[0]); A.J_diff = (T)(J[0] - J[2]);
+  A.half_inv_rest_vor = (T)(0.5 / rl); A.half_rest_vor = (T)(0.5 * rl);
+  {
+    const double cw2[] = SR_COEF_BENDW, ne[] = SR_COEF_EXP3;
+    for (int i = 0; i < 11; i++) A.bendw[i] = (T)(cw2[i] * (-0.5 / rl));
+    // c_w^e = c_w exp(z), z = (e - 1) ln c_w, |z| <= kNarrowExpZ: exp's cubic with the powers of ln c_w folded in
+    double lmax = 0.0;
+    for (int k = 0; k < 2; k++) {
+      const double lc = lcw[2 * k], cw = exp(lc);
+      lmax = fmax(lmax, fabs(lc));
+      double pw = 1.0;
+      for (int i = 0; i < 4; i++) { A.cwp[k][i] = (T)(cw * ne[i] * pw); pw *= lc; }
+    }
+    A.lim_rot_hi = hi_word(sr::kNarrowRotQ);
+    A.lim_bend_hi = hi_word(sr::kNarrowBendW2);
+    A.lim_em1_hi = lmax > 0.0 ? hi_word(fmin(sr::kNarrowExpZ / lmax, 1e300)) : 0x7fefffff;   // no damper: any finite stretch
   }
 }
 
-// kernel choice for the fast path: "packed" (thread per element, rods packed across a CTA)
-// or "warp" (warp per rod).  SOFTROD_KERNEL overrides the default for experiments.
-bool use_packed_kernel(const sr_handle *h) {
-  static int v = -1;
-  if (v < 0) {
-    const char *e = getenv("SOFTROD_KERNEL");
-    v = (e && strcmp(e, "warp") == 0) ? 0 : 1;
-  }
-  return v == 1 && h->cfg.math == SR_MATH_FAST && h->cfg.n_elem + 1 <= 1024;
+int cuda_fail(const char *what, cudaError_t e) {
+  return fail(SR_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-int fastpath_setting() {   // SOFTROD_FASTPATH=0: single safe kernel with warp-vote fallbacks (experiments)
+int fastpath_setting() {   // SOFTROD_FASTPATH=0: single safe kernel with per-thread fallbacks (experiments; same bits)
   static int v = -1;
   if (v < 0) { const char *e = getenv("SOFTROD_FASTPATH"); v = e ? atoi(e) != 0 : 1; }
   return v;
 }
 
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false,
-          bool FASTONLY = false>
-int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  const int group = (MULTI ? A.n_rod : 1) * (A.n_elem + 1) + (MULTI ? A.has_head : 0);   // threads per env
-  const int rods_per_cta = NT / group;
-  if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
-  const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
-  const size_t smem = (size_t)sr::packed_smem_words(NT, MULTI, TORQUE) * sizeof(T);
-  auto kern = sr::rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE, FASTONLY>;
-  static bool attr_set = false;   // per instantiation
-  if (!attr_set) {
-    SR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  kern<<<grid, NT, smem, s>>>(A, rods_per_cta);
-  h->launches++;
-  SR_CUDA(cudaGetLastError());
-  return SR_OK;
+int rodsync_setting() {    // SOFTROD_RODSYNC=0: CTA-wide barriers instead of per-rod named barriers (experiments; same bits)
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SOFTROD_RODSYNC"); v = e ? atoi(e) != 0 : 1; }
+  return v;
 }
 
-// Whether this step runs the fast-only kernel + fallback pair.  One flagged env re-runs its whole CTA (4-5 envs)
-// in the fallback, so the pair only pays while about 1 % of the envs or fewer leave the fast-math range (a pair
-// gains 5-10 %).  The fast-only kernel counts the env-steps it hands over (redo_count); every 8 steps the count is
-// fetched asynchronously, and when more than 1 % of a window's env-steps fell back (violently actuated arms do)
-// the handle uses the single safe kernel for the next 512 steps, then probes again.
+int streamk_setting() {    // SOFTROD_STREAMK=0: one CTA per item instead of equal substep ranges per slot (experiments; same bits)
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SOFTROD_STREAMK"); v = e ? atoi(e) != 0 : 1; }
+  return v;
+}
+
+// Whether this step runs the fast-only kernel + fallback pair.  Both ways give every env the same bits (the safe
+// kernel falls back per thread, and inside the range evaluates exactly what the fast-only kernel evaluates), so
+// this is a pure scheduling choice: one flagged env re-runs its whole CTA (4-5 envs) in the fallback, and the pair
+// only pays while about 1 % of the envs or fewer leave the fast-math range (a pair gains 5-10 %).  The fast-only
+// kernel counts the env-steps it hands over (redo_count); every 8 steps the count is fetched asynchronously, and
+// when more than 1 % of a window's env-steps fell back (violently actuated arms do) the handle uses the single
+// safe kernel for the next 512 steps, then probes again.
 template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (!fastpath_setting() || !A.redo) return false;
   h->pair_steps++;
@@ -258,10 +238,67 @@ template <typename T> bool use_fast_pair(sr_handle *h, sr::RodArgs<T> &A, cudaSt
   return true;
 }
 
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false,
+          bool FASTONLY = false>
+int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  const int group = (MULTI ? A.n_rod : 1) * (A.n_elem + 1) + (MULTI ? A.has_head : 0);   // threads per env
+  const int rods_per_cta = NT / group;
+  if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
+  const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
+  cudaError_t e = sr::launch_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE, FASTONLY>(A, rods_per_cta, grid, s);
+  h->launches++;
+  if (e != cudaSuccess) return cuda_fail("rod_packed_kernel launch", e);
+  return SR_OK;
+}
+
+// Lean FP64 path: grid and stream-K schedule.  With more items than resident CTA slots the grid is the slot
+// count and every slot gets the same number of item-substeps (rod_kernel_lean.cuh); partial items travel through
+// sk_scratch.  The fallback launch (redo_filter) visits flagged envs only and keeps one CTA per item.
+template <int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_handle *h, sr::RodArgs<double> &A, cudaStream_t s) {
+  const int rods_per_cta = NT / (A.n_elem + 1);
+  if (rods_per_cta < 1) return fail(SR_E_INVALID, "rod does not fit one CTA of the lean kernel");
+  const int items = (A.n_env + rods_per_cta - 1) / rods_per_cta;
+  if (h->sk_slots == 0) {
+    cudaDeviceProp prop;
+    SR_CUDA(cudaGetDeviceProperties(&prop, h->cfg.device));
+    // both variants of a pair are sized alike (same launch bounds); take the smaller answer to be safe
+    const int a = sr::lean_ctas_per_sm<NT, MINB, true>(), b = sr::lean_ctas_per_sm<NT, MINB, false>();
+    h->sk_slots = prop.multiProcessorCount * (a < b ? a : b);
+    if (h->sk_slots < 1) return fail(SR_E_CUDA, "lean kernel: occupancy query failed");
+    SR_CUDA(cudaMalloc(&h->sk_scratch, (size_t)h->sk_slots * 18 * NT * sizeof(double)));
+    SR_CUDA(cudaMalloc(&h->sk_flag, (size_t)h->sk_slots * sizeof(int)));
+    SR_CUDA(cudaMemset(h->sk_flag, 0, (size_t)h->sk_slots * sizeof(int)));
+  }
+  A.sk_rods_per_cta = rods_per_cta; A.sk_items = items;
+  A.sk_split = (streamk_setting() && !A.redo_filter && items > h->sk_slots && A.n_substeps > 0) ? 1 : 0;
+  A.sk_scratch = (double *)h->sk_scratch; A.sk_flag = h->sk_flag;
+  A.sk_rodsync = rodsync_setting();
+  const int grid = A.sk_split ? h->sk_slots : items;
+  cudaError_t e = sr::launch_lean_kernel<NT, MINB, FASTONLY>(A, grid, s);
+  h->launches++;
+  if (e != cudaSuccess) return cuda_fail("rod_lean_kernel launch", e);
+  return SR_OK;
+}
+
+template <int NT, int MINB> int launch_lean_pair(sr_handle *h, sr::RodArgs<double> &A, cudaStream_t s) {
+  if (use_fast_pair(h, A, s)) {
+    // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
+    int rc = launch_lean_impl<NT, MINB, true>(h, A, s);
+    if (rc != SR_OK) return rc;
+    A.redo_filter = 1;
+  }
+  return launch_lean_impl<NT, MINB, false>(h, A, s);
+}
+
+template <typename T> bool is_lean_config(const sr::RodArgs<T> &A) {
+  return !(A.n_rod > 1 || A.has_head || A.muscle_on || A.spline_mask || A.contact_on || A.rest_kappa ||
+           A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE);
+}
+
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  // the feature-complete instantiation serves SoftPendulum3D-style configs, the lean one the rest
+  constexpr bool F64 = std::is_same<T, double>::value;
   if (A.n_rod > 1 || A.has_head) {
-    if constexpr (std::is_same<T, double>::value) {
+    if constexpr (F64) {
       if (use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, false, false, true, true, false, true>(h, A, s);
         if (rc != SR_OK) return rc;
@@ -271,7 +308,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     return launch_packed_impl<T, NT, MINB, false, false, true, true>(h, A, s);
   }
   if (A.muscle_on || A.spline_mask) {
-    if constexpr (std::is_same<T, double>::value) {
+    if constexpr (F64) {
       // (the spline forcing updates its cached control values / magnitudes inside the launch: safe kernel only)
       if (!A.spline_mask && use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, false, false, true, false, true, true>(h, A, s);
@@ -282,7 +319,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
   }
   if (A.contact_on || A.rest_kappa) {
-    if constexpr (std::is_same<T, double>::value) {
+    if constexpr (F64) {
       if (use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, false, false, true, false, false, true>(h, A, s);
         if (rc != SR_OK) return rc;
@@ -292,7 +329,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     return launch_packed_impl<T, NT, MINB, false, false, true, false>(h, A, s);
   }
   if (A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE) {
-    if constexpr (std::is_same<T, double>::value) {
+    if constexpr (F64) {
       if (use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, true, true, false, false, false, true>(h, A, s);
         if (rc != SR_OK) return rc;
@@ -301,30 +338,31 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     }
     return launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s);
   }
-  {   // lean instantiation: FP64 and FP32
+  if constexpr (F64) {   // lean FP64: its own kernel
+    return launch_lean_pair<NT, MINB>(h, A, s);
+  } else {               // lean FP32: generic kernel
     if (use_fast_pair(h, A, s)) {
-      // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
       int rc = launch_packed_impl<T, NT, MINB, false, false, false, false, false, true>(h, A, s);
       if (rc != SR_OK) return rc;
       A.redo_filter = 1;
     }
+    return launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
   }
-  return launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
 }
 
-// CTA size of the packed kernel.  Registers cap the SM at 512 resident threads (128 regs), so the
+// CTA size of the packed kernels.  Registers cap the SM at 512 resident threads (128 regs), so the
 // choice is 2 x 256 or 1 x 512; take whichever wastes fewer lanes for this rod length
 // (n = 50: 5 x 51 = 255/256; n = 100: 2 x 101 = 202/256 but 5 x 101 = 505/512).
-// SOFTROD_PACKED_THREADS={256,320,384,512} overrides it for experiments.
+// SOFTROD_PACKED_THREADS={256,384,512} overrides it for experiments.
 int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   static int forced = -1;
   if (forced < 0) {
     const char *e = getenv("SOFTROD_PACKED_THREADS");
     forced = e ? atoi(e) : 0;
-    if (forced != 256 && forced != 320 && forced != 384 && forced != 512 && forced != 544 && forced != 768 && forced != 1024) forced = 0;
+    if (forced != 256 && forced != 384 && forced != 512 && forced != 544 && forced != 768 && forced != 1024) forced = 0;
   }
-  if (forced) return forced;
   const int tpr = (n_rod > 1 ? n_rod : 1) * (n_elem + 1) + has_head;   // threads per env group
+  if (forced && forced >= tpr) return forced;
   auto util = [&](int nt) { return (double)((nt / tpr) * tpr) / nt; };
   // 2 x 256 (128 regs) is the default; 1 x 384 (168 regs) / 1 x 512 (128 regs) only when they waste
   // clearly fewer lanes for this group size
@@ -337,24 +375,39 @@ int packed_threads_setting(int n_elem, int n_rod = 1, int has_head = 0) {
   return best;
 }
 
-template <typename T> int dispatch_substeps(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  if (use_packed_kernel(h)) {
-    const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head), mb = min_ctas_setting();
-    if (nt == 1024) return launch_packed<T, 1024, 1>(h, A, s);
-    if (nt == 768) return launch_packed<T, 768, 1>(h, A, s);
-    if (nt == 544) return launch_packed<T, 544, 1>(h, A, s);
-    if (nt == 512) return launch_packed<T, 512, 1>(h, A, s);
-    if (nt == 320) return launch_packed<T, 320, 2>(h, A, s);
-    if (nt == 384) return launch_packed<T, 384, 1>(h, A, s);
-    if (mb == 3) return launch_packed<T, 256, 3>(h, A, s);
-    return launch_packed<T, 256, 2>(h, A, s);
+int lean_threads_override() {   // SOFTROD_LEAN_THREADS={160,320}: experimental CTA shapes of the lean FP64 kernel (3 x 160, 2 x 320)
+  static int v = -1;
+  if (v < 0) { const char *e = getenv("SOFTROD_LEAN_THREADS"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
+template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (is_lean_config(A) && A.n_elem + 1 <= 160) {
+      if (lean_threads_override() == 160) return launch_lean_pair<160, 3>(h, A, s);
+      if (lean_threads_override() == 320) return launch_lean_pair<320, 2>(h, A, s);
+    }
   }
-  switch (h->epl) {
-    case 1: return dispatch_math<T, 1>(h, A, s);
-    case 2: return dispatch_math<T, 2>(h, A, s);
-    case 4: return dispatch_math<T, 4>(h, A, s);
+  switch (packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head)) {
+    case 1024: return launch_packed<T, 1024, 1>(h, A, s);
+    case 768: return launch_packed<T, 768, 1>(h, A, s);
+    case 544: return launch_packed<T, 544, 1>(h, A, s);
+    case 512: return launch_packed<T, 512, 1>(h, A, s);
+    case 384: return launch_packed<T, 384, 1>(h, A, s);
+    default: return launch_packed<T, 256, 2>(h, A, s);
   }
-  return fail(SR_E_INVALID, "unsupported elements-per-lane");
+}
+
+int dispatch_substeps(sr_handle *h, sr::RodArgs<double> &A, cudaStream_t s) {
+  if (h->cfg.math == SR_MATH_FAST) return dispatch_packed<double>(h, A, s);
+  // faithful math (libm calls in the reference's operation order): warp-per-rod kernel, the parity build
+  const int grid = (A.n_env + sr::WARPS_PER_CTA - 1) / sr::WARPS_PER_CTA;
+  cudaError_t e = h->epl == 1 ? sr::launch_warp_faithful<double, 1>(A, grid, s)
+                  : h->epl == 2 ? sr::launch_warp_faithful<double, 2>(A, grid, s)
+                                : sr::launch_warp_faithful<double, 4>(A, grid, s);
+  h->launches++;
+  if (e != cudaSuccess) return cuda_fail("rod_substeps_kernel launch", e);
+  return SR_OK;
 }
 
 }  // namespace
@@ -517,7 +570,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFree(h->sk_scratch); cudaFree(h->sk_flag); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -566,18 +619,12 @@ int sr_step(sr_handle *h, const float *action_dev, int n_substeps, float *obs_de
     sr::RodArgs<float> A = h->a32;
     A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
     A.n_substeps = n_substeps;
-    const int nt = packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head);
-    return nt == 1024  ? launch_packed<float, 1024, 1>(h, A, (cudaStream_t)stream)
-           : nt == 768 ? launch_packed<float, 768, 1>(h, A, (cudaStream_t)stream)
-           : nt == 544 ? launch_packed<float, 544, 1>(h, A, (cudaStream_t)stream)
-           : nt == 512 ? launch_packed<float, 512, 1>(h, A, (cudaStream_t)stream)
-           : nt == 384 ? launch_packed<float, 384, 1>(h, A, (cudaStream_t)stream)
-                       : launch_packed<float, 256, 2>(h, A, (cudaStream_t)stream);
+    return dispatch_packed<float>(h, A, (cudaStream_t)stream);
   }
   sr::RodArgs<double> A = h->a64;
   A.action = action_dev; A.obs = obs_dev; A.reward = reward_dev; A.terminated = terminated_dev;
   A.n_substeps = n_substeps;
-  return dispatch_substeps<double>(h, A, (cudaStream_t)stream);
+  return dispatch_substeps(h, A, (cudaStream_t)stream);
 }
 
 int sr_observe(sr_handle *h, const float *prev_action_dev, float *obs_dev, void *stream) {
@@ -785,6 +832,22 @@ static int measure_fp64_peak_impl(int device, double *tflops_out, bool three_reg
 
 int sr_measure_fp64_peak(int device, double *tflops_out) { return measure_fp64_peak_impl(device, tflops_out, false); }
 int sr_measure_fp64_peak_regs(int device, double *tflops_out) { return measure_fp64_peak_impl(device, tflops_out, true); }
+
+int sr_probe_latency(int device, double *out) {
+  if (!out) return fail(SR_E_INVALID, "sr_probe_latency: null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(SR_E_NO_DEVICE, "no CUDA device"); }
+  SR_CUDA(cudaSetDevice(device));
+  double *d = nullptr;
+  SR_CUDA(cudaMalloc(&d, 8 * sizeof(double)));
+  SR_CUDA(cudaMemset(d, 0, 8 * sizeof(double)));
+  for (int rep = 0; rep < 2; rep++) sr::latency_probe_kernel<<<1, 32>>>(d, 1.0);
+  SR_CUDA(cudaGetLastError());
+  cudaError_t e = cudaMemcpy(out, d, 8 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(SR_E_CUDA, cudaGetErrorString(e));
+  return SR_OK;
+}
 
 int sr_selftest_reciprocals(int device, int32_t n, double lo, double hi, double *out) {
   if (!out || n < 2 || !(lo > 0.0) || !(hi > lo)) return fail(SR_E_INVALID, "sr_selftest_reciprocals: bad argument");

@@ -15,7 +15,11 @@ for p in re.split(r"\n\s*Function : ", txt)[1:]:
         if op.startswith("BRA"):
             mm = re.search(r"0x([0-9a-f]+)", rest)
             if mm and int(mm.group(1), 16) < a: back.append((a, int(mm.group(1), 16)))
-    a1, a0 = max(back, key=lambda t: t[0] - t[1])
+    # the substep loop = the smallest backward-branch span that still holds the bulk of the FP64 work
+    def n_dfma(t):
+        return sum(1 for i in ins if t[1] <= i[0] <= t[0] and i[1].startswith("DFMA"))
+    cands = [t for t in back if n_dfma(t) >= 100]
+    a1, a0 = min(cands, key=lambda t: t[0] - t[1]) if cands else max(back, key=lambda t: t[0] - t[1])
     loop = [i for i in ins if a0 <= i[0] <= a1]
     c = collections.Counter(i[1].split(".")[0] for i in loop)
     fp64 = sum(c[k] for k in ("DFMA", "DMUL", "DADD", "DSETP"))

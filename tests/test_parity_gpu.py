@@ -990,70 +990,117 @@ def test_octo_cfg4_8x40_vs_reference_fixture(golden_dir):
     env.close()
 
 
-@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
-def test_randomized_assembly_vs_c_oracle(seed):
-    """Arms + rigid head + FixedJoint2Rigid + BodyBoundaryCondition + plane friction with per-seed arm count, element
-    count, joint stiffness / damping / torsional stiffness, head size and density and per-arm rest curvature, against
-    the multi-rod C oracle (oracle/rod_oracle.c: ro_assembly): 1e-9 on every field over 900 substeps."""
-    import torch
+def _random_assembly(seed, friction_multiplier):
+    """Per-seed assembly parameters + a factory of the multi-rod C oracle for them."""
     import rod_oracle as ro
-    nat = _native()
     rng = np.random.default_rng(1000 + seed)
     n_arm = int(rng.integers(2, 9))
     n_elem = [8, 10, 13, 20, 31, 40][seed]   # every seed a different element count, 40 (config 4) included
     L0, r0 = 0.35, 0.35 * 0.02
-    head_radius, head_density = float(rng.uniform(0.03, 0.06)), float(rng.uniform(300, 900))
-    kt, nu = float(10 ** rng.uniform(-1, 2)), float(10 ** rng.uniform(-4, -2))
+    p = dict(n_arm=n_arm, n_elem=n_elem, head_radius=float(rng.uniform(0.03, 0.06)), head_density=float(rng.uniform(300, 900)),
+             kt=float(10 ** rng.uniform(-1, 2)), nu=float(10 ** rng.uniform(-4, -2)))
     # explicit stability of the joint spring on the half-mass end node: dt < 2 sqrt(m / k), keep a factor 3
     m_end = 0.5 * 1000.0 * np.pi * r0 * r0 * L0 / n_elem
-    k = float(10 ** rng.uniform(4.5, 6))
-    dt = float(min(7e-5, 2 * np.sqrt(m_end / k) / 3, 0.25 * (L0 / n_elem) / np.sqrt(1e6 / 1000.0)))
-    asm = ro.octopus_assembly(n_arm=n_arm, n_elem=n_elem, time_step=dt, head_radius=head_radius, head_density=head_density,
-                              body_arm_k=k, body_arm_kt=kt, body_arm_nu=nu)
+    p["k"] = float(10 ** rng.uniform(4.5, 6))
+    p["dt"] = float(min(7e-5, 2 * np.sqrt(m_end / p["k"]) / 3, 0.25 * (L0 / n_elem) / np.sqrt(1e6 / 1000.0)))
+    s = np.linspace(0, 1, n_elem - 1)
+    p["rest_kappa"] = []          # smooth random rest curvature about d1 and a little about d2, per chunk and arm
+    for chunk in range(3):
+        rk = np.zeros((n_arm, 3, n_elem - 1))
+        for a in range(n_arm):
+            rk[a, 0] = rng.uniform(-12, 12) * np.sin(np.pi * s) + rng.uniform(-6, 6) * np.sin(2 * np.pi * s)
+            rk[a, 1] = rng.uniform(-3, 3) * np.sin(np.pi * s)
+        p["rest_kappa"].append(rk)
+
+    def make_oracle():
+        return ro.octopus_assembly(n_arm=n_arm, n_elem=n_elem, time_step=p["dt"], head_radius=p["head_radius"],
+                                   head_density=p["head_density"], body_arm_k=p["k"], body_arm_kt=p["kt"],
+                                   body_arm_nu=p["nu"], friction_multiplier=friction_multiplier)
+    return p, make_oracle
+
+
+def _oracle_states(asm, p):
+    out = []
+    for rk in p["rest_kappa"]:
+        for a, rod in enumerate(asm.arms):
+            rod.rest_kappa[...] = rk[a]
+        asm.substeps(300)
+        st = {fk: np.stack([getattr(rod, fk).copy() for rod in asm.arms]) for fk in FIELDS.values()}
+        st["head"] = np.concatenate([asm.head_position, asm.head_velocity, asm.head_director.reshape(-1), asm.head_omega])
+        out.append(st)
+    return out
+
+
+HEAD_SLICES = ((slice(0, 3), "position_collection"), (slice(3, 6), "velocity_collection"),
+               (slice(6, 15), "director_collection"), (slice(15, 18), "omega_collection"))
+
+
+@pytest.mark.parametrize("friction", [False, True], ids=["frictionless-plane", "friction"])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3, 4, 5])
+def test_randomized_assembly_vs_c_oracle(seed, friction):
+    """Arms + rigid head + FixedJoint2Rigid + BodyBoundaryCondition on the plane with per-seed arm count, element
+    count, joint stiffness / damping / torsional stiffness, head size and density and per-arm rest curvature, against
+    the multi-rod C oracle (oracle/rod_oracle.c: ro_assembly), every field, 900 substeps.
+
+    frictionless-plane (normal response, gravity, joints, head, BC all active): 1e-9.
+    friction: the anisotropic friction law is regularised over |v| in [1e-8, 2e-8] m/s and integrated explicitly with
+    dt mu g / tol >> 2, so it amplifies round-off wherever an element sticks: the ORACLE ITSELF, restarted with its
+    velocities perturbed at the level the frictionless comparison shows (1e-11 relative), moves by up to 4e-7 within
+    300 substeps (seed 3; frictionless: 1e-15).  The bound is therefore calibrated on the spot: 20 x the largest
+    divergence among three such perturbed oracle replicas, and never below 1e-9."""
+    import torch
+    nat = _native()
+    p, make_oracle = _random_assembly(seed, 1.0 if friction else 0.0)
+    n_arm, n_elem, dt = p["n_arm"], p["n_elem"], p["dt"]
+    asm = make_oracle()
+    ref = _oracle_states(asm, p)
+    asm.close()
+    bound = [{fk: TOL for fk in list(FIELDS.values()) + ["head"]} for _ in ref]
+    if friction:
+        for rep in range(3):
+            asm = make_oracle()
+            prng = np.random.default_rng(77 + rep)
+            for rod in asm.arms:      # what "another correct implementation" looks like after a few substeps
+                rod.velocity_collection[...] += 1e-11 * prng.standard_normal(rod.velocity_collection.shape) * 0.1
+            for c, st in enumerate(_oracle_states(asm, p)):
+                for fk in FIELDS.values():
+                    bound[c][fk] = max(bound[c][fk], 20 * max(_asm_err(st[fk][a], ref[c][fk][a], fk) for a in range(n_arm)))
+                bound[c]["head"] = max(bound[c]["head"], 20 * max(_asm_err(st["head"][sl], ref[c]["head"][sl], fk) for sl, fk in HEAD_SLICES))
+            asm.close()
     from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
-    n_env = 3
+    n_env, r0 = 3, 0.35 * 0.02
     h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n_elem, dt=dt, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
-                   bc_kind=nat.BC_FREE, contact=arm_contact_params(), n_rod=n_arm,
-                   head=dict(length=2 * r0, radius=head_radius, density=head_density),
-                   joint=dict(radius=head_radius, angles_deg=[360 / n_arm * a for a in range(n_arm)], k=k, nu=nu, kt=kt),
+                   bc_kind=nat.BC_FREE, contact=arm_contact_params(friction_multiplier=1.0 if friction else 0.0), n_rod=n_arm,
+                   head=dict(length=2 * r0, radius=p["head_radius"], density=p["head_density"]),
+                   joint=dict(radius=p["head_radius"], angles_deg=[360 / n_arm * a for a in range(n_arm)], k=p["k"], nu=p["nu"], kt=p["kt"]),
                    **_ROD)
     row = []
     for a in range(n_arm):
         c, s = np.cos(np.deg2rad(360 / n_arm * a)), np.sin(np.deg2rad(360 / n_arm * a))
-        row += [c * head_radius, s * head_radius, 0.0, c, s, 0.0, 0.0, 0.0, 1.0]
+        row += [c * p["head_radius"], s * p["head_radius"], 0.0, c, s, 0.0, 0.0, 0.0, 1.0]
     row += [0.0, 0.0, -r0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0]
     h.reset(torch.as_tensor(np.repeat(np.array([row]), n_env, axis=0), device="cuda").contiguous())
     o6 = torch.empty((n_env, 6), dtype=torch.float32, device="cuda")
     rew = torch.empty(n_env, dtype=torch.float64, device="cuda")
     term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
-    worst = 0.0
-    for chunk in range(3):
-        # smooth random rest curvature about d1 and a little about d2 (flat_env actuates d1 only), per arm
-        s = np.linspace(0, 1, n_elem - 1)
-        rk = np.zeros((n_arm, 3, n_elem - 1))
-        for a in range(n_arm):
-            rk[a, 0] = rng.uniform(-12, 12) * np.sin(np.pi * s) + rng.uniform(-6, 6) * np.sin(2 * np.pi * s)
-            rk[a, 1] = rng.uniform(-3, 3) * np.sin(np.pi * s)
+    worst, worst_ratio = 0.0, 0.0
+    for chunk, rk in enumerate(p["rest_kappa"]):
         h.rest_kappa_tensor().unflatten(0, (n_env, n_arm))[:] = torch.as_tensor(rk, device="cuda")
-        for a, rod in enumerate(asm.arms):
-            rod.rest_kappa[...] = rk[a]
         h.step(None, 300, o6, rew, term)
-        asm.substeps(300)
         f = {k_: v.cpu().numpy() for k_, v in h.fields().items()}
-        if n_arm == 1:
-            f = {k_: v[:, None] for k_, v in f.items()}
         hd = h.head_tensor().cpu().numpy()
         assert int(term.sum()) == 0
         for e in range(n_env):
-            for a, rod in enumerate(asm.arms):
+            for a in range(n_arm):
                 for fk in FIELDS.values():
-                    err = _asm_err(f[fk][e, a], getattr(rod, fk), fk)
-                    worst = max(worst, err)
-                    assert err < TOL, f"seed {seed} (n_arm {n_arm}, n_elem {n_elem}, k {k:.2e}) chunk {chunk} env {e} arm {a} {fk}: {err:.3e}"
-            for sl, mine, fk in ((slice(0, 3), asm.head_position, "position_collection"), (slice(3, 6), asm.head_velocity, "velocity_collection"),
-                                 (slice(6, 15), asm.head_director.reshape(-1), "director_collection"), (slice(15, 18), asm.head_omega, "omega_collection")):
-                err = _asm_err(hd[e, sl], mine, fk)
-                worst = max(worst, err)
-                assert err < TOL, f"seed {seed} chunk {chunk} head {fk}: {err:.3e}"
-    print(f"randomized assembly seed {seed}: n_arm {n_arm} n_elem {n_elem} dt {dt:.2e} worst {worst:.2e}")
-    h.close(); asm.close()
+                    err = _asm_err(f[fk][e, a], ref[chunk][fk][a], fk)
+                    worst, worst_ratio = max(worst, err), max(worst_ratio, err / bound[chunk][fk])
+                    assert err < bound[chunk][fk], (f"seed {seed} (n_arm {n_arm}, n_elem {n_elem}, k {p['k']:.2e}) chunk {chunk} env {e} "
+                                                     f"arm {a} {fk}: {err:.3e} (bound {bound[chunk][fk]:.1e})")
+            for sl, fk in HEAD_SLICES:
+                err = _asm_err(hd[e, sl], ref[chunk]["head"][sl], fk)
+                worst, worst_ratio = max(worst, err), max(worst_ratio, err / bound[chunk]["head"])
+                assert err < bound[chunk]["head"], f"seed {seed} chunk {chunk} head {fk}: {err:.3e} (bound {bound[chunk]['head']:.1e})"
+    print(f"randomized assembly seed {seed} friction {friction}: n_arm {n_arm} n_elem {n_elem} dt {dt:.2e} worst {worst:.2e} "
+          f"(worst err/bound {worst_ratio:.2f}; largest bound {max(max(b.values()) for b in bound):.1e})")
+    h.close()
