@@ -31,6 +31,7 @@
 // Algorithm: SURVEY.md Appendix A.2/A.3; reference boundary
 // /root/reference/gym_softrobot/envs/soft_pendulum/soft_pendulum.py:183-184.
 #pragma once
+#include <type_traits>
 #include "rod_kernels.cuh"
 
 namespace sr {
@@ -38,6 +39,43 @@ namespace sr {
 // high word of a double as an ordered integer (x >= 0): range tests on the integer pipe instead of DSETP.
 // NaN compares as "large" (0x7ff8....), i.e. out of range, which is what the callers want.
 __device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7fffffff; }
+
+// Q <- R Q with R = I + A K + B K^2, A = sin(t)/t = 1 + q g(q), B = (1 - cos t)/t^2 = 1/2 + q h(q), q = t^2 <= 0.01
+// (g, h: SR_COEF_SINCG / SR_COEF_COSCH, leading constants exact so that they are instruction immediates).  The
+// reference's guard (axis = a / (|a| + 1e-14)) multiplies A by rho and B by rho^2, rho = 1 - d,
+// d = eps / sqrt(q + eps^2) ~ 1e-10; A rho = A - d (1 - q/6 + ..) and B rho^2 = B - d (1 - q/12 + ..) to first order
+// in d, and dropping d q / 6 changes the guard's own 1e-10 effect by a relative 1e-3: the guard becomes a subtraction
+// folded into the constant terms of the two Horner chains, off the critical path.  (The 4e-28 under the root only
+// keeps d finite at q = 0, where the rotation vanishes anyway.)
+__device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], const double (&ch)[3], double a0, double a1,
+                                                      double a2, double q, double eps, double (&Q)[9]) {
+  const double d = eps * rsqrt_approx(q + 4e-28);
+  double pa = fma(cg[2], q, cg[1]), pb = fma(ch[2], q, ch[1]);
+  pa = fma(pa, q, cg[0]); pb = fma(pb, q, ch[0]);
+  const double A = fma(pa, q, 1.0 - d), B = fma(pb, q, 0.5 - d);
+  const double Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
+  const double Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
+  double D[9];
+  D[0] = -fma(Ba1, a1, Ba2 * a2); D[4] = -fma(Ba0, a0, Ba2 * a2); D[8] = -fma(Ba0, a0, Ba1 * a1);
+  D[1] = fma(Ba0, a1, Aa2); D[3] = fma(Ba0, a1, -Aa2);
+  D[2] = fma(Ba0, a2, -Aa1); D[6] = fma(Ba0, a2, Aa1);
+  D[5] = fma(Ba1, a2, Aa0); D[7] = fma(Ba1, a2, -Aa0);
+  double nq[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) nq[3 * i + m] = fma(D[3 * i], Q[m], Q[3 * i + m]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) nq[3 * i + m] = fma(D[3 * i + 1], Q[3 + m], nq[3 * i + m]);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 3; m++) nq[3 * i + m] = fma(D[3 * i + 2], Q[6 + m], nq[3 * i + m]);
+#pragma unroll
+  for (int i = 0; i < 9; i++) Q[i] = nq[i];
+}
 
 constexpr int LEAN_REC = 18;        // exchange record per thread (doubles), 144-byte stride: conflict-free LDS.128
 constexpr int lean_smem_words(int nt) { return (LEAN_REC + 6) * (nt + 2); }
@@ -149,17 +187,15 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
     }
-    // per-thread constants: zero where there is nothing to integrate (tip thread's pseudo-element, idle threads)
+    // per-thread constants: zero where there is nothing to integrate (tip thread's pseudo-element, idle threads).
+    // Only three 64-bit values stay live across the substep loop (dtim_cv, irg, base0): the kernel sits at the
+    // 128-register cap of 2 x 256 threads per SM, and every further invariant becomes a local-memory reload per substep.
     const T dtim_cv = active ? A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
-    const T gJ0 = elem_ok ? A.dt * A.Jinv[0] : T(0), gJ2 = elem_ok ? A.dt * A.Jinv[2] : T(0);
-    const T gam = elem_ok ? st[F_GAMMA * stride + j] : T(1);   // (L/n) / rest_length_j, see F_GAMMA
-    const T irg = A.inv_rest_len * gam;
-    T act0 = T(0);
-    if (active && A.action_dim > 0) act0 = (T)A.action[(size_t)env * A.action_dim];
+    const T irg = A.inv_rest_len * (elem_ok ? st[F_GAMMA * stride + j] : T(1));   // 1 / rest_length_j (F_GAMMA = (L/n) / l0_j)
     const bool bc_thread = active && first && A.bc_kind != BC_FREE;
     // BCs pin node 0 / element 0 by overwriting after every kinematic update; applying the overwrite once and
-    // never moving the pinned quantities is the same thing (see rod_kernel_packed.cuh)
-    const T rot_on = bc_thread ? T(0) : T(1);
+    // never moving the pinned quantities is the same thing (see rod_kernel_packed.cuh): the BC thread integrates its
+    // frame with a zero rotation vector
     if (bc_thread) {
       const T *bc = A.bc + (size_t)env * BC_DIM;
       if (A.bc_kind == BC_PENDULUM_SLIDER) {
@@ -176,11 +212,14 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
     const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
     const bool pin_fixed = bc_thread && A.bc_kind != BC_PENDULUM_SLIDER;
     const bool z12 = pin_slider || pin_fixed;   // v_y, v_z, w_x, w_z are pinned by both; v_x, w_y by the clamp only
-    const bool force_thread = active && first && A.point_force;
+    // x component of the velocity update's constant term: dt c_v g_x, or, on the node that carries the base point
+    // force, dt c_v F / m (soft_pendulum/build.py:94-105: the force REPLACES gravity's x component there)
+    T base0 = A.gdt_cv[0];
+    if (active && first && A.point_force) base0 = (A.action_dim > 0 ? (T)A.action[(size_t)env * A.action_dim] : T(0)) * dtim_cv;
 
     // x += hh v ; Q <- R(hh w) Q (merged half steps)
     auto kinematic = [&](T hh, T eps) {
-      const T hw = hh * rot_on;
+      const T hw = bc_thread ? T(0) : hh;
       T a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
 #pragma unroll
       for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
@@ -188,17 +227,17 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       const bool out = hi_abs(q) > A.lim_rot_hi;
       if (FASTONLY) {
         dom_bad = dom_bad || out;
-        rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
-      } else if (!out) rotate_directors_fast<T, true>(A.poly, a0, a1, a2, q, eps, Q);
+        rotate_directors_lean(A.sincg, A.cosch, a0, a1, a2, q, eps, Q);
+      } else if (!out) rotate_directors_lean(A.sincg, A.cosch, a0, a1, a2, q, eps, Q);
       else rotate_directors_ref<T>(a0, a1, a2, Q);
     };
 
     const T h = A.half_dt, dt = A.dt;
     if (s_begin == 0 && K > 0) kinematic(h, T(1e-14));
 
-#pragma unroll 1
-    for (int s = s_begin; s < s_end; s++) {
-      const bool last = (s == K - 1);
+    bool check_trace = true;   // first substep of the segment: rule out a state that starts beyond 90 degrees of bend
+    auto substep = [&](auto last_tag) {
+      constexpr bool last = decltype(last_tag)::value;
       // ---- publish what the neighbours need ----------------------------------------------------------------
       {
         double2 *o = reinterpret_cast<double2 *>(rec + LEAN_REC * tid);
@@ -242,10 +281,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
 #pragma unroll
       for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]);
       // n = S (sigma - 0): shear components are O(strain); the stretch component is a difference of near-equal
-      // numbers and must see the element's own rest length (gam = (L/n) / l0_k = 1 +- 1e-14)
+      // numbers and must see the element's own rest length (irg = 1 / l0_k, within 1e-14 of n / L)
       nst[0] = A.S_over_l[0] * Qdx[0];
       nst[1] = A.S_over_l[0] * Qdx[1];
-      nst[2] = fma(A.S_over_l[2], Qdx[2] * gam, -A.S[2]);
+      nst[2] = fma(A.S[2], Qdx[2] * irg, -A.S[2]);
 #pragma unroll
       for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
 #pragma unroll
@@ -278,7 +317,8 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       if (!vor_ok) w2 = T(0);
       bool bend_out = hi_abs(w2) > A.lim_bend_hi;
       T u_ref = T(0);
-      if (s == s_begin || !FASTONLY) {
+      if (check_trace || !FASTONLY) {
+        check_trace = false;
         const T tr = fma(Qn[8], Q[8], fma(Qn[7], Q[7], fma(Qn[6], Q[6], fma(Qn[5], Q[5], fma(Qn[4], Q[4], fma(Qn[3], Q[3],
                      fma(Qn[2], Q[2], fma(Qn[1], Q[1], Qn[0] * Q[0]))))))));
         bend_out = bend_out || (vor_ok && !(tr > T(2.0)));   // cos(theta) <= 1/2
@@ -287,13 +327,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       if (FASTONLY) dom_bad = dom_bad || bend_out;
       T fs;
       {
-        const T *c = A.bendw;   // ascending powers of w2, pre-multiplied by -1/(2 D); even / odd halves interleaved
+        const T *c = A.bendw;   // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved
         const T z = w2 * w2;
-        T pe = fma(c[10], z, c[8]), po = fma(c[9], z, c[7]);
-        pe = fma(pe, z, c[6]); po = fma(po, z, c[5]);
-        pe = fma(pe, z, c[4]); po = fma(po, z, c[3]);
-        pe = fma(pe, z, c[2]); po = fma(po, z, c[1]);
-        pe = fma(pe, z, c[0]);
+        T pe = fma(c[8], z, c[6]), po = fma(c[9], z, c[7]);
+        pe = fma(pe, z, c[4]); po = fma(po, z, c[5]);
+        pe = fma(pe, z, c[2]); po = fma(po, z, c[3]);
+        pe = fma(pe, z, c[0]); po = fma(po, z, c[1]);
         fs = fma(po, w2, pe);
       }
       // reference map (elastica/_rotations.py:_inv_rotate) for this thread only
@@ -303,41 +342,40 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       for (int i = 0; i < 3; i++) kp[i] = vec[i] * fs;
       tau[0] = A.B[0] * kp[0]; tau[1] = A.B[0] * kp[1]; tau[2] = A.B[2] * kp[2];
       // kappa x (B kappa) with B1 = B2:  ((B3 - B1) k2 k3, (B1 - B3) k1 k3, 0)
-      const T k2b = kp[2] * A.B_diff;                     // B3 - B1
+      const T k2b = kp[2] * A.BDH;                        // (B3 - B1) D / 2: the quadrature weight of A_h folded in
       const T kx0 = kp[1] * k2b, kx1 = -(kp[0] * k2b);
       const T eps_v = (lgn + lg) * A.half_inv_rest_vor;
       T ie3 = rcp_nr(eps_v * eps_v * eps_v);
       if (!vor_ok) ie3 = T(0);
-      const T hc = A.half_rest_vor * ie3;
       const T m0 = tau[0] * ie3, m1 = tau[1] * ie3, m2 = tau[2] * ie3;
       // local couples share one 1/e factor:  (Qt x n) l0 + (Jw/e) x w + (Jw/e) (de/dt)/e
       //   = [ (Q dx) x n + (Jw) x w + (Jw) (de/dt)/e ] / e ; with S1 = S2 and J1 = J2 the cross products collapse:
       //   (Q dx) x n = (Qdx1 c, -Qdx0 c, 0), c = n3 - S1' Qdx3 ;  (Jw) x w = (w1 t, -w0 t, 0), t = (J1 - J3) w3
       const T cc = fma(-A.S_over_l[0], Qdx[2], nst[2]);
-      const T tg = w[2] * A.J_diff;                       // J1 - J3
-      const T je = ede * A.J[0], je2 = ede * A.J[2];
+      const T tg = -(w[2] * A.J[0]);                      // (J1 - J3) w3 = -J1 w3 for a circular section (J3 = 2 J1)
+      const T je = ede * A.J[0], je2 = je + je;
       const T h0 = fma(Qdx[1], cc, fma(w[1], tg, je * w[0]));
       const T h1 = fma(-Qdx[0], cc, fma(-w[0], tg, je * w[1]));
       const T h2 = je2 * w[2];
       T tql[3];
-      tql[0] = fma(h0, inv_e, fma(kx0, hc, m0));          // + m_j + c_j/2  (own element)
-      tql[1] = fma(h1, inv_e, fma(kx1, hc, m1));
+      tql[0] = fma(h0, inv_e, fma(kx0, ie3, m0));          // + m_j + c_j/2  (own element)
+      tql[1] = fma(h1, inv_e, fma(kx1, ie3, m1));
       tql[2] = fma(h2, inv_e, m2);
       {   // {s0 s1 | s2 N0 | N1 m2}: N = c_j/2 - m_j goes to element j+1 (third component: -m2, negated by the reader)
         double2 *o = reinterpret_cast<double2 *>(sn + 6 * tid);
         o[0] = make_double2(sfl[0], sfl[1]);
-        o[1] = make_double2(sfl[2], fma(kx0, hc, -m0));
-        o[2] = make_double2(fma(kx1, hc, -m1), m2);
+        o[1] = make_double2(sfl[2], fma(kx0, ie3, -m0));
+        o[2] = make_double2(fma(kx1, ie3, -m1), m2);
       }
-      // rotational damper c_w^e = c_w exp((e-1) ln c_w) as a cubic in (e-1) (coefficients made on the host);
-      // c_w1 = c_w2 for a circular cross-section
+      // rotational damper c_w^e = c_w exp((e-1) ln c_w) as a quadratic in (e-1) (coefficients made on the host; the
+      // range limit keeps the dropped cubic term below 1.4e-15); c_w1 = c_w2 for a circular cross-section
       T cw0, cw2;
       {
         const bool out = hi_abs(em1) > A.lim_em1_hi;
-        if (FASTONLY) dom_bad = dom_bad || out;
+        if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
         if (FASTONLY || !out) {
-          cw0 = fma(fma(fma(A.cwp[0][3], em1, A.cwp[0][2]), em1, A.cwp[0][1]), em1, A.cwp[0][0]);
-          cw2 = fma(fma(fma(A.cwp[1][3], em1, A.cwp[1][2]), em1, A.cwp[1][1]), em1, A.cwp[1][0]);
+          cw0 = fma(fma(A.cwp[0][2], em1, A.cwp[0][1]), em1, A.cwp[0][0]);
+          cw2 = fma(fma(A.cwp[1][2], em1, A.cwp[1][1]), em1, A.cwp[1][0]);
         } else {
           cw0 = exp_ref<T>(e * A.logc_w[0]);
           cw2 = exp_ref<T>(e * A.logc_w[2]);
@@ -363,17 +401,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
         fint[0] = sfl[0] - a0.x; fint[1] = sfl[1] - a0.y; fint[2] = sfl[2] - a1.x;
         tq[0] = tql[0] + a1.y; tq[1] = tql[1] + a2.x; tq[2] = tql[2] - a2.y;
       }
-      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update; the base point force
-      // replaces gravity's x component on node 0 (soft_pendulum/build.py:94-105: assignment)
+      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
+      v[0] = fma(fint[0], dtim_cv, fma(v[0], A.c_v, base0));
+      v[1] = fma(fint[1], dtim_cv, fma(v[1], A.c_v, A.gdt_cv[1]));
+      v[2] = fma(fint[2], dtim_cv, fma(v[2], A.c_v, A.gdt_cv[2]));
       {
-        const T f0 = force_thread ? fint[0] + act0 : fint[0];
-        const T g0 = force_thread ? T(0) : A.gdt_cv[0];
-        v[0] = fma(f0, dtim_cv, fma(v[0], A.c_v, g0));
-        v[1] = fma(fint[1], dtim_cv, fma(v[1], A.c_v, A.gdt_cv[1]));
-        v[2] = fma(fint[2], dtim_cv, fma(v[2], A.c_v, A.gdt_cv[2]));
-      }
-      {
-        const T g = e * gJ0, g2 = e * gJ2;                // dt e / J
+        const T g = elem_ok ? e * A.dt_Jinv0 : T(0), g2 = g * T(0.5);   // dt e / J ; J3 = 2 J1 for a circular section
         w[0] = fma(g, tq[0], w[0]) * cw0;
         w[1] = fma(g, tq[1], w[1]) * cw0;
         w[2] = fma(g2, tq[2], w[2]) * cw2;
@@ -383,7 +416,13 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       w[0] = z12 ? T(0) : w[0]; w[1] = pin_fixed ? T(0) : w[1]; w[2] = z12 ? T(0) : w[2];
 
       kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
-    }
+    };
+    // the item's last substep ends with a half kinematic step and exports the stale observables: its own copy of the
+    // body, so that the loop carries neither the selects nor the branch
+    const int s_loop_end = (s_end == K) ? K - 1 : s_end;
+#pragma unroll 1
+    for (int s = s_begin; s < s_loop_end; s++) substep(std::false_type{});
+    if (s_end == K && s_begin < K) substep(std::true_type{});
 
     __syncthreads();   // all reads of the exchange buffers are done
     if (s_end < K) {
@@ -447,7 +486,8 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
     if (active && first && !redo) {
       const bool invalid = sh_flag[r] != 0;
       if (A.model == MODEL_SOFT_PENDULUM) {
-        soft_pendulum_outputs<T>(sh_t + tid, RS, n, (double)x[0], (double)v[0], (float)act0, invalid,
+        soft_pendulum_outputs<T>(sh_t + tid, RS, n, (double)x[0], (double)v[0],
+                                 A.action_dim > 0 ? A.action[(size_t)env * A.action_dim] : 0.0f, invalid,
                                  A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
       } else {
         A.reward[env] = 0.0;

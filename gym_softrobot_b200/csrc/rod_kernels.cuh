@@ -87,10 +87,12 @@ template <typename T> struct RodArgs {
   PolyCoef<T> poly;
   // ---- lean kernel (rod_kernel_lean.cuh) ---------------------------------------------------------------------
   // circular cross-section shortcuts and host-made tables
-  T B_diff, J_diff;                   // B3 - B1, J1 - J3
-  T half_inv_rest_vor, half_rest_vor; // 1 / (2 D), D / 2
-  T bendw[11];                        // -theta'/(2 D sin theta') as a polynomial in |axial(R - R^T)|^2 (SR_COEF_BENDW)
-  T cwp[2][4];                        // c_w^e as a cubic in (e - 1), components 0 (= 1) and 2
+  T BDH;                              // (B3 - B1) D / 2
+  T half_inv_rest_vor;                // 1 / (2 D)
+  T dt_Jinv0;                         // dt / J1
+  T bendw[10];                        // -theta'/(2 D sin theta') as a polynomial in |axial(R - R^T)|^2 (SR_COEF_BENDW)
+  T cwp[2][3];                        // c_w^e as a quadratic in (e - 1), components 0 (= 1) and 2
+  T sincg[3], cosch[3];               // sin(t)/t = 1 + q g(q), (1 - cos t)/t^2 = 1/2 + q h(q)
   int lim_rot_hi, lim_bend_hi, lim_em1_hi;   // range limits as high words (integer-pipe compares)
   // stream-K schedule: items of sk_rods_per_cta envs; sk_split = slots own equal substep ranges and hand partial
   // items over through sk_scratch[slot][18][NT] / sk_flag[slot]

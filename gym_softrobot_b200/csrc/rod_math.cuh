@@ -127,12 +127,18 @@ constexpr double kSmallExpZ = 1.0e-2;
                        0.40634874789975095, 0.3694252997188034, 0.34061379942887826, 0.32344955229361544, \
                        0.2573124543735613, 0.46543435203468897}
 // theta'/sin(theta') as a function of w2 = |axial(R - R^T)|^2 = 4 sin^2(theta), theta' = acos(cos(theta) - 1e-10) (the
-// reference's guarded angle), for w2 <= 0.6144 (the same 23.07 degrees as kNarrowBendU); degree 10, 1.6e-17 fit error
-// (scripts/fit_poly.py bendw 0.6144).  The lean kernel needs no trace of R with this map.
-#define SR_COEF_BENDW {1.0000000000333333, 0.041666666669996605, 0.004687500000696534, 0.0006975446373716595, \
-                       0.00011867954236079726, 2.1847272372761355e-05, 4.239023801646341e-06, 8.449104406962946e-07, \
-                       1.9022731141479846e-07, 2.1403135860719077e-08, 1.7464483725740306e-08}
+// reference's guarded angle), for w2 <= 0.6144 (the same 23.07 degrees as kNarrowBendU); degree 9, 2.8e-16 fit error
+// (scripts/fit_poly.py bendw 0.6144 9).  The lean kernel needs no trace of R with this map.
+#define SR_COEF_BENDW {1.0000000000333331, 0.041666666670077346, 0.004687499996336051, 0.0006975447286339237, \
+                       0.00011867857307313035, 2.185318201165154e-05, 4.217099326139182e-06, 8.952330387027554e-07, \
+                       1.2044932536293865e-07, 7.495667373584703e-08}
 constexpr double kNarrowBendW2 = 0.6144;
+// sin(t)/t = 1 + q g(q) and (1 - cos t)/t^2 = 1/2 + q h(q), q = t^2 <= kNarrowRotQ: degree-2 g, h with the leading
+// constants exact (instruction immediates in the lean kernel); 8.6e-16 / 1.7e-16 relative on the range
+#define SR_COEF_SINCG {-0.16666666666658056, 0.008333333178343767, -0.0001983713666611297}
+#define SR_COEF_COSCH {-0.04166666666665805, 0.0013888888733895929, -2.4797454055979264e-05}
+// the lean kernel's c_w^e = c_w exp(z) drops z^3/6: |z| <= 2e-5 keeps that below 1.4e-15
+constexpr double kLeanExpZ = 2.0e-5;
 constexpr double kNarrowRotQ = 0.01, kNarrowBendU = 0.04, kMidBendU = 0.1, kNarrowExpZ = 2.5e-4;
 
 template <typename T> struct PolyCoef {

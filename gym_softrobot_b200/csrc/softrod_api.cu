@@ -166,22 +166,23 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   }
   // ---- lean kernel tables (rod_kernel_lean.cuh) ----------------------------------------------------------------
   auto hi_word = [](double x) { long long b; memcpy(&b, &x, 8); return (int)((b >> 32) & 0x7fffffff); };
-  A.B_diff = (T)(Bv[2] - Bv[0]); A.J_diff = (T)(J[0] - J[2]);
-  A.half_inv_rest_vor = (T)(0.5 / rl); A.half_rest_vor = (T)(0.5 * rl);
+  A.BDH = (T)((Bv[2] - Bv[0]) * 0.5 * rl);
+  A.half_inv_rest_vor = (T)(0.5 / rl);
+  A.dt_Jinv0 = (T)(c.dt / J[0]);
   {
-    const double cw2[] = SR_COEF_BENDW, ne[] = SR_COEF_EXP3;
-    for (int i = 0; i < 11; i++) A.bendw[i] = (T)(cw2[i] * (-0.5 / rl));
-    // c_w^e = c_w exp(z), z = (e - 1) ln c_w, |z| <= kNarrowExpZ: exp's cubic with the powers of ln c_w folded in
+    const double cw2[] = SR_COEF_BENDW, sg[] = SR_COEF_SINCG, ch[] = SR_COEF_COSCH;
+    for (int i = 0; i < 10; i++) A.bendw[i] = (T)(cw2[i] * (-0.5 / rl));
+    for (int i = 0; i < 3; i++) { A.sincg[i] = (T)sg[i]; A.cosch[i] = (T)ch[i]; }
+    // c_w^e = c_w exp(z), z = (e - 1) ln c_w, |z| <= kLeanExpZ: 1 + z + z^2/2 with the powers of ln c_w folded in
     double lmax = 0.0;
     for (int k = 0; k < 2; k++) {
       const double lc = lcw[2 * k], cw = exp(lc);
       lmax = fmax(lmax, fabs(lc));
-      double pw = 1.0;
-      for (int i = 0; i < 4; i++) { A.cwp[k][i] = (T)(cw * ne[i] * pw); pw *= lc; }
+      A.cwp[k][0] = (T)cw; A.cwp[k][1] = (T)(cw * lc); A.cwp[k][2] = (T)(cw * 0.5 * lc * lc);
     }
     A.lim_rot_hi = hi_word(sr::kNarrowRotQ);
     A.lim_bend_hi = hi_word(sr::kNarrowBendW2);
-    A.lim_em1_hi = lmax > 0.0 ? hi_word(fmin(sr::kNarrowExpZ / lmax, 1e300)) : 0x7fefffff;   // no damper: any finite stretch
+    A.lim_em1_hi = lmax > 0.0 ? hi_word(fmin(sr::kLeanExpZ / lmax, 1e300)) : 0x7fefffff;   // no damper: any finite stretch
   }
 }
 
@@ -381,11 +382,36 @@ int lean_threads_override() {   // SOFTROD_LEAN_THREADS={160,320}: experimental 
   return v;
 }
 
+// CTA size of the lean FP64 kernel.  With per-rod barriers one 512-thread CTA per SM (16 warps, 10 rods of n = 50)
+// beats two of 256 (measured: 1.51 vs 1.64 ms per 4096-env step): take 512 whenever it wastes no more lanes.
+int lean_threads_setting(int n_elem) {
+  const int tpr = n_elem + 1;
+  if (tpr > 512) return packed_threads_setting(n_elem);
+  static int forced = -1;
+  if (forced < 0) { const char *e = getenv("SOFTROD_PACKED_THREADS"); forced = e ? atoi(e) : 0; }
+  if ((forced == 256 || forced == 384 || forced == 512) && forced >= tpr) return forced;
+  auto util = [&](int nt) { return (double)((nt / tpr) * tpr) / nt; };
+  int best = 512;
+  if (util(384) > util(best) + 0.02) best = 384;
+  if (util(256) > util(best) + 0.02) best = 256;
+  return best;
+}
+
 template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if constexpr (std::is_same<T, double>::value) {
-    if (is_lean_config(A) && A.n_elem + 1 <= 160) {
-      if (lean_threads_override() == 160) return launch_lean_pair<160, 3>(h, A, s);
-      if (lean_threads_override() == 320) return launch_lean_pair<320, 2>(h, A, s);
+    if (is_lean_config(A)) {
+      if (A.n_elem + 1 <= 160) {
+        if (lean_threads_override() == 160) return launch_lean_pair<160, 3>(h, A, s);
+        if (lean_threads_override() == 320) return launch_lean_pair<320, 2>(h, A, s);
+      }
+      switch (lean_threads_setting(h->cfg.n_elem)) {
+        case 1024: return launch_lean_pair<1024, 1>(h, A, s);
+        case 768: return launch_lean_pair<768, 1>(h, A, s);
+        case 544: return launch_lean_pair<544, 1>(h, A, s);
+        case 512: return launch_lean_pair<512, 1>(h, A, s);
+        case 384: return launch_lean_pair<384, 1>(h, A, s);
+        default: return launch_lean_pair<256, 2>(h, A, s);
+      }
     }
   }
   switch (packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head)) {

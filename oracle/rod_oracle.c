@@ -952,3 +952,34 @@ double *ro_asm_head_position(ro_assembly *a) { return a->hx; }
 double *ro_asm_head_velocity(ro_assembly *a) { return a->hv; }
 double *ro_asm_head_director(ro_assembly *a) { return a->hQ; }
 double *ro_asm_head_omega(ro_assembly *a) { return a->hw; }
+
+/* generic batch runners for the CPU baselines of the other workloads (bench.py --config 3/4/5) */
+typedef struct { ro_rod **rods; ro_assembly **asms; int n_substeps, lo, hi; } generic_job;
+
+static void *generic_worker(void *p) {
+  generic_job *j = (generic_job *)p;
+  for (int e = j->lo; e < j->hi; e++) {
+    if (j->rods) ro_substeps(j->rods[e], j->n_substeps, 0.0, NULL, NULL);
+    else ro_asm_substeps(j->asms[e], j->n_substeps);
+  }
+  return NULL;
+}
+
+static void generic_batch(ro_rod **rods, ro_assembly **asms, int n, int n_substeps, int n_threads) {
+  if (n_threads <= 0) n_threads = ro_max_threads();
+  if (n_threads > n) n_threads = n;
+  if (n_threads < 1) n_threads = 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  generic_job *jobs = (generic_job *)malloc(sizeof(generic_job) * (size_t)n_threads);
+  for (int t = 0; t < n_threads; t++) {
+    generic_job j = {rods, asms, n_substeps, (int)((long)n * t / n_threads), (int)((long)n * (t + 1) / n_threads)};
+    jobs[t] = j;
+    if (t > 0) pthread_create(&th[t], NULL, generic_worker, &jobs[t]);
+  }
+  generic_worker(&jobs[0]);
+  for (int t = 1; t < n_threads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
+void ro_substeps_batch(ro_rod **rods, int n, int n_substeps, int n_threads) { generic_batch(rods, NULL, n, n_substeps, n_threads); }
+void ro_asm_substeps_batch(ro_assembly **asms, int n, int n_substeps, int n_threads) { generic_batch(NULL, asms, n, n_substeps, n_threads); }

@@ -114,6 +114,9 @@ double *ro_asm_head_position(ro_assembly *);  /* (3) */
 double *ro_asm_head_velocity(ro_assembly *);  /* (3) */
 double *ro_asm_head_director(ro_assembly *);  /* (3,3) rows */
 double *ro_asm_head_omega(ro_assembly *);     /* (3) */
+/* pthread-parallel batches of independent rods / assemblies (CPU baselines of bench.py --config 3/4/5) */
+void ro_substeps_batch(ro_rod **rods, int n, int n_substeps, int n_threads);
+void ro_asm_substeps_batch(ro_assembly **asms, int n, int n_substeps, int n_threads);
 
 #ifdef __cplusplus
 }

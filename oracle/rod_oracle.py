@@ -132,6 +132,8 @@ def lib():
             f = getattr(L, "ro_asm_head_" + name)
             f.restype = C.POINTER(C.c_double)
             f.argtypes = [C.c_void_p]
+        L.ro_substeps_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
+        L.ro_asm_substeps_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
         _lib = L
     return _lib
 
@@ -291,6 +293,15 @@ class OracleAssembly:
             self.close()
         except Exception:
             pass
+
+
+def substeps_batch(systems, n_substeps, n_threads=0):
+    """Advance a list of OracleRod or OracleAssembly objects by n_substeps each on n_threads pthreads."""
+    arr = (C.c_void_p * len(systems))(*[s._h for s in systems])
+    if isinstance(systems[0], OracleAssembly):
+        lib().ro_asm_substeps_batch(arr, len(systems), int(n_substeps), int(n_threads))
+    else:
+        lib().ro_substeps_batch(arr, len(systems), int(n_substeps), int(n_threads))
 
 
 def pendulum_direction_normal(u01: float):

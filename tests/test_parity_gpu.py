@@ -38,6 +38,37 @@ def rate_floors(E, rho, L, n, r, max_abs_x):
             "omega_collection": fv / r}
 
 
+# a rate field counts as "the rod has barely started to move" below these magnitudes; only then may the absolute
+# round-off floor of rate_floors() stand in for the relative bound
+TINY_RATE = {"velocity_collection": 1e-2, "omega_collection": 1e-1}
+# Magnitude floors of the strain fields: a straight rod at rest holds kappa / sigma of pure round-off size (computed by
+# cancellation: axial(Q+ Q^T) / D, e Q t - z), where "relative to max|ref|" is meaningless; they are compared relative
+# to max(|ref|, the magnitude a gently loaded rod reaches): 1e-3 1/m of curvature, 1e-6 of strain.
+STRAIN_FLOOR = {"kappa": 1e-3, "sigma": 1e-6}
+
+
+def assert_state_close(mine, ref, name, floors, what, tol=TOL):
+    """max|mine - ref| <= tol * max|ref|.  A rate field whose reference magnitude is still tiny (TINY_RATE) may meet the
+    configuration's absolute round-off floor instead; nothing else gets an absolute allowance."""
+    scale, err = float(np.abs(ref).max()), float(np.abs(mine - ref).max())
+    if err <= tol * max(scale, STRAIN_FLOOR.get(name, 0.0)):
+        return
+    ok = name in TINY_RATE and scale < TINY_RATE[name] and err <= tol * scale + floors[name]
+    assert ok, f"{what} {name}: abs err {err:.3e}, rel {err / max(scale, 1e-300):.3e} (|ref| {scale:.3e}, floor {floors.get(name, 0.0):.2e})"
+
+
+# ---- multi-rod assemblies against the multi-rod C oracle (VERDICT r1 item 1) ------------------------------------
+# Scale floors of the assembly comparisons: a field is compared relative to max|ref| over the arm, but not below
+# the magnitude it has once the arm is actuated (a straight arm at rest holds kappa / sigma / rates of pure
+# round-off size, where "relative" is meaningless).  Same table as tests/test_oracle_golden.py.
+ASM_FLOOR = dict(position_collection=1e-2, velocity_collection=1e-3, director_collection=1.0, omega_collection=1e-2,
+                 tangents=1.0, kappa=1.0, sigma=1e-3, dilatation=1.0)
+
+
+def _asm_err(mine, ref, key):
+    return float(np.abs(mine - ref).max() / max(np.abs(ref).max(), ASM_FLOOR[key]))
+
+
 def make_pendulum_handle(n_env, math, n_elem=50, dt=1e-4):
     from gym_softrobot_b200.envs.soft_pendulum import _make_handle
     return _make_handle(n_env, n_elem, dt, 0, math)
@@ -63,11 +94,7 @@ def test_golden_substeps(golden_dir, math):
         torch.cuda.synchronize()
         f = {k: v[0].cpu().numpy() for k, v in h.fields().items()}
         for gk, fk in FIELDS.items():
-            err = rel(f[fk], g[f"sub{target}/{gk}"])
-            # kappa/sigma are ~0 quantities computed by cancellation (axial(Q+ Q^T), e Qt - z):
-            # their round-off floor is absolute (~1e-16/D), not relative
-            ok = err < TOL or np.abs(f[fk] - g[f"sub{target}/{gk}"]).max() < 1e-10
-            assert ok, f"math={math} substeps={target} field={gk} rel err {err:.3e}"
+            assert_state_close(f[fk], g[f"sub{target}/{gk}"], fk, {}, f"math={math} substeps={target}")
     h.close()
 
 
@@ -88,10 +115,7 @@ def test_golden_episode_single_env(golden_dir, math):
         if i < 3:  # 1200 substeps: the 1e-9 window of the north star
             st = env.rod_state()
             for gk, fk in FIELDS.items():
-                if gk in ("kappa", "sigma"):
-                    continue
-                err = rel(st[fk], g[f"state{i + 1}/{gk}"])
-                assert err < TOL, f"step {i} field {gk} rel err {err:.3e}"
+                assert_state_close(st[fk], g[f"state{i + 1}/{gk}"], fk, {}, f"step {i}")
             assert abs(r - g["reward"][i]) <= TOL * max(1.0, abs(g["reward"][i]))
         np.testing.assert_allclose(obs, g["obs"][i], rtol=2e-6, atol=1e-7)
         assert abs(r - g["reward"][i]) <= 1e-6 * max(1.0, abs(g["reward"][i]))
@@ -255,10 +279,7 @@ def test_generic_rod_vs_oracle(n_elem, dt, radius):
             r.substeps(chunk)
             floors = rate_floors(1e6, 1000.0, 1.0, n_elem, radius, np.abs(r.position_collection).max())
             for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-                ref = getattr(r, name)
-                err_abs = float(np.abs(f[name][i] - ref).max())
-                assert err_abs <= TOL * np.abs(ref).max() + floors[name], \
-                    f"n={n_elem} env={i} {name}: rel {err_abs / np.abs(ref).max():.3e} floor {floors[name]:.2e}"
+                assert_state_close(f[name][i], getattr(r, name), name, floors, f"n={n_elem} env={i}")
             np.testing.assert_allclose(obs[i, :3], r.position_collection[:, -1], rtol=2e-6, atol=1e-7)
         assert term.sum() == 0
     h.close()
@@ -401,11 +422,10 @@ def test_arm_single_env_golden(golden_dir):
     for i, a in enumerate(g["actions"]):
         obs, r, te, tr, info = env.step(a)
         st = env.rod_state()
+        # 714 substeps per env-step: the first step is inside the north star's 1000-substep window (1e-9, every field);
+        # the later ones (up to 3570 substeps) get 1e-8
         for gk, fk in FIELDS.items():
-            if gk in ("kappa", "sigma"):
-                continue
-            err = rel(st[fk], g[f"state{i + 1}/{gk}"])
-            assert err < 1e-8, f"step {i} field {gk} rel err {err:.3e}"   # 714 substeps per step, 3570 in total
+            assert_state_close(st[fk], g[f"state{i + 1}/{gk}"], fk, {}, f"step {i}", tol=TOL if i == 0 else 1e-8)
         np.testing.assert_allclose(obs, g["obs"][i], rtol=1e-4, atol=1e-5)
         assert abs(r - float(g["reward"][i])) < 1e-6
         assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
@@ -426,16 +446,16 @@ def test_octo_flat_env_golden(golden_dir):
     for i, a in enumerate(g["actions"]):
         obs, r, te, tr, info = env.step(a)
         st = env.state()
+        # 3 x 285 = 855 substeps in total: inside the 1000-substep window, 1e-9 on every field (kappa, sigma included)
         for arm in range(8):
-            for gk, fk in (("position", "position_collection"), ("velocity", "velocity_collection"),
-                           ("director", "director_collection"), ("omega", "omega_collection")):
-                err = rel(st[fk][arm], g[f"state{i + 1}/arm{arm}/{gk}"])
-                assert err < 1e-8, f"step {i} arm {arm} {gk}: {err:.3e}"
+            for gk, fk in FIELDS.items():
+                err = _asm_err(st[fk][arm], g[f"state{i + 1}/arm{arm}/{gk}"], fk)
+                assert err < TOL, f"step {i} arm {arm} {gk}: {err:.3e}"
         hd = st["head"]
-        assert rel(hd[0:3], g[f"state{i + 1}/head/position"][:, 0]) < 1e-8
-        assert rel(hd[3:6], g[f"state{i + 1}/head/velocity"][:, 0]) < 1e-8
-        assert rel(hd[6:15].reshape(3, 3), g[f"state{i + 1}/head/director"][:, :, 0]) < 1e-8
-        assert rel(hd[15:18], g[f"state{i + 1}/head/omega"][:, 0]) < 1e-8
+        for sl, gk, fk in ((slice(0, 3), "position", "position_collection"), (slice(3, 6), "velocity", "velocity_collection"),
+                           (slice(6, 15), "director", "director_collection"), (slice(15, 18), "omega", "omega_collection")):
+            err = _asm_err(hd[sl], g[f"state{i + 1}/head/{gk}"].reshape(-1), fk)
+            assert err < TOL, f"step {i} head {gk}: {err:.3e}"
         np.testing.assert_allclose(obs["individual"], g[f"obs{i + 1}/individual"], rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(obs["shared"], g[f"obs{i + 1}/shared"], rtol=1e-4, atol=1e-6)
         assert abs(r - float(g["reward"][i])) < 1e-6
@@ -553,11 +573,7 @@ def test_randomized_rods_vs_oracle(seed):
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
         floors = rate_floors(c["E"], c["rho"], c["L"], c["n"], c["r"], np.abs(o.position_collection).max())
         for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-            ref = getattr(o, name)
-            err_abs = float(np.abs(f[name][1] - ref).max())
-            err = err_abs / max(np.abs(ref).max(), 1e-300)
-            assert err_abs <= TOL * np.abs(ref).max() + floors[name], \
-                f"seed={seed} math={math} n={c['n']} bc={c['bc']} {name}: rel {err:.3e} abs {err_abs:.3e} floor {floors[name]:.3e}"
+            assert_state_close(f[name][1], getattr(o, name), name, floors, f"seed={seed} math={math} n={c['n']} bc={c['bc']}")
         h.close()
 
 
@@ -773,10 +789,7 @@ def test_muscle_torques_without_friction_are_roundoff_limited(golden_dir, case):
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
         floors = rate_floors(E, 1000.0, L, n, L * 0.011, L)      # the rod hardly moves in 12-24 ms: see rate_floors
         for gk in ("position", "velocity", "director", "omega"):
-            ref = g[f"{case}/seg{seg + 1}/{gk}"]
-            err = float(np.abs(f[FIELDS[gk]][1] - ref).max())
-            tol = 1e-9 * float(np.abs(ref).max()) + floors[FIELDS[gk]]
-            assert err < tol, f"case {case} segment {seg} field {gk}: abs err {err:.3e} > {tol:.3e} (|ref| {np.abs(ref).max():.3e})"
+            assert_state_close(f[FIELDS[gk]][1], g[f"{case}/seg{seg + 1}/{gk}"], FIELDS[gk], floors, f"case {case} segment {seg}")
     assert float(mu[0, 0]) == float(g[f"{case}/time"])
     h.close()
 
@@ -822,9 +835,7 @@ def test_fast_only_kernel_falls_back_per_env():
             r.substeps(chunk)
             floors = rate_floors(1e6, 1000.0, 1.0, n, radius, np.abs(r.position_collection).max())
             for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-                ref = getattr(r, name)
-                err = float(np.abs(f[name][i] - ref).max())
-                assert err <= 1e-9 * np.abs(ref).max() + floors[name], f"env {i} {name}: abs err {err:.3e}"
+                assert_state_close(f[name][i], getattr(r, name), name, floors, f"env {i}")
         assert term.sum() == 0
     assert h.launch_count >= 1 + 2 * 2        # reset + (fast-only, fallback) per step
     h.close()
@@ -897,9 +908,7 @@ def test_muscle_torques_vs_c_oracle_randomized(seed):
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
         floors = rate_floors(E, rho, L, n, r0, L)
         for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-            ref = getattr(o, name)
-            err = float(np.abs(f[name][1] - ref).max())
-            assert err < 1e-9 * float(np.abs(ref).max()) + floors[name], f"seed {seed} {name}: {err:.3e} vs |ref| {np.abs(ref).max():.3e}"
+            assert_state_close(f[name][1], getattr(o, name), name, floors, f"seed {seed}")
     assert float(mu[0, 0]) == o.time
     h.close(); o.close()
 
@@ -935,24 +944,10 @@ def test_spline_torques_vs_c_oracle_randomized(seed):
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
         floors = rate_floors(E, rho, L, n, r0, L)
         for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-            ref = getattr(o, name)
-            err = float(np.abs(f[name][1] - ref).max())
-            assert err < 1e-9 * float(np.abs(ref).max()) + floors[name], f"seed {seed} seg {seg} {name}: {err:.3e} vs |ref| {np.abs(ref).max():.3e}"
+            assert_state_close(f[name][1], getattr(o, name), name, floors, f"seed {seed} seg {seg}")
         for d in dirs:
             np.testing.assert_allclose(mags[1, d].cpu().numpy(), o.spline_magnitude[d], rtol=1e-9, atol=1e-12 * spl["scale"])
     h.close(); o.close()
-
-
-# ---- multi-rod assemblies against the multi-rod C oracle ------------------------------------
-# Scale floors of the assembly comparisons: a field is compared relative to max|ref| over the arm, but not below
-# the magnitude it has once the arm is actuated (a straight arm at rest holds kappa / sigma / rates of pure
-# round-off size, where "relative" is meaningless).  Same table as tests/test_oracle_golden.py.
-ASM_FLOOR = dict(position_collection=1e-2, velocity_collection=1e-3, director_collection=1.0, omega_collection=1e-2,
-                 tangents=1.0, kappa=1.0, sigma=1e-3, dilatation=1.0)
-
-
-def _asm_err(mine, ref, key):
-    return float(np.abs(mine - ref).max() / max(np.abs(ref).max(), ASM_FLOOR[key]))
 
 
 def test_octo_cfg4_8x40_vs_reference_fixture(golden_dir):
@@ -1042,12 +1037,13 @@ def test_randomized_assembly_vs_c_oracle(seed, friction):
     count, joint stiffness / damping / torsional stiffness, head size and density and per-arm rest curvature, against
     the multi-rod C oracle (oracle/rod_oracle.c: ro_assembly), every field, 900 substeps.
 
-    frictionless-plane (normal response, gravity, joints, head, BC all active): 1e-9.
-    friction: the anisotropic friction law is regularised over |v| in [1e-8, 2e-8] m/s and integrated explicitly with
-    dt mu g / tol >> 2, so it amplifies round-off wherever an element sticks: the ORACLE ITSELF, restarted with its
-    velocities perturbed at the level the frictionless comparison shows (1e-11 relative), moves by up to 4e-7 within
-    300 substeps (seed 3; frictionless: 1e-15).  The bound is therefore calibrated on the spot: 20 x the largest
-    divergence among three such perturbed oracle replicas, and never below 1e-9."""
+    frictionless-plane (normal response, gravity, joints, head, BC all active): 1e-9 throughout.
+    friction: 1e-9 as well once the arms move (chunks 2 and 3, 600 substeps).  The start from rest is different: with
+    every velocity inside the friction law's regularisation band (|v| in [1e-8, 2e-8] m/s, integrated explicitly with
+    dt mu g / tol >> 2) the model amplifies round-off by 1e7 within 60 substeps — the ORACLE ITSELF, restarted with its
+    velocities perturbed by 1e-12 m/s, moves by 1e-5 m/s in chunk 1 and not at all (2.6e-12) in chunks 2 and 3
+    (measured, seeds 2-5).  Chunk 1 is therefore bounded by 20 x the largest divergence among three perturbed oracle
+    replicas (calibrated on the spot, never below 1e-9), after which the CUDA state is re-synchronised with the oracle's."""
     import torch
     nat = _native()
     p, make_oracle = _random_assembly(seed, 1.0 if friction else 0.0)
@@ -1061,11 +1057,11 @@ def test_randomized_assembly_vs_c_oracle(seed, friction):
             asm = make_oracle()
             prng = np.random.default_rng(77 + rep)
             for rod in asm.arms:      # what "another correct implementation" looks like after a few substeps
-                rod.velocity_collection[...] += 1e-11 * prng.standard_normal(rod.velocity_collection.shape) * 0.1
-            for c, st in enumerate(_oracle_states(asm, p)):
-                for fk in FIELDS.values():
-                    bound[c][fk] = max(bound[c][fk], 20 * max(_asm_err(st[fk][a], ref[c][fk][a], fk) for a in range(n_arm)))
-                bound[c]["head"] = max(bound[c]["head"], 20 * max(_asm_err(st["head"][sl], ref[c]["head"][sl], fk) for sl, fk in HEAD_SLICES))
+                rod.velocity_collection[...] += 1e-12 * prng.standard_normal(rod.velocity_collection.shape)
+            st = _oracle_states(asm, dict(p, rest_kappa=p["rest_kappa"][:1]))[0]
+            for fk in FIELDS.values():
+                bound[0][fk] = max(bound[0][fk], 20 * max(_asm_err(st[fk][a], ref[0][fk][a], fk) for a in range(n_arm)))
+            bound[0]["head"] = max(bound[0]["head"], 20 * max(_asm_err(st["head"][sl], ref[0]["head"][sl], fk) for sl, fk in HEAD_SLICES))
             asm.close()
     from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
     n_env, r0 = 3, 0.35 * 0.02
@@ -1101,6 +1097,15 @@ def test_randomized_assembly_vs_c_oracle(seed, friction):
                 err = _asm_err(hd[e, sl], ref[chunk]["head"][sl], fk)
                 worst, worst_ratio = max(worst, err), max(worst_ratio, err / bound[chunk]["head"])
                 assert err < bound[chunk]["head"], f"seed {seed} chunk {chunk} head {fk}: {err:.3e} (bound {bound[chunk]['head']:.1e})"
+        if friction and chunk == 0:
+            # re-synchronise after the chaotic start from rest: the oracle's state goes into the CUDA handle
+            fl = h.fields()
+            for fk in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
+                fl[fk][:] = torch.as_tensor(ref[0][fk], device="cuda")
+            h.head_tensor()[:, :18] = torch.as_tensor(ref[0]["head"], device="cuda")
+            worst_chunk0, worst = worst, 0.0
+    if friction:
+        print(f"   (chunk 1, start from rest: worst {worst_chunk0:.2e} against a calibrated bound of {max(bound[0].values()):.1e})")
     print(f"randomized assembly seed {seed} friction {friction}: n_arm {n_arm} n_elem {n_elem} dt {dt:.2e} worst {worst:.2e} "
           f"(worst err/bound {worst_ratio:.2f}; largest bound {max(max(b.values()) for b in bound):.1e})")
     h.close()

@@ -73,3 +73,32 @@ def test_ranges_are_nested_and_match_the_documented_angles():
     assert const("kNarrowExpZ") < const("kSmallExpZ")
     deg = lambda u: math.degrees(2 * math.asin(math.sqrt(u)))
     assert abs(deg(const("kNarrowBendU")) - 23.1) < 0.1 and abs(deg(const("kMidBendU")) - 36.9) < 0.1 and abs(deg(const("kSmallBendU")) - 60.0) < 1e-9
+
+
+def test_lean_kernel_maps():
+    """Tables of the lean kernel (rod_kernel_lean.cuh): the trace-free bend map in w2 = 4 sin^2(theta) with the
+    reference's 1e-10 guard inside, and sin(t)/t, (1 - cos t)/t^2 with exact leading constants."""
+    rng = np.random.default_rng(1)
+    # bend: theta'/sin(theta'), theta' = acos(cos(theta) - 1e-10), as a function of w2
+    c, hi = table("SR_COEF_BENDW"), const("kNarrowBendW2")
+    assert len(c) == 10
+    w2 = np.concatenate([rng.uniform(0, hi, 1500), [0.0, hi, 1e-12, 1e-6]])
+    def ref(w):
+        th = mp.acos(mp.sqrt(1 - mp.mpf(float(w)) / 4) - mp.mpf("1e-10"))
+        return float(th / mp.sin(th))
+    want = np.array([ref(w) for w in w2])
+    assert np.abs(horner(c, w2) / want - 1.0).max() < 8e-16
+    # the range is the same 23.07 degrees as the u-based narrow map: w2 = 4 sin^2(theta) = 16 u (1 - u)
+    u = const("kNarrowBendU")
+    assert abs(16 * u * (1 - u) - hi) < 1e-12
+    # rotation maps
+    q = np.concatenate([rng.uniform(0, const("kNarrowRotQ"), 1500), [const("kNarrowRotQ"), 1e-14]])
+    g, h = table("SR_COEF_SINCG"), table("SR_COEF_COSCH")
+    assert len(g) == 3 and len(h) == 3
+    A = 1.0 + q * horner(g, q)
+    B = 0.5 + q * horner(h, q)
+    wantA = np.array([float(SINC(mp.mpf(float(v)))) for v in q])
+    wantB = np.array([float(COSC(mp.mpf(float(v)))) for v in q])
+    assert np.abs(A / wantA - 1.0).max() < 1.5e-15 and np.abs(B / wantB - 1.0).max() < 6e-16
+    # the damper's quadratic drops z^3 / 6
+    assert const("kLeanExpZ") ** 3 / 6 < 1.5e-15
