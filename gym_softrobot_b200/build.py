@@ -31,16 +31,13 @@ PACKED_SIZES = [(256, 2), (384, 1), (512, 1), (544, 1), (768, 1), (1024, 1)]   #
 def translation_units():
     """[(object name, source, extra -D flags, header deps)]"""
     tus = [("api", "softrod_api.cu", [], _COMMON), ("warp", "inst_warp.cu", [], _COMMON)]
-    for nt, minb in LEAN_EXTRA_SIZES:
-        tus.append((f"lean_{nt}", "inst_lean.cu", [f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}"],
-                    _COMMON + ["rod_kernel_lean.cuh"]))
+    for t in ("double", "float"):
+        for nt, minb in LEAN_EXTRA_SIZES + PACKED_SIZES:
+            tus.append((f"lean_{t}_{nt}", "inst_lean.cu", [f"-DSR_TU_T={t}", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}"],
+                        _COMMON + ["rod_kernel_lean.cuh"]))
     for nt, minb in PACKED_SIZES:
-        tus.append((f"lean_{nt}", "inst_lean.cu", [f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}"],
-                    _COMMON + ["rod_kernel_lean.cuh"]))
         for t in ("double", "float"):
-            for grp in (0, 1, 2, 3):
-                if t == "double" and grp == 0:
-                    continue    # FP64 lean path = rod_kernel_lean.cuh
+            for grp in (1, 2, 3):    # (the lean configs of both types run rod_kernel_lean.cuh)
                 tus.append((f"packed_{t}_{nt}_g{grp}", "inst_packed.cu",
                             [f"-DSR_TU_T={t}", f"-DSR_TU_F64={int(t == 'double')}", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}", f"-DSR_TU_GROUP={grp}"],
                             _COMMON + ["rod_kernel_packed.cuh"]))

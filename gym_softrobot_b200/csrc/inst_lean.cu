@@ -1,18 +1,20 @@
-// inst_lean.cu — the lean FP64 kernel (rod_kernel_lean.cuh) for one CTA size:  -DSR_TU_NT=<threads> -DSR_TU_MINB=<n>
+// inst_lean.cu — the lean kernel (rod_kernel_lean.cuh) for one storage type and CTA size:
+//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n>
 #include <atomic>
 #include "launch.cuh"
 #include "rod_kernel_lean.cuh"
 
 namespace sr {
 
-template <int NT, int MINB, bool FASTONLY> static cudaError_t lean_opt_in() {
+template <typename T, int NT, int MINB, bool FASTONLY> static cudaError_t lean_opt_in() {
+  // the opt-in above 48 KB is a per-device attribute of the function: one bit per device ordinal
   static std::atomic<unsigned long long> opted{0};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   const unsigned long long bit = 1ULL << (dev & 63);
   if (!(opted.load(std::memory_order_relaxed) & bit)) {
-    e = cudaFuncSetAttribute(rod_lean_kernel<NT, MINB, FASTONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(rod_lean_kernel<T, NT, MINB, FASTONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(lean_smem_words(NT) * sizeof(double)));
     if (e != cudaSuccess) return e;
     opted.fetch_or(bit, std::memory_order_relaxed);
@@ -20,24 +22,24 @@ template <int NT, int MINB, bool FASTONLY> static cudaError_t lean_opt_in() {
   return cudaSuccess;
 }
 
-template <int NT, int MINB, bool FASTONLY> cudaError_t launch_lean_kernel(const RodArgs<double> &A, int grid, cudaStream_t s) {
-  cudaError_t e = lean_opt_in<NT, MINB, FASTONLY>();
+template <typename T, int NT, int MINB, bool FASTONLY> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s) {
+  cudaError_t e = lean_opt_in<T, NT, MINB, FASTONLY>();
   if (e != cudaSuccess) return e;
-  rod_lean_kernel<NT, MINB, FASTONLY><<<grid, NT, lean_smem_words(NT) * sizeof(double), s>>>(A);
+  rod_lean_kernel<T, NT, MINB, FASTONLY><<<grid, NT, lean_smem_words(NT) * sizeof(double), s>>>(A);
   return cudaGetLastError();
 }
 
-template <int NT, int MINB, bool FASTONLY> int lean_ctas_per_sm() {
-  if (lean_opt_in<NT, MINB, FASTONLY>() != cudaSuccess) return 0;
+template <typename T, int NT, int MINB, bool FASTONLY> int lean_ctas_per_sm() {
+  if (lean_opt_in<T, NT, MINB, FASTONLY>() != cudaSuccess) return 0;
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rod_lean_kernel<NT, MINB, FASTONLY>, NT,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rod_lean_kernel<T, NT, MINB, FASTONLY>, NT,
                                                     lean_smem_words(NT) * sizeof(double)) != cudaSuccess) return 0;
   return nb;
 }
 
-template cudaError_t launch_lean_kernel<SR_TU_NT, SR_TU_MINB, true>(const RodArgs<double> &, int, cudaStream_t);
-template cudaError_t launch_lean_kernel<SR_TU_NT, SR_TU_MINB, false>(const RodArgs<double> &, int, cudaStream_t);
-template int lean_ctas_per_sm<SR_TU_NT, SR_TU_MINB, true>();
-template int lean_ctas_per_sm<SR_TU_NT, SR_TU_MINB, false>();
+template cudaError_t launch_lean_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, true>(const RodArgs<SR_TU_T> &, int, cudaStream_t);
+template cudaError_t launch_lean_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, false>(const RodArgs<SR_TU_T> &, int, cudaStream_t);
+template int lean_ctas_per_sm<SR_TU_T, SR_TU_NT, SR_TU_MINB, true>();
+template int lean_ctas_per_sm<SR_TU_T, SR_TU_NT, SR_TU_MINB, false>();
 
 }  // namespace sr

@@ -11,10 +11,10 @@ namespace sr {
 template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY>
 cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid, cudaStream_t s);
 
-// lean FP64 kernel (rod_kernel_lean.cuh); grid / split schedule are in A.sk_*
-template <int NT, int MINB, bool FASTONLY> cudaError_t launch_lean_kernel(const RodArgs<double> &A, int grid, cudaStream_t s);
+// lean kernel (rod_kernel_lean.cuh; T = storage type: double = FP64, float = mixed precision); grid / split schedule in A.sk_*
+template <typename T, int NT, int MINB, bool FASTONLY> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s);
 // resident CTAs per SM of that instantiation on the current device (sizes the stream-K grid)
-template <int NT, int MINB, bool FASTONLY> int lean_ctas_per_sm();
+template <typename T, int NT, int MINB, bool FASTONLY> int lean_ctas_per_sm();
 
 // warp-per-rod kernel, faithful (libm, reference operation order) math: the parity build
 template <typename T, int EPL> cudaError_t launch_warp_faithful(const RodArgs<T> &A, int grid, cudaStream_t s);

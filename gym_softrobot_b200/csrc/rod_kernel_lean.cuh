@@ -80,13 +80,32 @@ __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], con
 constexpr int LEAN_REC = 18;        // exchange record per thread (doubles), 144-byte stride: conflict-free LDS.128
 constexpr int lean_smem_words(int nt) { return (LEAN_REC + 6) * (nt + 2); }
 
-template <int NT, int MINB, bool FASTONLY>
+// float overloads of the reciprocal helpers for the FP32 force evaluation of the mixed mode
+__device__ __forceinline__ bool out_of_range(double x, int lim_hi, float) { return hi_abs(x) > lim_hi; }
+__device__ __forceinline__ bool out_of_range(float x, int, float limf) { return !(fabsf(x) <= limf); }
+
+// ST = storage type of the state in HBM.
+//   ST = double: everything in FP64 (the default; parity 1e-9).
+//   ST = float : the optional FP32 mode (SR_DTYPE_F32), mixed precision.  What limits a plain FP32 rod step is not
+//     the accumulation but the force evaluation's input: the stretch / shear strains are differences of O(1)
+//     quantities, Q dx / l0 - z, and every 6e-8 of rounding in Q or dx becomes S * 6e-8 = 5e-4 N of force noise per
+//     element and substep (measured with the all-FP32 kernel of round 1: velocities 4e-4, omega 2e-3 after 1200
+//     substeps).  So the state registers (x, v, Q, w), the kinematic update, the edge vectors, Q dx and the
+//     relative rotation Q+ Q^T stay in FP64 inside a launch (about 130 of the 226 FP64 instructions of a substep);
+//     stresses, couples, damper and all the scalar algebra run in FP32.  Between launches the state is stored in
+//     FP32, with the element edge vectors as fields of their own (F_EDGE) so that the strain survives the
+//     rounding of absolute positions: the launch rebuilds FP64 node positions from node 0 + the running sum of edges.
+template <typename ST, int NT, int MINB, bool FASTONLY>
 __global__ void __launch_bounds__(NT, MINB)
-rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
-  using T = double;
+rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
+  using D = double;
+  constexpr bool MIXED = sizeof(ST) == 4;
+  using F = typename std::conditional<MIXED, float, double>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T *rec = reinterpret_cast<T *>(smem_raw);            // {x0 x1 | x2 v0 | v1 v2 | Q0 Q1 | ... | Q6 Q7 | Q8 - | - -}
-  T *sn = rec + LEAN_REC * (NT + 2);                   // {s0 s1 | s2 N0 | N1 m2}; record NT = zeros (left of element 0)
+  D *rec = reinterpret_cast<D *>(smem_raw);            // {x0 x1 | x2 v0 | v1 v2 | Q0 Q1 | ... | Q6 Q7 | Q8 - | - -}
+  // {s0 s1 | s2 N0 | N1 m2} (FP64: 48-byte records; mixed: 8 floats, 32-byte records); record NT = zeros (left of element 0)
+  F *sn = reinterpret_cast<F *>(rec + LEAN_REC * (NT + 2));
+  constexpr int SNR = MIXED ? 8 : 6;
   __shared__ int sh_flag[256], sh_dom[256];   // one per rod of the CTA (<= NT / 4)
 
   const int tid = threadIdx.x;
@@ -95,7 +114,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
   const int r = tid / tpr, j = tid - r * tpr;
   const bool in_cta = r < rods_per_cta;
   const bool first = (j == 0);
-  if (tid < 6) sn[6 * NT + tid] = T(0);
+  if (tid < SNR) sn[SNR * NT + tid] = F(0);
 
   // Barriers: data only crosses threads of the same rod, so a substep's two synchronisations can be per rod
   // (named barriers over the warps that hold the rod's threads; a warp holding the end of one rod and the start of
@@ -118,6 +137,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
     if (bar_cnt0) asm volatile("bar.sync %0, %1;" ::"r"(bar_id0), "r"(bar_cnt0) : "memory");
     if (bar_cnt1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id1), "r"(bar_cnt1) : "memory");
   };
+
+  // constants of the FP64 part (the mixed mode reads double copies: a float dt would be off by 1e-8)
+  const D c_dt = MIXED ? A.k_dt : (D)A.dt, c_half_dt = MIXED ? A.k_half_dt : (D)A.half_dt;
+  const D c_cv = MIXED ? A.k_c_v : (D)A.c_v;
 
   // ---- the segments this CTA runs ------------------------------------------------------------------------------
   const int K = A.n_substeps;
@@ -159,9 +182,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
     const int t_next2 = vor_ok ? tid + 2 : t_next;
     const int t_prev = (active && j > 0) ? tid - 1 : NT;
 
-    T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
-    T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
-    T *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
+    D x[3] = {D(0), D(0), D(0)}, v[3] = {D(0), D(0), D(0)}, w[3] = {D(0), D(0), D(0)};
+    D Q[9] = {D(1), D(0), D(0), D(0), D(1), D(0), D(0), D(0), D(1)};
+    ST *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
+    const ST *bc = A.bc + (size_t)(active ? env : 0) * BC_DIM;
     if (s_begin > 0) {
       // continue an item the previous slot started: wait for its hand-over, then take the registers back
       if (tid == 0) {
@@ -170,43 +194,67 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
         __threadfence();
       }
       __syncthreads();
-      const T *sc = A.sk_scratch + (size_t)(p - 1) * LEAN_REC * NT;
+      const D *sc = A.sk_scratch + (size_t)(p - 1) * LEAN_REC * NT;
 #pragma unroll
       for (int c = 0; c < 3; c++) { x[c] = sc[c * NT + tid]; v[c] = sc[(3 + c) * NT + tid]; w[c] = sc[(15 + c) * NT + tid]; }
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c] = sc[(6 + c) * NT + tid];
       __syncthreads();
       if (tid == 0) A.sk_flag[p - 1] = 0;   // (graph-safe: the flag is back to 0 before the launch ends)
-    } else if (active) {
+    } else {
+      if (active) {
 #pragma unroll
-      for (int c = 0; c < 3; c++) {
-        x[c] = st[(F_POS + c) * stride + j];
-        v[c] = st[(F_VEL + c) * stride + j];
-        w[c] = st[(F_OMEGA + c) * stride + j];   // slot n holds 0 (never written by anyone)
+        for (int c = 0; c < 3; c++) {
+          x[c] = (D)st[(F_POS + c) * stride + j];
+          v[c] = (D)st[(F_VEL + c) * stride + j];
+          w[c] = (D)st[(F_OMEGA + c) * stride + j];   // slot n holds 0 (never written by anyone)
+        }
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c] = (D)st[(F_DIR + c) * stride + j];  // slot n holds I
       }
+      if (MIXED) {
+        // FP64 node positions whose differences are the stored FP32 edge vectors exactly: node 0 (after the BC's
+        // overwrite) + the running sum of the rod's edges, accumulated in element order
+        D *eb = rec;   // 3 rows of NT + 2
 #pragma unroll
-      for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
+        for (int c = 0; c < 3; c++) eb[c * (NT + 2) + tid] = elem_ok ? (D)st[(F_EDGE + c) * stride + j] : D(0);
+        __syncthreads();
+        if (active) {
+          D xb[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) xb[c] = (D)st[(F_POS + c) * stride];
+          if (A.bc_kind == BC_PENDULUM_SLIDER) { xb[1] = (D)bc[1]; xb[2] = (D)bc[2]; }
+          else if (A.bc_kind != BC_FREE) { xb[0] = (D)bc[0]; xb[1] = (D)bc[1]; xb[2] = (D)bc[2]; }
+          for (int i = 0; i < j; i++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) xb[c] += eb[c * (NT + 2) + tid - j + i];
+          }
+#pragma unroll
+          for (int c = 0; c < 3; c++) x[c] = xb[c];
+        }
+        __syncthreads();
+      }
     }
     // per-thread constants: zero where there is nothing to integrate (tip thread's pseudo-element, idle threads).
     // Only three 64-bit values stay live across the substep loop (dtim_cv, irg, base0): the kernel sits at the
     // 128-register cap of 2 x 256 threads per SM, and every further invariant becomes a local-memory reload per substep.
-    const T dtim_cv = active ? A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
-    const T irg = A.inv_rest_len * (elem_ok ? st[F_GAMMA * stride + j] : T(1));   // 1 / rest_length_j (F_GAMMA = (L/n) / l0_j)
+    const D dtim_cv = active ? (MIXED ? A.k_dt_inv_mass : (D)A.dt_inv_mass) * c_cv * ((j == 0 || j == n) ? D(2) : D(1)) : D(0);
+    // 1 / rest_length_j (F_GAMMA = (L/n) / l0_j); the mixed mode's uniform 1/l0 is the double copy
+    const D irg = (MIXED ? A.k_inv_rest_len : (D)A.inv_rest_len) * (elem_ok ? (D)st[F_GAMMA * stride + j] : D(1));
     const bool bc_thread = active && first && A.bc_kind != BC_FREE;
     // BCs pin node 0 / element 0 by overwriting after every kinematic update; applying the overwrite once and
     // never moving the pinned quantities is the same thing (see rod_kernel_packed.cuh): the BC thread integrates its
     // frame with a zero rotation vector
     if (bc_thread) {
-      const T *bc = A.bc + (size_t)env * BC_DIM;
       if (A.bc_kind == BC_PENDULUM_SLIDER) {
-        x[1] = bc[1]; x[2] = bc[2];
+        x[1] = (D)bc[1]; x[2] = (D)bc[2];
 #pragma unroll
-        for (int m = 0; m < 3; m++) { Q[0 + m] = bc[3 + m]; Q[6 + m] = bc[9 + m]; }
+        for (int m = 0; m < 3; m++) { Q[0 + m] = (D)bc[3 + m]; Q[6 + m] = (D)bc[9 + m]; }
       } else {
 #pragma unroll
-        for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+        for (int c = 0; c < 9; c++) Q[c] = (D)bc[3 + c];
 #pragma unroll
-        for (int c = 0; c < 3; c++) x[c] = bc[c];
+        for (int c = 0; c < 3; c++) x[c] = (D)bc[c];
       }
     }
     const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
@@ -214,26 +262,25 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
     const bool z12 = pin_slider || pin_fixed;   // v_y, v_z, w_x, w_z are pinned by both; v_x, w_y by the clamp only
     // x component of the velocity update's constant term: dt c_v g_x, or, on the node that carries the base point
     // force, dt c_v F / m (soft_pendulum/build.py:94-105: the force REPLACES gravity's x component there)
-    T base0 = A.gdt_cv[0];
-    if (active && first && A.point_force) base0 = (A.action_dim > 0 ? (T)A.action[(size_t)env * A.action_dim] : T(0)) * dtim_cv;
+    D base0 = MIXED ? A.k_gdt_cv[0] : (D)A.gdt_cv[0];
+    if (active && first && A.point_force) base0 = (A.action_dim > 0 ? (D)A.action[(size_t)env * A.action_dim] : D(0)) * dtim_cv;
 
     // x += hh v ; Q <- R(hh w) Q (merged half steps)
-    auto kinematic = [&](T hh, T eps) {
-      const T hw = bc_thread ? T(0) : hh;
-      T a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
+    auto kinematic = [&](D hh, D eps) {
+      const D hw = bc_thread ? D(0) : hh;
+      D a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
 #pragma unroll
       for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
-      T q = fma(a2, a2, fma(a1, a1, a0 * a0));
+      D q = fma(a2, a2, fma(a1, a1, a0 * a0));
       const bool out = hi_abs(q) > A.lim_rot_hi;
       if (FASTONLY) {
         dom_bad = dom_bad || out;
         rotate_directors_lean(A.sincg, A.cosch, a0, a1, a2, q, eps, Q);
       } else if (!out) rotate_directors_lean(A.sincg, A.cosch, a0, a1, a2, q, eps, Q);
-      else rotate_directors_ref<T>(a0, a1, a2, Q);
+      else rotate_directors_ref<D>(a0, a1, a2, Q);
     };
 
-    const T h = A.half_dt, dt = A.dt;
-    if (s_begin == 0 && K > 0) kinematic(h, T(1e-14));
+    if (s_begin == 0 && K > 0) kinematic(c_half_dt, D(1e-14));
 
     bool check_trace = true;   // first substep of the segment: rule out a state that starts beyond 90 degrees of bend
     auto substep = [&](auto last_tag) {
@@ -248,174 +295,196 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       rod_sync();
 
       // ---- geometry, shear/stretch strain, internal force ---------------------------------------------------
-      T dx[3], dv[3], dx2[3], Qn[9];
+      D dx[3], dv[3], dx2[3], Qn[9];
       {
         const double2 *qq = reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next);
         const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2], a3 = qq[3], a4 = qq[4], a5 = qq[5], a6 = qq[6];
         Qn[0] = a3.x; Qn[1] = a3.y; Qn[2] = a4.x; Qn[3] = a4.y; Qn[4] = a5.x; Qn[5] = a5.y;
         Qn[6] = a6.x; Qn[7] = a6.y; Qn[8] = rec[LEAN_REC * t_next + 14];
         const double2 b0 = *reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next2);
-        const T b2 = rec[LEAN_REC * t_next2 + 2];
+        const D b2 = rec[LEAN_REC * t_next2 + 2];
         dx[0] = a0.x - x[0]; dx[1] = a0.y - x[1]; dx[2] = a1.x - x[2];
         dv[0] = a1.y - v[0]; dv[1] = a2.x - v[1]; dv[2] = a2.y - v[2];
         dx2[0] = b0.x - a0.x; dx2[1] = b0.y - a0.y; dx2[2] = b2 - a1.x;
       }
-      if (!elem_ok) dx[2] = A.rest_len;   // keeps the pseudo-element's quantities finite
-      if (!vor_ok) dx2[2] = A.rest_len;
-      const T l2 = dot3(dx, dx), l2n = dot3(dx2, dx2);
-      const T il = rsqrt_nr(l2), iln = rsqrt_nr(l2n);
-      const T lg = fma(l2, il, T(1e-14));                 // |dx| + 1e-14 (reference guard)
-      const T ilg = fma(T(-1e-14) * il, il, il);          // 1/(l + 1e-14) to first order in 1e-14/l
-      const T lgn = fma(l2n, iln, T(1e-14));              // length of element j+1, recomputed locally
-      const T e = lg * irg;
-      const T em1 = fma(lg, irg, T(-1.0));
-      const T inv_e = A.rest_len * ilg;
-      const T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
-      const T ede = dot3(dx, dv) * (ilg * ilg);           // (de/dt) / e = (dx . dv) / l^2
-      // sigma = e Q t - z = Q dx / l0 - z exactly (e t = dx / l0): no tangent needed here
-      T Qdx[3], nst[3], sfl[3];
+      if (!elem_ok) dx[2] = (D)A.rest_len;   // keeps the pseudo-element's quantities finite
+      if (!vor_ok) dx2[2] = (D)A.rest_len;
+      // lengths: squared in FP64 (they are sums of squares of the FP64 edge), roots and everything after in F
+      const F l2 = (F)dot3(dx, dx), l2n = (F)dot3(dx2, dx2);
+      const F il = rsqrt_nr(l2), iln = rsqrt_nr(l2n);
+      const F lg = fma(l2, il, F(1e-14));                 // |dx| + 1e-14 (reference guard)
+      const F ilg = MIXED ? il : fma(F(-1e-14) * il, il, il);   // 1/(l + 1e-14) to first order in 1e-14/l
+      const F lgn = fma(l2n, iln, F(1e-14));              // length of element j+1, recomputed locally
+      const F e = lg * (F)irg;
+      const F em1 = fma(lg, (F)irg, F(-1.0));
+      const F inv_e = A.rest_len * ilg;
+      const F inv_e_s = elem_ok ? inv_e : F(0);           // the tip thread's pseudo-element carries no stress
+      const F ede = (F)dot3(dx, dv) * (ilg * ilg);        // (de/dt) / e = (dx . dv) / l^2
+      // sigma = e Q t - z = Q dx / l0 - z exactly (e t = dx / l0): no tangent needed here.  FP64 in both modes: this
+      // is the difference of O(1) quantities everything else hangs on.
+      D Qdx[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) Qdx[i] = Q[3 * i] * dx[0];
 #pragma unroll
       for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 1], dx[1], Qdx[i]);
 #pragma unroll
       for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]);
-      // n = S (sigma - 0): shear components are O(strain); the stretch component is a difference of near-equal
-      // numbers and must see the element's own rest length (irg = 1 / l0_k, within 1e-14 of n / L)
-      nst[0] = A.S_over_l[0] * Qdx[0];
-      nst[1] = A.S_over_l[0] * Qdx[1];
-      nst[2] = fma(A.S[2], Qdx[2] * irg, -A.S[2]);
+      const D s3 = fma(Qdx[2], irg, D(-1.0));             // stretch strain, against the element's own rest length
+      // n = S (sigma - 0): shear components are O(strain); the stretch component is a difference of near-equal numbers
+      const F qd0 = (F)Qdx[0], qd1 = (F)Qdx[1], qd2 = (F)Qdx[2];
+      F nst[3];
+      nst[0] = A.S_over_l[0] * qd0;
+      nst[1] = A.S_over_l[0] * qd1;
+      nst[2] = MIXED ? A.S[2] * (F)s3 : (F)fma((D)A.S[2], Qdx[2] * irg, -(D)A.S[2]);
+      F sfl[3];
+      {
+        D sd[3];
+        const D n0 = (D)nst[0], n1 = (D)nst[1], n2 = (D)nst[2];
 #pragma unroll
-      for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
+        for (int i = 0; i < 3; i++) sd[i] = Q[i] * n0;
 #pragma unroll
-      for (int i = 0; i < 3; i++) sfl[i] = fma(Q[3 + i], nst[1], sfl[i]);
+        for (int i = 0; i < 3; i++) sd[i] = fma(Q[3 + i], n1, sd[i]);
 #pragma unroll
-      for (int i = 0; i < 3; i++) sfl[i] = fma(Q[6 + i], nst[2], sfl[i]);
+        for (int i = 0; i < 3; i++) sd[i] = fma(Q[6 + i], n2, sd[i]);
 #pragma unroll
-      for (int i = 0; i < 3; i++) sfl[i] *= inv_e_s;
+        for (int i = 0; i < 3; i++) sfl[i] = (F)sd[i] * inv_e_s;
+      }
 
       // ---- curvature, bending couple --------------------------------------------------------------------------
-      T vec[3];
+      F vec[3];
       {
-        // axial part of Rm - Rm^T (Rm = Q_{j+1} Q_j^T), each component one 6-term FMA chain
+        // axial part of Rm - Rm^T (Rm = Q_{j+1} Q_j^T), each component one 6-term FMA chain (FP64: differences of products)
         auto rm_diff = [&](int a, int b) {
-          T t = Qn[3 * a] * Q[3 * b];
+          D t = Qn[3 * a] * Q[3 * b];
           t = fma(Qn[3 * a + 1], Q[3 * b + 1], t);
           t = fma(Qn[3 * a + 2], Q[3 * b + 2], t);
           t = fma(-Qn[3 * b], Q[3 * a], t);
           t = fma(-Qn[3 * b + 1], Q[3 * a + 1], t);
           return fma(-Qn[3 * b + 2], Q[3 * a + 2], t);
         };
-        vec[0] = rm_diff(2, 1); vec[1] = rm_diff(0, 2); vec[2] = rm_diff(1, 0);
+        vec[0] = (F)rm_diff(2, 1); vec[1] = (F)rm_diff(0, 2); vec[2] = (F)rm_diff(1, 0);
       }
       // |vec|^2 = 4 sin^2(theta): below 90 degrees the log-map factor -theta'/(2 sin theta') / D (theta' the
       // reference's guarded angle acos(cos(theta) - 1e-10)) is a smooth function of it alone.  A bend cannot pass
       // the polynomial's range unseen: every element rotates by <= 0.1 rad per update (the rotation range check),
       // so the angle between neighbours grows by <= 0.2 rad per substep and lands in (range, 90 degrees) first;
       // the first substep of a segment checks the trace once to rule out a state that starts beyond.
-      T w2 = dot3(vec, vec);
-      if (!vor_ok) w2 = T(0);
-      bool bend_out = hi_abs(w2) > A.lim_bend_hi;
-      T u_ref = T(0);
+      F w2 = dot3(vec, vec);
+      if (!vor_ok) w2 = F(0);
+      bool bend_out = out_of_range(w2, A.lim_bend_hi, A.limf_bend);
+      F u_ref = F(0);
       if (check_trace || !FASTONLY) {
         check_trace = false;
-        const T tr = fma(Qn[8], Q[8], fma(Qn[7], Q[7], fma(Qn[6], Q[6], fma(Qn[5], Q[5], fma(Qn[4], Q[4], fma(Qn[3], Q[3],
+        const D tr = fma(Qn[8], Q[8], fma(Qn[7], Q[7], fma(Qn[6], Q[6], fma(Qn[5], Q[5], fma(Qn[4], Q[4], fma(Qn[3], Q[3],
                      fma(Qn[2], Q[2], fma(Qn[1], Q[1], Qn[0] * Q[0]))))))));
-        bend_out = bend_out || (vor_ok && !(tr > T(2.0)));   // cos(theta) <= 1/2
-        u_ref = fma(T(-0.25), tr, T(0.75 + 0.5e-10));        // sin^2(theta'/2), for the reference map
+        bend_out = bend_out || (vor_ok && !(tr > D(2.0)));   // cos(theta) <= 1/2
+        u_ref = (F)fma(D(-0.25), tr, D(0.75 + 0.5e-10));     // sin^2(theta'/2), for the reference map
       }
       if (FASTONLY) dom_bad = dom_bad || bend_out;
-      T fs;
+      F fs;
       {
-        const T *c = A.bendw;   // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved
-        const T z = w2 * w2;
-        T pe = fma(c[8], z, c[6]), po = fma(c[9], z, c[7]);
+        const auto &c = A.bendw;   // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved
+        const F z = w2 * w2;
+        F pe = fma(c[8], z, c[6]), po = fma(c[9], z, c[7]);
         pe = fma(pe, z, c[4]); po = fma(po, z, c[5]);
         pe = fma(pe, z, c[2]); po = fma(po, z, c[3]);
         pe = fma(pe, z, c[0]); po = fma(po, z, c[1]);
         fs = fma(po, w2, pe);
       }
       // reference map (elastica/_rotations.py:_inv_rotate) for this thread only
-      if (!FASTONLY && bend_out) fs = bend_factor_ref<T>(u_ref) * A.inv_rest_vor;
-      T kp[3], tau[3];
+      if (!FASTONLY && bend_out) fs = bend_factor_ref<F>(u_ref) * A.inv_rest_vor;
+      F kp[3], tau[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) kp[i] = vec[i] * fs;
       tau[0] = A.B[0] * kp[0]; tau[1] = A.B[0] * kp[1]; tau[2] = A.B[2] * kp[2];
       // kappa x (B kappa) with B1 = B2:  ((B3 - B1) k2 k3, (B1 - B3) k1 k3, 0)
-      const T k2b = kp[2] * A.BDH;                        // (B3 - B1) D / 2: the quadrature weight of A_h folded in
-      const T kx0 = kp[1] * k2b, kx1 = -(kp[0] * k2b);
-      const T eps_v = (lgn + lg) * A.half_inv_rest_vor;
-      T ie3 = rcp_nr(eps_v * eps_v * eps_v);
-      if (!vor_ok) ie3 = T(0);
-      const T m0 = tau[0] * ie3, m1 = tau[1] * ie3, m2 = tau[2] * ie3;
+      const F k2b = kp[2] * A.BDH;                        // (B3 - B1) D / 2: the quadrature weight of A_h folded in
+      const F kx0 = kp[1] * k2b, kx1 = -(kp[0] * k2b);
+      const F eps_v = (lgn + lg) * A.half_inv_rest_vor;
+      F ie3 = rcp_nr(eps_v * eps_v * eps_v);
+      if (!vor_ok) ie3 = F(0);
+      const F m0 = tau[0] * ie3, m1 = tau[1] * ie3, m2 = tau[2] * ie3;
       // local couples share one 1/e factor:  (Qt x n) l0 + (Jw/e) x w + (Jw/e) (de/dt)/e
       //   = [ (Q dx) x n + (Jw) x w + (Jw) (de/dt)/e ] / e ; with S1 = S2 and J1 = J2 the cross products collapse:
       //   (Q dx) x n = (Qdx1 c, -Qdx0 c, 0), c = n3 - S1' Qdx3 ;  (Jw) x w = (w1 t, -w0 t, 0), t = (J1 - J3) w3
-      const T cc = fma(-A.S_over_l[0], Qdx[2], nst[2]);
-      const T tg = -(w[2] * A.J[0]);                      // (J1 - J3) w3 = -J1 w3 for a circular section (J3 = 2 J1)
-      const T je = ede * A.J[0], je2 = je + je;
-      const T h0 = fma(Qdx[1], cc, fma(w[1], tg, je * w[0]));
-      const T h1 = fma(-Qdx[0], cc, fma(-w[0], tg, je * w[1]));
-      const T h2 = je2 * w[2];
-      T tql[3];
+      const F wf0 = (F)w[0], wf1 = (F)w[1], wf2 = (F)w[2];
+      const F cc = fma(-A.S_over_l[0], qd2, nst[2]);
+      const F tg = -(wf2 * A.J[0]);                       // (J1 - J3) w3 = -J1 w3 for a circular section (J3 = 2 J1)
+      const F je = ede * A.J[0], je2 = je + je;
+      const F h0 = fma(qd1, cc, fma(wf1, tg, je * wf0));
+      const F h1 = fma(-qd0, cc, fma(-wf0, tg, je * wf1));
+      const F h2 = je2 * wf2;
+      F tql[3];
       tql[0] = fma(h0, inv_e, fma(kx0, ie3, m0));          // + m_j + c_j/2  (own element)
       tql[1] = fma(h1, inv_e, fma(kx1, ie3, m1));
       tql[2] = fma(h2, inv_e, m2);
-      {   // {s0 s1 | s2 N0 | N1 m2}: N = c_j/2 - m_j goes to element j+1 (third component: -m2, negated by the reader)
-        double2 *o = reinterpret_cast<double2 *>(sn + 6 * tid);
-        o[0] = make_double2(sfl[0], sfl[1]);
-        o[1] = make_double2(sfl[2], fma(kx0, ie3, -m0));
-        o[2] = make_double2(fma(kx1, ie3, -m1), m2);
+      // {s0 s1 | s2 N0 | N1 m2}: N = c_j/2 - m_j goes to element j+1 (third component: -m2, negated by the reader)
+      if (MIXED) {
+        float4 *o = reinterpret_cast<float4 *>(sn + SNR * tid);
+        o[0] = make_float4((float)sfl[0], (float)sfl[1], (float)sfl[2], (float)fma(kx0, ie3, -m0));
+        o[1] = make_float4((float)fma(kx1, ie3, -m1), (float)m2, 0.0f, 0.0f);
+      } else {
+        double2 *o = reinterpret_cast<double2 *>(sn + SNR * tid);
+        o[0] = make_double2((double)sfl[0], (double)sfl[1]);
+        o[1] = make_double2((double)sfl[2], (double)fma(kx0, ie3, -m0));
+        o[2] = make_double2((double)fma(kx1, ie3, -m1), (double)m2);
       }
       // rotational damper c_w^e = c_w exp((e-1) ln c_w) as a quadratic in (e-1) (coefficients made on the host; the
       // range limit keeps the dropped cubic term below 1.4e-15); c_w1 = c_w2 for a circular cross-section
-      T cw0, cw2;
+      F cw0, cw2;
       {
-        const bool out = hi_abs(em1) > A.lim_em1_hi;
+        const bool out = out_of_range(em1, A.lim_em1_hi, A.limf_em1);
         if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
         if (FASTONLY || !out) {
           cw0 = fma(fma(A.cwp[0][2], em1, A.cwp[0][1]), em1, A.cwp[0][0]);
           cw2 = fma(fma(A.cwp[1][2], em1, A.cwp[1][1]), em1, A.cwp[1][0]);
         } else {
-          cw0 = exp_ref<T>(e * A.logc_w[0]);
-          cw2 = exp_ref<T>(e * A.logc_w[2]);
+          cw0 = exp_ref<F>(e * A.logc_w[0]);
+          cw2 = exp_ref<F>(e * A.logc_w[2]);
         }
       }
       if (last && active) {
         // stale observables of the reference: last force evaluation
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          st[(F_TAN + i) * stride + j] = dx[i] * ilg;
-          st[(F_KAPPA + i) * stride + j] = kp[i];
-          st[(F_SIGMA + i) * stride + j] = fma(irg, Qdx[i], (i == 2) ? T(-1) : T(0));
+          st[(F_TAN + i) * stride + j] = (ST)((F)dx[i] * ilg);
+          st[(F_KAPPA + i) * stride + j] = (ST)kp[i];
         }
-        st[F_DIL * stride + j] = e;
+        st[(F_SIGMA + 0) * stride + j] = (ST)(Qdx[0] * irg);
+        st[(F_SIGMA + 1) * stride + j] = (ST)(Qdx[1] * irg);
+        st[(F_SIGMA + 2) * stride + j] = (ST)s3;
+        st[F_DIL * stride + j] = (ST)e;
       }
       rod_sync();
 
       // ---- add the left neighbour's share, dynamic step ---------------------------------------------------------
-      T fint[3], tq[3];
-      {
-        const double2 *qq = reinterpret_cast<const double2 *>(sn + 6 * t_prev);
+      F fint[3], tq[3];
+      if (MIXED) {
+        const float4 *qq = reinterpret_cast<const float4 *>(sn + SNR * t_prev);
+        const float4 a0 = qq[0], a1 = qq[1];
+        fint[0] = sfl[0] - (F)a0.x; fint[1] = sfl[1] - (F)a0.y; fint[2] = sfl[2] - (F)a0.z;
+        tq[0] = tql[0] + (F)a0.w; tq[1] = tql[1] + (F)a1.x; tq[2] = tql[2] - (F)a1.y;
+      } else {
+        const double2 *qq = reinterpret_cast<const double2 *>(sn + SNR * t_prev);
         const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2];
-        fint[0] = sfl[0] - a0.x; fint[1] = sfl[1] - a0.y; fint[2] = sfl[2] - a1.x;
-        tq[0] = tql[0] + a1.y; tq[1] = tql[1] + a2.x; tq[2] = tql[2] - a2.y;
+        fint[0] = sfl[0] - (F)a0.x; fint[1] = sfl[1] - (F)a0.y; fint[2] = sfl[2] - (F)a1.x;
+        tq[0] = tql[0] + (F)a1.y; tq[1] = tql[1] + (F)a2.x; tq[2] = tql[2] - (F)a2.y;
       }
-      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
-      v[0] = fma(fint[0], dtim_cv, fma(v[0], A.c_v, base0));
-      v[1] = fma(fint[1], dtim_cv, fma(v[1], A.c_v, A.gdt_cv[1]));
-      v[2] = fma(fint[2], dtim_cv, fma(v[2], A.c_v, A.gdt_cv[2]));
+      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update (FP64 accumulation)
+      v[0] = fma((D)fint[0], dtim_cv, fma(v[0], c_cv, base0));
+      v[1] = fma((D)fint[1], dtim_cv, fma(v[1], c_cv, MIXED ? A.k_gdt_cv[1] : (D)A.gdt_cv[1]));
+      v[2] = fma((D)fint[2], dtim_cv, fma(v[2], c_cv, MIXED ? A.k_gdt_cv[2] : (D)A.gdt_cv[2]));
       {
-        const T g = elem_ok ? e * A.dt_Jinv0 : T(0), g2 = g * T(0.5);   // dt e / J ; J3 = 2 J1 for a circular section
-        w[0] = fma(g, tq[0], w[0]) * cw0;
-        w[1] = fma(g, tq[1], w[1]) * cw0;
-        w[2] = fma(g2, tq[2], w[2]) * cw2;
+        const F g = elem_ok ? e * A.dt_Jinv0 : F(0), g2 = g * F(0.5);   // dt e / J ; J3 = 2 J1 for a circular section
+        w[0] = fma((D)g, (D)tq[0], w[0]) * (D)cw0;
+        w[1] = fma((D)g, (D)tq[1], w[1]) * (D)cw0;
+        w[2] = fma((D)g2, (D)tq[2], w[2]) * (D)cw2;
       }
       // rate constraints (zeroing BCs commute with the multiplicative damper)
-      v[0] = pin_fixed ? T(0) : v[0]; v[1] = z12 ? T(0) : v[1]; v[2] = z12 ? T(0) : v[2];
-      w[0] = z12 ? T(0) : w[0]; w[1] = pin_fixed ? T(0) : w[1]; w[2] = z12 ? T(0) : w[2];
+      v[0] = pin_fixed ? D(0) : v[0]; v[1] = z12 ? D(0) : v[1]; v[2] = z12 ? D(0) : v[2];
+      w[0] = z12 ? D(0) : w[0]; w[1] = pin_fixed ? D(0) : w[1]; w[2] = z12 ? D(0) : w[2];
 
-      kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));
+      kinematic(last ? c_half_dt : c_dt, last ? D(1e-14) : D(2e-14));
     };
     // the item's last substep ends with a half kinematic step and exports the stale observables: its own copy of the
     // body, so that the loop carries neither the selects nor the branch
@@ -434,7 +503,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
         __syncthreads();
         if (active && first && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
       }
-      T *sc = A.sk_scratch + (size_t)p * LEAN_REC * NT;
+      D *sc = A.sk_scratch + (size_t)p * LEAN_REC * NT;
 #pragma unroll
       for (int c = 0; c < 3; c++) { sc[c * NT + tid] = x[c]; sc[(3 + c) * NT + tid] = v[c]; sc[(15 + c) * NT + tid] = w[c]; }
 #pragma unroll
@@ -456,28 +525,38 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
       redo = active && (sh_dom[r] != 0 || A.redo[env] != 0);
       if (redo && first && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
     }
+    constexpr int RS = NT + 2;
+    if (MIXED) {       // edge vectors of the final FP64 positions: the strain state the next launch starts from
+#pragma unroll
+      for (int c = 0; c < 3; c++) rec[c * RS + tid] = x[c];
+      __syncthreads();
+      if (active && !redo) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) st[(F_EDGE + c) * stride + j] = elem_ok ? (ST)(rec[c * RS + tid + 1] - x[c]) : ST(0);
+      }
+      __syncthreads();
+    }
     bool bad = false;
     if (active && !redo) {
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        st[(F_POS + c) * stride + j] = x[c];
-        st[(F_VEL + c) * stride + j] = v[c];
+        st[(F_POS + c) * stride + j] = (ST)x[c];
+        st[(F_VEL + c) * stride + j] = (ST)v[c];
         bad = bad || (x[c] != x[c]) || (v[c] != v[c]);
       }
       if (j < n) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) st[(F_OMEGA + c) * stride + j] = w[c];
+        for (int c = 0; c < 3; c++) st[(F_OMEGA + c) * stride + j] = (ST)w[c];
 #pragma unroll
-        for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + j] = Q[c];
+        for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + j] = (ST)Q[c];
       }
     }
     // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)
-    T *sh_t = rec;   // 3 rows of NT + 2
-    constexpr int RS = NT + 2;
+    D *sh_t = rec;   // 3 rows of NT + 2
     if (tid < 256) sh_flag[tid] = 0;
     if (active && A.model == MODEL_SOFT_PENDULUM) {
 #pragma unroll
-      for (int i = 0; i < 3; i++) sh_t[i * RS + tid] = (j < n) ? st[(F_TAN + i) * stride + j] : T(0);
+      for (int i = 0; i < 3; i++) sh_t[i * RS + tid] = (j < n) ? (D)st[(F_TAN + i) * stride + j] : D(0);
     }
     __syncthreads();
     if (active && bad) atomicOr(&sh_flag[r], 1);
@@ -486,7 +565,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<double> A) {
     if (active && first && !redo) {
       const bool invalid = sh_flag[r] != 0;
       if (A.model == MODEL_SOFT_PENDULUM) {
-        soft_pendulum_outputs<T>(sh_t + tid, RS, n, (double)x[0], (double)v[0],
+        soft_pendulum_outputs<D>(sh_t + tid, RS, n, x[0], v[0],
                                  A.action_dim > 0 ? A.action[(size_t)env * A.action_dim] : 0.0f, invalid,
                                  A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
       } else {

@@ -92,12 +92,15 @@ template <typename T> struct RodArgs {
   T dt_Jinv0;                         // dt / J1
   T bendw[10];                        // -theta'/(2 D sin theta') as a polynomial in |axial(R - R^T)|^2 (SR_COEF_BENDW)
   T cwp[2][3];                        // c_w^e as a quadratic in (e - 1), components 0 (= 1) and 2
-  T sincg[3], cosch[3];               // sin(t)/t = 1 + q g(q), (1 - cos t)/t^2 = 1/2 + q h(q)
+  double sincg[3], cosch[3];          // sin(t)/t = 1 + q g(q), (1 - cos t)/t^2 = 1/2 + q h(q)  (the rotation update is FP64 in both modes)
+  // double copies of what the FP64 part of the mixed (FP32-storage) mode reads
+  double k_dt, k_half_dt, k_c_v, k_gdt_cv[3], k_dt_inv_mass, k_inv_rest_len;
+  float limf_bend, limf_em1;          // range limits of the mixed mode's FP32 quantities
   int lim_rot_hi, lim_bend_hi, lim_em1_hi;   // range limits as high words (integer-pipe compares)
   // stream-K schedule: items of sk_rods_per_cta envs; sk_split = slots own equal substep ranges and hand partial
   // items over through sk_scratch[slot][18][NT] / sk_flag[slot]
   int sk_rods_per_cta, sk_items, sk_split, sk_rodsync;   // sk_rodsync: per-rod named barriers inside the substep loop
-  T *sk_scratch; int *sk_flag;
+  double *sk_scratch; int *sk_flag;
 };
 
 template <typename T, int EPL> struct Vec;

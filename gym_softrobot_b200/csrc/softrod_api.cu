@@ -172,7 +172,7 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   {
     const double cw2[] = SR_COEF_BENDW, sg[] = SR_COEF_SINCG, ch[] = SR_COEF_COSCH;
     for (int i = 0; i < 10; i++) A.bendw[i] = (T)(cw2[i] * (-0.5 / rl));
-    for (int i = 0; i < 3; i++) { A.sincg[i] = (T)sg[i]; A.cosch[i] = (T)ch[i]; }
+    for (int i = 0; i < 3; i++) { A.sincg[i] = sg[i]; A.cosch[i] = ch[i]; }
     // c_w^e = c_w exp(z), z = (e - 1) ln c_w, |z| <= kLeanExpZ: 1 + z + z^2/2 with the powers of ln c_w folded in
     double lmax = 0.0;
     for (int k = 0; k < 2; k++) {
@@ -180,6 +180,11 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
       lmax = fmax(lmax, fabs(lc));
       A.cwp[k][0] = (T)cw; A.cwp[k][1] = (T)(cw * lc); A.cwp[k][2] = (T)(cw * 0.5 * lc * lc);
     }
+    A.k_dt = c.dt; A.k_half_dt = 0.5 * c.dt; A.k_dt_inv_mass = c.dt / mass; A.k_inv_rest_len = 1.0 / rl;
+    A.k_c_v = c.damping_constant >= 0.0 ? exp(-c.damping_constant * c.dt) : 1.0;
+    for (int i = 0; i < 3; i++) A.k_gdt_cv[i] = c.gravity[i] * c.dt * A.k_c_v;
+    A.limf_bend = (float)sr::kNarrowBendW2;
+    A.limf_em1 = lmax > 0.0 ? (float)fmin(sr::kLeanExpZ / lmax, 1e30) : 3.0e38f;
     A.lim_rot_hi = hi_word(sr::kNarrowRotQ);
     A.lim_bend_hi = hi_word(sr::kNarrowBendW2);
     A.lim_em1_hi = lmax > 0.0 ? hi_word(fmin(sr::kLeanExpZ / lmax, 1e300)) : 0x7fefffff;   // no damper: any finite stretch
@@ -255,7 +260,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 // Lean FP64 path: grid and stream-K schedule.  With more items than resident CTA slots the grid is the slot
 // count and every slot gets the same number of item-substeps (rod_kernel_lean.cuh); partial items travel through
 // sk_scratch.  The fallback launch (redo_filter) visits flagged envs only and keeps one CTA per item.
-template <int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_handle *h, sr::RodArgs<double> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / (A.n_elem + 1);
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "rod does not fit one CTA of the lean kernel");
   const int items = (A.n_env + rods_per_cta - 1) / rods_per_cta;
@@ -263,7 +268,7 @@ template <int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_handle *h, sr
     cudaDeviceProp prop;
     SR_CUDA(cudaGetDeviceProperties(&prop, h->cfg.device));
     // both variants of a pair are sized alike (same launch bounds); take the smaller answer to be safe
-    const int a = sr::lean_ctas_per_sm<NT, MINB, true>(), b = sr::lean_ctas_per_sm<NT, MINB, false>();
+    const int a = sr::lean_ctas_per_sm<T, NT, MINB, true>(), b = sr::lean_ctas_per_sm<T, NT, MINB, false>();
     h->sk_slots = prop.multiProcessorCount * (a < b ? a : b);
     if (h->sk_slots < 1) return fail(SR_E_CUDA, "lean kernel: occupancy query failed");
     SR_CUDA(cudaMalloc(&h->sk_scratch, (size_t)h->sk_slots * 18 * NT * sizeof(double)));
@@ -275,20 +280,20 @@ template <int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_handle *h, sr
   A.sk_scratch = (double *)h->sk_scratch; A.sk_flag = h->sk_flag;
   A.sk_rodsync = rodsync_setting();
   const int grid = A.sk_split ? h->sk_slots : items;
-  cudaError_t e = sr::launch_lean_kernel<NT, MINB, FASTONLY>(A, grid, s);
+  cudaError_t e = sr::launch_lean_kernel<T, NT, MINB, FASTONLY>(A, grid, s);
   h->launches++;
   if (e != cudaSuccess) return cuda_fail("rod_lean_kernel launch", e);
   return SR_OK;
 }
 
-template <int NT, int MINB> int launch_lean_pair(sr_handle *h, sr::RodArgs<double> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB> int launch_lean_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_fast_pair(h, A, s)) {
     // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
-    int rc = launch_lean_impl<NT, MINB, true>(h, A, s);
+    int rc = launch_lean_impl<T, NT, MINB, true>(h, A, s);
     if (rc != SR_OK) return rc;
     A.redo_filter = 1;
   }
-  return launch_lean_impl<NT, MINB, false>(h, A, s);
+  return launch_lean_impl<T, NT, MINB, false>(h, A, s);
 }
 
 template <typename T> bool is_lean_config(const sr::RodArgs<T> &A) {
@@ -339,16 +344,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     }
     return launch_packed_impl<T, NT, MINB, true, true, false, false>(h, A, s);
   }
-  if constexpr (F64) {   // lean FP64: its own kernel
-    return launch_lean_pair<NT, MINB>(h, A, s);
-  } else {               // lean FP32: generic kernel
-    if (use_fast_pair(h, A, s)) {
-      int rc = launch_packed_impl<T, NT, MINB, false, false, false, false, false, true>(h, A, s);
-      if (rc != SR_OK) return rc;
-      A.redo_filter = 1;
-    }
-    return launch_packed_impl<T, NT, MINB, false, false, false, false>(h, A, s);
-  }
+  return launch_lean_pair<T, NT, MINB>(h, A, s);   // lean configs (FP64, and FP32 storage = mixed precision): rod_kernel_lean.cuh
 }
 
 // CTA size of the packed kernels.  Registers cap the SM at 512 resident threads (128 regs), so the
@@ -398,20 +394,18 @@ int lean_threads_setting(int n_elem) {
 }
 
 template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  if constexpr (std::is_same<T, double>::value) {
-    if (is_lean_config(A)) {
-      if (A.n_elem + 1 <= 160) {
-        if (lean_threads_override() == 160) return launch_lean_pair<160, 3>(h, A, s);
-        if (lean_threads_override() == 320) return launch_lean_pair<320, 2>(h, A, s);
-      }
-      switch (lean_threads_setting(h->cfg.n_elem)) {
-        case 1024: return launch_lean_pair<1024, 1>(h, A, s);
-        case 768: return launch_lean_pair<768, 1>(h, A, s);
-        case 544: return launch_lean_pair<544, 1>(h, A, s);
-        case 512: return launch_lean_pair<512, 1>(h, A, s);
-        case 384: return launch_lean_pair<384, 1>(h, A, s);
-        default: return launch_lean_pair<256, 2>(h, A, s);
-      }
+  if (is_lean_config(A)) {
+    if (A.n_elem + 1 <= 160) {
+      if (lean_threads_override() == 160) return launch_lean_pair<T, 160, 3>(h, A, s);
+      if (lean_threads_override() == 320) return launch_lean_pair<T, 320, 2>(h, A, s);
+    }
+    switch (lean_threads_setting(h->cfg.n_elem)) {
+      case 1024: return launch_lean_pair<T, 1024, 1>(h, A, s);
+      case 768: return launch_lean_pair<T, 768, 1>(h, A, s);
+      case 544: return launch_lean_pair<T, 544, 1>(h, A, s);
+      case 512: return launch_lean_pair<T, 512, 1>(h, A, s);
+      case 384: return launch_lean_pair<T, 384, 1>(h, A, s);
+      default: return launch_lean_pair<T, 256, 2>(h, A, s);
     }
   }
   switch (packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head)) {

@@ -118,7 +118,8 @@ class ArmSingleVectorEnv:
     def reset(self, seed: int = 0):
         self._reset_envs()
         self.step_count.zero_()
-        self.prev_action.zero_()
+        # (the previous action survives a reset, as in the reference: arm_single_env.py:100,203,227 set it at
+        # construction and in step() only)
         self.prev_kappa = self.handle.fields()["kappa"][:, 0, :].clone()
         self.prev_com = self._com().clone()
         obs = self._obs()
@@ -160,7 +161,6 @@ class ArmSingleVectorEnv:
             info["final_obs"], info["reset_idx"] = obs[idx].clone(), idx
             self._reset_envs(idx)
             self.step_count[idx] = 0
-            self.prev_action[idx] = 0
             self.prev_kappa[idx] = self.handle.fields()["kappa"][idx, 0, :]
             self.prev_com[idx] = self._com()[idx]
             fresh = self._obs()

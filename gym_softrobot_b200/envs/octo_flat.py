@@ -158,7 +158,7 @@ class OctoFlatVectorEnv:
         self._n_autoreset = 0
         self._reset_envs(initial=True)
         self.step_count.zero_()
-        self.prev_action.zero_()
+        # (the previous action survives a reset, as in the reference: flat_env.py:135-139,288-293)
         return self._obs(), {}
 
     def step(self, action):
@@ -201,7 +201,6 @@ class OctoFlatVectorEnv:
             info["reset_idx"] = idx
             self._reset_envs(idx)
             self.step_count[idx] = 0
-            self.prev_action[idx] = 0
             fresh = self._obs()
             for k in obs:
                 obs[k][idx] = fresh[k][idx]
@@ -248,7 +247,6 @@ class FlatEnv(Env):
         self._target = (2 - 0.5) * self.np_random.random(2) + 0.5
         self._vec.target[0] = torch.as_tensor(self._target, device=self._vec.device)
         self._vec.step_count.zero_()
-        self._vec.prev_action.zero_()
         self.time = np.float64(0.0)
         self.counter = 0
         return {k: v[0].cpu().numpy() for k, v in self._vec._obs().items()}, {}

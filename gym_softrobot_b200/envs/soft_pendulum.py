@@ -173,6 +173,9 @@ class SoftPendulumVectorEnv:
         self._time_table = np.array(table)
         self._first_truncated = int(np.argmax(self._time_table > final_time))
         self.step_count = torch.zeros(n_env, dtype=torch.int64, device=self.device)
+        # like the reference env (soft_pendulum.py:97,108-147,165) the previous action is set at construction and by
+        # step() only: the observation right after a reset still carries the last action of the episode before
+        self.prev_action = torch.zeros((n_env, 1), dtype=torch.float32, device=self.device)
         self._seed = 0
         self._n_autoreset = 0
 
@@ -194,13 +197,14 @@ class SoftPendulumVectorEnv:
         init = torch.as_tensor(pendulum_init_params(self._draws(range(self.n_env), True)), device=self.device)
         self.handle.reset(init.contiguous())
         self.step_count.zero_()
-        self.handle.observe(None, self.obs)
+        self.handle.observe(self.prev_action, self.obs)
         return self.obs.clone(), {}
 
     def step(self, action):
         torch = self.torch
         action = action.to(device=self.device, dtype=torch.float32).reshape(self.n_env, 1).contiguous()
         self.handle.step(action, self.step_skip, self.obs, self.reward, self.terminated)
+        self.prev_action = action
         self.step_count += 1
         truncated = self.step_count >= self._first_truncated
         terminated = self.terminated.bool()
@@ -217,7 +221,7 @@ class SoftPendulumVectorEnv:
             self.handle.reset(init.contiguous(), idx.to(torch.int32).contiguous())
             self.step_count[idx] = 0
             fresh = torch.empty_like(self.obs)
-            self.handle.observe(None, fresh)
+            self.handle.observe(self.prev_action, fresh)
             obs[idx] = fresh[idx]
         return obs, reward, terminated, truncated, info
 

@@ -230,6 +230,30 @@ def gen_octo_cfg4(seed=42, n=3, n_elems=40, time_step=3e-5, recording_fps=100):
     print("octo cfg4:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
 
 
+def gen_second_episode_reset_obs():
+    """Which observation does reset() return in the SECOND episode?  SoftPendulum / OctoArmSingle / OctoFlat never clear
+    `_prev_action` in reset (soft_pendulum.py:97, arm_single_env.py:100, flat_env.py:135-139), so it still carries the
+    last action; SoftPendulum3D clears it (soft_pendulum_3d.py:68)."""
+    out = {"label": LABEL}
+    for env_id, kw in (("SoftPendulum-v0", {}), ("SoftPendulum3D-v0", {}), ("OctoArmSingle-v0", {}),
+                       ("OctoFlat-v0", {"recording_fps": 50})):
+        env = ref_loader.load_reference_env(env_id, **kw)
+        env.reset(seed=1)
+        env.action_space.seed(1)
+        a = env.action_space.sample()
+        env.step(a)
+        obs2, _ = env.reset(seed=2)
+        tag = env_id.split("-")[0]
+        out[f"{tag}/action"] = np.asarray(a)
+        if isinstance(obs2, dict):
+            for k, v in obs2.items():
+                out[f"{tag}/obs2/{k}"] = v
+        else:
+            out[f"{tag}/obs2"] = obs2
+    np.savez_compressed(os.path.join(OUT, "second_episode_reset_obs.npz"), **out)
+    print("second-episode reset observations:", out["SoftPendulum/obs2"], out["SoftPendulum3D/obs2"][6:8])
+
+
 def gen_spline_forcing(seed=5):
     """The reference's `MuscleTorquesWithVaryingBetaSplines` (muscle_torques_with_bspline.py) driven directly,
     outside any env, to cover what SoftArmTracking-v0 does not: a finite max_rate_of_change_of_activation
@@ -430,6 +454,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "decentralized":
         gen_octo_flat_decentralized()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "episode2":
+        gen_second_episode_reset_obs()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         gen_octo_cfg4()
         sys.exit(0)
@@ -446,6 +473,7 @@ if __name__ == "__main__":
     gen_octo_flat()
     gen_octo_flat_decentralized()
     gen_octo_cfg4()
+    gen_second_episode_reset_obs()
     gen_spline_forcing()
     gen_muscle_torques()
     gen_soft_arm(game_mode=1)

@@ -180,3 +180,25 @@ def test_state_get_set_roundtrip():
     assert torch.equal(h1.state_tensor(), h2.state_tensor()) and torch.equal(o1, o2) and torch.equal(r1, r2)
     assert h1.launch_count >= 3
     h1.close(); h2.close()
+
+
+def test_second_episode_reset_observation_matches_reference(golden_dir):
+    """the reference never clears `_prev_action` in reset() for SoftPendulum / OctoArmSingle / OctoFlat
+    (soft_pendulum.py:97, arm_single_env.py:100, flat_env.py:135-139), so the observation returned by the reset that
+    opens the second episode still carries the last action; SoftPendulum3D does clear it (soft_pendulum_3d.py:68).
+    Fixture: the reference envs themselves (oracle/gen_golden.py:gen_second_episode_reset_obs)."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "second_episode_reset_obs.npz"))
+    for env_id, kw in (("SoftPendulum-v0", {}), ("SoftPendulum3D-v0", {}), ("OctoArmSingle-v0", {}),
+                       ("OctoFlat-v0", {"recording_fps": 50})):
+        tag = env_id.split("-")[0]
+        env = gsb.make(env_id, **kw)
+        env.reset(seed=1)
+        env.step(g[f"{tag}/action"])
+        obs2, _ = env.reset(seed=2)
+        if isinstance(obs2, dict):
+            for k, v in obs2.items():
+                np.testing.assert_allclose(v, g[f"{tag}/obs2/{k}"], rtol=1e-5, atol=1e-6, err_msg=f"{env_id} {k}")
+        else:
+            np.testing.assert_allclose(obs2, g[f"{tag}/obs2"], rtol=1e-5, atol=1e-6, err_msg=env_id)
+        env.close()

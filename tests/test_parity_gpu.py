@@ -7,6 +7,7 @@ are FP64 functions of the state (compared to 1e-9 — they cannot be bit-exact
 unless the state is).
 """
 import os
+import time
 
 import numpy as np
 import pytest
@@ -47,14 +48,38 @@ TINY_RATE = {"velocity_collection": 1e-2, "omega_collection": 1e-1}
 STRAIN_FLOOR = {"kappa": 1e-3, "sigma": 1e-6}
 
 
-def assert_state_close(mine, ref, name, floors, what, tol=TOL):
-    """max|mine - ref| <= tol * max|ref|.  A rate field whose reference magnitude is still tiny (TINY_RATE) may meet the
-    configuration's absolute round-off floor instead; nothing else gets an absolute allowance."""
+def assert_state_close(mine, ref, name, floors, what, tol=TOL, measured=None):
+    """max|mine - ref| <= tol * max|ref|.  Two documented ways out, nothing else:
+    * `measured` (name -> abs divergence of the ORACLE from itself when its input positions move by one ulp, see
+      one_ulp_divergence): up to 20x that — the reference cannot reproduce its own numbers better than this;
+    * a rate field whose reference magnitude is still tiny (TINY_RATE) may meet the absolute round-off floor of
+      rate_floors() instead."""
     scale, err = float(np.abs(ref).max()), float(np.abs(mine - ref).max())
     if err <= tol * max(scale, STRAIN_FLOOR.get(name, 0.0)):
         return
-    ok = name in TINY_RATE and scale < TINY_RATE[name] and err <= tol * scale + floors[name]
-    assert ok, f"{what} {name}: abs err {err:.3e}, rel {err / max(scale, 1e-300):.3e} (|ref| {scale:.3e}, floor {floors.get(name, 0.0):.2e})"
+    if measured is not None and err <= 20.0 * measured.get(name, 0.0):
+        return
+    ok = name in TINY_RATE and scale < TINY_RATE[name] and err <= tol * scale + floors.get(name, 0.0)
+    assert ok, (f"{what} {name}: abs err {err:.3e}, rel {err / max(scale, 1e-300):.3e} (|ref| {scale:.3e}, floor "
+                f"{floors.get(name, 0.0):.2e}, one-ulp divergence of the oracle {(measured or {}).get(name, 0.0):.2e})")
+
+
+def one_ulp_divergence(make_rod, advance, ref, n_rep=2):
+    """How far the C oracle moves from its own result `ref` (name -> array) when every initial position coordinate is
+    nudged to a neighbouring double: the round-off sensitivity of the configuration, measured instead of estimated.
+    (Thin, finely discretised rods amplify position round-off through eps |x| / dl strains: 3e-9 rad/s on
+    |w| = 0.6 rad/s for n_elem = 1023, r = 4 mm after 1000 substeps.)"""
+    out = {k: 0.0 for k in ref}
+    for rep in range(n_rep):
+        rng = np.random.default_rng(4242 + rep)
+        rod = make_rod()
+        x = rod.position_collection
+        x[...] = np.nextafter(x, np.where(rng.random(x.shape) < 0.5, -np.inf, np.inf))
+        advance(rod)
+        for k in ref:
+            out[k] = max(out[k], float(np.abs(getattr(rod, k) - ref[k]).max()))
+        rod.close()
+    return out
 
 
 # ---- multi-rod assemblies against the multi-rod C oracle (VERDICT r1 item 1) ------------------------------------
@@ -93,8 +118,10 @@ def test_golden_substeps(golden_dir, math):
         done = target
         torch.cuda.synchronize()
         f = {k: v[0].cpu().numpy() for k, v in h.fields().items()}
+        # (after 1 and 10 substeps the rod has not started to move: |w| ~ 1e-13 rad/s of pure round-off)
+        floors = rate_floors(1e6, 1000.0, 1.0, 50, 0.05, 1.0)
         for gk, fk in FIELDS.items():
-            assert_state_close(f[fk], g[f"sub{target}/{gk}"], fk, {}, f"math={math} substeps={target}")
+            assert_state_close(f[fk], g[f"sub{target}/{gk}"], fk, floors, f"math={math} substeps={target}")
     h.close()
 
 
@@ -272,14 +299,22 @@ def test_generic_rod_vs_oracle(n_elem, dt, radius):
     rods = [ro.OracleRod(n_elem, init[i, 0:3], init[i, 3:6], init[i, 6:9], 1.0, radius, 1000.0, 1e6, dt,
                          gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3, bc_kind=ro.BC_ONE_END_FIXED)
             for i in range(n_env)]
+    names = ("position_collection", "velocity_collection", "director_collection", "omega_collection")
+    done = 0
     for chunk in (400, 600):   # 1000 substeps in two launches
         obs, rew, term = h.step_host(None, chunk)
+        done += chunk
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
         for i, r in enumerate(rods):
             r.substeps(chunk)
             floors = rate_floors(1e6, 1000.0, 1.0, n_elem, radius, np.abs(r.position_collection).max())
-            for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-                assert_state_close(f[name][i], getattr(r, name), name, floors, f"n={n_elem} env={i}")
+            measured = None
+            if i == 0:    # the oracle's own one-ulp sensitivity for this configuration (same for every env)
+                mk = lambda: ro.OracleRod(n_elem, init[0, 0:3], init[0, 3:6], init[0, 6:9], 1.0, radius, 1000.0, 1e6, dt,
+                                          gravity=(0.0, -9.80665, 0.0), damping_constant=2e-3, bc_kind=ro.BC_ONE_END_FIXED)
+                sens = one_ulp_divergence(mk, lambda rod: rod.substeps(done), {k: getattr(r, k).copy() for k in names})
+            for name in names:
+                assert_state_close(f[name][i], getattr(r, name), name, floors, f"n={n_elem} env={i}", measured=sens)
             np.testing.assert_allclose(obs[i, :3], r.position_collection[:, -1], rtol=2e-6, atol=1e-7)
         assert term.sum() == 0
     h.close()
@@ -340,10 +375,12 @@ def test_soft_pendulum_3d_batched_vs_oracle():
 
 
 def test_fp32_mode_accuracy():
-    """Optional FP32 mode (north star: 1e-4 over 1000 substeps).  Measured after 1200 substeps: positions
-    1e-5 and directors 2e-5 (bar met); velocities 4e-4 (element edge vectors are carried as FP32 state so the
-    strain keeps ~1e-7 resolution; with absolute positions only it was 6e-3); angular velocities are
-    dominated by the reference's runaway base-element w1 (~1e5 rad/s), 2e-3 of that."""
+    """Optional FP32 mode (north star: 1e-4 over 1000 substeps), all four integrated fields after 1200 substeps.
+    SR_DTYPE_F32 stores the state in FP32 and evaluates stresses, couples and the damper in FP32; the kinematic update,
+    the edge vectors, Q dx and Q+ Q^T stay FP64 inside a launch (rod_kernel_lean.cuh) — an all-FP32 step is limited by
+    the strain's cancellation, not by accumulation (round 1: velocities 4e-4, omega 2e-3).  omega is compared on the
+    elements the reference integrates sensibly; the base element's w1, which the reference env lets run away to ~1e5
+    rad/s, is compared relative to itself."""
     import rod_oracle
     from gym_softrobot_b200.envs.soft_pendulum import pendulum_init_params
     nat = _native()
@@ -356,17 +393,23 @@ def test_fp32_mode_accuracy():
     orc = [rod_oracle.OracleSoftPendulum() for _ in range(n_env)]
     for i, o in enumerate(orc):
         o.reset(u01=u[i])
+    worst = {}
     for s in range(3):   # 1200 substeps
         obs, rew, term = h.step_host(acts[s], 400)
         f = {k: v.double().cpu().numpy() for k, v in h.fields().items()}
         for i, o in enumerate(orc):
             ob, r, te, tr, _ = o.step(acts[s][i])
-            assert rel(f["position_collection"][i], o.rod.position_collection) < 1e-4
-            assert rel(f["director_collection"][i], o.rod.director_collection) < 1e-4
-            assert rel(f["velocity_collection"][i], o.rod.velocity_collection) < 2e-3
-            assert rel(f["omega_collection"][i], o.rod.omega_collection) < 1e-2
-            np.testing.assert_allclose(obs[i], ob, rtol=5e-3, atol=5e-3)
+            errs = {"position": rel(f["position_collection"][i], o.rod.position_collection),
+                    "director": rel(f["director_collection"][i], o.rod.director_collection),
+                    "velocity": rel(f["velocity_collection"][i], o.rod.velocity_collection),
+                    "omega": rel(f["omega_collection"][i][:, 1:], o.rod.omega_collection[:, 1:]),
+                    "omega_base": rel(f["omega_collection"][i][:, 0], o.rod.omega_collection[:, 0])}
+            for k, e in errs.items():
+                worst[k] = max(worst.get(k, 0.0), e)
+                assert e < 1e-4, f"step {s} env {i} {k}: {e:.3e}"
+            np.testing.assert_allclose(obs[i], ob, rtol=1e-4, atol=1e-4)
             assert bool(term[i]) == te
+    print("fp32 mode after 1200 substeps:", {k: f"{e:.1e}" for k, e in worst.items()})
     assert h.state_tensor().dtype.itemsize == 4
     h.close()
 
@@ -564,6 +607,10 @@ def test_randomized_rods_vs_oracle(seed):
                      gravity=c["g"], damping_constant=c["damping"], bc_kind=c["bc"])
     o.substeps(300)
     assert np.isfinite(o.position_collection).all(), "unstable random case (test generator problem)"
+    names = ("position_collection", "velocity_collection", "director_collection", "omega_collection")
+    mk = lambda: ro.OracleRod(c["n"], c["init"][0:3], c["init"][3:6], c["init"][6:9], c["L"], c["r"], c["rho"], c["E"], c["dt"],
+                              gravity=c["g"], damping_constant=c["damping"], bc_kind=c["bc"])
+    sens = one_ulp_divergence(mk, lambda rod: rod.substeps(300), {k: getattr(o, k).copy() for k in names})
     for math in (nat.MATH_FAST, nat.MATH_FAITHFUL):
         h = nat.Handle(model=nat.MODEL_ROD, n_env=3, n_elem=c["n"], dt=c["dt"], base_length=c["L"], base_radius=c["r"],
                        density=c["rho"], youngs_modulus=c["E"], gravity=tuple(c["g"]), damping_constant=c["damping"],
@@ -573,7 +620,7 @@ def test_randomized_rods_vs_oracle(seed):
         f = {k: v.cpu().numpy() for k, v in h.fields().items()}
         floors = rate_floors(c["E"], c["rho"], c["L"], c["n"], c["r"], np.abs(o.position_collection).max())
         for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection"):
-            assert_state_close(f[name][1], getattr(o, name), name, floors, f"seed={seed} math={math} n={c['n']} bc={c['bc']}")
+            assert_state_close(f[name][1], getattr(o, name), name, floors, f"seed={seed} math={math} n={c['n']} bc={c['bc']}", measured=sens)
         h.close()
 
 
@@ -1109,3 +1156,95 @@ def test_randomized_assembly_vs_c_oracle(seed, friction):
     print(f"randomized assembly seed {seed} friction {friction}: n_arm {n_arm} n_elem {n_elem} dt {dt:.2e} worst {worst:.2e} "
           f"(worst err/bound {worst_ratio:.2f}; largest bound {max(max(b.values()) for b in bound):.1e})")
     h.close()
+
+
+# ---- an env's bits depend on nothing but the env ----------------------------------------------------
+def _pendulum_batch(n_env, wild, steps, use_async):
+    """SoftPendulum handle of n_env envs: env 0 is the probe (seed 42), the others are either well behaved or spin so
+    fast that every one of them leaves the fast-math range at every step (they are re-run by the safe kernel, and after
+    the first poll of the fallback counter the whole handle drops to the safe kernel alone).  Returns env 0's state after
+    each step, the launch count per step, and the final count."""
+    import torch
+    from gym_softrobot_b200.envs.soft_pendulum import pendulum_init_params
+    nat = _native()
+    h = make_pendulum_handle(n_env, nat.MATH_FAST)
+    u = np.array([u01_for_seed(42)] + [u01_for_seed(100 + i) for i in range(1, n_env)])
+    h.reset_host(pendulum_init_params(u))
+    if wild and n_env > 1:
+        h.fields()["omega_collection"][1:, 2, 1:] = 3000.0     # 0.3 rad per substep about d3: out of the rotation range
+    rng = np.random.default_rng(7)
+    acts = rng.uniform(-22, 22, size=(steps, 1)).astype(np.float32)
+    obs = torch.empty((n_env, 4), dtype=torch.float32, device="cuda")
+    rew = torch.empty(n_env, dtype=torch.float64, device="cuda")
+    term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+    states, launches = [], []
+    for s in range(steps):
+        a = np.repeat(acts[s][None, :], n_env, axis=0)
+        if use_async:
+            h.step(torch.as_tensor(a, device="cuda"), 400, obs, rew, term)
+            if s % 3 == 0:
+                time.sleep(0.002 * (s % 5))       # perturb the host timing the adaptive switch could be sensitive to
+        else:
+            h.step_host(a, 400)
+        states.append(h.state_tensor()[0].clone())
+        launches.append(h.launch_count)
+    torch.cuda.synchronize()
+    h.close()
+    return states, np.diff([1] + launches)
+
+
+def test_env_bits_are_independent_of_the_batch_and_of_the_kernel_pair():
+    """DESIGN.md §5 "bit-identical whatever the batch": one SoftPendulum env stepped 20 times (8000 substeps, actions
+    from a fixed list) alone, among 15 well-behaved envs, and among 15 envs that all fall back — the last case crosses
+    the handle-wide switch from the fast-only / fallback pair to the safe kernel alone (checked through the launch
+    count), so it also shows that both kernels compute the same bits.  torch.equal on the whole state block, every step."""
+    import torch
+    alone, l_alone = _pendulum_batch(1, False, 20, False)
+    calm, l_calm = _pendulum_batch(16, False, 20, False)
+    wild, l_wild = _pendulum_batch(16, True, 20, False)
+    assert np.all(l_alone == 2) and np.all(l_calm == 2)       # fast-only + (empty) fallback every step
+    assert l_wild[0] == 2 and l_wild[-1] == 1, l_wild          # the pair switched itself off on the way
+    for s in range(20):
+        assert torch.equal(alone[s], calm[s]), f"step {s}: env 0 differs between a batch of 1 and a batch of 16"
+        assert torch.equal(alone[s], wild[s]), f"step {s}: env 0 differs when its neighbours fall back / after the switch"
+    assert torch.isfinite(alone[-1][:18]).all()
+
+
+def test_async_path_is_reproducible_across_runs_and_host_timing():
+    """Two runs of the stream-ordered sr_step path (device pointers, no host synchronisation) with different host-side
+    timing, on a handle that crosses the adaptive switch: identical bits for the probe env, step by step."""
+    import torch
+    a, la = _pendulum_batch(16, True, 20, True)
+    b, lb = _pendulum_batch(16, True, 20, False)
+    c, lc = _pendulum_batch(16, True, 20, True)
+    for s in range(20):
+        assert torch.equal(a[s], b[s]) and torch.equal(a[s], c[s]), f"step {s}"
+
+
+def test_contact_env_bits_are_independent_of_its_neighbours():
+    """Same property for a generic-kernel instantiation (plane contact + rest curvature, OctoArmSingle's model): the
+    probe arm's state is bit-identical alone, among calm arms, and among arms bent far outside the fast bend range."""
+    import torch
+    from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
+    nat = _native()
+
+    def run(n_env, wild):
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=50, dt=7e-5, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
+                       bc_kind=nat.BC_FREE, contact=arm_contact_params(), **_ROD)
+        init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+        h.reset_host(init)
+        s = np.linspace(0, 1, 49)
+        rk = h.rest_kappa_tensor()
+        rk[:, 0, :] = torch.as_tensor(8.0 * np.sin(np.pi * s), device="cuda")
+        if wild and n_env > 1:
+            rk[1:, 0, :] = 150.0      # ~60 degrees per element once relaxed: far outside the 37-degree map
+        out = []
+        for _ in range(12):
+            h.step_host(None, 200)
+            out.append(h.state_tensor()[0].clone())
+        h.close()
+        return out
+
+    alone, calm, wild = run(1, False), run(11, False), run(11, True)
+    for s in range(12):
+        assert torch.equal(alone[s], calm[s]) and torch.equal(alone[s], wild[s]), f"step {s}"
