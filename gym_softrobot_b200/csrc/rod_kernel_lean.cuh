@@ -115,6 +115,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   const bool in_cta = r < rods_per_cta;
   const bool first = (j == 0);
   if (tid < SNR) sn[SNR * NT + tid] = F(0);
+  __syncthreads();   // (the per-rod barriers below do not order this store against the other rods' reads)
 
   // Barriers: data only crosses threads of the same rod, so a substep's two synchronisations can be per rod
   // (named barriers over the warps that hold the rod's threads; a warp holding the end of one rod and the start of

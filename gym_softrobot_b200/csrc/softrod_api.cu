@@ -251,6 +251,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / group;
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
+  A.sk_rodsync = rodsync_setting();
   cudaError_t e = sr::launch_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE, FASTONLY>(A, rods_per_cta, grid, s);
   h->launches++;
   if (e != cudaSuccess) return cuda_fail("rod_packed_kernel launch", e);

@@ -1,6 +1,8 @@
 """GPU: Gymnasium-API conformance of every registered env, mirroring the reference's own tests
 (`/root/reference/tests/envs/test_envs.py:18-68`, `test_determinism.py:7-58`), plus the batched
 envs' autoreset and the state get/set entry points."""
+import os
+
 import numpy as np
 import pytest
 
