@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
+    "sr_get_state", "sr_set_state", "sr_copy_from", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
 ]
 
 
@@ -93,6 +93,7 @@ def load_library():
     L.sr_observe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sr_get_state.argtypes = [C.c_void_p, C.POINTER(SrStateView)]
     L.sr_set_state.argtypes = [C.c_void_p, C.POINTER(SrStateView), C.c_void_p]
+    L.sr_copy_from.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     L.sr_get_aux.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_head.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
@@ -373,5 +374,11 @@ class Handle:
         return t[:, :3 * ch].unflatten(1, (3, ch)), t[:, 3 * ch:].unflatten(1, (3, self.n_elem))
 
     def set_state_from(self, other: "Handle"):
+        """Rod arrays only (sr_set_state): see clone_from for a whole-handle copy."""
         v = other.state_view()
         _check(self._lib.sr_set_state(self._h, C.byref(v), self._stream_ptr()))
+
+    def clone_from(self, other: "Handle"):
+        """Everything that evolves or parametrises the envs (sr_copy_from): rod arrays, BC anchors, base controller,
+        rigid heads, rest curvatures, forcing state."""
+        _check(self._lib.sr_copy_from(self._h, other._h, self._stream_ptr()))

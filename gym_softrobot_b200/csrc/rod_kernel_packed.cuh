@@ -103,6 +103,33 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     if (bar_cnt1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id1), "r"(bar_cnt1) : "memory");
   };
 
+  // The contact models work in a frame whose z axis is the plane normal (every dot / cross product with the normal
+  // becomes a component pick).  When the configured normal is not +z (ContinuumSnake: +y) lab-frame vectors —
+  // positions, velocities, director rows, BC anchors, the stale tangents, observations — are rotated by A.lab2int on
+  // load and back on store; for an axis-aligned normal that is a signed permutation, i.e. exact.  Gravity and the
+  // plane origin arrive rotated from the host; omega, kappa, sigma live in the material frame and are untouched.
+  const bool rot_frame = CONTACT && A.rot_on;
+  auto to_int = [&](T (&u)[3]) {
+    if (!rot_frame) return;
+    const T a = u[0], b = u[1], c = u[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[i] = fma(A.lab2int[3 * i + 2], c, fma(A.lab2int[3 * i + 1], b, A.lab2int[3 * i] * a));
+  };
+  auto to_lab = [&](T (&u)[3]) {      // transpose
+    if (!rot_frame) return;
+    const T a = u[0], b = u[1], c = u[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[i] = fma(A.lab2int[6 + i], c, fma(A.lab2int[3 + i], b, A.lab2int[i] * a));
+  };
+  auto rows_to_int = [&](T (&M)[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { T u[3] = {M[3 * i], M[3 * i + 1], M[3 * i + 2]}; to_int(u); M[3 * i] = u[0]; M[3 * i + 1] = u[1]; M[3 * i + 2] = u[2]; }
+  };
+  auto rows_to_lab = [&](T (&M)[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { T u[3] = {M[3 * i], M[3 * i + 1], M[3 * i + 2]}; to_lab(u); M[3 * i] = u[0]; M[3 * i + 1] = u[1]; M[3 * i + 2] = u[2]; }
+  };
+
   T x[3] = {T(0), T(0), T(0)}, v[3] = {T(0), T(0), T(0)}, w[3] = {T(0), T(0), T(0)};
   T Q[9] = {T(1), T(0), T(0), T(0), T(1), T(0), T(0), T(0), T(1)};
   T *st = A.state + (size_t)(active ? rod : 0) * N_FIELDS * stride;
@@ -115,6 +142,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
 #pragma unroll
     for (int c = 0; c < 9; c++) Q[c] = st[(F_DIR + c) * stride + j];  // slot n holds I
+    to_int(x); to_int(v); rows_to_int(Q);
   }
   // FP32: absolute positions resolve an element's strain only to ulp(x)/dl ~ 3e-6, which excites stiff
   // modes; the edge vector dx = x_{j+1} - x_j is therefore carried as state of its own (ulp 2e-9) and
@@ -125,9 +153,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   if (EDGE && active) {
 #pragma unroll
     for (int c = 0; c < 3; c++) ed[c] = st[(F_EDGE + c) * stride + j];
+    to_int(ed);
   }
   T *hd = (MULTI && is_head && live) ? A.head + (size_t)env * HEAD_DIM : nullptr;
-  if (MULTI && hd) {
+  if (MULTI && hd) {     // (assemblies stand on a z-normal plane: sr_create checks, no rotation here)
 #pragma unroll
     for (int c = 0; c < 3; c++) { x[c] = hd[c]; v[c] = hd[3 + c]; w[c] = hd[15 + c]; }
 #pragma unroll
@@ -199,9 +228,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     } else {
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c] = bc[3 + c];
+      rows_to_int(Q);
       if (!MOVING || A.bc_kind == BC_ONE_END_FIXED) {
 #pragma unroll
         for (int c = 0; c < 3; c++) x[c] = bc[c];
+        to_int(x);
       } else {
         T *aux = A.aux + (size_t)env * AUX_DIM;
         if (A.model == MODEL_SOFT_PENDULUM_3D && A.n_substeps > 0) {
@@ -557,8 +588,11 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       // stale observables of the reference: last force evaluation
       if (active) {
 #pragma unroll
+        T tg_out[3] = {dx[0] * ilg, dx[1] * ilg, dx[2] * ilg};
+        to_lab(tg_out);
+#pragma unroll
         for (int i = 0; i < 3; i++) {
-          st[(F_TAN + i) * stride + j] = dx[i] * ilg;
+          st[(F_TAN + i) * stride + j] = tg_out[i];
           st[(F_KAPPA + i) * stride + j] = kp[i];
           st[(F_SIGMA + i) * stride + j] = fma(A.inv_rest_len, Qdx[i], (i == 2) ? T(-1) : T(0));
         }
@@ -611,105 +645,101 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
     if (CONTACT && A.contact_on) {
       // RodPlaneContactWithAnisotropicFriction (elastica/_contact_functions.py), per element j
-      // between nodes j and j+1.  Stage 1: normal response + kinetic friction from the nodal forces
-      // accumulated so far; stage 2: static friction from the forces INCLUDING stage 1 of both
-      // neighbours (nodal forces mix adjacent elements), hence two more exchanges.
+      // between nodes j and j+1, in the frame whose z axis is the plane normal.  Stage 1: normal response + kinetic
+      // friction from the nodal forces accumulated so far; stage 2: static friction from the forces INCLUDING
+      // stage 1 of both neighbours (nodal forces mix adjacent elements), hence two more exchanges.
       // stage-1 loads travel through the (now free) Q rows; the final loads through the s rows, which
       // nobody overwrites before the next strain phase (the Q rows are re-published right after this step)
       T *sh_c1 = sh_Q, *sh_c12 = sh_s;
-      const T *N = A.plane_normal;
       const bool has_left = active && j > 0, has_right = active && j + 1 < n;
-      const T m0 = A.mass * ((j == 0) ? T(0.5) : T(1)), m1 = A.mass * ((j + 1 == n) ? T(0.5) : T(1));
-      const T w0 = m0 / (m1 + m0), w1 = m1 / (m1 + m0);   // loop-invariant mass weights of the element velocity
-      T etf[3], evel[3], xe[3], t[3];
+      const bool end0 = (j == 0), end1 = (j + 1 == n);
+      // mass weights of the element velocity (m_k v_k + m_k+1 v_k+1) / (m_k + m_k+1): end nodes carry half a mass
+      const T w0 = (end0 == end1) ? T(0.5) : end0 ? T(1.0 / 3.0) : T(2.0 / 3.0), w1 = T(1) - w0;
+      const T hm0 = end0 ? T(0.5) : T(1), hm1 = end1 ? T(0.5) : T(1);
+      T etf[3], evel[3], t[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         T f0 = fint[i], f1 = sh_s[i * RS + t_next] - sfl[i];   // internal force on nodes j, j+1
         if (!A.contact_before_forcing) {                       // external loads so far: gravity, joints (+ base force)
-          f0 += A.g[i] * m0; f1 += A.g[i] * m1;
+          f0 = fma(A.gm[i], hm0, f0); f1 = fma(A.gm[i], hm1, f1);
           if (i == 0 && A.point_force && first) f0 = fint[i] + act0;
           if (MULTI) f0 += fj[i];                              // joint force on node 0 (zero elsewhere)
         }
-        etf[i] = T(0.5) * (f0 + f1) + ((j == 0) ? T(0.5) * f0 : T(0)) + ((j + 1 == n) ? T(0.5) * f1 : T(0));
-        T v1 = sh_v[i * RS + t_next];
-        evel[i] = fma(w1, v1, w0 * v[i]);
-        xe[i] = x[i] + T(0.5) * dx[i];
+        etf[i] = T(0.5) * (f0 + f1) + (end0 ? T(0.5) * f0 : T(0)) + (end1 ? T(0.5) * f1 : T(0));
+        evel[i] = fma(w1, sh_v[i * RS + t_next], w0 * v[i]);
         t[i] = dx[i] * ilg;
       }
-      T rad2 = A.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
-      T fn = dot3(N, etf), dist = N[0] * (xe[0] - A.plane_origin[0]) + N[1] * (xe[1] - A.plane_origin[1]) +
-                                  N[2] * (xe[2] - A.plane_origin[2]);
-      T gap = dist - rad, pen = fmin(gap, T(0)), vn = dot3(N, evel);
+      const T rad2 = A.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
+      const T fn = etf[2], vn = evel[2];
+      const T gap = (fma(T(0.5), dx[2], x[2]) - A.plane_z0) - rad, pen = fmin(gap, T(0));
       const bool nocontact = !elem_ok || (gap > A.surface_tol);
-      T resp_mag = (nocontact || fn > T(0)) ? T(0) : fabs_(fn);   // |N fn| with |N| = 1
+      const T resp_mag = (nocontact || fn > T(0)) ? T(0) : fabs_(fn);
       T c1[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        T resp = (fn > T(0)) ? T(0) : -(N[i] * fn);
-        c1[i] = nocontact ? T(0) : resp - A.contact_k * (N[i] * pen) - A.contact_nu * (N[i] * vn);
-      }
-      T tn = dot3(N, t);
-      T tp[3] = {t[0] - N[0] * tn, t[1] - N[1] * tn, t[2] - N[2] * tn};
-      T inv_tp = rcp_nr(sqrt_(dot3(tp, tp)) + T(1e-14));
-      T ax[3] = {tp[0] * inv_tp, tp[1] * inv_tp, tp[2] * inv_tp}, rl[3];
-      cross3(ax, N, rl);
-      auto slip_fn = [&](T a) {   // find_slipping_elements on |v|
+      c1[2] = nocontact ? T(0) : ((fn > T(0)) ? T(0) : -fn) - A.contact_k * pen - A.contact_nu * vn;
+      // axial direction = the tangent's projection on the plane, normalised with the reference's guard
+      // 1 / (|tp| + 1e-14) (to first order in 1e-14 / |tp|); rolling direction = axial x normal
+      const T tp2 = fma(t[1], t[1], t[0] * t[0]);
+      const T rtp = rsqrt_nr(tp2 + T(sizeof(T) == 8 ? 1e-300 : 1e-30));   // (a rod standing on end: tp = 0, axial direction 0)
+      const T inv_tp = fma(T(-1e-14) * rtp, rtp, rtp);
+      const T ax0 = t[0] * inv_tp, ax1 = t[1] * inv_tp, rl0 = ax1, rl1 = -ax0;
+      auto slip_fn = [&](T a) {   // find_slipping_elements on |v| (|axial| = |rolling| = 1 - 1e-14 / |tp|: taken as 1)
         return (a > A.slip_tol) ? fabs_(T(1) - fmin(T(1), a * A.inv_slip_tol - T(1))) : T(1);
       };
       auto sgn = [](T a) { return T((a > T(0)) - (a < T(0))); };
-      T vax = dot3(evel, ax), sg = sgn(vax);
-      T kmu = T(0.5) * (A.kin_mu[0] * (T(1) + sg) + A.kin_mu[1] * (T(1) - sg));
-      T slipa = slip_fn(fabs_(vax) * sqrt_(dot3(ax, ax)));
-      T arm[3] = {-N[0] * rad, -N[1] * rad, -N[2] * rad};
-      T qa[3], wq[3], rv[3];
+      const T vax = fma(evel[1], ax1, evel[0] * ax0), sg = sgn(vax);
+      const T kmu = T(0.5) * (A.kin_mu[0] * (T(1) + sg) + A.kin_mu[1] * (T(1) - sg));
+      const T slipa = slip_fn(fabs_(vax));
+      // velocity of the contact point relative to the axis: Q^T (w x Q arm), arm = -rad z
+      T qa[3], wq[3];
 #pragma unroll
-      for (int i = 0; i < 3; i++) qa[i] = Q[3 * i] * arm[0] + Q[3 * i + 1] * arm[1] + Q[3 * i + 2] * arm[2];
+      for (int i = 0; i < 3; i++) qa[i] = -(Q[3 * i + 2] * rad);
       cross3(w, qa, wq);
-#pragma unroll
-      for (int i = 0; i < 3; i++) rv[i] = Q[i] * wq[0] + Q[3 + i] * wq[1] + Q[6 + i] * wq[2];
-      T smag = dot3(evel, rl) + dot3(rv, rl);
-      T slipr = slip_fn(fabs_(smag) * sqrt_(dot3(rl, rl)));
-      T ut[3] = {smag * rl[0] + vax * ax[0], smag * rl[1] + vax * ax[1], smag * rl[2] + vax * ax[2]};
-      T ug[3] = {ut[0] + T(1e-14), ut[1] + T(1e-14), ut[2] + T(1e-14)};
-      T iun = rsqrt_nr(dot3(ug, ug));
-      T uax = dot3(ut, ax) * iun, url = dot3(ut, rl) * iun;
-      T ka = nocontact ? T(0) : -((T(1) - slipa) * kmu * resp_mag * uax);
-      T kr = nocontact ? T(0) : -((T(1) - slipr) * A.kin_mu[2] * resp_mag * url);
-      T fr[3], text[3], cr[3];
-#pragma unroll
-      for (int i = 0; i < 3; i++) { fr[i] = kr * rl[i]; c1[i] += ka * ax[i] + fr[i]; }
-      cross3(arm, fr, cr);
+      const T rv0 = fma(Q[6], wq[2], fma(Q[3], wq[1], Q[0] * wq[0])), rv1 = fma(Q[7], wq[2], fma(Q[4], wq[1], Q[1] * wq[0]));
+      const T smag = fma(evel[1] + rv1, rl1, (evel[0] + rv0) * rl0);
+      const T slipr = slip_fn(fabs_(smag));
+      const T ut0 = fma(smag, rl0, vax * ax0), ut1 = fma(smag, rl1, vax * ax1);
+      const T ug0 = ut0 + T(1e-14), ug1 = ut1 + T(1e-14);
+      const T iun = rsqrt_nr(fma(ug1, ug1, fma(ug0, ug0, T(1e-28))));
+      const T uax = fma(ut1, ax1, ut0 * ax0) * iun, url = fma(ut1, rl1, ut0 * rl0) * iun;
+      const T ka = nocontact ? T(0) : -((T(1) - slipa) * kmu * resp_mag * uax);
+      const T kr = nocontact ? T(0) : -((T(1) - slipr) * A.kin_mu[2] * resp_mag * url);
+      T fr0 = kr * rl0, fr1 = kr * rl1;
+      c1[0] = fma(ka, ax0, fr0); c1[1] = fma(ka, ax1, fr1);
+      // couple of the rolling friction: Q (arm x F) = Q (rad F_y, -rad F_x, 0)
+      T cr0 = rad * fr1, cr1 = -(rad * fr0);
+      T text[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        text[i] = Q[3 * i] * cr[0] + Q[3 * i + 1] * cr[1] + Q[3 * i + 2] * cr[2];
+        text[i] = fma(Q[3 * i + 1], cr1, Q[3 * i] * cr0);
         sh_c1[i * RS + tid] = c1[i];
       }
       grp_sync();
-      // stage 2: static friction
-      T etf2[3];
+      // stage 2: static friction (in-plane components only)
+      T e2[2];
 #pragma unroll
-      for (int i = 0; i < 3; i++) {
-        T cl = has_left ? sh_c1[i * RS + tid - 1] : T(0), crr = has_right ? sh_c1[i * RS + tid + 1] : T(0);
-        T nc0 = T(0.5) * (cl + c1[i]), nc1 = T(0.5) * (c1[i] + crr);   // stage-1 response on nodes j, j+1
-        etf2[i] = etf[i] + T(0.5) * (nc0 + nc1) + ((j == 0) ? T(0.5) * nc0 : T(0)) + ((j + 1 == n) ? T(0.5) * nc1 : T(0));
+      for (int i = 0; i < 2; i++) {
+        const T cl = has_left ? sh_c1[i * RS + tid - 1] : T(0), crr = has_right ? sh_c1[i * RS + tid + 1] : T(0);
+        const T nc0 = T(0.5) * (cl + c1[i]), nc1 = T(0.5) * (c1[i] + crr);   // stage-1 response on nodes j, j+1
+        e2[i] = etf[i] + T(0.5) * (nc0 + nc1) + (end0 ? T(0.5) * nc0 : T(0)) + (end1 ? T(0.5) * nc1 : T(0));
       }
-      T fax = dot3(etf2, ax), sga = sgn(fax);
-      T smu = T(0.5) * (A.stat_mu[0] * (T(1) + sga) + A.stat_mu[1] * (T(1) - sga));
-      T sa = nocontact ? T(0) : -(fmin(fabs_(fax), slipa * smu * resp_mag) * sga);
-      T tsum[3] = {tq[0] + text[0], tq[1] + text[1], tq[2] + text[2]}, tt[3];
+      const T fax = fma(e2[1], ax1, e2[0] * ax0), sga = sgn(fax);
+      const T smu = T(0.5) * (A.stat_mu[0] * (T(1) + sga) + A.stat_mu[1] * (T(1) - sga));
+      const T sa = nocontact ? T(0) : -(fmin(fabs_(fax), slipa * smu * resp_mag) * sga);
+      T tsum[3] = {tq[0] + text[0], tq[1] + text[1], tq[2] + text[2]};
       if (MULTI && !A.contact_before_forcing) {   // the joint's couple on element 0 is already registered
 #pragma unroll
         for (int i = 0; i < 3; i++) tsum[i] += tj[i];
       }
+      const T tt0 = fma(Q[6], tsum[2], fma(Q[3], tsum[1], Q[0] * tsum[0])), tt1 = fma(Q[7], tsum[2], fma(Q[4], tsum[1], Q[1] * tsum[0]));
+      const T noslip = -((rad * fma(e2[1], rl1, e2[0] * rl0) - T(2) * fma(tt1, ax1, tt0 * ax0)) * (T(1.0 / 3.0) * inv_rad));
+      const T sr_ = nocontact ? T(0) : fmin(fabs_(noslip), slipr * A.stat_mu[2] * resp_mag) * sgn(noslip);
+      fr0 = sr_ * rl0; fr1 = sr_ * rl1;
+      sh_c12[0 * RS + tid] = c1[0] + fma(sa, ax0, fr0);
+      sh_c12[1 * RS + tid] = c1[1] + fma(sa, ax1, fr1);
+      sh_c12[2 * RS + tid] = c1[2];
+      cr0 = rad * fr1; cr1 = -(rad * fr0);
 #pragma unroll
-      for (int i = 0; i < 3; i++) tt[i] = Q[i] * tsum[0] + Q[3 + i] * tsum[1] + Q[6 + i] * tsum[2];
-      T noslip = -((rad * dot3(etf2, rl) - T(2) * dot3(tt, ax)) * (T(1.0 / 3.0) * inv_rad));
-      T sr_ = nocontact ? T(0) : fmin(fabs_(noslip), slipr * A.stat_mu[2] * resp_mag) * sgn(noslip);
-#pragma unroll
-      for (int i = 0; i < 3; i++) { fr[i] = sr_ * rl[i]; sh_c12[i * RS + tid] = c1[i] + sa * ax[i] + fr[i]; }
-      cross3(arm, fr, cr);
-#pragma unroll
-      for (int i = 0; i < 3; i++) tq[i] += text[i] + (Q[3 * i] * cr[0] + Q[3 * i + 1] * cr[1] + Q[3 * i + 2] * cr[2]);
+      for (int i = 0; i < 3; i++) tq[i] += text[i] + fma(Q[3 * i + 1], cr1, Q[3 * i] * cr0);
       grp_sync();
 #pragma unroll
       for (int i = 0; i < 3; i++)   // node j collects half of the plane's load on elements j-1 and j
@@ -742,12 +772,15 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     } else {
 #pragma unroll
       for (int i = 0; i < 3; i++) {
-        T fi = fint[i] + (MULTI ? fj[i] : T(0));
+        T fi = fint[i];
+        if (MULTI) fi += fj[i];
         T gd = A.gdt_cv[i];
         if (i == 0 && A.point_force && first) { fi += act0; gd = T(0); }
         // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update
         v[i] = fma(fi, dtim_cv, fma(v[i], A.c_v, gmask * gd));
-        w[i] = fma(dtee, A.Jinv[i] * (tq[i] + (MULTI ? tj[i] : T(0))), w[i]);
+        T ti = tq[i];
+        if (MULTI) ti += tj[i];
+        w[i] = fma(dtee, A.Jinv[i] * ti, w[i]);
       }
     }
 
@@ -830,6 +863,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
   }
   if (EDGE && A.n_substeps > 0 && active && !redo) {
+    to_lab(ed);
 #pragma unroll
     for (int c = 0; c < 3; c++) st[(F_EDGE + c) * stride + j] = elem_ok ? ed[c] : T(0);
   }
@@ -843,6 +877,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
   }
   if (active && !redo) {
+    to_lab(x); to_lab(v); rows_to_lab(Q);     // (x, v, Q are final: nothing below reads them in the internal frame)
 #pragma unroll
     for (int c = 0; c < 3; c++) {
       st[(F_POS + c) * stride + j] = x[c];

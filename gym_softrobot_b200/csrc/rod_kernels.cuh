@@ -67,6 +67,9 @@ template <typename T> struct RodArgs {
   int contact_on, contact_before_forcing;
   T plane_origin[3], plane_normal[3], contact_k, contact_nu, slip_tol, inv_slip_tol, surface_tol;
   T kin_mu[3], stat_mu[3], vol_over_pi;
+  // the contact models' internal frame: z = plane normal.  lab2int rotates lab vectors into it (identity / unused when
+  // the normal is +z: rot_on = 0); plane_z0 = height of the plane in that frame; gm = interior nodal mass x gravity there
+  T lab2int[9], plane_z0, gm[3]; int rot_on;
   // multi-rod environments (octopus: n_rod arms + one rigid Cylinder head joined by FixedJoint2Rigid,
   // envs/octopus/build.py:52-217, utils/custom_elastica/joint.py, constraint.py)
   int n_rod, has_head;

@@ -108,15 +108,24 @@ class ContinuumSnakeVectorEnv:
         self._vel = torch.zeros_like(self._com)
         self._times = []
         self._substeps = 0
+        self._clock = np.float64(0.0)
 
     # -- helpers -----------------------------------------------------------------------------
     def _sample(self):
         # ContinuumSnakeCallBack.make_callback (continuum_snake.py:115-131)
         f = self.handle.fields()
         k = len(self._times)
+        if k >= self._com.shape[1]:      # stepping past the time limit without a reset (the reference keeps going too)
+            grow = self.torch.zeros_like(self._com)
+            self._com, self._vel = self.torch.cat([self._com, grow], dim=1), self.torch.cat([self._vel, grow], dim=1)
         self._com[:, k] = (f["position_collection"] * self._mass_w).sum(dim=2)
         self._vel[:, k] = (f["velocity_collection"] * self._mass_w).sum(dim=2)
-        self._times.append(float(self.handle.muscle_tensor()[0, 0].item()))
+        self._times.append(float(self._clock))      # host mirror of the in-kernel clock: no device read-back per sample
+
+    def _advance_clock(self, n_substeps):
+        # the kernel (and PositionVerlet) advance time by dt/2 twice per substep; cumsum adds left to right, so this
+        # is that very sequence of float64 additions
+        self._clock = np.cumsum(np.concatenate([[self._clock], np.full(2 * n_substeps, 0.5 * self.time_step)]))[-1]
 
     def _obs(self):
         f = self.handle.fields()
@@ -136,7 +145,7 @@ class ContinuumSnakeVectorEnv:
         mu = self.handle.muscle_tensor()
         mu.zero_()
         mu[:, 1] = float(np.float32(2.0 * np.pi) / np.float32(1.0))       # _build: b_coeff = 0, wave_length = 1
-        self._times, self._substeps = [], 0
+        self._times, self._substeps, self._clock = [], 0, np.float64(0.0)
         self._sample()                                                     # the callback's finalize-time sample
         return self._obs(), {}
 
@@ -156,6 +165,7 @@ class ContinuumSnakeVectorEnv:
         while left > 0:
             k = min(left, self.callback_step_skip - self._substeps % self.callback_step_skip)
             self.handle.step(None, k, obs6, rew, term)
+            self._advance_clock(k)
             self._substeps += k
             left -= k
             if self._substeps % self.callback_step_skip == 0:

@@ -106,13 +106,14 @@ class SoftArmTrackingVectorEnv:
             rows.append(w[::_UPDATE][:self.n_updates + 1])
         self._targets[idx] = torch.as_tensor(np.stack(rows), device=self.device)
 
-    def _reset_envs(self, idx=None, seed=None):
+    def _reset_envs(self, idx=None, seed=None, new_targets=True):
         torch = self.torch
         n = self.n_env if idx is None else int(idx.numel())
         init = torch.as_tensor(np.repeat(self._init, n, axis=0), device=self.device).contiguous()
         self.handle.reset(init, None if idx is None else idx.to(torch.int32).contiguous())
         all_idx = torch.arange(self.n_env, device=self.device) if idx is None else idx
-        self._new_targets(all_idx, seed)
+        if new_targets:     # (the single-env facade supplies the trajectory from its own generator)
+            self._new_targets(all_idx, seed)
         self.tick[all_idx] = 0
 
     # -- API ---------------------------------------------------------------------------------
@@ -177,7 +178,7 @@ class SoftArmTrackingEnv(Env):
         # the trajectory draws come from the env's own generator, right after reset(seed) (line 412-418)
         if self.mode == 2:
             v = self._vec
-            v._reset_envs(None, None)
+            v._reset_envs(None, None, new_targets=False)
             w = target_trajectory(_FINAL_TIME, _DT, 0.1, self.np_random)
             v._targets[0] = v.torch.as_tensor(w[::_UPDATE][:v.n_updates + 1], device=v.device)
             obs = v._state()

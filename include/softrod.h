@@ -175,8 +175,14 @@ int sr_step_host(sr_handle *h, const float *action_host, int n_substeps, float *
 int sr_observe(sr_handle *h, const float *prev_action_dev, float *obs_dev, void *stream);
 
 int sr_get_state(sr_handle *h, sr_state_view *out);
-/* copy a full state (same layout, device memory) into the handle */
+/* Copy the structure-of-arrays ROD block (the fields of sr_state_view, same layout, device memory) into the handle.
+ * Rod arrays only: BC anchors, the rigid head, rest curvatures, the 3D pendulum's base controller and the
+ * forcings' state are not part of the view — use sr_copy_from to clone a whole handle. */
 int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
+/* Clone everything that evolves or parametrises the envs of `src` into `dst` (created with the same shapes): rod
+ * arrays, BC anchors, model scratch, rigid heads, rest curvatures, muscle / spline forcing state.  Checkpoint /
+ * restore; works across devices (peer copy).  Stream-ordered on `stream` of dst's device. */
+int sr_copy_from(sr_handle *dst, sr_handle *src, void *stream);
 
 /* Per-env model scratch, [n_env][*dim] of the handle's dtype: SoftPendulum3D keeps the base controller there
  * (0-2 position, 3-5 velocity, 6 last tilt angle, `info["tilt"]` of soft_pendulum_3d.py:157). */

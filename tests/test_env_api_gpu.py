@@ -204,3 +204,32 @@ def test_second_episode_reset_observation_matches_reference(golden_dir):
         else:
             np.testing.assert_allclose(obs2, g[f"{tag}/obs2"], rtol=1e-5, atol=1e-6, err_msg=env_id)
         env.close()
+
+
+@pytest.mark.parametrize("env_id,kw", [("SoftPendulum3D-v0", {}), ("OctoFlat-v0", dict(recording_fps=100)),
+                                       ("ContinuumSnake-v0", {}), ("SoftArmTracking-v0", {})])
+def test_clone_from_copies_everything_that_evolves(env_id, kw):
+    """sr_copy_from: unlike sr_set_state (rod arrays only) it also carries BC anchors, the 3D pendulum's
+    base controller, rigid heads, rest curvatures and the forcings' state — a cloned handle continues bit for bit."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    n_env = 5
+    e1, e2 = gsb.make_vec(env_id, n_env, autoreset=False, **kw), gsb.make_vec(env_id, n_env, autoreset=False, **kw)
+    e1.reset(seed=3); e2.reset(seed=99)
+    sp = e1.single_action_space
+    rng = np.random.default_rng(0)
+    act = lambda: torch.as_tensor(rng.uniform(sp.low, sp.high, size=(n_env,) + sp.shape).astype(sp.dtype), device="cuda")
+    for _ in range(2):
+        e1.step(act())
+    e2.handle.clone_from(e1.handle)
+    K, obs = 150, torch.empty((n_env, e1.handle.obs_dim), dtype=torch.float32, device="cuda")
+    rew, term = torch.empty(n_env, dtype=torch.float64, device="cuda"), torch.empty(n_env, dtype=torch.uint8, device="cuda")
+    a = torch.zeros((n_env, max(e1.handle.action_dim, 1)), dtype=torch.float32, device="cuda")
+    for h in (e1.handle, e2.handle):
+        h.step(a if h.action_dim else None, K, obs, rew, term)
+    torch.cuda.synchronize()
+    assert torch.equal(e1.handle.state_tensor(), e2.handle.state_tensor())
+    assert torch.equal(e1.handle.aux_tensor(), e2.handle.aux_tensor())
+    if env_id == "OctoFlat-v0":
+        assert torch.equal(e1.handle.head_tensor(), e2.handle.head_tensor())
+    e1.close(); e2.close()
