@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_copy_from", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
+    "sr_get_state", "sr_set_state", "sr_copy_from", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_sucker", "sr_get_ext_loads", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
 ]
 
 
@@ -48,6 +48,7 @@ class SrConfig(C.Structure):
         ("muscle_direction", C.c_double * 3),
         ("spline_dir_mask", C.c_int32), ("spline_n_ctrl", C.c_int32),
         ("spline_scale", C.c_double), ("spline_max_rate", C.c_double),
+        ("tip_radius", C.c_double), ("sucker_on", C.c_int32), ("sucker_index", C.c_int32),
     ]
 
 
@@ -97,6 +98,8 @@ def load_library():
     L.sr_get_aux.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_head.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sr_get_sucker.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sr_get_ext_loads.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.sr_get_muscle.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_spline.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_spline_basis.argtypes = [C.c_int32, C.c_double, C.c_void_p]
@@ -170,7 +173,8 @@ class Handle:
                  shear_modulus=0.0, gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, bc_kind=BC_FREE,
                  point_force_on_base=False, damping_before_constraints=False, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
-                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None, spline=None):
+                 base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None, spline=None,
+                 tip_radius=0.0, sucker_index=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -211,6 +215,9 @@ class Handle:
             cfg.spline_dir_mask = sum(1 << int(d) for d in spline["directions"])
             cfg.spline_n_ctrl = spline["n_ctrl"]
             cfg.spline_scale, cfg.spline_max_rate = spline["scale"], spline.get("max_rate", float("inf"))
+        cfg.tip_radius = float(tip_radius)
+        if sucker_index is not None:
+            cfg.sucker_on, cfg.sucker_index = 1, int(sucker_index)
         self.n_rod = max(1, n_rod)
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -354,6 +361,25 @@ class Handle:
         t = torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod, 3, v.stride), ts),
                             device=f"cuda:{self.device}")
         return t[:, :, :self.n_elem - 1]
+
+    def sucker_tensor(self):
+        """torch view [n_env * n_rod] of the ControllableFixConstraint reduction ratios (sr_get_sucker)."""
+        import torch
+        ptr = C.c_void_p()
+        _check(self._lib.sr_get_sucker(self._h, C.byref(ptr)))
+        ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod,), ts), device=f"cuda:{self.device}")
+
+    def ext_load_tensors(self):
+        """(force, couple): torch views [n_env * n_rod, 3, n_elem + 1] / [.., 3, n_elem] of the external nodal forces
+        (lab frame) and element couples (material frame) added every substep (sr_get_ext_loads)."""
+        import torch
+        pf, pc = C.c_void_p(), C.c_void_p()
+        _check(self._lib.sr_get_ext_loads(self._h, C.byref(pf), C.byref(pc)))
+        v = self.state_view()
+        ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
+        mk = lambda p: torch.as_tensor(_DevMem(p.value, (self.n_env * self.n_rod, 3, v.stride), ts), device=f"cuda:{self.device}")
+        return mk(pf)[:, :, :self.n_elem + 1], mk(pc)[:, :, :self.n_elem]
 
     def muscle_tensor(self):
         """torch view [n_env, n_elem + 2] (float64): simulation time, wave number, beta(s_k) (sr_get_muscle)."""

@@ -41,6 +41,10 @@ def translation_units():
                 tus.append((f"packed_{t}_{nt}_g{grp}", "inst_packed.cu",
                             [f"-DSR_TU_T={t}", f"-DSR_TU_F64={int(t == 'double')}", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}", f"-DSR_TU_GROUP={grp}"],
                             _COMMON + ["rod_kernel_packed.cuh"]))
+    for nt, minb in ((384, 1), (1024, 1)):     # tapered rods: per-element constants in registers (168 / 64 of them)
+        tus.append((f"packed_double_{nt}_g4", "inst_packed.cu",
+                    ["-DSR_TU_T=double", "-DSR_TU_F64=1", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}", "-DSR_TU_GROUP=4"],
+                    _COMMON + ["rod_kernel_packed.cuh"]))
     return tus
 
 

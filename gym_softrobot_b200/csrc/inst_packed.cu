@@ -2,16 +2,17 @@
 // Compiled by build.py with  -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n> -DSR_TU_GROUP=<g>:
 //   group 0: lean (FP32 only; the FP64 lean path is rod_kernel_lean.cuh)   1: SoftPendulum3D (filter + moving base)
 //   group 2: plane contact and the muscle-torque forcings                    3: multi-rod assemblies
+//   group 4: tapered rods (FP64; CTA sizes 384 and 1024 only)
 #include <atomic>
 #include "launch.cuh"
 #include "rod_kernel_packed.cuh"
 
 namespace sr {
 
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY>
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY, bool VARY>
 cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid, cudaStream_t s) {
   const size_t smem = (size_t)packed_smem_words(NT, MULTI, TORQUE) * sizeof(T);
-  auto kern = rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE, FASTONLY>;
+  auto kern = rod_packed_kernel<T, NT, MINB, LAPLACE, MOVING, CONTACT, MULTI, TORQUE, FASTONLY, VARY>;
   // the opt-in above 48 KB is a per-device attribute of the function: one bit per device ordinal
   static std::atomic<unsigned long long> opted{0};
   int dev = 0;
@@ -28,7 +29,9 @@ cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid
 }
 
 #define SR_I(L, M, C, MU, TQ, F) \
-  template cudaError_t launch_packed_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, L, M, C, MU, TQ, F>(const RodArgs<SR_TU_T> &, int, int, cudaStream_t);
+  template cudaError_t launch_packed_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, L, M, C, MU, TQ, F, false>(const RodArgs<SR_TU_T> &, int, int, cudaStream_t);
+#define SR_I_VARY(C, MU) \
+  template cudaError_t launch_packed_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, false, false, C, MU, false, false, true>(const RodArgs<SR_TU_T> &, int, int, cudaStream_t);
 
 // the fast-only / fallback pair exists for FP64 (every group) and for the FP32 lean kernel
 #if SR_TU_F64
@@ -51,6 +54,9 @@ SR_I_FAST(false, false, true, false, true)
 #elif SR_TU_GROUP == 3
 SR_I(false, false, true, true, false, false)
 SR_I_FAST(false, false, true, true, false)
+#elif SR_TU_GROUP == 4   // tapered rods (per-element constants from HBM): single rod and assembly, safe variants
+SR_I_VARY(true, false)
+SR_I_VARY(true, true)
 #endif
 
 }  // namespace sr

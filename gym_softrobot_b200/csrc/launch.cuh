@@ -8,7 +8,7 @@
 namespace sr {
 
 // generic CTA-packed kernel (rod_kernel_packed.cuh); opts the dynamic shared memory in on the current device
-template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY>
+template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY, bool VARY = false>
 cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid, cudaStream_t s);
 
 // lean kernel (rod_kernel_lean.cuh; T = storage type: double = FP64, float = mixed precision); grid / split schedule in A.sk_*

@@ -35,8 +35,12 @@ constexpr int packed_smem_words(int nt, bool multi, bool torque = false) {
 // a thread that sees an argument outside the polynomials' range raises a flag instead, the env's state is
 // then NOT written back (global memory still holds the pre-launch state) and redo[env] is set: the safe
 // instantiation, launched right behind with redo_filter = 1, steps exactly those envs.
+// VARY (ElemConst / ET_* in rod_kernels.cuh): element / node / Voronoi constants come from a per-handle table in HBM (tapered rods: base_radius an array,
+// /root/reference/gym_softrobot/envs/octopus/build_muscle_octopus.py:61-63) into per-thread registers instead of
+// the constant bank; only instantiated for the safe contact / multi-rod variants (168 registers, one CTA per SM).
+
 template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false,
-          bool FASTONLY = false>
+          bool FASTONLY = false, bool VARY = false>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -166,7 +170,28 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   // time-step multipliers are zero where there is nothing to integrate (tip thread's
   // pseudo-element, idle threads): no selects in the update expressions.
   // (c_v is 1 when the damper is off)
-  const T dtim_cv = active ? A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1)) : T(0);
+  // K: where the element constants come from — the kernel parameters (uniform rod) or this thread's table row
+  ElemConst<T> ec;
+  T mass_j = A.mass * ((j == 0 || j == n) ? T(0.5) : T(1)), mass_j1 = A.mass * ((j + 1 == n) ? T(0.5) : T(1));
+  if (VARY) {
+    const T *tab = A.elem_tab;
+    const int je = min(j, n - 1), jv = min(j, n - 2), es = A.stride;
+    ec.rest_len = tab[ET_REST_LEN * es + je]; ec.inv_rest_len = T(1) / ec.rest_len;
+    ec.rest_vor = tab[ET_REST_VOR * es + jv]; ec.inv_rest_vor = T(1) / ec.rest_vor;
+    ec.S[0] = ec.S[1] = tab[ET_S0 * es + je]; ec.S[2] = tab[ET_S2 * es + je];
+    ec.B[0] = ec.B[1] = tab[ET_B0 * es + jv]; ec.B[2] = tab[ET_B2 * es + jv];
+    ec.J[0] = ec.J[1] = tab[ET_J0 * es + je]; ec.J[2] = tab[ET_J2 * es + je];
+    ec.logc_w[0] = ec.logc_w[1] = tab[ET_LOGCW0 * es + je]; ec.logc_w[2] = tab[ET_LOGCW2 * es + je];
+    ec.vol_over_pi = tab[ET_VOL_PI * es + je];
+    ec.isotropic = 1;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      ec.S_over_l[i] = ec.S[i] * ec.inv_rest_len; ec.Jinv[i] = T(1) / ec.J[i]; ec.c_w[i] = exp_ref<T>(ec.logc_w[i]);
+    }
+    mass_j = tab[ET_MASS * es + min(j, n)]; mass_j1 = tab[ET_MASS * es + min(j + 1, n)];
+  }
+  const auto &K = [&]() -> const auto & { if constexpr (VARY) return ec; else return A; }();
+  const T dtim_cv = !active ? T(0) : VARY ? A.dt / mass_j * A.c_v : A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1));
   const T gmask = active ? T(1) : T(0);
   const T dte = elem_ok ? A.dt : T(0);
 
@@ -390,8 +415,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       }
     }
     if (EDGE) hh_prev = T(0);
-    if (!elem_ok) dx[2] = A.rest_len;   // keeps the pseudo-element's quantities finite
-    if (!vor_ok) dx2[2] = A.rest_len;
+    if (!elem_ok) dx[2] = K.rest_len;   // keeps the pseudo-element's quantities finite
+    if (!vor_ok) dx2[2] = K.rest_len;
     T l2 = dot3(dx, dx);
     T l2n = dot3(dx2, dx2);
     T il = rsqrt_nr(l2);
@@ -421,10 +446,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         sh_need[r] = need;
       }
     }
-    T e = lg * A.inv_rest_len * gam;
-    T inv_e = A.rest_len * ilg;
+    T e = lg * K.inv_rest_len * gam;
+    T inv_e = K.rest_len * ilg;
     T inv_e_s = elem_ok ? inv_e : T(0);           // the tip thread's pseudo-element carries no stress
-    T edot = dot3(dx, dv) * (ilg * A.inv_rest_len);
+    T edot = dot3(dx, dv) * (ilg * K.inv_rest_len);
     // sigma = e Q t - z = Q dx / l0 - z exactly (e t = dx / l0): no tangent needed here
     T Qdx[3], nst[3], sfl[3];
 #pragma unroll
@@ -435,7 +460,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     for (int i = 0; i < 3; i++) Qdx[i] = fma(Q[3 * i + 2], dx[2], Qdx[i]) * gam;   // strain against the element's own rest length
 #pragma unroll
     for (int i = 0; i < 3; i++)
-      nst[i] = (i == 2) ? fma(A.S_over_l[i], Qdx[i], -A.S[i]) : A.S_over_l[i] * Qdx[i];
+      nst[i] = (i == 2) ? fma(K.S_over_l[i], Qdx[i], -K.S[i]) : K.S_over_l[i] * Qdx[i];
 #pragma unroll
     for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
 #pragma unroll
@@ -468,7 +493,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       for (int c = 0; c < 3; c++) {
         cf[c] = A.joint_k * dd[c] - A.joint_nu * (rvn * nh[c]);
         fj[c] = -cf[c];
-        tgt[c] = anchor[c] + A.rest_len * dir[c];
+        tgt[c] = anchor[c] + K.rest_len * dir[c];
         fd[c] = -A.joint_kt * ((x[c] + dx[c]) - tgt[c]);       // x + dx = node 1 of the arm
       }
       cross3(dx, fd, tau);                                        // link_direction x force
@@ -528,19 +553,19 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       fac = bend_factor_ref<T>(u);
     }
     T kp[3], tau[3], kxt[3];
-    T fs = fac * A.inv_rest_vor;
+    T fs = fac * K.inv_rest_vor;
 #pragma unroll
-    for (int i = 0; i < 3; i++) { kp[i] = vec[i] * fs; tau[i] = A.B[i] * (CONTACT ? kp[i] - rk[i] : kp[i]); }
+    for (int i = 0; i < 3; i++) { kp[i] = vec[i] * fs; tau[i] = K.B[i] * (CONTACT ? kp[i] - rk[i] : kp[i]); }
     cross3(kp, tau, kxt);
-    T eps = (T(0.5) * (lgn + lg)) * A.inv_rest_vor;
+    T eps = (T(0.5) * (lgn + lg)) * K.inv_rest_vor;
     T ie3 = rcp_nr(eps * eps * eps);
     if (!vor_ok) ie3 = T(0);
-    T hc = T(0.5) * A.rest_vor * ie3;
+    T hc = T(0.5) * K.rest_vor * ie3;
     // local couples share one 1/e factor:  (Qt x n) l0 + (Jw/e) x w + (Jw/e) (de/dt)/e
     //   = [ (Q dx) x n + (Jw) x w + (Jw) (de/dt)/e ] / e      (Qt l0 = Q dx / e)
     // Everything that does not need the left neighbour is folded into tql[] before the second
     // barrier, so only x,v,Q,w + tql + sfl + e stay live across it.
-    T pw[3] = {A.J[0] * w[0], A.J[1] * w[1], A.J[2] * w[2]};
+    T pw[3] = {K.J[0] * w[0], K.J[1] * w[1], K.J[2] * w[2]};
     T ede = edot * inv_e;
     T Gc[3];
     Gc[0] = fma(Qdx[1], nst[2], -(Qdx[2] * nst[1]));
@@ -568,20 +593,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     T cw0 = T(1), cw1 = T(1), cw2 = T(1);
     if (FASTONLY || A.damping_on) {   // damper off = identity constants (c_w = 1, ln c_w = 0): no branch needed
       T em1 = e - T(1);
-      T z0 = em1 * A.logc_w[0], z1 = em1 * A.logc_w[1], z2 = em1 * A.logc_w[2];
+      T z0 = em1 * K.logc_w[0], z1 = em1 * K.logc_w[1], z2 = em1 * K.logc_w[2];
       // the contact / filtered models damp harder and stretch more (z up to ~1e-3): they use the wide exp map
       constexpr bool NARROW_EXP = !CONTACT && !LAPLACE;
       constexpr double kz = NARROW_EXP ? kNarrowExpZ : kSmallExpZ;
       const bool exp_out = !(fabs_(z0) <= T(kz)) || !(fabs_(z1) <= T(kz)) || !(fabs_(z2) <= T(kz));
       if (FASTONLY) dom_bad = dom_bad || exp_out;
       if (FASTONLY || !exp_out) {
-        cw0 = A.c_w[0] * (NARROW_EXP ? exp_narrow(A.poly, z0) : exp_small(A.poly, z0));
-        cw2 = A.c_w[2] * (NARROW_EXP ? exp_narrow(A.poly, z2) : exp_small(A.poly, z2));
-        cw1 = A.isotropic ? cw0 : A.c_w[1] * (NARROW_EXP ? exp_narrow(A.poly, z1) : exp_small(A.poly, z1));
+        cw0 = K.c_w[0] * (NARROW_EXP ? exp_narrow(A.poly, z0) : exp_small(A.poly, z0));
+        cw2 = K.c_w[2] * (NARROW_EXP ? exp_narrow(A.poly, z2) : exp_small(A.poly, z2));
+        cw1 = K.isotropic ? cw0 : K.c_w[1] * (NARROW_EXP ? exp_narrow(A.poly, z1) : exp_small(A.poly, z1));
       } else {
-        cw0 = exp_ref<T>(e * A.logc_w[0]);
-        cw1 = exp_ref<T>(e * A.logc_w[1]);
-        cw2 = exp_ref<T>(e * A.logc_w[2]);
+        cw0 = exp_ref<T>(e * K.logc_w[0]);
+        cw1 = exp_ref<T>(e * K.logc_w[1]);
+        cw2 = exp_ref<T>(e * K.logc_w[2]);
       }
     }
     if (last) {
@@ -594,7 +619,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         for (int i = 0; i < 3; i++) {
           st[(F_TAN + i) * stride + j] = tg_out[i];
           st[(F_KAPPA + i) * stride + j] = kp[i];
-          st[(F_SIGMA + i) * stride + j] = fma(A.inv_rest_len, Qdx[i], (i == 2) ? T(-1) : T(0));
+          st[(F_SIGMA + i) * stride + j] = fma(K.inv_rest_len, Qdx[i], (i == 2) ? T(-1) : T(0));
         }
         st[F_DIL * stride + j] = e;
       }
@@ -616,6 +641,21 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       const double2 a0 = q[0], a1 = q[1], a2 = q[2];
       fint[0] = sfl[0] - a0.x; fint[1] = sfl[1] - a0.y; fint[2] = sfl[2] - a1.x;
       tq[0] = tql[0] + a1.y; tq[1] = tql[1] + a2.x; tq[2] = tql[2] + a2.y;
+    }
+    // generic per-element external loads (a forcing: what COOMM's ApplyMuscles would feed,
+    // /root/reference/gym_softrobot/envs/octopus/build_muscle_octopus.py:171-176): nodal forces in the lab frame,
+    // element couples in the material frame, constant during a launch, added every substep ahead of the contact
+    if (A.ext_force && active) {
+      T fe[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) fe[i] = A.ext_force[((size_t)rod * 3 + i) * stride + j];
+      to_int(fe);
+#pragma unroll
+      for (int i = 0; i < 3; i++) fint[i] += fe[i];
+    }
+    if (A.ext_couple && elem_ok) {
+#pragma unroll
+      for (int i = 0; i < 3; i++) tq[i] += A.ext_couple[((size_t)rod * 3 + i) * stride + j];
     }
     if (spl) {
       const int need = live ? sh_need[r] : 0;
@@ -654,22 +694,32 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       const bool has_left = active && j > 0, has_right = active && j + 1 < n;
       const bool end0 = (j == 0), end1 = (j + 1 == n);
       // mass weights of the element velocity (m_k v_k + m_k+1 v_k+1) / (m_k + m_k+1): end nodes carry half a mass
-      const T w0 = (end0 == end1) ? T(0.5) : end0 ? T(1.0 / 3.0) : T(2.0 / 3.0), w1 = T(1) - w0;
+      const T w0 = VARY ? mass_j / (mass_j + mass_j1) : (end0 == end1) ? T(0.5) : end0 ? T(1.0 / 3.0) : T(2.0 / 3.0), w1 = T(1) - w0;
       const T hm0 = end0 ? T(0.5) : T(1), hm1 = end1 ? T(0.5) : T(1);
       T etf[3], evel[3], t[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) {
         T f0 = fint[i], f1 = sh_s[i * RS + t_next] - sfl[i];   // internal force on nodes j, j+1
         if (!A.contact_before_forcing) {                       // external loads so far: gravity, joints (+ base force)
-          f0 = fma(A.gm[i], hm0, f0); f1 = fma(A.gm[i], hm1, f1);
+          if (VARY) { f0 = fma(A.g[i], mass_j, f0); f1 = fma(A.g[i], mass_j1, f1); }
+          else { f0 = fma(A.gm[i], hm0, f0); f1 = fma(A.gm[i], hm1, f1); }
           if (i == 0 && A.point_force && first) f0 = fint[i] + act0;
           if (MULTI) f0 += fj[i];                              // joint force on node 0 (zero elsewhere)
         }
+        // (an external nodal force is a forcing as well; node j's share is already in fint, node j+1's is added below)
         etf[i] = T(0.5) * (f0 + f1) + (end0 ? T(0.5) * f0 : T(0)) + (end1 ? T(0.5) * f1 : T(0));
         evel[i] = fma(w1, sh_v[i * RS + t_next], w0 * v[i]);
         t[i] = dx[i] * ilg;
       }
-      const T rad2 = A.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
+      if (A.ext_force && elem_ok && !A.contact_before_forcing) {
+        T fe[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) fe[i] = A.ext_force[((size_t)rod * 3 + i) * stride + j + 1];
+        to_int(fe);
+#pragma unroll
+        for (int i = 0; i < 3; i++) etf[i] += (end1 ? T(1.0) : T(0.5)) * fe[i];
+      }
+      const T rad2 = K.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
       const T fn = etf[2], vn = evel[2];
       const T gap = (fma(T(0.5), dx[2], x[2]) - A.plane_z0) - rad, pen = fmin(gap, T(0));
       const bool nocontact = !elem_ok || (gap > A.surface_tol);
@@ -780,7 +830,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         v[i] = fma(fi, dtim_cv, fma(v[i], A.c_v, gmask * gd));
         T ti = tq[i];
         if (MULTI) ti += tj[i];
-        w[i] = fma(dtee, A.Jinv[i] * ti, w[i]);
+        w[i] = fma(dtee, K.Jinv[i] * ti, w[i]);
       }
     }
 
@@ -828,6 +878,13 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       // BCs that only zero components commute with the (multiplicative / interior-only) dampers: no order branch
       if ((FASTONLY && !MOVING) || A.damp_first) { dampen(); constrain_rates(); }
       else { constrain_rates(); dampen(); }
+      // ControllableFixConstraint ("sucker", envs/octopus/controllable_constraint.py:46-69): the rates of one node /
+      // element index are scaled by 1 - reduction_ratio (per rod, 0 = released); registered after the dampers
+      if (A.sucker && active && j == A.sucker_index) {
+        const T f = T(1) - A.sucker[rod];
+#pragma unroll
+        for (int i = 0; i < 3; i++) { v[i] *= f; w[i] *= f; }
+      }
     }
 
     kinematic(last ? h : dt, last ? T(1e-14) : T(2e-14));

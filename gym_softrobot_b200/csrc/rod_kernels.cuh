@@ -70,6 +70,11 @@ template <typename T> struct RodArgs {
   // the contact models' internal frame: z = plane normal.  lab2int rotates lab vectors into it (identity / unused when
   // the normal is +z: rot_on = 0); plane_z0 = height of the plane in that frame; gm = interior nodal mass x gravity there
   T lab2int[9], plane_z0, gm[3]; int rot_on;
+  // optional per-rod inputs (nullptr = off): ControllableFixConstraint ratios [n_rods] acting on index sucker_index;
+  // external nodal forces (lab frame) / element couples (material frame) [n_rods][3][stride]; tapered-rod table
+  const T *sucker; int sucker_index;
+  const T *ext_force, *ext_couple;
+  const T *elem_tab;                  // [ET_FIELDS][stride] element constants (VARY instantiations)
   // multi-rod environments (octopus: n_rod arms + one rigid Cylinder head joined by FixedJoint2Rigid,
   // envs/octopus/build.py:52-217, utils/custom_elastica/joint.py, constraint.py)
   int n_rod, has_head;
@@ -105,6 +110,13 @@ template <typename T> struct RodArgs {
   int sk_rods_per_cta, sk_items, sk_split, sk_rodsync;   // sk_rodsync: per-rod named barriers inside the substep loop
   double *sk_scratch; int *sk_flag;
 };
+
+// per-thread copy of the element / node / Voronoi constants of a tapered rod, and the rows of the HBM table they come from
+template <typename T> struct ElemConst {
+  T rest_len, inv_rest_len, rest_vor, inv_rest_vor, S[3], S_over_l[3], B[3], J[3], Jinv[3], c_w[3], logc_w[3], vol_over_pi;
+  int isotropic;
+};
+enum : int { ET_REST_LEN = 0, ET_REST_VOR, ET_S0, ET_S2, ET_B0, ET_B2, ET_J0, ET_J2, ET_LOGCW0, ET_LOGCW2, ET_VOL_PI, ET_MASS, ET_FIELDS };
 
 template <typename T, int EPL> struct Vec;
 template <> struct Vec<double, 1> { using type = double; };

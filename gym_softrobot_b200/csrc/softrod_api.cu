@@ -47,6 +47,7 @@ struct sr_handle {
   void *state = nullptr, *bc = nullptr, *aux = nullptr, *rest_kappa = nullptr, *head = nullptr;
   double *muscle = nullptr; int muscle_dim = 0;
   double *spline = nullptr, *spline_tab = nullptr; int spline_dim = 0;
+  void *sucker = nullptr, *ext_force = nullptr, *ext_couple = nullptr, *elem_tab = nullptr;
   int *redo = nullptr;   // per-env flags of the fast-only / fallback kernel pair
   unsigned long long *redo_count = nullptr, *h_redo_count = nullptr, pair_last_count = 0;
   cudaEvent_t pair_event = nullptr; bool pair_copy_pending = false;
@@ -331,7 +332,22 @@ template <typename T, int NT, int MINB> int launch_lean_pair(sr_handle *h, sr::R
 
 template <typename T> bool is_lean_config(const sr::RodArgs<T> &A) {
   return !(A.n_rod > 1 || A.has_head || A.muscle_on || A.spline_mask || A.contact_on || A.rest_kappa ||
-           A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE);
+           A.laplace_order > 0 || A.bc_kind == sr::BC_MOVING_BASE || A.sucker || A.ext_force || A.ext_couple || A.elem_tab);
+}
+
+// tapered rods: safe kernel with per-element constants in registers (CTA sizes 384 / 1024 only)
+template <int NT> int launch_tapered(sr_handle *h, sr::RodArgs<double> &A, cudaStream_t s) {
+  const bool multi = A.n_rod > 1 || A.has_head;
+  const int group = (multi ? A.n_rod : 1) * (A.n_elem + 1) + (multi ? A.has_head : 0);
+  const int rods_per_cta = NT / group;
+  if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
+  const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
+  A.sk_rodsync = rodsync_setting();
+  cudaError_t e = multi ? sr::launch_packed_kernel<double, NT, 1, false, false, true, true, false, false, true>(A, rods_per_cta, grid, s)
+                        : sr::launch_packed_kernel<double, NT, 1, false, false, true, false, false, false, true>(A, rods_per_cta, grid, s);
+  h->launches++;
+  if (e != cudaSuccess) return cuda_fail("rod_packed_kernel (tapered) launch", e);
+  return SR_OK;
 }
 
 template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
@@ -357,7 +373,7 @@ template <typename T, int NT, int MINB> int launch_packed(sr_handle *h, sr::RodA
     }
     return launch_packed_impl<T, NT, MINB, false, false, true, false, true>(h, A, s);
   }
-  if (A.contact_on || A.rest_kappa) {
+  if (A.contact_on || A.rest_kappa || A.sucker || A.ext_force || A.ext_couple) {
     if constexpr (F64) {
       if (use_fast_pair(h, A, s)) {
         int rc = launch_packed_impl<T, NT, MINB, false, false, true, false, false, true>(h, A, s);
@@ -427,6 +443,12 @@ int lean_threads_setting(int n_elem) {
 }
 
 template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (A.elem_tab) {
+      const int group = h->n_rod * (h->cfg.n_elem + 1) + (h->cfg.has_head ? 1 : 0);
+      return group <= 384 ? launch_tapered<384>(h, A, s) : launch_tapered<1024>(h, A, s);
+    }
+  }
   if (is_lean_config(A)) {
     if (A.n_elem + 1 <= 160) {
       if (lean_threads_override() == 160) return launch_lean_pair<T, 160, 3>(h, A, s);
@@ -532,6 +554,19 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     if (cfg->spline_n_ctrl < 2 || cfg->spline_n_ctrl > 14) return fail(SR_E_INVALID, "sr_create: spline_n_ctrl must be in [2, 14]");
     if (!(cfg->spline_max_rate > 0.0)) return fail(SR_E_INVALID, "sr_create: spline_max_rate must be > 0 (inf = unlimited)");
   }
+  if (cfg->tip_radius > 0.0) {
+    if (cfg->dtype != SR_DTYPE_F64 || cfg->math != SR_MATH_FAST)
+      return fail(SR_E_INVALID, "sr_create: tapered rods (tip_radius) are built for SR_DTYPE_F64 / SR_MATH_FAST");
+    if (cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE || cfg->bc_kind == SR_BC_PENDULUM_SLIDER ||
+        cfg->model != SR_MODEL_ROD || cfg->muscle_on || cfg->spline_dir_mask)
+      return fail(SR_E_INVALID, "sr_create: tapered rods are built for SR_MODEL_ROD with the plane-contact / multi-rod model family");
+  }
+  if (cfg->sucker_on) {
+    if (cfg->math != SR_MATH_FAST || cfg->model != SR_MODEL_ROD || cfg->laplace_filter_order != 0 || cfg->bc_kind == SR_BC_MOVING_BASE)
+      return fail(SR_E_INVALID, "sr_create: ControllableFixConstraint is built for SR_MATH_FAST / SR_MODEL_ROD");
+    if (cfg->sucker_index < 0 || cfg->sucker_index >= cfg->n_elem)
+      return fail(SR_E_INVALID, "sr_create: sucker_index must address an element (0 .. n_elem - 1)");
+  }
   if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
     return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
@@ -611,16 +646,69 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       return fail(SR_E_ALLOC, m);
     }
   }
+  if (cfg->sucker_on) {
+    const size_t sb = n_rods * h->elem_size;
+    if ((e = cudaMalloc(&h->sucker, sb)) != cudaSuccess || (e = cudaMemset(h->sucker, 0, sb)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
+  if (cfg->tip_radius > 0.0) {
+    // SURVEY A.1 / A.4 per element: radius_k = linspace(base, tip, n)[k]; uniform rest lengths L/n (the per-element
+    // deviation of the reference's linspace positions is carried by F_GAMMA as for uniform rods)
+    const int n = cfg->n_elem, st = h->stride;
+    const double PI = 3.141592653589793, rl = cfg->base_length / n, E = cfg->youngs_modulus;
+    const double G = cfg->shear_modulus > 0.0 ? cfg->shear_modulus : E / (2.0 * (1.0 + 0.5)), ac = 27.0 / 28.0;
+    std::vector<double> tab((size_t)sr::ET_FIELDS * st, 1.0), rad(n), Bel0(n), Bel2(n), mel(n), J0(n), J2(n);
+    const double stepr = n > 1 ? (cfg->tip_radius - cfg->base_radius) / (n - 1) : 0.0;
+    for (int k = 0; k < n; k++) {
+      rad[k] = (k == n - 1 && n > 1) ? cfg->tip_radius : k * stepr + cfg->base_radius;
+      const double A0 = PI * rad[k] * rad[k], I1 = A0 * A0 / (4.0 * PI), I3 = 2.0 * I1;
+      J0[k] = I1 * cfg->density * rl; J2[k] = I3 * cfg->density * rl;
+      Bel0[k] = E * I1; Bel2[k] = G * I3;
+      mel[k] = cfg->density * PI * (rad[k] * rad[k]) * rl;
+      tab[sr::ET_REST_LEN * st + k] = rl;
+      tab[sr::ET_S0 * st + k] = ac * G * A0; tab[sr::ET_S2 * st + k] = E * A0;
+      tab[sr::ET_J0 * st + k] = J0[k]; tab[sr::ET_J2 * st + k] = J2[k];
+      tab[sr::ET_VOL_PI * st + k] = (rad[k] * rad[k]) * rl;
+    }
+    for (int k = 0; k < n - 1; k++) {
+      tab[sr::ET_REST_VOR * st + k] = rl;
+      tab[sr::ET_B0 * st + k] = (Bel0[k + 1] * rl + Bel0[k] * rl) / (rl + rl);
+      tab[sr::ET_B2 * st + k] = (Bel2[k + 1] * rl + Bel2[k] * rl) / (rl + rl);
+    }
+    std::vector<double> mnode(n + 1, 0.0);
+    for (int k = 0; k < n; k++) { mnode[k] += 0.5 * mel[k]; mnode[k + 1] += 0.5 * mel[k]; }
+    for (int k = 0; k <= n; k++) tab[sr::ET_MASS * st + k] = mnode[k];
+    for (int k = 0; k < n; k++) {
+      double em = 0.5 * (mnode[k + 1] + mnode[k]);
+      if (k == 0) em += 0.5 * mnode[0];
+      if (k == n - 1) em += 0.5 * mnode[n];
+      const double c = cfg->damping_constant >= 0.0 ? cfg->damping_constant : 0.0;
+      tab[sr::ET_LOGCW0 * st + k] = -c * cfg->dt * em / J0[k];
+      tab[sr::ET_LOGCW2 * st + k] = -c * cfg->dt * em / J2[k];
+    }
+    const size_t tb = tab.size() * sizeof(double);
+    if ((e = cudaMalloc(&h->elem_tab, tb)) != cudaSuccess ||
+        (e = cudaMemcpy(h->elem_tab, tab.data(), tb, cudaMemcpyHostToDevice)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
   *h->h_redo_count = 0;
   fill_args<double>(*cfg, h->stride, h->a64);
   h->a64.spline = h->spline; h->a64.spline_tab = h->spline_tab;
   h->a64.redo = h->redo;
+  h->a64.sucker = (const double *)h->sucker; h->a64.sucker_index = cfg->sucker_index; h->a64.elem_tab = (const double *)h->elem_tab;
   h->a64.muscle = h->muscle;
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
   fill_args<float>(*cfg, h->stride, h->a32);
   h->a32.spline = h->spline; h->a32.spline_tab = h->spline_tab;
   h->a32.redo = h->redo;
+  h->a32.sucker = (const float *)h->sucker; h->a32.sucker_index = cfg->sucker_index;
   h->a32.muscle = h->muscle;
   h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
   h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim; h->a32.head = (float *)h->head;
@@ -631,7 +719,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFree(h->sk_scratch); cudaFree(h->sk_flag); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFree(h->sucker); cudaFree(h->ext_force); cudaFree(h->ext_couple); cudaFree(h->elem_tab); cudaFree(h->sk_scratch); cudaFree(h->sk_flag); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -825,6 +913,32 @@ int sr_get_rest_kappa(sr_handle *h, void **rest_kappa_dev) {
   return SR_OK;
 }
 
+int sr_get_sucker(sr_handle *h, void **ratio_dev) {
+  if (!h || !ratio_dev) return fail(SR_E_INVALID, "sr_get_sucker: null argument");
+  if (!h->sucker) return fail(SR_E_INVALID, "sr_get_sucker: handle was created without sucker_on");
+  *ratio_dev = h->sucker;
+  return SR_OK;
+}
+
+int sr_get_ext_loads(sr_handle *h, void **force_dev, void **couple_dev) {
+  if (!h || !force_dev || !couple_dev) return fail(SR_E_INVALID, "sr_get_ext_loads: null argument");
+  if (h->cfg.math != SR_MATH_FAST || h->cfg.model != SR_MODEL_ROD || h->cfg.laplace_filter_order != 0 ||
+      h->cfg.bc_kind == SR_BC_MOVING_BASE)
+    return fail(SR_E_INVALID, "sr_get_ext_loads: external loads are built for SR_MATH_FAST / SR_MODEL_ROD without filter / moving base");
+  if (!h->ext_force) {
+    SR_CUDA(cudaSetDevice(h->cfg.device));
+    const size_t bytes = (size_t)h->cfg.n_env * h->n_rod * 3 * h->stride * h->elem_size;
+    SR_CUDA(cudaMalloc(&h->ext_force, bytes));
+    SR_CUDA(cudaMalloc(&h->ext_couple, bytes));
+    SR_CUDA(cudaMemset(h->ext_force, 0, bytes));
+    SR_CUDA(cudaMemset(h->ext_couple, 0, bytes));
+    h->a64.ext_force = (const double *)h->ext_force; h->a64.ext_couple = (const double *)h->ext_couple;
+    h->a32.ext_force = (const float *)h->ext_force; h->a32.ext_couple = (const float *)h->ext_couple;
+  }
+  *force_dev = h->ext_force; *couple_dev = h->ext_couple;
+  return SR_OK;
+}
+
 int sr_get_head(sr_handle *h, void **head_dev, int32_t *dim) {
   if (!h || !head_dev || !dim) return fail(SR_E_INVALID, "sr_get_head: null argument");
   if (!h->cfg.has_head) return fail(SR_E_INVALID, "sr_get_head: this handle has no rigid head");
@@ -874,6 +988,14 @@ int sr_copy_from(sr_handle *dst, sr_handle *src, void *stream) {
     int rc = sr_get_rest_kappa(dst, &rk);     // allocates on first use
     if (rc != SR_OK) return rc;
     SR_CUDA(cp(rk, src->rest_kappa, n_rods * 3 * dst->stride * es));
+  }
+  if (src->sucker && dst->sucker) SR_CUDA(cp(dst->sucker, src->sucker, n_rods * es));
+  if (src->ext_force) {
+    void *f = nullptr, *c = nullptr;
+    int rc = sr_get_ext_loads(dst, &f, &c);
+    if (rc != SR_OK) return rc;
+    SR_CUDA(cp(f, src->ext_force, n_rods * 3 * dst->stride * es));
+    SR_CUDA(cp(c, src->ext_couple, n_rods * 3 * dst->stride * es));
   }
   if (src->muscle) SR_CUDA(cp(dst->muscle, src->muscle, n_env * dst->muscle_dim * sizeof(double)));
   if (src->spline) SR_CUDA(cp(dst->spline, src->spline, n_env * dst->spline_dim * sizeof(double)));

@@ -118,6 +118,15 @@ typedef struct sr_config {
    * substep where the reference does it.  Targets / cached values / cached magnitudes: sr_get_spline. */
   int32_t spline_dir_mask, spline_n_ctrl;
   double spline_scale, spline_max_rate;
+
+  /* Tapered rod: `base_radius` an array np.linspace(base_radius, tip_radius, n_elem)
+   * (envs/octopus/build_muscle_octopus.py:61-63); <= 0: uniform radius.  FP64, SR_MATH_FAST, plane-contact / multi-rod
+   * model family only (the element constants then travel in an HBM table instead of the constant bank). */
+  double tip_radius;
+  /* ControllableFixConstraint (envs/octopus/controllable_constraint.py:24-69, the octopus arms' "sucker"): after the
+   * dampers, velocity and angular velocity of node / element `sucker_index` of every rod are scaled by
+   * 1 - reduction_ratio; the per-rod ratios (0 = released) are device data the caller writes (sr_get_sucker). */
+  int32_t sucker_on, sucker_index;
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -179,6 +188,14 @@ int sr_get_state(sr_handle *h, sr_state_view *out);
  * Rod arrays only: BC anchors, the rigid head, rest curvatures, the 3D pendulum's base controller and the
  * forcings' state are not part of the view — use sr_copy_from to clone a whole handle. */
 int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
+/* ControllableFixConstraint ratios, [n_env * n_rod_per_env] of the handle's element type (needs sucker_on). */
+int sr_get_sucker(sr_handle *h, void **ratio_dev);
+/* Generic per-element external loads evaluated every substep as a forcing (what COOMM's ApplyMuscles would feed,
+ * envs/octopus/build_muscle_octopus.py:171-176): nodal forces in the lab frame, [n_rods][3][stride] slots 0..n_elem,
+ * and element couples in the material frame, [n_rods][3][stride] slots 0..n_elem-1, of the handle's element type;
+ * allocated (zeroed) by the first call.  Plane-contact / multi-rod / forcing model family (the lean path stays lean). */
+int sr_get_ext_loads(sr_handle *h, void **force_dev, void **couple_dev);
+
 /* Clone everything that evolves or parametrises the envs of `src` into `dst` (created with the same shapes): rod
  * arrays, BC anchors, model scratch, rigid heads, rest curvatures, muscle / spline forcing state.  Checkpoint /
  * restore; works across devices (peer copy).  Stream-ordered on `stream` of dst's device. */

@@ -548,8 +548,11 @@ static void sucker_rates(ro_rod *r) {
 }
 
 static void phase_rates(ro_rod *r, const double *bv) {
-  if (r->cfg.damping_before_constraints) { dampen_rates(r); constrain_rates(r, bv); sucker_rates(r); }
-  else { constrain_rates(r, bv); sucker_rates(r); dampen_rates(r); }
+  /* the sucker constraint is registered by the env after the build function registered the dampers
+   * (crawl_env.py:146-157 after build_muscle_octopus.py:95-107; arm_push_env.py:182-195): it runs last */
+  if (r->cfg.damping_before_constraints) { dampen_rates(r); constrain_rates(r, bv); }
+  else { constrain_rates(r, bv); dampen_rates(r); }
+  sucker_rates(r);
 }
 
 static void phase_second_half(ro_rod *r, const double *bp) {

@@ -408,25 +408,26 @@ class OracleSoftPendulum3D:
 
 def octopus_assembly(n_arm=8, n_elem=10, time_step=7e-5, head_radius=0.04, head_density=700.0,
                      body_arm_k=1e6, body_arm_kt=1.0, body_arm_nu=1e-3, friction_multiplier=1.0,
-                     base_length=0.35, base_radius=0.35 * 0.02, youngs_modulus=1e6, density=1000.0):
+                     base_length=0.35, base_radius=0.35 * 0.02, youngs_modulus=1e6, density=1000.0,
+                     tip_radius=0.0, plane=True, gravity=-9.81, damping_constant=1e-2, angle_offset=0.0):
     """The systems `build_octopus` assembles (reference envs/octopus/build.py:52-217), on the C oracle:
     n_arm arms at 360/n_arm degrees around a rigid Cylinder head, FixedJoint2Rigid joints, gravity and
     AnalyticalLinearDamper(1e-2) on the arms, anisotropic plane friction under each arm."""
     L0, r0 = base_length, base_radius
-    g = -9.81
-    mu = L0 / (2.0 * 2.0 * abs(g) * 0.1)
+    g = gravity
+    mu = L0 / (2.0 * 2.0 * 9.81 * 0.1)
     kinetic = np.array([mu, 1.5 * mu, 2.0 * mu]) * friction_multiplier
     contact = dict(plane_origin=(0.0, 0.0, -r0), plane_normal=(0.0, 0.0, 1.0), k=1e2, nu=1e1,
                    slip_velocity_tol=1e-8, static_mu=2 * kinetic, kinetic_mu=kinetic)
-    angles = [360 / n_arm * i for i in range(n_arm)]
+    angles = [angle_offset + 360 / n_arm * i for i in range(n_arm)]
     arms = []
     for ang in angles:
         # scipy Rotation.from_euler("z", ang, degrees=True).apply(v) for v along x
         c, s = np.cos(np.deg2rad(ang)), np.sin(np.deg2rad(ang))
         arms.append(dict(n_elem=n_elem, start=(c * head_radius, s * head_radius, 0.0), direction=(c, s, 0.0),
                          normal=(0.0, 0.0, 1.0), base_length=L0, base_radius=r0, density=density,
-                         youngs_modulus=youngs_modulus, gravity=(0.0, 0.0, g), damping_constant=1e-2,
-                         contact=contact))
+                         youngs_modulus=youngs_modulus, gravity=(0.0, 0.0, g), damping_constant=damping_constant,
+                         contact=contact if plane else None, tip_radius=tip_radius))
     head = dict(start=(0.0, 0.0, -r0), direction=(0.0, 0.0, 1.0), normal=(0.0, 1.0, 0.0), length=2 * r0,
                 radius=head_radius, density=head_density)
     joint = dict(k=body_arm_k, nu=body_arm_nu, kt=body_arm_kt, radius=head_radius)

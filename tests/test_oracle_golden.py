@@ -310,3 +310,29 @@ def test_c_oracle_assembly_matches_reference_octopus_fixture(golden_dir, fixture
         worst = max(worst, _check_assembly(asm, g, f"state{i + 1}", 1e-9))
     print("assembly oracle vs shim fixture: worst", worst)
     asm.close()
+
+
+@pytest.mark.parametrize("convention,G_over_E", [(0, 1.0 / 3.0), (1, 1.0 / 1.5)])
+def test_default_shear_modulus_conventions_are_separated_by_a_short_beam(convention, G_over_E):
+    """SURVEY B-4 (unverifiable without pyelastica 1.0.0): which shear modulus does `straight_rod` take when none is
+    passed — E / (2 (1 + nu)) = E/3 (this build's default, convention 0) or E / (1 + nu) = E/1.5 (what the reference's
+    authors write wherever they do pass it: build_muscle_octopus.py:30, continuum_snake.py:302)?  A short thick
+    cantilever (L / r = 5) puts 9 % / 5 % of its tip deflection into the shear term F L / (alpha_c G A), so the two
+    readings differ by 4 % — the oracle must land on Timoshenko's value for whichever convention is selected, which
+    shows both the default-G path and the size of what is at stake for the envs that rely on it (SoftPendulum, OctoFlat)."""
+    n, L, r, E, rho, F = 20, 0.5, 0.1, 1e6, 5000.0, -40.0
+    dl = L / n
+    dt = 0.01 * dl
+    rod = ro.OracleRod(n, [0, 0, 0], [0, 0, 1.0], [0, 1.0, 0], L, r, rho, E, dt, shear_convention=convention,
+                       damping_constant=3.0, bc_kind=ro.BC_ONE_END_FIXED)
+    rod.user_forces[0, -1] = F
+    rod.substeps(int(15 / dt))
+    A = np.pi * r * r
+    I = A * A / (4 * np.pi)
+    # (the discrete clamp acts at the centre of element 0: both the bending arm and the sheared length are L - dl/2)
+    bend, shear = F * (L - 0.5 * dl) ** 3 / (3 * E * I), F * (L - 0.5 * dl) / ((27 / 28) * (G_over_E * E) * A)
+    assert abs(rod.position_collection[0, -1] / (bend + shear) - 1) < 2e-3      # linear beam theory at 4 % deflection
+    other = F * (L - 0.5 * dl) / ((27 / 28) * ((1.0 - G_over_E) * E) * A)      # (1/3 <-> 2/3)
+    assert abs((bend + other) / (bend + shear) - 1) > 0.03           # the two conventions are 3-4 % apart here
+    assert np.abs(rod.velocity_collection).max() < 1e-5
+    rod.close()

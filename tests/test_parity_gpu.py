@@ -1248,3 +1248,140 @@ def test_contact_env_bits_are_independent_of_its_neighbours():
     alone, calm, wild = run(1, False), run(11, False), run(11, True)
     for s in range(12):
         assert torch.equal(alone[s], calm[s]) and torch.equal(alone[s], wild[s]), f"step {s}"
+
+
+# ---- groundwork for the muscle-driven octopus envs: tapered rods, sucker constraint, external loads ----
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_tapered_rod_with_sucker_and_external_loads_vs_c_oracle(seed):
+    """A single tapered arm (base_radius = linspace(base, tip, n): build_muscle_octopus.py:61-63), one end free or
+    clamped, with a ControllableFixConstraint on node / element 0 (controllable_constraint.py:46-69), smooth external
+    nodal forces (lab frame) and element couples (material frame) applied every substep as a forcing, gravity and the
+    analytical damper; odd seeds add the frictionless plane.  CUDA (per-element constants from the HBM table) vs the
+    C oracle (whose arrays are per element anyway), every field, 600 substeps, 1e-9."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    rng = np.random.default_rng(300 + seed)
+    n = int(rng.choice([12, 25, 40, 63]))
+    L, r_base = 0.2, 0.012
+    r_tip = float(r_base * rng.uniform(0.08, 0.5))
+    E, rho = 1e5, 1050.0
+    dt = float(0.05 * (L / n) / np.sqrt(E / rho))
+    bc = int(rng.choice([0, 1]))
+    ratio = float(rng.uniform(0.0, 1.0))
+    plane = dict(plane_origin=(0.0, 0.0, -r_base), plane_normal=(0.0, 0.0, 1.0), k=1e2, nu=1e1, slip_velocity_tol=1e-8,
+                 static_mu=(0.0, 0.0, 0.0), kinetic_mu=(0.0, 0.0, 0.0)) if seed % 2 else None
+    s_n, s_e = np.linspace(0, 1, n + 1), np.linspace(0, 1, n)
+    # loads scaled with the local cross-section (a muscle's force goes with its area, its couple with area x radius)
+    tn, te = (1 + (r_tip / r_base - 1) * s_n) ** 2, (1 + (r_tip / r_base - 1) * s_e) ** 3
+    fext = 2e-3 * tn * np.stack([rng.uniform(-1, 1) * np.sin(np.pi * s_n), rng.uniform(-1, 1) * s_n, rng.uniform(-1, 1) * np.cos(np.pi * s_n)])
+    cext = 2e-4 * te * np.stack([rng.uniform(-1, 1) * np.sin(np.pi * s_e), rng.uniform(-1, 1) * np.sin(2 * np.pi * s_e), rng.uniform(-1, 1) * s_e])
+    o = ro.OracleRod(n, [0, 0, 0], [1.0, 0, 0], [0, 0, 1.0], L, r_base, rho, E, dt, gravity=(0.0, 0.0, -9.81),
+                     damping_constant=0.05, bc_kind=bc, contact=plane, tip_radius=r_tip)
+    o.user_forces[...] = fext; o.user_torques[...] = cext
+    o.set_sucker(0, 0, ratio)
+    n_env = 3
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, base_length=L, base_radius=r_base, density=rho,
+                   youngs_modulus=E, gravity=(0.0, 0.0, -9.81), damping_constant=0.05, bc_kind=bc, contact=plane,
+                   tip_radius=r_tip, sucker_index=0)
+    init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+    h.reset_host(init)
+    h.sucker_tensor()[:] = ratio
+    f_t, c_t = h.ext_load_tensors()
+    f_t[:] = torch.as_tensor(fext, device="cuda"); c_t[:] = torch.as_tensor(cext, device="cuda")
+    worst = 0.0
+    for chunk in (250, 350):
+        h.step_host(None, chunk); o.substeps(chunk)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        for fk in FIELDS.values():
+            ref = getattr(o, fk)
+            err = float(np.abs(f[fk][1] - ref).max() / max(np.abs(ref).max(), ASM_FLOOR[fk] * 0.1))
+            worst = max(worst, err)
+            assert err < TOL, f"seed {seed} (n {n}, tip/base {r_tip / r_base:.2f}, bc {bc}, plane {plane is not None}) {fk}: {err:.3e}"
+    assert np.abs(o.velocity_collection).max() > 1e-3      # the loads did move the arm
+    print(f"tapered rod seed {seed}: n {n} tip/base {r_tip / r_base:.2f} bc {bc} plane {plane is not None} worst {worst:.2e}")
+    h.close(); o.close()
+
+
+def test_tapered_muscle_octopus_topology_vs_c_oracle():
+    """The systems build_octopus_muscles assembles (build_muscle_octopus.py:70-179), minus the COOMM forcing: eight
+    tapered arms at 22.5 + 45 i degrees around a light rigid head, FixedJoint2Rigid (kt = 1e2), dampers, no gravity,
+    no plane; a sucker on node 0 of every arm (crawl_env.py:146-157) with per-arm ratios, and synthetic per-element
+    external couples standing in for ApplyMuscles.  CUDA vs the multi-rod C oracle, every field, 600 substeps, 1e-9."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    rng = np.random.default_rng(77)
+    n_arm, n, L, r_base, r_tip, head_radius = 8, 20, 0.2, 0.012, 0.0012, 0.02
+    E, rho, dt = 1e5, 1050.0, 1e-5
+    k, kt, nu, head_density = 1e4, 1e2, 1e-3, 50.0
+    asm = ro.octopus_assembly(n_arm=n_arm, n_elem=n, time_step=dt, head_radius=head_radius, head_density=head_density,
+                              body_arm_k=k, body_arm_kt=kt, body_arm_nu=nu, base_length=L, base_radius=r_base,
+                              youngs_modulus=E, density=rho, tip_radius=r_tip, plane=False, gravity=0.0,
+                              damping_constant=0.05, angle_offset=22.5)
+    s_e = np.linspace(0, 1, n)
+    ratios = rng.uniform(0, 1, n_arm)
+    te = (1 + (r_tip / r_base - 1) * s_e) ** 3
+    cext = np.stack([2e-4 * te * np.stack([rng.uniform(-1, 1) * np.sin(np.pi * s_e), rng.uniform(-1, 1) * np.sin(np.pi * s_e),
+                                            0.2 * rng.uniform(-1, 1) * s_e]) for _ in range(n_arm)])
+    for a, rod in enumerate(asm.arms):
+        rod.user_torques[...] = cext[a]
+        rod.set_sucker(0, 0, ratios[a])
+    n_env = 2
+    angles = [22.5 + 45.0 * a for a in range(n_arm)]
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, base_length=L, base_radius=r_base, density=rho,
+                   youngs_modulus=E, gravity=(0.0, 0.0, 0.0), damping_constant=0.05, bc_kind=nat.BC_FREE, n_rod=n_arm,
+                   head=dict(length=2 * r_base, radius=head_radius, density=head_density),
+                   joint=dict(radius=head_radius, angles_deg=angles, k=k, nu=nu, kt=kt), tip_radius=r_tip, sucker_index=0)
+    row = []
+    for ang in angles:
+        c, s = np.cos(np.deg2rad(ang)), np.sin(np.deg2rad(ang))
+        row += [c * head_radius, s * head_radius, 0.0, c, s, 0.0, 0.0, 0.0, 1.0]
+    row += [0.0, 0.0, -r_base, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0]
+    h.reset(torch.as_tensor(np.repeat(np.array([row]), n_env, axis=0), device="cuda").contiguous())
+    h.sucker_tensor().unflatten(0, (n_env, n_arm))[:] = torch.as_tensor(ratios, device="cuda")
+    f_t, c_t = h.ext_load_tensors()
+    c_t.unflatten(0, (n_env, n_arm))[:] = torch.as_tensor(cext, device="cuda")
+    o6 = torch.empty((n_env, 6), dtype=torch.float32, device="cuda")
+    rew = torch.empty(n_env, dtype=torch.float64, device="cuda")
+    term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+    # the oracle's own one-ulp sensitivity (arms that have barely started to move amplify position round-off through
+    # the stiff joint springs): a replica whose arm positions sit on neighbouring doubles
+    def make():
+        a2 = ro.octopus_assembly(n_arm=n_arm, n_elem=n, time_step=dt, head_radius=head_radius, head_density=head_density,
+                                 body_arm_k=k, body_arm_kt=kt, body_arm_nu=nu, base_length=L, base_radius=r_base,
+                                 youngs_modulus=E, density=rho, tip_radius=r_tip, plane=False, gravity=0.0,
+                                 damping_constant=0.05, angle_offset=22.5)
+        for a, rod in enumerate(a2.arms):
+            rod.user_torques[...] = cext[a]
+            rod.set_sucker(0, 0, ratios[a])
+        return a2
+    rep = make()
+    prng = np.random.default_rng(5)
+    for rod in rep.arms:
+        x = rod.position_collection
+        x[...] = np.nextafter(x, np.where(prng.random(x.shape) < 0.5, -np.inf, np.inf))
+    worst, worst_rel = 0.0, 0.0
+    for chunk in (300, 300):
+        h.step(None, chunk, o6, rew, term); asm.substeps(chunk); rep.substeps(chunk)
+        f = {k_: v.cpu().numpy() for k_, v in h.fields().items()}
+        hd = h.head_tensor().cpu().numpy()
+        assert int(term.sum()) == 0
+        for a, rod in enumerate(asm.arms):
+            for fk in FIELDS.values():
+                ref = getattr(rod, fk)
+                sens = float(np.abs(getattr(rep.arms[a], fk) - ref).max())
+                err_abs = float(np.abs(f[fk][1, a] - ref).max())
+                scale = max(float(np.abs(ref).max()), ASM_FLOOR[fk])
+                worst, worst_rel = max(worst, err_abs / scale), max(worst_rel, err_abs / max(TOL * scale, 20 * sens))
+                assert err_abs < max(TOL * scale, 20 * sens), f"arm {a} {fk}: {err_abs / scale:.3e} (one-ulp divergence of the oracle {sens / scale:.1e})"
+        mine = np.concatenate([asm.head_position, asm.head_velocity, asm.head_director.reshape(-1), asm.head_omega])
+        repl = np.concatenate([rep.head_position, rep.head_velocity, rep.head_director.reshape(-1), rep.head_omega])
+        for sl, fk in HEAD_SLICES:
+            scale = max(float(np.abs(mine[sl]).max()), ASM_FLOOR[fk])
+            err_abs, sens = float(np.abs(hd[1, sl] - mine[sl]).max()), float(np.abs(repl[sl] - mine[sl]).max())
+            worst = max(worst, err_abs / scale)
+            assert err_abs < max(TOL * scale, 20 * sens), f"head {fk}: {err_abs / scale:.3e}"
+    rep.close()
+    print(f"tapered muscle-octopus topology: worst {worst:.2e}")
+    h.close(); asm.close()
