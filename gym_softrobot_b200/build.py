@@ -95,8 +95,9 @@ def build_library(force: bool = False, verbose: bool = False, only=None) -> str:
                 obj = os.path.join(OBJ_DIR, name + ".o")
                 objs.append(obj)
                 fresh = os.path.exists(obj) and os.path.getmtime(obj) >= _newest(_tu_deps(src, deps))
-                if only is not None and only not in name and os.path.exists(obj):
-                    continue
+                if only is not None and only not in name and os.path.exists(obj) and \
+                        os.path.getmtime(obj) >= _newest(_tu_deps(src, _COMMON)):
+                    continue     # quick partial rebuild: allowed only while the shared headers (RodArgs layout!) are older
                 if force or not fresh:
                     jobs.append((name, src, defs, obj, verbose))
             workers = max(1, min(len(jobs), os.cpu_count() or 1))

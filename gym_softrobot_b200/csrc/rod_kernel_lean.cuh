@@ -95,6 +95,10 @@ __device__ __forceinline__ bool out_of_range(float x, int, float limf) { return 
 //     stresses, couples, damper and all the scalar algebra run in FP32.  Between launches the state is stored in
 //     FP32, with the element edge vectors as fields of their own (F_EDGE) so that the strain survives the
 //     rounding of absolute positions: the launch rebuilds FP64 node positions from node 0 + the running sum of edges.
+//     Measured (4096 x SoftPendulum, B200): 1.644 ms per env step against 1.524 ms in FP64 — this mode halves the
+//     state in HBM, it is not the fast mode.  Pushing more into FP32 (FP32 rates, FP32 rotation increments accumulated
+//     into FP64 frames: 56 FP64 instructions + 35 conversions per element-substep) was tried and was slower still,
+//     1.728 ms: F2F conversions issue at the FP64 rate, and velocity error rose to 3.6e-5 (scripts/gpu_r2n.sh).
 template <typename ST, int NT, int MINB, bool FASTONLY>
 __global__ void __launch_bounds__(NT, MINB)
 rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
@@ -122,7 +126,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   // the next takes part in both, in rod order) instead of CTA-wide: rods then drift apart and fill each other's
   // pipeline bubbles.  Needs tpr >= 32 (a warp touches at most two rods) and <= 15 rods per CTA (barrier ids 1..15).
   int bar_id0 = 0, bar_cnt0 = 0, bar_id1 = 0, bar_cnt1 = 0;
-  const bool rod_barriers = A.sk_rodsync && tpr >= 32 && rods_per_cta <= 15;
+  const bool rod_barriers = A.sk_rodsync && tpr >= 32 && rods_per_cta >= 2 && rods_per_cta <= 15;
   if (rod_barriers) {
     const int wp = tid >> 5;
     for (int rr = 0; rr < rods_per_cta; rr++) {

@@ -90,7 +90,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   // drift apart and fill each other's pipeline bubbles (lean kernel: +13 % with one 512-thread CTA per SM).  Needs
   // G >= 32 (a warp touches at most two groups) and <= 15 groups per CTA (barrier ids 1..15).
   int bar_id0 = 0, bar_cnt0 = 0, bar_id1 = 0, bar_cnt1 = 0;
-  const bool grp_barriers = A.sk_rodsync && G >= 32 && rods_per_cta <= 15;
+  // (one group per CTA: nothing to decouple; the filtered model's 9 synchronisations per substep are cheaper CTA-wide)
+  const bool grp_barriers = !LAPLACE && A.sk_rodsync && G >= 32 && rods_per_cta >= 2 && rods_per_cta <= 15;
   if (grp_barriers) {
     const int wp = tid >> 5;
     for (int rr = 0; rr < rods_per_cta; rr++) {
@@ -846,7 +847,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         T fw[3] = {elem_in ? w[0] : T(0), elem_in ? w[1] : T(0), elem_in ? w[2] : T(0)};
         // pass 0 sees the *unfiltered* ends (w[0], w[-1] are only zeroed after the first update)
         T ev[3] = {v[0], v[1], v[2]}, ew[3] = {w[0], w[1], w[2]};
-        const int t_left = (j > 0) ? tid - 1 : tid;
+        // end nodes / elements (and idle threads) take themselves as both neighbours: (-f - f + 2 f) / 4 = 0 exactly,
+        // which is the "ends held at 0" of the reference without a select per component and pass
+        const int tv_next = node_in ? tid + 1 : tid, tv_left = node_in ? tid - 1 : tid;
+        const int tw_next = elem_in ? tid + 1 : tid, tw_left = elem_in ? tid - 1 : tid;
         auto pass = [&](T *buf, bool first_pass) {
 #pragma unroll
           for (int c = 0; c < 3; c++) {
@@ -857,10 +861,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
           for (int c = 0; c < 3; c++) {
             T mv = first_pass ? ev[c] : fv[c], mw = first_pass ? ew[c] : fw[c];
-            T nv = (-buf[c * RS + t_next] - buf[c * RS + t_left] + T(2) * mv) * T(0.25);
-            T nw = (-buf[(3 + c) * RS + t_next] - buf[(3 + c) * RS + t_left] + T(2) * mw) * T(0.25);
-            fv[c] = node_in ? nv : T(0);
-            fw[c] = elem_in ? nw : T(0);
+            fv[c] = (-buf[c * RS + tv_next] - buf[c * RS + tv_left] + T(2) * mv) * T(0.25);
+            fw[c] = (-buf[(3 + c) * RS + tw_next] - buf[(3 + c) * RS + tw_left] + T(2) * mw) * T(0.25);
           }
         };
         if (A.laplace_order == 7) {   // SoftPendulum3D-v0's order: unrolled, buffers and the first-pass case resolved at compile time

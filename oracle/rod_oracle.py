@@ -81,23 +81,42 @@ class ROAsmConfig(C.Structure):
     ]
 
 
-def build(force: bool = False) -> str:
-    """Compile the C oracle (gcc, -ffp-contract=off).  Building the checker is not using it."""
+_VARIANTS = {None: "librod_oracle.so", "fma": "librod_oracle_fma.so"}
+
+
+def build(force: bool = False, variant=None) -> str:
+    """Compile the C oracle (gcc, -ffp-contract=off; variant "fma": -O3 with FMA contraction — the same source built
+    the other legitimate way, used to MEASURE how far two correct builds drift apart).  Building the checker is not using it."""
     src = os.path.join(_HERE, "rod_oracle.c")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", _HERE, "-B", "_build/librod_oracle.so"], check=True,
-                       stdout=subprocess.DEVNULL)
-    return _LIB_PATH
+    path = os.path.join(_HERE, "_build", _VARIANTS[variant])
+    if force or not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(src), os.path.getmtime(src[:-1] + "h")):
+        subprocess.run(["make", "-C", _HERE, "-B", "_build/" + _VARIANTS[variant]], check=True, stdout=subprocess.DEVNULL)
+    return path
 
 
-_lib = None
+_libs = {}
+_variant = None
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        L = C.CDLL(_LIB_PATH)
+class variant:
+    """`with rod_oracle.variant("fma"): ...` — oracle objects created inside use that build of the library."""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        global _variant
+        self.prev, _variant = _variant, self.name
+
+    def __exit__(self, *a):
+        global _variant
+        _variant = self.prev
+
+
+def lib(which="current"):
+    v = _variant if which == "current" else which
+    if v not in _libs:
+        L = C.CDLL(build(variant=v))
         L.ro_create.restype = C.c_void_p
         L.ro_create.argtypes = [C.POINTER(ROConfig)]
         L.ro_destroy.argtypes = [C.c_void_p]
@@ -134,8 +153,8 @@ def lib():
             f.argtypes = [C.c_void_p]
         L.ro_substeps_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
         L.ro_asm_substeps_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int]
-        _lib = L
-    return _lib
+        _libs[v] = L
+    return _libs[v]
 
 
 class OracleRod:
@@ -187,7 +206,8 @@ class OracleRod:
         self.cfg = cfg
         self.n = n_elem
         self._owned = _handle is None
-        self._h = C.c_void_p(lib().ro_create(C.byref(cfg))) if _handle is None else C.c_void_p(_handle)
+        self._L = lib()
+        self._h = C.c_void_p(self._L.ro_create(C.byref(cfg))) if _handle is None else C.c_void_p(_handle)
         n = n_elem
         self.position_collection = self._view("position", (3, n + 1))
         self.velocity_collection = self._view("velocity", (3, n + 1))
@@ -210,27 +230,27 @@ class OracleRod:
         self.spline_magnitude = self._view("spline_magnitude", (3, n))
 
     def _view(self, name, shape):
-        p = getattr(lib(), "ro_" + name)(self._h)
+        p = getattr(self._L, "ro_" + name)(self._h)
         return np.ctypeslib.as_array(p, shape=(int(np.prod(shape)),)).reshape(shape)
 
     @property
     def time(self):
-        return lib().ro_time(self._h)
+        return self._L.ro_time(self._h)
 
     def substeps(self, n, action=0.0, base_pos=None, base_vel=None):
         bp = None if base_pos is None else np.ascontiguousarray(base_pos, dtype=np.float64)
         bv = None if base_vel is None else np.ascontiguousarray(base_vel, dtype=np.float64)
-        lib().ro_substeps(self._h, int(n), float(action),
+        self._L.ro_substeps(self._h, int(n), float(action),
                           None if bp is None else bp.ctypes.data, None if bv is None else bv.ctypes.data)
 
     def set_sucker(self, slot, index, ratio):
         """ControllableFixConstraint(index, reduction_ratio) in slot `slot` (ratio 0 = released)."""
-        lib().ro_set_sucker(self._h, int(slot), int(index), float(ratio))
+        self._L.ro_set_sucker(self._h, int(slot), int(index), float(ratio))
 
     def close(self):
         if self._h:
             if self._owned:
-                lib().ro_destroy(self._h)
+                self._L.ro_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -266,26 +286,27 @@ class OracleAssembly:
             ac.head_direction[:] = [0.0, 0.0, 1.0]
             ac.head_normal[:] = [0.0, 1.0, 0.0]
             ac.head_length = ac.head_radius = ac.head_density = 1.0
-        self._h = C.c_void_p(lib().ro_asm_create(cfgs, C.byref(ac)))
+        self._L = lib()
+        self._h = C.c_void_p(self._L.ro_asm_create(cfgs, C.byref(ac)))
         assert self._h
-        self.arms = [OracleRod(dt=dt, _handle=lib().ro_asm_arm(self._h, i), **kw) for i, kw in enumerate(arm_kwargs)]
-        hv = lambda name, shape: np.ctypeslib.as_array(getattr(lib(), "ro_asm_head_" + name)(self._h),
+        self.arms = [OracleRod(dt=dt, _handle=self._L.ro_asm_arm(self._h, i), **kw) for i, kw in enumerate(arm_kwargs)]
+        hv = lambda name, shape: np.ctypeslib.as_array(getattr(self._L, "ro_asm_head_" + name)(self._h),
                                                        shape=(int(np.prod(shape)),)).reshape(shape)
         self.head_position, self.head_velocity = hv("position", (3,)), hv("velocity", (3,))
         self.head_director, self.head_omega = hv("director", (3, 3)), hv("omega", (3,))
 
     @property
     def time(self):
-        return lib().ro_asm_time(self._h)
+        return self._L.ro_asm_time(self._h)
 
     def substeps(self, n):
-        lib().ro_asm_substeps(self._h, int(n))
+        self._L.ro_asm_substeps(self._h, int(n))
 
     def close(self):
         if self._h:
             for a in self.arms:
                 a.close()
-            lib().ro_asm_destroy(self._h)
+            self._L.ro_asm_destroy(self._h)
             self._h = None
 
     def __del__(self):
