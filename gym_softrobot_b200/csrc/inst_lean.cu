@@ -1,12 +1,12 @@
 // inst_lean.cu — the lean kernel (rod_kernel_lean.cuh) for one storage type and CTA size:
-//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n>
+//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n> [-DSR_TU_CONTACT=1: the contact variant, FP64 only]
 #include <atomic>
 #include "launch.cuh"
 #include "rod_kernel_lean.cuh"
 
 namespace sr {
 
-template <typename T, int NT, int MINB, bool FASTONLY> static cudaError_t lean_opt_in() {
+template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT> static cudaError_t lean_opt_in() {
   // the opt-in above 48 KB is a per-device attribute of the function: one bit per device ordinal
   static std::atomic<unsigned long long> opted{0};
   int dev = 0;
@@ -14,7 +14,7 @@ template <typename T, int NT, int MINB, bool FASTONLY> static cudaError_t lean_o
   if (e != cudaSuccess) return e;
   const unsigned long long bit = 1ULL << (dev & 63);
   if (!(opted.load(std::memory_order_relaxed) & bit)) {
-    e = cudaFuncSetAttribute(rod_lean_kernel<T, NT, MINB, FASTONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    e = cudaFuncSetAttribute(rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(lean_smem_words(NT) * sizeof(double)));
     if (e != cudaSuccess) return e;
     opted.fetch_or(bit, std::memory_order_relaxed);
@@ -22,24 +22,27 @@ template <typename T, int NT, int MINB, bool FASTONLY> static cudaError_t lean_o
   return cudaSuccess;
 }
 
-template <typename T, int NT, int MINB, bool FASTONLY> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s) {
-  cudaError_t e = lean_opt_in<T, NT, MINB, FASTONLY>();
+template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s) {
+  cudaError_t e = lean_opt_in<T, NT, MINB, FASTONLY, CONTACT>();
   if (e != cudaSuccess) return e;
-  rod_lean_kernel<T, NT, MINB, FASTONLY><<<grid, NT, lean_smem_words(NT) * sizeof(double), s>>>(A);
+  rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT><<<grid, NT, lean_smem_words(NT) * sizeof(double), s>>>(A);
   return cudaGetLastError();
 }
 
-template <typename T, int NT, int MINB, bool FASTONLY> int lean_ctas_per_sm() {
-  if (lean_opt_in<T, NT, MINB, FASTONLY>() != cudaSuccess) return 0;
+template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT> int lean_ctas_per_sm() {
+  if (lean_opt_in<T, NT, MINB, FASTONLY, CONTACT>() != cudaSuccess) return 0;
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rod_lean_kernel<T, NT, MINB, FASTONLY>, NT,
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT>, NT,
                                                     lean_smem_words(NT) * sizeof(double)) != cudaSuccess) return 0;
   return nb;
 }
 
-template cudaError_t launch_lean_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, true>(const RodArgs<SR_TU_T> &, int, cudaStream_t);
-template cudaError_t launch_lean_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, false>(const RodArgs<SR_TU_T> &, int, cudaStream_t);
-template int lean_ctas_per_sm<SR_TU_T, SR_TU_NT, SR_TU_MINB, true>();
-template int lean_ctas_per_sm<SR_TU_T, SR_TU_NT, SR_TU_MINB, false>();
+#ifndef SR_TU_CONTACT
+#define SR_TU_CONTACT 0
+#endif
+template cudaError_t launch_lean_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, true, SR_TU_CONTACT != 0>(const RodArgs<SR_TU_T> &, int, cudaStream_t);
+template cudaError_t launch_lean_kernel<SR_TU_T, SR_TU_NT, SR_TU_MINB, false, SR_TU_CONTACT != 0>(const RodArgs<SR_TU_T> &, int, cudaStream_t);
+template int lean_ctas_per_sm<SR_TU_T, SR_TU_NT, SR_TU_MINB, true, SR_TU_CONTACT != 0>();
+template int lean_ctas_per_sm<SR_TU_T, SR_TU_NT, SR_TU_MINB, false, SR_TU_CONTACT != 0>();
 
 }  // namespace sr

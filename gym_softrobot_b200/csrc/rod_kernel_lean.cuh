@@ -99,11 +99,18 @@ __device__ __forceinline__ bool out_of_range(float x, int, float limf) { return 
 //     state in HBM, it is not the fast mode.  Pushing more into FP32 (FP32 rates, FP32 rotation increments accumulated
 //     into FP64 frames: 56 FP64 instructions + 35 conversions per element-substep) was tried and was slower still,
 //     1.728 ms: F2F conversions issue at the FP64 rate, and velocity error rose to 3.6e-5 (scripts/gpu_r2n.sh).
-template <typename ST, int NT, int MINB, bool FASTONLY>
+//
+// CONTACT = true (FP64 only): the same skeleton for a single rod on the frictional plane — per-env rest curvature
+// (flat_env.py:310-311 style actuation), RodPlaneContactWithAnisotropicFriction (two more exchanges and
+// per-rod barriers per substep), the MuscleTorques travelling wave of ContinuumSnake-v0, and the internal frame whose
+// z axis is the plane normal (see rod_kernel_packed.cuh).  OctoArmSingle-v0, ContinuumSnake-v0 and BASELINE config 5.
+template <typename ST, int NT, int MINB, bool FASTONLY, bool CONTACT = false>
 __global__ void __launch_bounds__(NT, MINB)
 rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   using D = double;
   constexpr bool MIXED = sizeof(ST) == 4;
+  static_assert(!CONTACT || !MIXED, "the contact variant is FP64 only");
+  constexpr int SCR = CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
   using F = typename std::conditional<MIXED, float, double>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   D *rec = reinterpret_cast<D *>(smem_raw);            // {x0 x1 | x2 v0 | v1 v2 | Q0 Q1 | ... | Q6 Q7 | Q8 - | - -}
@@ -119,6 +126,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   const bool in_cta = r < rods_per_cta;
   const bool first = (j == 0);
   if (tid < SNR) sn[SNR * NT + tid] = F(0);
+  if (CONTACT && tid < 2) rec[LEAN_REC * NT + 16 + tid] = D(0);   // stage-1 contact load "left of element 0"
   __syncthreads();   // (the per-rod barriers below do not order this store against the other rods' reads)
 
   // Barriers: data only crosses threads of the same rod, so a substep's two synchronisations can be per rod
@@ -141,6 +149,29 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     if (!rod_barriers) { __syncthreads(); return; }
     if (bar_cnt0) asm volatile("bar.sync %0, %1;" ::"r"(bar_id0), "r"(bar_cnt0) : "memory");
     if (bar_cnt1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id1), "r"(bar_cnt1) : "memory");
+  };
+
+  // contact variant: lab <-> internal frame (z = plane normal), a signed permutation for axis-aligned normals
+  const bool rot_frame = CONTACT && A.rot_on;
+  auto to_int = [&](D (&u)[3]) {
+    if (!rot_frame) return;
+    const D a = u[0], b = u[1], c = u[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[i] = fma((D)A.lab2int[3 * i + 2], c, fma((D)A.lab2int[3 * i + 1], b, (D)A.lab2int[3 * i] * a));
+  };
+  auto to_lab = [&](D (&u)[3]) {      // transpose
+    if (!rot_frame) return;
+    const D a = u[0], b = u[1], c = u[2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) u[i] = fma((D)A.lab2int[6 + i], c, fma((D)A.lab2int[3 + i], b, (D)A.lab2int[i] * a));
+  };
+  auto rows_to_int = [&](D (&M)[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { D u[3] = {M[3 * i], M[3 * i + 1], M[3 * i + 2]}; to_int(u); M[3 * i] = u[0]; M[3 * i + 1] = u[1]; M[3 * i + 2] = u[2]; }
+  };
+  auto rows_to_lab = [&](D (&M)[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { D u[3] = {M[3 * i], M[3 * i + 1], M[3 * i + 2]}; to_lab(u); M[3 * i] = u[0]; M[3 * i + 1] = u[1]; M[3 * i + 2] = u[2]; }
   };
 
   // constants of the FP64 part (the mixed mode reads double copies: a float dt would be off by 1e-8)
@@ -191,6 +222,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     D Q[9] = {D(1), D(0), D(0), D(0), D(1), D(0), D(0), D(0), D(1)};
     ST *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
     const ST *bc = A.bc + (size_t)(active ? env : 0) * BC_DIM;
+    // travelling-wave muscle torque (contact variant): time, (sin, cos) of the wave's common phase w t + phi, and this
+    // element's two amplitude combinations (below)
+    const bool mus = CONTACT && A.muscle_on;
+    D mus_t = D(0), mus_S = D(0), mus_C = D(1);
     if (s_begin > 0) {
       // continue an item the previous slot started: wait for its hand-over, then take the registers back
       if (tid == 0) {
@@ -199,11 +234,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         __threadfence();
       }
       __syncthreads();
-      const D *sc = A.sk_scratch + (size_t)(p - 1) * LEAN_REC * NT;
+      const D *sc = A.sk_scratch + (size_t)(p - 1) * SCR * NT;
 #pragma unroll
       for (int c = 0; c < 3; c++) { x[c] = sc[c * NT + tid]; v[c] = sc[(3 + c) * NT + tid]; w[c] = sc[(15 + c) * NT + tid]; }
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c] = sc[(6 + c) * NT + tid];
+      if (CONTACT) { mus_S = sc[18 * NT + tid]; mus_C = sc[19 * NT + tid]; mus_t = sc[20 * NT + tid]; }
       __syncthreads();
       if (tid == 0) A.sk_flag[p - 1] = 0;   // (graph-safe: the flag is back to 0 before the launch ends)
     } else {
@@ -216,6 +252,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         }
 #pragma unroll
         for (int c = 0; c < 9; c++) Q[c] = (D)st[(F_DIR + c) * stride + j];  // slot n holds I
+        if (CONTACT) { to_int(x); to_int(v); rows_to_int(Q); }
       }
       if (MIXED) {
         // FP64 node positions whose differences are the stored FP32 edge vectors exactly: node 0 (after the BC's
@@ -260,6 +297,38 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         for (int c = 0; c < 9; c++) Q[c] = (D)bc[3 + c];
 #pragma unroll
         for (int c = 0; c < 3; c++) x[c] = (D)bc[c];
+        if (CONTACT) { rows_to_int(Q); to_int(x); }
+      }
+    }
+    // contact variant: rest curvature at Voronoi point j (actuation), constant during a launch; the muscle wave
+    D rk[3] = {D(0), D(0), D(0)};
+    D mus_P = D(0), mus_R = D(0);
+    if constexpr (CONTACT) {
+      if (A.rest_kappa && vor_ok) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) rk[c] = (D)A.rest_kappa[((size_t)env * 3 + c) * stride + j];
+      }
+      if (mus && active) {
+        // MuscleTorques (continuum_snake.py:186-198): element k gets Q_k d (m_k [k >= 1] - m_{k+1} [k <= n-2]),
+        // m_k = min(1, t/ramp) beta_{n-1-k} sin(w t - kw s_{n-1-k} + phi).  sin(p - s) = sin p cos s - cos p sin s, so
+        // m_k - m_{k+1} = ramp (sin p * P - cos p * R) with per-element constants P = b0 cos s0 - b1 cos s1,
+        // R = b0 sin s0 - b1 sin s1; (sin p, cos p) advance by the fixed angle w dt per substep (a rotation, seeded
+        // from sincos at the start of the launch) instead of two libm sines per element and substep.
+        const double *mu = A.muscle + (size_t)env * A.muscle_dim;
+        if (s_begin == 0) {
+          mus_t = mu[0];
+          sincos(A.mus_omega * (mus_t + (double)c_half_dt) + A.mus_phase, &mus_S, &mus_C);
+        }
+        if (elem_ok) {
+          const double kw = mu[1], inv_n = 1.0 / (double)n;
+          const int k0 = n - 1 - j, k1 = n - 2 - j;
+          double b0 = 0.0, s0 = 0.0, b1 = 0.0, s1 = 0.0;
+          if (j >= 1) { b0 = mu[2 + k0]; s0 = kw * ((double)(k0 + 1) * inv_n); }
+          if (j <= n - 2) { b1 = mu[2 + k1]; s1 = kw * ((double)(k1 + 1) * inv_n); }
+          double sn0, cs0, sn1, cs1;
+          sincos(s0, &sn0, &cs0); sincos(s1, &sn1, &cs1);
+          mus_P = b0 * cs0 - b1 * cs1; mus_R = b0 * sn0 - b1 * sn1;
+        }
       }
     }
     const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
@@ -290,6 +359,20 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     bool check_trace = true;   // first substep of the segment: rule out a state that starts beyond 90 degrees of bend
     auto substep = [&](auto last_tag) {
       constexpr bool last = decltype(last_tag)::value;
+      D mtq[3] = {D(0), D(0), D(0)};
+      if constexpr (CONTACT) {
+        if (mus) {
+          mus_t += (double)c_half_dt;   // time of the force evaluation: after the first half step
+          const D cf = fmin(1.0, mus_t * A.mus_inv_ramp) * fma(mus_S, mus_P, -(mus_C * mus_R));
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+            mtq[i] = fma(Q[3 * i + 2], (D)A.mus_dir[2], fma(Q[3 * i + 1], (D)A.mus_dir[1], Q[3 * i] * (D)A.mus_dir[0])) * cf;
+          mus_t += (double)c_half_dt;
+          const D nS = fma(mus_C, A.mus_sd, mus_S * A.mus_cd);   // phase += w dt
+          mus_C = fma(-mus_S, A.mus_sd, mus_C * A.mus_cd);
+          mus_S = nS;
+        }
+      }
       // ---- publish what the neighbours need ----------------------------------------------------------------
       {
         double2 *o = reinterpret_cast<double2 *>(rec + LEAN_REC * tid);
@@ -401,10 +484,19 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       F kp[3], tau[3];
 #pragma unroll
       for (int i = 0; i < 3; i++) kp[i] = vec[i] * fs;
-      tau[0] = A.B[0] * kp[0]; tau[1] = A.B[0] * kp[1]; tau[2] = A.B[2] * kp[2];
-      // kappa x (B kappa) with B1 = B2:  ((B3 - B1) k2 k3, (B1 - B3) k1 k3, 0)
-      const F k2b = kp[2] * A.BDH;                        // (B3 - B1) D / 2: the quadrature weight of A_h folded in
-      const F kx0 = kp[1] * k2b, kx1 = -(kp[0] * k2b);
+      F kx0, kx1, kx2 = F(0);
+      if constexpr (CONTACT) {
+        // with a rest curvature the cross product keeps all its terms: kappa x (B (kappa - kappa0)), times D / 2
+        tau[0] = A.B[0] * (kp[0] - rk[0]); tau[1] = A.B[0] * (kp[1] - rk[1]); tau[2] = A.B[2] * (kp[2] - rk[2]);
+        kx0 = fma(kp[1], tau[2], -(kp[2] * tau[1])) * A.half_rest_vor;
+        kx1 = fma(kp[2], tau[0], -(kp[0] * tau[2])) * A.half_rest_vor;
+        kx2 = fma(kp[0], tau[1], -(kp[1] * tau[0])) * A.half_rest_vor;
+      } else {
+        tau[0] = A.B[0] * kp[0]; tau[1] = A.B[0] * kp[1]; tau[2] = A.B[2] * kp[2];
+        // kappa x (B kappa) with B1 = B2:  ((B3 - B1) k2 k3, (B1 - B3) k1 k3, 0)
+        const F k2b = kp[2] * A.BDH;                        // (B3 - B1) D / 2: the quadrature weight of A_h folded in
+        kx0 = kp[1] * k2b; kx1 = -(kp[0] * k2b);
+      }
       const F eps_v = (lgn + lg) * A.half_inv_rest_vor;
       F ie3 = rcp_nr(eps_v * eps_v * eps_v);
       if (!vor_ok) ie3 = F(0);
@@ -422,7 +514,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       F tql[3];
       tql[0] = fma(h0, inv_e, fma(kx0, ie3, m0));          // + m_j + c_j/2  (own element)
       tql[1] = fma(h1, inv_e, fma(kx1, ie3, m1));
-      tql[2] = fma(h2, inv_e, m2);
+      tql[2] = CONTACT ? fma(h2, inv_e, fma(kx2, ie3, m2)) : fma(h2, inv_e, m2);
       // {s0 s1 | s2 N0 | N1 m2}: N = c_j/2 - m_j goes to element j+1 (third component: -m2, negated by the reader)
       if (MIXED) {
         float4 *o = reinterpret_cast<float4 *>(sn + SNR * tid);
@@ -432,17 +524,24 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         double2 *o = reinterpret_cast<double2 *>(sn + SNR * tid);
         o[0] = make_double2((double)sfl[0], (double)sfl[1]);
         o[1] = make_double2((double)sfl[2], (double)fma(kx0, ie3, -m0));
-        o[2] = make_double2((double)fma(kx1, ie3, -m1), (double)m2);
+        o[2] = make_double2((double)fma(kx1, ie3, -m1), CONTACT ? (double)fma(-kx2, ie3, m2) : (double)m2);   // (the reader subtracts)
       }
       // rotational damper c_w^e = c_w exp((e-1) ln c_w) as a quadratic in (e-1) (coefficients made on the host; the
       // range limit keeps the dropped cubic term below 1.4e-15); c_w1 = c_w2 for a circular cross-section
       F cw0, cw2;
       {
-        const bool out = out_of_range(em1, A.lim_em1_hi, A.limf_em1);
+        const bool out = out_of_range(em1, CONTACT ? A.lim_em1c_hi : A.lim_em1_hi, A.limf_em1);
         if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
         if (FASTONLY || !out) {
-          cw0 = fma(fma(A.cwp[0][2], em1, A.cwp[0][1]), em1, A.cwp[0][0]);
-          cw2 = fma(fma(A.cwp[1][2], em1, A.cwp[1][1]), em1, A.cwp[1][0]);
+          if constexpr (CONTACT) {   // harder dampers, larger stretches: degree 5, |z| <= kLeanExpZc
+            F p0 = fma(A.cwc[0][5], em1, A.cwc[0][4]), p2 = fma(A.cwc[1][5], em1, A.cwc[1][4]);
+#pragma unroll
+            for (int k = 3; k >= 0; k--) { p0 = fma(p0, em1, A.cwc[0][k]); p2 = fma(p2, em1, A.cwc[1][k]); }
+            cw0 = p0; cw2 = p2;
+          } else {
+            cw0 = fma(fma(A.cwp[0][2], em1, A.cwp[0][1]), em1, A.cwp[0][0]);
+            cw2 = fma(fma(A.cwp[1][2], em1, A.cwp[1][1]), em1, A.cwp[1][0]);
+          }
         } else {
           cw0 = exp_ref<F>(e * A.logc_w[0]);
           cw2 = exp_ref<F>(e * A.logc_w[2]);
@@ -451,8 +550,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       if (last && active) {
         // stale observables of the reference: last force evaluation
 #pragma unroll
+        D tg_out[3] = {dx[0] * (D)ilg, dx[1] * (D)ilg, dx[2] * (D)ilg};
+        if (CONTACT) to_lab(tg_out);
+#pragma unroll
         for (int i = 0; i < 3; i++) {
-          st[(F_TAN + i) * stride + j] = (ST)((F)dx[i] * ilg);
+          st[(F_TAN + i) * stride + j] = (ST)tg_out[i];
           st[(F_KAPPA + i) * stride + j] = (ST)kp[i];
         }
         st[(F_SIGMA + 0) * stride + j] = (ST)(Qdx[0] * irg);
@@ -474,6 +576,123 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2];
         fint[0] = sfl[0] - (F)a0.x; fint[1] = sfl[1] - (F)a0.y; fint[2] = sfl[2] - (F)a1.x;
         tq[0] = tql[0] + (F)a1.y; tq[1] = tql[1] + (F)a2.x; tq[2] = tql[2] - (F)a2.y;
+      }
+      if constexpr (CONTACT) {
+        // forcing registered before the contact: the static-friction torque balance sees the muscle couple
+        if (mus && !A.contact_before_forcing) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) tq[i] += mtq[i];
+        }
+        if (A.contact_on) {
+          // RodPlaneContactWithAnisotropicFriction (elastica/_contact_functions.py), per element j between
+          // nodes j and j+1, in the frame whose z axis is the plane normal.  Stage 1: normal response + kinetic friction
+          // from the nodal forces accumulated so far; stage 2: static friction from the forces INCLUDING stage 1 of both
+          // neighbours (nodal forces mix adjacent elements), hence two more exchanges: stage-1 in-plane loads through the
+          // spare words 16..17 of the state records, the final loads through the (by then fully read) stress records.
+          const bool end0 = (j == 0), end1 = (j + 1 == n);
+          // element load = a0 f_j + a1 f_{j+1} (half of each node's force, an end node's in full); the mass weights of
+          // the element velocity: end nodes carry half a mass
+          const D a0 = end0 ? D(1.0) : D(0.5), a1 = end1 ? D(1.0) : D(0.5);
+          const D w0 = (end0 == end1) ? D(0.5) : end0 ? D(1.0 / 3.0) : D(2.0 / 3.0), w1 = D(1.0) - w0;
+          D etf[3], evel[3], t[3];
+          {
+            const double2 *qs = reinterpret_cast<const double2 *>(sn + SNR * t_next);
+            const double2 s01 = qs[0];
+            const D s2n = sn[SNR * t_next + 2];
+            const double2 *qr = reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next);
+            const double2 r1 = qr[1], r2 = qr[2];
+            const D sN[3] = {s01.x, s01.y, s2n}, vN[3] = {r1.y, r2.x, r2.y};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              const D f1 = sN[i] - sfl[i];                       // internal force on node j+1 (node j's is fint)
+              // external loads so far: gravity (a0 hm0 + a1 hm1 = 1 for every element: one whole nodal weight)
+              const D gi = A.contact_before_forcing ? D(0) : (D)A.gm[i];
+              etf[i] = fma(a1, f1, fma(a0, fint[i], gi));
+              evel[i] = fma(w1, vN[i], w0 * v[i]);
+              t[i] = dx[i] * ilg;
+            }
+          }
+          const D rad2 = A.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
+          const D fn = etf[2], vn = evel[2];
+          const D gap = (fma(D(0.5), dx[2], x[2]) - A.plane_z0) - rad, pen = fmin(gap, D(0));
+          const bool nocontact = !elem_ok || (gap > A.surface_tol);
+          const D resp_mag = (nocontact || fn > D(0)) ? D(0) : fabs(fn);
+          D c1[3];
+          c1[2] = nocontact ? D(0) : ((fn > D(0)) ? D(0) : -fn) - A.contact_k * pen - A.contact_nu * vn;
+          // axial direction = the tangent's projection on the plane, normalised with the reference's guard
+          // 1 / (|tp| + 1e-14) (to first order in 1e-14 / |tp|); rolling direction = axial x normal
+          const D tp2 = fma(t[1], t[1], t[0] * t[0]);
+          const D rtp = rsqrt_nr(tp2 + D(1e-300));   // (a rod standing on end: tp = 0, axial direction 0)
+          const D inv_tp = fma(D(-1e-14) * rtp, rtp, rtp);
+          const D ax0 = t[0] * inv_tp, ax1 = t[1] * inv_tp, rl0 = ax1, rl1 = -ax0;
+          auto slip_fn = [&](D a) {   // find_slipping_elements on |v| (|axial| = |rolling| = 1 - 1e-14 / |tp|: taken as 1)
+            return (a > A.slip_tol) ? fabs(D(1) - fmin(D(1), a * A.inv_slip_tol - D(1))) : D(1);
+          };
+          // sign(a) with sign(0) = +1: every use below multiplies a factor that vanishes with a
+          auto sgn1 = [](D a) { return __hiloint2double((__double2hiint(a) & 0x80000000) | 0x3ff00000, 0); };
+          const D vax = fma(evel[1], ax1, evel[0] * ax0);
+          const D kmu = (__double2hiint(vax) < 0) ? (D)A.kin_mu[1] : (D)A.kin_mu[0];
+          const D slipa = slip_fn(fabs(vax));
+          // velocity of the contact point relative to the axis: Q^T (w x Q arm), arm = -rad z
+          D qa[3], wq[3];
+#pragma unroll
+          for (int i = 0; i < 3; i++) qa[i] = -(Q[3 * i + 2] * rad);
+          cross3(w, qa, wq);
+          const D rv0 = fma(Q[6], wq[2], fma(Q[3], wq[1], Q[0] * wq[0])), rv1 = fma(Q[7], wq[2], fma(Q[4], wq[1], Q[1] * wq[0]));
+          const D smag = fma(evel[1] + rv1, rl1, (evel[0] + rv0) * rl0);
+          const D slipr = slip_fn(fabs(smag));
+          const D ut0 = fma(smag, rl0, vax * ax0), ut1 = fma(smag, rl1, vax * ax1);
+          const D ug0 = ut0 + D(1e-14), ug1 = ut1 + D(1e-14);
+          const D iun = rsqrt_nr(fma(ug1, ug1, fma(ug0, ug0, D(1e-28))));
+          const D uax = fma(ut1, ax1, ut0 * ax0) * iun, url = fma(ut1, rl1, ut0 * rl0) * iun;
+          const D ka = nocontact ? D(0) : -((D(1) - slipa) * kmu * resp_mag * uax);
+          const D kr = nocontact ? D(0) : -((D(1) - slipr) * A.kin_mu[2] * resp_mag * url);
+          D fr0 = kr * rl0, fr1 = kr * rl1;
+          c1[0] = fma(ka, ax0, fr0); c1[1] = fma(ka, ax1, fr1);
+          // couple of the rolling friction: Q (arm x F) = Q (rad F_y, -rad F_x, 0)
+          D cr0 = rad * fr1, cr1 = -(rad * fr0);
+          D text[3];
+#pragma unroll
+          for (int i = 0; i < 3; i++) text[i] = fma(Q[3 * i + 1], cr1, Q[3 * i] * cr0);
+          *reinterpret_cast<double2 *>(rec + LEAN_REC * tid + 16) = make_double2(c1[0], c1[1]);
+          rod_sync();
+          // stage 2: static friction (in-plane components only)
+          D e2[2];
+          {
+            const double2 cl = *reinterpret_cast<const double2 *>(rec + LEAN_REC * t_prev + 16);
+            const double2 cr = *reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next + 16);
+            const D nl[2] = {cl.x, cl.y}, nr[2] = {cr.x, cr.y};
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const D nc0 = D(0.5) * (nl[i] + c1[i]), nc1 = D(0.5) * (c1[i] + (end1 ? D(0) : nr[i]));   // stage-1 response on nodes j, j+1
+              e2[i] = fma(a1, nc1, fma(a0, nc0, etf[i]));
+            }
+          }
+          const D fax = fma(e2[1], ax1, e2[0] * ax0);
+          const D smu = (__double2hiint(fax) < 0) ? (D)A.stat_mu[1] : (D)A.stat_mu[0];
+          const D sa = nocontact ? D(0) : -(fmin(fabs(fax), slipa * smu * resp_mag) * sgn1(fax));
+          const D ts0 = tq[0] + text[0], ts1 = tq[1] + text[1], ts2 = tq[2] + text[2];
+          const D tt0 = fma(Q[6], ts2, fma(Q[3], ts1, Q[0] * ts0)), tt1 = fma(Q[7], ts2, fma(Q[4], ts1, Q[1] * ts0));
+          const D noslip = -((rad * fma(e2[1], rl1, e2[0] * rl0) - D(2) * fma(tt1, ax1, tt0 * ax0)) * (D(1.0 / 3.0) * inv_rad));
+          const D sr_ = nocontact ? D(0) : fmin(fabs(noslip), slipr * A.stat_mu[2] * resp_mag) * sgn1(noslip);
+          fr0 = sr_ * rl0; fr1 = sr_ * rl1;
+          const D p0 = c1[0] + fma(sa, ax0, fr0), p1 = c1[1] + fma(sa, ax1, fr1);
+          *reinterpret_cast<double2 *>(sn + SNR * tid) = make_double2(p0, p1);
+          sn[SNR * tid + 2] = c1[2];
+          cr0 = rad * fr1; cr1 = -(rad * fr0);
+#pragma unroll
+          for (int i = 0; i < 3; i++) tq[i] += text[i] + fma(Q[3 * i + 1], cr1, Q[3 * i] * cr0);
+          rod_sync();
+          {   // node j collects half of the plane's load on elements j-1 and j
+            const double2 l01 = *reinterpret_cast<const double2 *>(sn + SNR * t_prev);
+            const D l2v = sn[SNR * t_prev + 2];
+            fint[0] += D(0.5) * (p0 + l01.x); fint[1] += D(0.5) * (p1 + l01.y); fint[2] += D(0.5) * (c1[2] + l2v);
+          }
+        }
+        if (mus && A.contact_before_forcing) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) tq[i] += mtq[i];
+        }
       }
       // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update (FP64 accumulation)
       v[0] = fma((D)fint[0], dtim_cv, fma(v[0], c_cv, base0));
@@ -508,11 +727,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         __syncthreads();
         if (active && first && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
       }
-      D *sc = A.sk_scratch + (size_t)p * LEAN_REC * NT;
+      D *sc = A.sk_scratch + (size_t)p * SCR * NT;
 #pragma unroll
       for (int c = 0; c < 3; c++) { sc[c * NT + tid] = x[c]; sc[(3 + c) * NT + tid] = v[c]; sc[(15 + c) * NT + tid] = w[c]; }
 #pragma unroll
       for (int c = 0; c < 9; c++) sc[(6 + c) * NT + tid] = Q[c];
+      if (CONTACT) { sc[18 * NT + tid] = mus_S; sc[19 * NT + tid] = mus_C; sc[20 * NT + tid] = mus_t; }
       __threadfence();
       __syncthreads();
       if (tid == 0) { *(volatile int *)(A.sk_flag + p) = 1; }
@@ -543,6 +763,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     }
     bool bad = false;
     if (active && !redo) {
+      if (CONTACT) { to_lab(x); to_lab(v); rows_to_lab(Q); }   // (final: nothing below reads them in the internal frame)
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         st[(F_POS + c) * stride + j] = (ST)x[c];
@@ -569,6 +790,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     if (!FASTONLY && A.redo_filter && active && first) A.redo[env] = 0;
     if (active && first && !redo) {
       const bool invalid = sh_flag[r] != 0;
+      if (mus) A.muscle[(size_t)env * A.muscle_dim] = mus_t;
       if (A.model == MODEL_SOFT_PENDULUM) {
         soft_pendulum_outputs<D>(sh_t + tid, RS, n, x[0], v[0],
                                  A.action_dim > 0 ? A.action[(size_t)env * A.action_dim] : 0.0f, invalid,

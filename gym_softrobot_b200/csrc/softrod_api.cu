@@ -212,6 +212,8 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
       const double lc = lcw[2 * k], cw = exp(lc);
       lmax = fmax(lmax, fabs(lc));
       A.cwp[k][0] = (T)cw; A.cwp[k][1] = (T)(cw * lc); A.cwp[k][2] = (T)(cw * 0.5 * lc * lc);
+      double term = cw;
+      for (int i = 0; i < 6; i++) { A.cwc[k][i] = (T)term; term *= lc / (double)(i + 1); }
     }
     A.k_dt = c.dt; A.k_half_dt = 0.5 * c.dt; A.k_dt_inv_mass = c.dt / mass; A.k_inv_rest_len = 1.0 / rl;
     A.k_c_v = c.damping_constant >= 0.0 ? exp(-c.damping_constant * c.dt) : 1.0;
@@ -221,6 +223,10 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     A.lim_rot_hi = hi_word(sr::kNarrowRotQ);
     A.lim_bend_hi = hi_word(sr::kNarrowBendW2);
     A.lim_em1_hi = lmax > 0.0 ? hi_word(fmin(sr::kLeanExpZ / lmax, 1e300)) : 0x7fefffff;   // no damper: any finite stretch
+    A.lim_em1c_hi = lmax > 0.0 ? hi_word(fmin(sr::kLeanExpZc / lmax, 1e300)) : 0x7fefffff;
+    A.half_rest_vor = (T)(0.5 * rl);
+    A.mus_cd = cos(A.mus_omega * c.dt); A.mus_sd = sin(A.mus_omega * c.dt);
+    A.mus_inv_ramp = 1.0 / A.mus_ramp;   // (ramp 0: inf, and fmin(1, t * inf) = 1 like the reference's t / 0)
   }
 }
 
@@ -294,7 +300,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 // Lean FP64 path: grid and stream-K schedule.  With more items than resident CTA slots the grid is the slot
 // count and every slot gets the same number of item-substeps (rod_kernel_lean.cuh); partial items travel through
 // sk_scratch.  The fallback launch (redo_filter) visits flagged envs only and keeps one CTA per item.
-template <typename T, int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT = false> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / (A.n_elem + 1);
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "rod does not fit one CTA of the lean kernel");
   const int items = (A.n_env + rods_per_cta - 1) / rods_per_cta;
@@ -302,10 +308,10 @@ template <typename T, int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_h
     cudaDeviceProp prop;
     SR_CUDA(cudaGetDeviceProperties(&prop, h->cfg.device));
     // both variants of a pair are sized alike (same launch bounds); take the smaller answer to be safe
-    const int a = sr::lean_ctas_per_sm<T, NT, MINB, true>(), b = sr::lean_ctas_per_sm<T, NT, MINB, false>();
+    const int a = sr::lean_ctas_per_sm<T, NT, MINB, true, CONTACT>(), b = sr::lean_ctas_per_sm<T, NT, MINB, false, CONTACT>();
     h->sk_slots = prop.multiProcessorCount * (a < b ? a : b);
     if (h->sk_slots < 1) return fail(SR_E_CUDA, "lean kernel: occupancy query failed");
-    SR_CUDA(cudaMalloc(&h->sk_scratch, (size_t)h->sk_slots * 18 * NT * sizeof(double)));
+    SR_CUDA(cudaMalloc(&h->sk_scratch, (size_t)h->sk_slots * sr::LEAN_SCR_CONTACT * NT * sizeof(double)));
     SR_CUDA(cudaMalloc(&h->sk_flag, (size_t)h->sk_slots * sizeof(int)));
     SR_CUDA(cudaMemset(h->sk_flag, 0, (size_t)h->sk_slots * sizeof(int)));
   }
@@ -314,20 +320,34 @@ template <typename T, int NT, int MINB, bool FASTONLY> int launch_lean_impl(sr_h
   A.sk_scratch = (double *)h->sk_scratch; A.sk_flag = h->sk_flag;
   A.sk_rodsync = rodsync_setting();
   const int grid = A.sk_split ? h->sk_slots : items;
-  cudaError_t e = sr::launch_lean_kernel<T, NT, MINB, FASTONLY>(A, grid, s);
+  cudaError_t e = sr::launch_lean_kernel<T, NT, MINB, FASTONLY, CONTACT>(A, grid, s);
   h->launches++;
   if (e != cudaSuccess) return cuda_fail("rod_lean_kernel launch", e);
   return SR_OK;
 }
 
-template <typename T, int NT, int MINB> int launch_lean_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB, bool CONTACT = false> int launch_lean_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_fast_pair(h, A, s)) {
     // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
-    int rc = launch_lean_impl<T, NT, MINB, true>(h, A, s);
+    int rc = launch_lean_impl<T, NT, MINB, true, CONTACT>(h, A, s);
     if (rc != SR_OK) return rc;
     A.redo_filter = 1;
   }
-  return launch_lean_impl<T, NT, MINB, false>(h, A, s);
+  return launch_lean_impl<T, NT, MINB, false, CONTACT>(h, A, s);
+}
+
+// single rod on the frictional plane / with rest-curvature actuation / travelling-wave muscle: the lean kernel's contact
+// variant (FP64).  Everything else the generic kernel offers (spline forcing, suckers, external loads, tapered rods,
+// assemblies, the moving base, the Laplace filter, the base point force) stays with rod_kernel_packed.cuh.
+template <typename T> bool is_lean_contact_config(const sr::RodArgs<T> &A) {
+  if (!std::is_same<T, double>::value) return false;
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("SOFTROD_LEAN_CONTACT"); off = (e && atoi(e) == 0) ? 1 : 0; }   // =0: generic kernel (A/B)
+  if (off) return false;
+  if (A.n_rod > 1 || A.has_head || A.spline_mask || A.laplace_order > 0 || A.sucker || A.ext_force || A.ext_couple || A.elem_tab ||
+      A.point_force) return false;
+  if (A.bc_kind != sr::BC_FREE && A.bc_kind != sr::BC_ONE_END_FIXED) return false;
+  return A.contact_on || A.rest_kappa || A.muscle_on;
 }
 
 template <typename T> bool is_lean_config(const sr::RodArgs<T> &A) {
@@ -447,6 +467,18 @@ template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaS
     if (A.elem_tab) {
       const int group = h->n_rod * (h->cfg.n_elem + 1) + (h->cfg.has_head ? 1 : 0);
       return group <= 384 ? launch_tapered<384>(h, A, s) : launch_tapered<1024>(h, A, s);
+    }
+  }
+  if constexpr (std::is_same<T, double>::value) {
+    if (is_lean_contact_config(A)) {
+      switch (lean_threads_setting(h->cfg.n_elem)) {
+        case 1024: return launch_lean_pair<T, 1024, 1, true>(h, A, s);
+        case 768: return launch_lean_pair<T, 768, 1, true>(h, A, s);
+        case 544: return launch_lean_pair<T, 544, 1, true>(h, A, s);
+        case 512: return launch_lean_pair<T, 512, 1, true>(h, A, s);
+        case 384: return launch_lean_pair<T, 384, 1, true>(h, A, s);
+        default: return launch_lean_pair<T, 256, 2, true>(h, A, s);
+      }
     }
   }
   if (is_lean_config(A)) {

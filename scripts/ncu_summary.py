@@ -4,8 +4,15 @@ rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
+min_ms = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0      # skip launches shorter than this (resets, zero-substep launches)
+seen = set()
 for vals in rows[2:]:
     d = {h: (u, v) for h, u, v in zip(hdr, units, vals)}
+    dur = d.get("gpu__time_duration.sum", ("ms", "0"))
+    dur_ms = float(dur[1].replace(",", "")) * {"us": 1e-3, "ms": 1.0, "s": 1e3, "ns": 1e-6}.get(dur[0], 1.0)
+    if dur_ms < min_ms or (min_ms > 0 and d.get("Kernel Name", ("", "?"))[1] in seen):
+        continue
+    seen.add(d.get("Kernel Name", ("", "?"))[1])
     print("kernel:", d.get("Kernel Name", ("", "?"))[1], "grid", d.get("launch__grid_size", ("", "?"))[1], "block", d.get("launch__block_size", ("", "?"))[1])
     keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__waves_per_multiprocessor",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg", "smsp__inst_executed.sum",
