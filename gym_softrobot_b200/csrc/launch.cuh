@@ -13,9 +13,9 @@ cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid
 
 constexpr int LEAN_SCR_CONTACT = 21;   // rows of a stream-K slot's hand-over scratch (contact variant: 18 + the travelling wave's sin, cos, time)
 // lean kernel (rod_kernel_lean.cuh; T = storage type: double = FP64, float = mixed precision); grid / split schedule in A.sk_*
-template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT = false> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s);
+template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s);
 // resident CTAs per SM of that instantiation on the current device (sizes the stream-K grid)
-template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT = false> int lean_ctas_per_sm();
+template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> int lean_ctas_per_sm();
 
 // warp-per-rod kernel, faithful (libm, reference operation order) math: the parity build
 template <typename T, int EPL> cudaError_t launch_warp_faithful(const RodArgs<T> &A, int grid, cudaStream_t s);

@@ -104,11 +104,12 @@ __device__ __forceinline__ bool out_of_range(float x, int, float limf) { return 
 // (flat_env.py:310-311 style actuation), RodPlaneContactWithAnisotropicFriction (two more exchanges and
 // per-rod barriers per substep), the MuscleTorques travelling wave of ContinuumSnake-v0, and the internal frame whose
 // z axis is the plane normal (see rod_kernel_packed.cuh).  OctoArmSingle-v0, ContinuumSnake-v0 and BASELINE config 5.
-template <typename ST, int NT, int MINB, bool FASTONLY, bool CONTACT = false>
+template <typename ST, int NT, int MINB, bool FASTONLY, int CVAR = 0>
 __global__ void __launch_bounds__(NT, MINB)
 rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   using D = double;
   constexpr bool MIXED = sizeof(ST) == 4;
+  constexpr bool CONTACT = CVAR != 0, MUS = CVAR == 2;   // CVAR: 0 plain rod, 1 contact variant, 2 contact variant + travelling-wave muscle
   static_assert(!CONTACT || !MIXED, "the contact variant is FP64 only");
   constexpr int SCR = CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
   using F = typename std::conditional<MIXED, float, double>::type;
@@ -224,7 +225,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     const ST *bc = A.bc + (size_t)(active ? env : 0) * BC_DIM;
     // travelling-wave muscle torque (contact variant): time, (sin, cos) of the wave's common phase w t + phi, and this
     // element's two amplitude combinations (below)
-    const bool mus = CONTACT && A.muscle_on;
+    const bool mus = MUS && A.muscle_on;
     D mus_t = D(0), mus_S = D(0), mus_C = D(1);
     if (s_begin > 0) {
       // continue an item the previous slot started: wait for its hand-over, then take the registers back
@@ -357,9 +358,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     if (s_begin == 0 && K > 0) kinematic(c_half_dt, D(1e-14));
 
     bool check_trace = true;   // first substep of the segment: rule out a state that starts beyond 90 degrees of bend
-    auto substep = [&](auto last_tag) {
+    auto substep = [&](auto last_tag, int s_now) {
       constexpr bool last = decltype(last_tag)::value;
       D mtq[3] = {D(0), D(0), D(0)};
+      // zero, but not provably so (a launch never has 2^30 substeps): see the bend polynomial below
+      const int oz = CONTACT ? (s_now >> 30) : 0;
+      const RodArgs<ST> &Z = (&A)[oz];   // the kernel parameters through that index: constant-bank loads that stay inside the loop
       if constexpr (CONTACT) {
         if (mus) {
           mus_t += (double)c_half_dt;   // time of the force evaluation: after the first half step
@@ -471,7 +475,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       if (FASTONLY) dom_bad = dom_bad || bend_out;
       F fs;
       {
-        const auto &c = A.bendw;   // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved
+        // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved.  (Contact
+        // variant: indexed through a register the compiler cannot see through, so that the ten coefficients are
+        // constant-bank loads inside the loop instead of hoisted, spilled and reloaded registers.)
+        const F *c = Z.bendw;
         const F z = w2 * w2;
         F pe = fma(c[8], z, c[6]), po = fma(c[9], z, c[7]);
         pe = fma(pe, z, c[4]); po = fma(po, z, c[5]);
@@ -534,9 +541,9 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
         if (FASTONLY || !out) {
           if constexpr (CONTACT) {   // harder dampers, larger stretches: degree 5, |z| <= kLeanExpZc
-            F p0 = fma(A.cwc[0][5], em1, A.cwc[0][4]), p2 = fma(A.cwc[1][5], em1, A.cwc[1][4]);
+            F p0 = fma(Z.cwc[0][5], em1, Z.cwc[0][4]), p2 = fma(Z.cwc[1][5], em1, Z.cwc[1][4]);
 #pragma unroll
-            for (int k = 3; k >= 0; k--) { p0 = fma(p0, em1, A.cwc[0][k]); p2 = fma(p2, em1, A.cwc[1][k]); }
+            for (int k = 3; k >= 0; k--) { p0 = fma(p0, em1, Z.cwc[0][k]); p2 = fma(p2, em1, Z.cwc[1][k]); }
             cw0 = p0; cw2 = p2;
           } else {
             cw0 = fma(fma(A.cwp[0][2], em1, A.cwp[0][1]), em1, A.cwp[0][0]);
@@ -606,82 +613,86 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
             for (int i = 0; i < 3; i++) {
               const D f1 = sN[i] - sfl[i];                       // internal force on node j+1 (node j's is fint)
               // external loads so far: gravity (a0 hm0 + a1 hm1 = 1 for every element: one whole nodal weight)
-              const D gi = A.contact_before_forcing ? D(0) : (D)A.gm[i];
+              const D gi = A.contact_before_forcing ? D(0) : (D)Z.gm[i];
               etf[i] = fma(a1, f1, fma(a0, fint[i], gi));
               evel[i] = fma(w1, vN[i], w0 * v[i]);
               t[i] = dx[i] * ilg;
             }
           }
-          const D rad2 = A.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
+          const D rad2 = Z.vol_over_pi * ilg, inv_rad = rsqrt_nr(rad2), rad = rad2 * inv_rad;   // sqrt(V / (pi l))
           const D fn = etf[2], vn = evel[2];
-          const D gap = (fma(D(0.5), dx[2], x[2]) - A.plane_z0) - rad, pen = fmin(gap, D(0));
-          const bool nocontact = !elem_ok || (gap > A.surface_tol);
-          const D resp_mag = (nocontact || fn > D(0)) ? D(0) : fabs(fn);
+          // sign tests and clamps of non-negative quantities run on the integer pipe (high words / bit patterns), not DSETP
+          const D gap = (fma(D(0.5), dx[2], x[2]) - Z.plane_z0) - rad, pen = (__double2hiint(gap) < 0) ? gap : D(0);   // min(gap, 0)
+          const bool nocontact = !elem_ok || (gap > Z.surface_tol);
+          const D fn_neg = (__double2hiint(fn) < 0) ? -fn : D(0);        // max(-fn, 0): the plane only pushes
+          // no contact: zero response, and every friction term below is bounded by or proportional to it
+          const D resp_mag = nocontact ? D(0) : fn_neg;
           D c1[3];
-          c1[2] = nocontact ? D(0) : ((fn > D(0)) ? D(0) : -fn) - A.contact_k * pen - A.contact_nu * vn;
+          c1[2] = nocontact ? D(0) : fma(-Z.contact_nu, vn, fma(-Z.contact_k, pen, fn_neg));
           // axial direction = the tangent's projection on the plane, normalised with the reference's guard
           // 1 / (|tp| + 1e-14) (to first order in 1e-14 / |tp|); rolling direction = axial x normal
           const D tp2 = fma(t[1], t[1], t[0] * t[0]);
           const D rtp = rsqrt_nr(tp2 + D(1e-300));   // (a rod standing on end: tp = 0, axial direction 0)
           const D inv_tp = fma(D(-1e-14) * rtp, rtp, rtp);
           const D ax0 = t[0] * inv_tp, ax1 = t[1] * inv_tp, rl0 = ax1, rl1 = -ax0;
-          auto slip_fn = [&](D a) {   // find_slipping_elements on |v| (|axial| = |rolling| = 1 - 1e-14 / |tp|: taken as 1)
-            return (a > A.slip_tol) ? fabs(D(1) - fmin(D(1), a * A.inv_slip_tol - D(1))) : D(1);
+          // find_slipping_elements on a = |v| (|axial| = |rolling| = 1 - 1e-14 / |tp|: taken as 1):
+          // a <= tol: 1;  a > tol: |1 - min(1, a / tol - 1)|  =  clamp(2 - a / tol, 0, 1) in both cases
+          auto slip_fn = [&](D a) {
+            const D u = fma(-a, Z.inv_slip_tol, D(2.0));
+            const int hu = __double2hiint(u);
+            return (hu < 0) ? D(0) : (hu >= 0x3ff00000) ? D(1) : u;
           };
+          // min(a, b) for a, b >= 0: doubles of one sign order like their bit patterns
+          auto min_pos = [](D a, D b) { return (__double_as_longlong(a) < __double_as_longlong(b)) ? a : b; };
           // sign(a) with sign(0) = +1: every use below multiplies a factor that vanishes with a
           auto sgn1 = [](D a) { return __hiloint2double((__double2hiint(a) & 0x80000000) | 0x3ff00000, 0); };
           const D vax = fma(evel[1], ax1, evel[0] * ax0);
-          const D kmu = (__double2hiint(vax) < 0) ? (D)A.kin_mu[1] : (D)A.kin_mu[0];
+          const D kmu = (__double2hiint(vax) < 0) ? (D)Z.kin_mu[1] : (D)Z.kin_mu[0];
           const D slipa = slip_fn(fabs(vax));
-          // velocity of the contact point relative to the axis: Q^T (w x Q arm), arm = -rad z
-          D qa[3], wq[3];
-#pragma unroll
-          for (int i = 0; i < 3; i++) qa[i] = -(Q[3 * i + 2] * rad);
-          cross3(w, qa, wq);
-          const D rv0 = fma(Q[6], wq[2], fma(Q[3], wq[1], Q[0] * wq[0])), rv1 = fma(Q[7], wq[2], fma(Q[4], wq[1], Q[1] * wq[0]));
+          // velocity of the contact point relative to the axis: Q^T (w x Q arm) = (Q^T w) x arm, arm = -rad z, i.e.
+          // (-rad W_y, rad W_x, 0) with W = Q^T w the angular velocity in the plane's frame
+          const D W0 = fma(Q[6], w[2], fma(Q[3], w[1], Q[0] * w[0])), W1 = fma(Q[7], w[2], fma(Q[4], w[1], Q[1] * w[0]));
+          const D rv0 = -(rad * W1), rv1 = rad * W0;
           const D smag = fma(evel[1] + rv1, rl1, (evel[0] + rv0) * rl0);
           const D slipr = slip_fn(fabs(smag));
           const D ut0 = fma(smag, rl0, vax * ax0), ut1 = fma(smag, rl1, vax * ax1);
           const D ug0 = ut0 + D(1e-14), ug1 = ut1 + D(1e-14);
           const D iun = rsqrt_nr(fma(ug1, ug1, fma(ug0, ug0, D(1e-28))));
-          const D uax = fma(ut1, ax1, ut0 * ax0) * iun, url = fma(ut1, rl1, ut0 * rl0) * iun;
-          const D ka = nocontact ? D(0) : -((D(1) - slipa) * kmu * resp_mag * uax);
-          const D kr = nocontact ? D(0) : -((D(1) - slipr) * A.kin_mu[2] * resp_mag * url);
+          // u . axial = vax |axial|^2, u . rolling = smag |rolling|^2, and |axial|^2 = |rolling|^2 = 1 - 2e-14 / |tp|: taken as 1
+          const D uax = vax * iun, url = smag * iun;
+          const D ka = -((D(1) - slipa) * kmu * resp_mag * uax);
+          const D kr = -((D(1) - slipr) * Z.kin_mu[2] * resp_mag * url);
           D fr0 = kr * rl0, fr1 = kr * rl1;
           c1[0] = fma(ka, ax0, fr0); c1[1] = fma(ka, ax1, fr1);
-          // couple of the rolling friction: Q (arm x F) = Q (rad F_y, -rad F_x, 0)
+          // couple of the rolling friction: Q (arm x F) = Q (rad F_y, -rad F_x, 0); kept in the plane's frame until the end
           D cr0 = rad * fr1, cr1 = -(rad * fr0);
-          D text[3];
-#pragma unroll
-          for (int i = 0; i < 3; i++) text[i] = fma(Q[3 * i + 1], cr1, Q[3 * i] * cr0);
           *reinterpret_cast<double2 *>(rec + LEAN_REC * tid + 16) = make_double2(c1[0], c1[1]);
           rod_sync();
           // stage 2: static friction (in-plane components only)
           D e2[2];
           {
+            // stage-1 response on nodes j, j+1: (left + own) / 2, (own + right) / 2, weighted a0, a1 like the loads above
+            // (the tip thread's own stage-1 load is zero: no select for the last element's right neighbour)
             const double2 cl = *reinterpret_cast<const double2 *>(rec + LEAN_REC * t_prev + 16);
             const double2 cr = *reinterpret_cast<const double2 *>(rec + LEAN_REC * t_next + 16);
-            const D nl[2] = {cl.x, cl.y}, nr[2] = {cr.x, cr.y};
-#pragma unroll
-            for (int i = 0; i < 2; i++) {
-              const D nc0 = D(0.5) * (nl[i] + c1[i]), nc1 = D(0.5) * (c1[i] + (end1 ? D(0) : nr[i]));   // stage-1 response on nodes j, j+1
-              e2[i] = fma(a1, nc1, fma(a0, nc0, etf[i]));
-            }
+            const D b0 = D(0.5) * a0, b1 = D(0.5) * a1, bm = b0 + b1;
+            e2[0] = fma(b1, cr.x, fma(b0, cl.x, fma(bm, c1[0], etf[0])));
+            e2[1] = fma(b1, cr.y, fma(b0, cl.y, fma(bm, c1[1], etf[1])));
           }
           const D fax = fma(e2[1], ax1, e2[0] * ax0);
-          const D smu = (__double2hiint(fax) < 0) ? (D)A.stat_mu[1] : (D)A.stat_mu[0];
-          const D sa = nocontact ? D(0) : -(fmin(fabs(fax), slipa * smu * resp_mag) * sgn1(fax));
-          const D ts0 = tq[0] + text[0], ts1 = tq[1] + text[1], ts2 = tq[2] + text[2];
-          const D tt0 = fma(Q[6], ts2, fma(Q[3], ts1, Q[0] * ts0)), tt1 = fma(Q[7], ts2, fma(Q[4], ts1, Q[1] * ts0));
+          const D smu = (__double2hiint(fax) < 0) ? (D)Z.stat_mu[1] : (D)Z.stat_mu[0];
+          const D sa = -(min_pos(fabs(fax), slipa * smu * resp_mag) * sgn1(fax));
+          // in-plane components of the couples so far, Q^T (tq + Q cr) = Q^T tq + cr
+          const D tt0 = fma(Q[6], tq[2], fma(Q[3], tq[1], fma(Q[0], tq[0], cr0))), tt1 = fma(Q[7], tq[2], fma(Q[4], tq[1], fma(Q[1], tq[0], cr1)));
           const D noslip = -((rad * fma(e2[1], rl1, e2[0] * rl0) - D(2) * fma(tt1, ax1, tt0 * ax0)) * (D(1.0 / 3.0) * inv_rad));
-          const D sr_ = nocontact ? D(0) : fmin(fabs(noslip), slipr * A.stat_mu[2] * resp_mag) * sgn1(noslip);
+          const D sr_ = min_pos(fabs(noslip), slipr * Z.stat_mu[2] * resp_mag) * sgn1(noslip);
           fr0 = sr_ * rl0; fr1 = sr_ * rl1;
           const D p0 = c1[0] + fma(sa, ax0, fr0), p1 = c1[1] + fma(sa, ax1, fr1);
           *reinterpret_cast<double2 *>(sn + SNR * tid) = make_double2(p0, p1);
           sn[SNR * tid + 2] = c1[2];
-          cr0 = rad * fr1; cr1 = -(rad * fr0);
+          cr0 = fma(rad, fr1, cr0); cr1 = fma(-rad, fr0, cr1);   // both stages' rolling couples
 #pragma unroll
-          for (int i = 0; i < 3; i++) tq[i] += text[i] + fma(Q[3 * i + 1], cr1, Q[3 * i] * cr0);
+          for (int i = 0; i < 3; i++) tq[i] = fma(Q[3 * i + 1], cr1, fma(Q[3 * i], cr0, tq[i]));
           rod_sync();
           {   // node j collects half of the plane's load on elements j-1 and j
             const double2 l01 = *reinterpret_cast<const double2 *>(sn + SNR * t_prev);
@@ -714,8 +725,8 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     // body, so that the loop carries neither the selects nor the branch
     const int s_loop_end = (s_end == K) ? K - 1 : s_end;
 #pragma unroll 1
-    for (int s = s_begin; s < s_loop_end; s++) substep(std::false_type{});
-    if (s_end == K && s_begin < K) substep(std::true_type{});
+    for (int s = s_begin; s < s_loop_end; s++) substep(std::false_type{}, s);
+    if (s_end == K && s_begin < K) substep(std::true_type{}, K - 1);
 
     __syncthreads();   // all reads of the exchange buffers are done
     if (s_end < K) {

@@ -300,7 +300,7 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 // Lean FP64 path: grid and stream-K schedule.  With more items than resident CTA slots the grid is the slot
 // count and every slot gets the same number of item-substeps (rod_kernel_lean.cuh); partial items travel through
 // sk_scratch.  The fallback launch (redo_filter) visits flagged envs only and keeps one CTA per item.
-template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT = false> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   const int rods_per_cta = NT / (A.n_elem + 1);
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "rod does not fit one CTA of the lean kernel");
   const int items = (A.n_env + rods_per_cta - 1) / rods_per_cta;
@@ -326,7 +326,7 @@ template <typename T, int NT, int MINB, bool FASTONLY, bool CONTACT = false> int
   return SR_OK;
 }
 
-template <typename T, int NT, int MINB, bool CONTACT = false> int launch_lean_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
+template <typename T, int NT, int MINB, int CONTACT = 0> int launch_lean_pair(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
   if (use_fast_pair(h, A, s)) {
     // fast-only kernel, then the safe one over the envs it flagged (an empty launch in the normal case)
     int rc = launch_lean_impl<T, NT, MINB, true, CONTACT>(h, A, s);
@@ -471,14 +471,17 @@ template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaS
   }
   if constexpr (std::is_same<T, double>::value) {
     if (is_lean_contact_config(A)) {
-      switch (lean_threads_setting(h->cfg.n_elem)) {
-        case 1024: return launch_lean_pair<T, 1024, 1, true>(h, A, s);
-        case 768: return launch_lean_pair<T, 768, 1, true>(h, A, s);
-        case 544: return launch_lean_pair<T, 544, 1, true>(h, A, s);
-        case 512: return launch_lean_pair<T, 512, 1, true>(h, A, s);
-        case 384: return launch_lean_pair<T, 384, 1, true>(h, A, s);
-        default: return launch_lean_pair<T, 256, 2, true>(h, A, s);
+      const int nt = lean_threads_setting(h->cfg.n_elem);
+#define SR_LEANC(NT_, MB_) (A.muscle_on ? launch_lean_pair<T, NT_, MB_, 2>(h, A, s) : launch_lean_pair<T, NT_, MB_, 1>(h, A, s))
+      switch (nt) {
+        case 1024: return SR_LEANC(1024, 1);
+        case 768: return SR_LEANC(768, 1);
+        case 544: return SR_LEANC(544, 1);
+        case 512: return SR_LEANC(512, 1);
+        case 384: return SR_LEANC(384, 1);
+        default: return SR_LEANC(256, 2);
       }
+#undef SR_LEANC
     }
   }
   if (is_lean_config(A)) {
