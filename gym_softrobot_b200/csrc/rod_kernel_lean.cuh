@@ -78,7 +78,8 @@ __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], con
 }
 
 constexpr int LEAN_REC = 18;        // exchange record per thread (doubles), 144-byte stride: conflict-free LDS.128
-constexpr int lean_smem_words(int nt) { return (LEAN_REC + 6) * (nt + 2); }
+constexpr int LEAN_JREC = 10;      // assemblies: joint record of an arm's first thread {reaction force, couple on the head, couple on element 0, -}
+constexpr int lean_smem_words(int nt, bool multi = false) { return (LEAN_REC + 6 + (multi ? LEAN_JREC : 0)) * (nt + 2); }
 
 // float overloads of the reciprocal helpers for the FP32 force evaluation of the mixed mode
 __device__ __forceinline__ bool out_of_range(double x, int lim_hi, float) { return hi_abs(x) > lim_hi; }
@@ -109,7 +110,9 @@ __global__ void __launch_bounds__(NT, MINB)
 rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   using D = double;
   constexpr bool MIXED = sizeof(ST) == 4;
-  constexpr bool CONTACT = CVAR != 0, MUS = CVAR == 2;   // CVAR: 0 plain rod, 1 contact variant, 2 contact variant + travelling-wave muscle
+  // CVAR: 0 plain rod, 1 contact variant, 2 contact variant + travelling-wave muscle, 3 contact variant for assemblies
+  // (several rods + one rigid head thread per env, FixedJoint2Rigid joints, BodyBoundaryCondition on the head)
+  constexpr bool CONTACT = CVAR != 0, MUS = CVAR == 2, MULTI = CVAR == 3;
   static_assert(!CONTACT || !MIXED, "the contact variant is FP64 only");
   constexpr int SCR = CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
   using F = typename std::conditional<MIXED, float, double>::type;
@@ -122,10 +125,19 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 
   const int tid = threadIdx.x;
   const int n = A.n_elem, stride = A.stride, tpr = n + 1;
-  const int rods_per_cta = A.sk_rods_per_cta;
-  const int r = tid / tpr, j = tid - r * tpr;
+  // env group = the threads of one env: a rod, or (assemblies) n_rod rods of tpr threads + one head thread
+  const int n_rod = MULTI ? A.n_rod : 1, has_head = MULTI ? A.has_head : 0;
+  const int G = n_rod * tpr + has_head;
+  const int rods_per_cta = A.sk_rods_per_cta;       // env groups per CTA
+  const int r = tid / G, u_grp = tid - r * G;
+  const bool is_head = MULTI && has_head && (u_grp == G - 1);
+  const int arm = (MULTI && !is_head) ? u_grp / tpr : 0;
+  const int j = is_head ? 0 : u_grp - arm * tpr;
   const bool in_cta = r < rods_per_cta;
-  const bool first = (j == 0);
+  const bool first = (j == 0) && !is_head;          // first thread of a rod
+  const bool lead = first && arm == 0;              // one thread per env: env-level flags and outputs
+  const int t_head = r * G + G - 1;                 // where this env's head publishes its state
+  D *sj = reinterpret_cast<D *>(sn + 6 * (NT + 2)); // assemblies: joint records (LEAN_JREC doubles per thread slot)
   if (tid < SNR) sn[SNR * NT + tid] = F(0);
   if (CONTACT && tid < 2) rec[LEAN_REC * NT + 16 + tid] = D(0);   // stage-1 contact load "left of element 0"
   __syncthreads();   // (the per-rod barriers below do not order this store against the other rods' reads)
@@ -135,11 +147,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   // the next takes part in both, in rod order) instead of CTA-wide: rods then drift apart and fill each other's
   // pipeline bubbles.  Needs tpr >= 32 (a warp touches at most two rods) and <= 15 rods per CTA (barrier ids 1..15).
   int bar_id0 = 0, bar_cnt0 = 0, bar_id1 = 0, bar_cnt1 = 0;
-  const bool rod_barriers = A.sk_rodsync && tpr >= 32 && rods_per_cta >= 2 && rods_per_cta <= 15;
+  const bool rod_barriers = A.sk_rodsync && G >= 32 && rods_per_cta >= 2 && rods_per_cta <= 15;
   if (rod_barriers) {
     const int wp = tid >> 5;
     for (int rr = 0; rr < rods_per_cta; rr++) {
-      const int wa = (rr * tpr) >> 5, wb = (rr * tpr + tpr - 1) >> 5;
+      const int wa = (rr * G) >> 5, wb = (rr * G + G - 1) >> 5;
       if (wp >= wa && wp <= wb) {
         if (bar_cnt0 == 0) { bar_id0 = rr + 1; bar_cnt0 = 32 * (wb - wa + 1); }
         else { bar_id1 = rr + 1; bar_cnt1 = 32 * (wb - wa + 1); }
@@ -212,7 +224,9 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       selected = in_grid && A.redo[env] != 0;
       if (!__syncthreads_or(selected)) continue;
     }
-    const bool active = in_grid && selected;
+    const bool live = in_grid && selected;             // a thread of an env that is being stepped
+    const bool active = live && !is_head;              // ... that owns a node / element of a rod
+    const int rod = env * n_rod + arm;                 // global rod slot in the state arrays
     bool dom_bad = false;
     const bool elem_ok = active && j < n, vor_ok = active && j < n - 1;
     const int t_next = elem_ok ? tid + 1 : tid;
@@ -221,8 +235,9 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 
     D x[3] = {D(0), D(0), D(0)}, v[3] = {D(0), D(0), D(0)}, w[3] = {D(0), D(0), D(0)};
     D Q[9] = {D(1), D(0), D(0), D(0), D(1), D(0), D(0), D(0), D(1)};
-    ST *st = A.state + (size_t)(active ? env : 0) * N_FIELDS * stride;
-    const ST *bc = A.bc + (size_t)(active ? env : 0) * BC_DIM;
+    ST *st = A.state + (size_t)(active ? rod : 0) * N_FIELDS * stride;
+    const ST *bc = A.bc + (size_t)(active ? rod : 0) * BC_DIM;
+    ST *hd = (MULTI && is_head && live) ? A.head + (size_t)env * HEAD_DIM : nullptr;   // the rigid head's state
     // travelling-wave muscle torque (contact variant): time, (sin, cos) of the wave's common phase w t + phi, and this
     // element's two amplitude combinations (below)
     const bool mus = MUS && A.muscle_on;
@@ -254,6 +269,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 #pragma unroll
         for (int c = 0; c < 9; c++) Q[c] = (D)st[(F_DIR + c) * stride + j];  // slot n holds I
         if (CONTACT) { to_int(x); to_int(v); rows_to_int(Q); }
+      }
+      if (MULTI && hd) {     // (assemblies stand on a z-normal plane: sr_create checks, no rotation here)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { x[c] = (D)hd[c]; v[c] = (D)hd[3 + c]; w[c] = (D)hd[15 + c]; }
+#pragma unroll
+        for (int c = 0; c < 9; c++) Q[c] = (D)hd[6 + c];
       }
       if (MIXED) {
         // FP64 node positions whose differences are the stored FP32 edge vectors exactly: node 0 (after the BC's
@@ -307,7 +328,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     if constexpr (CONTACT) {
       if (A.rest_kappa && vor_ok) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) rk[c] = (D)A.rest_kappa[((size_t)env * 3 + c) * stride + j];
+        for (int c = 0; c < 3; c++) rk[c] = (D)A.rest_kappa[((size_t)rod * 3 + c) * stride + j];
       }
       if (mus && active) {
         // MuscleTorques (continuum_snake.py:186-198): element k gets Q_k d (m_k [k >= 1] - m_{k+1} [k <= n-2]),
@@ -355,7 +376,19 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       else rotate_directors_ref<D>(a0, a1, a2, Q);
     };
 
-    if (s_begin == 0 && K > 0) kinematic(c_half_dt, D(1e-14));
+    // BodyBoundaryCondition on the head (utils/custom_elastica/constraint.py:43-58): z pinned, d3 = z, d1 / d2 renormalised in-plane
+    auto head_constrain_values = [&]() {
+      if (MULTI && hd) {
+        x[2] = (D)hd[18];
+        Q[6] = D(0); Q[7] = D(0); Q[8] = D(1);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const D il = rsqrt_nr(Q[3 * i] * Q[3 * i] + Q[3 * i + 1] * Q[3 * i + 1]);   // rows stay ~unit: never 0
+          Q[3 * i] *= il; Q[3 * i + 1] *= il; Q[3 * i + 2] = D(0);
+        }
+      }
+    };
+    if (s_begin == 0 && K > 0) { kinematic(c_half_dt, D(1e-14)); head_constrain_values(); }
 
     bool check_trace = true;   // first substep of the segment: rule out a state that starts beyond 90 degrees of bend
     auto substep = [&](auto last_tag, int s_now) {
@@ -442,6 +475,57 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         for (int i = 0; i < 3; i++) sfl[i] = (F)sd[i] * inv_e_s;
       }
 
+      if constexpr (MULTI) {
+        // FixedJoint2Rigid(head, -1, arm, 0) (utils/custom_elastica/joint.py:48-123 forces, :125-219 torques): spring
+        // + normal damping between the head's rim point and node 0, restoring force on node 1 towards the mounting
+        // direction.  Joint a of an env is computed by the env's a-th thread (not by arm a's own first thread): the
+        // joints of an env then share one warp's instructions instead of costing every warp that holds the start of an
+        // arm the whole block.  Inputs come from the published records; the result {reaction on the head, couple on
+        // the head, couple on element 0} goes to the joint record of arm a's first thread, which re-reads its share
+        // after the barrier, as the head does.
+        if (live && u_grp < n_rod && has_head) {
+          const int ta = r * G + u_grp * tpr;                    // arm u_grp's first thread
+          D hx[3], hv[3], d2[3], Qh[9], ax_[3], av[3], aQ[9], adx[3];
+          {
+            const double2 *qh = reinterpret_cast<const double2 *>(rec + LEAN_REC * t_head);
+            const double2 h0 = qh[0], h1 = qh[1], h2 = qh[2], h3 = qh[3], h4 = qh[4], h5 = qh[5], h6 = qh[6];
+            hx[0] = h0.x; hx[1] = h0.y; hx[2] = h1.x; hv[0] = h1.y; hv[1] = h2.x; hv[2] = h2.y;
+            Qh[0] = h3.x; Qh[1] = h3.y; Qh[2] = h4.x; Qh[3] = h4.y; Qh[4] = h5.x; Qh[5] = h5.y; Qh[6] = h6.x; Qh[7] = h6.y;
+            Qh[8] = rec[LEAN_REC * t_head + 14];
+            d2[0] = Qh[3]; d2[1] = Qh[4]; d2[2] = Qh[5];
+            const double2 *qa = reinterpret_cast<const double2 *>(rec + LEAN_REC * ta);
+            const double2 a0 = qa[0], a1 = qa[1], a2 = qa[2], a3 = qa[3], a4 = qa[4], a5 = qa[5], a6 = qa[6];
+            ax_[0] = a0.x; ax_[1] = a0.y; ax_[2] = a1.x; av[0] = a1.y; av[1] = a2.x; av[2] = a2.y;
+            aQ[0] = a3.x; aQ[1] = a3.y; aQ[2] = a4.x; aQ[3] = a4.y; aQ[4] = a5.x; aQ[5] = a5.y; aQ[6] = a6.x; aQ[7] = a6.y;
+            aQ[8] = rec[LEAN_REC * ta + 14];
+            const double2 b0 = *reinterpret_cast<const double2 *>(rec + LEAN_REC * (ta + 1));
+            adx[0] = b0.x - ax_[0]; adx[1] = b0.y - ax_[1]; adx[2] = rec[LEAN_REC * (ta + 1) + 2] - ax_[2];
+          }
+          const D cs = (D)A.joint_cs[u_grp][0], sn_ = (D)A.joint_cs[u_grp][1];
+          const D dir[3] = {-(cs * d2[0] - sn_ * d2[1]), -(sn_ * d2[0] + cs * d2[1]), -d2[2]};   // -Rz(angle) d2
+          const D anchor[3] = {hx[0] + A.joint_radius * dir[0], hx[1] + A.joint_radius * dir[1], D(0) + A.joint_radius * dir[2]};
+          const D dd[3] = {ax_[0] - anchor[0], ax_[1] - anchor[1], ax_[2] - anchor[2]};
+          const D dist2 = dot3(dd, dd);
+          const D inv = (dist2 <= D(4.930380657631324e-24)) ? D(0) : rsqrt_nr(dist2);   // 1 / dist; the reference's guard dist <= 1e4 eps (discards rsqrt(0))
+          const D nh[3] = {dd[0] * inv, dd[1] * inv, dd[2] * inv};
+          const D rvn = (av[0] - hv[0]) * nh[0] + (av[1] - hv[1]) * nh[1] + (av[2] - hv[2]) * nh[2];
+          D cf[3], fd[3], tauj[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            cf[c] = A.joint_k * dd[c] - A.joint_nu * (rvn * nh[c]);
+            const D tgt = anchor[c] + A.rest_len * dir[c];
+            fd[c] = -A.joint_kt * ((ax_[c] + adx[c]) - tgt);    // node 1 of the arm
+          }
+          cross3(adx, fd, tauj);                                 // link_direction x force
+          D *o = sj + LEAN_JREC * ta;
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            o[i] = cf[i];
+            o[3 + i] = -(Qh[3 * i] * tauj[0] + Qh[3 * i + 1] * tauj[1] + Qh[3 * i + 2] * tauj[2]);
+            o[6 + i] = aQ[3 * i] * tauj[0] + aQ[3 * i + 1] * tauj[1] + aQ[3 * i + 2] * tauj[2];
+          }
+        }
+      }
       // ---- curvature, bending couple --------------------------------------------------------------------------
       F vec[3];
       {
@@ -465,7 +549,15 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       if (!vor_ok) w2 = F(0);
       bool bend_out = out_of_range(w2, A.lim_bend_hi, A.limf_bend);
       F u_ref = F(0);
-      if (check_trace || !FASTONLY) {
+      if constexpr (MULTI) {
+        // the 10-element arms of the octopus assemblies bend up to ~45 degrees per element: full-range map in
+        // u = sin^2(theta'/2) from the trace (u <= 1/4, 60 degrees), as in rod_kernel_packed.cuh
+        const D tr = fma(Qn[8], Q[8], fma(Qn[7], Q[7], fma(Qn[6], Q[6], fma(Qn[5], Q[5], fma(Qn[4], Q[4], fma(Qn[3], Q[3],
+                     fma(Qn[2], Q[2], fma(Qn[1], Q[1], Qn[0] * Q[0]))))))));
+        u_ref = fma(D(-0.25), tr, D(0.75 + 0.5e-10));
+        if (!vor_ok) u_ref = D(5e-11);
+        bend_out = !(u_ref <= D(kSmallBendU));
+      } else if (check_trace || !FASTONLY) {
         check_trace = false;
         const D tr = fma(Qn[8], Q[8], fma(Qn[7], Q[7], fma(Qn[6], Q[6], fma(Qn[5], Q[5], fma(Qn[4], Q[4], fma(Qn[3], Q[3],
                      fma(Qn[2], Q[2], fma(Qn[1], Q[1], Qn[0] * Q[0]))))))));
@@ -474,7 +566,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       }
       if (FASTONLY) dom_bad = dom_bad || bend_out;
       F fs;
-      {
+      if constexpr (MULTI) {
+        const D g = theta_over_sin(Z.poly, u_ref);
+        const D cot = fma(D(-2.0), u_ref, D(1.0)) * rsqrt_approx(D(4.0) * u_ref * (D(1.0) - u_ref));   // scales the 1e-14 guard term only
+        fs = g * fma(D(0.5e-14), cot, D(-0.5)) * A.inv_rest_vor;
+      } else {
         // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved.  (Contact
         // variant: indexed through a register the compiler cannot see through, so that the ten coefficients are
         // constant-bank loads inside the loop instead of hoisted, spilled and reloaded registers.)
@@ -583,6 +679,18 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2];
         fint[0] = sfl[0] - (F)a0.x; fint[1] = sfl[1] - (F)a0.y; fint[2] = sfl[2] - (F)a1.x;
         tq[0] = tql[0] + (F)a1.y; tq[1] = tql[1] + (F)a2.x; tq[2] = tql[2] - (F)a2.y;
+      }
+      D fj[3] = {D(0), D(0), D(0)}, tj[3] = {D(0), D(0), D(0)};   // assemblies: joint force on node 0 / couple on element 0
+      if constexpr (MULTI) {
+        if (active && first && has_head) {
+          const D *o = sj + LEAN_JREC * tid;
+#pragma unroll
+          for (int i = 0; i < 3; i++) { fj[i] = -o[i]; tj[i] = o[6 + i]; }
+        }
+        if (!A.contact_before_forcing) {   // the joint is registered before the contact: the friction balance sees its loads
+#pragma unroll
+          for (int i = 0; i < 3; i++) { fint[i] += fj[i]; tq[i] += tj[i]; }
+        }
       }
       if constexpr (CONTACT) {
         // forcing registered before the contact: the static-friction torque balance sees the muscle couple
@@ -705,21 +813,51 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
           for (int i = 0; i < 3; i++) tq[i] += mtq[i];
         }
       }
-      // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update (FP64 accumulation)
-      v[0] = fma((D)fint[0], dtim_cv, fma(v[0], c_cv, base0));
-      v[1] = fma((D)fint[1], dtim_cv, fma(v[1], c_cv, MIXED ? A.k_gdt_cv[1] : (D)A.gdt_cv[1]));
-      v[2] = fma((D)fint[2], dtim_cv, fma(v[2], c_cv, MIXED ? A.k_gdt_cv[2] : (D)A.gdt_cv[2]));
-      {
-        const F g = elem_ok ? e * A.dt_Jinv0 : F(0), g2 = g * F(0.5);   // dt e / J ; J3 = 2 J1 for a circular section
-        w[0] = fma((D)g, (D)tq[0], w[0]) * (D)cw0;
-        w[1] = fma((D)g, (D)tq[1], w[1]) * (D)cw0;
-        w[2] = fma((D)g2, (D)tq[2], w[2]) * (D)cw2;
+      if constexpr (MULTI) {
+        if (A.contact_before_forcing) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) { fint[i] += fj[i]; tq[i] += tj[i]; }
+        }
       }
-      // rate constraints (zeroing BCs commute with the multiplicative damper)
-      v[0] = pin_fixed ? D(0) : v[0]; v[1] = z12 ? D(0) : v[1]; v[2] = z12 ? D(0) : v[2];
-      w[0] = z12 ? D(0) : w[0]; w[1] = pin_fixed ? D(0) : w[1]; w[2] = z12 ? D(0) : w[2];
+      if (MULTI && is_head) {
+        // rigid head: a = F/m, alpha = J^-1 ((J w) x w + T)  (SURVEY D.1); loads = the joints' reactions, summed in
+        // connection order; no gravity, no damper (octopus/build.py:141-152); then the rate part of
+        // BodyBoundaryCondition: v_z = 0, w_x = w_y = 0
+        if (hd) {
+          D Fh[3] = {D(0), D(0), D(0)}, Th[3] = {D(0), D(0), D(0)};
+          for (int a = 0; a < n_rod; a++) {
+            const D *o = sj + LEAN_JREC * (r * G + a * tpr);
+#pragma unroll
+            for (int i = 0; i < 3; i++) { Fh[i] += o[i]; Th[i] += o[3 + i]; }
+          }
+          const D Jw[3] = {A.head_J[0] * w[0], A.head_J[1] * w[1], A.head_J[2] * w[2]};
+          D lt[3];
+          cross3(Jw, w, lt);
+#pragma unroll
+          for (int i = 0; i < 3; i++) {
+            v[i] = fma(Fh[i], (D)A.head_dt_inv_mass, v[i]);
+            w[i] = fma(c_dt, A.head_Jinv[i] * (lt[i] + Th[i]), w[i]);
+          }
+          v[2] = D(0); w[0] = D(0); w[1] = D(0);
+        }
+      } else {
+        // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update (FP64 accumulation)
+        v[0] = fma((D)fint[0], dtim_cv, fma(v[0], c_cv, base0));
+        v[1] = fma((D)fint[1], dtim_cv, fma(v[1], c_cv, MIXED ? A.k_gdt_cv[1] : (D)A.gdt_cv[1]));
+        v[2] = fma((D)fint[2], dtim_cv, fma(v[2], c_cv, MIXED ? A.k_gdt_cv[2] : (D)A.gdt_cv[2]));
+        {
+          const F g = elem_ok ? e * A.dt_Jinv0 : F(0), g2 = g * F(0.5);   // dt e / J ; J3 = 2 J1 for a circular section
+          w[0] = fma((D)g, (D)tq[0], w[0]) * (D)cw0;
+          w[1] = fma((D)g, (D)tq[1], w[1]) * (D)cw0;
+          w[2] = fma((D)g2, (D)tq[2], w[2]) * (D)cw2;
+        }
+        // rate constraints (zeroing BCs commute with the multiplicative damper)
+        v[0] = pin_fixed ? D(0) : v[0]; v[1] = z12 ? D(0) : v[1]; v[2] = z12 ? D(0) : v[2];
+        w[0] = z12 ? D(0) : w[0]; w[1] = pin_fixed ? D(0) : w[1]; w[2] = z12 ? D(0) : w[2];
+      }
 
       kinematic(last ? c_half_dt : c_dt, last ? D(1e-14) : D(2e-14));
+      head_constrain_values();
     };
     // the item's last substep ends with a half kinematic step and exports the stale observables: its own copy of the
     // body, so that the loop carries neither the selects nor the branch
@@ -734,9 +872,9 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       if (FASTONLY) {
         if (tid < 256) sh_dom[tid] = 0;
         __syncthreads();
-        if (active && dom_bad) atomicOr(&sh_dom[r], 1);
+        if (live && dom_bad) atomicOr(&sh_dom[r], 1);
         __syncthreads();
-        if (active && first && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
+        if (active && lead && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
       }
       D *sc = A.sk_scratch + (size_t)p * SCR * NT;
 #pragma unroll
@@ -755,11 +893,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     if (FASTONLY) {    // env-level OR of the range flags; a flagged env keeps its pre-launch state in global memory
       if (tid < 256) sh_dom[tid] = 0;
       __syncthreads();
-      if (active && dom_bad) atomicOr(&sh_dom[r], 1);
+      if (live && dom_bad) atomicOr(&sh_dom[r], 1);
       __syncthreads();
       // (a part of this item run by the previous slot may have flagged the env already)
-      redo = active && (sh_dom[r] != 0 || A.redo[env] != 0);
-      if (redo && first && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
+      redo = live && (sh_dom[r] != 0 || A.redo[env] != 0);
+      if (redo && lead && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
     }
     constexpr int RS = NT + 2;
     if (MIXED) {       // edge vectors of the final FP64 positions: the strain state the next launch starts from
@@ -773,6 +911,14 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       __syncthreads();
     }
     bool bad = false;
+    if (MULTI && hd && !redo) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { hd[c] = (ST)x[c]; hd[3 + c] = (ST)v[c]; hd[15 + c] = (ST)w[c]; }
+#pragma unroll
+      for (int c = 0; c < 9; c++) hd[6 + c] = (ST)Q[c];
+      float *o = A.obs + (size_t)env * A.obs_dim;
+      for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
+    }
     if (active && !redo) {
       if (CONTACT) { to_lab(x); to_lab(v); rows_to_lab(Q); }   // (final: nothing below reads them in the internal frame)
 #pragma unroll
@@ -798,8 +944,8 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     __syncthreads();
     if (active && bad) atomicOr(&sh_flag[r], 1);
     __syncthreads();
-    if (!FASTONLY && A.redo_filter && active && first) A.redo[env] = 0;
-    if (active && first && !redo) {
+    if (!FASTONLY && A.redo_filter && active && lead) A.redo[env] = 0;
+    if (active && lead && !redo) {
       const bool invalid = sh_flag[r] != 0;
       if (mus) A.muscle[(size_t)env * A.muscle_dim] = mus_t;
       if (A.model == MODEL_SOFT_PENDULUM) {
@@ -811,7 +957,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         A.terminated[env] = invalid ? 1 : 0;
       }
     }
-    if (active && A.model == MODEL_ROD && j == n && !redo) {
+    if (active && A.model == MODEL_ROD && j == n && !MULTI && !redo) {
       float *o = A.obs + (size_t)env * A.obs_dim;
       for (int c = 0; c < 3; c++) { o[c] = (float)x[c]; o[3 + c] = (float)v[c]; }
     }

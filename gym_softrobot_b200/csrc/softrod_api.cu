@@ -301,8 +301,10 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 // count and every slot gets the same number of item-substeps (rod_kernel_lean.cuh); partial items travel through
 // sk_scratch.  The fallback launch (redo_filter) visits flagged envs only and keeps one CTA per item.
 template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  const int rods_per_cta = NT / (A.n_elem + 1);
-  if (rods_per_cta < 1) return fail(SR_E_INVALID, "rod does not fit one CTA of the lean kernel");
+  const bool multi = CONTACT == 3;
+  const int group = (multi ? A.n_rod : 1) * (A.n_elem + 1) + (multi ? A.has_head : 0);
+  const int rods_per_cta = NT / group;   // env groups per CTA
+  if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the lean kernel");
   const int items = (A.n_env + rods_per_cta - 1) / rods_per_cta;
   if (h->sk_slots == 0) {
     cudaDeviceProp prop;
@@ -348,6 +350,17 @@ template <typename T> bool is_lean_contact_config(const sr::RodArgs<T> &A) {
       A.point_force) return false;
   if (A.bc_kind != sr::BC_FREE && A.bc_kind != sr::BC_ONE_END_FIXED) return false;
   return A.contact_on || A.rest_kappa || A.muscle_on;
+}
+
+// assemblies (OctoFlat: arms + rigid head + FixedJoint2Rigid joints on the plane): the lean kernel's third contact variant
+template <typename T> bool is_lean_multi_config(const sr::RodArgs<T> &A) {
+  if (!std::is_same<T, double>::value) return false;
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("SOFTROD_LEAN_MULTI"); off = (e && atoi(e) == 0) ? 1 : 0; }   // =0: generic kernel (A/B)
+  if (off) return false;
+  if (!(A.n_rod > 1 || A.has_head)) return false;
+  if (A.spline_mask || A.muscle_on || A.laplace_order > 0 || A.sucker || A.ext_force || A.ext_couple || A.elem_tab || A.point_force) return false;
+  return A.bc_kind == sr::BC_FREE && A.rot_on == 0;
 }
 
 template <typename T> bool is_lean_config(const sr::RodArgs<T> &A) {
@@ -470,6 +483,16 @@ template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaS
     }
   }
   if constexpr (std::is_same<T, double>::value) {
+    if (is_lean_multi_config(A)) {
+      switch (packed_threads_setting(h->cfg.n_elem, h->n_rod, h->cfg.has_head)) {
+        case 1024: return launch_lean_pair<T, 1024, 1, 3>(h, A, s);
+        case 768: return launch_lean_pair<T, 768, 1, 3>(h, A, s);
+        case 544: return launch_lean_pair<T, 544, 1, 3>(h, A, s);
+        case 512: return launch_lean_pair<T, 512, 1, 3>(h, A, s);
+        case 384: return launch_lean_pair<T, 384, 1, 3>(h, A, s);
+        default: return launch_lean_pair<T, 256, 2, 3>(h, A, s);
+      }
+    }
     if (is_lean_contact_config(A)) {
       const int nt = lean_threads_setting(h->cfg.n_elem);
 #define SR_LEANC(NT_, MB_) (A.muscle_on ? launch_lean_pair<T, NT_, MB_, 2>(h, A, s) : launch_lean_pair<T, NT_, MB_, 1>(h, A, s))
