@@ -1,5 +1,5 @@
 // inst_lean.cu — the lean kernel (rod_kernel_lean.cuh) for one storage type and CTA size:
-//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n> [-DSR_TU_CONTACT=1|2|3: the contact variant without / with the muscle wave / for assemblies, FP64 only]
+//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n> [-DSR_TU_CONTACT=1|2|3|4: contact variant without / with the muscle wave / for assemblies; 4: filter + moving base; FP64 only]
 #include <atomic>
 #include "launch.cuh"
 #include "rod_kernel_lean.cuh"
@@ -15,7 +15,7 @@ template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT> static cudaE
   const unsigned long long bit = 1ULL << (dev & 63);
   if (!(opted.load(std::memory_order_relaxed) & bit)) {
     e = cudaFuncSetAttribute(rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(lean_smem_words(NT, CONTACT == 3) * sizeof(double)));
+                             (int)(lean_smem_words(NT, CONTACT) * sizeof(double)));
     if (e != cudaSuccess) return e;
     opted.fetch_or(bit, std::memory_order_relaxed);
   }
@@ -25,7 +25,7 @@ template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT> static cudaE
 template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s) {
   cudaError_t e = lean_opt_in<T, NT, MINB, FASTONLY, CONTACT>();
   if (e != cudaSuccess) return e;
-  rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT><<<grid, NT, lean_smem_words(NT, CONTACT == 3) * sizeof(double), s>>>(A);
+  rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT><<<grid, NT, lean_smem_words(NT, CONTACT) * sizeof(double), s>>>(A);
   return cudaGetLastError();
 }
 
@@ -33,7 +33,7 @@ template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT> int lean_cta
   if (lean_opt_in<T, NT, MINB, FASTONLY, CONTACT>() != cudaSuccess) return 0;
   int nb = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, rod_lean_kernel<T, NT, MINB, FASTONLY, CONTACT>, NT,
-                                                    lean_smem_words(NT, CONTACT == 3) * sizeof(double)) != cudaSuccess) return 0;
+                                                    lean_smem_words(NT, CONTACT) * sizeof(double)) != cudaSuccess) return 0;
   return nb;
 }
 

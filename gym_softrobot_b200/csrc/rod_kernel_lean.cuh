@@ -79,7 +79,11 @@ __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], con
 
 constexpr int LEAN_REC = 18;        // exchange record per thread (doubles), 144-byte stride: conflict-free LDS.128
 constexpr int LEAN_JREC = 10;      // assemblies: joint record of an arm's first thread {reaction force, couple on the head, couple on element 0, -}
-constexpr int lean_smem_words(int nt, bool multi = false) { return (LEAN_REC + 6 + (multi ? LEAN_JREC : 0)) * (nt + 2); }
+// filter variant: records of 6 doubles with 6 ghost records on either side of every rod (rods of >= 9 threads)
+constexpr int lean_ghost_records(int nt) { return nt + 12 * (nt / 9) + 16; }
+constexpr int lean_smem_words(int nt, int cvar = 0) {
+  return (LEAN_REC + 6 + (cvar == 3 ? LEAN_JREC : 0)) * (nt + 2) + (cvar == 4 ? 6 * lean_ghost_records(nt) : 0);
+}
 
 // float overloads of the reciprocal helpers for the FP32 force evaluation of the mixed mode
 __device__ __forceinline__ bool out_of_range(double x, int lim_hi, float) { return hi_abs(x) > lim_hi; }
@@ -112,8 +116,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   constexpr bool MIXED = sizeof(ST) == 4;
   // CVAR: 0 plain rod, 1 contact variant, 2 contact variant + travelling-wave muscle, 3 contact variant for assemblies
   // (several rods + one rigid head thread per env, FixedJoint2Rigid joints, BodyBoundaryCondition on the head)
-  constexpr bool CONTACT = CVAR != 0, MUS = CVAR == 2, MULTI = CVAR == 3;
-  static_assert(!CONTACT || !MIXED, "the contact variant is FP64 only");
+  // 4: SoftPendulum3D-v0 — LaplaceDissipationFilter + host-commanded moving base (no contact)
+  constexpr bool LAPL = CVAR == 4;
+  constexpr bool CONTACT = CVAR >= 1 && CVAR <= 3, MUS = CVAR == 2, MULTI = CVAR == 3;
+  static_assert(CVAR == 0 || !MIXED, "the variants are FP64 only");
   constexpr int SCR = CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
   using F = typename std::conditional<MIXED, float, double>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -138,6 +144,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   const bool lead = first && arm == 0;              // one thread per env: env-level flags and outputs
   const int t_head = r * G + G - 1;                 // where this env's head publishes its state
   D *sj = reinterpret_cast<D *>(sn + 6 * (NT + 2)); // assemblies: joint records (LEAN_JREC doubles per thread slot)
+  D *gb = sj;                                       // filter variant: ghost-padded records of the filtered rates
   if (tid < SNR) sn[SNR * NT + tid] = F(0);
   if (CONTACT && tid < 2) rec[LEAN_REC * NT + 16 + tid] = D(0);   // stage-1 contact load "left of element 0"
   __syncthreads();   // (the per-rod barriers below do not order this store against the other rods' reads)
@@ -353,8 +360,33 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         }
       }
     }
+    // SoftPendulum3D-v0: the base is commanded by the host (set_action, soft_pendulum_3d.py:106-120): float32
+    // displacement, float64 clipped position, velocity = actual displacement / (step_skip * time_step); the base jumps
+    // at once and is re-pinned after every kinematic update.  The controller's state (aux) is only written back by the
+    // epilogue of the item's last segment, so a fallback re-run or a split item recomputes the same command from the
+    // pre-launch aux.
+    const bool moving = LAPL && bc_thread && A.bc_kind == BC_MOVING_BASE;
+    D pin_x = D(0), pin_y = D(0), base_vx = D(0), base_vy = D(0);
+    float act_f0 = 0.0f, act_f1 = 0.0f;
+    if constexpr (LAPL) {
+      if (active && A.action_dim > 0) act_f0 = A.action[(size_t)env * A.action_dim];
+      if (active && A.action_dim > 1) act_f1 = A.action[(size_t)env * A.action_dim + 1];
+      if (moving) {
+        const ST *aux = A.aux + (size_t)env * AUX_DIM;
+        pin_x = (D)aux[0]; pin_y = (D)aux[1]; base_vx = (D)aux[3]; base_vy = (D)aux[4];
+        if (A.model == MODEL_SOFT_PENDULUM_3D && K > 0) {
+          const D px = pin_x, py = pin_y;
+          D nx = px + (D)__fmul_rn(A.base_step_f32, act_f0), ny = py + (D)__fmul_rn(A.base_step_f32, act_f1);
+          nx = fmin(fmax(nx, -(D)A.base_limit), (D)A.base_limit);
+          ny = fmin(fmax(ny, -(D)A.base_limit), (D)A.base_limit);
+          base_vx = (nx - px) * A.inv_move_period; base_vy = (ny - py) * A.inv_move_period;
+          pin_x = nx; pin_y = ny;
+        }
+        if (s_begin == 0) { x[0] = pin_x; x[1] = pin_y; x[2] = (D)bc[2]; }
+      }
+    }
     const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
-    const bool pin_fixed = bc_thread && A.bc_kind != BC_PENDULUM_SLIDER;
+    const bool pin_fixed = bc_thread && A.bc_kind != BC_PENDULUM_SLIDER && !moving;
     const bool z12 = pin_slider || pin_fixed;   // v_y, v_z, w_x, w_z are pinned by both; v_x, w_y by the clamp only
     // x component of the velocity update's constant term: dt c_v g_x, or, on the node that carries the base point
     // force, dt c_v F / m (soft_pendulum/build.py:94-105: the force REPLACES gravity's x component there)
@@ -367,6 +399,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       D a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
 #pragma unroll
       for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
+      if (LAPL && moving) { x[0] = pin_x; x[1] = pin_y; }
       D q = fma(a2, a2, fma(a1, a1, a0 * a0));
       const bool out = hi_abs(q) > A.lim_rot_hi;
       if (FASTONLY) {
@@ -395,7 +428,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       constexpr bool last = decltype(last_tag)::value;
       D mtq[3] = {D(0), D(0), D(0)};
       // zero, but not provably so (a launch never has 2^30 substeps): see the bend polynomial below
-      const int oz = CONTACT ? (s_now >> 30) : 0;
+      const int oz = (CONTACT || LAPL) ? (s_now >> 30) : 0;
       const RodArgs<ST> &Z = (&A)[oz];   // the kernel parameters through that index: constant-bank loads that stay inside the loop
       if constexpr (CONTACT) {
         if (mus) {
@@ -633,13 +666,13 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       // range limit keeps the dropped cubic term below 1.4e-15); c_w1 = c_w2 for a circular cross-section
       F cw0, cw2;
       {
-        const bool out = out_of_range(em1, CONTACT ? A.lim_em1c_hi : A.lim_em1_hi, A.limf_em1);
+        const bool out = out_of_range(em1, (CONTACT || LAPL) ? A.lim_em1c_hi : A.lim_em1_hi, A.limf_em1);
         if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
         if (FASTONLY || !out) {
-          if constexpr (CONTACT) {   // harder dampers, larger stretches: degree 5, |z| <= kLeanExpZc
-            F p0 = fma(Z.cwc[0][5], em1, Z.cwc[0][4]), p2 = fma(Z.cwc[1][5], em1, Z.cwc[1][4]);
+          if constexpr (CONTACT || LAPL) {   // harder dampers, larger stretches: degree 6, |z| <= kLeanExpZc
+            F p0 = fma(Z.cwc[0][6], em1, Z.cwc[0][5]), p2 = fma(Z.cwc[1][6], em1, Z.cwc[1][5]);
 #pragma unroll
-            for (int k = 3; k >= 0; k--) { p0 = fma(p0, em1, Z.cwc[0][k]); p2 = fma(p2, em1, Z.cwc[1][k]); }
+            for (int k = 4; k >= 0; k--) { p0 = fma(p0, em1, Z.cwc[0][k]); p2 = fma(p2, em1, Z.cwc[1][k]); }
             cw0 = p0; cw2 = p2;
           } else {
             cw0 = fma(fma(A.cwp[0][2], em1, A.cwp[0][1]), em1, A.cwp[0][0]);
@@ -852,8 +885,85 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
           w[2] = fma((D)g2, (D)tq[2], w[2]) * (D)cw2;
         }
         // rate constraints (zeroing BCs commute with the multiplicative damper)
-        v[0] = pin_fixed ? D(0) : v[0]; v[1] = z12 ? D(0) : v[1]; v[2] = z12 ? D(0) : v[2];
-        w[0] = z12 ? D(0) : w[0]; w[1] = pin_fixed ? D(0) : w[1]; w[2] = z12 ? D(0) : w[2];
+        auto constrain_rates = [&]() {
+          v[0] = pin_fixed ? D(0) : v[0]; v[1] = z12 ? D(0) : v[1]; v[2] = z12 ? D(0) : v[2];
+          w[0] = z12 ? D(0) : w[0]; w[1] = pin_fixed ? D(0) : w[1]; w[2] = z12 ? D(0) : w[2];
+          if (LAPL && moving) {
+            // [constrain, dampen] order: the analytical damper (already applied above) rescales the commanded velocity too
+            const D sc = A.damp_first ? D(1) : c_cv;
+            v[0] = base_vx * sc; v[1] = base_vy * sc; v[2] = D(0);
+            w[0] = D(0); w[1] = D(0); w[2] = D(0);
+          }
+        };
+        if constexpr (LAPL) {
+          // LaplaceDissipationFilter of order 7 (elastica/dissipation.py:nb_filter_rate): seven passes of
+          // f <- (-f[k+1] - f[k-1] + 2 f[k]) / 4 on interior nodes / elements with the ends held at 0 (pass 0 sees the
+          // unfiltered ends), then rate -= f.  After pass 0 the field g vanishes at both ends, and six more passes of a
+          // symmetric stencil with zero ends are ONE 13-tap convolution of g's odd extension about the ends,
+          //   f7[k] = sum_m c_m g[k+m],  c_m = (-1)^m C(12, 6+m) / 4096,  g[-k] = -g[k], g[last+k] = -g[last-k]:
+          // two exchanges and barriers instead of seven.  The odd extension is materialised by the threads next to
+          // the ends, which also write their (negated) g into ghost records beyond the rod; every thread then reads
+          // its twelve neighbours at fixed offsets.  Nodes reflect about node n, elements about element n-1, so the
+          // two halves of a right-hand ghost record come from different threads.
+          auto laplace = [&]() {
+            if (A.laplace_order != 7) return;    // (the host only selects this variant for order 7 or none)
+            const bool node_in = active && j > 0 && j < n, elem_in = active && j > 0 && j < n - 1;
+            double2 *own = reinterpret_cast<double2 *>(rec + LEAN_REC * tid);
+            own[0] = make_double2(v[0], v[1]); own[1] = make_double2(v[2], w[0]); own[2] = make_double2(w[1], w[2]);
+            rod_sync();
+            D g[6];
+            {
+              // end nodes / elements (and idle threads) take themselves as both neighbours: (-f - f + 2 f) / 4 = 0 exactly
+              const double2 *ql = reinterpret_cast<const double2 *>(rec + LEAN_REC * (node_in ? tid - 1 : tid));
+              const double2 *qr = reinterpret_cast<const double2 *>(rec + LEAN_REC * (node_in ? tid + 1 : tid));
+              const double2 l0 = ql[0], l1 = ql[1], l2 = ql[2], r0 = qr[0], r1 = qr[1], r2 = qr[2];
+              const D lv[6] = {l0.x, l0.y, l1.x, elem_in ? l1.y : w[0], elem_in ? l2.x : w[1], elem_in ? l2.y : w[2]};
+              const D rv[6] = {r0.x, r0.y, r1.x, elem_in ? r1.y : w[0], elem_in ? r2.x : w[1], elem_in ? r2.y : w[2]};
+              const D mv[6] = {v[0], v[1], v[2], w[0], w[1], w[2]};
+#pragma unroll
+              for (int c = 0; c < 6; c++) g[c] = ((-rv[c] - lv[c]) + D(2) * mv[c]) * D(0.25);
+            }
+            D *slot = gb + 6 * (r * (tpr + 12) + 6 + j);
+            {
+              double2 *o = reinterpret_cast<double2 *>(slot);
+              if (j < n) { o[0] = make_double2(g[0], g[1]); o[1] = make_double2(g[2], g[3]); o[2] = make_double2(g[4], g[5]); }
+              else { o[0] = make_double2(g[0], g[1]); slot[2] = g[2]; }   // tip node: its record's element half is element n-2's ghost
+              if (j >= 1 && j <= 6) {              // left ghosts: both fields reflect about index 0
+                double2 *gl = reinterpret_cast<double2 *>(slot - 12 * j);
+                gl[0] = make_double2(-g[0], -g[1]); gl[1] = make_double2(-g[2], -g[3]); gl[2] = make_double2(-g[4], -g[5]);
+              }
+              if (j >= n - 6 && j <= n - 1) {      // right ghosts of the node field: about node n
+                D *gr = slot + 12 * (n - j);
+                gr[0] = -g[0]; gr[1] = -g[1]; gr[2] = -g[2];
+              }
+              if (j >= n - 7 && j <= n - 2) {      // right ghosts of the element field: about element n - 1
+                D *gr = slot + 12 * (n - 1 - j);
+                gr[3] = -g[3]; gr[4] = -g[4]; gr[5] = -g[5];
+              }
+            }
+            rod_sync();
+            D acc[6] = {v[0], v[1], v[2], w[0], w[1], w[2]};
+            constexpr double cm[7] = {924.0 / 4096.0, -792.0 / 4096.0, 495.0 / 4096.0, -220.0 / 4096.0, 66.0 / 4096.0, -12.0 / 4096.0, 1.0 / 4096.0};
+#pragma unroll
+            for (int c = 0; c < 6; c++) acc[c] = fma(D(-cm[0]), g[c], acc[c]);
+#pragma unroll
+            for (int m = 1; m <= 6; m++) {
+              const double2 *ql = reinterpret_cast<const double2 *>(slot - 6 * m), *qr = reinterpret_cast<const double2 *>(slot + 6 * m);
+              const double2 l0 = ql[0], l1 = ql[1], l2 = ql[2], r0 = qr[0], r1 = qr[1], r2 = qr[2];
+              acc[0] = fma(D(-cm[m]), l0.x + r0.x, acc[0]); acc[1] = fma(D(-cm[m]), l0.y + r0.y, acc[1]);
+              acc[2] = fma(D(-cm[m]), l1.x + r1.x, acc[2]); acc[3] = fma(D(-cm[m]), l1.y + r1.y, acc[3]);
+              acc[4] = fma(D(-cm[m]), l2.x + r2.x, acc[4]); acc[5] = fma(D(-cm[m]), l2.y + r2.y, acc[5]);
+            }
+            // ends: g and its odd extension give exactly 0 there; the selects only keep idle lanes and the tip's pseudo-element clean
+            if (node_in) { v[0] = acc[0]; v[1] = acc[1]; v[2] = acc[2]; }
+            if (elem_in) { w[0] = acc[3]; w[1] = acc[4]; w[2] = acc[5]; }
+          };
+          if (!A.damp_first) constrain_rates();     // (one copy of the filter, two of the small constraint)
+          laplace();
+          if (A.damp_first) constrain_rates();
+        } else {
+          constrain_rates();
+        }
       }
 
       kinematic(last ? c_half_dt : c_dt, last ? D(1e-14) : D(2e-14));
@@ -937,7 +1047,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)
     D *sh_t = rec;   // 3 rows of NT + 2
     if (tid < 256) sh_flag[tid] = 0;
-    if (active && A.model == MODEL_SOFT_PENDULUM) {
+    if (active && (A.model == MODEL_SOFT_PENDULUM || (LAPL && A.model == MODEL_SOFT_PENDULUM_3D))) {
 #pragma unroll
       for (int i = 0; i < 3; i++) sh_t[i * RS + tid] = (j < n) ? (D)st[(F_TAN + i) * stride + j] : D(0);
     }
@@ -952,6 +1062,15 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         soft_pendulum_outputs<D>(sh_t + tid, RS, n, x[0], v[0],
                                  A.action_dim > 0 ? A.action[(size_t)env * A.action_dim] : 0.0f, invalid,
                                  A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env);
+      } else if (LAPL && A.model == MODEL_SOFT_PENDULUM_3D) {
+        const double x0[3] = {x[0], x[1], x[2]}, v0[3] = {v[0], v[1], v[2]};
+        ST *aux = A.aux + (size_t)env * AUX_DIM;
+        if (moving && K > 0) {   // the base controller's state, deferred from the prologue
+          aux[0] = (ST)pin_x; aux[1] = (ST)pin_y; aux[3] = (ST)base_vx; aux[4] = (ST)base_vy; aux[5] = ST(0);
+        }
+        soft_pendulum_3d_outputs<D>(sh_t + tid, RS, n, x0, v0, act_f0, act_f1, (double)aux[0], (double)aux[1],
+                                    invalid, A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env,
+                                    reinterpret_cast<D *>(aux + 6));
       } else {
         A.reward[env] = 0.0;
         A.terminated[env] = invalid ? 1 : 0;

@@ -100,9 +100,9 @@ template <typename T> struct RodArgs {
   T dt_Jinv0;                         // dt / J1
   T bendw[10];                        // -theta'/(2 D sin theta') as a polynomial in |axial(R - R^T)|^2 (SR_COEF_BENDW)
   T cwp[2][3];                        // c_w^e as a quadratic in (e - 1), components 0 (= 1) and 2
-  // contact variant of the lean kernel: c_w^e to degree 5 (|z| <= kLeanExpZc), D / 2, the travelling wave's rotation
+  // contact variant of the lean kernel: c_w^e to degree 6 (|z| <= kLeanExpZc), D / 2, the travelling wave's rotation
   // per substep (cos / sin of mus_omega dt) and 1 / ramp-up time
-  T cwc[2][6], half_rest_vor; int lim_em1c_hi;
+  T cwc[2][7], half_rest_vor; int lim_em1c_hi;
   double mus_cd, mus_sd, mus_inv_ramp;
   double sincg[3], cosch[3];          // sin(t)/t = 1 + q g(q), (1 - cos t)/t^2 = 1/2 + q h(q)  (the rotation update is FP64 in both modes)
   // double copies of what the FP64 part of the mixed (FP32-storage) mode reads

@@ -139,7 +139,7 @@ constexpr double kNarrowBendW2 = 0.6144;
 #define SR_COEF_COSCH {-0.04166666666665805, 0.0013888888733895929, -2.4797454055979264e-05}
 // the lean kernel's c_w^e = c_w exp(z) drops z^3/6: |z| <= 2e-5 keeps that below 1.4e-15
 constexpr double kLeanExpZ = 2.0e-5;
-constexpr double kLeanExpZc = 4.0e-3;   // degree-5 variant: z^6 / 720 < 6e-18
+constexpr double kLeanExpZc = 1.0e-2;   // degree-6 variant: z^7 / 5040 < 2e-18 (the generic kernel's range)
 constexpr double kNarrowRotQ = 0.01, kNarrowBendU = 0.04, kMidBendU = 0.1, kNarrowExpZ = 2.5e-4;
 
 template <typename T> struct PolyCoef {

@@ -213,7 +213,7 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
       lmax = fmax(lmax, fabs(lc));
       A.cwp[k][0] = (T)cw; A.cwp[k][1] = (T)(cw * lc); A.cwp[k][2] = (T)(cw * 0.5 * lc * lc);
       double term = cw;
-      for (int i = 0; i < 6; i++) { A.cwc[k][i] = (T)term; term *= lc / (double)(i + 1); }
+      for (int i = 0; i < 7; i++) { A.cwc[k][i] = (T)term; term *= lc / (double)(i + 1); }
     }
     A.k_dt = c.dt; A.k_half_dt = 0.5 * c.dt; A.k_dt_inv_mass = c.dt / mass; A.k_inv_rest_len = 1.0 / rl;
     A.k_c_v = c.damping_constant >= 0.0 ? exp(-c.damping_constant * c.dt) : 1.0;
@@ -350,6 +350,19 @@ template <typename T> bool is_lean_contact_config(const sr::RodArgs<T> &A) {
       A.point_force) return false;
   if (A.bc_kind != sr::BC_FREE && A.bc_kind != sr::BC_ONE_END_FIXED) return false;
   return A.contact_on || A.rest_kappa || A.muscle_on;
+}
+
+// SoftPendulum3D-v0's model: LaplaceDissipationFilter (order 7, or none) + moving base or clamp, no contact: variant 4
+template <typename T> bool is_lean_filter_config(const sr::RodArgs<T> &A) {
+  if (!std::is_same<T, double>::value) return false;
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("SOFTROD_LEAN_FILTER"); off = (e && atoi(e) == 0) ? 1 : 0; }   // =0: generic kernel (A/B)
+  if (off) return false;
+  if (A.n_rod > 1 || A.has_head || A.spline_mask || A.muscle_on || A.contact_on || A.rest_kappa || A.sucker || A.ext_force ||
+      A.ext_couple || A.elem_tab || A.point_force) return false;
+  if (!(A.laplace_order == 7 || (A.laplace_order == 0 && A.bc_kind == sr::BC_MOVING_BASE))) return false;
+  if (A.bc_kind != sr::BC_MOVING_BASE && A.bc_kind != sr::BC_ONE_END_FIXED && A.bc_kind != sr::BC_FREE) return false;
+  return A.n_elem >= 8;     // (the filter's ghost records assume one reflection per end)
 }
 
 // assemblies (OctoFlat: arms + rigid head + FixedJoint2Rigid joints on the plane): the lean kernel's third contact variant
@@ -491,6 +504,16 @@ template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaS
         case 512: return launch_lean_pair<T, 512, 1, 3>(h, A, s);
         case 384: return launch_lean_pair<T, 384, 1, 3>(h, A, s);
         default: return launch_lean_pair<T, 256, 2, 3>(h, A, s);
+      }
+    }
+    if (is_lean_filter_config(A)) {
+      switch (lean_threads_setting(h->cfg.n_elem)) {
+        case 1024: return launch_lean_pair<T, 1024, 1, 4>(h, A, s);
+        case 768: return launch_lean_pair<T, 768, 1, 4>(h, A, s);
+        case 544: return launch_lean_pair<T, 544, 1, 4>(h, A, s);
+        case 512: return launch_lean_pair<T, 512, 1, 4>(h, A, s);
+        case 384: return launch_lean_pair<T, 384, 1, 4>(h, A, s);
+        default: return launch_lean_pair<T, 256, 2, 4>(h, A, s);
       }
     }
     if (is_lean_contact_config(A)) {
@@ -789,6 +812,16 @@ int sr_obs_dim(const sr_handle *h) { return h ? h->obs_dim : 0; }
 int sr_action_dim(const sr_handle *h) { return h ? h->action_dim : 0; }
 int sr_init_dim(const sr_handle *h) { return h ? h->init_dim : 0; }
 int64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
+int64_t sr_fallback_count(const sr_handle *h) {
+  if (!h || !h->redo_count) return 0;
+  unsigned long long v = 0;
+  int prev = 0;
+  cudaGetDevice(&prev); cudaSetDevice(h->cfg.device);
+  cudaDeviceSynchronize();
+  cudaMemcpy(&v, h->redo_count, sizeof(v), cudaMemcpyDeviceToHost);
+  cudaSetDevice(prev);
+  return (int64_t)v;
+}
 
 int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init_dev, void *stream) {
   if (!h || !init_dev) return fail(SR_E_INVALID, "sr_reset: null argument");

@@ -232,6 +232,9 @@ int sr_spline_basis(int32_t n_ctrl, double base_length, double *out);
 
 /* number of kernels this library launched on behalf of the handle so far */
 int64_t sr_launch_count(const sr_handle *h);
+/* Env-steps the fast-only kernels handed to the safe kernel since sr_create (arguments outside the polynomial maps'
+ * ranges; csrc/rod_kernel_lean.cuh).  Synchronises the handle's device: a diagnostic, not for the step loop. */
+int64_t sr_fallback_count(const sr_handle *h);
 
 /* Measure the device's FP64 FMA issue peak with a register-resident DFMA chain
  * (roofline denominator; not in MEASURED_PEAKS.json).  Returns TFLOP/s. */

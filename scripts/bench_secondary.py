@@ -19,9 +19,9 @@ def timed(fn, K=6, W=3):
     torch.cuda.synchronize()
     return sorted(a.elapsed_time(b) for a, b in ev)[K // 2] * 1e-3
 
-def report(name, n_env, elems, K, sec, flop):
+def report(name, n_env, elems, K, sec, flop, handle=None):
     es = n_env * elems * K / sec
-    print(json.dumps(dict(config=name, n_env=n_env, ms_per_step=round(sec * 1e3, 4), elem_substeps_per_s=es, fp64_frac=round(es * flop / 1e12 / peak, 4),
+    print(json.dumps(dict(config=name, fallback_env_steps=(handle.fallback_count() if handle is not None else None), launches=(handle.launch_count if handle is not None else None), n_env=n_env, ms_per_step=round(sec * 1e3, 4), elem_substeps_per_s=es, fp64_frac=round(es * flop / 1e12 / peak, 4),
                           knobs={k: v for k, v in os.environ.items() if k.startswith("SOFTROD_")})), flush=True)
 
 def outs(n_env):
@@ -36,13 +36,13 @@ if "contact50" in which:
     h.reset_host(init)
     h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.random.default_rng(1).uniform(-5, 5, (n_env, 1)) * np.ones((1, 49)), device="cuda")
     o, r, t = outs(n_env)
-    report("rod on frictional plane n=50 (OctoArmSingle model)", n_env, 50, 400, timed(lambda: h.step(None, 400, o, r, t)), 720)
+    report("rod on frictional plane n=50 (OctoArmSingle model)", n_env, 50, 400, timed(lambda: h.step(None, 400, o, r, t)), 720, h)
     assert int(t.sum()) == 0; h.close()
 if "sp3d" in which:
     n_env = 4096
     env = g.make_vec("SoftPendulum3D-v0", n_env, autoreset=False); env.reset(seed=42)
     a = (torch.rand((n_env, 2), device="cuda") * 2 - 1).float()
-    report("SoftPendulum3D-v0", n_env, 50, 400, timed(lambda: env.handle.step(a, 400, env.obs, env.reward, env.terminated)), 608)
+    report("SoftPendulum3D-v0", n_env, 50, 400, timed(lambda: env.handle.step(a, 400, env.obs, env.reward, env.terminated)), 608, env.handle)
     env.close()
 from gym_softrobot_b200.envs.octo_flat import OctoFlatVectorEnv
 for tag, n_elem, n_env, dt in (("multi10", 10, 16384, 7e-5), ("multi40", 40, 4096, 3e-5)):
@@ -50,7 +50,7 @@ for tag, n_elem, n_env, dt in (("multi10", 10, 16384, 7e-5), ("multi40", 40, 409
     env = OctoFlatVectorEnv(n_env, n_elems=n_elem, time_step=dt, autoreset=False); env.reset(seed=42)
     env.handle.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.random.default_rng(2).uniform(-5, 5, (n_env * 8, 1)) * np.ones((1, n_elem - 1)), device="cuda")
     o6, rew, term = env._scratch
-    report(f"8-arm assembly n_elem={n_elem}", n_env, 8 * n_elem, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=4), 720)
+    report(f"8-arm assembly n_elem={n_elem}", n_env, 8 * n_elem, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=4), 720, env.handle)
     assert int(term.sum()) == 0; env.close()
 if "contact512" in which:
     n_env = 4096
@@ -60,7 +60,7 @@ if "contact512" in which:
     h.reset_host(init)
     h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.random.default_rng(1).uniform(-3, 3, (n_env, 1)) * np.ones((1, 511)), device="cuda")
     o, r, t = outs(n_env)
-    report("long slender rod n=512 on frictional plane", n_env, 512, 50, timed(lambda: h.step(None, 50, o, r, t)), 720)
+    report("long slender rod n=512 on frictional plane", n_env, 512, 50, timed(lambda: h.step(None, 50, o, r, t)), 720, h)
     assert int(t.sum()) == 0; h.close()
 if "snake" in which:
     n_env = 4096
@@ -69,7 +69,7 @@ if "snake" in which:
     mu[:, 2:] = torch.as_tensor(np.random.default_rng(3).uniform(-4e-3, 4e-3, (n_env, 6)), device="cuda") @ env._W.T
     mu[:, 1] = 2 * np.pi / 0.97
     o6, rew, term = env._scratch
-    report("ContinuumSnake-v0 (400-substep segment)", n_env, 50, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=4), 840)
+    report("ContinuumSnake-v0 (400-substep segment)", n_env, 50, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=4), 840, env.handle)
     env.close()
 if "softarm" in which:
     n_env = 16384
@@ -77,5 +77,5 @@ if "softarm" in which:
     o6, rew, term = outs(n_env)
     pts, mags = env.handle.spline_tensors()
     pts[:, :, :env.handle.cfg.spline_n_ctrl] = 0.3
-    report("SoftArmTracking-v0 kernel (400 substeps)", n_env, 40, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=4), 460)
+    report("SoftArmTracking-v0 kernel (400 substeps)", n_env, 40, 400, timed(lambda: env.handle.step(None, 400, o6, rew, term), K=4), 460, env.handle)
     env.close()
