@@ -7,7 +7,7 @@ os.makedirs(dst, exist_ok=True)
 rep = os.path.join(src, f"{tag}_prof.ncu-rep")
 summ = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), rep], stdout=subprocess.PIPE, text=True).stdout
 open(os.path.join(dst, f"{tag}_ncu_summary.txt"), "w").write(
-    f"# ncu --set full --clock-control none --import-source on -k regex:rod_packed -s 6 -c 1 python bench.py --steps 4 --warmup 3\n" + summ)
+    f"# ncu --set full --clock-control none --import-source on -k regex:rod_lean_kernel -s 6 -c 1 python bench.py --steps 4 --warmup 3 --no-cpu-baseline\n" + summ)
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 d = dict(zip(rows[0], rows[2])); u = dict(zip(rows[0], rows[1]))
@@ -28,9 +28,10 @@ with open(os.path.join(dst, f"{tag}_launches.csv"), "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 80 python bench.py --steps 5 --warmup 3 --no-cpu-baseline\nkernel,duration_ns\n")
     for k, v in out: f.write(f"{k},{v}\n")
 tot = sum(float(v) for _, v in out)
-step = sum(float(v) for k, v in out if "rod_packed" in k or "rod_substeps" in k)
+step = sum(float(v) for k, v in out if "rod_lean" in k or "rod_packed" in k or "rod_substeps" in k)
 open(os.path.join(dst, f"{tag}_launches.csv"), "a").write(f"# share of the substep kernel in all profiled launch time: {step / tot:.4f} (excluding the dfma peak probe: {step / (tot - sum(float(v) for k, v in out if 'dfma' in k)):.4f})\n")
-for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_pytest_gpu.log", f"{tag}_smoke.log"):
+for f in (f"{tag}_bench.json", f"{tag}_bench_reference.json", f"{tag}_pytest_gpu.log", f"{tag}_smoke.log", f"{tag}_bench_cfg3.json",
+          f"{tag}_bench_cfg4.json", f"{tag}_bench_cfg5.json", f"{tag}_secondary.jsonl", f"{tag}_ncu_variants.txt", f"{tag}_smi.txt"):
     if os.path.exists(os.path.join(src, f)):
         shutil.copy(os.path.join(src, f), os.path.join(dst, f))
 print(open(os.path.join(dst, f"{tag}_ncu_summary.txt")).read()[:600]); print(open(os.path.join(dst, "latest_traffic.json")).read()); print(open(os.path.join(dst, f"{tag}_launches.csv")).read()[-400:])

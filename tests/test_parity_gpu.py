@@ -1407,3 +1407,120 @@ def test_tapered_muscle_octopus_topology_vs_c_oracle():
     print(f"tapered muscle-octopus topology: worst {worst:.2e}; head omega [one-ulp, fma build, 1e-13 replica, CUDA] = "
           + ", ".join(f"{v:.1e}" for v in head_sens["omega_collection"]))
     h.close(); asm.close()
+
+
+def test_two_handles_on_two_devices_agree():
+    """The opt-in above 48 KB of dynamic shared memory is a per-device attribute of a kernel (cudaFuncSetAttribute):
+    a second handle on another device of the same process has to set it again (round-1 advisory).  Two SoftPendulum
+    handles (lean kernel, split schedule: 600 envs > resident slots) and two contact handles (lean contact variant) on
+    cuda:0 and cuda:1 are stepped through host buffers, interleaved, and must agree bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from gym_softrobot_b200.envs.soft_pendulum import _make_handle, pendulum_init_params
+    from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
+    nat = _native()
+    n_env = 600
+    hs = [_make_handle(n_env, 50, 1e-4, d, nat.MATH_FAST) for d in (0, 1)]
+    u = np.array([u01_for_seed(42 + i) for i in range(n_env)])
+    acts = np.random.default_rng(3).uniform(-22, 22, size=(3, n_env, 1)).astype(np.float32)
+    for h in hs:
+        h.reset_host(pendulum_init_params(u))
+    outs = []
+    for s in range(3):
+        outs.append([h.step_host(acts[s], 400) for h in hs])
+    for s in range(3):
+        for a, b in zip(outs[s][0], outs[s][1]):
+            assert np.array_equal(np.asarray(a), np.asarray(b)), f"SoftPendulum step {s}: devices disagree"
+    st = [h.fields()["velocity_collection"].cpu().numpy() for h in hs]
+    assert np.array_equal(st[0], st[1]) and np.isfinite(st[0]).all()
+    for h in hs:
+        h.close()
+    cs = [nat.Handle(model=nat.MODEL_ROD, n_env=64, n_elem=50, dt=7e-5, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
+                     bc_kind=nat.BC_FREE, contact=arm_contact_params(), device=d, **_ROD) for d in (1, 0)]
+    init = np.zeros((64, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+    for h in cs:
+        h.reset_host(init)
+        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.linspace(-4, 4, 64)[:, None] * np.ones((1, 49)), device=f"cuda:{h.device}")
+        h.step_host(None, 300)
+    st = [h.fields()["position_collection"].cpu().numpy() for h in cs]
+    assert np.array_equal(st[0], st[1]) and np.isfinite(st[0]).all()
+    for h in cs:
+        h.close()
+
+
+def test_split_schedule_keeps_every_lean_variant_bit_identical():
+    """The lean kernel deals work by substep count: with more env groups than resident CTA slots an item is started by
+    one CTA and finished by another, its registers (and the travelling wave's phase, the assembly's head) travelling
+    through global scratch.  For every variant — contact, contact + muscle wave, assembly, filter + moving base — a
+    batch large enough to be split must give env 0 (and the last env) the bits it gets in a batch small enough not to
+    be: the hand-over is exact, and an env's result does not depend on where the schedule cut its item."""
+    import torch
+    import gym_softrobot_b200 as g
+    from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
+    from gym_softrobot_b200.envs.octo_flat import OctoFlatVectorEnv
+    nat = _native()
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+
+    def contact(n_env):
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=50, dt=7e-5, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
+                       bc_kind=nat.BC_FREE, contact=arm_contact_params(), **_ROD)
+        init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+        h.reset_host(init)
+        amp = np.where(np.arange(n_env) % 2 == 0, 8.0, -5.0)[:, None]      # env 0 and the last env of both batches: known shapes
+        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(amp * np.sin(np.pi * np.linspace(0, 1, 49))[None, :], device="cuda")
+        for _ in range(3):
+            h.step_host(None, 333)
+        st = h.state_tensor()
+        out = (st[0].clone(), st[n_env - 2].clone())
+        h.close()
+        return out
+
+    def snake(n_env):
+        env = g.make_vec("ContinuumSnake-v0", n_env, autoreset=False); env.reset()
+        mu = env.handle.muscle_tensor()
+        mu[:, 2:] = torch.as_tensor(np.random.default_rng(3).uniform(-4e-3, 4e-3, (1, 6)), device="cuda") @ env._W.T
+        mu[:, 1] = 2 * np.pi / 0.97
+        o6, rew, term = env._scratch
+        for _ in range(3):
+            env.handle.step(None, 333, o6, rew, term)
+        st = env.handle.state_tensor()
+        out = (st[0].clone(), st[n_env - 1].clone(), mu[0].clone())
+        env.close()
+        return out
+
+    def assembly(n_env):
+        env = OctoFlatVectorEnv(n_env, n_elems=10, time_step=7e-5, autoreset=False); env.reset(seed=42)
+        env.handle.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(np.linspace(-5, 5, 8)[:, None] * np.ones((1, 9)), device="cuda").repeat(n_env, 1)
+        o6, rew, term = env._scratch
+        for _ in range(3):
+            env.handle.step(None, 333, o6, rew, term)
+        st = env.handle.state_tensor()
+        out = (st[:8].clone(), st[-8:].clone(), env.handle.head_tensor()[0].clone(), env.handle.head_tensor()[-1].clone())
+        env.close()
+        return out
+
+    def filt(n_env):
+        env = g.make_vec("SoftPendulum3D-v0", n_env, autoreset=False); env.reset(seed=42)
+        a = torch.as_tensor(np.tile(np.array([[0.7, -0.4]], dtype=np.float32), (n_env, 1)), device="cuda")
+        for _ in range(3):
+            env.handle.step(a, 333, env.obs, env.reward, env.terminated)
+        st = env.handle.state_tensor()
+        out = (st[0].clone(), env.handle.aux_tensor()[0].clone(), env.obs[0].clone())
+        env.close()
+        return out
+
+    # (envs per CTA: 10 single rods of 51 threads in 512, 4 assemblies of 89 in 384; split needs more items than SMs)
+    for name, fn, small, big in (("contact", contact, 20, 10 * sm + 1500), ("snake", snake, 20, 10 * sm + 1500),
+                                 ("assembly", assembly, 8, 4 * sm + 300), ("filter", filt, 20, 10 * sm + 1500)):
+        a, b = fn(small), fn(big)
+        if name in ("contact",):
+            assert torch.equal(a[0], b[0]), name
+        elif name == "snake":
+            assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), name
+        elif name == "assembly":
+            assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), name
+            assert torch.equal(b[0], b[1]) and torch.equal(b[2], b[3]), "identical envs at both ends of a split batch differ"
+        else:
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), name
+        assert all(torch.isfinite(t).all() for t in b), name
