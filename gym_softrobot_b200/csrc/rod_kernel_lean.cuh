@@ -128,6 +128,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   F *sn = reinterpret_cast<F *>(rec + LEAN_REC * (NT + 2));
   constexpr int SNR = MIXED ? 8 : 6;
   __shared__ int sh_flag[256], sh_dom[256];   // one per rod of the CTA (<= NT / 4)
+  __shared__ double sh_base[CVAR == 4 ? 128 : 1][4];   // filter variant: the moving base's command, per rod (rods of >= 9 threads)
 
   const int tid = threadIdx.x;
   const int n = A.n_elem, stride = A.stride, tpr = n + 1;
@@ -365,16 +366,16 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     // at once and is re-pinned after every kinematic update.  The controller's state (aux) is only written back by the
     // epilogue of the item's last segment, so a fallback re-run or a split item recomputes the same command from the
     // pre-launch aux.
+    // (Only the rod's first thread uses the command, so it lives in shared memory, sh_base[r] = {x, y, v_x, v_y}, not
+    // in four 64-bit registers of every thread: the filter's taps need the registers, see below.)
     const bool moving = LAPL && bc_thread && A.bc_kind == BC_MOVING_BASE;
-    D pin_x = D(0), pin_y = D(0), base_vx = D(0), base_vy = D(0);
-    float act_f0 = 0.0f, act_f1 = 0.0f;
     if constexpr (LAPL) {
-      if (active && A.action_dim > 0) act_f0 = A.action[(size_t)env * A.action_dim];
-      if (active && A.action_dim > 1) act_f1 = A.action[(size_t)env * A.action_dim + 1];
       if (moving) {
         const ST *aux = A.aux + (size_t)env * AUX_DIM;
-        pin_x = (D)aux[0]; pin_y = (D)aux[1]; base_vx = (D)aux[3]; base_vy = (D)aux[4];
+        D pin_x = (D)aux[0], pin_y = (D)aux[1], base_vx = (D)aux[3], base_vy = (D)aux[4];
         if (A.model == MODEL_SOFT_PENDULUM_3D && K > 0) {
+          const float act_f0 = A.action_dim > 0 ? A.action[(size_t)env * A.action_dim] : 0.0f;
+          const float act_f1 = A.action_dim > 1 ? A.action[(size_t)env * A.action_dim + 1] : 0.0f;
           const D px = pin_x, py = pin_y;
           D nx = px + (D)__fmul_rn(A.base_step_f32, act_f0), ny = py + (D)__fmul_rn(A.base_step_f32, act_f1);
           nx = fmin(fmax(nx, -(D)A.base_limit), (D)A.base_limit);
@@ -383,6 +384,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
           pin_x = nx; pin_y = ny;
         }
         if (s_begin == 0) { x[0] = pin_x; x[1] = pin_y; x[2] = (D)bc[2]; }
+        sh_base[r][0] = pin_x; sh_base[r][1] = pin_y; sh_base[r][2] = base_vx; sh_base[r][3] = base_vy;   // (own thread only: no barrier)
       }
     }
     const bool pin_slider = bc_thread && A.bc_kind == BC_PENDULUM_SLIDER;
@@ -391,7 +393,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     // x component of the velocity update's constant term: dt c_v g_x, or, on the node that carries the base point
     // force, dt c_v F / m (soft_pendulum/build.py:94-105: the force REPLACES gravity's x component there)
     D base0 = MIXED ? A.k_gdt_cv[0] : (D)A.gdt_cv[0];
-    if (active && first && A.point_force) base0 = (A.action_dim > 0 ? (D)A.action[(size_t)env * A.action_dim] : D(0)) * dtim_cv;
+    if (!LAPL && active && first && A.point_force) base0 = (A.action_dim > 0 ? (D)A.action[(size_t)env * A.action_dim] : D(0)) * dtim_cv;
 
     // x += hh v ; Q <- R(hh w) Q (merged half steps)
     auto kinematic = [&](D hh, D eps) {
@@ -399,7 +401,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       D a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
 #pragma unroll
       for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
-      if (LAPL && moving) { x[0] = pin_x; x[1] = pin_y; }
+      if (LAPL && moving) { x[0] = sh_base[r][0]; x[1] = sh_base[r][1]; }
       D q = fma(a2, a2, fma(a1, a1, a0 * a0));
       const bool out = hi_abs(q) > A.lim_rot_hi;
       if (FASTONLY) {
@@ -891,7 +893,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
           if (LAPL && moving) {
             // [constrain, dampen] order: the analytical damper (already applied above) rescales the commanded velocity too
             const D sc = A.damp_first ? D(1) : c_cv;
-            v[0] = base_vx * sc; v[1] = base_vy * sc; v[2] = D(0);
+            v[0] = sh_base[r][2] * sc; v[1] = sh_base[r][3] * sc; v[2] = D(0);
             w[0] = D(0); w[1] = D(0); w[2] = D(0);
           }
         };
@@ -946,13 +948,22 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
             constexpr double cm[7] = {924.0 / 4096.0, -792.0 / 4096.0, 495.0 / 4096.0, -220.0 / 4096.0, 66.0 / 4096.0, -12.0 / 4096.0, 1.0 / 4096.0};
 #pragma unroll
             for (int c = 0; c < 6; c++) acc[c] = fma(D(-cm[0]), g[c], acc[c]);
+            // one third of a record at a time (two components, twelve independent 128-bit loads in flight, four
+            // accumulator registers) rather than tap by tap: at the 128-register cap the compiler otherwise issues
+            // the loads two at a time, each pair followed at once by its consumers
 #pragma unroll
-            for (int m = 1; m <= 6; m++) {
-              const double2 *ql = reinterpret_cast<const double2 *>(slot - 6 * m), *qr = reinterpret_cast<const double2 *>(slot + 6 * m);
-              const double2 l0 = ql[0], l1 = ql[1], l2 = ql[2], r0 = qr[0], r1 = qr[1], r2 = qr[2];
-              acc[0] = fma(D(-cm[m]), l0.x + r0.x, acc[0]); acc[1] = fma(D(-cm[m]), l0.y + r0.y, acc[1]);
-              acc[2] = fma(D(-cm[m]), l1.x + r1.x, acc[2]); acc[3] = fma(D(-cm[m]), l1.y + r1.y, acc[3]);
-              acc[4] = fma(D(-cm[m]), l2.x + r2.x, acc[4]); acc[5] = fma(D(-cm[m]), l2.y + r2.y, acc[5]);
+            for (int part = 0; part < 3; part++) {
+              double2 lv[6], rv[6];
+#pragma unroll
+              for (int m = 1; m <= 6; m++) {
+                lv[m - 1] = reinterpret_cast<const double2 *>(slot - 6 * m)[part];
+                rv[m - 1] = reinterpret_cast<const double2 *>(slot + 6 * m)[part];
+              }
+#pragma unroll
+              for (int m = 1; m <= 6; m++) {
+                acc[2 * part] = fma(D(-cm[m]), lv[m - 1].x + rv[m - 1].x, acc[2 * part]);
+                acc[2 * part + 1] = fma(D(-cm[m]), lv[m - 1].y + rv[m - 1].y, acc[2 * part + 1]);
+              }
             }
             // ends: g and its odd extension give exactly 0 there; the selects only keep idle lanes and the tip's pseudo-element clean
             if (node_in) { v[0] = acc[0]; v[1] = acc[1]; v[2] = acc[2]; }
@@ -1066,8 +1077,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         const double x0[3] = {x[0], x[1], x[2]}, v0[3] = {v[0], v[1], v[2]};
         ST *aux = A.aux + (size_t)env * AUX_DIM;
         if (moving && K > 0) {   // the base controller's state, deferred from the prologue
-          aux[0] = (ST)pin_x; aux[1] = (ST)pin_y; aux[3] = (ST)base_vx; aux[4] = (ST)base_vy; aux[5] = ST(0);
+          aux[0] = (ST)sh_base[r][0]; aux[1] = (ST)sh_base[r][1]; aux[3] = (ST)sh_base[r][2]; aux[4] = (ST)sh_base[r][3]; aux[5] = ST(0);
         }
+        const float act_f0 = A.action_dim > 0 ? A.action[(size_t)env * A.action_dim] : 0.0f;
+        const float act_f1 = A.action_dim > 1 ? A.action[(size_t)env * A.action_dim + 1] : 0.0f;
         soft_pendulum_3d_outputs<D>(sh_t + tid, RS, n, x0, v0, act_f0, act_f1, (double)aux[0], (double)aux[1],
                                     invalid, A.obs + (size_t)env * A.obs_dim, A.reward + env, A.terminated + env,
                                     reinterpret_cast<D *>(aux + 6));

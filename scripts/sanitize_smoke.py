@@ -41,4 +41,26 @@ h = nat.Handle(model=nat.MODEL_ROD, n_env=5, n_elem=30, dt=1e-4, base_length=1.0
 init = np.zeros((5, 9)); init[:, 3] = 1; init[:, 7] = 1; h.reset_host(init)
 h.fields()["omega_collection"][1, 2, :] = 2.0e4; h.fields()["omega_collection"][3, 2, :] = -2.0e4
 h.step_host(None, K); h.step_host(None, K); h.close()
+# round 2: the split schedule (more env groups than resident CTA slots: items change CTAs through global scratch) of the
+# lean kernel's plain, contact and assembly variants; a tapered rod with sucker and external loads (generic kernel, VARY)
+sm = torch.cuda.get_device_properties(0).multi_processor_count
+env = g.make_vec("SoftPendulum-v0", 10 * sm + 37, autoreset=False); env.reset(seed=1)
+env.handle.step(torch.ones((10 * sm + 37, 1), device="cuda"), 5, env.obs, env.reward, env.terminated); torch.cuda.synchronize(); env.close()
+n_big = 10 * sm + 23
+h = nat.Handle(model=nat.MODEL_ROD, n_env=n_big, n_elem=50, dt=7e-5, gravity=(0, 0, -9.81), damping_constant=1e-2,
+               bc_kind=nat.BC_FREE, contact=arm_contact_params(), **_ROD)
+init = np.zeros((n_big, 9)); init[:, 3] = 1; init[:, 8] = 1; h.reset_host(init); h.rest_kappa_tensor()[:, 0, :] = 3.0
+h.step_host(None, 5); h.close()
+env = g.make_vec("OctoFlat-v0", 4 * sm + 9, autoreset=False); env.reset(seed=1)
+env.handle.rest_kappa_tensor()[:, 0, :] = 2.0
+o6, rew, term = env._scratch
+env.handle.step(None, 5, o6, rew, term); torch.cuda.synchronize(); env.close()
+env = g.make_vec("SoftPendulum3D-v0", 10 * sm + 11, autoreset=False); env.reset(seed=1)
+env.handle.step(torch.full((10 * sm + 11, 2), 0.5, device="cuda"), 5, env.obs, env.reward, env.terminated); torch.cuda.synchronize(); env.close()
+h = nat.Handle(model=nat.MODEL_ROD, n_env=5, n_elem=25, dt=2e-5, base_length=0.2, base_radius=0.012, density=1050.0, youngs_modulus=1e5,
+               gravity=(0, 0, -9.81), damping_constant=0.05, bc_kind=nat.BC_FREE, tip_radius=0.002, sucker_index=0)
+init = np.zeros((5, 9)); init[:, 3] = 1; init[:, 8] = 1; h.reset_host(init)
+h.sucker_tensor()[:] = 0.5
+f_t, c_t = h.ext_load_tensors(); f_t[:, 2, :] = 1e-4; c_t[:, 0, :] = 1e-6
+h.step_host(None, K); h.close()
 print("sanitize_smoke done")
