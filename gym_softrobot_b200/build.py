@@ -35,8 +35,8 @@ def translation_units():
         for nt, minb in LEAN_EXTRA_SIZES + PACKED_SIZES:
             tus.append((f"lean_{t}_{nt}", "inst_lean.cu", [f"-DSR_TU_T={t}", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}"],
                         _COMMON + ["rod_kernel_lean.cuh"]))
-    for nt, minb in PACKED_SIZES:      # the lean kernel's contact variant (FP64): plain, with the travelling-wave muscle, for assemblies; 4 = filter + moving base
-        for cv in (1, 2, 3, 4):
+    for nt, minb in PACKED_SIZES:      # the lean kernel's contact variant (FP64): plain, with the travelling-wave muscle, for assemblies; 4 = filter + moving base; 5 = spline torques
+        for cv in (1, 2, 3, 4, 5):
             tus.append((f"leanc{cv}_double_{nt}", "inst_lean.cu", ["-DSR_TU_T=double", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}", f"-DSR_TU_CONTACT={cv}"],
                         _COMMON + ["rod_kernel_lean.cuh"]))
     for nt, minb in PACKED_SIZES:

@@ -118,6 +118,8 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   // (several rods + one rigid head thread per env, FixedJoint2Rigid joints, BodyBoundaryCondition on the head)
   // 4: SoftPendulum3D-v0 — LaplaceDissipationFilter + host-commanded moving base (no contact)
   constexpr bool LAPL = CVAR == 4;
+  // 5: clamped / free rod + MuscleTorquesWithVaryingBetaSplines (SoftArmTracking-v0); safe variant only, see below
+  constexpr bool SPL = CVAR == 5;
   constexpr bool CONTACT = CVAR >= 1 && CVAR <= 3, MUS = CVAR == 2, MULTI = CVAR == 3;
   static_assert(CVAR == 0 || !MIXED, "the variants are FP64 only");
   constexpr int SCR = CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
@@ -128,6 +130,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   F *sn = reinterpret_cast<F *>(rec + LEAN_REC * (NT + 2));
   constexpr int SNR = MIXED ? 8 : 6;
   __shared__ int sh_flag[256], sh_dom[256];   // one per rod of the CTA (<= NT / 4)
+  __shared__ int sh_need[CVAR == 5 ? 128 : 1];          // spline variant: which directions re-fit their magnitudes this substep, per rod
   __shared__ double sh_base[CVAR == 4 ? 128 : 1][4];   // filter variant: the moving base's command, per rod (rods of >= 9 threads)
 
   const int tid = threadIdx.x;
@@ -361,6 +364,23 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         }
       }
     }
+    // MuscleTorquesWithVaryingBetaSplines (muscle_torques_with_bspline.py:126-160,181-228): per enabled material
+    // direction d, external_torques[d, k] += mag_d[k]; mag is re-evaluated (not-a-knot cubic through the rate-limited
+    // control values, at s = cumsum(current lengths)) in every substep that finds the cached values different from the
+    // caller's targets, and kept otherwise — across launches too (the cache lives in HBM, A.spline).  The forcing
+    // mutates that cache inside the launch, so this variant only exists as the safe kernel (a fast-only run that is
+    // re-done would apply the rate limit twice).
+    const bool spl = SPL && A.spline_mask != 0;
+    double *sp = (spl && active) ? A.spline + (size_t)env * A.spline_dim : nullptr;
+    const int sP = A.spline_p, sCH = 2 * sP + 2;
+    D smag[3] = {D(0), D(0), D(0)};
+    if constexpr (SPL) {
+      if (spl && elem_ok) {
+#pragma unroll
+        for (int d = 0; d < 3; d++)
+          if (A.spline_mask >> d & 1) smag[d] = sp[3 * sCH + d * n + j];
+      }
+    }
     // SoftPendulum3D-v0: the base is commanded by the host (set_action, soft_pendulum_3d.py:106-120): float32
     // displacement, float64 clipped position, velocity = actual displacement / (step_skip * time_step); the base jumps
     // at once and is re-pinned after every kinematic update.  The controller's state (aux) is only written back by the
@@ -430,7 +450,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       constexpr bool last = decltype(last_tag)::value;
       D mtq[3] = {D(0), D(0), D(0)};
       // zero, but not provably so (a launch never has 2^30 substeps): see the bend polynomial below
-      const int oz = (CONTACT || LAPL) ? (s_now >> 30) : 0;
+      const int oz = (CONTACT || LAPL || SPL) ? (s_now >> 30) : 0;
       const RodArgs<ST> &Z = (&A)[oz];   // the kernel parameters through that index: constant-bank loads that stay inside the loop
       if constexpr (CONTACT) {
         if (mus) {
@@ -475,6 +495,30 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       const F lg = fma(l2, il, F(1e-14));                 // |dx| + 1e-14 (reference guard)
       const F ilg = MIXED ? il : fma(F(-1e-14) * il, il, il);   // 1/(l + 1e-14) to first order in 1e-14/l
       const F lgn = fma(l2n, iln, F(1e-14));              // length of element j+1, recomputed locally
+      if constexpr (SPL) {
+        if (spl) {
+          rec[LEAN_REC * tid + 15] = lg;     // element length, for the arc-length prefix sums below (spare word of the record)
+          if (active && first) {             // the forcing's own bookkeeping, once per env
+            int need = 0;
+            for (int d = 0; d < 3; d++) {
+              if (!(A.spline_mask >> d & 1)) continue;
+              double *ch = sp + d * sCH;
+              bool differ = ch[2 * sP] == 0.0;                      // initial_call_flag
+              for (int i = 0; i < sP; i++) differ = differ || !(ch[sP + i] == ch[i]);   // not np.array_equal
+              if (differ) {
+                ch[2 * sP] = 1.0;
+                for (int i = 0; i < sP; i++) {                      // filter_activation
+                  const double dd = ch[i] - ch[sP + i];
+                  const double sg = (double)((dd > 0.0) - (dd < 0.0));
+                  ch[sP + i] += sg * fmin(A.spline_rate, fabs(dd));
+                }
+                need |= 1 << d;
+              }
+            }
+            sh_need[r] = need;
+          }
+        }
+      }
       const F e = lg * (F)irg;
       const F em1 = fma(lg, (F)irg, F(-1.0));
       const F inv_e = A.rest_len * ilg;
@@ -668,10 +712,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       // range limit keeps the dropped cubic term below 1.4e-15); c_w1 = c_w2 for a circular cross-section
       F cw0, cw2;
       {
-        const bool out = out_of_range(em1, (CONTACT || LAPL) ? A.lim_em1c_hi : A.lim_em1_hi, A.limf_em1);
+        const bool out = out_of_range(em1, (CONTACT || LAPL || SPL) ? A.lim_em1c_hi : A.lim_em1_hi, A.limf_em1);
         if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
         if (FASTONLY || !out) {
-          if constexpr (CONTACT || LAPL) {   // harder dampers, larger stretches: degree 6, |z| <= kLeanExpZc
+          if constexpr (CONTACT || LAPL || SPL) {   // harder dampers, larger stretches: degree 6, |z| <= kLeanExpZc
             F p0 = fma(Z.cwc[0][6], em1, Z.cwc[0][5]), p2 = fma(Z.cwc[1][6], em1, Z.cwc[1][5]);
 #pragma unroll
             for (int k = 4; k >= 0; k--) { p0 = fma(p0, em1, Z.cwc[0][k]); p2 = fma(p2, em1, Z.cwc[1][k]); }
@@ -714,6 +758,29 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         const double2 a0 = qq[0], a1 = qq[1], a2 = qq[2];
         fint[0] = sfl[0] - (F)a0.x; fint[1] = sfl[1] - (F)a0.y; fint[2] = sfl[2] - (F)a1.x;
         tq[0] = tql[0] + (F)a1.y; tq[1] = tql[1] + (F)a2.x; tq[2] = tql[2] - (F)a2.y;
+      }
+      if constexpr (SPL) {
+        if (spl) {
+          const int need = active ? sh_need[r] : 0;
+          if (need && elem_ok) {
+            double s_k = 0.0;                                        // np.cumsum(system.lengths)[j]
+            for (int i = 0; i <= j; i++) s_k += rec[LEAN_REC * (tid - j + i) + 15];
+            const int m = min(max((int)floor(s_k * A.spline_inv_dx), 0), sP);
+            const double t = s_k - (double)m / A.spline_inv_dx;
+            for (int d = 0; d < 3; d++) {
+              if (!(need >> d & 1)) continue;
+              const double *ch = sp + d * sCH, *tb = A.spline_tab + (size_t)m * sP * 4;
+              double val = 0.0;
+              for (int i = 0; i < sP; i++)
+                val += ch[sP + i] * (tb[4 * i] + t * (tb[4 * i + 1] + t * (tb[4 * i + 2] + t * tb[4 * i + 3])));
+              val *= A.spline_scale;
+              sp[3 * sCH + d * n + j] = val;
+              smag[d] = val;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 3; i++) tq[i] += smag[i];
+        }
       }
       D fj[3] = {D(0), D(0), D(0)}, tj[3] = {D(0), D(0), D(0)};   // assemblies: joint force on node 0 / couple on element 0
       if constexpr (MULTI) {

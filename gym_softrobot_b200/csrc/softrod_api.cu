@@ -365,6 +365,17 @@ template <typename T> bool is_lean_filter_config(const sr::RodArgs<T> &A) {
   return A.n_elem >= 8;     // (the filter's ghost records assume one reflection per end)
 }
 
+// SoftArmTracking-v0's model: clamped / free rod + spline muscle torques, nothing else: variant 5 (safe kernel only)
+template <typename T> bool is_lean_spline_config(const sr::RodArgs<T> &A) {
+  if (!std::is_same<T, double>::value) return false;
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("SOFTROD_LEAN_SPLINE"); off = (e && atoi(e) == 0) ? 1 : 0; }   // =0: generic kernel (A/B)
+  if (off) return false;
+  if (!A.spline_mask || A.n_rod > 1 || A.has_head || A.muscle_on || A.contact_on || A.rest_kappa || A.sucker || A.ext_force ||
+      A.ext_couple || A.elem_tab || A.point_force || A.laplace_order > 0) return false;
+  return A.bc_kind == sr::BC_ONE_END_FIXED || A.bc_kind == sr::BC_FREE;
+}
+
 // assemblies (OctoFlat: arms + rigid head + FixedJoint2Rigid joints on the plane): the lean kernel's third contact variant
 template <typename T> bool is_lean_multi_config(const sr::RodArgs<T> &A) {
   if (!std::is_same<T, double>::value) return false;
@@ -504,6 +515,16 @@ template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaS
         case 512: return launch_lean_pair<T, 512, 1, 3>(h, A, s);
         case 384: return launch_lean_pair<T, 384, 1, 3>(h, A, s);
         default: return launch_lean_pair<T, 256, 2, 3>(h, A, s);
+      }
+    }
+    if (is_lean_spline_config(A)) {   // (mutates the forcing's cache inside the launch: no fast-only / redo pair)
+      switch (lean_threads_setting(h->cfg.n_elem)) {
+        case 1024: return launch_lean_impl<T, 1024, 1, false, 5>(h, A, s);
+        case 768: return launch_lean_impl<T, 768, 1, false, 5>(h, A, s);
+        case 544: return launch_lean_impl<T, 544, 1, false, 5>(h, A, s);
+        case 512: return launch_lean_impl<T, 512, 1, false, 5>(h, A, s);
+        case 384: return launch_lean_impl<T, 384, 1, false, 5>(h, A, s);
+        default: return launch_lean_impl<T, 256, 2, false, 5>(h, A, s);
       }
     }
     if (is_lean_filter_config(A)) {

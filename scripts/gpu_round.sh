@@ -25,7 +25,7 @@ timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --cs
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:rod_lean_kernel -s 6 -c 1 -f -o gpurun_out/${TAG}_prof python bench.py --steps 4 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
 : > gpurun_out/${TAG}_ncu_variants.txt
 for c in contact50 snake multi10 multi40 sp3d contact512 softarm; do
-  timeout 700 ncu --set full --clock-control none -k regex:rod_ -c 8 -f -o /tmp/${TAG}_$c python scripts/bench_secondary.py $c > /dev/null 2>&1
+  timeout 700 ncu --set full --clock-control none -k "regex:rod_(lean|packed)" -c 8 -f -o /tmp/${TAG}_$c python scripts/bench_secondary.py $c > /dev/null 2>&1
   echo "## $c" >> gpurun_out/${TAG}_ncu_variants.txt
   python scripts/ncu_summary.py /tmp/${TAG}_$c.ncu-rep 0.5 >> gpurun_out/${TAG}_ncu_variants.txt 2>&1
 done
