@@ -445,6 +445,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     };
     if (s_begin == 0 && K > 0) { kinematic(c_half_dt, D(1e-14)); head_constrain_values(); }
 
+    bool spl_settled = false;   // spline variant: the cached control values have reached their targets
     bool check_trace = true;   // first substep of the segment: rule out a state that starts beyond 90 degrees of bend
     auto substep = [&](auto last_tag, int s_now) {
       constexpr bool last = decltype(last_tag)::value;
@@ -498,7 +499,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       if constexpr (SPL) {
         if (spl) {
           rec[LEAN_REC * tid + 15] = lg;     // element length, for the arc-length prefix sums below (spare word of the record)
-          if (active && first) {             // the forcing's own bookkeeping, once per env
+          // the forcing's own bookkeeping, once per env.  The targets cannot change during a launch and the cached
+          // values only change here, so once a substep finds them equal nothing happens until the launch ends: the
+          // first thread then stops re-reading the cache from HBM (a chain of dependent global loads ahead of the
+          // barrier the whole rod waits at).
+          if (active && first && !spl_settled) {
             int need = 0;
             for (int d = 0; d < 3; d++) {
               if (!(A.spline_mask >> d & 1)) continue;
@@ -516,6 +521,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
               }
             }
             sh_need[r] = need;
+            spl_settled = (need == 0);
           }
         }
       }
