@@ -1524,3 +1524,50 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
         else:
             assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), name
         assert all(torch.isfinite(t).all() for t in b), name
+
+
+@pytest.mark.parametrize("normal", [(0.3, -0.2, 1.0), (0.0, -1.0, 0.0), (0.0, 0.0, -1.0)], ids=["oblique", "minus-y", "minus-z"])
+def test_rod_on_a_tilted_frictional_plane_vs_c_oracle(normal):
+    """The contact kernels work in a frame whose z axis is the plane normal and rotate lab vectors on load / store; the
+    reference envs only ever use +z (octopus) and +y (snake).  Here the plane is tilted (a genuinely non-permutation
+    rotation), or flipped: an actuated rod lying on it under a gravity that presses it onto the plane and drags it
+    sideways, sliding from the start (kinetic regime).  CUDA vs the C oracle (which takes dot products with the normal as
+    PyElastica does), every field, 600 substeps, 1e-9."""
+    import torch
+    import rod_oracle as ro
+    from gym_softrobot_b200.envs.arm_single import curvature_interp_matrix, _ROD
+    nat = _native()
+    N = np.array(normal, dtype=float); N /= np.linalg.norm(N)
+    a = np.cross(N, [1.0, 0.0, 0.0]); a /= np.linalg.norm(a)        # rod axis, in the plane
+    b = np.cross(N, a)                                               # second in-plane direction
+    n_env, n, dt = 4, 50, 7e-5
+    r0 = _ROD["base_radius"]
+    c = _arm_contact(False)
+    c["plane_origin"] = list(-r0 * N); c["plane_normal"] = list(N)
+    grav = tuple(-9.81 * N + 1.5 * b)
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, gravity=grav, damping_constant=1e-2,
+                   bc_kind=nat.BC_FREE, contact=c, **_ROD)
+    init = np.zeros((n_env, 9)); init[:, 3:6] = a; init[:, 6:9] = N
+    h.reset_host(init)
+    W = curvature_interp_matrix(7, n - 1)
+    rk = np.random.default_rng(11).uniform(-8, 8, size=(n_env, 7)) @ W.T
+    h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(rk, device="cuda")
+    v0 = 0.05 * a + 0.03 * b
+    h.fields()["velocity_collection"][:] = torch.as_tensor(v0, device="cuda")[None, :, None]
+    rods = [ro.OracleRod(n, [0, 0, 0], list(a), list(N), _ROD["base_length"], r0, 1000.0, 1e6, dt,
+                         gravity=grav, damping_constant=1e-2, contact=c) for _ in range(n_env)]
+    for i, r in enumerate(rods):
+        r.rest_kappa[0, :] = rk[i]
+        r.velocity_collection[...] = v0[:, None]
+    for chunk in (300, 300):
+        h.step_host(None, chunk)
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        for i, r in enumerate(rods):
+            r.substeps(chunk)
+            for name in ("position_collection", "velocity_collection", "director_collection", "omega_collection", "kappa", "tangents"):
+                assert_state_close(f[name][i], getattr(r, name), name, {}, f"env {i}", TOL)
+    # it slid along the plane and stayed on it
+    x = f["position_collection"][0]
+    height = (N[:, None] * x).sum(0)
+    assert np.abs(height).max() < 5e-3 and np.abs((b[:, None] * x).sum(0)).max() > 1e-4
+    h.close()
