@@ -238,7 +238,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     const bool live = in_grid && selected;             // a thread of an env that is being stepped
     const bool active = live && !is_head;              // ... that owns a node / element of a rod
     const int rod = env * n_rod + arm;                 // global rod slot in the state arrays
-    bool dom_bad = false;
+    int dom_bad = 0;                                   // which range a fast-only thread left: 1 rotation, 2 bend, 4 stretch (damper map)
     const bool elem_ok = active && j < n, vor_ok = active && j < n - 1;
     const int t_next = elem_ok ? tid + 1 : tid;
     const int t_next2 = vor_ok ? tid + 2 : t_next;
@@ -328,8 +328,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       } else {
 #pragma unroll
         for (int c = 0; c < 9; c++) Q[c] = (D)bc[3 + c];
+        // (a moving base is positioned by its controller below — and, when this CTA continues an item another one
+        // started, by the hand-over: the anchor stored at finalize time is not where the base is)
+        if (!(LAPL && A.bc_kind == BC_MOVING_BASE)) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) x[c] = (D)bc[c];
+          for (int c = 0; c < 3; c++) x[c] = (D)bc[c];
+        }
         if (CONTACT) { rows_to_int(Q); to_int(x); }
       }
     }
@@ -425,7 +429,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       D q = fma(a2, a2, fma(a1, a1, a0 * a0));
       const bool out = hi_abs(q) > A.lim_rot_hi;
       if (FASTONLY) {
-        dom_bad = dom_bad || out;
+        if (out) dom_bad |= 1;
         rotate_directors_lean(A.sincg, A.cosch, a0, a1, a2, q, eps, Q);
       } else if (!out) rotate_directors_lean(A.sincg, A.cosch, a0, a1, a2, q, eps, Q);
       else rotate_directors_ref<D>(a0, a1, a2, Q);
@@ -649,7 +653,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         bend_out = bend_out || (vor_ok && !(tr > D(2.0)));   // cos(theta) <= 1/2
         u_ref = (F)fma(D(-0.25), tr, D(0.75 + 0.5e-10));     // sin^2(theta'/2), for the reference map
       }
-      if (FASTONLY) dom_bad = dom_bad || bend_out;
+      if (FASTONLY && bend_out) dom_bad |= 2;
       F fs;
       if constexpr (MULTI) {
         const D g = theta_over_sin(Z.poly, u_ref);
@@ -719,7 +723,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       F cw0, cw2;
       {
         const bool out = out_of_range(em1, (CONTACT || LAPL || SPL) ? A.lim_em1c_hi : A.lim_em1_hi, A.limf_em1);
-        if (FASTONLY) dom_bad = dom_bad || (out && elem_ok);
+        if (FASTONLY && out && elem_ok) dom_bad |= 4;
         if (FASTONLY || !out) {
           if constexpr (CONTACT || LAPL || SPL) {   // harder dampers, larger stretches: degree 6, |z| <= kLeanExpZc
             F p0 = fma(Z.cwc[0][6], em1, Z.cwc[0][5]), p2 = fma(Z.cwc[1][6], em1, Z.cwc[1][5]);
@@ -1066,9 +1070,12 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       if (FASTONLY) {
         if (tid < 256) sh_dom[tid] = 0;
         __syncthreads();
-        if (live && dom_bad) atomicOr(&sh_dom[r], 1);
+        if (live && dom_bad) atomicOr(&sh_dom[r], dom_bad);
         __syncthreads();
-        if (active && lead && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
+        if (active && lead && sh_dom[r] != 0 && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) {
+          atomicAdd(A.redo_count, 1ULL);
+          for (int b = 0; b < 3; b++) if (sh_dom[r] >> b & 1) atomicAdd(A.redo_count + 1 + b, 1ULL);
+        }
       }
       D *sc = A.sk_scratch + (size_t)p * SCR * NT;
 #pragma unroll
@@ -1087,11 +1094,14 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     if (FASTONLY) {    // env-level OR of the range flags; a flagged env keeps its pre-launch state in global memory
       if (tid < 256) sh_dom[tid] = 0;
       __syncthreads();
-      if (live && dom_bad) atomicOr(&sh_dom[r], 1);
+      if (live && dom_bad) atomicOr(&sh_dom[r], dom_bad);
       __syncthreads();
       // (a part of this item run by the previous slot may have flagged the env already)
       redo = live && (sh_dom[r] != 0 || A.redo[env] != 0);
-      if (redo && lead && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) atomicAdd(A.redo_count, 1ULL);
+      if (redo && lead && atomicExch(&A.redo[env], 1) == 0 && A.redo_count) {
+        atomicAdd(A.redo_count, 1ULL);     // [0] env-steps handed over, [1..3] by cause (an env can count under several)
+        for (int b = 0; b < 3; b++) if (sh_dom[r] >> b & 1) atomicAdd(A.redo_count + 1 + b, 1ULL);
+      }
     }
     constexpr int RS = NT + 2;
     if (MIXED) {       // edge vectors of the final FP64 positions: the strain state the next launch starts from

@@ -716,8 +716,8 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       (e = cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (e = cudaMalloc(&h->redo, n_env * sizeof(int))) != cudaSuccess ||
       (e = cudaMemset(h->redo, 0, n_env * sizeof(int))) != cudaSuccess ||
-      (e = cudaMalloc(&h->redo_count, sizeof(unsigned long long))) != cudaSuccess ||
-      (e = cudaMemset(h->redo_count, 0, sizeof(unsigned long long))) != cudaSuccess ||
+      (e = cudaMalloc(&h->redo_count, 4 * sizeof(unsigned long long))) != cudaSuccess ||     // [0] total, [1..3] by cause (lean kernel)
+      (e = cudaMemset(h->redo_count, 0, 4 * sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaMallocHost(&h->h_redo_count, sizeof(unsigned long long))) != cudaSuccess ||
       (e = cudaEventCreateWithFlags(&h->pair_event, cudaEventDisableTiming)) != cudaSuccess ||
       (e = cudaMemset(h->state, 0, state_bytes)) != cudaSuccess) {
@@ -833,15 +833,26 @@ int sr_obs_dim(const sr_handle *h) { return h ? h->obs_dim : 0; }
 int sr_action_dim(const sr_handle *h) { return h ? h->action_dim : 0; }
 int sr_init_dim(const sr_handle *h) { return h ? h->init_dim : 0; }
 int64_t sr_launch_count(const sr_handle *h) { return h ? h->launches : 0; }
-int64_t sr_fallback_count(const sr_handle *h) {
-  if (!h || !h->redo_count) return 0;
-  unsigned long long v = 0;
+static void read_fallback_counters(const sr_handle *h, unsigned long long (&v)[4]) {
+  for (int i = 0; i < 4; i++) v[i] = 0;
+  if (!h || !h->redo_count) return;
   int prev = 0;
   cudaGetDevice(&prev); cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
-  cudaMemcpy(&v, h->redo_count, sizeof(v), cudaMemcpyDeviceToHost);
+  cudaMemcpy(v, h->redo_count, sizeof(v), cudaMemcpyDeviceToHost);
   cudaSetDevice(prev);
-  return (int64_t)v;
+}
+int64_t sr_fallback_count(const sr_handle *h) {
+  unsigned long long v[4];
+  read_fallback_counters(h, v);
+  return (int64_t)v[0];
+}
+int sr_fallback_causes(const sr_handle *h, int64_t out[3]) {
+  if (!h || !out) return fail(SR_E_INVALID, "sr_fallback_causes: null argument");
+  unsigned long long v[4];
+  read_fallback_counters(h, v);
+  for (int i = 0; i < 3; i++) out[i] = (int64_t)v[1 + i];
+  return SR_OK;
 }
 
 int sr_reset(sr_handle *h, const int32_t *env_idx_dev, int n, const double *init_dev, void *stream) {

@@ -235,6 +235,10 @@ int64_t sr_launch_count(const sr_handle *h);
 /* Env-steps the fast-only kernels handed to the safe kernel since sr_create (arguments outside the polynomial maps'
  * ranges; csrc/rod_kernel_lean.cuh).  Synchronises the handle's device: a diagnostic, not for the step loop. */
 int64_t sr_fallback_count(const sr_handle *h);
+/* The same count by cause, for the kernels of csrc/rod_kernel_lean.cuh (an env-step can count under several):
+ * out[0] rotation per kinematic update > 0.1 rad, out[1] bend between neighbouring elements beyond the log map's
+ * polynomial range, out[2] stretch beyond the rotational damper's polynomial range. */
+int sr_fallback_causes(const sr_handle *h, int64_t out[3]);
 
 /* Measure the device's FP64 FMA issue peak with a register-resident DFMA chain
  * (roofline denominator; not in MEASURED_PEAKS.json).  Returns TFLOP/s. */

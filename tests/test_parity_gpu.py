@@ -1451,28 +1451,45 @@ def test_two_handles_on_two_devices_agree():
 
 def test_split_schedule_keeps_every_lean_variant_bit_identical():
     """The lean kernel deals work by substep count: with more env groups than resident CTA slots an item is started by
-    one CTA and finished by another, its registers (and the travelling wave's phase, the assembly's head) travelling
-    through global scratch.  For every variant — contact, contact + muscle wave, assembly, filter + moving base — a
-    batch large enough to be split must give env 0 (and the last env) the bits it gets in a batch small enough not to
-    be: the hand-over is exact, and an env's result does not depend on where the schedule cut its item."""
+    one CTA and finished by another, its registers (and the travelling wave's phase, the assembly's head, the moving
+    base's command) travelling through global scratch.  For every variant — plain, contact, contact + muscle wave,
+    assembly, filter + moving base, spline torques — a batch of IDENTICAL envs large enough to be split must come out
+    identical in every env, wherever the schedule cut the env's item, and equal to a batch small enough not to be split.
+    (This is the test that caught the moving base being reset to its finalize-time anchor on resume.)"""
     import torch
     import gym_softrobot_b200 as g
     from gym_softrobot_b200.envs.arm_single import arm_contact_params, _ROD, _G
     from gym_softrobot_b200.envs.octo_flat import OctoFlatVectorEnv
+    from gym_softrobot_b200.envs.soft_pendulum import pendulum_init_params
     nat = _native()
     sm = torch.cuda.get_device_properties(0).multi_processor_count
+
+    def same_everywhere(t, group, name):
+        ref = t[:group]
+        n = t.shape[0] // group
+        eq = (t.reshape(n, group, *t.shape[1:]) == ref[None]).flatten(1).all(dim=1)
+        assert bool(eq.all()), f"{name}: {int((~eq).sum())} of {n} identical envs differ from env 0 (first: {int((~eq).nonzero()[0])})"
+        return ref.clone()
+
+    def plain(n_env):
+        h = make_pendulum_handle(n_env, nat.MATH_FAST)
+        h.reset_host(pendulum_init_params(np.full(n_env, u01_for_seed(42))))
+        a = np.full((n_env, 1), 7.5, dtype=np.float32)
+        for _ in range(3):
+            h.step_host(a, 333)
+        out = same_everywhere(h.state_tensor(), 1, "plain")
+        h.close()
+        return out
 
     def contact(n_env):
         h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=50, dt=7e-5, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
                        bc_kind=nat.BC_FREE, contact=arm_contact_params(), **_ROD)
         init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
         h.reset_host(init)
-        amp = np.where(np.arange(n_env) % 2 == 0, 8.0, -5.0)[:, None]      # env 0 and the last env of both batches: known shapes
-        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(amp * np.sin(np.pi * np.linspace(0, 1, 49))[None, :], device="cuda")
+        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(8.0 * np.sin(np.pi * np.linspace(0, 1, 49)), device="cuda")
         for _ in range(3):
             h.step_host(None, 333)
-        st = h.state_tensor()
-        out = (st[0].clone(), st[n_env - 2].clone())
+        out = same_everywhere(h.state_tensor(), 1, "contact")
         h.close()
         return out
 
@@ -1484,8 +1501,7 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
         o6, rew, term = env._scratch
         for _ in range(3):
             env.handle.step(None, 333, o6, rew, term)
-        st = env.handle.state_tensor()
-        out = (st[0].clone(), st[n_env - 1].clone(), mu[0].clone())
+        out = (same_everywhere(env.handle.state_tensor(), 1, "snake"), same_everywhere(mu, 1, "snake clock"))
         env.close()
         return out
 
@@ -1495,35 +1511,44 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
         o6, rew, term = env._scratch
         for _ in range(3):
             env.handle.step(None, 333, o6, rew, term)
-        st = env.handle.state_tensor()
-        out = (st[:8].clone(), st[-8:].clone(), env.handle.head_tensor()[0].clone(), env.handle.head_tensor()[-1].clone())
+        out = (same_everywhere(env.handle.state_tensor(), 8, "assembly arms"), same_everywhere(env.handle.head_tensor(), 1, "assembly head"))
         env.close()
         return out
 
     def filt(n_env):
+        from gym_softrobot_b200.envs.soft_pendulum_3d import pendulum3d_init_params
         env = g.make_vec("SoftPendulum3D-v0", n_env, autoreset=False); env.reset(seed=42)
-        a = torch.as_tensor(np.tile(np.array([[0.7, -0.4]], dtype=np.float32), (n_env, 1)), device="cuda")
-        for _ in range(3):
-            env.handle.step(a, 333, env.obs, env.reward, env.terminated)
-        st = env.handle.state_tensor()
-        out = (st[0].clone(), env.handle.aux_tensor()[0].clone(), env.obs[0].clone())
+        env.handle.reset(torch.as_tensor(pendulum3d_init_params(np.full(n_env, 0.37)), device="cuda").contiguous())   # every env alike
+        a = torch.as_tensor(np.tile(np.array([[1.0, -0.8]], dtype=np.float32), (n_env, 1)), device="cuda")
+        for _ in range(12):           # the base walks 12 mm away from its finalize-time anchor (element length 20 mm)
+            env.handle.step(a, 200, env.obs, env.reward, env.terminated)
+        out = (same_everywhere(env.handle.state_tensor(), 1, "filter"), same_everywhere(env.handle.aux_tensor(), 1, "filter base"),
+               same_everywhere(env.obs, 1, "filter obs"))
+        assert env.handle.fallback_count() == 0, env.handle.fallback_causes()
         env.close()
         return out
 
-    # (envs per CTA: 10 single rods of 51 threads in 512, 4 assemblies of 89 in 384; split needs more items than SMs)
-    for name, fn, small, big in (("contact", contact, 20, 10 * sm + 1500), ("snake", snake, 20, 10 * sm + 1500),
-                                 ("assembly", assembly, 8, 4 * sm + 300), ("filter", filt, 20, 10 * sm + 1500)):
+    def spline(n_env):
+        env = g.make_vec("SoftArmTracking-v0", n_env, autoreset=False); env.reset(seed=1)   # (the arm's build has no randomness)
+        pts, mags = env.handle.spline_tensors()
+        o6 = torch.empty((n_env, 6), dtype=torch.float32, device="cuda"); rew = torch.empty(n_env, dtype=torch.float64, device="cuda")
+        term = torch.empty(n_env, dtype=torch.uint8, device="cuda")
+        for k in range(3):
+            pts[:, :, :env.handle.cfg.spline_n_ctrl] = 0.3 - 0.25 * k
+            env.handle.step(None, 333, o6, rew, term)
+        out = (same_everywhere(env.handle.state_tensor(), 1, "spline"), same_everywhere(mags, 1, "spline cache"))
+        env.close()
+        return out
+
+    # (envs per CTA: 10 / 12 single rods in 512 threads, 4 assemblies of 89 threads in 384; a split needs more items than SMs)
+    for name, fn, small, big in (("plain", plain, 20, 10 * sm + 1500), ("contact", contact, 20, 10 * sm + 1500),
+                                 ("snake", snake, 20, 10 * sm + 1500), ("assembly", assembly, 8, 4 * sm + 300),
+                                 ("filter", filt, 20, 10 * sm + 1500), ("spline", spline, 24, 12 * sm + 1500)):
         a, b = fn(small), fn(big)
-        if name in ("contact",):
-            assert torch.equal(a[0], b[0]), name
-        elif name == "snake":
-            assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), name
-        elif name == "assembly":
-            assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]), name
-            assert torch.equal(b[0], b[1]) and torch.equal(b[2], b[3]), "identical envs at both ends of a split batch differ"
-        else:
-            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), name
-        assert all(torch.isfinite(t).all() for t in b), name
+        a, b = (a, b) if isinstance(a, tuple) else ((a,), (b,))
+        for ta, tb in zip(a, b):
+            assert torch.equal(ta, tb), f"{name}: split and unsplit batches differ"
+            assert torch.isfinite(tb).all(), name
 
 
 @pytest.mark.parametrize("normal", [(0.3, -0.2, 1.0), (0.0, -1.0, 0.0), (0.0, 0.0, -1.0)], ids=["oblique", "minus-y", "minus-z"])
