@@ -636,7 +636,8 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       // the first substep of a segment checks the trace once to rule out a state that starts beyond.
       F w2 = dot3(vec, vec);
       if (!vor_ok) w2 = F(0);
-      bool bend_out = out_of_range(w2, A.lim_bend_hi, A.limf_bend);
+      constexpr bool MIDBEND = CVAR == 1 || CVAR == 2;   // actuated arms on the plane: the 37-degree map
+      bool bend_out = out_of_range(w2, MIDBEND ? A.lim_bendm_hi : A.lim_bend_hi, A.limf_bend);
       F u_ref = F(0);
       if constexpr (MULTI) {
         // the 10-element arms of the octopus assemblies bend up to ~45 degrees per element: full-range map in
@@ -663,9 +664,16 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         // ascending powers of w2 (degree 9), pre-multiplied by -1/(2 D); even / odd halves interleaved.  (Contact
         // variant: indexed through a register the compiler cannot see through, so that the ten coefficients are
         // constant-bank loads inside the loop instead of hoisted, spilled and reloaded registers.)
-        const F *c = Z.bendw;
+        const F *c = MIDBEND ? Z.bendw_mid : Z.bendw;
         const F z = w2 * w2;
-        F pe = fma(c[8], z, c[6]), po = fma(c[9], z, c[7]);
+        F pe, po;
+        if constexpr (MIDBEND) {      // degree 13
+          pe = fma(c[12], z, c[10]); po = fma(c[13], z, c[11]);
+          pe = fma(pe, z, c[8]); po = fma(po, z, c[9]);
+          pe = fma(pe, z, c[6]); po = fma(po, z, c[7]);
+        } else {                      // degree 9
+          pe = fma(c[8], z, c[6]); po = fma(c[9], z, c[7]);
+        }
         pe = fma(pe, z, c[4]); po = fma(po, z, c[5]);
         pe = fma(pe, z, c[2]); po = fma(po, z, c[3]);
         pe = fma(pe, z, c[0]); po = fma(po, z, c[1]);

@@ -133,6 +133,13 @@ constexpr double kSmallExpZ = 1.0e-2;
                        0.00011867857307313035, 2.185318201165154e-05, 4.217099326139182e-06, 8.952330387027554e-07, \
                        1.2044932536293865e-07, 7.495667373584703e-08}
 constexpr double kNarrowBendW2 = 0.6144;
+// the same map on w2 <= 1.449 (37 degrees per element: actuated arms on the plane, where random +-22 actions push a few
+// per cent of the arms past 23 degrees every step), degree 13, 5.9e-16 (scripts/fit_poly.py bendw 1.449 13)
+#define SR_COEF_BENDW_MID {1.000000000033333, 0.04166666667010045, 0.004687499995989267, 0.0006975447215852305, \
+                           0.00011867875407192913, 2.1851702201916664e-05, 4.22290674826398e-06, 8.84413715124705e-07, \
+                           1.2412692505191034e-07, 9.612245287938274e-08, -3.7674586576030154e-08, 2.5214678884575354e-08, \
+                           -6.966131831983577e-09, 1.2127546473309148e-09}
+constexpr double kMidBendW2 = 1.449;
 // sin(t)/t = 1 + q g(q) and (1 - cos t)/t^2 = 1/2 + q h(q), q = t^2 <= kNarrowRotQ: degree-2 g, h with the leading
 // constants exact (instruction immediates in the lean kernel); 8.6e-16 / 1.7e-16 relative on the range
 #define SR_COEF_SINCG {-0.16666666666658056, 0.008333333178343767, -0.0001983713666611297}

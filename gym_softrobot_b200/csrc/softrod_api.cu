@@ -205,6 +205,7 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
   {
     const double cw2[] = SR_COEF_BENDW, sg[] = SR_COEF_SINCG, ch[] = SR_COEF_COSCH;
     for (int i = 0; i < 10; i++) A.bendw[i] = (T)(cw2[i] * (-0.5 / rl));
+    { const double cm[] = SR_COEF_BENDW_MID; for (int i = 0; i < 14; i++) A.bendw_mid[i] = (T)(cm[i] * (-0.5 / rl)); }
     for (int i = 0; i < 3; i++) { A.sincg[i] = sg[i]; A.cosch[i] = ch[i]; }
     // c_w^e = c_w exp(z), z = (e - 1) ln c_w, |z| <= kLeanExpZ: 1 + z + z^2/2 with the powers of ln c_w folded in
     double lmax = 0.0;
@@ -222,6 +223,7 @@ template <typename T> void fill_args(const sr_config &c, int stride, sr::RodArgs
     A.limf_em1 = lmax > 0.0 ? (float)fmin(sr::kLeanExpZ / lmax, 1e30) : 3.0e38f;
     A.lim_rot_hi = hi_word(sr::kNarrowRotQ);
     A.lim_bend_hi = hi_word(sr::kNarrowBendW2);
+    A.lim_bendm_hi = hi_word(sr::kMidBendW2);
     A.lim_em1_hi = lmax > 0.0 ? hi_word(fmin(sr::kLeanExpZ / lmax, 1e300)) : 0x7fefffff;   // no damper: any finite stretch
     A.lim_em1c_hi = lmax > 0.0 ? hi_word(fmin(sr::kLeanExpZc / lmax, 1e300)) : 0x7fefffff;
     A.half_rest_vor = (T)(0.5 * rl);

@@ -9,6 +9,8 @@ which = sys.argv[1] if len(sys.argv) > 1 else "pend3d"
 n_env = 4096
 if which == "pend3d":
     env = g.make_vec("SoftPendulum3D-v0", n_env); lo, hi, shape, dt, dl = -1.0, 1.0, (2,), 1e-4, 1.0 / 50
+elif which == "flat":
+    env = g.make_vec("OctoFlat-v0", n_env); lo, hi, shape, dt, dl = -22.0, 22.0, (24,), 7e-5, None
 else:
     env = g.make_vec("OctoArmSingle-v0", n_env); lo, hi, shape, dt, dl = -22.0, 22.0, (7,), 7e-5, None
 env.reset(seed=1)
