@@ -1596,3 +1596,59 @@ def test_rod_on_a_tilted_frictional_plane_vs_c_oracle(normal):
     height = (N[:, None] * x).sum(0)
     assert np.abs(height).max() < 5e-3 and np.abs((b[:, None] * x).sum(0)).max() > 1e-4
     h.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_randomized_contact_rods_vs_c_oracle(seed):
+    """The lean kernel's contact variant over its whole configuration space, drawn per seed: rod size (12..160 elements:
+    different CTA shapes and rods per CTA), material, plane orientation (arbitrary normal), free or clamped base, rest
+    curvature about both bending axes and twist, friction coefficients, slip tolerance, contact spring and damping, the
+    order of contact vs forcing, gravity pressing the rod onto the plane at an angle, and an initial slide.  CUDA vs the C
+    oracle, six fields, 2 x 200 substeps, 1e-9 (or 20 x the oracle's own one-ulp divergence, measured)."""
+    import torch
+    import rod_oracle as ro
+    nat = _native()
+    rng = np.random.default_rng(5000 + seed)
+    n = int(rng.choice([12, 25, 50, 63, 100, 160]))
+    L, r0 = float(rng.uniform(0.15, 0.4)), float(rng.uniform(0.006, 0.012))
+    E, rho = float(10 ** rng.uniform(5.5, 6.5)), float(rng.uniform(800, 1500))
+    dt = float(0.04 * (L / n) / np.sqrt(E / rho))
+    N = rng.normal(size=3); N /= np.linalg.norm(N)
+    a = np.cross(N, rng.normal(size=3)); a /= np.linalg.norm(a)
+    b = np.cross(N, a)
+    bc = [nat.BC_FREE, nat.BC_ONE_END_FIXED][seed % 2]
+    c = dict(plane_origin=list(-r0 * N), plane_normal=list(N), k=float(10 ** rng.uniform(1.5, 2.5)), nu=float(10 ** rng.uniform(0, 1.2)),
+             slip_velocity_tol=float(10 ** rng.uniform(-6, -3)), static_mu=list(rng.uniform(0.2, 1.0, 3)),
+             kinetic_mu=list(rng.uniform(0.1, 0.6, 3)), before_forcing=bool(rng.integers(2)))
+    grav = tuple(-9.81 * N + rng.uniform(-2, 2) * a + rng.uniform(-2, 2) * b)
+    damping = float(10 ** rng.uniform(-3, -1.5))
+    kw = dict(gravity=grav, damping_constant=damping, contact=c, bc_kind=bc)
+    n_env = 3
+    h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=n, dt=dt, base_length=L, base_radius=r0, density=rho, youngs_modulus=E, **kw)
+    init = np.zeros((n_env, 9)); init[:, 3:6] = a; init[:, 6:9] = N
+    h.reset_host(init)
+    s = np.linspace(0, 1, n - 1)
+    rk = np.stack([rng.uniform(-6, 6) * np.sin(np.pi * s * rng.integers(1, 3)), rng.uniform(-6, 6) * np.cos(np.pi * s), rng.uniform(-2, 2) * s])
+    h.rest_kappa_tensor()[:] = torch.as_tensor(rk, device="cuda")[None]
+    v0 = rng.uniform(-0.1, 0.1) * a + rng.uniform(-0.1, 0.1) * b
+    if bc == nat.BC_FREE:
+        h.fields()["velocity_collection"][:] = torch.as_tensor(v0, device="cuda")[None, :, None]
+
+    def make():
+        r = ro.OracleRod(n, [0, 0, 0], list(a), list(N), L, r0, rho, E, dt, **kw)
+        r.rest_kappa[...] = rk
+        if bc == nat.BC_FREE:
+            r.velocity_collection[...] = v0[:, None]
+        return r
+    names = ("position_collection", "velocity_collection", "director_collection", "omega_collection", "kappa", "tangents")
+    o = make()
+    done = 0
+    for chunk in (200, 200):
+        h.step_host(None, chunk); o.substeps(chunk); done += chunk
+        assert np.isfinite(o.position_collection).all(), "unstable random case (test generator problem)"
+        sens = one_ulp_divergence(make, lambda rod: rod.substeps(done), {k: getattr(o, k).copy() for k in names})
+        f = {k: v.cpu().numpy() for k, v in h.fields().items()}
+        floors = rate_floors(E, rho, L, n, r0, np.abs(o.position_collection).max())
+        for name in names:
+            assert_state_close(f[name][1], getattr(o, name), name, floors, f"seed={seed} n={n} bc={bc} substeps={done}", measured=sens)
+    h.close(); o.close()
