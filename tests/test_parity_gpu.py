@@ -1471,15 +1471,19 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
         assert bool(eq.all()), f"{name}: {int((~eq).sum())} of {n} identical envs differ from env 0 (first: {int((~eq).nonzero()[0])})"
         return ref.clone()
 
-    def plain(n_env):
-        h = make_pendulum_handle(n_env, nat.MATH_FAST)
+    def plain(n_env, dtype=None):
+        from gym_softrobot_b200.envs.soft_pendulum import _make_handle
+        h = make_pendulum_handle(n_env, nat.MATH_FAST) if dtype is None else _make_handle(n_env, 50, 1e-4, 0, nat.MATH_FAST, dtype)
         h.reset_host(pendulum_init_params(np.full(n_env, u01_for_seed(42))))
         a = np.full((n_env, 1), 7.5, dtype=np.float32)
         for _ in range(3):
             h.step_host(a, 333)
-        out = same_everywhere(h.state_tensor(), 1, "plain")
+        out = same_everywhere(h.state_tensor(), 1, "plain" if dtype is None else "plain, FP32 storage")
         h.close()
         return out
+
+    def plain_f32(n_env):
+        return plain(n_env, nat.DTYPE_F32)
 
     def contact(n_env):
         h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=50, dt=7e-5, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
@@ -1541,7 +1545,8 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
         return out
 
     # (envs per CTA: 10 / 12 single rods in 512 threads, 4 assemblies of 89 threads in 384; a split needs more items than SMs)
-    for name, fn, small, big in (("plain", plain, 20, 10 * sm + 1500), ("contact", contact, 20, 10 * sm + 1500),
+    for name, fn, small, big in (("plain", plain, 20, 10 * sm + 1500), ("plain-f32", plain_f32, 20, 10 * sm + 1500),
+                                 ("contact", contact, 20, 10 * sm + 1500),
                                  ("snake", snake, 20, 10 * sm + 1500), ("assembly", assembly, 8, 4 * sm + 300),
                                  ("filter", filt, 20, 10 * sm + 1500), ("spline", spline, 24, 12 * sm + 1500)):
         a, b = fn(small), fn(big)
