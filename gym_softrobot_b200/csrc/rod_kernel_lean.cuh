@@ -749,7 +749,6 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       }
       if (last && active) {
         // stale observables of the reference: last force evaluation
-#pragma unroll
         D tg_out[3] = {dx[0] * (D)ilg, dx[1] * (D)ilg, dx[2] * (D)ilg};
         if (CONTACT) to_lab(tg_out);
 #pragma unroll
