@@ -39,6 +39,9 @@ def translation_units():
         for cv in (1, 2, 3, 4, 5):
             tus.append((f"leanc{cv}_double_{nt}", "inst_lean.cu", ["-DSR_TU_T=double", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}", f"-DSR_TU_CONTACT={cv}"],
                         _COMMON + ["rod_kernel_lean.cuh"]))
+    for cv in (6, 7):     # plain / contact variant with the tip node folded into the last element's thread (n_elem = 512)
+        tus.append((f"leanc{cv}_double_512", "inst_lean.cu", ["-DSR_TU_T=double", "-DSR_TU_NT=512", "-DSR_TU_MINB=1", f"-DSR_TU_CONTACT={cv}"],
+                    _COMMON + ["rod_kernel_lean.cuh"]))
     for nt, minb in PACKED_SIZES:
         for t in ("double", "float"):
             for grp in (1, 2, 3):    # (the lean configs of both types run rod_kernel_lean.cuh)

@@ -1,5 +1,5 @@
 // inst_lean.cu — the lean kernel (rod_kernel_lean.cuh) for one storage type and CTA size:
-//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n> [-DSR_TU_CONTACT=1|2|3|4: contact variant without / with the muscle wave / for assemblies; 4: filter + moving base; 5: spline torques; FP64 only]
+//   -DSR_TU_T=double|float -DSR_TU_NT=<threads> -DSR_TU_MINB=<n> [-DSR_TU_CONTACT=1|2|3|4: contact variant without / with the muscle wave / for assemblies; 4: filter + moving base; 5: spline torques; 6 / 7: variants 0 / 1 with the tip node folded into the last thread; FP64 only]
 #include <atomic>
 #include "launch.cuh"
 #include "rod_kernel_lean.cuh"

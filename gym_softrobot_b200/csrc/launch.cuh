@@ -12,6 +12,7 @@ template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT,
 cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid, cudaStream_t s);
 
 constexpr int LEAN_SCR_CONTACT = 21;   // rows of a stream-K slot's hand-over scratch (contact variant: 18 + the travelling wave's sin, cos, time)
+constexpr int LEAN_SCR_FOLD = 27;      // folded-tip variants: + position and velocity of the tip node
 // lean kernel (rod_kernel_lean.cuh; T = storage type: double = FP64, float = mixed precision); grid / split schedule in A.sk_*
 template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> cudaError_t launch_lean_kernel(const RodArgs<T> &A, int grid, cudaStream_t s);
 // resident CTAs per SM of that instantiation on the current device (sizes the stream-K grid)

@@ -120,9 +120,14 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   constexpr bool LAPL = CVAR == 4;
   // 5: clamped / free rod + MuscleTorquesWithVaryingBetaSplines (SoftArmTracking-v0); safe variant only, see below
   constexpr bool SPL = CVAR == 5;
-  constexpr bool CONTACT = CVAR >= 1 && CVAR <= 3, MUS = CVAR == 2, MULTI = CVAR == 3;
+  // 6 / 7: variants 0 / 1 with the tip node folded into the last element's thread: a rod of n elements then takes n
+  // threads, not n + 1 — what lets the 512-element rod (BASELINE config 5) run in a 512-thread CTA with 128 registers
+  // instead of a 544-thread one capped at 96 (17 warps put five on one scheduler).  One rod per CTA.
+  constexpr bool FOLD = CVAR == 6 || CVAR == 7;
+  constexpr bool CONTACT = (CVAR >= 1 && CVAR <= 3) || CVAR == 7, MUS = CVAR == 2, MULTI = CVAR == 3;
   static_assert(CVAR == 0 || !MIXED, "the variants are FP64 only");
-  constexpr int SCR = CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
+  static_assert(!FOLD || LEAN_SCR_FOLD >= 27, "hand-over rows of the folded tip");
+  constexpr int SCR = FOLD ? LEAN_SCR_FOLD : CONTACT ? LEAN_SCR_CONTACT : LEAN_REC;   // rows of a slot's hand-over scratch
   using F = typename std::conditional<MIXED, float, double>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   D *rec = reinterpret_cast<D *>(smem_raw);            // {x0 x1 | x2 v0 | v1 v2 | Q0 Q1 | ... | Q6 Q7 | Q8 - | - -}
@@ -134,7 +139,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   __shared__ double sh_base[CVAR == 4 ? 128 : 1][4];   // filter variant: the moving base's command, per rod (rods of >= 9 threads)
 
   const int tid = threadIdx.x;
-  const int n = A.n_elem, stride = A.stride, tpr = n + 1;
+  const int n = A.n_elem, stride = A.stride, tpr = FOLD ? n : n + 1;
   // env group = the threads of one env: a rod, or (assemblies) n_rod rods of tpr threads + one head thread
   const int n_rod = MULTI ? A.n_rod : 1, has_head = MULTI ? A.has_head : 0;
   const int G = n_rod * tpr + has_head;
@@ -151,6 +156,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
   D *gb = sj;                                       // filter variant: ghost-padded records of the filtered rates
   if (tid < SNR) sn[SNR * NT + tid] = F(0);
   if (CONTACT && tid < 2) rec[LEAN_REC * NT + 16 + tid] = D(0);   // stage-1 contact load "left of element 0"
+  if (FOLD && tid < LEAN_REC) rec[LEAN_REC * NT + tid] = D(0);     // the folded tip's record: x, v published by the last thread, the rest finite
   __syncthreads();   // (the per-rod barriers below do not order this store against the other rods' reads)
 
   // Barriers: data only crosses threads of the same rod, so a substep's two synchronisations can be per rod
@@ -240,12 +246,15 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
     const int rod = env * n_rod + arm;                 // global rod slot in the state arrays
     int dom_bad = 0;                                   // which range a fast-only thread left: 1 rotation, 2 bend, 4 stretch (damper map)
     const bool elem_ok = active && j < n, vor_ok = active && j < n - 1;
-    const int t_next = elem_ok ? tid + 1 : tid;
-    const int t_next2 = vor_ok ? tid + 2 : t_next;
+    // (folded variants: the tip node's record is record NT, published by the last element's thread)
+    const int t_next = elem_ok ? ((FOLD && j == n - 1) ? NT : tid + 1) : tid;
+    const int t_next2 = vor_ok ? ((FOLD && j == n - 2) ? NT : tid + 2) : t_next;
     const int t_prev = (active && j > 0) ? tid - 1 : NT;
 
     D x[3] = {D(0), D(0), D(0)}, v[3] = {D(0), D(0), D(0)}, w[3] = {D(0), D(0), D(0)};
     D Q[9] = {D(1), D(0), D(0), D(0), D(1), D(0), D(0), D(0), D(1)};
+    D xt[3] = {D(0), D(0), D(0)}, vt[3] = {D(0), D(0), D(0)};   // folded variants: the tip node, integrated by the last element's thread
+    const bool is_last = FOLD && active && j == n - 1;
     ST *st = A.state + (size_t)(active ? rod : 0) * N_FIELDS * stride;
     const ST *bc = A.bc + (size_t)(active ? rod : 0) * BC_DIM;
     ST *hd = (MULTI && is_head && live) ? A.head + (size_t)env * HEAD_DIM : nullptr;   // the rigid head's state
@@ -267,6 +276,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 #pragma unroll
       for (int c = 0; c < 9; c++) Q[c] = sc[(6 + c) * NT + tid];
       if (CONTACT) { mus_S = sc[18 * NT + tid]; mus_C = sc[19 * NT + tid]; mus_t = sc[20 * NT + tid]; }
+      if (FOLD) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { xt[c] = sc[(21 + c) * NT + tid]; vt[c] = sc[(24 + c) * NT + tid]; }
+      }
       __syncthreads();
       if (tid == 0) A.sk_flag[p - 1] = 0;   // (graph-safe: the flag is back to 0 before the launch ends)
     } else {
@@ -280,6 +293,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 #pragma unroll
         for (int c = 0; c < 9; c++) Q[c] = (D)st[(F_DIR + c) * stride + j];  // slot n holds I
         if (CONTACT) { to_int(x); to_int(v); rows_to_int(Q); }
+        if (is_last) {
+#pragma unroll
+          for (int c = 0; c < 3; c++) { xt[c] = (D)st[(F_POS + c) * stride + n]; vt[c] = (D)st[(F_VEL + c) * stride + n]; }
+          if (CONTACT) { to_int(xt); to_int(vt); }
+        }
       }
       if (MULTI && hd) {     // (assemblies stand on a z-normal plane: sr_create checks, no rotation here)
 #pragma unroll
@@ -425,6 +443,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       D a0 = hw * w[0], a1 = hw * w[1], a2 = hw * w[2];
 #pragma unroll
       for (int c = 0; c < 3; c++) x[c] = fma(hh, v[c], x[c]);
+      if (FOLD && is_last) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) xt[c] = fma(hh, vt[c], xt[c]);
+      }
       if (LAPL && moving) { x[0] = sh_base[r][0]; x[1] = sh_base[r][1]; }
       D q = fma(a2, a2, fma(a1, a1, a0 * a0));
       const bool out = hi_abs(q) > A.lim_rot_hi;
@@ -476,6 +498,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         o[0] = make_double2(x[0], x[1]); o[1] = make_double2(x[2], v[0]); o[2] = make_double2(v[1], v[2]);
         o[3] = make_double2(Q[0], Q[1]); o[4] = make_double2(Q[2], Q[3]); o[5] = make_double2(Q[4], Q[5]);
         o[6] = make_double2(Q[6], Q[7]); rec[LEAN_REC * tid + 14] = Q[8];
+        if (FOLD && is_last) {
+          double2 *ot = reinterpret_cast<double2 *>(rec + LEAN_REC * NT);
+          ot[0] = make_double2(xt[0], xt[1]); ot[1] = make_double2(xt[2], vt[0]); ot[2] = make_double2(vt[1], vt[2]);
+        }
       }
       rod_sync();
 
@@ -636,7 +662,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
       // the first substep of a segment checks the trace once to rule out a state that starts beyond.
       F w2 = dot3(vec, vec);
       if (!vor_ok) w2 = F(0);
-      constexpr bool MIDBEND = CVAR == 1 || CVAR == 2;   // actuated arms on the plane: the 37-degree map
+      constexpr bool MIDBEND = CVAR == 1 || CVAR == 2 || CVAR == 7;   // actuated arms on the plane: the 37-degree map
       bool bend_out = out_of_range(w2, MIDBEND ? A.lim_bendm_hi : A.lim_bend_hi, A.limf_bend);
       F u_ref = F(0);
       if constexpr (MULTI) {
@@ -811,6 +837,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
           for (int i = 0; i < 3; i++) { fint[i] += fj[i]; tq[i] += tj[i]; }
         }
       }
+      D ct[3] = {D(0), D(0), D(0)};      // folded variants: the tip node's half of the plane's load on the last element
       if constexpr (CONTACT) {
         // forcing registered before the contact: the static-friction torque balance sees the muscle couple
         if (mus && !A.contact_before_forcing) {
@@ -925,6 +952,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
             const double2 l01 = *reinterpret_cast<const double2 *>(sn + SNR * t_prev);
             const D l2v = sn[SNR * t_prev + 2];
             fint[0] += D(0.5) * (p0 + l01.x); fint[1] += D(0.5) * (p1 + l01.y); fint[2] += D(0.5) * (c1[2] + l2v);
+            if (FOLD) { ct[0] = D(0.5) * p0; ct[1] = D(0.5) * p1; ct[2] = D(0.5) * c1[2]; }
           }
         }
         if (mus && A.contact_before_forcing) {
@@ -960,6 +988,11 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
           v[2] = D(0); w[0] = D(0); w[1] = D(0);
         }
       } else {
+        if (FOLD && is_last) {   // tip node (half a nodal mass): internal force -s_{n-1}, its share of the plane's load, gravity, damper
+          const D dtim_tip = (D)A.dt_inv_mass * c_cv * D(2);
+#pragma unroll
+          for (int i = 0; i < 3; i++) vt[i] = fma(ct[i] - (D)sfl[i], dtim_tip, fma(vt[i], c_cv, (D)A.gdt_cv[i]));
+        }
         // v <- c_v (v + dt f/m + dt g): the translational damper folded into the update (FP64 accumulation)
         v[0] = fma((D)fint[0], dtim_cv, fma(v[0], c_cv, base0));
         v[1] = fma((D)fint[1], dtim_cv, fma(v[1], c_cv, MIXED ? A.k_gdt_cv[1] : (D)A.gdt_cv[1]));
@@ -1090,6 +1123,10 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 #pragma unroll
       for (int c = 0; c < 9; c++) sc[(6 + c) * NT + tid] = Q[c];
       if (CONTACT) { sc[18 * NT + tid] = mus_S; sc[19 * NT + tid] = mus_C; sc[20 * NT + tid] = mus_t; }
+      if (FOLD) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { sc[(21 + c) * NT + tid] = xt[c]; sc[(24 + c) * NT + tid] = vt[c]; }
+      }
       __threadfence();
       __syncthreads();
       if (tid == 0) { *(volatile int *)(A.sk_flag + p) = 1; }
@@ -1143,6 +1180,19 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         for (int c = 0; c < 3; c++) st[(F_OMEGA + c) * stride + j] = (ST)w[c];
 #pragma unroll
         for (int c = 0; c < 9; c++) st[(F_DIR + c) * stride + j] = (ST)Q[c];
+      }
+      if (FOLD && is_last) {
+        if (CONTACT) { to_lab(xt); to_lab(vt); }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          st[(F_POS + c) * stride + n] = (ST)xt[c];
+          st[(F_VEL + c) * stride + n] = (ST)vt[c];
+          bad = bad || (xt[c] != xt[c]) || (vt[c] != vt[c]);
+        }
+        if (A.model == MODEL_ROD) {
+          float *o = A.obs + (size_t)env * A.obs_dim;
+          for (int c = 0; c < 3; c++) { o[c] = (float)xt[c]; o[3 + c] = (float)vt[c]; }
+        }
       }
     }
     // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)

@@ -303,8 +303,8 @@ int launch_packed_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
 // count and every slot gets the same number of item-substeps (rod_kernel_lean.cuh); partial items travel through
 // sk_scratch.  The fallback launch (redo_filter) visits flagged envs only and keeps one CTA per item.
 template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> int launch_lean_impl(sr_handle *h, sr::RodArgs<T> &A, cudaStream_t s) {
-  const bool multi = CONTACT == 3;
-  const int group = (multi ? A.n_rod : 1) * (A.n_elem + 1) + (multi ? A.has_head : 0);
+  const bool multi = CONTACT == 3, fold = CONTACT == 6 || CONTACT == 7;   // (fold: the tip node lives in the last element's thread)
+  const int group = fold ? A.n_elem : (multi ? A.n_rod : 1) * (A.n_elem + 1) + (multi ? A.has_head : 0);
   const int rods_per_cta = NT / group;   // env groups per CTA
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the lean kernel");
   const int items = (A.n_env + rods_per_cta - 1) / rods_per_cta;
@@ -315,7 +315,7 @@ template <typename T, int NT, int MINB, bool FASTONLY, int CONTACT = 0> int laun
     const int a = sr::lean_ctas_per_sm<T, NT, MINB, true, CONTACT>(), b = sr::lean_ctas_per_sm<T, NT, MINB, false, CONTACT>();
     h->sk_slots = prop.multiProcessorCount * (a < b ? a : b);
     if (h->sk_slots < 1) return fail(SR_E_CUDA, "lean kernel: occupancy query failed");
-    SR_CUDA(cudaMalloc(&h->sk_scratch, (size_t)h->sk_slots * sr::LEAN_SCR_CONTACT * NT * sizeof(double)));
+    SR_CUDA(cudaMalloc(&h->sk_scratch, (size_t)h->sk_slots * sr::LEAN_SCR_FOLD * NT * sizeof(double)));
     SR_CUDA(cudaMalloc(&h->sk_flag, (size_t)h->sk_slots * sizeof(int)));
     SR_CUDA(cudaMemset(h->sk_flag, 0, (size_t)h->sk_slots * sizeof(int)));
   }
@@ -538,6 +538,14 @@ template <typename T> int dispatch_packed(sr_handle *h, sr::RodArgs<T> &A, cudaS
         case 384: return launch_lean_pair<T, 384, 1, 4>(h, A, s);
         default: return launch_lean_pair<T, 256, 2, 4>(h, A, s);
       }
+    }
+    // a rod of exactly 512 elements: 512 threads with the tip node folded into the last one (128 registers) instead of
+    // 513 threads in a 544-thread CTA (96 registers); SOFTROD_LEAN_FOLD=0 switches back (A/B)
+    static int fold_off = -1;
+    if (fold_off < 0) { const char *e = getenv("SOFTROD_LEAN_FOLD"); fold_off = (e && atoi(e) == 0) ? 1 : 0; }
+    if (!fold_off && A.n_elem == 512 && A.model == sr::MODEL_ROD && !A.muscle_on) {
+      if (is_lean_contact_config(A)) return launch_lean_pair<T, 512, 1, 7>(h, A, s);
+      if (is_lean_config(A)) return launch_lean_pair<T, 512, 1, 6>(h, A, s);
     }
     if (is_lean_contact_config(A)) {
       const int nt = lean_threads_setting(h->cfg.n_elem);

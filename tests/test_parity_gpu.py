@@ -285,7 +285,8 @@ def _tilted_init(n_env, seed=42, max_deg=5.0):
 
 
 @pytest.mark.parametrize("n_elem,dt,radius", [(100, 5e-5, 0.025), (20, 1e-4, 0.05), (63, 5e-5, 0.03), (200, 2e-5, 0.025),
-                                              (3, 1e-4, 0.05), (4, 1e-4, 0.05), (255, 1e-5, 0.01), (1023, 2e-6, 0.004)])
+                                              (3, 1e-4, 0.05), (4, 1e-4, 0.05), (255, 1e-5, 0.01), (1023, 2e-6, 0.004),
+                                              (512, 5e-6, 0.008)])     # 512: the folded-tip variant of the lean kernel
 def test_generic_rod_vs_oracle(n_elem, dt, radius):
     """BASELINE config 3 family: clamped rod (OneEndFixedBC) + gravity + analytical damping, no action."""
     import rod_oracle as ro
@@ -1497,6 +1498,19 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
         h.close()
         return out
 
+    def fold(n_env):     # 512 elements: one rod per CTA, the tip node folded into the last thread and handed over with it
+        h = nat.Handle(model=nat.MODEL_ROD, n_env=n_env, n_elem=512, dt=5e-6, gravity=(0.0, 0.0, _G), damping_constant=1e-2,
+                       bc_kind=nat.BC_FREE, contact={**arm_contact_params(), "plane_origin": [0.0, 0.0, -0.005]}, base_length=1.0,
+                       base_radius=0.005, density=1000.0, youngs_modulus=1e6)
+        init = np.zeros((n_env, 9)); init[:, 3] = 1.0; init[:, 8] = 1.0
+        h.reset_host(init)
+        h.rest_kappa_tensor()[:, 0, :] = torch.as_tensor(3.0 * np.sin(np.linspace(0, 3 * np.pi, 511)), device="cuda")
+        for _ in range(3):
+            h.step_host(None, 133)
+        out = same_everywhere(h.state_tensor(), 1, "folded tip")
+        h.close()
+        return out
+
     def snake(n_env):
         env = g.make_vec("ContinuumSnake-v0", n_env, autoreset=False); env.reset()
         mu = env.handle.muscle_tensor()
@@ -1546,7 +1560,7 @@ def test_split_schedule_keeps_every_lean_variant_bit_identical():
 
     # (envs per CTA: 10 / 12 single rods in 512 threads, 4 assemblies of 89 threads in 384; a split needs more items than SMs)
     for name, fn, small, big in (("plain", plain, 20, 10 * sm + 1500), ("plain-f32", plain_f32, 20, 10 * sm + 1500),
-                                 ("contact", contact, 20, 10 * sm + 1500),
+                                 ("contact", contact, 20, 10 * sm + 1500), ("fold", fold, 3, sm + 61),
                                  ("snake", snake, 20, 10 * sm + 1500), ("assembly", assembly, 8, 4 * sm + 300),
                                  ("filter", filt, 20, 10 * sm + 1500), ("spline", spline, 24, 12 * sm + 1500)):
         a, b = fn(small), fn(big)
