@@ -80,7 +80,9 @@ __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], con
 constexpr int LEAN_REC = 18;        // exchange record per thread (doubles), 144-byte stride: conflict-free LDS.128
 constexpr int LEAN_JREC = 10;      // assemblies: joint record of an arm's first thread {reaction force, couple on the head, couple on element 0, -}
 // filter variant: records of 6 doubles with 6 ghost records on either side of every rod (rods of >= 9 threads)
-constexpr int lean_ghost_records(int nt) { return nt + 12 * (nt / 9) + 16; }
+// (8 ghost records per side, 6 used: a rod's records then start a multiple of 8 records = 96 words after where the
+// previous rod's would continue, so a quarter-warp that straddles two rods still hits eight distinct 4-bank groups)
+constexpr int lean_ghost_records(int nt) { return nt + 16 * (nt / 9) + 16; }
 constexpr int lean_smem_words(int nt, int cvar = 0) {
   return (LEAN_REC + 6 + (cvar == 3 ? LEAN_JREC : 0)) * (nt + 2) + (cvar == 4 ? 6 * lean_ghost_records(nt) : 0);
 }
@@ -1042,7 +1044,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
 #pragma unroll
               for (int c = 0; c < 6; c++) g[c] = ((-rv[c] - lv[c]) + D(2) * mv[c]) * D(0.25);
             }
-            D *slot = gb + 6 * (r * (tpr + 12) + 6 + j);
+            D *slot = gb + 6 * (r * (tpr + 16) + 8 + j);
             {
               double2 *o = reinterpret_cast<double2 *>(slot);
               if (j < n) { o[0] = make_double2(g[0], g[1]); o[1] = make_double2(g[2], g[3]); o[2] = make_double2(g[4], g[5]); }
