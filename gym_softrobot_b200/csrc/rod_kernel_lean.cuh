@@ -1,5 +1,8 @@
-// rod_kernel_lean.cuh — the headline kernel: FP64, single rod per env, no contact / filter / joints / forcing
-// (SoftPendulum-v0 and plain rods: BASELINE configs 2 and 3), sm_100a.
+// rod_kernel_lean.cuh — the product kernel, sm_100a.  Variant 0 (template parameter CVAR) is the headline: FP64 or
+// FP32 storage, single rod per env, no contact / filter / joints / forcing (SoftPendulum-v0 and plain rods: BASELINE
+// configs 2 and 3).  Variants 1-7 put the other models on the same skeleton (see the comment at the kernel):
+// 1 plane contact + rest curvature, 2 + travelling-wave muscle, 3 assemblies (arms + rigid head + joints), 4 Laplace
+// filter + moving base, 5 spline muscle torques, 6 / 7 = 0 / 1 with the tip node folded into the last thread.
 //
 // Same mapping as rod_kernel_packed.cuh (one thread per node/element, rods packed back to back across a
 // 256-thread CTA, state in registers for the whole launch, neighbour data through array-of-structures
