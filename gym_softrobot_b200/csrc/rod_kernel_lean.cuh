@@ -45,17 +45,21 @@ __device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7
 
 // Q <- R Q with R = I + A K + B K^2, A = sin(t)/t = 1 + q g(q), B = (1 - cos t)/t^2 = 1/2 + q h(q), q = t^2 <= 0.01
 // (g, h: SR_COEF_SINCG / SR_COEF_COSCH, leading constants exact so that they are instruction immediates).  The
-// reference's guard (axis = a / (|a| + 1e-14)) multiplies A by rho and B by rho^2, rho = 1 - d,
-// d = eps / sqrt(q + eps^2) ~ 1e-10; A rho = A - d (1 - q/6 + ..) and B rho^2 = B - d (1 - q/12 + ..) to first order
-// in d, and dropping d q / 6 changes the guard's own 1e-10 effect by a relative 1e-3: the guard becomes a subtraction
-// folded into the constant terms of the two Horner chains, off the critical path.  (The 4e-28 under the root only
-// keeps d finite at q = 0, where the rotation vanishes anyway.)
+// reference's guard (axis = a / (|a| + eps)) multiplies A by rho and B by rho^2, rho = |a| / (|a| + eps) = 1 - d with
+// d = eps / (|a| + eps) EXACTLY — two MUFU approximations are enough, d only needs 1e-6 relative.  (Round 1 used the
+// expansion d ~ eps / |a|: fine at 1e-10, but a rod that starts from exact rest passes through |a| ~ 1e-14 in its first
+// ten substeps, where the expansion is off by tens of per cent of a 1e-14 rad rotation; the 1e-14 rad of director
+// error it left next to a clamp then rang through the rod as 2e-10 rad/s of omega — 2e-9 of |omega| when the test
+// looked, scripts/diag_omega.py.)  A rho = A - A d is one FMA; B rho^2 = B - d (1 - q/12 + ..) stays first order: it
+// multiplies K^2 = O(|a|^2), so its guard matters to O(eps |a|).
 __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], const double (&ch)[3], double a0, double a1,
                                                       double a2, double q, double eps, double (&Q)[9]) {
-  const double d = eps * rsqrt_approx(q + 4e-28);
+  const double s = q * rsqrt_approx(q + 1e-300);       // |a| (0 at q = 0)
+  const double d = eps * rcp_approx(s + eps);
   double pa = fma(cg[2], q, cg[1]), pb = fma(ch[2], q, ch[1]);
   pa = fma(pa, q, cg[0]); pb = fma(pb, q, ch[0]);
-  const double A = fma(pa, q, 1.0 - d), B = fma(pb, q, 0.5 - d);
+  const double A1 = fma(pa, q, 1.0), B = fma(pb, q, 0.5 - d);
+  const double A = fma(-A1, d, A1);
   const double Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
   const double Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
   double D[9];
