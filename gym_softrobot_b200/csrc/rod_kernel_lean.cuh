@@ -50,15 +50,14 @@ __device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7
 // expansion d ~ eps / |a|: fine at 1e-10, but a rod that starts from exact rest passes through |a| ~ 1e-14 in its first
 // ten substeps, where the expansion is off by tens of per cent of a 1e-14 rad rotation; the 1e-14 rad of director
 // error it left next to a clamp then rang through the rod as 2e-10 rad/s of omega — 2e-9 of |omega| when the test
-// looked, scripts/diag_omega.py.)  A rho = A - A d is one FMA; B rho^2 = B - d (1 - q/12 + ..) stays first order: it
-// multiplies K^2 = O(|a|^2), so its guard matters to O(eps |a|).
+// looked, scripts/diag_omega.py.)  A rho = A - A d is one FMA.  B rho^2 multiplies K^2 = O(|a|^2): its guard changes the
+// rotation by |a|^2 d <= eps |a| <= 1e-15 rad per update and is left out.
 __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], const double (&ch)[3], double a0, double a1,
                                                       double a2, double q, double eps, double (&Q)[9]) {
-  const double s = q * rsqrt_approx(q + 1e-300);       // |a| (0 at q = 0)
-  const double d = eps * rcp_approx(s + eps);
+  const double d = eps * rcp_approx(fma(q, rsqrt_approx(q + 1e-300), eps));   // |a| = q / sqrt(q)  (0 at q = 0)
   double pa = fma(cg[2], q, cg[1]), pb = fma(ch[2], q, ch[1]);
   pa = fma(pa, q, cg[0]); pb = fma(pb, q, ch[0]);
-  const double A1 = fma(pa, q, 1.0), B = fma(pb, q, 0.5 - d);
+  const double A1 = fma(pa, q, 1.0), B = fma(pb, q, 0.5);
   const double A = fma(-A1, d, A1);
   const double Aa0 = A * a0, Aa1 = A * a1, Aa2 = A * a2;
   const double Ba0 = B * a0, Ba1 = B * a1, Ba2 = B * a2;
