@@ -54,7 +54,7 @@ __device__ __forceinline__ int hi_abs(double x) { return __double2hiint(x) & 0x7
 // rotation by |a|^2 d <= eps |a| <= 1e-15 rad per update and is left out.
 __device__ __forceinline__ void rotate_directors_lean(const double (&cg)[3], const double (&ch)[3], double a0, double a1,
                                                       double a2, double q, double eps, double (&Q)[9]) {
-  const double d = eps * rcp_approx(fma(q, rsqrt_approx(q + 1e-300), eps));   // |a| = q / sqrt(q)  (0 at q = 0)
+  const double d = eps * rcp_approx(fma(q, rsqrt_approx(q), eps));   // |a| = q / sqrt(q); the caller's q carries +1e-300
   double pa = fma(cg[2], q, cg[1]), pb = fma(ch[2], q, ch[1]);
   pa = fma(pa, q, cg[0]); pb = fma(pb, q, ch[0]);
   const double A1 = fma(pa, q, 1.0), B = fma(pb, q, 0.5);
@@ -456,7 +456,7 @@ rod_lean_kernel(const __grid_constant__ RodArgs<ST> A) {
         for (int c = 0; c < 3; c++) xt[c] = fma(hh, vt[c], xt[c]);
       }
       if (LAPL && moving) { x[0] = sh_base[r][0]; x[1] = sh_base[r][1]; }
-      D q = fma(a2, a2, fma(a1, a1, a0 * a0));
+      D q = fma(a2, a2, fma(a1, a1, fma(a0, a0, D(1e-300))));   // (+1e-300: rsqrt(q) below stays finite at rest)
       const bool out = hi_abs(q) > A.lim_rot_hi;
       if (FASTONLY) {
         if (out) dom_bad |= 1;
