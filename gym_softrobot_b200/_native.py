@@ -49,6 +49,8 @@ class SrConfig(C.Structure):
         ("spline_dir_mask", C.c_int32), ("spline_n_ctrl", C.c_int32),
         ("spline_scale", C.c_double), ("spline_max_rate", C.c_double),
         ("tip_radius", C.c_double), ("sucker_on", C.c_int32), ("sucker_index", C.c_int32),
+        ("taper_node_mean", C.c_int32), ("tm_muscle_on", C.c_int32),
+        ("tm_max_stress", C.c_double), ("tm_radius_ref", C.c_double),
     ]
 
 
@@ -100,6 +102,8 @@ def load_library():
     L.sr_get_rest_kappa.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_get_sucker.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_get_ext_loads.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    L.sr_get_sucker_index.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sr_get_tm_activation.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_get_muscle.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_spline.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_spline_basis.argtypes = [C.c_int32, C.c_double, C.c_void_p]
@@ -177,7 +181,7 @@ class Handle:
                  point_force_on_base=False, damping_before_constraints=False, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
                  base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None, spline=None,
-                 tip_radius=0.0, sucker_index=None):
+                 tip_radius=0.0, sucker_index=None, taper_node_mean=False, tm_muscle=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -221,6 +225,10 @@ class Handle:
         cfg.tip_radius = float(tip_radius)
         if sucker_index is not None:
             cfg.sucker_on, cfg.sucker_index = 1, int(sucker_index)
+        cfg.taper_node_mean = int(taper_node_mean)
+        if tm_muscle is not None:   # dict: max_stress, radius_ref (TransverseMuscle of create_es_muscle_layers)
+            cfg.tm_muscle_on = 1
+            cfg.tm_max_stress, cfg.tm_radius_ref = float(tm_muscle["max_stress"]), float(tm_muscle["radius_ref"])
         self.n_rod = max(1, n_rod)
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -380,6 +388,21 @@ class Handle:
         import torch
         ptr = C.c_void_p()
         _check(self._lib.sr_get_sucker(self._h, C.byref(ptr)))
+        ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod,), ts), device=f"cuda:{self.device}")
+
+    def sucker_index_tensor(self):
+        """torch view [n_env * n_rod] (int32) of the index each ControllableFixConstraint acts on (sr_get_sucker_index)."""
+        import torch
+        ptr = C.c_void_p()
+        _check(self._lib.sr_get_sucker_index(self._h, C.byref(ptr)))
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod,), "<i4"), device=f"cuda:{self.device}")
+
+    def tm_activation_tensor(self):
+        """torch view [n_env * n_rod] of the transverse-muscle activations (sr_get_tm_activation)."""
+        import torch
+        ptr = C.c_void_p()
+        _check(self._lib.sr_get_tm_activation(self._h, C.byref(ptr)))
         ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
         return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod,), ts), device=f"cuda:{self.device}")
 

@@ -191,6 +191,17 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
     }
     mass_j = tab[ET_MASS * es + min(j, n)]; mass_j1 = tab[ET_MASS * es + min(j + 1, n)];
   }
+  // COOMM TransverseMuscle (see the force block below): activation x (-max_stress x rest area), constant during a launch
+  T tm_gain = T(0);
+  if constexpr (VARY) {
+    if (A.tm_act && elem_ok) tm_gain = A.tm_act[rod] * A.elem_tab[ET_TM * A.stride + min(j, n - 1)];
+  }
+  // ControllableFixConstraint index of this rod: node / element it acts on (python indexing of arrays of n + 1 / n slots)
+  int sk_node = A.sucker_index, sk_elem = A.sucker_index;
+  if (A.sucker_idx && active) {
+    const int si = A.sucker_idx[rod];
+    sk_node = si < 0 ? si + n + 1 : si; sk_elem = si < 0 ? si + n : si;
+  }
   const auto &K = [&]() -> const auto & { if constexpr (VARY) return ec; else return A; }();
   const T dtim_cv = !active ? T(0) : VARY ? A.dt / mass_j * A.c_v : A.dt_inv_mass * A.c_v * ((j == 0 || j == n) ? T(2) : T(1));
   const T gmask = active ? T(1) : T(0);
@@ -462,6 +473,23 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int i = 0; i < 3; i++)
       nst[i] = (i == 2) ? fma(K.S_over_l[i], Qdx[i], -K.S[i]) : K.S_over_l[i] * Qdx[i];
+    if constexpr (VARY) {
+      // COOMM `ApplyMuscles` with the TransverseMuscle active (call sites /root/reference/gym_softrobot/envs/octopus/
+      // build.py:329-333, build_muscle_octopus.py:165-177, arm_push_env.py:198-209; the package itself is not in the
+      // reference tree: published model restated, oracle/rod_oracle.c:apply_tm_muscle).  Radial fibres on the centre
+      // line: normalised length 1/sqrt(e), area rest_area / e, force along nu = sigma + e3 = Q dx / l0 (|nu| = e):
+      //   n_m = a (-sigma_max) (A0 / e) h(1/sqrt(e)) nu / e,   h(l) = max(3.06 l^3 - 13.64 l^2 + 18.01 l - 6.44, 0).
+      // It enters like the rod's own stress resultant (Delta_h(Q^T n) on the nodes, (Q t e) x n l0 on the elements; the
+      // latter vanishes for n_m || nu), so e n_m joins nst[] ahead of the common 1/e.
+      if (tm_gain != T(0)) {
+        const T l = sqrt_(inv_e);
+        T hw = fma(fma(fma(T(3.06), l, T(-13.64)), l, T(18.01)), l, T(-6.44));
+        hw = hw > T(0) ? hw : T(0);
+        const T Fm = tm_gain * inv_e * hw * K.inv_rest_len;
+#pragma unroll
+        for (int i = 0; i < 3; i++) nst[i] = fma(Fm, Qdx[i], nst[i]);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
 #pragma unroll
@@ -882,10 +910,16 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       else { constrain_rates(); dampen(); }
       // ControllableFixConstraint ("sucker", envs/octopus/controllable_constraint.py:46-69): the rates of one node /
       // element index are scaled by 1 - reduction_ratio (per rod, 0 = released); registered after the dampers
-      if (A.sucker && active && j == A.sucker_index) {
+      if (A.sucker && active) {
         const T f = T(1) - A.sucker[rod];
+        if (j == sk_node) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) { v[i] *= f; w[i] *= f; }
+          for (int i = 0; i < 3; i++) v[i] *= f;
+        }
+        if (j == sk_elem) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) w[i] *= f;
+        }
       }
     }
 

@@ -73,7 +73,11 @@ template <typename T> struct RodArgs {
   // optional per-rod inputs (nullptr = off): ControllableFixConstraint ratios [n_rods] acting on index sucker_index;
   // external nodal forces (lab frame) / element couples (material frame) [n_rods][3][stride]; tapered-rod table
   const T *sucker; int sucker_index;
+  const int *sucker_idx;              // [n_rods] per-rod index (python indexing: -1 = last node / last element) or nullptr = sucker_index
   const T *ext_force, *ext_couple;
+  // COOMM TransverseMuscle under ApplyMuscles (tapered rods): per-rod scalar activation [n_rods] or nullptr = off; the
+  // per-element factor -max_stress * rest_muscle_area is row ET_TM of elem_tab
+  const T *tm_act;
   const T *elem_tab;                  // [ET_FIELDS][stride] element constants (VARY instantiations)
   // multi-rod environments (octopus: n_rod arms + one rigid Cylinder head joined by FixedJoint2Rigid,
   // envs/octopus/build.py:52-217, utils/custom_elastica/joint.py, constraint.py)
@@ -121,7 +125,7 @@ template <typename T> struct ElemConst {
   T rest_len, inv_rest_len, rest_vor, inv_rest_vor, S[3], S_over_l[3], B[3], J[3], Jinv[3], c_w[3], logc_w[3], vol_over_pi;
   int isotropic;
 };
-enum : int { ET_REST_LEN = 0, ET_REST_VOR, ET_S0, ET_S2, ET_B0, ET_B2, ET_J0, ET_J2, ET_LOGCW0, ET_LOGCW2, ET_VOL_PI, ET_MASS, ET_FIELDS };
+enum : int { ET_REST_LEN = 0, ET_REST_VOR, ET_S0, ET_S2, ET_B0, ET_B2, ET_J0, ET_J2, ET_LOGCW0, ET_LOGCW2, ET_VOL_PI, ET_MASS, ET_TM, ET_FIELDS };
 
 template <typename T, int EPL> struct Vec;
 template <> struct Vec<double, 1> { using type = double; };

@@ -48,6 +48,8 @@ struct sr_handle {
   double *muscle = nullptr; int muscle_dim = 0;
   double *spline = nullptr, *spline_tab = nullptr; int spline_dim = 0;
   void *sucker = nullptr, *ext_force = nullptr, *ext_couple = nullptr, *elem_tab = nullptr;
+  int32_t *sucker_idx = nullptr;   // per-rod ControllableFixConstraint index (python indexing)
+  void *tm_act = nullptr;          // per-rod TransverseMuscle activation
   int *redo = nullptr;   // per-env flags of the fast-only / fallback kernel pair
   unsigned long long *redo_count = nullptr, *h_redo_count = nullptr, pair_last_count = 0;
   cudaEvent_t pair_event = nullptr; bool pair_copy_pending = false;
@@ -679,6 +681,12 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     if (cfg->sucker_index < 0 || cfg->sucker_index >= cfg->n_elem)
       return fail(SR_E_INVALID, "sr_create: sucker_index must address an element (0 .. n_elem - 1)");
   }
+  if (cfg->taper_node_mean && !(cfg->tip_radius > 0.0))
+    return fail(SR_E_INVALID, "sr_create: taper_node_mean needs tip_radius > 0");
+  if (cfg->tm_muscle_on) {
+    if (!(cfg->tip_radius > 0.0) || !(cfg->tm_radius_ref > 0.0))
+      return fail(SR_E_INVALID, "sr_create: the transverse muscle is built for tapered rods (tip_radius > 0) and needs tm_radius_ref > 0");
+  }
   if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
     return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
@@ -760,7 +768,18 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   }
   if (cfg->sucker_on) {
     const size_t sb = n_rods * h->elem_size;
-    if ((e = cudaMalloc(&h->sucker, sb)) != cudaSuccess || (e = cudaMemset(h->sucker, 0, sb)) != cudaSuccess) {
+    std::vector<int32_t> idx(n_rods, cfg->sucker_index);
+    if ((e = cudaMalloc(&h->sucker, sb)) != cudaSuccess || (e = cudaMemset(h->sucker, 0, sb)) != cudaSuccess ||
+        (e = cudaMalloc(&h->sucker_idx, n_rods * sizeof(int32_t))) != cudaSuccess ||
+        (e = cudaMemcpy(h->sucker_idx, idx.data(), n_rods * sizeof(int32_t), cudaMemcpyHostToDevice)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
+  if (cfg->tm_muscle_on) {
+    const size_t sb = n_rods * h->elem_size;
+    if ((e = cudaMalloc(&h->tm_act, sb)) != cudaSuccess || (e = cudaMemset(h->tm_act, 0, sb)) != cudaSuccess) {
       std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
       sr_destroy(h);
       return fail(SR_E_ALLOC, m);
@@ -774,8 +793,17 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     const double G = cfg->shear_modulus > 0.0 ? cfg->shear_modulus : E / (2.0 * (1.0 + 0.5)), ac = 27.0 / 28.0;
     std::vector<double> tab((size_t)sr::ET_FIELDS * st, 1.0), rad(n), Bel0(n), Bel2(n), mel(n), J0(n), J2(n);
     const double stepr = n > 1 ? (cfg->tip_radius - cfg->base_radius) / (n - 1) : 0.0;
+    const double stepn = (cfg->tip_radius - cfg->base_radius) / n;
     for (int k = 0; k < n; k++) {
       rad[k] = (k == n - 1 && n > 1) ? cfg->tip_radius : k * stepr + cfg->base_radius;
+      if (cfg->taper_node_mean) {
+        // radius = np.linspace(base, tip, n + 1); element radius = mean of its two nodes (arm_push_env.py:161-175)
+        const double r0 = k * stepn + cfg->base_radius, r1 = (k + 1 == n) ? cfg->tip_radius : (k + 1) * stepn + cfg->base_radius;
+        rad[k] = (r0 + r1) / 2.0;
+      }
+      // TransverseMuscle(rest_muscle_area=(radius / radius_base)**2, max_muscle_stress) handing -max_stress to its base
+      // class (envs/octopus/build.py:329-333): the per-element factor of the muscle force
+      tab[sr::ET_TM * st + k] = cfg->tm_muscle_on ? -cfg->tm_max_stress * ((rad[k] / cfg->tm_radius_ref) * (rad[k] / cfg->tm_radius_ref)) : 0.0;
       const double A0 = PI * rad[k] * rad[k], I1 = A0 * A0 / (4.0 * PI), I3 = 2.0 * I1;
       J0[k] = I1 * cfg->density * rl; J2[k] = I3 * cfg->density * rl;
       Bel0[k] = E * I1; Bel2[k] = G * I3;
@@ -814,6 +842,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   h->a64.spline = h->spline; h->a64.spline_tab = h->spline_tab;
   h->a64.redo = h->redo;
   h->a64.sucker = (const double *)h->sucker; h->a64.sucker_index = cfg->sucker_index; h->a64.elem_tab = (const double *)h->elem_tab;
+  h->a64.sucker_idx = h->sucker_idx; h->a64.tm_act = (const double *)h->tm_act;
   h->a64.muscle = h->muscle;
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
@@ -821,6 +850,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   h->a32.spline = h->spline; h->a32.spline_tab = h->spline_tab;
   h->a32.redo = h->redo;
   h->a32.sucker = (const float *)h->sucker; h->a32.sucker_index = cfg->sucker_index;
+  h->a32.sucker_idx = h->sucker_idx; h->a32.tm_act = nullptr;
   h->a32.muscle = h->muscle;
   h->a32.state = (float *)h->state; h->a32.bc = (const float *)h->bc; h->a32.aux = (float *)h->aux;
   h->a32.action_dim = h->action_dim; h->a32.obs_dim = h->obs_dim; h->a32.head = (float *)h->head;
@@ -831,7 +861,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
-  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFree(h->sucker); cudaFree(h->ext_force); cudaFree(h->ext_couple); cudaFree(h->elem_tab); cudaFree(h->sk_scratch); cudaFree(h->sk_flag); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
+  cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFree(h->sucker); cudaFree(h->sucker_idx); cudaFree(h->tm_act); cudaFree(h->ext_force); cudaFree(h->ext_couple); cudaFree(h->elem_tab); cudaFree(h->sk_scratch); cudaFree(h->sk_flag); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
   cudaFreeHost(h->h_init);
@@ -1053,6 +1083,20 @@ int sr_get_sucker(sr_handle *h, void **ratio_dev) {
   return SR_OK;
 }
 
+int sr_get_sucker_index(sr_handle *h, int32_t **index_dev) {
+  if (!h || !index_dev) return fail(SR_E_INVALID, "sr_get_sucker_index: null argument");
+  if (!h->sucker_idx) return fail(SR_E_INVALID, "sr_get_sucker_index: handle was created without sucker_on");
+  *index_dev = h->sucker_idx;
+  return SR_OK;
+}
+
+int sr_get_tm_activation(sr_handle *h, void **activation_dev) {
+  if (!h || !activation_dev) return fail(SR_E_INVALID, "sr_get_tm_activation: null argument");
+  if (!h->tm_act) return fail(SR_E_INVALID, "sr_get_tm_activation: handle was created without tm_muscle_on");
+  *activation_dev = h->tm_act;
+  return SR_OK;
+}
+
 int sr_get_ext_loads(sr_handle *h, void **force_dev, void **couple_dev) {
   if (!h || !force_dev || !couple_dev) return fail(SR_E_INVALID, "sr_get_ext_loads: null argument");
   if (h->cfg.math != SR_MATH_FAST || h->cfg.model != SR_MODEL_ROD || h->cfg.laplace_filter_order != 0 ||
@@ -1123,6 +1167,8 @@ int sr_copy_from(sr_handle *dst, sr_handle *src, void *stream) {
     SR_CUDA(cp(rk, src->rest_kappa, n_rods * 3 * dst->stride * es));
   }
   if (src->sucker && dst->sucker) SR_CUDA(cp(dst->sucker, src->sucker, n_rods * es));
+  if (src->sucker_idx && dst->sucker_idx) SR_CUDA(cp(dst->sucker_idx, src->sucker_idx, n_rods * sizeof(int32_t)));
+  if (src->tm_act && dst->tm_act) SR_CUDA(cp(dst->tm_act, src->tm_act, n_rods * es));
   if (src->ext_force) {
     void *f = nullptr, *c = nullptr;
     int rc = sr_get_ext_loads(dst, &f, &c);

@@ -127,6 +127,17 @@ typedef struct sr_config {
    * dampers, velocity and angular velocity of node / element `sucker_index` of every rod are scaled by
    * 1 - reduction_ratio; the per-rod ratios (0 = released) are device data the caller writes (sr_get_sucker). */
   int32_t sucker_on, sucker_index;
+  /* 1: the taper is given on the NODES, np.linspace(base_radius, tip_radius, n_elem + 1), each element taking the mean of
+   * its two nodes (envs/octopus/arm_push_env.py:161-175,524-538); 0: np.linspace(base, tip, n_elem) on the elements. */
+  int32_t taper_node_mean;
+  /* COOMM `ApplyMuscles` with the `TransverseMuscle(rest_muscle_area=(radius / tm_radius_ref)**2,
+   * max_muscle_stress=tm_max_stress)` of create_es_muscle_layers (envs/octopus/build.py:292-338; registered at
+   * build_muscle_octopus.py:165-177, arm_push_env.py:198-209,601-606) evaluated every substep; tapered rods only.  The
+   * two longitudinal muscles of that layer set never receive a non-zero activation in OctoCrawl / OctoArmPush /
+   * OctoArmPullWeight and are not evaluated.  Per-rod scalar activations: sr_get_tm_activation.  coomm is not part of
+   * the reference tree: the published model is restated. */
+  int32_t tm_muscle_on;
+  double tm_max_stress, tm_radius_ref;
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -190,6 +201,13 @@ int sr_get_state(sr_handle *h, sr_state_view *out);
 int sr_set_state(sr_handle *h, const sr_state_view *src, void *stream);
 /* ControllableFixConstraint ratios, [n_env * n_rod_per_env] of the handle's element type (needs sucker_on). */
 int sr_get_sucker(sr_handle *h, void **ratio_dev);
+/* Per-rod index the ControllableFixConstraint acts on, int32 [n_env * n_rod_per_env], initialised to cfg.sucker_index;
+ * what `controller.index = ...` sets every env-step (crawl_env.py:239-241, arm_push_env.py:255-270).  Python indexing of
+ * the reference's arrays: i >= 0 scales node i and element i; i < 0 scales node n_elem + 1 + i and element n_elem + i. */
+int sr_get_sucker_index(sr_handle *h, int32_t **index_dev);
+/* Per-rod activation of the transverse muscle, [n_env * n_rod_per_env] of the handle's element type (needs tm_muscle_on);
+ * what `muscle_layers[2].apply_activation(a)` sets (crawl_env.py:242, arm_push_env.py:259,271). */
+int sr_get_tm_activation(sr_handle *h, void **activation_dev);
 /* Generic per-element external loads evaluated every substep as a forcing (what COOMM's ApplyMuscles would feed,
  * envs/octopus/build_muscle_octopus.py:171-176): nodal forces in the lab frame, [n_rods][3][stride] slots 0..n_elem,
  * and element couples in the material frame, [n_rods][3][stride] slots 0..n_elem-1, of the handle's element type;

@@ -439,6 +439,80 @@ def gen_soft_arm(seed=42, n=40, game_mode=1):
     print("soft_arm mode", game_mode, ":", rew[-1], obs[-1][8:11])
 
 
+COOMM_LABEL = ("unpinned (reference gym-softrobot code on restated PyElastica AND restated COOMM muscle model, "
+               "oracle/shims/elastica + oracle/shims/coomm; coomm 0.1.1 @ d33fa034 is not obtainable offline)")
+
+
+def gen_arm_push(env_id="OctoArmPush-v0", tag="octo_arm_push_v0", seed=42, n=6):
+    """OctoArmPush-v0 (discrete: 0 = hold the base + contract the transverse muscle, 1 = hold the tip + release),
+    OctoArmPush-v1 (continuous: sucker location, activation) and OctoArmPullWeight-v0 (the same arm dragging a rigid
+    cylinder through a FixedJoint2Rigid): tapered free arm, ControllableFixConstraint, COOMM ApplyMuscles
+    (/root/reference/gym_softrobot/envs/octopus/arm_push_env.py)."""
+    env = ref_loader.load_reference_env(env_id)
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    rod = e.shearable_rod
+    out = {"label": COOMM_LABEL, "seed": seed, "obs0": obs0, "step_skip": e.step_skip, "time_step": e.time_step,
+           "radius0": rod.radius.copy(), "mass": rod.mass.copy()}
+    head = getattr(e, "rigid_rod", None)
+
+    def snap(tagk):
+        pack(tagk, rod_state(rod), out)
+        if head is not None:
+            out[f"{tagk}/head/position"] = head.position_collection.copy()
+            out[f"{tagk}/head/velocity"] = head.velocity_collection.copy()
+            out[f"{tagk}/head/director"] = head.director_collection.copy()
+            out[f"{tagk}/head/omega"] = head.omega_collection.copy()
+
+    snap("state0")
+    acts, obs, rew, term, trunc, times = [], [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        if e.mode == 0:
+            a = i % 2 if i < 4 else int(a)        # the crawling gait first, then whatever the space samples
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr); times.append(info["time"])
+        snap(f"state{i + 1}")
+    out.update(actions=np.array(acts), obs=np.array(obs, dtype=np.float32), reward=np.array(rew, dtype=np.float64),
+               terminated=np.array(term), truncated=np.array(trunc), time=np.array(times))
+    np.savez_compressed(os.path.join(OUT, f"{tag}_seed{seed}.npz"), **out)
+    print(env_id, "rewards", rew, "tip x", rod.position_collection[0, -1])
+
+
+def gen_octo_crawl(seed=42, n=3):
+    """OctoCrawl-v0: build_octopus_muscles (eight tapered arms, light head, joints, BodyBoundaryCondition), one
+    ControllableFixConstraint per arm whose index / ratio the action moves, transverse-muscle activation per arm
+    (/root/reference/gym_softrobot/envs/octopus/crawl_env.py, build_muscle_octopus.py:70-179)."""
+    env = ref_loader.load_reference_env("OctoCrawl-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    out = {"label": COOMM_LABEL, "seed": seed, "obs0": obs0, "step_skip": e.step_skip, "time_step": e.time_step,
+           "n_elems": e.n_elems}
+
+    def snap(tag):
+        for a, rod in enumerate(e.shearable_rods):
+            pack(f"{tag}/arm{a}", rod_state(rod), out)
+        h = e.rigid_rod
+        out[f"{tag}/head/position"] = h.position_collection.copy()
+        out[f"{tag}/head/velocity"] = h.velocity_collection.copy()
+        out[f"{tag}/head/director"] = h.director_collection.copy()
+        out[f"{tag}/head/omega"] = h.omega_collection.copy()
+
+    snap("state0")
+    acts, obs, rew, term, trunc = [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr)
+        snap(f"state{i + 1}")
+    out.update(actions=np.array(acts, dtype=np.float32), obs=np.array(obs, dtype=np.float32),
+               reward=np.array(rew, dtype=np.float64), terminated=np.array(term), truncated=np.array(trunc))
+    np.savez_compressed(os.path.join(OUT, f"octo_crawl_seed{seed}.npz"), **out)
+    print("octo crawl:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
@@ -460,6 +534,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         gen_octo_cfg4()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "coomm":
+        gen_arm_push("OctoArmPush-v0", "octo_arm_push_v0")
+        gen_arm_push("OctoArmPush-v1", "octo_arm_push_v1")
+        gen_arm_push("OctoArmPullWeight-v0", "octo_arm_pull_weight", n=3)
+        gen_octo_crawl()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "soft_arm":
         gen_soft_arm(game_mode=1)
         gen_soft_arm(game_mode=2)
@@ -478,5 +558,9 @@ if __name__ == "__main__":
     gen_muscle_torques()
     gen_soft_arm(game_mode=1)
     gen_soft_arm(game_mode=2)
+    gen_arm_push("OctoArmPush-v0", "octo_arm_push_v0")
+    gen_arm_push("OctoArmPush-v1", "octo_arm_push_v1")
+    gen_arm_push("OctoArmPullWeight-v0", "octo_arm_pull_weight", n=3)
+    gen_octo_crawl()
     gen_snake()   # ~25 min of NumPy stepping
     gen_snake_perturbed()   # another ~25 min

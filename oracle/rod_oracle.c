@@ -39,8 +39,12 @@ struct ro_rod {
   /* derived (A.3) — refreshed only inside the force evaluation (A.6) */
   double *len, *tang, *dil, *vdil, *dil_rate, *sigma, *kappa;
   double *stress, *couple, *f_int, *t_int, *f_ext, *t_ext, *f_user, *t_user;
-  int n_sucker, sucker_idx[8];            /* ControllableFixConstraint: indices and ratios */
+  int n_sucker, sucker_idx[8], sucker_node[8]; /* ControllableFixConstraint: element / node indices and ratios */
   double sucker_ratio[8];
+  /* COOMM TransverseMuscle under ApplyMuscles (restated, see apply_tm_muscle) */
+  int tm_on;
+  double tm_max_stress, tm_radius_ref, tm_activation;
+  double *rest_radius;
   /* plugins */
   double fixed_pos[3], fixed_Q[9];
   double c_v, *c_w;                      /* AnalyticalLinearDamper coefficients */
@@ -508,6 +512,61 @@ static void phase_first_half(ro_rod *r, const double *bp) {
   constrain_values(r, bp);
 }
 
+/* ---- COOMM `ApplyMuscles` with one active `TransverseMuscle` ------------------------------------------
+ * Third-party: coomm 0.1.1, git rev d33fa034 of hanson-hschang/COOMM (branch refactor-numba-hotloops),
+ * pinned at /root/reference/uv.lock:172-179 — NOT in /root/reference and not obtainable offline.  PARITY
+ * UNPINNED: this restates the published model (Chang et al., "Energy-shaping control of a muscular octopus
+ * arm moving in three dimensions", Proc. R. Soc. A 2023, and the public COOMM package layout
+ * coomm/actuations/muscles/{muscle,transverse_muscle}.py) as recalled; anchored on the reference's call sites:
+ *   create_es_muscle_layers   /root/reference/gym_softrobot/envs/octopus/build.py:292-338
+ *     TransverseMuscle(rest_muscle_area=(radius/radius_base)**2, max_muscle_stress=1.0)
+ *   ApplyMuscles registration build_muscle_octopus.py:165-177, arm_push_env.py:198-209
+ *   apply_activation(scalar)  crawl_env.py:242, arm_push_env.py:259,271
+ * In the envs built here only the transverse muscle (index 2) is ever activated; the two longitudinal
+ * muscles keep zero activation and a muscle's force is proportional to its activation, so they add exact
+ * zeros (oracle/shims/coomm restates them too and the fixtures run through them).
+ * Model, per element k (material frame):
+ *   muscle position  = 0 (the TM acts on the centre line)
+ *   muscle strain    nu = sigma + e3            (= e Q t)
+ *   muscle tangent   t_m = nu / |nu|
+ *   muscle length    l = 1 / sqrt(|nu|)         (radial fibres of an incompressible arm: r / r0)
+ *   muscle area      A = rest_area / e
+ *   weight           h(l) = max(3.06 l^3 - 13.64 l^2 + 18.01 l - 6.44, 0)
+ *   internal force   n_m = activation * (-max_stress) * A * h(l) * t_m      (contraction lengthens the arm)
+ *   internal couple  0
+ * and, as for any continuous actuation, the loads handed to the rod are
+ *   external_forces  (nodes, lab)      += Delta_h( Q^T n_m )
+ *   external_torques (elements, mat.)  += (Q t e) x n_m * rest_length       (round-off zero for the TM) */
+static void apply_tm_muscle(ro_rod *r) {
+  const int n = r->n;
+  double *fl = r->tmp + 9 * (n + 1); /* (3,n) lab-frame internal muscle force */
+  for (int k = 0; k < n; k++) {
+    double nu[3], nm[3], qt[3];
+    for (int i = 0; i < 3; i++) nu[i] = r->sigma[i * n + k] + (i == 2 ? 1.0 : 0.0);
+    const double len = sqrt(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]);
+    const double l = 1.0 / sqrt(len);
+    double h = ((3.06 * l - 13.64) * l + 18.01) * l - 6.44;
+    if (h < 0.0) h = 0.0;
+    const double a0 = (r->rest_radius[k] / r->tm_radius_ref) * (r->rest_radius[k] / r->tm_radius_ref);
+    const double F = r->tm_activation * (-r->tm_max_stress) * (a0 / r->dil[k]) * h;
+    for (int i = 0; i < 3; i++) nm[i] = F * (nu[i] / len);
+    for (int i = 0; i < 3; i++) {
+      double s = 0.0, a = 0.0;
+      for (int j = 0; j < 3; j++) { s += QQ(j, i, k) * nm[j]; a += QQ(i, j, k) * r->tang[j * n + k]; }
+      fl[i * n + k] = s;
+      qt[i] = a * r->dil[k];
+    }
+    r->t_ext[0 * n + k] += (qt[1] * nm[2] - qt[2] * nm[1]) * r->rest_len[k];
+    r->t_ext[1 * n + k] += (qt[2] * nm[0] - qt[0] * nm[2]) * r->rest_len[k];
+    r->t_ext[2 * n + k] += (qt[0] * nm[1] - qt[1] * nm[0]) * r->rest_len[k];
+  }
+  for (int i = 0; i < 3; i++) {
+    r->f_ext[i * (n + 1) + 0] += fl[i * n + 0];
+    for (int k = 1; k < n; k++) r->f_ext[i * (n + 1) + k] += fl[i * n + k] - fl[i * n + k - 1];
+    r->f_ext[i * (n + 1) + n] += -fl[i * n + n - 1];
+  }
+}
+
 static void phase_forcing(ro_rod *r, double action) {
   /* forcings in registration order: gravity, then point force (build.py:88-105), muscle / spline torques */
   const int n = r->n;
@@ -519,6 +578,7 @@ static void phase_forcing(ro_rod *r, double action) {
   if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
   if (r->cfg.muscle_on) apply_muscle_torques(r);         /* a forcing, registered after gravity (continuum_snake.py:325-337) */
   if (r->cfg.spline_dir_mask) apply_spline_torques(r);   /* forcings (soft_arm_tracking.py:366-400) */
+  if (r->tm_on) apply_tm_muscle(r);                      /* ApplyMuscles (build_muscle_octopus.py:165-177, arm_push_env.py:204-209) */
 }
 
 static void phase_dynamic(ro_rod *r) {
@@ -541,9 +601,9 @@ static void phase_dynamic(ro_rod *r) {
 static void sucker_rates(ro_rod *r) {
   const int n = r->n;
   for (int q = 0; q < r->n_sucker; q++) {
-    const int idx = r->sucker_idx[q];
+    const int idx = r->sucker_idx[q], nod = r->sucker_node[q];
     const double f = 1.0 - r->sucker_ratio[q];
-    for (int i = 0; i < 3; i++) { V(i, idx) *= f; W(i, idx) *= f; }
+    for (int i = 0; i < 3; i++) { V(i, nod) *= f; W(i, idx) *= f; }
   }
 }
 
@@ -590,7 +650,7 @@ ro_rod *ro_create(const ro_config *cfg) {
   r->x = zalloc(3 * (n + 1)); r->v = zalloc(3 * (n + 1)); r->Q = zalloc(9 * n); r->w = zalloc(3 * n);
   r->acc = zalloc(3 * (n + 1)); r->alpha = zalloc(3 * n);
   r->rest_len = zalloc(n); r->rest_vor = zalloc(nv); r->mass = zalloc(n + 1); r->volume = zalloc(n);
-  r->radius = zalloc(n); r->J = zalloc(3 * n); r->Jinv = zalloc(3 * n); r->S = zalloc(3 * n); r->B = zalloc(3 * nv);
+  r->radius = zalloc(n); r->rest_radius = zalloc(n); r->J = zalloc(3 * n); r->Jinv = zalloc(3 * n); r->S = zalloc(3 * n); r->B = zalloc(3 * nv);
   r->rest_sigma = zalloc(3 * n); r->rest_kappa = zalloc(3 * nv);
   r->muscle = zalloc(1 + n);
   r->spl_pts = zalloc(3 * (2 * (size_t)(cfg->spline_n_ctrl > 0 ? cfg->spline_n_ctrl : 0) + 1));
@@ -625,11 +685,19 @@ ro_rod *ro_create(const ro_config *cfg) {
     QQ(1, 2, k) = t[0] * nor[1] - t[1] * nor[0];
     /* base_radius may be an array: np.linspace(base, tip, n_elem) (build_muscle_octopus.py:61-63) */
     double rad = cfg->base_radius;
-    if (cfg->tip_radius > 0.0 && n > 1) {
+    if (cfg->tip_radius > 0.0 && n > 1 && !cfg->taper_node_mean) {
       const double step = (cfg->tip_radius - cfg->base_radius) / (double)(n - 1);
       rad = (k == n - 1) ? cfg->tip_radius : (double)k * step + cfg->base_radius;
+    } else if (cfg->tip_radius > 0.0 && cfg->taper_node_mean) {
+      /* radius = np.linspace(base, tip, n_elem + 1); radius_mean = (radius[:-1] + radius[1:]) / 2
+       * (/root/reference/gym_softrobot/envs/octopus/arm_push_env.py:161-164) */
+      const double step = (cfg->tip_radius - cfg->base_radius) / (double)n;
+      const double r0 = (double)k * step + cfg->base_radius;
+      const double r1 = (k + 1 == n) ? cfg->tip_radius : (double)(k + 1) * step + cfg->base_radius;
+      rad = (r0 + r1) / 2.0;
     }
     r->radius[k] = rad;
+    r->rest_radius[k] = rad;
     double A0 = PI * rad * rad;
     double I1 = A0 * A0 / (4.0 * PI), I2 = I1, I3 = 2.0 * I2;
     double rho_l = cfg->density * rl;
@@ -675,7 +743,7 @@ void ro_destroy(ro_rod *r) {
   double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
                     r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
                     r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
-                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->t_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag};
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->t_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag, r->rest_radius};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
   free(r);
 }
@@ -696,7 +764,10 @@ double *ro_external_torques(ro_rod *r) { return r->t_user; }
 void ro_set_sucker(ro_rod *r, int slot, int index, double ratio) {
   if (slot < 0 || slot >= 8) return;
   if (slot >= r->n_sucker) r->n_sucker = slot + 1;
-  r->sucker_idx[slot] = index < 0 ? index + r->n : index;   /* -1 = last element (python indexing on the element arrays) */
+  /* python indexing on arrays of different length: velocity_collection[..., -1] is the LAST NODE (n),
+   * omega_collection[..., -1] the last element (n - 1) (controllable_constraint.py:68-69, arm_push_env.py:261) */
+  r->sucker_idx[slot] = index < 0 ? index + r->n : index;
+  r->sucker_node[slot] = index < 0 ? index + r->n + 1 : index;
   r->sucker_ratio[slot] = ratio;
 }
 double *ro_mass(ro_rod *r) { return r->mass; }
@@ -704,6 +775,10 @@ double *ro_internal_forces(ro_rod *r) { return r->f_int; }
 double *ro_internal_torques(ro_rod *r) { return r->t_int; }
 double *ro_radius(ro_rod *r) { return r->radius; }
 double *ro_muscle(ro_rod *r) { return r->muscle; }
+void ro_set_tm_muscle(ro_rod *r, double max_stress, double radius_ref) {
+  r->tm_on = max_stress != 0.0; r->tm_max_stress = max_stress; r->tm_radius_ref = radius_ref;
+}
+void ro_set_tm_activation(ro_rod *r, double activation) { r->tm_activation = activation; }
 double *ro_spline_points(ro_rod *r) { return r->spl_pts; }
 double *ro_spline_magnitude(ro_rod *r) { return r->spl_mag; }
 

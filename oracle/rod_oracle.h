@@ -45,6 +45,9 @@ typedef struct {
   /* tapered rod: base_radius array = np.linspace(base_radius, tip_radius, n_elem)
    * (/root/reference/gym_softrobot/envs/octopus/build_muscle_octopus.py:61-63); <= 0: uniform */
   double tip_radius;
+  /* 1: the taper is given on the nodes, np.linspace(base, tip, n_elem + 1), and each element takes the mean of its
+   * two nodes (/root/reference/gym_softrobot/envs/octopus/arm_push_env.py:161-175) */
+  int taper_node_mean;
 } ro_config;
 
 typedef struct ro_rod ro_rod;
@@ -72,6 +75,11 @@ double *ro_external_torques(ro_rod *); /* (3,n) constant extra element couple (m
 /* ControllableFixConstraint (/root/reference/gym_softrobot/envs/octopus/controllable_constraint.py:42-69):
  * after the dynamic step, v[:, index] and omega[:, index] are scaled by (1 - ratio); up to 8 slots */
 void ro_set_sucker(ro_rod *, int slot, int index, double ratio);
+/* COOMM TransverseMuscle under ApplyMuscles (restated from the published model — the package is not in
+ * /root/reference; see rod_oracle.c:apply_tm_muscle): rest_muscle_area_k = (rest radius_k / radius_ref)^2,
+ * scalar activation broadcast over the elements (crawl_env.py:242, arm_push_env.py:259,271).  max_stress = 0 disables. */
+void ro_set_tm_muscle(ro_rod *, double max_stress, double radius_ref);
+void ro_set_tm_activation(ro_rod *, double activation);
 double *ro_mass(ro_rod *);
 double *ro_internal_forces(ro_rod *);
 double *ro_internal_torques(ro_rod *);

@@ -56,6 +56,7 @@ class ROConfig(C.Structure):
         ("spline_scale", C.c_double),
         ("spline_max_rate", C.c_double),
         ("tip_radius", C.c_double),
+        ("taper_node_mean", C.c_int),
     ]
 
 
@@ -139,6 +140,8 @@ def lib(which="current"):
                                                  C.c_void_p, C.c_int]
         L.ro_max_threads.restype = C.c_int
         L.ro_set_sucker.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.ro_set_tm_muscle.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.ro_set_tm_activation.argtypes = [C.c_void_p, C.c_double]
         L.ro_asm_create.restype = C.c_void_p
         L.ro_asm_create.argtypes = [C.POINTER(ROConfig), C.POINTER(ROAsmConfig)]
         L.ro_asm_destroy.argtypes = [C.c_void_p]
@@ -165,9 +168,10 @@ class OracleRod:
                      youngs_modulus, dt, shear_modulus=0.0, shear_convention=0,
                      gravity=(0.0, 0.0, 0.0), damping_constant=-1.0, laplace_filter_order=0,
                      bc_kind=BC_FREE, point_force_on_base=False, damping_before_constraints=False,
-                     contact=None, muscle=None, spline=None, tip_radius=0.0):
+                     contact=None, muscle=None, spline=None, tip_radius=0.0, taper_node_mean=False):
         cfg = ROConfig()
         cfg.tip_radius = float(tip_radius)
+        cfg.taper_node_mean = int(taper_node_mean)
         cfg.n_elem = n_elem
         cfg.start[:] = list(map(float, start))
         cfg.direction[:] = list(map(float, direction))
@@ -246,6 +250,13 @@ class OracleRod:
     def set_sucker(self, slot, index, ratio):
         """ControllableFixConstraint(index, reduction_ratio) in slot `slot` (ratio 0 = released)."""
         self._L.ro_set_sucker(self._h, int(slot), int(index), float(ratio))
+
+    def set_tm_muscle(self, max_stress, radius_ref):
+        """COOMM TransverseMuscle(rest_muscle_area=(radius / radius_ref)**2, max_muscle_stress) under ApplyMuscles."""
+        self._L.ro_set_tm_muscle(self._h, float(max_stress), float(radius_ref))
+
+    def set_tm_activation(self, activation):
+        self._L.ro_set_tm_activation(self._h, float(activation))
 
     def close(self):
         if self._h:
