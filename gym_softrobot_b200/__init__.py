@@ -17,6 +17,10 @@ REGISTRY = {
     "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:FlatEnv", dict(n_arm=1, n_action=8)),
     "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeEnv", {}),
     "SoftArmTracking-v0": ("gym_softrobot_b200.envs.soft_arm_tracking:SoftArmTrackingEnv", {}),
+    "OctoCrawl-v0": ("gym_softrobot_b200.envs.octo_crawl:CrawlEnv", {}),
+    "OctoArmPush-v0": ("gym_softrobot_b200.envs.arm_push:ArmPushEnv", {}),
+    "OctoArmPush-v1": ("gym_softrobot_b200.envs.arm_push:ArmPushEnv", dict(mode="continuous")),
+    "OctoArmPullWeight-v0": ("gym_softrobot_b200.envs.arm_push:ArmPullWeightEnv", dict(mode="continuous")),
 }
 VECTOR_REGISTRY = {
     "SoftPendulum-v0": ("gym_softrobot_b200.envs.soft_pendulum:SoftPendulumVectorEnv", {}),
@@ -26,6 +30,11 @@ VECTOR_REGISTRY = {
     "OctoFlatLite-v0": ("gym_softrobot_b200.envs.octo_flat:OctoFlatVectorEnv", dict(n_arm=1, n_action=8)),
     "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeVectorEnv", {}),
     "SoftArmTracking-v0": ("gym_softrobot_b200.envs.soft_arm_tracking:SoftArmTrackingVectorEnv", {}),
+    "OctoCrawl-v0": ("gym_softrobot_b200.envs.octo_crawl:OctoCrawlVectorEnv", {}),
+    "OctoArmPush-v0": ("gym_softrobot_b200.envs.arm_push:ArmPushVectorEnv", {}),
+    "OctoArmPush-v1": ("gym_softrobot_b200.envs.arm_push:ArmPushVectorEnv", dict(mode="continuous")),
+    "OctoArmPullWeight-v0": ("gym_softrobot_b200.envs.arm_push:ArmPushVectorEnv",
+                             dict(mode="continuous", pull_weight=True, time_step=2.5e-5)),
 }
 
 

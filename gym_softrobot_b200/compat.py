@@ -16,6 +16,7 @@ try:  # pragma: no cover - depends on the image
     Env = _gym.Env
     Box = _spaces.Box
     Dict = _spaces.Dict
+    Discrete = _spaces.Discrete
 except ImportError:
     HAVE_GYMNASIUM = False
 
@@ -107,6 +108,44 @@ except ImportError:
 
         def __repr__(self):
             return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
+
+    class Discrete:
+        """`gymnasium.spaces.Discrete` stand-in ({start, ..., start + n - 1}; OctoArmPush-v0's action space,
+        arm_push_env.py:101)."""
+
+        def __init__(self, n, seed=None, start=0):
+            self.n, self.start = int(n), int(start)
+            self.dtype, self._shape = np.dtype(np.int64), ()
+            self._np_random = None
+            if seed is not None:
+                self.seed(seed)
+
+        @property
+        def shape(self):
+            return self._shape
+
+        @property
+        def np_random(self):
+            if self._np_random is None:
+                self.seed()
+            return self._np_random
+
+        def seed(self, seed=None):
+            self._np_random, s = np_random(seed)
+            return s
+
+        def sample(self):
+            return np.int64(self.start + self.np_random.integers(self.n))
+
+        def contains(self, x):
+            try:
+                xi = int(x)
+            except (TypeError, ValueError):
+                return False
+            return xi == x and self.start <= xi < self.start + self.n
+
+        def __repr__(self):
+            return f"Discrete({self.n})"
 
     class Dict:
         """`gymnasium.spaces.Dict` stand-in: an ordered mapping of sub-spaces (FlatEnv's observation space,

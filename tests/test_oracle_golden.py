@@ -336,3 +336,97 @@ def test_default_shear_modulus_conventions_are_separated_by_a_short_beam(convent
     assert abs((bend + other) / (bend + shear) - 1) > 0.03           # the two conventions are 3-4 % apart here
     assert np.abs(rod.velocity_collection).max() < 1e-5
     rod.close()
+
+
+# ---- COOMM-driven envs (coomm restated from the published model: PARITY UNPINNED) ------------
+MUSCLE_FIELDS = dict(FIELDS, kappa="kappa", sigma="sigma")
+MUSCLE_FLOOR = dict(position_collection=1e-2, velocity_collection=1e-3, director_collection=1.0, omega_collection=1e-2,
+                    tangents=1.0, kappa=1.0, sigma=1e-3)
+
+
+def _mrel(a, b, key):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), MUSCLE_FLOOR[key]))
+
+
+@pytest.mark.parametrize("tag,pull", [("octo_arm_push_v0", False), ("octo_arm_push_v1", False), ("octo_arm_pull_weight", True)])
+def test_c_oracle_matches_arm_push_fixtures(golden_dir, tag, pull):
+    """C oracle (tapered arm, python-indexed sucker, transverse muscle; PullWeight: + cylinder, joint, BodyBC) vs the
+    fixtures the unmodified reference ArmPushEnv / ArmPullWeightEnv produced on the elastica + coomm shims."""
+    g = np.load(os.path.join(golden_dir, f"{tag}_seed42.npz"), allow_pickle=True)
+    n, dt = 40, float(g["time_step"])
+    arm = dict(n_elem=n, start=(0, 0, 0), direction=(1, 0, 0), normal=(0, 1, 0), base_length=0.2, base_radius=0.012,
+               density=700.0, youngs_modulus=1e4, shear_modulus=1e4 / 1.5,
+               damping_constant=0.05 * 2 * (5e2 if pull else 1e2), tip_radius=0.001, taper_node_mean=True)
+    if pull:
+        head = dict(start=(-0.015 * 0.9, 0, -0.024), direction=(0, 0, 1), normal=(0, 1, 0), length=0.024, radius=0.015, density=700.0)
+        asm = ro.OracleAssembly([arm], dt, head=head, joint=dict(k=1e6, nu=1e-2, kt=1e0, radius=0.015), angles_deg=[0.0])
+        rod = asm.arms[0]
+    else:
+        asm, rod = None, ro.OracleRod(dt=dt, **arm)
+    assert np.array_equal(rod.radius, g["radius0"]) and np.array_equal(rod.mass, g["mass"])
+    rod.set_tm_muscle(1.0, 0.012)
+    for i, a in enumerate(g["actions"]):
+        if np.ndim(a) == 0:
+            idx, act = (0, 0.5) if int(a) == 0 else (-1, 0.0)        # arm_push_env.py:254-264
+        else:
+            idx, act = int(np.clip(a[0] * n, 0, n - 1)), float(a[1])   # :266-271
+        rod.set_sucker(0, idx, 0.9 if pull else 1.0)
+        rod.set_tm_activation(act)
+        (asm or rod).substeps(int(g["step_skip"]))
+        for gk, fk in MUSCLE_FIELDS.items():
+            assert _mrel(getattr(rod, fk), g[f"state{i + 1}/{gk}"], fk) < 1e-10, (i, gk)
+        if pull:
+            for gk in ("position", "velocity", "director", "omega"):
+                ref = g[f"state{i + 1}/head/{gk}"]
+                assert _mrel(getattr(asm, "head_" + gk).reshape(ref.shape), ref, gk + "_collection") < 1e-10, (i, gk)
+    assert float(np.abs(g[f"state{len(g['actions'])}/sigma"]).max()) > 0.2      # the muscle stretched the arm a lot
+
+
+def test_c_oracle_matches_octo_crawl_fixture(golden_dir):
+    """Multi-rod C oracle vs the fixture the unmodified reference CrawlEnv produced on the shims (3 x 800 substeps).  The
+    env's damper is built with the literal time_step=7e-5 although the env steps at 5e-5
+    (build_muscle_octopus.py:102-107): same exponent through nu' = nu 7e-5 / dt."""
+    g = np.load(os.path.join(golden_dir, "octo_crawl_seed42.npz"), allow_pickle=True)
+    n, dt, hr, r0 = int(g["n_elems"]), float(g["time_step"]), 0.04, 0.013
+    angles = [22.5 + 45 * i for i in range(8)]
+    arms = []
+    for ang in angles:
+        c, s = np.cos(np.deg2rad(ang)), np.sin(np.deg2rad(ang))
+        arms.append(dict(n_elem=n, start=(c * hr, s * hr, 0.0), direction=(c, s, 0.0), normal=(0, 0, 1), base_length=0.25,
+                         base_radius=r0, density=1000.0, youngs_modulus=1.5e4, shear_modulus=1.5e4 / 1.5,
+                         damping_constant=0.2 * 1e-2 * (7e-5 / dt), tip_radius=0.0042))
+    head = dict(start=(0, 0, -2 * r0), direction=(0, 0, 1), normal=(0, 1, 0), length=2 * r0, radius=hr, density=50.0)
+    asm = ro.OracleAssembly(arms, dt, head=head, joint=dict(k=1e6, nu=1e-3, kt=1e2, radius=hr), angles_deg=angles)
+    for rod in asm.arms:
+        rod.set_tm_muscle(1.0, r0)
+    for i, a in enumerate(g["actions"]):
+        a = a.reshape(8, 3)
+        for k, rod in enumerate(asm.arms):
+            rod.set_sucker(0, int(np.clip(a[k, 0] * n, 0, n - 1)), float(a[k, 2]))     # crawl_env.py:236-243
+            rod.set_tm_activation(float(a[k, 1]))
+        asm.substeps(int(g["step_skip"]))
+        for k, rod in enumerate(asm.arms):
+            for gk, fk in MUSCLE_FIELDS.items():
+                assert _mrel(getattr(rod, fk), g[f"state{i + 1}/arm{k}/{gk}"], fk) < 1e-9, (i, k, gk)
+        for gk in ("position", "velocity", "director", "omega"):
+            ref = g[f"state{i + 1}/head/{gk}"]
+            assert _mrel(getattr(asm, "head_" + gk).reshape(ref.shape), ref, gk + "_collection") < 2e-9, (i, gk)
+
+
+def test_transverse_muscle_static_stretch_known_answer():
+    """Physics check of the restated transverse muscle (independent of any fixture): at rest the axial balance of an
+    element is  S33 (e - 1) = a sigma_max A0 h(1 / sqrt(e))  with S33 = E pi r^2 and A0 = (r / r_ref)^2 — both scale
+    with r^2, so every element of a tapered arm settles at the SAME stretch e.  Heavily damped C oracle vs the root."""
+    n, L, r_ref, E, a, smax = 16, 0.2, 0.012, 1e4, 0.6, 1.0
+    rod = ro.OracleRod(n, (0, 0, 0), (1, 0, 0), (0, 1, 0), L, r_ref, 700.0, E, 2e-5, shear_modulus=E / 1.5,
+                       damping_constant=400.0, tip_radius=0.004, taper_node_mean=True)
+    rod.set_tm_muscle(smax, r_ref)
+    rod.set_tm_activation(a)
+    rod.substeps(60000)
+    h = lambda l: max(((3.06 * l - 13.64) * l + 18.01) * l - 6.44, 0.0)
+    e = 1.0
+    for _ in range(200):   # fixed point of e = 1 + a smax h(1/sqrt(e)) / (E pi r_ref^2)
+        e = 1.0 + a * smax * h(1.0 / np.sqrt(e)) / (E * np.pi * r_ref ** 2)
+    assert 1.05 < e < 1.2
+    np.testing.assert_allclose(rod.dilatation, e, rtol=1e-6)
+    assert float(np.abs(rod.velocity_collection).max()) < 1e-5      # settled (1.2 s of heavy damping)
