@@ -945,7 +945,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   bool redo = false;
   if (FASTONLY) {    // env-level OR of the domain flags; a flagged env keeps its pre-launch state in global memory
     int *sh_dom = reinterpret_cast<int *>(sh_N);
-    if (tid < 64) sh_dom[tid] = 0;
+    if (tid < rods_per_cta) sh_dom[tid] = 0;   // (rods_per_cta <= NT / 4: one slot per env group of this CTA)
     __syncthreads();
     if (live && dom_bad) atomicOr(&sh_dom[r], 1);
     __syncthreads();
@@ -986,7 +986,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   }
   // per-rod NaN flag and tangents for the observation (rod r occupies tids r*tpr .. r*tpr+n)
   int *sh_flag = reinterpret_cast<int *>(sh_s);
-  if (tid < 64) sh_flag[tid] = 0;
+  if (tid < rods_per_cta) sh_flag[tid] = 0;
   if (active && (A.model == MODEL_SOFT_PENDULUM || A.model == MODEL_SOFT_PENDULUM_3D)) {
     // the tangents were stored to global memory at the last substep; stage them for lane j=0
 #pragma unroll

@@ -40,3 +40,7 @@ if "pend3d" in which: e2e("SoftPendulum3D-v0", 4096, (2,), np.float32(-1.0), np.
 if "arm" in which: e2e("OctoArmSingle-v0", 4096, (7,), np.float32(-22.0), np.float32(22.0), 5)
 if "flat" in which: e2e("OctoFlat-v0", 4096, (24,), np.float32(-22.0), np.float32(22.0), 3)
 if "softarm" in which: e2e("SoftArmTracking-v0", 16384, (8,), -0.3, 0.3, 10, dtype=torch.float64)
+# the COOMM muscle envs (transverse muscle in the kernel, tapered-rod generic kernel): continuous actions in [0, 1]
+if "push" in which: e2e("OctoArmPush-v1", 4096, (2,), np.float32(0.0), np.float32(1.0), 5)
+if "pull" in which: e2e("OctoArmPullWeight-v0", 4096, (2,), np.float32(0.0), np.float32(1.0), 3)
+if "crawl" in which: e2e("OctoCrawl-v0", 1024, (24,), np.float32(0.0), np.float32(1.0), 3)
