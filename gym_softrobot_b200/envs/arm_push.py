@@ -9,7 +9,8 @@ through `FixedJoint2Rigid` and held upright by `BodyBoundaryCondition`.  The sub
 the activation are per-env device arrays written by `set_action`.
 
 COOMM is a third-party package outside the reference tree: its published muscle model is restated.
-`config_early_termination` (an energy criterion, arm_push_env.py:309-312,436-452) is not built.
+`config_early_termination` (arm_push_env.py:309-312,436-452): the episode ends once kinetic + shear + bending energy
+drop below 1e-7 J, every reward is -10; the energies are torch reductions over the state with the rod's constants.
 """
 from typing import Optional
 
@@ -37,6 +38,24 @@ def arm_push_node_masses(n_elem=_N_ELEM):
     return mass
 
 
+def arm_push_energy_tables(n_elem=_N_ELEM):
+    """(node mass [n+1], J [3, n], S [3, n], B [3, n-1], rest_lengths [n], rest_voronoi_lengths [n-1]) of the arm, as
+    `CosseratRod.straight_rod` allocates them — what PyElastica's compute_*_energy read."""
+    E, G, rho = _ARM["youngs_modulus"], _ARM["shear_modulus"], _ARM["density"]
+    radius = np.linspace(_ARM["base_radius"], _ARM["tip_radius"], n_elem + 1)
+    radius = (radius[:-1] + radius[1:]) / 2
+    x = np.linspace(0.0, _ARM["base_length"], n_elem + 1)
+    rl = x[1:] - x[:-1]
+    A0 = np.pi * radius * radius
+    I1 = A0 * A0 / (4.0 * np.pi)
+    I = np.stack([I1, I1, 2.0 * I1])
+    J = I * (rho * rl)
+    S = np.stack([27.0 / 28.0 * G * A0, 27.0 / 28.0 * G * A0, E * A0])
+    Bel = np.stack([E * I[0], E * I[1], G * I[2]])
+    B = (Bel[:, 1:] * rl[1:] + Bel[:, :-1] * rl[:-1]) / (rl[1:] + rl[:-1])
+    return arm_push_node_masses(n_elem), J, S, B, rl, 0.5 * (rl[1:] + rl[:-1])
+
+
 def _make_handle(n_env, time_step, device, pull_weight):
     damp = 0.05 * 2 * (5e2 if pull_weight else 1e2)
     kw = {}
@@ -53,8 +72,9 @@ class ArmPushVectorEnv:
     `mode` "discrete": actions are an integer tensor [n_env] in {0, 1}; "continuous": float [n_env, 2] in [0, 1]."""
 
     def __init__(self, n_env, final_time=2.5, time_step=5.0e-5, recording_fps=40, mode="discrete",
-                 pull_weight=False, device: int = 0, autoreset: bool = True):
+                 pull_weight=False, device: int = 0, autoreset: bool = True, config_early_termination: bool = False):
         import torch
+        self.config_early_termination = config_early_termination
         self.torch = torch
         if mode not in ("discrete", "continuous"):
             raise NotImplementedError(f"The mode {mode} is not available.")
@@ -75,6 +95,7 @@ class ArmPushVectorEnv:
         m = arm_push_node_masses(self.n_elem)
         self._mass = torch.as_tensor(m, device=self.device)
         self._mass_sum = float(m.sum())
+        self._etab = [torch.as_tensor(t, device=self.device) for t in arm_push_energy_tables(self.n_elem)]
         row = [0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0, -0.0]
         if pull_weight:   # the cylinder: start, direction, normal (arm_push_env.py:551-562)
             row += [-0.015 * 0.9, 0.0, -2 * _ARM["base_radius"], 0.0, 0.0, 1.0, 0.0, 1.0, 0.0]
@@ -96,6 +117,23 @@ class ArmPushVectorEnv:
         # compute_position_center_of_mass()[:2]
         x = self.handle.fields()["position_collection"].reshape(self.n_env, 3, self.n_elem + 1)
         return (x[:, :2, :] * self._mass).sum(dim=2) / self._mass_sum
+
+    def desired_hamiltonian(self):
+        """cal_desired_Hamiltonian (arm_push_env.py:442-452): translational + rotational + shear + bending energy, with
+        PyElastica's expressions; sigma / kappa / dilatation are the stale fields of the last force evaluation, as there."""
+        f = self.handle.fields()
+        mass, J, S, B, rl, rvl = self._etab
+        n = self.n_elem
+        v = f["velocity_collection"].reshape(self.n_env, 3, n + 1)
+        w = f["omega_collection"].reshape(self.n_env, 3, n)
+        sg = f["sigma"].reshape(self.n_env, 3, n)
+        kp = f["kappa"].reshape(self.n_env, 3, n - 1)
+        e = f["dilatation"].reshape(self.n_env, n)
+        trans = 0.5 * (mass * (v * v).sum(dim=1)).sum(dim=1)
+        rot = 0.5 * (w * (J * w / e[:, None, :])).sum(dim=1).sum(dim=1)
+        shear = 0.5 * ((sg * (S * sg)).sum(dim=1) * rl).sum(dim=1)
+        bend = 0.5 * ((kp * (B * kp)).sum(dim=1) * rvl).sum(dim=1)
+        return trans + rot + shear + bend
 
     def _obs(self):
         torch = self.torch
@@ -159,6 +197,11 @@ class ArmPushVectorEnv:
         reward = torch.where(invalid, torch.full_like(forward, -20.0), forward)
         terminated = invalid.clone()
         truncated = self.step_count >= self._first_truncated
+        if self.config_early_termination:
+            # arm_push_env.py:309-312: this branch comes first — no NaN penalty, no forward reward, always -10
+            terminated = self.desired_hamiltonian() < 1e-7
+            truncated = truncated | terminated
+            reward = torch.full_like(forward, -10.0)
         bad = torch.isnan(reward)
         terminated |= bad
         reward = torch.where(bad, torch.full_like(reward, -20.0), reward)
@@ -198,11 +241,9 @@ class ArmPushEnv(Env):
         super().__init__()
         if render_mode not in {None, *self.metadata["render_modes"]}:
             raise ValueError(f"Unsupported render mode: {render_mode}")
-        if config_early_termination:
-            raise NotImplementedError("config_early_termination (energy criterion) is not built")
         self.render_mode = render_mode
         self._vec = ArmPushVectorEnv(1, final_time, time_step, recording_fps, mode, self._pull_weight, device,
-                                     autoreset=False)
+                                     autoreset=False, config_early_termination=config_early_termination)
         self.final_time, self.time_step, self.step_skip = final_time, time_step, self._vec.step_skip
         self.total_steps = int(final_time / time_step)
         self.recording_fps, self.n_elem, self.mode = recording_fps, _N_ELEM, self._vec.mode
@@ -226,8 +267,16 @@ class ArmPushEnv(Env):
         obs, reward, term, trunc, _ = self._vec.step(a)
         self.time = _advance_time(self.time, self.time_step, self.step_skip)
         timelimit = bool(self.time > self.final_time)
-        return (obs[0].cpu().numpy(), np.float64(reward[0].item()), bool(term[0]), timelimit,
+        # (with config_early_termination the reference sets truncated = terminated first, then the time limit ORs in)
+        truncated = timelimit or (self.config_early_termination and bool(term[0]))
+        return (obs[0].cpu().numpy(), np.float64(reward[0].item()), bool(term[0]), truncated,
                 {"time": self.time, "TimeLimit.truncated": timelimit})
+
+    def check_early_termination(self, cutoff_error=1e-7):
+        return bool(self.cal_desired_Hamiltonian() < cutoff_error)
+
+    def cal_desired_Hamiltonian(self):
+        return float(self._vec.desired_hamiltonian()[0].item())
 
     def rod_state(self):
         return {k: v[0].cpu().numpy() for k, v in self._vec.fields().items()}

@@ -480,6 +480,22 @@ def gen_arm_push(env_id="OctoArmPush-v0", tag="octo_arm_push_v0", seed=42, n=6):
     print(env_id, "rewards", rew, "tip x", rod.position_collection[0, -1])
 
 
+def gen_arm_push_early(seed=1):
+    """OctoArmPush-v1 with config_early_termination=True (arm_push_env.py:309-312,436-452): every reward is -10,
+    the episode ends when kinetic + shear + bending energy < 1e-7 J — true on a first step without activation."""
+    env = ref_loader.load_reference_env("OctoArmPush-v1", config_early_termination=True)
+    env.reset(seed=seed)
+    e = env.unwrapped
+    acts = np.array([[0.3, 0.0], [0.3, 0.6], [0.3, 0.0], [0.5, 0.2]], dtype=np.float32)
+    rew, term, trunc, ham = [], [], [], []
+    for a in acts:
+        o, r, te, tr, info = env.step(a)
+        rew.append(r); term.append(te); trunc.append(tr); ham.append(e.cal_desired_Hamiltonian())
+    np.savez_compressed(os.path.join(OUT, f"octo_arm_push_early_seed{seed}.npz"), label=COOMM_LABEL, actions=acts,
+                        reward=np.array(rew), terminated=np.array(term), truncated=np.array(trunc), hamiltonian=np.array(ham))
+    print("arm push early termination:", term, trunc, ham)
+
+
 def gen_octo_crawl(seed=42, n=3):
     """OctoCrawl-v0: build_octopus_muscles (eight tapered arms, light head, joints, BodyBoundaryCondition), one
     ControllableFixConstraint per arm whose index / ratio the action moves, transverse-muscle activation per arm
@@ -538,6 +554,7 @@ if __name__ == "__main__":
         gen_arm_push("OctoArmPush-v0", "octo_arm_push_v0")
         gen_arm_push("OctoArmPush-v1", "octo_arm_push_v1")
         gen_arm_push("OctoArmPullWeight-v0", "octo_arm_pull_weight", n=3)
+        gen_arm_push_early()
         gen_octo_crawl()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "soft_arm":
@@ -561,6 +578,7 @@ if __name__ == "__main__":
     gen_arm_push("OctoArmPush-v0", "octo_arm_push_v0")
     gen_arm_push("OctoArmPush-v1", "octo_arm_push_v1")
     gen_arm_push("OctoArmPullWeight-v0", "octo_arm_pull_weight", n=3)
+    gen_arm_push_early()
     gen_octo_crawl()
     gen_snake()   # ~25 min of NumPy stepping
     gen_snake_perturbed()   # another ~25 min

@@ -254,3 +254,23 @@ class CosseratRod(RodBase):
 
     def compute_velocity_center_of_mass(self):
         return (self.mass * self.velocity_collection).sum(axis=1) / self.mass.sum()
+
+    # -- energies (PyElastica `CosseratRod.compute_*_energy`, [PE-recall]; used by the reference's
+    #    `ArmPushEnv.cal_desired_Hamiltonian`, /root/reference/gym_softrobot/envs/octopus/arm_push_env.py:442-452)
+    def compute_translational_energy(self):
+        v = self.velocity_collection
+        return (0.5 * (self.mass * np.einsum("ij,ij->j", v, v)).sum())
+
+    def compute_rotational_energy(self):
+        j_omega_upon_e = _batch_matvec(self.mass_second_moment_of_inertia, self.omega_collection) / self.dilatation
+        return 0.5 * np.einsum("ik,ik->k", self.omega_collection, j_omega_upon_e).sum()
+
+    def compute_bending_energy(self):
+        kappa_diff = self.kappa - self.rest_kappa
+        bending_internal_torques = _batch_matvec(self.bend_matrix, kappa_diff)
+        return 0.5 * (np.einsum("ik,ik->k", kappa_diff, bending_internal_torques) * self.rest_voronoi_lengths).sum()
+
+    def compute_shear_energy(self):
+        strain_diff = self.sigma - self.rest_sigma
+        shear_internal_forces = _batch_matvec(self.shear_matrix, strain_diff)
+        return 0.5 * (np.einsum("ik,ik->k", strain_diff, shear_internal_forces) * self.rest_lengths).sum()

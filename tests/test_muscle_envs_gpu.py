@@ -245,3 +245,45 @@ def test_transverse_muscle_on_a_bent_arm_vs_c_oracle():
     for rod in rods:
         rod.close()
     h.close()
+
+
+def test_arm_push_early_termination_mode(golden_dir):
+    """config_early_termination=True (arm_push_env.py:309-312,436-452) vs the reference env on the shims: reward -10
+    whatever happens, terminated = truncated = (kinetic + shear + bending energy < 1e-7 J); the energy itself to 1e-9."""
+    import gym_softrobot_b200 as gsb
+    g = np.load(os.path.join(golden_dir, "octo_arm_push_early_seed1.npz"), allow_pickle=True)
+    env = gsb.make("OctoArmPush-v1", config_early_termination=True)
+    env.reset(seed=1)
+    for i, a in enumerate(g["actions"]):
+        obs, r, te, tr, info = env.step(a)
+        assert r == float(g["reward"][i]) == -10.0
+        assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
+        ham, ref = env.cal_desired_Hamiltonian(), float(g["hamiltonian"][i])
+        assert abs(ham - ref) <= 1e-9 * max(ref, 1e-3), (i, ham, ref)
+    assert bool(g["terminated"][0]) and not bool(g["terminated"][1])
+    env.close()
+
+
+@pytest.mark.parametrize("env_id,n_act", [("OctoArmPush-v1", 2), ("OctoArmPullWeight-v0", 2), ("OctoCrawl-v0", 24)])
+def test_muscle_vector_envs_are_batch_independent_and_autoreset(env_id, n_act):
+    """An env's bits do not depend on the batch it runs in (1 env vs the same env among 7 others with other actions),
+    and a finished env is rebuilt inside the same step() (fresh muscles / suckers) while the others keep stepping."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    kw = dict(final_time=0.06) if env_id != "OctoCrawl-v0" else dict(final_time=0.09)
+    gen = torch.Generator().manual_seed(3)
+    acts = torch.rand((4, 8, n_act), generator=gen).cuda()
+    solo, batch = gsb.make_vec(env_id, 1, **kw), gsb.make_vec(env_id, 8, **kw)
+    solo.reset(seed=0); batch.reset(seed=0)
+    first = int((solo._time_table > kw["final_time"]).nonzero()[0][0]) if not hasattr(solo, "_first_truncated") else solo._first_truncated
+    for s in range(4):
+        o1, r1, te1, tr1, i1 = solo.step(acts[s, 5:6])
+        o8, r8, te8, tr8, i8 = batch.step(acts[s])
+        assert torch.equal(o1[0], o8[5]) and torch.equal(r1[0], r8[5]) and bool(te1[0]) == bool(te8[5])
+        assert bool(tr8.all()) == (s + 1 == first), (s, first)
+        if s + 1 == first:
+            assert "final_obs" in i8 and int(batch.step_count.max()) == 0
+            assert float(batch.handle.tm_activation_tensor().abs().max()) == 0.0      # fresh muscles
+            assert int(batch.handle.sucker_index_tensor().abs().max()) == 0           # fresh SuckerController(index=0)
+    assert torch.isfinite(o8).all()
+    solo.close(); batch.close()
