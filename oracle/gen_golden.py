@@ -529,6 +529,38 @@ def gen_octo_crawl(seed=42, n=3):
     print("octo crawl:", rew, term, "head", e.rigid_rod.position_collection[:, 0])
 
 
+def gen_octo_reach(seed=42, n=2):
+    """OctoReach-v0: build_octopus_muscles with all three muscles driven by per-element activations and the head
+    pinned by OneEndFixedBC on top of BodyBoundaryCondition (/root/reference/gym_softrobot/envs/octopus/reach_env.py)."""
+    env = ref_loader.load_reference_env("OctoReach-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    out = {"label": COOMM_LABEL, "seed": seed, "obs0": obs0, "step_skip": e.step_skip, "time_step": e.time_step,
+           "n_elems": e.n_elems, "target": np.asarray(e._target, dtype=np.float64)}
+
+    def snap(tag):
+        for a, rod in enumerate(e.shearable_rods):
+            pack(f"{tag}/arm{a}", rod_state(rod), out)
+        h = e.rigid_rod
+        out[f"{tag}/head/position"] = h.position_collection.copy()
+        out[f"{tag}/head/velocity"] = h.velocity_collection.copy()
+        out[f"{tag}/head/director"] = h.director_collection.copy()
+        out[f"{tag}/head/omega"] = h.omega_collection.copy()
+
+    snap("state0")
+    acts, obs, rew, term, trunc = [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr)
+        snap(f"state{i + 1}")
+    out.update(actions=np.array(acts, dtype=np.float32), obs=np.array(obs, dtype=np.float32),
+               reward=np.array(rew, dtype=np.float64), terminated=np.array(term), truncated=np.array(trunc))
+    np.savez_compressed(os.path.join(OUT, f"octo_reach_seed{seed}.npz"), **out)
+    print("octo reach:", rew, term, trunc, "tip0", e.shearable_rods[0].position_collection[:, -1])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
@@ -549,6 +581,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cfg4":
         gen_octo_cfg4()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "reach":
+        gen_octo_reach()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "coomm":
         gen_arm_push("OctoArmPush-v0", "octo_arm_push_v0")
@@ -580,5 +615,6 @@ if __name__ == "__main__":
     gen_arm_push("OctoArmPullWeight-v0", "octo_arm_pull_weight", n=3)
     gen_arm_push_early()
     gen_octo_crawl()
+    gen_octo_reach()
     gen_snake()   # ~25 min of NumPy stepping
     gen_snake_perturbed()   # another ~25 min

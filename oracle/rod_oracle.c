@@ -45,6 +45,11 @@ struct ro_rod {
   int tm_on;
   double tm_max_stress, tm_radius_ref, tm_activation;
   double *rest_radius;
+  /* general COOMM muscle layers (apply_muscle_layers): up to 3 per rod, per-element activations */
+  int ml_kind[3];                         /* 0 off, 1 longitudinal, 2 transverse */
+  double ml_stress[3], ml_rref[3], ml_px[3], ml_py[3];
+  double *ml_act;                         /* (3,n) */
+  double *ml_tmp;                         /* scratch 16 n */
   /* plugins */
   double fixed_pos[3], fixed_Q[9];
   double c_v, *c_w;                      /* AnalyticalLinearDamper coefficients */
@@ -567,6 +572,83 @@ static void apply_tm_muscle(ro_rod *r) {
   }
 }
 
+/* ---- COOMM `ApplyMuscles` over a list of muscle layers with per-element activations (OctoReach-v0, OctoArmTwo-v0:
+ * /root/reference/gym_softrobot/envs/octopus/reach_env.py:214-227, arm_two_env.py:222-247; layers from
+ * create_es_muscle_layers, envs/octopus/build.py:292-338).  Same unpinned restatement as apply_tm_muscle, general in
+ * the muscle's material-frame offset x_m = ratio * radius (oracle/shims/coomm/actuations/muscles/muscle.py):
+ *   nu_m = sigma + e3 + kappa_e x x_m + d x_m / ds      kappa_e = trapezoid of kappa with zero ghosts,
+ *                                                        d/ds = central difference over element centres
+ *   l_m = |nu_m| (longitudinal) or 1 / sqrt(|nu_m|) (transverse), t_m = nu_m / |nu_m|, A = rest_area / e
+ *   n_m = a sigma_max A h(l_m) t_m,   c_m = x_m x n_m (elements),   m_m = Voronoi average of c_m
+ *   external_forces += Delta_h(Q^T n_m);  external_torques += Delta_h(m_m) + A_h(kappa x m_m D) + (Q t e) x n_m l0 */
+static void apply_muscle_layers(ro_rod *r) {
+  const int n = r->n, nv = n - 1;
+  double *pos = r->ml_tmp, *frc = pos + 3 * (n + 1), *cpl = frc + 3 * (n + 1), *fl = cpl + 3 * (n + 1), *mv = fl + 3 * (n + 1);
+  for (int m = 0; m < 3; m++) {
+    if (!r->ml_kind[m]) continue;
+    const double ratio[3] = {r->ml_px[m], r->ml_py[m], 0.0};
+    for (int k = 0; k < n; k++)
+      for (int i = 0; i < 3; i++) pos[i * n + k] = ratio[i] * r->radius[k];
+    for (int k = 0; k < n; k++) {
+      double nu[3], ke[3], dp[3], st[3], xm[3] = {pos[k], pos[n + k], pos[2 * n + k]};
+      for (int i = 0; i < 3; i++) {
+        nu[i] = r->sigma[i * n + k] + (i == 2 ? 1.0 : 0.0);
+        const double kl = k > 0 ? r->kappa[i * nv + k - 1] : 0.0, kr = k < nv ? r->kappa[i * nv + k] : 0.0;
+        ke[i] = (k == 0) ? 0.5 * kr : (k == n - 1) ? 0.5 * kl : 0.5 * (kr + kl);
+        dp[i] = 0.0;
+      }
+      if (n > 2) {   /* element centres s_k = cumsum(rest_len)_k - rest_len_k / 2 */
+        const int a = k == 0 ? 0 : k - 1, b = k == n - 1 ? n - 1 : k + 1;
+        double sa = 0.0, sb = 0.0, acc = 0.0;
+        for (int q = 0; q <= b; q++) { acc += r->rest_len[q]; if (q == a) sa = acc - 0.5 * r->rest_len[q]; if (q == b) sb = acc - 0.5 * r->rest_len[q]; }
+        for (int i = 0; i < 3; i++) dp[i] = (pos[i * n + b] - pos[i * n + a]) / (sb - sa);
+      }
+      st[0] = nu[0] + (ke[1] * xm[2] - ke[2] * xm[1]) + dp[0];
+      st[1] = nu[1] + (ke[2] * xm[0] - ke[0] * xm[2]) + dp[1];
+      st[2] = nu[2] + (ke[0] * xm[1] - ke[1] * xm[0]) + dp[2];
+      const double len = sqrt(st[0] * st[0] + st[1] * st[1] + st[2] * st[2]);
+      const double l = r->ml_kind[m] == 2 ? 1.0 / sqrt(len) : len;
+      double h = ((3.06 * l - 13.64) * l + 18.01) * l - 6.44;
+      if (h < 0.0) h = 0.0;
+      const double a0 = (r->rest_radius[k] / r->ml_rref[m]) * (r->rest_radius[k] / r->ml_rref[m]);
+      const double F = r->ml_act[m * n + k] * r->ml_stress[m] * (a0 / r->dil[k]) * h;
+      double nm[3] = {F * (st[0] / len), F * (st[1] / len), F * (st[2] / len)}, qt[3];
+      for (int i = 0; i < 3; i++) frc[i * n + k] = nm[i];
+      cpl[0 * n + k] = xm[1] * nm[2] - xm[2] * nm[1];
+      cpl[1 * n + k] = xm[2] * nm[0] - xm[0] * nm[2];
+      cpl[2 * n + k] = xm[0] * nm[1] - xm[1] * nm[0];
+      for (int i = 0; i < 3; i++) {
+        double s_ = 0.0, a_ = 0.0;
+        for (int j = 0; j < 3; j++) { s_ += QQ(j, i, k) * nm[j]; a_ += QQ(i, j, k) * (r->tang[j * n + k] * r->dil[k]); }
+        fl[i * n + k] = s_;
+        qt[i] = a_;
+      }
+      r->t_ext[0 * n + k] += (qt[1] * nm[2] - qt[2] * nm[1]) * r->rest_len[k];
+      r->t_ext[1 * n + k] += (qt[2] * nm[0] - qt[0] * nm[2]) * r->rest_len[k];
+      r->t_ext[2 * n + k] += (qt[0] * nm[1] - qt[1] * nm[0]) * r->rest_len[k];
+    }
+    for (int i = 0; i < 3; i++) {
+      r->f_ext[i * (n + 1) + 0] += fl[i * n + 0];
+      for (int k = 1; k < n; k++) r->f_ext[i * (n + 1) + k] += fl[i * n + k] - fl[i * n + k - 1];
+      r->f_ext[i * (n + 1) + n] += -fl[i * n + n - 1];
+    }
+    for (int k = 0; k < nv; k++)
+      for (int i = 0; i < 3; i++) mv[i * nv + k] = 0.5 * (cpl[i * n + k + 1] + cpl[i * n + k]);
+    for (int k = 0; k < n; k++) {
+      for (int i = 0; i < 3; i++) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        /* kappa x m_m * rest_voronoi_length at Voronoi points k-1 and k */
+        const double cl = k > 0 ? (r->kappa[i1 * nv + k - 1] * mv[i2 * nv + k - 1] - r->kappa[i2 * nv + k - 1] * mv[i1 * nv + k - 1]) * r->rest_vor[k - 1] : 0.0;
+        const double cr = k < nv ? (r->kappa[i1 * nv + k] * mv[i2 * nv + k] - r->kappa[i2 * nv + k] * mv[i1 * nv + k]) * r->rest_vor[k] : 0.0;
+        const double ml = k > 0 ? mv[i * nv + k - 1] : 0.0, mr = k < nv ? mv[i * nv + k] : 0.0;
+        const double dif = (k == 0) ? mr : (k == n - 1) ? -ml : mr - ml;
+        const double quad = (k == 0) ? 0.5 * cr : (k == n - 1) ? 0.5 * cl : 0.5 * (cr + cl);
+        r->t_ext[i * n + k] += dif + quad;
+      }
+    }
+  }
+}
+
 static void phase_forcing(ro_rod *r, double action) {
   /* forcings in registration order: gravity, then point force (build.py:88-105), muscle / spline torques */
   const int n = r->n;
@@ -578,7 +660,8 @@ static void phase_forcing(ro_rod *r, double action) {
   if (r->cfg.point_force_on_base) r->f_ext[0] = action; /* assignment (build.py:101) */
   if (r->cfg.muscle_on) apply_muscle_torques(r);         /* a forcing, registered after gravity (continuum_snake.py:325-337) */
   if (r->cfg.spline_dir_mask) apply_spline_torques(r);   /* forcings (soft_arm_tracking.py:366-400) */
-  if (r->tm_on) apply_tm_muscle(r);                      /* ApplyMuscles (build_muscle_octopus.py:165-177, arm_push_env.py:204-209) */
+  if (r->tm_on) apply_tm_muscle(r);
+  if (r->ml_kind[0] || r->ml_kind[1] || r->ml_kind[2]) apply_muscle_layers(r);                      /* ApplyMuscles (build_muscle_octopus.py:165-177, arm_push_env.py:204-209) */
 }
 
 static void phase_dynamic(ro_rod *r) {
@@ -650,6 +733,7 @@ ro_rod *ro_create(const ro_config *cfg) {
   r->x = zalloc(3 * (n + 1)); r->v = zalloc(3 * (n + 1)); r->Q = zalloc(9 * n); r->w = zalloc(3 * n);
   r->acc = zalloc(3 * (n + 1)); r->alpha = zalloc(3 * n);
   r->rest_len = zalloc(n); r->rest_vor = zalloc(nv); r->mass = zalloc(n + 1); r->volume = zalloc(n);
+  r->ml_act = zalloc(3 * n); r->ml_tmp = zalloc(16 * (n + 1));
   r->radius = zalloc(n); r->rest_radius = zalloc(n); r->J = zalloc(3 * n); r->Jinv = zalloc(3 * n); r->S = zalloc(3 * n); r->B = zalloc(3 * nv);
   r->rest_sigma = zalloc(3 * n); r->rest_kappa = zalloc(3 * nv);
   r->muscle = zalloc(1 + n);
@@ -743,7 +827,7 @@ void ro_destroy(ro_rod *r) {
   double *ptrs[] = {r->x, r->v, r->Q, r->w, r->acc, r->alpha, r->rest_len, r->rest_vor, r->mass,
                     r->volume, r->radius, r->J, r->Jinv, r->S, r->B, r->rest_sigma, r->rest_kappa,
                     r->len, r->tang, r->dil, r->vdil, r->dil_rate, r->sigma, r->kappa, r->stress,
-                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->t_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag, r->rest_radius};
+                    r->couple, r->f_int, r->t_int, r->f_ext, r->t_ext, r->f_user, r->t_user, r->c_w, r->filt, r->tmp, r->ctmp, r->muscle, r->spl_pts, r->spl_mag, r->rest_radius, r->ml_act, r->ml_tmp};
   for (size_t i = 0; i < sizeof(ptrs) / sizeof(ptrs[0]); i++) free(ptrs[i]);
   free(r);
 }
@@ -779,6 +863,11 @@ void ro_set_tm_muscle(ro_rod *r, double max_stress, double radius_ref) {
   r->tm_on = max_stress != 0.0; r->tm_max_stress = max_stress; r->tm_radius_ref = radius_ref;
 }
 void ro_set_tm_activation(ro_rod *r, double activation) { r->tm_activation = activation; }
+void ro_set_muscle_layer(ro_rod *r, int slot, int kind, double max_stress, double radius_ref, double px, double py) {
+  if (slot < 0 || slot >= 3) return;
+  r->ml_kind[slot] = kind; r->ml_stress[slot] = max_stress; r->ml_rref[slot] = radius_ref; r->ml_px[slot] = px; r->ml_py[slot] = py;
+}
+double *ro_muscle_activation(ro_rod *r) { return r->ml_act; }
 double *ro_spline_points(ro_rod *r) { return r->spl_pts; }
 double *ro_spline_magnitude(ro_rod *r) { return r->spl_mag; }
 
@@ -903,6 +992,7 @@ struct ro_assembly {
   double hx[3], hv[3], hQ[9], hw[3], hF[3], hT[3];
   double h_mass, hJ[3], hJinv[3];
   double h_fixed_pos[3];
+  int head_fixed; double h_fix_x[3], h_fix_Q[9];   /* OneEndFixedBC on the head (reach_env.py:128-132) */
 };
 
 static void head_kinematic(ro_assembly *a, double prefac) {
@@ -967,12 +1057,19 @@ static void apply_joint(ro_assembly *a, int ai) {
     }
 }
 
+static void head_fix_values(ro_assembly *a) {   /* OneEndFixedBC.constrain_values: position / directors of "node 0" back to their initial values */
+  if (!a->head_fixed) return;
+  for (int i = 0; i < 3; i++) a->hx[i] = a->h_fix_x[i];
+  for (int i = 0; i < 9; i++) a->hQ[i] = a->h_fix_Q[i];
+}
+
 static void asm_substep(ro_assembly *a) {
   const double dt = a->cfg.dt, prefac = 0.5 * dt;
   for (int i = 0; i < a->n_arm; i++) phase_first_half(a->arm[i], NULL);   /* arms carry no BC of their own */
   head_kinematic(a, prefac);
   a->time += prefac;
   if (a->cfg.has_head) head_constrain_values(a);
+  head_fix_values(a);
   for (int i = 0; i < a->n_arm; i++) compute_internal_forces_and_torques(a->arm[i]);
   if (a->cfg.has_head)
     for (int i = 0; i < a->n_arm; i++) apply_joint(a, i);
@@ -990,11 +1087,13 @@ static void asm_substep(ro_assembly *a) {
     }
   }
   if (a->cfg.has_head) { a->hv[2] = 0.0; a->hw[0] = 0.0; a->hw[1] = 0.0; }   /* constraint.py:62-85 */
+  if (a->head_fixed) for (int i = 0; i < 3; i++) { a->hv[i] = 0.0; a->hw[i] = 0.0; }   /* OneEndFixedBC.constrain_rates, registered after */
   for (int i = 0; i < a->n_arm; i++) phase_rates(a->arm[i], NULL);
   for (int i = 0; i < a->n_arm; i++) phase_second_half(a->arm[i], NULL);
   head_kinematic(a, prefac);
   a->time += prefac;
   if (a->cfg.has_head) head_constrain_values(a);
+  head_fix_values(a);
   for (int i = 0; i < 3; i++) { a->hF[i] = 0.0; a->hT[i] = 0.0; }
 }
 
@@ -1022,6 +1121,11 @@ void ro_asm_destroy(ro_assembly *a) {
   if (!a) return;
   for (int i = 0; i < a->n_arm; i++) ro_destroy(a->arm[i]);
   free(a);
+}
+void ro_asm_set_head_fixed(ro_assembly *a, int on) {
+  a->head_fixed = on;
+  for (int i = 0; i < 3; i++) { a->h_fix_x[i] = a->hx[i]; if (on) { a->hv[i] = 0.0; a->hw[i] = 0.0; } }
+  for (int i = 0; i < 9; i++) a->h_fix_Q[i] = a->hQ[i];
 }
 void ro_asm_substeps(ro_assembly *a, int n_substeps) { for (int s = 0; s < n_substeps; s++) asm_substep(a); }
 ro_rod *ro_asm_arm(ro_assembly *a, int i) { return (i >= 0 && i < a->n_arm) ? a->arm[i] : NULL; }

@@ -80,6 +80,11 @@ void ro_set_sucker(ro_rod *, int slot, int index, double ratio);
  * scalar activation broadcast over the elements (crawl_env.py:242, arm_push_env.py:259,271).  max_stress = 0 disables. */
 void ro_set_tm_muscle(ro_rod *, double max_stress, double radius_ref);
 void ro_set_tm_activation(ro_rod *, double activation);
+/* General muscle layers with per-element activations (OctoReach-v0 / OctoArmTwo-v0): slot 0..2, kind 1 = longitudinal
+ * at material-frame offset (px, py) * radius, 2 = transverse (max_stress is handed over SIGNED: the transverse class
+ * passes -max_muscle_stress); ro_muscle_activation: (3, n) activations, one row per slot.  Same unpinned restatement. */
+void ro_set_muscle_layer(ro_rod *, int slot, int kind, double max_stress, double radius_ref, double px, double py);
+double *ro_muscle_activation(ro_rod *);
 double *ro_mass(ro_rod *);
 double *ro_internal_forces(ro_rod *);
 double *ro_internal_torques(ro_rod *);
@@ -116,6 +121,10 @@ typedef struct ro_assembly ro_assembly;
 ro_assembly *ro_asm_create(const ro_config *arm_cfgs /* [n_arm] */, const ro_asm_config *cfg);
 void ro_asm_destroy(ro_assembly *);
 void ro_asm_substeps(ro_assembly *, int n_substeps);
+/* OneEndFixedBC(constrained_position_idx=(0,), constrained_director_idx=(0,)) on the rigid head, registered after the
+ * BodyBoundaryCondition (/root/reference/gym_softrobot/envs/octopus/reach_env.py:128-132): the head is pinned at the
+ * pose it has when this is called, all its rates are zeroed. */
+void ro_asm_set_head_fixed(ro_assembly *, int on);
 ro_rod *ro_asm_arm(ro_assembly *, int i);   /* owned by the assembly */
 double ro_asm_time(const ro_assembly *);
 double *ro_asm_head_position(ro_assembly *);  /* (3) */

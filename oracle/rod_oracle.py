@@ -142,9 +142,13 @@ def lib(which="current"):
         L.ro_set_sucker.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.ro_set_tm_muscle.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.ro_set_tm_activation.argtypes = [C.c_void_p, C.c_double]
+        L.ro_set_muscle_layer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double]
+        L.ro_muscle_activation.restype = C.POINTER(C.c_double)
+        L.ro_muscle_activation.argtypes = [C.c_void_p]
         L.ro_asm_create.restype = C.c_void_p
         L.ro_asm_create.argtypes = [C.POINTER(ROConfig), C.POINTER(ROAsmConfig)]
         L.ro_asm_destroy.argtypes = [C.c_void_p]
+        L.ro_asm_set_head_fixed.argtypes = [C.c_void_p, C.c_int]
         L.ro_asm_substeps.argtypes = [C.c_void_p, C.c_int]
         L.ro_asm_arm.restype = C.c_void_p
         L.ro_asm_arm.argtypes = [C.c_void_p, C.c_int]
@@ -255,6 +259,17 @@ class OracleRod:
         """COOMM TransverseMuscle(rest_muscle_area=(radius / radius_ref)**2, max_muscle_stress) under ApplyMuscles."""
         self._L.ro_set_tm_muscle(self._h, float(max_stress), float(radius_ref))
 
+    def set_es_muscle_layers(self, radius_ref):
+        """create_es_muscle_layers (envs/octopus/build.py:292-338): LM at (0, -2/3, 0) rotated by +-pi/2 about the axis
+        (max stress 0.5), TM (max stress 1.0, sign flipped by the class); returns the (3, n) activation view."""
+        for slot, ang in enumerate((np.pi / 2, -np.pi / 2)):
+            c, s = np.cos(ang), np.sin(ang)
+            px, py = c * 0.0 - s * (-6 / 9), s * 0.0 + c * (-6 / 9)
+            self._L.ro_set_muscle_layer(self._h, slot, 1, 0.5, float(radius_ref), float(px), float(py))
+        self._L.ro_set_muscle_layer(self._h, 2, 2, -1.0, float(radius_ref), 0.0, 0.0)
+        p = self._L.ro_muscle_activation(self._h)
+        return np.ctypeslib.as_array(p, shape=(3 * self.n,)).reshape(3, self.n)
+
     def set_tm_activation(self, activation):
         self._L.ro_set_tm_activation(self._h, float(activation))
 
@@ -312,6 +327,10 @@ class OracleAssembly:
 
     def substeps(self, n):
         self._L.ro_asm_substeps(self._h, int(n))
+
+    def set_head_fixed(self, on=True):
+        """OneEndFixedBC on the rigid head (reach_env.py:128-132)."""
+        self._L.ro_asm_set_head_fixed(self._h, int(on))
 
     def close(self):
         if self._h:

@@ -430,3 +430,42 @@ def test_transverse_muscle_static_stretch_known_answer():
     assert 1.05 < e < 1.2
     np.testing.assert_allclose(rod.dilatation, e, rtol=1e-6)
     assert float(np.abs(rod.velocity_collection).max()) < 1e-5      # settled (1.2 s of heavy damping)
+
+
+def _reach_assembly(g):
+    """The C-oracle twin of ReachEnv.reset (reach_env.py:108-140): build_octopus_muscles + OneEndFixedBC on the head,
+    three muscle layers per arm with per-element activations."""
+    n, dt, hr, r0 = int(g["n_elems"]), float(g["time_step"]), 0.04, 0.013
+    angles = [22.5 + 45 * i for i in range(8)]
+    arms = []
+    for ang in angles:
+        c, s = np.cos(np.deg2rad(ang)), np.sin(np.deg2rad(ang))
+        arms.append(dict(n_elem=n, start=(c * hr, s * hr, 0.0), direction=(c, s, 0.0), normal=(0, 0, 1), base_length=0.25,
+                         base_radius=r0, density=1000.0, youngs_modulus=1.5e4, shear_modulus=1.5e4 / 1.5,
+                         damping_constant=0.2 * 1e-2 * (7e-5 / dt), tip_radius=0.0042))
+    head = dict(start=(0, 0, -2 * r0), direction=(0, 0, 1), normal=(0, 1, 0), length=2 * r0, radius=hr, density=50.0)
+    asm = ro.OracleAssembly(arms, dt, head=head, joint=dict(k=1e6, nu=1e-3, kt=1e2, radius=hr), angles_deg=angles)
+    asm.set_head_fixed(True)
+    acts = [rod.set_es_muscle_layers(r0) for rod in asm.arms]
+    return asm, acts, n
+
+
+def test_c_oracle_matches_octo_reach_fixture(golden_dir):
+    """Multi-rod C oracle with the general muscle layers (two off-axis longitudinal muscles + the transverse muscle,
+    per-element activations) and the pinned head vs the fixture the unmodified reference ReachEnv produced on the shims
+    (2 x 800 substeps, random activations in [0, 1] on all 480 muscle elements)."""
+    g = np.load(os.path.join(golden_dir, "octo_reach_seed42.npz"), allow_pickle=True)
+    asm, acts, n = _reach_assembly(g)
+    for i, a in enumerate(g["actions"]):
+        a = a.reshape(8, 3, n).astype(np.float64)       # reach_env.py:214-227
+        for k in range(8):
+            acts[k][...] = a[k]
+        asm.substeps(int(g["step_skip"]))
+        for k, rod in enumerate(asm.arms):
+            for gk, fk in MUSCLE_FIELDS.items():
+                assert _mrel(getattr(rod, fk), g[f"state{i + 1}/arm{k}/{gk}"], fk) < 1e-9, (i, k, gk)
+        for gk in ("position", "velocity", "director", "omega"):
+            ref = g[f"state{i + 1}/head/{gk}"]
+            np.testing.assert_array_equal(getattr(asm, "head_" + gk).reshape(ref.shape), ref)   # pinned: exactly still
+    tip = np.array([asm.arms[0].position_collection[:, -1]])
+    assert float(np.abs(g["state2/arm0/kappa"]).max()) > 1.0      # the longitudinal muscles bent the arms
