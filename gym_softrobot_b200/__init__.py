@@ -18,6 +18,8 @@ REGISTRY = {
     "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeEnv", {}),
     "SoftArmTracking-v0": ("gym_softrobot_b200.envs.soft_arm_tracking:SoftArmTrackingEnv", {}),
     "OctoCrawl-v0": ("gym_softrobot_b200.envs.octo_crawl:CrawlEnv", {}),
+    "OctoReach-v0": ("gym_softrobot_b200.envs.octo_reach:ReachEnv", {}),
+    "OctoArmTwo-v0": ("gym_softrobot_b200.envs.arm_two:ArmTwoEnv", {}),
     "OctoArmPush-v0": ("gym_softrobot_b200.envs.arm_push:ArmPushEnv", {}),
     "OctoArmPush-v1": ("gym_softrobot_b200.envs.arm_push:ArmPushEnv", dict(mode="continuous")),
     "OctoArmPullWeight-v0": ("gym_softrobot_b200.envs.arm_push:ArmPullWeightEnv", dict(mode="continuous")),
@@ -31,6 +33,8 @@ VECTOR_REGISTRY = {
     "ContinuumSnake-v0": ("gym_softrobot_b200.envs.snake:ContinuumSnakeVectorEnv", {}),
     "SoftArmTracking-v0": ("gym_softrobot_b200.envs.soft_arm_tracking:SoftArmTrackingVectorEnv", {}),
     "OctoCrawl-v0": ("gym_softrobot_b200.envs.octo_crawl:OctoCrawlVectorEnv", {}),
+    "OctoReach-v0": ("gym_softrobot_b200.envs.octo_reach:OctoReachVectorEnv", {}),
+    "OctoArmTwo-v0": ("gym_softrobot_b200.envs.arm_two:ArmTwoVectorEnv", {}),
     "OctoArmPush-v0": ("gym_softrobot_b200.envs.arm_push:ArmPushVectorEnv", {}),
     "OctoArmPush-v1": ("gym_softrobot_b200.envs.arm_push:ArmPushVectorEnv", dict(mode="continuous")),
     "OctoArmPullWeight-v0": ("gym_softrobot_b200.envs.arm_push:ArmPushVectorEnv",

@@ -21,7 +21,7 @@ MATH_FAST, MATH_FAITHFUL = 0, 1
 EXPORTED_SYMBOLS = [
     "sr_abi_version", "sr_last_error", "sr_create", "sr_destroy", "sr_obs_dim", "sr_action_dim",
     "sr_init_dim", "sr_reset", "sr_step", "sr_reset_host", "sr_step_host", "sr_observe",
-    "sr_get_state", "sr_set_state", "sr_copy_from", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_sucker", "sr_get_sucker_index", "sr_get_tm_activation", "sr_get_ext_loads", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_fallback_count", "sr_fallback_causes", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
+    "sr_get_state", "sr_set_state", "sr_copy_from", "sr_get_aux", "sr_get_head", "sr_get_rest_kappa", "sr_get_sucker", "sr_get_sucker_index", "sr_get_tm_activation", "sr_get_muscle_activation", "sr_get_fixed_suckers", "sr_get_ext_loads", "sr_get_muscle", "sr_get_spline", "sr_spline_basis", "sr_launch_count", "sr_fallback_count", "sr_fallback_causes", "sr_measure_fp64_peak", "sr_measure_fp64_peak_regs", "sr_selftest_reciprocals", "sr_probe_latency",
 ]
 
 
@@ -51,6 +51,9 @@ class SrConfig(C.Structure):
         ("tip_radius", C.c_double), ("sucker_on", C.c_int32), ("sucker_index", C.c_int32),
         ("taper_node_mean", C.c_int32), ("tm_muscle_on", C.c_int32),
         ("tm_max_stress", C.c_double), ("tm_radius_ref", C.c_double),
+        ("muscle_layers_on", C.c_int32), ("head_fixed", C.c_int32),
+        ("lm_max_stress", C.c_double), ("lm_px", C.c_double * 2), ("lm_py", C.c_double * 2),
+        ("n_fixed_sucker", C.c_int32), ("fixed_sucker_index", C.c_int32 * 3),
     ]
 
 
@@ -104,6 +107,8 @@ def load_library():
     L.sr_get_ext_loads.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     L.sr_get_sucker_index.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_get_tm_activation.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sr_get_muscle_activation.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sr_get_fixed_suckers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
     L.sr_get_muscle.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_get_spline.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int32)]
     L.sr_spline_basis.argtypes = [C.c_int32, C.c_double, C.c_void_p]
@@ -181,7 +186,8 @@ class Handle:
                  point_force_on_base=False, damping_before_constraints=False, laplace_filter_order=0,
                  device=0, dtype=DTYPE_F64, math=MATH_FAST, base_step=0.0, base_limit=0.0,
                  base_move_period=0.0, contact=None, n_rod=1, head=None, joint=None, muscle=None, spline=None,
-                 tip_radius=0.0, sucker_index=None, taper_node_mean=False, tm_muscle=None):
+                 tip_radius=0.0, sucker_index=None, taper_node_mean=False, tm_muscle=None,
+                 muscle_layers=None, head_fixed=False, fixed_suckers=None):
         self._lib = load_library()
         cfg = SrConfig()
         cfg.struct_size = C.sizeof(SrConfig)
@@ -229,6 +235,16 @@ class Handle:
         if tm_muscle is not None:   # dict: max_stress, radius_ref (TransverseMuscle of create_es_muscle_layers)
             cfg.tm_muscle_on = 1
             cfg.tm_max_stress, cfg.tm_radius_ref = float(tm_muscle["max_stress"]), float(tm_muscle["radius_ref"])
+        if muscle_layers is not None:   # dict: lm_max_stress, lm_positions [(px, py), (px, py)] in units of the radius
+            cfg.muscle_layers_on = 1
+            cfg.lm_max_stress = float(muscle_layers["lm_max_stress"])
+            for m, (px, py) in enumerate(muscle_layers["lm_positions"]):
+                cfg.lm_px[m], cfg.lm_py[m] = float(px), float(py)
+        cfg.head_fixed = int(head_fixed)
+        if fixed_suckers is not None:   # up to three node / element indices, one ControllableFixConstraint each
+            cfg.n_fixed_sucker = len(fixed_suckers)
+            for s_, loc in enumerate(fixed_suckers):
+                cfg.fixed_sucker_index[s_] = int(loc)
         self.n_rod = max(1, n_rod)
         self.cfg = cfg
         self._h = C.c_void_p()
@@ -405,6 +421,21 @@ class Handle:
         _check(self._lib.sr_get_tm_activation(self._h, C.byref(ptr)))
         ts = "<f8" if self.cfg.dtype == DTYPE_F64 else "<f4"
         return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod,), ts), device=f"cuda:{self.device}")
+
+    def muscle_activation_tensor(self):
+        """torch view [n_env * n_rod, 3, n_elem] (float64) of the per-element activations of the muscle layers:
+        longitudinal 1, longitudinal 2, transverse (sr_get_muscle_activation)."""
+        import torch
+        ptr = C.c_void_p()
+        _check(self._lib.sr_get_muscle_activation(self._h, C.byref(ptr)))
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod, 3, self.n_elem), "<f8"), device=f"cuda:{self.device}")
+
+    def fixed_sucker_tensor(self):
+        """torch view [n_env * n_rod, 3] (float64) of the fixed-index ControllableFixConstraint ratios (sr_get_fixed_suckers)."""
+        import torch
+        ptr = C.c_void_p()
+        _check(self._lib.sr_get_fixed_suckers(self._h, C.byref(ptr)))
+        return torch.as_tensor(_DevMem(ptr.value, (self.n_env * self.n_rod, 3), "<f8"), device=f"cuda:{self.device}")
 
     def ext_load_tensors(self):
         """(force, couple): torch views [n_env * n_rod, 3, n_elem + 1] / [.., 3, n_elem] of the external nodal forces

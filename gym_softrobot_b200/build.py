@@ -52,6 +52,9 @@ def translation_units():
         tus.append((f"packed_double_{nt}_g4", "inst_packed.cu",
                     ["-DSR_TU_T=double", "-DSR_TU_F64=1", f"-DSR_TU_NT={nt}", f"-DSR_TU_MINB={minb}", "-DSR_TU_GROUP=4"],
                     _COMMON + ["rod_kernel_packed.cuh"]))
+    tus.append(("packed_double_384_g5", "inst_packed.cu",     # tapered assembly + COOMM muscle layers (OctoReach / OctoArmTwo)
+                ["-DSR_TU_T=double", "-DSR_TU_F64=1", "-DSR_TU_NT=384", "-DSR_TU_MINB=1", "-DSR_TU_GROUP=5"],
+                _COMMON + ["rod_kernel_packed.cuh"]))
     return tus
 
 

@@ -11,6 +11,9 @@ namespace sr {
 template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE, bool FASTONLY, bool VARY = false>
 cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid, cudaStream_t s);
 
+// tapered multi-rod assembly with the COOMM muscle layers (two longitudinal + transverse, per-element activations)
+template <int NT> cudaError_t launch_packed_lmus_kernel(const RodArgs<double> &A, int rods_per_cta, int grid, cudaStream_t s);
+
 constexpr int LEAN_SCR_CONTACT = 21;   // rows of a stream-K slot's hand-over scratch (contact variant: 18 + the travelling wave's sin, cos, time)
 constexpr int LEAN_SCR_FOLD = 27;      // folded-tip variants: + position and velocity of the tip node
 // lean kernel (rod_kernel_lean.cuh; T = storage type: double = FP64, float = mixed precision); grid / split schedule in A.sk_*

@@ -21,8 +21,8 @@ constexpr int PACKED_MAX_THREADS = 1024;
 // the left of element 0), so the base thread needs no select when it reads "j-1"
 // shared-memory words: x(3) v(3) Q(9) | s(3) N(3), each row NT + 2 wide (+ 6 joint-reaction rows for
 // assemblies, + 1 element-length row for the spline-torque forcing of the contact / forcing variant)
-constexpr int packed_smem_words(int nt, bool multi, bool torque = false) {
-  return (multi ? 27 : 24) * (nt + 2);
+constexpr int packed_smem_words(int nt, bool multi, bool torque = false, bool lmus = false) {
+  return ((multi ? 27 : 24) + (lmus ? 7 : 0)) * (nt + 2);   // LMUS: + curvature (3), radius (1), muscle couple (3)
 }
 
 // LAPLACE / MOVING: compile the LaplaceDissipationFilter passes and the moving-base controller in
@@ -39,8 +39,13 @@ constexpr int packed_smem_words(int nt, bool multi, bool torque = false) {
 // /root/reference/gym_softrobot/envs/octopus/build_muscle_octopus.py:61-63) into per-thread registers instead of
 // the constant bank; only instantiated for the safe contact / multi-rod variants (168 registers, one CTA per SM).
 
+// LMUS (with VARY and MULTI): COOMM's `ApplyMuscles` over the whole layer set of create_es_muscle_layers
+// (envs/octopus/build.py:292-338) with per-element activations (OctoReach-v0 / OctoArmTwo-v0): two off-axis longitudinal
+// muscles + the transverse muscle, evaluated every substep; one more neighbour exchange (curvature and radius of the
+// neighbouring elements) and barrier per substep; optional OneEndFixedBC on the rigid head.
+
 template <typename T, int NT, int MINB, bool LAPLACE, bool MOVING, bool CONTACT, bool MULTI, bool TORQUE = false,
-          bool FASTONLY = false, bool VARY = false>
+          bool FASTONLY = false, bool VARY = false, bool LMUS = false>
 __global__ void __launch_bounds__(NT, MINB)
 rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -83,6 +88,8 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   T *rec = sh, *sn = sh + 18 * RS;
   if (AOS) { if (tid < 6) sn[6 * NT + tid] = T(0); }
   else if (tid < 6) sh_s[(tid % 3) * RS + NT + (tid / 3) * (3 * RS)] = T(0);  // zero slots of s and N
+  T *sh_M = sh + 27 * RS;             // LMUS: rows 0-2 curvature (zero slot NT), 3 element radius, 4-6 muscle couple
+  if (LMUS && tid < 3) sh_M[tid * RS + NT] = T(0);
   __syncthreads();
   // Barriers inside the substep loop: data only crosses threads of the same env group (a rod; an assembly's rods +
   // head), so the synchronisations are per group — named barriers over the warps that hold the group's threads; a
@@ -196,6 +203,25 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
   if constexpr (VARY) {
     if (A.tm_act && elem_ok) tm_gain = A.tm_act[rod] * A.elem_tab[ET_TM * A.stride + min(j, n - 1)];
   }
+  // COOMM muscle layers, per-element activations (constant during a launch): gains of the two longitudinal muscles
+  // = activation x max_stress x rest area, spacing of the neighbouring element centres, rest Voronoi length to the left
+  T lm_g0 = T(0), lm_g1 = T(0), lm_inv_ds = T(0), lm_rvl = T(0);
+  if constexpr (LMUS) {
+    if (elem_ok) {
+      const T *ma = A.mus_act + (size_t)rod * 3 * n;
+      const T area = A.elem_tab[ET_TM * A.stride + j];        // -max_stress(TM) x rest_muscle_area
+      lm_g0 = ma[j] * area * A.lm_gain;
+      lm_g1 = ma[n + j] * area * A.lm_gain;
+      tm_gain = ma[2 * n + j] * area;
+      const T *rl = A.elem_tab + ET_REST_LEN * A.stride;
+      const int ja = max(j - 1, 0), jb = min(j + 1, n - 1);
+      // s = cumsum(rest_lengths) - rest_lengths / 2 (muscle.py, restated): s[jb] - s[ja]
+      const T ds = T(0.5) * (rl[ja] + rl[jb]) + ((jb - ja == 2) ? rl[j] : T(0));
+      lm_inv_ds = T(1) / ds;
+      lm_rvl = A.elem_tab[ET_REST_VOR * A.stride + max(j - 1, 0)];
+    }
+  }
+  T lm_cpl[3] = {T(0), T(0), T(0)}, lm_kl[3] = {T(0), T(0), T(0)}, lm_kr[3] = {T(0), T(0), T(0)};
   // ControllableFixConstraint index of this rod: node / element it acts on (python indexing of arrays of n + 1 / n slots)
   int sk_node = A.sucker_index, sk_elem = A.sucker_index;
   if (A.sucker_idx && active) {
@@ -346,6 +372,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 
   // BodyBoundaryCondition on the head (utils/custom_elastica/constraint.py:43-58, 62-85)
   auto head_constrain_values = [&]() {
+    if (LMUS && A.head_fixed) return;   // OneEndFixedBC on top: zero rates keep the pose bit for bit (x += hh 0, Q <- R(0) Q)
     if (MULTI && hd) {
       x[2] = hd[18];
       Q[6] = T(0); Q[7] = T(0); Q[8] = T(1);
@@ -490,17 +517,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
         for (int i = 0; i < 3; i++) nst[i] = fma(Fm, Qdx[i], nst[i]);
       }
     }
+    auto publish_stress = [&]() {      // lab-frame stress resultant Q^T n / e of this element, for the neighbour to the right
 #pragma unroll
-    for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
+      for (int i = 0; i < 3; i++) sfl[i] = Q[i] * nst[0];
 #pragma unroll
-    for (int i = 0; i < 3; i++) sfl[i] = fma(Q[3 + i], nst[1], sfl[i]);
+      for (int i = 0; i < 3; i++) sfl[i] = fma(Q[3 + i], nst[1], sfl[i]);
 #pragma unroll
-    for (int i = 0; i < 3; i++) sfl[i] = fma(Q[6 + i], nst[2], sfl[i]);
+      for (int i = 0; i < 3; i++) sfl[i] = fma(Q[6 + i], nst[2], sfl[i]);
 #pragma unroll
-    for (int i = 0; i < 3; i++) {
-      sfl[i] *= inv_e_s;
-      if (!AOS) sh_s[i * RS + tid] = sfl[i];
-    }
+      for (int i = 0; i < 3; i++) {
+        sfl[i] *= inv_e_s;
+        if (!AOS) sh_s[i * RS + tid] = sfl[i];
+      }
+    };
+    if constexpr (!LMUS) publish_stress();   // (LMUS: the longitudinal muscles need the curvature first, see below)
 
     if (MULTI && active && first && has_head) {
       // FixedJoint2Rigid(head, -1, arm, 0) (utils/custom_elastica/joint.py:48-123 forces, :125-219 torques)
@@ -586,6 +616,56 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
 #pragma unroll
     for (int i = 0; i < 3; i++) { kp[i] = vec[i] * fs; tau[i] = K.B[i] * (CONTACT ? kp[i] - rk[i] : kp[i]); }
     cross3(kp, tau, kxt);
+    if constexpr (LMUS) {
+      // COOMM LongitudinalMuscle under ApplyMuscles (package outside the reference tree; published model restated in
+      // oracle/shims/coomm/actuations/muscles/muscle.py and oracle/rod_oracle.c:apply_muscle_layers): a muscle at
+      // material-frame offset x_m = (px, py, 0) r (r = current element radius) has
+      //   nu_m = sigma + e3 + kappa_e x x_m + d x_m / ds,   kappa_e = trapezoid of kappa (zero ghosts),
+      //   n_m = a sigma_max (A0 / e) h(|nu_m|) nu_m / |nu_m|,   couple x_m x n_m on the element.
+      // Its force loads the rod exactly like the rod's own stress resultant (Delta_h(Q^T n_m) on the nodes,
+      // (Q t e) x n_m l0 on the element), so e n_m joins nst[] ahead of the common 1 / e; the couple goes to the Voronoi
+      // points (average of the two elements) and comes back like the bending couple after the second barrier.
+      const T rad2 = K.vol_over_pi * ilg, rad = rad2 * rsqrt_nr(rad2);   // sqrt(V / (pi l))
+#pragma unroll
+      for (int i = 0; i < 3; i++) { lm_kr[i] = vor_ok ? kp[i] : T(0); sh_M[i * RS + tid] = lm_kr[i]; }
+      sh_M[3 * RS + tid] = rad;
+      grp_sync();
+      T ke[3], nu[3];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        lm_kl[i] = sh_M[i * RS + t_prev];
+        ke[i] = T(0.5) * (lm_kl[i] + lm_kr[i]);
+        nu[i] = K.inv_rest_len * Qdx[i];
+        lm_cpl[i] = T(0);
+      }
+      const T rad_a = (elem_ok && j > 0) ? sh_M[3 * RS + tid - 1] : rad;
+      const T rad_b = (elem_ok && j < n - 1) ? sh_M[3 * RS + tid + 1] : rad;
+      const T drad = (rad_b - rad_a) * lm_inv_ds;
+#pragma unroll
+      for (int m = 0; m < 2; m++) {
+        const T g = m ? lm_g1 : lm_g0;
+        if (g != T(0)) {
+          const T px = A.lm_px[m], py = A.lm_py[m], xm0 = px * rad, xm1 = py * rad;
+          T sm[3];
+          sm[0] = nu[0] - ke[2] * xm1 + px * drad;
+          sm[1] = nu[1] + ke[2] * xm0 + py * drad;
+          sm[2] = nu[2] + (ke[0] * xm1 - ke[1] * xm0);
+          const T len = sqrt_(dot3(sm, sm));
+          T hw = fma(fma(fma(T(3.06), len, T(-13.64)), len, T(18.01)), len, T(-6.44));
+          hw = hw > T(0) ? hw : T(0);
+          const T Fe = g * hw / len;                    // e x |n_m| / |nu_m|
+#pragma unroll
+          for (int i = 0; i < 3; i++) nst[i] = fma(Fe, sm[i], nst[i]);
+          const T Fn = Fe * inv_e;                      // n_m = Fn nu_m
+          lm_cpl[0] = fma(xm1, Fn * sm[2], lm_cpl[0]);
+          lm_cpl[1] = fma(-xm0, Fn * sm[2], lm_cpl[1]);
+          lm_cpl[2] += Fn * (xm0 * sm[1] - xm1 * sm[0]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) sh_M[(4 + i) * RS + tid] = lm_cpl[i];
+      publish_stress();
+    }
     T eps = (T(0.5) * (lgn + lg)) * K.inv_rest_vor;
     T ie3 = rcp_nr(eps * eps * eps);
     if (!vor_ok) ie3 = T(0);
@@ -670,6 +750,22 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       const double2 a0 = q[0], a1 = q[1], a2 = q[2];
       fint[0] = sfl[0] - a0.x; fint[1] = sfl[1] - a0.y; fint[2] = sfl[2] - a1.x;
       tq[0] = tql[0] + a1.y; tq[1] = tql[1] + a2.x; tq[2] = tql[2] + a2.y;
+    }
+    if constexpr (LMUS) {
+      // muscle couple on the Voronoi points m = (c_k + c_k+1) / 2; element k gets Delta_h(m) + A_h(kappa x m D)
+      if (elem_ok) {
+        T mr[3], ml[3], cr[3], cl[3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          mr[i] = vor_ok ? T(0.5) * (sh_M[(4 + i) * RS + tid + 1] + lm_cpl[i]) : T(0);
+          ml[i] = (j > 0) ? T(0.5) * (lm_cpl[i] + sh_M[(4 + i) * RS + tid - 1]) : T(0);
+        }
+        cross3(lm_kr, mr, cr);
+        cross3(lm_kl, ml, cl);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+          tq[i] += (mr[i] - ml[i]) + T(0.5) * (cr[i] * K.rest_vor + cl[i] * lm_rvl);
+      }
     }
     // generic per-element external loads (a forcing: what COOMM's ApplyMuscles would feed,
     // /root/reference/gym_softrobot/envs/octopus/build_muscle_octopus.py:171-176): nodal forces in the lab frame,
@@ -847,6 +943,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
           w[i] = fma(dt, A.head_Jinv[i] * (lt[i] + Tq[i]), w[i]);
         }
         v[2] = T(0); w[0] = T(0); w[1] = T(0);
+        if (LMUS && A.head_fixed) {   // OneEndFixedBC.constrain_rates, registered after the BodyBoundaryCondition
+#pragma unroll
+          for (int i = 0; i < 3; i++) { v[i] = T(0); w[i] = T(0); }
+        }
       }
     } else {
 #pragma unroll
@@ -910,6 +1010,20 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       else { constrain_rates(); dampen(); }
       // ControllableFixConstraint ("sucker", envs/octopus/controllable_constraint.py:46-69): the rates of one node /
       // element index are scaled by 1 - reduction_ratio (per rod, 0 = released); registered after the dampers
+      if constexpr (LMUS) {
+        // several ControllableFixConstraints at fixed, distinct indices (arm_two_env.py:133-145): node and element
+        // `index` of the rod scaled by 1 - reduction_ratio of that slot
+        if (A.msucker && active) {
+#pragma unroll
+          for (int sl = 0; sl < 3; sl++) {
+            if (sl < A.msucker_n && j == A.msucker_loc[sl]) {
+              const T f = T(1) - A.msucker[(size_t)rod * 3 + sl];
+#pragma unroll
+              for (int i = 0; i < 3; i++) { v[i] *= f; w[i] *= f; }
+            }
+          }
+        }
+      }
       if (A.sucker && active) {
         const T f = T(1) - A.sucker[rod];
         if (j == sk_node) {

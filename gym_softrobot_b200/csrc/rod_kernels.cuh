@@ -118,6 +118,14 @@ template <typename T> struct RodArgs {
   // items over through sk_scratch[slot][18][NT] / sk_flag[slot]
   int sk_rods_per_cta, sk_items, sk_split, sk_rodsync;   // sk_rodsync: per-rod named barriers inside the substep loop
   double *sk_scratch; int *sk_flag;
+  // ---- COOMM muscle layers with per-element activations (LMUS instantiation of the packed kernel; OctoReach-v0 /
+  // OctoArmTwo-v0: reach_env.py:214-227, arm_two_env.py:222-247, create_es_muscle_layers build.py:292-338) ----
+  const T *mus_act;                   // [n_rods][3][n_elem]: longitudinal 1, longitudinal 2, transverse; nullptr = off
+  T lm_px[2], lm_py[2];               // material-frame offset of the longitudinal muscles, in units of the element radius
+  T lm_gain;                          // max_stress(LM) / -max_stress(TM): scales row ET_TM (= -max_stress(TM) x rest area)
+  int head_fixed;                     // OneEndFixedBC on the rigid head (reach_env.py:128-132): all its rates are zeroed
+  // several ControllableFixConstraints per rod at fixed indices (arm_two_env.py:133-145): ratios [n_rods][3], nullptr = off
+  const T *msucker; int msucker_n, msucker_loc[3];
 };
 
 // per-thread copy of the element / node / Voronoi constants of a tapered rod, and the rows of the HBM table they come from

@@ -50,6 +50,8 @@ struct sr_handle {
   void *sucker = nullptr, *ext_force = nullptr, *ext_couple = nullptr, *elem_tab = nullptr;
   int32_t *sucker_idx = nullptr;   // per-rod ControllableFixConstraint index (python indexing)
   void *tm_act = nullptr;          // per-rod TransverseMuscle activation
+  double *mus_act = nullptr;       // per-element activations of the three muscle layers [n_rods][3][n_elem]
+  double *msucker = nullptr;       // ratios of the fixed-index ControllableFixConstraints [n_rods][3]
   int *redo = nullptr;   // per-env flags of the fast-only / fallback kernel pair
   unsigned long long *redo_count = nullptr, *h_redo_count = nullptr, pair_last_count = 0;
   cudaEvent_t pair_event = nullptr; bool pair_copy_pending = false;
@@ -404,6 +406,13 @@ template <int NT> int launch_tapered(sr_handle *h, sr::RodArgs<double> &A, cudaS
   if (rods_per_cta < 1) return fail(SR_E_INVALID, "environment does not fit one CTA of the packed kernel");
   const int grid = (A.n_env + rods_per_cta - 1) / rods_per_cta;
   A.sk_rodsync = rodsync_setting();
+  if (A.mus_act) {
+    if (NT != 384 || !multi) return fail(SR_E_INVALID, "muscle layers: multi-rod assemblies of at most 384 threads only");
+    cudaError_t el = sr::launch_packed_lmus_kernel<384>(A, rods_per_cta, grid, s);
+    h->launches++;
+    if (el != cudaSuccess) return cuda_fail("rod_packed_kernel (muscle layers) launch", el);
+    return SR_OK;
+  }
   cudaError_t e = multi ? sr::launch_packed_kernel<double, NT, 1, false, false, true, true, false, false, true>(A, rods_per_cta, grid, s)
                         : sr::launch_packed_kernel<double, NT, 1, false, false, true, false, false, false, true>(A, rods_per_cta, grid, s);
   h->launches++;
@@ -687,6 +696,23 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
     if (!(cfg->tip_radius > 0.0) || !(cfg->tm_radius_ref > 0.0))
       return fail(SR_E_INVALID, "sr_create: the transverse muscle is built for tapered rods (tip_radius > 0) and needs tm_radius_ref > 0");
   }
+  if (cfg->muscle_layers_on) {
+    if (!cfg->tm_muscle_on || !(cfg->tm_max_stress != 0.0) || !cfg->has_head || cfg->dtype != SR_DTYPE_F64 || cfg->n_elem < 3)
+      return fail(SR_E_INVALID, "sr_create: muscle_layers_on needs tm_muscle_on (non-zero tm_max_stress), FP64, n_elem >= 3 and a multi-rod assembly with a head");
+    if ((cfg->n_rod_per_env > 1 ? cfg->n_rod_per_env : 1) * (cfg->n_elem + 1) + 1 > 384)
+      return fail(SR_E_INVALID, "sr_create: muscle_layers_on: the assembly must fit one 384-thread CTA (n_rod * (n_elem + 1) + 1 <= 384)");
+    if (cfg->contact_on) return fail(SR_E_INVALID, "sr_create: muscle_layers_on is built without plane contact");
+    if (cfg->n_fixed_sucker < 0 || cfg->n_fixed_sucker > 3) return fail(SR_E_INVALID, "sr_create: n_fixed_sucker must be 0 .. 3");
+    for (int a = 0; a < cfg->n_fixed_sucker; a++) {
+      if (cfg->fixed_sucker_index[a] < 0 || cfg->fixed_sucker_index[a] >= cfg->n_elem)
+        return fail(SR_E_INVALID, "sr_create: fixed_sucker_index must address an element (0 .. n_elem - 1)");
+      for (int b = 0; b < a; b++)
+        if (cfg->fixed_sucker_index[a] == cfg->fixed_sucker_index[b])
+          return fail(SR_E_INVALID, "sr_create: fixed_sucker_index entries must be distinct");
+    }
+  } else if (cfg->head_fixed || cfg->n_fixed_sucker) {
+    return fail(SR_E_INVALID, "sr_create: head_fixed / n_fixed_sucker are honoured by the muscle-layer kernel only (muscle_layers_on)");
+  }
   if (cfg->model == SR_MODEL_SOFT_PENDULUM_3D && (cfg->bc_kind != SR_BC_MOVING_BASE || !(cfg->base_move_period > 0.0)))
     return fail(SR_E_INVALID, "sr_create: SoftPendulum3D needs SR_BC_MOVING_BASE and base_move_period > 0");
   if (!(cfg->dt > 0.0) || !(cfg->base_length > 0.0) || !(cfg->base_radius > 0.0) || !(cfg->density > 0.0) ||
@@ -785,6 +811,22 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
       return fail(SR_E_ALLOC, m);
     }
   }
+  if (cfg->muscle_layers_on) {
+    const size_t sb = n_rods * 3 * (size_t)cfg->n_elem * sizeof(double);
+    if ((e = cudaMalloc(&h->mus_act, sb)) != cudaSuccess || (e = cudaMemset(h->mus_act, 0, sb)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
+  if (cfg->n_fixed_sucker > 0) {
+    const size_t sb = n_rods * 3 * sizeof(double);
+    if ((e = cudaMalloc(&h->msucker, sb)) != cudaSuccess || (e = cudaMemset(h->msucker, 0, sb)) != cudaSuccess) {
+      std::string m = std::string("sr_create: allocation failed: ") + cudaGetErrorString(e);
+      sr_destroy(h);
+      return fail(SR_E_ALLOC, m);
+    }
+  }
   if (cfg->tip_radius > 0.0) {
     // SURVEY A.1 / A.4 per element: radius_k = linspace(base, tip, n)[k]; uniform rest lengths L/n (the per-element
     // deviation of the reference's linspace positions is carried by F_GAMMA as for uniform rods)
@@ -844,6 +886,12 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
   h->a64.sucker = (const double *)h->sucker; h->a64.sucker_index = cfg->sucker_index; h->a64.elem_tab = (const double *)h->elem_tab;
   h->a64.sucker_idx = h->sucker_idx; h->a64.tm_act = (const double *)h->tm_act;
   h->a64.muscle = h->muscle;
+  h->a64.mus_act = h->mus_act; h->a64.head_fixed = cfg->head_fixed;
+  h->a64.lm_gain = cfg->muscle_layers_on ? cfg->lm_max_stress / -cfg->tm_max_stress : 0.0;
+  for (int m = 0; m < 2; m++) { h->a64.lm_px[m] = cfg->lm_px[m]; h->a64.lm_py[m] = cfg->lm_py[m]; h->a32.lm_px[m] = h->a32.lm_py[m] = 0.0f; }
+  h->a32.mus_act = nullptr; h->a32.head_fixed = 0; h->a32.lm_gain = 0.0f;
+  h->a64.msucker = h->msucker; h->a64.msucker_n = cfg->n_fixed_sucker; h->a32.msucker = nullptr; h->a32.msucker_n = 0;
+  for (int a = 0; a < 3; a++) h->a64.msucker_loc[a] = h->a32.msucker_loc[a] = (a < cfg->n_fixed_sucker) ? cfg->fixed_sucker_index[a] : -1;
   h->a64.state = (double *)h->state; h->a64.bc = (const double *)h->bc; h->a64.aux = (double *)h->aux;
   h->a64.action_dim = h->action_dim; h->a64.obs_dim = h->obs_dim; h->a64.head = (double *)h->head;
   fill_args<float>(*cfg, h->stride, h->a32);
@@ -861,6 +909,7 @@ int sr_create(const sr_config *cfg, sr_handle **out) {
 void sr_destroy(sr_handle *h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  cudaFree(h->mus_act); cudaFree(h->msucker);
   cudaFree(h->state); cudaFree(h->bc); cudaFree(h->aux); cudaFree(h->rest_kappa); cudaFree(h->head); cudaFree(h->muscle); cudaFree(h->spline); cudaFree(h->spline_tab); cudaFree(h->redo); cudaFree(h->redo_count); cudaFree(h->sucker); cudaFree(h->sucker_idx); cudaFree(h->tm_act); cudaFree(h->ext_force); cudaFree(h->ext_couple); cudaFree(h->elem_tab); cudaFree(h->sk_scratch); cudaFree(h->sk_flag); cudaFreeHost(h->h_redo_count); if (h->pair_event) cudaEventDestroy(h->pair_event); cudaFree(h->d_action); cudaFree(h->d_obs);
   cudaFree(h->d_reward); cudaFree(h->d_term); cudaFree(h->d_init); cudaFree(h->d_idx);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward); cudaFreeHost(h->h_term);
@@ -1090,6 +1139,20 @@ int sr_get_sucker_index(sr_handle *h, int32_t **index_dev) {
   return SR_OK;
 }
 
+int sr_get_fixed_suckers(sr_handle *h, void **ratio_dev) {
+  if (!h || !ratio_dev) return fail(SR_E_INVALID, "sr_get_fixed_suckers: null argument");
+  if (!h->msucker) return fail(SR_E_INVALID, "sr_get_fixed_suckers: handle was created without n_fixed_sucker");
+  *ratio_dev = h->msucker;
+  return SR_OK;
+}
+
+int sr_get_muscle_activation(sr_handle *h, void **activation_dev) {
+  if (!h || !activation_dev) return fail(SR_E_INVALID, "sr_get_muscle_activation: null argument");
+  if (!h->mus_act) return fail(SR_E_INVALID, "sr_get_muscle_activation: handle was created without muscle_layers_on");
+  *activation_dev = h->mus_act;
+  return SR_OK;
+}
+
 int sr_get_tm_activation(sr_handle *h, void **activation_dev) {
   if (!h || !activation_dev) return fail(SR_E_INVALID, "sr_get_tm_activation: null argument");
   if (!h->tm_act) return fail(SR_E_INVALID, "sr_get_tm_activation: handle was created without tm_muscle_on");
@@ -1169,6 +1232,8 @@ int sr_copy_from(sr_handle *dst, sr_handle *src, void *stream) {
   if (src->sucker && dst->sucker) SR_CUDA(cp(dst->sucker, src->sucker, n_rods * es));
   if (src->sucker_idx && dst->sucker_idx) SR_CUDA(cp(dst->sucker_idx, src->sucker_idx, n_rods * sizeof(int32_t)));
   if (src->tm_act && dst->tm_act) SR_CUDA(cp(dst->tm_act, src->tm_act, n_rods * es));
+  if (src->msucker && dst->msucker) SR_CUDA(cp(dst->msucker, src->msucker, n_rods * 3 * sizeof(double)));
+  if (src->mus_act && dst->mus_act) SR_CUDA(cp(dst->mus_act, src->mus_act, n_rods * 3 * (size_t)src->cfg.n_elem * sizeof(double)));
   if (src->ext_force) {
     void *f = nullptr, *c = nullptr;
     int rc = sr_get_ext_loads(dst, &f, &c);

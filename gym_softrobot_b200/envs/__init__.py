@@ -6,3 +6,5 @@ from .snake import ContinuumSnakeEnv, ContinuumSnakeVectorEnv, snake_contact_par
 from .soft_arm_tracking import SoftArmTrackingEnv, SoftArmTrackingVectorEnv, target_trajectory
 from .arm_push import ArmPushEnv, ArmPullWeightEnv, ArmPushVectorEnv, arm_push_node_masses, arm_push_energy_tables
 from .octo_crawl import CrawlEnv, OctoCrawlVectorEnv, crawl_init_params
+from .octo_reach import ReachEnv, OctoReachVectorEnv, es_longitudinal_positions
+from .arm_two import ArmTwoEnv, ArmTwoVectorEnv, two_arm_init_params, activation_interp_matrix

@@ -138,6 +138,21 @@ typedef struct sr_config {
    * the reference tree: the published model is restated. */
   int32_t tm_muscle_on;
   double tm_max_stress, tm_radius_ref;
+  /* The whole layer set of create_es_muscle_layers with PER-ELEMENT activations (OctoReach-v0, OctoArmTwo-v0:
+   * envs/octopus/reach_env.py:214-227, arm_two_env.py:222-247): two `LongitudinalMuscle(max_muscle_stress=
+   * lm_max_stress)` at material-frame offsets (lm_px[m], lm_py[m]) x element radius (ratio_muscle_position rotated by
+   * muscle_init_angle) plus the transverse muscle above.  Needs tm_muscle_on and a multi-rod assembly of tapered rods;
+   * activations: sr_get_muscle_activation (the per-rod scalars of sr_get_tm_activation are then ignored). */
+  int32_t muscle_layers_on;
+  /* OneEndFixedBC(constrained_position_idx=(0,), constrained_director_idx=(0,)) on the rigid head, on top of its
+   * BodyBoundaryCondition (envs/octopus/reach_env.py:128-132): the head stays at its reset pose, all rates zero.
+   * Honoured by the muscle-layer kernel only (muscle_layers_on). */
+  int32_t head_fixed;
+  double lm_max_stress, lm_px[2], lm_py[2];
+  /* Up to three ControllableFixConstraints per rod at FIXED, distinct node / element indices (OctoArmTwo-v0:
+   * envs/octopus/arm_two_env.py:78-82,133-145) next to the muscle layers (muscle_layers_on); the reduction ratios are
+   * device data [n_env * n_rod_per_env][3] the caller writes every step (sr_get_fixed_suckers).  0 = none. */
+  int32_t n_fixed_sucker, fixed_sucker_index[3];
 } sr_config;
 
 /* Device views of the structure-of-arrays state (replaces the NumPy views the
@@ -208,6 +223,14 @@ int sr_get_sucker_index(sr_handle *h, int32_t **index_dev);
 /* Per-rod activation of the transverse muscle, [n_env * n_rod_per_env] of the handle's element type (needs tm_muscle_on);
  * what `muscle_layers[2].apply_activation(a)` sets (crawl_env.py:242, arm_push_env.py:259,271). */
 int sr_get_tm_activation(sr_handle *h, void **activation_dev);
+/* Per-element activations of the three muscle layers, [n_env * n_rod_per_env][3][n_elem] doubles: longitudinal 1,
+ * longitudinal 2, transverse (needs muscle_layers_on); replaces `muscle.apply_activation(array)` of
+ * envs/octopus/reach_env.py:221-225 / arm_two_env.py:243-245.  Constant during a launch; zeroed by sr_create only. */
+int sr_get_muscle_activation(sr_handle *h, void **activation_dev);
+/* Reduction ratios of the fixed-index ControllableFixConstraints, [n_env * n_rod_per_env][3] doubles (slot s acts on
+ * index fixed_sucker_index[s]; needs n_fixed_sucker > 0); replaces `controller.reduction_ratio = ...` of
+ * envs/octopus/arm_two_env.py:233-234.  Zeroed (released) by sr_create only. */
+int sr_get_fixed_suckers(sr_handle *h, void **ratio_dev);
 /* Generic per-element external loads evaluated every substep as a forcing (what COOMM's ApplyMuscles would feed,
  * envs/octopus/build_muscle_octopus.py:171-176): nodal forces in the lab frame, [n_rods][3][stride] slots 0..n_elem,
  * and element couples in the material frame, [n_rods][3][stride] slots 0..n_elem-1, of the handle's element type;

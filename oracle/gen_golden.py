@@ -561,6 +561,41 @@ def gen_octo_reach(seed=42, n=2):
     print("octo reach:", rew, term, trunc, "tip0", e.shearable_rods[0].position_collection[:, -1])
 
 
+def gen_octo_arm_two(seed=42, n=3):
+    """OctoArmTwo-v0: build_two_arms (two tapered arms at 90 / 270 degrees, free head), three fixed-index
+    ControllableFixConstraints per arm, cubic-interpolated per-element activations of all three muscles
+    (/root/reference/gym_softrobot/envs/octopus/arm_two_env.py)."""
+    env = ref_loader.load_reference_env("OctoArmTwo-v0")
+    obs0, _ = env.reset(seed=seed)
+    env.action_space.seed(seed)
+    e = env.unwrapped
+    out = {"label": COOMM_LABEL, "seed": seed, "obs0": obs0, "step_skip": e.step_skip, "time_step": e.time_step,
+           "n_elems": e.n_elems, "sucker_location": np.array(e.sucker_location)}
+
+    def snap(tag):
+        for a, rod in enumerate(e.shearable_rods):
+            pack(f"{tag}/arm{a}", rod_state(rod), out)
+        h = e.rigid_rod
+        out[f"{tag}/head/position"] = h.position_collection.copy()
+        out[f"{tag}/head/velocity"] = h.velocity_collection.copy()
+        out[f"{tag}/head/director"] = h.director_collection.copy()
+        out[f"{tag}/head/omega"] = h.omega_collection.copy()
+
+    snap("state0")
+    acts, obs, rew, term, trunc, musc = [], [], [], [], [], []
+    for i in range(n):
+        a = env.action_space.sample()
+        o, r, te, tr, info = env.step(a)
+        acts.append(a); obs.append(o); rew.append(r); term.append(te); trunc.append(tr)
+        musc.append(np.array([[m.activation.copy() for m in arm] for arm in e.muscle_activations]))
+        snap(f"state{i + 1}")
+    out.update(actions=np.array(acts, dtype=np.float32), obs=np.array(obs, dtype=np.float32),
+               reward=np.array(rew, dtype=np.float64), terminated=np.array(term), truncated=np.array(trunc),
+               muscle_activations=np.array(musc))
+    np.savez_compressed(os.path.join(OUT, f"octo_arm_two_seed{seed}.npz"), **out)
+    print("octo arm two:", rew, term, trunc, "head", e.rigid_rod.position_collection[:, 0])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "snake":
@@ -584,6 +619,9 @@ if __name__ == "__main__":
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "reach":
         gen_octo_reach()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "arm_two":
+        gen_octo_arm_two()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "coomm":
         gen_arm_push("OctoArmPush-v0", "octo_arm_push_v0")
@@ -616,5 +654,6 @@ if __name__ == "__main__":
     gen_arm_push_early()
     gen_octo_crawl()
     gen_octo_reach()
+    gen_octo_arm_two()
     gen_snake()   # ~25 min of NumPy stepping
     gen_snake_perturbed()   # another ~25 min

@@ -44,3 +44,6 @@ if "softarm" in which: e2e("SoftArmTracking-v0", 16384, (8,), -0.3, 0.3, 10, dty
 if "push" in which: e2e("OctoArmPush-v1", 4096, (2,), np.float32(0.0), np.float32(1.0), 5)
 if "pull" in which: e2e("OctoArmPullWeight-v0", 4096, (2,), np.float32(0.0), np.float32(1.0), 3)
 if "crawl" in which: e2e("OctoCrawl-v0", 1024, (24,), np.float32(0.0), np.float32(1.0), 3)
+# the muscle-layer kernel (two longitudinal + the transverse muscle, per-element activations)
+if "reach" in which: e2e("OctoReach-v0", 1024, (480,), np.float32(0.0), np.float32(1.0), 3, W=2)
+if "armtwo" in which: e2e("OctoArmTwo-v0", 4096, (18,), np.float32(0.0), np.float32(1.0), 3, W=2)

@@ -469,3 +469,38 @@ def test_c_oracle_matches_octo_reach_fixture(golden_dir):
             np.testing.assert_array_equal(getattr(asm, "head_" + gk).reshape(ref.shape), ref)   # pinned: exactly still
     tip = np.array([asm.arms[0].position_collection[:, -1]])
     assert float(np.abs(g["state2/arm0/kappa"]).max()) > 1.0      # the longitudinal muscles bent the arms
+
+
+def test_c_oracle_matches_octo_arm_two_fixture(golden_dir):
+    """Multi-rod C oracle vs the fixture the unmodified reference ArmTwoEnv produced on the shims (3 x 800 substeps):
+    two tapered arms at 90 / 270 degrees on a free head (BodyBoundaryCondition only), three fixed-index
+    ControllableFixConstraints per arm whose ratios the action sets, cubic-interpolated per-element activations of both
+    longitudinal muscles and the transverse muscle (arm_two_env.py:222-247)."""
+    g = np.load(os.path.join(golden_dir, "octo_arm_two_seed42.npz"), allow_pickle=True)
+    n, dt, hr, r0 = int(g["n_elems"]), float(g["time_step"]), 0.04, 0.013
+    angles = [90.0, 270.0]
+    arms = []
+    for k, ang in enumerate(angles):
+        p0 = g[f"state0/arm{k}/position"]
+        d = (p0[:, -1] - p0[:, 0]) / np.linalg.norm(p0[:, -1] - p0[:, 0])
+        arms.append(dict(n_elem=n, start=tuple(p0[:, 0]), direction=tuple(d), normal=(0, 0, 1), base_length=0.25,
+                         base_radius=r0, density=1000.0, youngs_modulus=1.5e4, shear_modulus=1.5e4 / 1.5,
+                         damping_constant=0.2 * 1e-2 * (7e-5 / dt), tip_radius=0.0042))
+    head = dict(start=(0, 0, -2 * r0), direction=(0, 0, 1), normal=(0, 1, 0), length=2 * r0, radius=hr, density=50.0)
+    asm = ro.OracleAssembly(arms, dt, head=head, joint=dict(k=1e6, nu=1e-3, kt=1e2, radius=hr), angles_deg=angles)
+    acts = [rod.set_es_muscle_layers(r0) for rod in asm.arms]
+    loc = [int(v) for v in g["sucker_location"]]
+    assert loc == [3, 9, 15]
+    for i, a in enumerate(g["actions"]):
+        a = a.reshape(2, 9)
+        for k, rod in enumerate(asm.arms):
+            for s_ in range(3):
+                rod.set_sucker(s_, loc[s_], float(a[k, s_]))          # arm_two_env.py:233-234
+            acts[k][...] = g["muscle_activations"][i, k]
+        asm.substeps(int(g["step_skip"]))
+        for k, rod in enumerate(asm.arms):
+            for gk, fk in MUSCLE_FIELDS.items():
+                assert _mrel(getattr(rod, fk), g[f"state{i + 1}/arm{k}/{gk}"], fk) < 1e-9, (i, k, gk)
+        for gk in ("position", "velocity", "director", "omega"):
+            ref = g[f"state{i + 1}/head/{gk}"]
+            assert _mrel(getattr(asm, "head_" + gk).reshape(ref.shape), ref, gk + "_collection") < 2e-9, (i, gk)
