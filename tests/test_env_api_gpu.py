@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 
 IDS = ["SoftPendulum-v0", "SoftPendulum3D-v0", "OctoArmSingle-v0", "OctoFlat-v0", "OctoFlatLite-v0",
        "ContinuumSnake-v0", "SoftArmTracking-v0", "OctoCrawl-v0", "OctoArmPush-v0", "OctoArmPush-v1",
-       "OctoArmPullWeight-v0"]
+       "OctoArmPullWeight-v0", "OctoReach-v0", "OctoArmTwo-v0"]
 INFO_KEY = {"ContinuumSnake-v0": None, "SoftArmTracking-v0": "ctime"}     # what the reference env puts in info
 FAST_KW = {"OctoArmSingle-v0": dict(recording_fps=100), "OctoFlat-v0": dict(recording_fps=100),
            "OctoFlatLite-v0": dict(recording_fps=100)}
