@@ -504,3 +504,26 @@ def test_c_oracle_matches_octo_arm_two_fixture(golden_dir):
         for gk in ("position", "velocity", "director", "omega"):
             ref = g[f"state{i + 1}/head/{gk}"]
             assert _mrel(getattr(asm, "head_" + gk).reshape(ref.shape), ref, gk + "_collection") < 2e-9, (i, gk)
+
+
+def test_longitudinal_muscle_first_substep_known_answer():
+    """Closed-form check of the restated longitudinal muscle (independent of any fixture): a straight, uniform, undamped
+    rod at rest with muscle 1 (offset +2/3 r on d1, max stress 0.5, rest area 1) activated uniformly at a.  At the first
+    force evaluation l_m = 1, h(1) = 0.99, n_m = F d3 with F = 0.5 a 0.99 on every element and the couple x_m x n_m =
+    -(2/3 r) F d2 is uniform: Delta_h leaves +-F on the end nodes and -+(2/3 r) F about d2 on the end elements only, so
+    after one substep  v_x[0] = -v_x[n] = dt F / (rho pi r^2 l0 / 2),  w_2[0] = -w_2[n-1] = -dt (2/3 r) F / (rho pi r^4 / 4 l0),
+    everything else zero."""
+    n, L, r0, E, a, rho, dt = 10, 0.2, 0.012, 1e4, 0.6, 700.0, 1e-5
+    rod = ro.OracleRod(n, (0, 0, 0), (1, 0, 0), (0, 1, 0), L, r0, rho, E, dt, shear_modulus=E / 1.5,
+                       damping_constant=0.0, tip_radius=r0, taper_node_mean=True)
+    act = rod.set_es_muscle_layers(r0)
+    act[0, :] = a
+    rod.substeps(1)
+    F, l0 = 0.5 * a * (3.06 - 13.64 + 18.01 - 6.44), L / n
+    v_end = dt * F / (rho * np.pi * r0 ** 2 * l0 / 2)
+    w_end = -dt * (2 / 3 * r0) * F / (rho * np.pi * r0 ** 4 / 4 * l0)
+    v, w = rod.velocity_collection, rod.omega_collection
+    np.testing.assert_allclose([v[0, 0], v[0, -1]], [v_end, -v_end], rtol=1e-12)
+    np.testing.assert_allclose([w[1, 0], w[1, -1]], [w_end, -w_end], rtol=1e-12)
+    assert float(np.abs(v[:, 1:-1]).max()) < 1e-15 * v_end and float(np.abs(w[:, 1:-1]).max()) == 0.0
+    assert float(np.abs(v[1:]).max()) == 0.0 and float(np.abs(w[[0, 2]]).max()) < 1e-15 * abs(w_end)
