@@ -650,10 +650,10 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
           sm[0] = nu[0] - ke[2] * xm1 + px * drad;
           sm[1] = nu[1] + ke[2] * xm0 + py * drad;
           sm[2] = nu[2] + (ke[0] * xm1 - ke[1] * xm0);
-          const T len = sqrt_(dot3(sm, sm));
+          const T l2m = dot3(sm, sm), ilm = rsqrt_nr(l2m), len = l2m * ilm;   // |nu_m| and its reciprocal (Newton-refined, ~1 ulp)
           T hw = fma(fma(fma(T(3.06), len, T(-13.64)), len, T(18.01)), len, T(-6.44));
           hw = hw > T(0) ? hw : T(0);
-          const T Fe = g * hw / len;                    // e x |n_m| / |nu_m|
+          const T Fe = g * hw * ilm;                    // e x |n_m| / |nu_m|
 #pragma unroll
           for (int i = 0; i < 3; i++) nst[i] = fma(Fe, sm[i], nst[i]);
           const T Fn = Fe * inv_e;                      // n_m = Fn nu_m

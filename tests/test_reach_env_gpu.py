@@ -246,3 +246,110 @@ def test_octo_arm_two_env_golden(golden_dir):
         assert (te, tr) == (bool(g["terminated"][i]), bool(g["truncated"][i]))
     print(f"OctoArmTwo-v0: worst field error {worst:.2e}, worst error / bound {worst_ratio:.2f}")
     env.close()
+
+
+@pytest.mark.parametrize("n_elems,time_step,fps", [(11, 5e-5, 100), (40, 2e-5, 250)], ids=["n11-three-envs-per-cta", "n40-one-env-per-cta"])
+def test_octo_reach_other_arm_resolutions_vs_c_oracle(n_elems, time_step, fps):
+    """The muscle-layer kernel away from the default 20 elements per arm: 11 (three env groups per 384-thread CTA, warps
+    shared between groups) and 40 (one group of 329 threads per CTA: CTA-wide barriers), random per-element activations,
+    live against the C oracle.  Two envs with different actions, so that a mix-up between env groups would show."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    rng = np.random.default_rng(n_elems)
+    vec = gsb.make_vec("OctoReach-v0", 2, n_elems=n_elems, time_step=time_step, recording_fps=fps, autoreset=False)
+    vec.reset(seed=1)
+    skip = vec.step_skip
+    acts = rng.random((2, 2, 8 * 3 * n_elems)).astype(np.float32)          # [step, env, action]
+    worst = 0.0
+    for env_i in range(2):
+        seq = [acts[s, env_i] for s in range(2)]
+        oracle = _reach_oracle(n_elems, time_step, seq, skip)
+        reps = [_reach_oracle(n_elems, time_step, seq, skip, perturb=1e-13, seed=5), _reach_oracle(n_elems, time_step, seq, skip, variant="fma")]
+        if env_i == 0:
+            states = []
+            for s in range(2):
+                vec.step(torch.as_tensor(acts[s], device=vec.device))
+                states.append({k: v.cpu().numpy() for k, v in vec.fields().items()})
+        for s in range(2):
+            oasm, rasm = next(oracle), [next(r_) for r_ in reps]
+            for arm in range(8):
+                for gk, fk in FIELDS.items():
+                    ref = getattr(oasm.arms[arm], fk)
+                    sens = max(float(np.abs(getattr(q.arms[arm], fk) - ref).max()) for q in rasm)
+                    scale = max(float(np.abs(ref).max()), FLOOR[fk])
+                    e = float(np.abs(states[s][fk][env_i, arm] - ref).max())
+                    worst = max(worst, e / scale)
+                    assert e <= max(TOL * scale, 20 * sens), \
+                        f"env {env_i} step {s} arm {arm} {gk}: {e / scale:.3e} (oracle replicas: {sens / scale:.1e})"
+    print(f"OctoReach-v0 n_elems={n_elems}: worst field error {worst:.2e}")
+    vec.close()
+
+
+def test_octo_arm_two_other_resolution_vs_c_oracle():
+    """OctoArmTwo-v0 at 30 elements per arm (suckers at elements 5 / 15 / 25; 384 // 63 = 6 env groups per CTA), three envs
+    with different actions, 2 env-steps live against the C oracle (activations taken from the env's own host-side map,
+    which test_octo_arm_two_env_golden checks against scipy)."""
+    import torch
+    import rod_oracle as ro
+    import gym_softrobot_b200 as gsb
+    from gym_softrobot_b200.envs.arm_two import two_arm_init_params
+    n, dt, fps = 30, 3e-5, 200
+    rng = np.random.default_rng(30)
+    vec = gsb.make_vec("OctoArmTwo-v0", 3, n_elems=n, time_step=dt, recording_fps=fps, autoreset=False)
+    assert vec.sucker_location == [5, 15, 25]
+    vec.reset()
+    acts = rng.random((2, 3, 18)).astype(np.float32)
+    init, angles = two_arm_init_params()
+    hr, r0 = 0.04, 0.013
+    arms = [dict(n_elem=n, start=init[0, 9 * a:9 * a + 3], direction=init[0, 9 * a + 3:9 * a + 6], normal=init[0, 9 * a + 6:9 * a + 9],
+                 base_length=0.25, base_radius=r0, density=1000.0, youngs_modulus=1.5e4, shear_modulus=1.5e4 / 1.5,
+                 damping_constant=0.2 * 1e-2 * (7e-5 / dt), tip_radius=0.0042) for a in range(2)]
+    head = dict(start=(0, 0, -2 * r0), direction=(0, 0, 1), normal=(0, 1, 0), length=2 * r0, radius=hr, density=50.0)
+
+    def make(perturb=0.0, variant=None):
+        mk = lambda: ro.OracleAssembly(arms, dt, head=head, joint=dict(k=1e6, nu=1e-3, kt=1e2, radius=hr), angles_deg=angles)
+        if variant:
+            with ro.variant(variant):
+                asm = mk()
+        else:
+            asm = mk()
+        views = [rod.set_es_muscle_layers(r0) for rod in asm.arms]
+        if perturb:
+            prng = np.random.default_rng(5)
+            for rod in asm.arms:
+                rod.position_collection[...] *= 1.0 + perturb * prng.standard_normal(rod.position_collection.shape)
+        return asm, views
+
+    systems = [[make(), make(1e-13), make(variant="fma")] for _ in range(3)]
+    worst = 0.0
+    for s in range(2):
+        a = torch.as_tensor(acts[s], device=vec.device)
+        mus = vec.muscle_activations(a).cpu().numpy()                       # [env, arm, 3, n]
+        vec.step(a)
+        st = {k: v.cpu().numpy() for k, v in vec.fields().items()}
+        hd = vec.handle.head_tensor().cpu().numpy()
+        for e_i in range(3):
+            for asm, views in systems[e_i]:
+                for k, rod in enumerate(asm.arms):
+                    for s_ in range(3):
+                        rod.set_sucker(s_, vec.sucker_location[s_], float(acts[s, e_i].reshape(2, 9)[k, s_]))
+                    views[k][...] = mus[e_i, k]
+                asm.substeps(vec.step_skip)
+            (oasm, _), reps = systems[e_i][0], [q for q, _ in systems[e_i][1:]]
+            for arm in range(2):
+                for gk, fk in FIELDS.items():
+                    ref = getattr(oasm.arms[arm], fk)
+                    sens = max(float(np.abs(getattr(q.arms[arm], fk) - ref).max()) for q in reps)
+                    scale = max(float(np.abs(ref).max()), FLOOR[fk])
+                    err = float(np.abs(st[fk][e_i, arm] - ref).max())
+                    worst = max(worst, err / scale)
+                    assert err <= max(TOL * scale, 20 * sens), \
+                        f"env {e_i} step {s} arm {arm} {gk}: {err / scale:.3e} (oracle replicas: {sens / scale:.1e})"
+            for (sl, gk, fk) in HEAD:
+                ref = getattr(oasm, "head_" + gk).reshape(-1)
+                sens = max(float(np.abs(getattr(q, "head_" + gk).reshape(-1) - ref).max()) for q in reps)
+                scale = max(float(np.abs(ref).max()), FLOOR[fk])
+                err = float(np.abs(hd[e_i, sl] - ref).max())
+                assert err <= max(TOL * scale, 20 * sens), f"env {e_i} step {s} head {gk}: {err / scale:.3e}"
+    print(f"OctoArmTwo-v0 n_elems={n}: worst field error {worst:.2e}")
+    vec.close()
