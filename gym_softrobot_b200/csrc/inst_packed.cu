@@ -31,7 +31,8 @@ cudaError_t launch_packed_kernel(const RodArgs<T> &A, int rods_per_cta, int grid
 // tapered assembly + COOMM muscle layers with per-element activations (group 5, 384 threads)
 template <int NT> cudaError_t launch_packed_lmus_kernel(const RodArgs<double> &A, int rods_per_cta, int grid, cudaStream_t s) {
   const size_t smem = (size_t)packed_smem_words(NT, true, false, true) * sizeof(double);
-  auto kern = rod_packed_kernel<double, NT, 1, false, false, true, true, false, false, true, true>;
+  // (no plane under these assemblies: sr_create rejects contact_on with muscle_layers_on, so the contact code stays out)
+  auto kern = rod_packed_kernel<double, NT, 1, false, false, false, true, false, false, true, true>;
   static std::atomic<unsigned long long> opted{0};
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);

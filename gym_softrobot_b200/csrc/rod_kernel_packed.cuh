@@ -704,7 +704,7 @@ rod_packed_kernel(const __grid_constant__ RodArgs<T> A, int rods_per_cta) {
       T em1 = e - T(1);
       T z0 = em1 * K.logc_w[0], z1 = em1 * K.logc_w[1], z2 = em1 * K.logc_w[2];
       // the contact / filtered models damp harder and stretch more (z up to ~1e-3): they use the wide exp map
-      constexpr bool NARROW_EXP = !CONTACT && !LAPLACE;
+      constexpr bool NARROW_EXP = !CONTACT && !LAPLACE && !LMUS;   // (muscles stretch the arms by tens of per cent)
       constexpr double kz = NARROW_EXP ? kNarrowExpZ : kSmallExpZ;
       const bool exp_out = !(fabs_(z0) <= T(kz)) || !(fabs_(z1) <= T(kz)) || !(fabs_(z2) <= T(kz));
       if (FASTONLY) dom_bad = dom_bad || exp_out;
