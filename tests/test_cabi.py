@@ -64,6 +64,9 @@ def _cfg(**kw):
     (dict(dt=0.0), "dt"),
     (dict(model=77), "model"),
     (dict(bc_kind=9), "bc_kind"),
+    (dict(muscle_layers_on=1), "muscle_layers_on needs"),          # no transverse muscle / head / tapered assembly
+    (dict(head_fixed=1), "muscle-layer kernel only"),
+    (dict(n_fixed_sucker=2), "muscle-layer kernel only"),
 ])
 def test_create_rejects_bad_config(kw, msg):
     lib = nat.load_library()

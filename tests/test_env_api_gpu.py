@@ -214,10 +214,12 @@ def test_second_episode_reset_observation_matches_reference(golden_dir):
 
 
 @pytest.mark.parametrize("env_id,kw", [("SoftPendulum3D-v0", {}), ("OctoFlat-v0", dict(recording_fps=100)),
-                                       ("ContinuumSnake-v0", {}), ("SoftArmTracking-v0", {})])
+                                       ("ContinuumSnake-v0", {}), ("SoftArmTracking-v0", {}),
+                                       ("OctoReach-v0", {}), ("OctoArmTwo-v0", {})])
 def test_clone_from_copies_everything_that_evolves(env_id, kw):
     """sr_copy_from: unlike sr_set_state (rod arrays only) it also carries BC anchors, the 3D pendulum's
-    base controller, rigid heads, rest curvatures and the forcings' state — a cloned handle continues bit for bit."""
+    base controller, rigid heads, rest curvatures and the forcings' state (incl. the per-element muscle activations and
+    the fixed-index sucker ratios of the muscle-layer envs) — a cloned handle continues bit for bit."""
     import torch
     import gym_softrobot_b200 as gsb
     n_env = 5
@@ -237,6 +239,8 @@ def test_clone_from_copies_everything_that_evolves(env_id, kw):
     torch.cuda.synchronize()
     assert torch.equal(e1.handle.state_tensor(), e2.handle.state_tensor())
     assert torch.equal(e1.handle.aux_tensor(), e2.handle.aux_tensor())
-    if env_id == "OctoFlat-v0":
+    if env_id in ("OctoFlat-v0", "OctoReach-v0", "OctoArmTwo-v0"):
         assert torch.equal(e1.handle.head_tensor(), e2.handle.head_tensor())
+    if env_id in ("OctoReach-v0", "OctoArmTwo-v0"):
+        assert float(e2.handle.muscle_activation_tensor().abs().max()) > 0.0      # the activations travelled with the clone
     e1.close(); e2.close()
