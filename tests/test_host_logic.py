@@ -16,7 +16,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_registry_keeps_reference_ids():
+    """Every id the reference registers (/root/reference/gym_softrobot/__init__.py:6-80; SoftArmTracking-v1 is commented
+    out there) has a drop-in facade and a batched vector env here, with the reference's registration kwargs."""
     assert "SoftPendulum-v0" in gsb.REGISTRY and "SoftPendulum-v0" in gsb.VECTOR_REGISTRY
+    reference_ids = ["OctoFlat-v0", "OctoFlatLite-v0", "OctoCrawl-v0", "OctoReach-v0", "OctoArmSingle-v0", "OctoArmTwo-v0",
+                     "OctoArmPush-v0", "OctoArmPush-v1", "OctoArmPullWeight-v0", "ContinuumSnake-v0", "SoftArmTracking-v0",
+                     "SoftPendulum-v0", "SoftPendulum3D-v0"]
+    assert sorted(gsb.REGISTRY) == sorted(reference_ids) == sorted(gsb.VECTOR_REGISTRY)
+    assert gsb.REGISTRY["OctoFlatLite-v0"][1] == dict(n_arm=1, n_action=8)                 # __init__.py:11-15
+    assert gsb.REGISTRY["OctoArmPush-v1"][1] == dict(mode="continuous")                    # :42-46
+    assert gsb.REGISTRY["OctoArmPullWeight-v0"][1] == dict(mode="continuous")              # :48-52
 
 
 def test_init_params_match_reference_build(golden_dir):
