@@ -209,3 +209,35 @@ def test_native_spline_basis_matches_scipy_not_a_knot():
         val = sum(y[1 + i] * (tab[m, i, 0] + t * (tab[m, i, 1] + t * (tab[m, i, 2] + t * tab[m, i, 3])))
                   for i in range(P))
         assert np.abs(val - ref(s)).max() < 5e-15 * max(1.0, np.abs(ref(s)).max())
+
+
+def test_arm_two_activation_map_and_layout_match_reference_fixture(golden_dir):
+    """Host logic of OctoArmTwo-v0 without a GPU: the [n_elems, 3] matrix that replaces the three cubic `interp1d` calls of
+    arm_two_env.py:236-247 reproduces the activations the unmodified reference env wrote into its muscles (fixture
+    `muscle_activations`), the sucker locations follow arm_two_env.py:78-82, and the arm layout is build_two_arms'."""
+    from gym_softrobot_b200.envs.arm_two import activation_interp_matrix, two_arm_init_params
+    g = np.load(os.path.join(golden_dir, "octo_arm_two_seed42.npz"), allow_pickle=True)
+    n = int(g["n_elems"])
+    loc = [n // 6 * (2 * i + 1) for i in range(3)]
+    assert loc == [int(v) for v in g["sucker_location"]]
+    W = activation_interp_matrix([0] + loc + [n - 1], n)
+    for i, a in enumerate(g["actions"]):
+        a = a.reshape(2, 9)
+        lm = a[:, 3:6] - np.float32(0.5)
+        ctrl = np.stack([np.maximum(lm, 0).astype(np.float64), np.abs(np.minimum(lm, 0)).astype(np.float64),
+                         a[:, 6:9].astype(np.float64)], axis=1)                      # [arm, muscle, control value]
+        np.testing.assert_allclose(ctrl @ W.T, g["muscle_activations"][i], rtol=0, atol=1e-14)
+    init, angles = two_arm_init_params()
+    assert angles == [90.0, 270.0]
+    for k in range(2):
+        p0 = g[f"state0/arm{k}/position"]
+        np.testing.assert_allclose(init[0, 9 * k:9 * k + 3], p0[:, 0], atol=1e-17)
+        np.testing.assert_allclose(init[0, 9 * k + 3:9 * k + 6], (p0[:, -1] - p0[:, 0]) / 0.25, atol=1e-15)
+
+
+def test_longitudinal_muscle_positions_match_the_layer_set():
+    """create_es_muscle_layers (envs/octopus/build.py:303-328): ratio_muscle_position (0, -6/9, 0) rotated by
+    muscle_init_angle = +-pi/2 puts the two longitudinal muscles at +-2/3 r on d1."""
+    from gym_softrobot_b200.envs.octo_reach import es_longitudinal_positions
+    (px0, py0), (px1, py1) = es_longitudinal_positions()
+    assert abs(px0 - 2 / 3) < 1e-15 and abs(px1 + 2 / 3) < 1e-15 and abs(py0) < 1e-16 and abs(py1) < 1e-16
