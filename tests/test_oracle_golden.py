@@ -527,3 +527,38 @@ def test_longitudinal_muscle_first_substep_known_answer():
     np.testing.assert_allclose([w[1, 0], w[1, -1]], [w_end, -w_end], rtol=1e-12)
     assert float(np.abs(v[:, 1:-1]).max()) < 1e-15 * v_end and float(np.abs(w[:, 1:-1]).max()) == 0.0
     assert float(np.abs(v[1:]).max()) == 0.0 and float(np.abs(w[[0, 2]]).max()) < 1e-15 * abs(w_end)
+
+
+def test_longitudinal_muscle_static_bend_known_answer():
+    """Physics check of the restated longitudinal muscle (independent of any fixture): a free, uniform rod whose muscle 1
+    (offset x_m = 2/3 r on d1) is activated uniformly settles into a uniformly stretched circular arc with
+        axial balance    E A (e - 1) = -F,            F = a sigma_max (A0 / e) h(l_m)
+        moment balance   E I kappa / e^3 = x_m F,     x_m = 2/3 r0 / sqrt(e),   l_m = e - kappa x_m
+    (the muscle runs on the concave side, so the curvature SHORTENS it: with l_m = e + kappa x_m the fixed point moves by
+    7.5e-4 (relative) in kappa and the test fails).  Damped C oracle vs the fixed point; the residual 2e-5 is the discretisation
+    (6 elements, 0.033 rad each: chord vs arc ~ theta^2 / 24 = 4.6e-5)."""
+    n, L, r0, E, a, smax, px, rho, dt = 6, 1.0, 0.05, 1e4, 0.6, 0.5, 2 / 3, 1000.0, 2e-4
+    rod = ro.OracleRod(n, (0, 0, 0), (1, 0, 0), (0, 1, 0), L, r0, rho, E, dt, shear_modulus=E / 1.5,
+                       damping_constant=0.3, tip_radius=r0, taper_node_mean=True)
+    act = rod.set_es_muscle_layers(r0)
+    act[0, :] = a
+    rod.substeps(400000)
+    assert float(np.abs(rod.velocity_collection).max()) < 1e-6 and float(np.abs(rod.omega_collection).max()) < 1e-7   # settled
+    h = lambda l: max(((3.06 * l - 13.64) * l + 18.01) * l - 6.44, 0.0)
+    EA, EI = E * np.pi * r0 ** 2, E * np.pi * r0 ** 4 / 4
+
+    def fixed_point(sign):
+        e, k = 1.0, 0.0
+        for _ in range(4000):
+            xm = px * r0 / np.sqrt(e)
+            F = a * smax * (1.0 / e) * h(e + sign * k * xm)
+            e, k = 0.5 * e + 0.5 * (1.0 - F / EA), 0.5 * k + 0.5 * (xm * F * e ** 3 / EI)
+        return e, k
+    e_ref, k_ref = fixed_point(-1.0)
+    _, k_wrong = fixed_point(+1.0)
+    kap = rod.kappa[1]
+    assert 0.15 < k_ref < 0.25 and abs(k_wrong - k_ref) > 5e-4 * k_ref       # (the test's 1e-4 separates the two)
+    assert float(np.ptp(kap)) < 1e-4 * k_ref and float(np.abs(rod.kappa[[0, 2]]).max()) < 1e-9      # a circular arc in one plane
+    np.testing.assert_allclose(kap, k_ref, rtol=1e-4)
+    np.testing.assert_allclose(rod.dilatation, e_ref, rtol=0, atol=5e-5)
+    assert float(np.abs(rod.sigma[:2]).max()) < 1e-8                                                   # no shear
