@@ -353,3 +353,30 @@ def test_octo_arm_two_other_resolution_vs_c_oracle():
                 assert err <= max(TOL * scale, 20 * sens), f"env {e_i} step {s} head {gk}: {err / scale:.3e}"
     print(f"OctoArmTwo-v0 n_elems={n}: worst field error {worst:.2e}")
     vec.close()
+
+
+def test_octo_arm_two_vector_env_autoreset_and_prev_kappa():
+    """Batched OctoArmTwo-v0: truncation past final_time rebuilds the envs inside step() (suckers back to ratio 1,
+    muscles at rest), the truncated step's reward carries the reference's `- distance` term (arm_two_env.py:312-314), and
+    the observation's prev_kappa block shows the previous observation's curvature (arm_two_env.py:201-219)."""
+    import torch
+    import gym_softrobot_b200 as gsb
+    rng = np.random.default_rng(2)
+    vec = gsb.make_vec("OctoArmTwo-v0", 4, final_time=0.075)
+    o0, _ = vec.reset()
+    n_seg = vec.n_seg
+    assert tuple(o0.shape) == (4, vec.single_observation_space.shape[0])
+    a = torch.as_tensor(rng.random((4, 18)).astype(np.float32), device=vec.device)
+    o1, r1, te1, tr1, _ = vec.step(a)
+    assert not bool(tr1.any()) and not bool(te1.any())
+    k1 = o1.reshape(4, 2, -1)[:, :, :n_seg].clone()
+    assert float(k1.abs().max()) > 0.0
+    o2, r2, te2, tr2, info = vec.step(a)
+    assert bool(tr2.all()) and "final_obs" in info and int(vec.step_count.max()) == 0
+    # the pre-reset observation of the truncated step carries the previous step's curvature in its prev_kappa block
+    assert torch.equal(info["final_obs"].reshape(4, 2, -1)[:, :, n_seg:2 * n_seg], k1)
+    assert bool((r2 < -4.0).all())                        # forward_reward -= |target - head| ~ 5 m
+    assert float(vec.handle.muscle_activation_tensor().abs().max()) == 0.0
+    assert float((vec.handle.fixed_sucker_tensor() - 1.0).abs().max()) == 0.0
+    assert float(o2.reshape(4, 2, -1)[:, :, :n_seg].abs().max()) < 1e-12      # fresh arms are straight
+    vec.close()
